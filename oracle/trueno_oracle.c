@@ -1,0 +1,750 @@
+/*
+ * trueno_oracle.c — CPU restatement of paiml/trueno's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle for the B200 kernels.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg may load it; the product (trueno_b200/,
+ * include/) never links, imports or falls back to it.
+ *
+ * The reference is Rust and cannot be built in this image (no cargo/rustc), so each function
+ * below restates the arithmetic AND the accumulation order of the reference function it cites
+ * (paths relative to /root/reference).  All hot-path arithmetic is in-tree in the reference;
+ * the only external piece is the platform libm (Rust's f32::exp/ln/tanh/sqrt lower to glibc
+ * expf/logf/tanhf/sqrtf on linux-gnu — the same functions called here).
+ *
+ * Parity pin: tests/test_oracle_kat.py checks every function against the known-answer tests
+ * and seeded fixtures the reference's own test-suite holds for this path.
+ *
+ * Build: see oracle/Makefile.  -ffp-contract=off is REQUIRED: Rust never contracts a*b+c into
+ * an FMA, so every fused operation here is spelled fmaf()/_mm256_fmadd_ps explicitly, exactly
+ * where the reference spells mul_add/_mm256_fmadd_ps.
+ */
+#include <immintrin.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* status codes == include/trueno_cuda.h trn_status (TruenoError variants, src/error.rs:8-41) */
+enum { ORC_OK = 0, ORC_SIZE_MISMATCH = 1, ORC_INVALID_INPUT = 2, ORC_EMPTY_VECTOR = 3 };
+
+static __thread char g_msg[512];
+static __thread uint64_t g_expected, g_actual;
+
+ORC_API const char* orc_last_message(void) { return g_msg; }
+ORC_API void orc_last_mismatch(uint64_t* e, uint64_t* a) { *e = g_expected; *a = g_actual; }
+
+static int fail_invalid(const char* m) {
+    snprintf(g_msg, sizeof g_msg, "%s", m);
+    return ORC_INVALID_INPUT;
+}
+static int fail_size(size_t expected, size_t actual) {
+    g_expected = expected; g_actual = actual;
+    snprintf(g_msg, sizeof g_msg, "Size mismatch: expected %zu, got %zu", expected, actual);
+    return ORC_SIZE_MISMATCH;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Scalar backend — the semantic ground truth (src/backends/scalar.rs)
+ * ---------------------------------------------------------------------------------------- */
+
+/* scalar.rs:66-94 — four fused-multiply-add chains, (c0+c1)+(c2+c3), fused tail */
+ORC_API float orc_scalar_dot(const float* a, const float* b, size_t n) {
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    size_t q = n / 4;
+    for (size_t i = 0; i < q; ++i) {
+        const float* pa = a + 4 * i; const float* pb = b + 4 * i;
+        c0 = fmaf(pa[0], pb[0], c0);
+        c1 = fmaf(pa[1], pb[1], c1);
+        c2 = fmaf(pa[2], pb[2], c2);
+        c3 = fmaf(pa[3], pb[3], c3);
+    }
+    float s = (c0 + c1) + (c2 + c3);
+    for (size_t i = 4 * q; i < n; ++i) s = fmaf(a[i], b[i], s);
+    return s;
+}
+
+/* scalar.rs:100-106 — plain left-to-right f32 sum */
+ORC_API float orc_scalar_sum(const float* a, size_t n) {
+    float t = 0.f;
+    for (size_t i = 0; i < n; ++i) t += a[i];
+    return t;
+}
+
+/* scalar.rs:112-120 / :126-134 — seed with a[0], strict compare (a NaN never wins, a NaN seed never loses) */
+ORC_API float orc_scalar_max(const float* a, size_t n) {
+    float m = a[0];
+    for (size_t i = 1; i < n; ++i) if (a[i] > m) m = a[i];
+    return m;
+}
+ORC_API float orc_scalar_min(const float* a, size_t n) {
+    float m = a[0];
+    for (size_t i = 1; i < n; ++i) if (a[i] < m) m = a[i];
+    return m;
+}
+
+/* scalar.rs:140-150 / :156-166 — first occurrence, strict compare, seed index 0 */
+ORC_API uint64_t orc_scalar_argmax(const float* a, size_t n) {
+    float m = a[0]; uint64_t at = 0;
+    for (size_t i = 0; i < n; ++i) if (a[i] > m) { m = a[i]; at = i; }
+    return at;
+}
+ORC_API uint64_t orc_scalar_argmin(const float* a, size_t n) {
+    float m = a[0]; uint64_t at = 0;
+    for (size_t i = 0; i < n; ++i) if (a[i] < m) { m = a[i]; at = i; }
+    return at;
+}
+
+/* scalar.rs:190-200 — sequential sum of val*val (mul, then add), sqrt */
+ORC_API float orc_scalar_norm_l2(const float* a, size_t n) {
+    if (n == 0) return 0.f;
+    float ss = 0.f;
+    for (size_t i = 0; i < n; ++i) { float sq = a[i] * a[i]; ss += sq; }
+    return sqrtf(ss);
+}
+
+static inline float sigmoid_libm(float v) {
+    /* scalar.rs:313-324 — hard cut-offs at +-50, libm expf in between */
+    if (v < -50.f) return 0.f;
+    if (v > 50.f) return 1.f;
+    return 1.f / (1.f + expf(-v));
+}
+static inline float gelu_libm(float x) {
+    /* scalar.rs:330-340 — tanh approximation with libm tanhf; (x*x)*x, c*x3, x+.., k*(..) */
+    const float k = 0.7978846f, c = 0.044715f;
+    float x3 = x * x * x;
+    float t = c * x3;
+    float inner = k * (x + t);
+    float h = 0.5f * x;
+    return h * (1.f + tanhf(inner));
+}
+ORC_API void orc_scalar_sigmoid(const float* a, float* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) out[i] = sigmoid_libm(a[i]);
+}
+ORC_API void orc_scalar_gelu(const float* a, float* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) out[i] = gelu_libm(a[i]);
+}
+ORC_API void orc_scalar_add(const float* a, const float* b, float* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) out[i] = a[i] + b[i];
+}
+ORC_API void orc_scalar_mul(const float* a, const float* b, float* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) out[i] = a[i] * b[i];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * AVX2 backend — what trueno returns by default on x86 (src/backends/avx2.rs)
+ * ---------------------------------------------------------------------------------------- */
+
+/* lane fold used by dot and sum: lo128+hi128, then +movehl, then +lane1 (avx2.rs:203-210, :239-246) */
+static inline float fold8_add(__m256 v) {
+    __m128 h = _mm_add_ps(_mm256_castps256_ps128(v), _mm256_extractf128_ps(v, 1));
+    __m128 t = _mm_add_ps(h, _mm_movehl_ps(h, h));
+    t = _mm_add_ss(t, _mm_shuffle_ps(t, t, 1));
+    return _mm_cvtss_f32(t);
+}
+
+/* avx2.rs:32-55 / :96-117 — one IEEE op per element: bit-exact with scalar */
+ORC_API void orc_avx2_add(const float* a, const float* b, float* out, size_t n) {
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        _mm256_storeu_ps(out + i, _mm256_add_ps(_mm256_loadu_ps(a + i), _mm256_loadu_ps(b + i)));
+    for (; i < n; ++i) out[i] = a[i] + b[i];
+}
+ORC_API void orc_avx2_mul(const float* a, const float* b, float* out, size_t n) {
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        _mm256_storeu_ps(out + i, _mm256_mul_ps(_mm256_loadu_ps(a + i), _mm256_loadu_ps(b + i)));
+    for (; i < n; ++i) out[i] = a[i] * b[i];
+}
+
+/* avx2.rs:159-216 — 4 vector FMA chains over 32-element steps, leftover 8-steps go to chain 0,
+ * (v0+v1)+(v2+v3), lane fold, then the scalar tail is summed SEPARATELY (mul, add from 0) and
+ * added last. */
+ORC_API float orc_avx2_dot(const float* a, const float* b, size_t n) {
+    __m256 v0 = _mm256_setzero_ps(), v1 = v0, v2 = v0, v3 = v0;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        v0 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i),      _mm256_loadu_ps(b + i),      v0);
+        v1 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i + 8),  _mm256_loadu_ps(b + i + 8),  v1);
+        v2 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i + 16), _mm256_loadu_ps(b + i + 16), v2);
+        v3 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i + 24), _mm256_loadu_ps(b + i + 24), v3);
+    }
+    for (; i + 8 <= n; i += 8)
+        v0 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i), _mm256_loadu_ps(b + i), v0);
+    float r = fold8_add(_mm256_add_ps(_mm256_add_ps(v0, v1), _mm256_add_ps(v2, v3)));
+    float tail = 0.f;
+    for (; i < n; ++i) { float p = a[i] * b[i]; tail += p; }
+    return r + tail;
+}
+
+/* avx2.rs:225-252 — ONE 8-lane accumulator (stagnates at large n: SURVEY.md top, fact 3) */
+ORC_API float orc_avx2_sum(const float* a, size_t n) {
+    __m256 acc = _mm256_setzero_ps();
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) acc = _mm256_add_ps(acc, _mm256_loadu_ps(a + i));
+    float r = fold8_add(acc);
+    float tail = 0.f;
+    for (; i < n; ++i) tail += a[i];
+    return r + tail;
+}
+
+/* avx2.rs:261-294 / :303-336 — lanes seeded with a[0]; vmaxps(acc, x) (returns x on NaN) */
+ORC_API float orc_avx2_max(const float* a, size_t n) {
+    __m256 m = _mm256_set1_ps(a[0]);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) m = _mm256_max_ps(m, _mm256_loadu_ps(a + i));
+    __m128 h = _mm_max_ps(_mm256_castps256_ps128(m), _mm256_extractf128_ps(m, 1));
+    __m128 t = _mm_max_ps(h, _mm_movehl_ps(h, h));
+    t = _mm_max_ss(t, _mm_shuffle_ps(t, t, 1));
+    float r = _mm_cvtss_f32(t);
+    for (; i < n; ++i) if (a[i] > r) r = a[i];
+    return r;
+}
+ORC_API float orc_avx2_min(const float* a, size_t n) {
+    __m256 m = _mm256_set1_ps(a[0]);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) m = _mm256_min_ps(m, _mm256_loadu_ps(a + i));
+    __m128 h = _mm_min_ps(_mm256_castps256_ps128(m), _mm256_extractf128_ps(m, 1));
+    __m128 t = _mm_min_ps(h, _mm_movehl_ps(h, h));
+    t = _mm_min_ss(t, _mm_shuffle_ps(t, t, 1));
+    float r = _mm_cvtss_f32(t);
+    for (; i < n; ++i) if (a[i] < r) r = a[i];
+    return r;
+}
+
+/* avx2.rs:345-400 / :409-464 — indices carried as f32 lanes (lossy above 2^24 — a reference
+ * DEFECT that the CUDA path does not reproduce; kept here to document what trueno returns). */
+ORC_API uint64_t orc_avx2_argmax(const float* a, size_t n) {
+    float best = a[0]; uint64_t at = 0;
+    __m256 vb = _mm256_set1_ps(a[0]), vi = _mm256_setzero_ps();
+    __m256 cur = _mm256_set_ps(7.f, 6.f, 5.f, 4.f, 3.f, 2.f, 1.f, 0.f);
+    const __m256 step = _mm256_set1_ps(8.f);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        __m256 x = _mm256_loadu_ps(a + i);
+        __m256 gt = _mm256_cmp_ps(x, vb, _CMP_GT_OQ);
+        vb = _mm256_blendv_ps(vb, x, gt);
+        vi = _mm256_blendv_ps(vi, cur, gt);
+        cur = _mm256_add_ps(cur, step);
+    }
+    float lv[8], li[8];
+    _mm256_storeu_ps(lv, vb); _mm256_storeu_ps(li, vi);
+    for (int l = 0; l < 8; ++l) if (lv[l] > best) { best = lv[l]; at = (uint64_t)li[l]; }
+    for (size_t j = i; j < n; ++j) if (a[j] > best) { best = a[j]; at = j; }
+    return at;
+}
+ORC_API uint64_t orc_avx2_argmin(const float* a, size_t n) {
+    float best = a[0]; uint64_t at = 0;
+    __m256 vb = _mm256_set1_ps(a[0]), vi = _mm256_setzero_ps();
+    __m256 cur = _mm256_set_ps(7.f, 6.f, 5.f, 4.f, 3.f, 2.f, 1.f, 0.f);
+    const __m256 step = _mm256_set1_ps(8.f);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        __m256 x = _mm256_loadu_ps(a + i);
+        __m256 lt = _mm256_cmp_ps(x, vb, _CMP_LT_OQ);
+        vb = _mm256_blendv_ps(vb, x, lt);
+        vi = _mm256_blendv_ps(vi, cur, lt);
+        cur = _mm256_add_ps(cur, step);
+    }
+    float lv[8], li[8];
+    _mm256_storeu_ps(lv, vb); _mm256_storeu_ps(li, vi);
+    for (int l = 0; l < 8; ++l) if (lv[l] < best) { best = lv[l]; at = (uint64_t)li[l]; }
+    for (size_t j = i; j < n; ++j) if (a[j] < best) { best = a[j]; at = j; }
+    return at;
+}
+
+/* avx2.rs:481-489 */
+ORC_API float orc_avx2_norm_l2(const float* a, size_t n) {
+    if (n == 0) return 0.f;
+    return sqrtf(orc_avx2_dot(a, a, n));
+}
+
+/* The reference's in-register exp (avx2.rs:798-866, reused at :900-935 and :1000-1025):
+ * clamp to [-87.33655, 88.37626]; k = floor(x*log2e + 0.5); r = x - k*ln2 (one step, mul then
+ * sub); degree-6 Taylor by Horner with FMAs; scale by 2^k through the exponent field. */
+static inline __m256 exp8_taylor(__m256 x) {
+    const __m256 one = _mm256_set1_ps(1.f);
+    x = _mm256_max_ps(_mm256_min_ps(x, _mm256_set1_ps(88.37626f)), _mm256_set1_ps(-87.33655f));
+    __m256 k = _mm256_floor_ps(_mm256_add_ps(_mm256_mul_ps(x, _mm256_set1_ps(1.44269504088896341f)),
+                                             _mm256_set1_ps(0.5f)));
+    __m256 r = _mm256_sub_ps(x, _mm256_mul_ps(k, _mm256_set1_ps(0.693147180559945309f)));
+    __m256 p = _mm256_set1_ps(0.001388889f);
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(0.008333334f));
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(0.041666668f));
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(0.16666667f));
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(0.5f));
+    p = _mm256_fmadd_ps(p, r, one);
+    p = _mm256_fmadd_ps(p, r, one);
+    __m256i e = _mm256_slli_epi32(_mm256_cvtps_epi32(k), 23);
+    __m256 two_k = _mm256_castsi256_ps(_mm256_add_epi32(_mm256_castps_si256(one), e));
+    return _mm256_mul_ps(p, two_k);
+}
+ORC_API void orc_avx2_exp(const float* a, float* out, size_t n) {
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) _mm256_storeu_ps(out + i, exp8_taylor(_mm256_loadu_ps(a + i)));
+    for (; i < n; ++i) out[i] = expf(a[i]);
+}
+/* avx2.rs:875-949 — 1/(1+exp8(-x)); the <8 tail uses the scalar rule */
+ORC_API void orc_avx2_sigmoid(const float* a, float* out, size_t n) {
+    const __m256 one = _mm256_set1_ps(1.f);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        __m256 nx = _mm256_sub_ps(_mm256_setzero_ps(), _mm256_loadu_ps(a + i));
+        __m256 e = exp8_taylor(nx);
+        _mm256_storeu_ps(out + i, _mm256_div_ps(one, _mm256_add_ps(one, e)));
+    }
+    for (; i < n; ++i) out[i] = sigmoid_libm(a[i]);
+}
+/* avx2.rs:958-1047 — tanh(u) = (e^{2u}-1)/(e^{2u}+1) with exp8; the <8 tail uses libm tanhf */
+ORC_API void orc_avx2_gelu(const float* a, float* out, size_t n) {
+    const __m256 one = _mm256_set1_ps(1.f);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        __m256 x = _mm256_loadu_ps(a + i);
+        __m256 x3 = _mm256_mul_ps(_mm256_mul_ps(x, x), x);
+        __m256 u = _mm256_mul_ps(_mm256_set1_ps(0.7978846f),
+                                 _mm256_fmadd_ps(_mm256_set1_ps(0.044715f), x3, x));
+        __m256 e = exp8_taylor(_mm256_mul_ps(_mm256_set1_ps(2.f), u));
+        __m256 th = _mm256_div_ps(_mm256_sub_ps(e, one), _mm256_add_ps(e, one));
+        _mm256_storeu_ps(out + i, _mm256_mul_ps(_mm256_set1_ps(0.5f),
+                                                _mm256_mul_ps(x, _mm256_add_ps(one, th))));
+    }
+    for (; i < n; ++i) out[i] = gelu_libm(a[i]);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * AVX-512 variants reached only on explicit request and only for dot/sum
+ * (src/backends/avx512.rs:151-223).  _mm512_reduce_add_ps folds 16->8->4->2->1 by halves.
+ * ---------------------------------------------------------------------------------------- */
+__attribute__((target("avx512f"))) static float fold16_add(__m512 v) {
+    return _mm512_reduce_add_ps(v);
+}
+ORC_API int orc_has_avx512(void) { return __builtin_cpu_supports("avx512f"); }
+
+__attribute__((target("avx512f")))
+ORC_API float orc_avx512_dot(const float* a, const float* b, size_t n) {
+    __m512 v0 = _mm512_setzero_ps(), v1 = v0;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        v0 = _mm512_fmadd_ps(_mm512_loadu_ps(a + i),      _mm512_loadu_ps(b + i),      v0);
+        v1 = _mm512_fmadd_ps(_mm512_loadu_ps(a + i + 16), _mm512_loadu_ps(b + i + 16), v1);
+    }
+    for (; i + 16 <= n; i += 16)
+        v0 = _mm512_fmadd_ps(_mm512_loadu_ps(a + i), _mm512_loadu_ps(b + i), v0);
+    float r = fold16_add(_mm512_add_ps(v0, v1));
+    float tail = 0.f;
+    for (; i < n; ++i) { float p = a[i] * b[i]; tail += p; }
+    return r + tail;
+}
+__attribute__((target("avx512f")))
+ORC_API float orc_avx512_sum(const float* a, size_t n) {
+    __m512 acc = _mm512_setzero_ps();
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) acc = _mm512_add_ps(acc, _mm512_loadu_ps(a + i));
+    float r = fold16_add(acc);
+    float tail = 0.f;
+    for (; i < n; ++i) tail += a[i];
+    return r + tail;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Vector-level entry points: validation + dispatch as in src/vector.rs (default backend AVX2).
+ * backend: 0 = scalar, 1 = avx2 (default stamp on x86, src/lib.rs:138-152), 2 = avx512
+ * (only dot/sum differ; everything else routes to AVX2 — src/vector.rs:665,713,761,809,2613)
+ * ---------------------------------------------------------------------------------------- */
+ORC_API int orc_vector_dot(const float* a, size_t na, const float* b, size_t nb, int backend, float* out) {
+    if (na != nb) return fail_size(na, nb);                       /* vector.rs:589-594 */
+    *out = backend == 0 ? orc_scalar_dot(a, b, na)
+         : backend == 2 ? orc_avx512_dot(a, b, na) : orc_avx2_dot(a, b, na);
+    return ORC_OK;
+}
+ORC_API int orc_vector_sum(const float* a, size_t n, int backend, float* out) {
+    *out = backend == 0 ? orc_scalar_sum(a, n)                    /* vector.rs:635: empty -> 0 */
+         : backend == 2 ? orc_avx512_sum(a, n) : orc_avx2_sum(a, n);
+    return ORC_OK;
+}
+ORC_API int orc_vector_max(const float* a, size_t n, int backend, float* out) {
+    if (n == 0) return fail_invalid("Empty vector");              /* vector.rs:654-656 */
+    *out = backend == 0 ? orc_scalar_max(a, n) : orc_avx2_max(a, n);
+    return ORC_OK;
+}
+ORC_API int orc_vector_min(const float* a, size_t n, int backend, float* out) {
+    if (n == 0) return fail_invalid("Empty vector");              /* vector.rs:702-704 */
+    *out = backend == 0 ? orc_scalar_min(a, n) : orc_avx2_min(a, n);
+    return ORC_OK;
+}
+ORC_API int orc_vector_argmax(const float* a, size_t n, int backend, uint64_t* out) {
+    if (n == 0) return fail_invalid("Empty vector");              /* vector.rs:750-752 */
+    *out = backend == 0 ? orc_scalar_argmax(a, n) : orc_avx2_argmax(a, n);
+    return ORC_OK;
+}
+ORC_API int orc_vector_argmin(const float* a, size_t n, int backend, uint64_t* out) {
+    if (n == 0) return fail_invalid("Empty vector");              /* vector.rs:798-800 */
+    *out = backend == 0 ? orc_scalar_argmin(a, n) : orc_avx2_argmin(a, n);
+    return ORC_OK;
+}
+ORC_API int orc_vector_norm_l2(const float* a, size_t n, int backend, float* out) {
+    *out = n == 0 ? 0.f                                           /* vector.rs:2602-2604 */
+         : backend == 0 ? orc_scalar_norm_l2(a, n) : orc_avx2_norm_l2(a, n);
+    return ORC_OK;
+}
+ORC_API int orc_vector_add(const float* a, size_t na, const float* b, size_t nb, float* out) {
+    if (na != nb) return fail_size(na, nb);                       /* vector.rs:358-366 */
+    orc_avx2_add(a, b, out, na);
+    return ORC_OK;
+}
+ORC_API int orc_vector_mul(const float* a, size_t na, const float* b, size_t nb, float* out) {
+    if (na != nb) return fail_size(na, nb);                       /* vector.rs:478-486 */
+    orc_avx2_mul(a, b, out, na);
+    return ORC_OK;
+}
+ORC_API int orc_vector_sigmoid(const float* a, size_t n, int backend, float* out) {
+    if (n == 0) { snprintf(g_msg, sizeof g_msg, "Empty vector"); return ORC_EMPTY_VECTOR; }
+    if (backend == 0) orc_scalar_sigmoid(a, out, n); else orc_avx2_sigmoid(a, out, n);
+    return ORC_OK;
+}
+ORC_API int orc_vector_gelu(const float* a, size_t n, int backend, float* out) {
+    if (n == 0) { snprintf(g_msg, sizeof g_msg, "Empty vector"); return ORC_EMPTY_VECTOR; }
+    if (backend == 0) orc_scalar_gelu(a, out, n); else orc_avx2_gelu(a, out, n);
+    return ORC_OK;
+}
+
+/* vector.rs:1540-1553 — max() via the vector's backend, then libm expf per element, a
+ * left-to-right f32 sum of the exponentials, one division per element. */
+ORC_API int orc_vector_softmax(const float* a, size_t n, int backend, float* out) {
+    if (n == 0) { snprintf(g_msg, sizeof g_msg, "Empty vector"); return ORC_EMPTY_VECTOR; }
+    float mx = backend == 0 ? orc_scalar_max(a, n) : orc_avx2_max(a, n);
+    for (size_t i = 0; i < n; ++i) out[i] = expf(a[i] - mx);
+    float s = 0.f;
+    for (size_t i = 0; i < n; ++i) s += out[i];
+    for (size_t i = 0; i < n; ++i) out[i] = out[i] / s;
+    return ORC_OK;
+}
+/* vector.rs:1605-1623 — out = (x - max) - ln(sum exp(x - max)), evaluated left to right */
+ORC_API int orc_vector_log_softmax(const float* a, size_t n, int backend, float* out) {
+    if (n == 0) { snprintf(g_msg, sizeof g_msg, "Empty vector"); return ORC_EMPTY_VECTOR; }
+    float mx = backend == 0 ? orc_scalar_max(a, n) : orc_avx2_max(a, n);
+    float s = 0.f;
+    for (size_t i = 0; i < n; ++i) s += expf(a[i] - mx);
+    float lse = logf(s);
+    for (size_t i = 0; i < n; ++i) { float d = a[i] - mx; out[i] = d - lse; }
+    return ORC_OK;
+}
+/* Row-batched convenience used by the config-5 parity tests: the reference has no batched API,
+ * a row is one Vector — so this is literally a loop of the above. */
+ORC_API int orc_softmax_rows(const float* a, float* out, size_t rows, size_t cols, int backend, int log_variant) {
+    if (cols == 0) { snprintf(g_msg, sizeof g_msg, "Empty vector"); return ORC_EMPTY_VECTOR; }
+    #pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < rows; ++r) {
+        if (log_variant) orc_vector_log_softmax(a + r * cols, cols, backend, out + r * cols);
+        else             orc_vector_softmax(a + r * cols, cols, backend, out + r * cols);
+    }
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Matrix paths (src/matrix.rs).  Row-major everywhere.
+ * ---------------------------------------------------------------------------------------- */
+
+/* matrix.rs:1590-1617 — result[j,i] = self[i,j]; blocking does not change values */
+ORC_API void orc_transpose(const float* a, float* out, size_t rows, size_t cols) {
+    for (size_t ib = 0; ib < rows; ib += 64)
+        for (size_t jb = 0; jb < cols; jb += 64) {
+            size_t ie = ib + 64 < rows ? ib + 64 : rows, je = jb + 64 < cols ? jb + 64 : cols;
+            for (size_t i = ib; i < ie; ++i)
+                for (size_t j = jb; j < je; ++j) out[j * rows + i] = a[i * cols + j];
+        }
+}
+
+/* matrix.rs:572-597 — sum += a*b (mul, then add), k ascending */
+ORC_API void orc_matmul_naive(const float* A, const float* B, float* C, size_t m, size_t k, size_t n) {
+    for (size_t i = 0; i < m; ++i)
+        for (size_t j = 0; j < n; ++j) {
+            float s = 0.f;
+            for (size_t p = 0; p < k; ++p) { float t = A[i * k + p] * B[p * n + j]; s += t; }
+            C[i * n + j] = s;
+        }
+}
+
+/* matrix.rs:540-569 — rows == 1 fast path: AXPY per k, skipping a_k == 0.0 exactly */
+static void matmul_row_vector(const float* a, const float* B, float* c, size_t k, size_t n) {
+    memset(c, 0, n * sizeof(float));
+    for (size_t p = 0; p < k; ++p) {
+        float ak = a[p];
+        if (ak == 0.0f) continue;
+        const float* brow = B + p * n;
+        for (size_t j = 0; j < n; ++j) { float t = ak * brow[j]; c[j] += t; }
+    }
+}
+
+/* matrix.rs:1476-1536 — per row, 8 running sums over ascending k (mul, then add); scalar tail cols */
+static void matmul_tiled8(const float* A, const float* B, float* C, size_t m, size_t k, size_t n) {
+    size_t n8 = n / 8 * 8;
+    for (size_t i = 0; i < m; ++i) {
+        const float* arow = A + i * k;
+        for (size_t j0 = 0; j0 < n8; j0 += 8) {
+            float acc[8] = {0};
+            for (size_t p = 0; p < k; ++p) {
+                float av = arow[p];
+                const float* b = B + p * n + j0;
+                for (int l = 0; l < 8; ++l) { float t = av * b[l]; acc[l] += t; }
+            }
+            memcpy(C + i * n + j0, acc, sizeof acc);
+        }
+        for (size_t j = n8; j < n; ++j) {
+            float s = 0.f;
+            for (size_t p = 0; p < k; ++p) { float t = arow[p] * B[p * n + j]; s += t; }
+            C[i * n + j] = s;
+        }
+    }
+}
+
+/* matrix.rs:674-688 — lo128+hi128 then two hadds: ((s0+s1)+(s2+s3)) */
+static inline float fold8_hadd(__m256 v) {
+    __m128 s = _mm_add_ps(_mm256_castps256_ps128(v), _mm256_extractf128_ps(v, 1));
+    s = _mm_hadd_ps(s, s);
+    s = _mm_hadd_ps(s, s);
+    return _mm_cvtss_f32(s);
+}
+
+/* matrix.rs:615-672 — 4 rows x 1 column over one k-block: 8-wide FMA chains, hadd fold,
+ * then the (<8) remainder as separate mul + add onto the folded value */
+static inline void microkernel_4x1(const float* a0, const float* a1, const float* a2, const float* a3,
+                                   const float* bt, size_t len, float out[4]) {
+    __m256 c0 = _mm256_setzero_ps(), c1 = c0, c2 = c0, c3 = c0;
+    size_t full = len / 8;
+    for (size_t q = 0; q < full; ++q) {
+        __m256 bv = _mm256_loadu_ps(bt + 8 * q);
+        c0 = _mm256_fmadd_ps(_mm256_loadu_ps(a0 + 8 * q), bv, c0);
+        c1 = _mm256_fmadd_ps(_mm256_loadu_ps(a1 + 8 * q), bv, c1);
+        c2 = _mm256_fmadd_ps(_mm256_loadu_ps(a2 + 8 * q), bv, c2);
+        c3 = _mm256_fmadd_ps(_mm256_loadu_ps(a3 + 8 * q), bv, c3);
+    }
+    out[0] = fold8_hadd(c0); out[1] = fold8_hadd(c1); out[2] = fold8_hadd(c2); out[3] = fold8_hadd(c3);
+    for (size_t p = 8 * full; p < len; ++p) {
+        float t;
+        t = a0[p] * bt[p]; out[0] += t;
+        t = a1[p] * bt[p]; out[1] += t;
+        t = a2[p] * bt[p]; out[2] += t;
+        t = a3[p] * bt[p]; out[3] += t;
+    }
+}
+
+/* One 64x64x64 (edge-clipped) L2 block: rows in groups of 4 through the microkernel, leftover
+ * rows through Avx2Backend::dot on the k-block; every partial is ADDED into C (matrix.rs:1040-1098). */
+static void l2_block(const float* A, const float* Bt, float* C, size_t k, size_t n,
+                     size_t i0, size_t i1, size_t j0, size_t j1, size_t p0, size_t p1) {
+    size_t len = p1 - p0, i = i0;
+    for (; i + 4 <= i1; i += 4) {
+        const float* r0 = A + i * k + p0;
+        for (size_t j = j0; j < j1; ++j) {
+            float part[4];
+            microkernel_4x1(r0, r0 + k, r0 + 2 * k, r0 + 3 * k, Bt + j * k + p0, len, part);
+            C[i * n + j] += part[0];
+            C[(i + 1) * n + j] += part[1];
+            C[(i + 2) * n + j] += part[2];
+            C[(i + 3) * n + j] += part[3];
+        }
+    }
+    for (; i < i1; ++i)
+        for (size_t j = j0; j < j1; ++j)
+            C[i * n + j] += orc_avx2_dot(A + i * k + p0, Bt + j * k + p0, len);
+}
+
+static inline size_t zmin(size_t a, size_t b) { return a < b ? a : b; }
+
+/* rows [r0,r1) of the 3-level blocked product (matrix.rs:711-905 / :1015-1098): L3 = 256, L2 = 64;
+ * for any C[i,j] the k-blocks arrive in ascending order. */
+static void l3_rows(const float* A, const float* Bt, float* C, size_t k, size_t n, size_t r0, size_t r1) {
+    for (size_t J = 0; J < n; J += 256) {
+        size_t Je = zmin(J + 256, n);
+        for (size_t P = 0; P < k; P += 256) {
+            size_t Pe = zmin(P + 256, k);
+            for (size_t i = r0; i < r1; i += 64)
+                for (size_t j = J; j < Je; j += 64)
+                    for (size_t p = P; p < Pe; p += 64)
+                        l2_block(A, Bt, C, k, n, i, zmin(i + 64, r1), j, zmin(j + 64, Je), p, zmin(p + 64, Pe));
+        }
+    }
+}
+
+/* matrix.rs:912-1401.  parallel != 0 mirrors `--features parallel` (rayon over 256-row blocks,
+ * only when all dims >= 1024, :942-1011) with OpenMP; per-element results are identical either way. */
+static void matmul_blocked(const float* A, const float* B, float* C, size_t m, size_t k, size_t n, int parallel) {
+    if (m <= 32 || k <= 32 || n <= 32) {
+        /* matmul_simd_simple (matrix.rs:1407-1465): transpose B, one Avx2 dot per element */
+        float* Bt = (float*)malloc(sizeof(float) * k * n + 64);
+        orc_transpose(B, Bt, k, n);
+        for (size_t i = 0; i < m; ++i)
+            for (size_t j = 0; j < n; ++j) C[i * n + j] = orc_avx2_dot(A + i * k, Bt + j * k, k);
+        free(Bt);
+        return;
+    }
+    float* Bt = (float*)malloc(sizeof(float) * k * n + 64);
+    orc_transpose(B, Bt, k, n);
+    memset(C, 0, sizeof(float) * m * n);
+    if (m >= 512 && k >= 512 && n >= 512) {
+        int par = parallel && m >= 1024 && k >= 1024 && n >= 1024;
+        size_t nblk = (m + 255) / 256;
+        #pragma omp parallel for schedule(dynamic) if (par)
+        for (size_t b = 0; b < nblk; ++b) l3_rows(A, Bt, C, k, n, b * 256, zmin(b * 256 + 256, m));
+    } else {
+        /* 2-level blocking (matrix.rs:1227-1300) */
+        for (size_t i = 0; i < m; i += 64)
+            for (size_t j = 0; j < n; j += 64)
+                for (size_t p = 0; p < k; p += 64)
+                    l2_block(A, Bt, C, k, n, i, zmin(i + 64, m), j, zmin(j + 64, n), p, zmin(p + 64, k));
+    }
+    free(Bt);
+}
+
+/* Matrix::matmul routing (matrix.rs:285-358), default features (no gpu), AVX2-stamped matrices */
+static void matmul_route(const float* A, const float* B, float* C, size_t m, size_t k, size_t n, int parallel) {
+    if (m == 1) { matmul_row_vector(A, B, C, k, n); return; }
+    if (m >= 64 || k >= 64 || n >= 64) {
+        size_t mx = m > k ? m : k; if (n > mx) mx = n;
+        if (mx < 512) matmul_tiled8(A, B, C, m, k, n);
+        else matmul_blocked(A, B, C, m, k, n, parallel);
+    } else {
+        orc_matmul_naive(A, B, C, m, k, n);
+    }
+}
+
+ORC_API int orc_matmul(const float* A, size_t a_rows, size_t a_cols,
+                       const float* B, size_t b_rows, size_t b_cols, float* C, int parallel) {
+    if (a_cols != b_rows) {
+        snprintf(g_msg, sizeof g_msg,
+                 "Matrix dimension mismatch for multiplication: %zu\xC3\x97%zu \xC3\x97 %zu\xC3\x97%zu "
+                 "(inner dimensions %zu and %zu must match)",
+                 a_rows, a_cols, b_rows, b_cols, a_cols, b_rows);
+        return ORC_INVALID_INPUT;
+    }
+    matmul_route(A, B, C, a_rows, a_cols, b_cols, parallel);
+    return ORC_OK;
+}
+/* forced-path entry for tests that compare paths (reference does the same: matrix.rs:2285-2715) */
+ORC_API void orc_matmul_simd(const float* A, const float* B, float* C, size_t m, size_t k, size_t n, int parallel) {
+    matmul_blocked(A, B, C, m, k, n, parallel);
+}
+
+/* matrix.rs:383-441 */
+ORC_API int orc_batched_matmul(const float* A, size_t a_len, const float* B, size_t b_len, float* C,
+                               size_t batch, size_t m, size_t k, size_t n, int parallel) {
+    if (a_len != batch * m * k) {
+        snprintf(g_msg, sizeof g_msg, "A data size mismatch: expected %zu (%zu\xC3\x97%zu\xC3\x97%zu), got %zu",
+                 batch * m * k, batch, m, k, a_len);
+        return ORC_INVALID_INPUT;
+    }
+    if (b_len != batch * k * n) {
+        snprintf(g_msg, sizeof g_msg, "B data size mismatch: expected %zu (%zu\xC3\x97%zu\xC3\x97%zu), got %zu",
+                 batch * k * n, batch, k, n, b_len);
+        return ORC_INVALID_INPUT;
+    }
+    for (size_t b = 0; b < batch; ++b)
+        matmul_route(A + b * m * k, B + b * k * n, C + b * m * n, m, k, n, parallel);
+    return ORC_OK;
+}
+/* matrix.rs:464-527 — sequential loop over batch*heads; `parallel` here fans heads out over
+ * OpenMP threads for the all-cores CPU baseline only (values per head are unchanged) */
+ORC_API int orc_batched_matmul_4d(const float* A, size_t a_len, const float* B, size_t b_len, float* C,
+                                  size_t batch, size_t heads, size_t m, size_t k, size_t n, int parallel) {
+    size_t total = batch * heads;
+    if (a_len != total * m * k) {
+        snprintf(g_msg, sizeof g_msg,
+                 "A data size mismatch: expected %zu (%zu\xC3\x97%zu\xC3\x97%zu\xC3\x97%zu), got %zu",
+                 total * m * k, batch, heads, m, k, a_len);
+        return ORC_INVALID_INPUT;
+    }
+    if (b_len != total * k * n) {
+        snprintf(g_msg, sizeof g_msg,
+                 "B data size mismatch: expected %zu (%zu\xC3\x97%zu\xC3\x97%zu\xC3\x97%zu), got %zu",
+                 total * k * n, batch, heads, k, n, b_len);
+        return ORC_INVALID_INPUT;
+    }
+    #pragma omp parallel for schedule(dynamic) if (parallel)
+    for (size_t h = 0; h < total; ++h)
+        matmul_route(A + h * m * k, B + h * k * n, C + h * m * n, m, k, n, 0);
+    return ORC_OK;
+}
+
+/* matrix.rs:1657-1741 — one Avx2 dot per row; rayon over rows at >= 4096 rows with `parallel` */
+ORC_API int orc_matvec(const float* A, size_t rows, size_t cols, const float* v, size_t vlen, float* y, int parallel) {
+    if (vlen != cols) {
+        snprintf(g_msg, sizeof g_msg,
+                 "Vector length %zu does not match matrix columns %zu for matrix-vector multiplication",
+                 vlen, cols);
+        return ORC_INVALID_INPUT;
+    }
+    int par = parallel && rows >= 4096;
+    #pragma omp parallel for schedule(static) if (par)
+    for (size_t i = 0; i < rows; ++i) y[i] = orc_avx2_dot(A + i * cols, v, cols);
+    return ORC_OK;
+}
+
+/* `parallel`-feature maps (vector.rs:369-390): rayon chunks of 65 536 at >= 100 000 elements.
+ * op: 0 add, 1 mul, 2 sigmoid, 3 gelu (sigmoid/gelu have no rayon path in the reference; the
+ * chunked form is used for the all-cores baseline only and gives identical values because
+ * 65 536 is a multiple of the 8-lane width). */
+ORC_API void orc_map_parallel(int op, const float* a, const float* b, float* out, size_t n) {
+    const size_t chunk = 65536;
+    size_t nchunks = (n + chunk - 1) / chunk;
+    #pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < nchunks; ++c) {
+        size_t o = c * chunk, len = zmin(chunk, n - o);
+        switch (op) {
+            case 0: orc_avx2_add(a + o, b + o, out + o, len); break;
+            case 1: orc_avx2_mul(a + o, b + o, out + o, len); break;
+            case 2: orc_avx2_sigmoid(a + o, out + o, len); break;
+            default: orc_avx2_gelu(a + o, out + o, len); break;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * f64 "truth" helpers for condition-aware tolerances: these are NOT reference
+ * behaviour, they are the yardstick both the reference order and the GPU result are measured on.
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_f64_sum(const float* a, size_t n, double* sum, double* abs_sum) {
+    double s = 0, t = 0;
+    #pragma omp parallel for reduction(+:s,t) schedule(static)
+    for (size_t i = 0; i < n; ++i) { s += (double)a[i]; t += fabs((double)a[i]); }
+    *sum = s; *abs_sum = t;
+}
+ORC_API void orc_f64_dot(const float* a, const float* b, size_t n, double* dot, double* abs_dot) {
+    double s = 0, t = 0;
+    #pragma omp parallel for reduction(+:s,t) schedule(static)
+    for (size_t i = 0; i < n; ++i) { double p = (double)a[i] * (double)b[i]; s += p; t += fabs(p); }
+    *dot = s; *abs_dot = t;
+}
+/* C[i,j] in f64 for a list of sampled (i,j) pairs, plus sum |a||b| for the tolerance scale */
+ORC_API void orc_f64_matmul_samples(const float* A, const float* B, size_t k, size_t n,
+                                    const uint64_t* rows, const uint64_t* cols, size_t count,
+                                    double* out, double* out_abs) {
+    #pragma omp parallel for schedule(static)
+    for (size_t s = 0; s < count; ++s) {
+        const float* a = A + rows[s] * k; const float* b = B + cols[s];
+        double acc = 0, aacc = 0;
+        for (size_t p = 0; p < k; ++p) { double t = (double)a[p] * (double)b[p * n]; acc += t; aacc += fabs(t); }
+        out[s] = acc; out_abs[s] = aacc;
+    }
+}
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+ORC_API void orc_set_threads(int t) {
+#ifdef _OPENMP
+    omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
