@@ -1,0 +1,190 @@
+/*
+ * trueno_cuda.h — C ABI of the B200 (sm_100a) backend for paiml/trueno's data-parallel hot path.
+ *
+ * This is the drop-in boundary: the symbols below are what trueno's `src/backends/cuda` backend
+ * (new) binds over FFI.  Every entry point cites the reference interface it
+ * replaces (paths relative to the trueno repository).  Plain pointers and sizes only; no C++,
+ * torch or CUDA types appear in any signature (`stream` is an opaque cudaStream_t, NULL = the
+ * backend's own stream).
+ *
+ * Conventions
+ *   - Every function returns a trn_status.  0 = OK.  The non-zero values map 1:1 onto the
+ *     variants of `TruenoError` (src/error.rs:8-41).  The message (byte-identical to the text the
+ *     reference formats) is fetched with trn_last_error(); for TRN_SIZE_MISMATCH the two fields
+ *     of `SizeMismatch { expected, actual }` come from trn_last_mismatch().  Error state is
+ *     thread-local.
+ *   - There is NO CPU fallback.  If no CUDA device is usable every compute call fails with
+ *     TRN_GPU_ERROR (TruenoError::GpuError), it never computes on the host.
+ *   - Host-slice functions (`trn_*_f32`) mirror `trait VectorBackend` (src/backends/mod.rs:52-385)
+ *     and the `GpuBackend::matmul` hook (src/backends/gpu/mod.rs:434): inputs are borrowed host
+ *     slices, outputs are caller-allocated host memory; the call returns when the result is in
+ *     host memory.  Host memory obtained from trn_host_alloc() is pinned and is copied without
+ *     an intermediate staging pass.
+ *   - Device-resident functions (`trn_*_f32_dev`) take device pointers (trn_buf_ptr() or any
+ *     CUDA allocation of the current device), are stream-ordered and return without
+ *     synchronising, so chains of ops stay in HBM (the reference's precedent for this is
+ *     `GpuCommandBatch`, src/backends/gpu/batch.rs:54-135).  Scalar results are written to
+ *     device memory (`*_out` device pointers).
+ *   - All functions are thread-safe.  One process drives one GPU (trn_cuda_init(device)); the
+ *     multi-GPU layer is one process per GPU (trueno_b200/parallel.py, torch.distributed/NCCL).
+ *   - Matrices are dense row-major f32, exactly like `Matrix<f32>` (src/matrix.rs:49-54).
+ */
+#ifndef TRUENO_CUDA_H
+#define TRUENO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TRN_API __attribute__((visibility("default")))
+#else
+#define TRN_API
+#endif
+
+/* TruenoError (src/error.rs:8-41) */
+typedef enum trn_status {
+    TRN_OK = 0,
+    TRN_SIZE_MISMATCH = 1,       /* SizeMismatch { expected, actual } */
+    TRN_INVALID_INPUT = 2,       /* InvalidInput(String) */
+    TRN_EMPTY_VECTOR = 3,        /* EmptyVector */
+    TRN_DIVISION_BY_ZERO = 4,    /* DivisionByZero (unused by the hot path; kept for ABI completeness) */
+    TRN_GPU_ERROR = 5,           /* GpuError(String) — any CUDA failure; never a fallback */
+    TRN_UNSUPPORTED_BACKEND = 6  /* UnsupportedBackend(Backend) — not an sm_100 device */
+} trn_status;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Replaces GpuBackend::new()/GpuDevice::new() (src/backends/gpu/mod.rs:63-120, device.rs:31):
+ * binds this process to `device` (use -1 for "current / LOCAL_RANK / 0") once; later calls are
+ * no-ops when the device matches.  Every compute entry point initialises lazily with -1. */
+TRN_API int trn_cuda_init(int device);
+TRN_API int trn_cuda_shutdown(void);
+/* GpuBackend::is_available() (src/backends/gpu/mod.rs:75): 1 if an sm_100 device is usable. */
+TRN_API int trn_cuda_is_available(void);
+TRN_API int trn_device_count(int* count);
+/* name (NUL-terminated, truncated to cap), SM count, total HBM bytes of the bound device */
+TRN_API int trn_device_info(char* name, size_t cap, int* sm_count, uint64_t* hbm_bytes);
+/* Copies the calling thread's last error message (NUL-terminated) and returns its full length. */
+TRN_API size_t trn_last_error(char* buf, size_t cap);
+TRN_API void trn_last_mismatch(uint64_t* expected, uint64_t* actual);
+/* Blocks until all work queued on `stream` (NULL = backend stream) has finished. */
+TRN_API int trn_synchronize(void* stream);
+/* Number of kernels this library has launched since init (bench.py reports it as gpu_launches). */
+TRN_API uint64_t trn_launch_count(void);
+
+/* ---- device buffers with pinned host staging ------------------------------------------------
+ * The device-buffer type of the north star.  Precedent: trueno-gpu GpuBuffer<T>
+ * (trueno-gpu/src/driver/memory.rs:53-164) and GpuCommandBatch::upload/read
+ * (src/backends/gpu/batch.rs:140-200). */
+typedef struct trn_buf trn_buf;
+TRN_API int trn_buf_alloc(size_t len, trn_buf** out);              /* len f32 elements in HBM */
+TRN_API int trn_buf_free(trn_buf* buf);
+TRN_API int trn_buf_upload(trn_buf* buf, const float* host, size_t len);
+TRN_API int trn_buf_download(const trn_buf* buf, float* host, size_t len);
+TRN_API size_t trn_buf_len(const trn_buf* buf);
+TRN_API float* trn_buf_ptr(const trn_buf* buf);                    /* device pointer */
+/* Pinned host memory (page-locked, 256-byte aligned) for zero-staging host-slice calls. */
+TRN_API int trn_host_alloc(size_t len, float** out);
+TRN_API int trn_host_free(float* ptr);
+
+/* ---- Vector reductions: host slices ---------------------------------------------------------
+ * trait VectorBackend::{dot,sum,max,min,argmax,argmin,norm_l2} (src/backends/mod.rs) behind
+ * Vector::{dot,sum,max,min,argmax,argmin,norm_l2} (src/vector.rs:588,635,653,701,749,797,2601).
+ * Validation and messages follow src/vector.rs:589-594,654-656,702-704,750-752,798-800,2602-2604:
+ *   dot: na != nb -> TRN_SIZE_MISMATCH{expected=na, actual=nb}; empty -> 0
+ *   sum: empty -> 0 ; norm_l2: empty -> 0
+ *   max/min/argmax/argmin: empty -> TRN_INVALID_INPUT "Empty vector"
+ * max/min/argmax/argmin implement the scalar backend's rule (src/backends/scalar.rs:112-166):
+ * seed with a[0], strict compare, first occurrence, 64-bit indices. */
+TRN_API int trn_dot_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_sum_f32(const float* a, size_t n, float* out);
+TRN_API int trn_max_f32(const float* a, size_t n, float* out);
+TRN_API int trn_min_f32(const float* a, size_t n, float* out);
+TRN_API int trn_argmax_f32(const float* a, size_t n, uint64_t* out);
+TRN_API int trn_argmin_f32(const float* a, size_t n, uint64_t* out);
+TRN_API int trn_norm_l2_f32(const float* a, size_t n, float* out);
+
+/* ---- Elementwise maps: host slices ----------------------------------------------------------
+ * VectorBackend::{add,mul,sigmoid,gelu} behind Vector::{add,mul,sigmoid,gelu}
+ * (src/vector.rs:358,478,1854,2179).  add/mul: na != nb -> TRN_SIZE_MISMATCH; bit-exact.
+ * sigmoid/gelu: empty -> TRN_EMPTY_VECTOR; scalar-backend definitions
+ * (src/backends/scalar.rs:313-340). */
+TRN_API int trn_add_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_mul_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_sigmoid_f32(const float* a, size_t n, float* out);
+TRN_API int trn_gelu_f32(const float* a, size_t n, float* out);
+
+/* ---- softmax / log_softmax ------------------------------------------------------------------
+ * Vector::softmax / log_softmax (src/vector.rs:1516,1581) and the GPU hook
+ * GpuDevice::softmax/log_softmax (src/backends/gpu/device.rs:951,980).  `rows` independent
+ * vectors of `cols` elements each, contiguous (rows == 1 is exactly Vector::softmax).
+ * cols == 0 (or rows == 0) -> TRN_EMPTY_VECTOR. */
+TRN_API int trn_softmax_rows_f32(const float* a, float* out, size_t rows, size_t cols);
+TRN_API int trn_log_softmax_rows_f32(const float* a, float* out, size_t rows, size_t cols);
+
+/* ---- Matrix products: host slices -----------------------------------------------------------
+ * Matrix::matmul (src/matrix.rs:285) / GpuBackend::matmul(a, b, m, k, n)
+ * (src/backends/gpu/mod.rs:434).  A is a_rows x a_cols, B is b_rows x b_cols, C is
+ * a_rows x b_cols.  a_cols != b_rows -> TRN_INVALID_INPUT
+ * "Matrix dimension mismatch for multiplication: {}x{} x {}x{} (inner dimensions {} and {} must match)"
+ * (with U+00D7 multiplication signs, as the reference formats it, src/matrix.rs:286-291). */
+TRN_API int trn_matmul_f32(const float* a, size_t a_rows, size_t a_cols,
+                           const float* b, size_t b_rows, size_t b_cols, float* c);
+/* Matrix::batched_matmul (src/matrix.rs:383): A [batch,m,k], B [batch,k,n] -> C [batch,m,n].
+ * a_len/b_len are the slice lengths; mismatch -> TRN_INVALID_INPUT "A data size mismatch: ..." */
+TRN_API int trn_batched_matmul_f32(const float* a, size_t a_len, const float* b, size_t b_len, float* c,
+                                   size_t batch, size_t m, size_t k, size_t n);
+/* Matrix::batched_matmul_4d (src/matrix.rs:464): A [batch,heads,m,k], B [batch,heads,k,n]. */
+TRN_API int trn_batched_matmul_4d_f32(const float* a, size_t a_len, const float* b, size_t b_len, float* c,
+                                      size_t batch, size_t heads, size_t m, size_t k, size_t n);
+/* Matrix::matvec (src/matrix.rs:1657): y = A v.  v_len != cols -> TRN_INVALID_INPUT
+ * "Vector length {} does not match matrix columns {} for matrix-vector multiplication". */
+TRN_API int trn_matvec_f32(const float* a, size_t rows, size_t cols, const float* v, size_t v_len, float* y);
+/* Matrix::transpose (src/matrix.rs:1590) — used by callers of matmul (eigen.rs:483-485). */
+TRN_API int trn_transpose_f32(const float* a, size_t rows, size_t cols, float* out);
+
+/* ---- device-resident twins ------------------------------------------------------------------
+ * Same semantics and validation; pointers are device pointers; results stay in HBM.  Scalar
+ * outputs (`out`) are device pointers to one f32 / one u64.  Stream-ordered, no host sync.
+ * The argmax/argmin twins also emit the winning value (`out_value`, may be NULL) so that a
+ * multi-GPU caller can combine (value, index) pairs across slices. */
+TRN_API int trn_dot_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_sum_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_max_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_min_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_argmax_f32_dev(const float* a, size_t n, uint64_t* out, float* out_value, void* stream);
+TRN_API int trn_argmin_f32_dev(const float* a, size_t n, uint64_t* out, float* out_value, void* stream);
+TRN_API int trn_norm_l2_f32_dev(const float* a, size_t n, float* out, void* stream);
+/* sum of squares without the sqrt: the per-slice partial of a sharded norm_l2 (allreduce, then sqrt) */
+TRN_API int trn_sumsq_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_add_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_mul_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_sigmoid_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_gelu_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_softmax_rows_f32_dev(const float* a, float* out, size_t rows, size_t cols, void* stream);
+TRN_API int trn_log_softmax_rows_f32_dev(const float* a, float* out, size_t rows, size_t cols, void* stream);
+TRN_API int trn_matmul_f32_dev(const float* a, size_t a_rows, size_t a_cols,
+                               const float* b, size_t b_rows, size_t b_cols, float* c, void* stream);
+TRN_API int trn_batched_matmul_f32_dev(const float* a, size_t a_len, const float* b, size_t b_len, float* c,
+                                       size_t batch, size_t m, size_t k, size_t n, void* stream);
+TRN_API int trn_batched_matmul_4d_f32_dev(const float* a, size_t a_len, const float* b, size_t b_len, float* c,
+                                          size_t batch, size_t heads, size_t m, size_t k, size_t n, void* stream);
+TRN_API int trn_matvec_f32_dev(const float* a, size_t rows, size_t cols, const float* v, size_t v_len,
+                               float* y, void* stream);
+TRN_API int trn_transpose_f32_dev(const float* a, size_t rows, size_t cols, float* out, void* stream);
+
+/* ---- GEMM engine selection (measurement and tests) ------------------------------------------
+ * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
+ * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them
+ * (BASELINE.json config 2: "3xTF32 tcgen05 vs SIMT FFMA").  0 = auto, 1 = SIMT FFMA,
+ * 2 = tcgen05 3xTF32, 3 = tcgen05 1xTF32 (peak probe only; NOT fp32-accurate, never auto-selected). */
+TRN_API int trn_set_gemm_engine(int engine);
+TRN_API int trn_get_gemm_engine(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRUENO_CUDA_H */

@@ -1,0 +1,153 @@
+"""Development micro-benchmark: times each hot-path kernel device-resident with CUDA events.
+Not the judged bench (that is bench.py) — this is the per-kernel exploration tool.
+usage: python scripts/quick_bench.py [reduce] [map] [softmax] [gemm] [batched] [matvec]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import trueno_b200 as trn  # noqa: E402
+
+PEAKS = {}
+try:
+    PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+except Exception:
+    pass
+HBM = PEAKS.get("hbm_gbs", 6650.0)
+
+
+def timeit(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for s, e in evs:
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    which = set(sys.argv[1:]) or {"reduce", "map", "softmax", "gemm", "batched", "matvec"}
+    torch.cuda.set_device(0)
+    trn.check(trn.lib.trn_cuda_init(0))
+    st = torch.cuda.current_stream().cuda_stream
+    L = trn.lib
+    print(trn.device_info(), "HBM peak (measured)", HBM)
+
+    if "reduce" in which:
+        n = 1 << 30
+        a = torch.rand(n, device="cuda") * 2 - 1
+        b = torch.rand(n, device="cuda") * 2 - 1
+        out = torch.zeros(4, device="cuda")
+        oidx = torch.zeros(2, device="cuda", dtype=torch.int64)
+        for name, fn, nbytes in [
+            ("sum", lambda: L.trn_sum_f32_dev(a.data_ptr(), n, out.data_ptr(), st), 4 * n),
+            ("dot", lambda: L.trn_dot_f32_dev(a.data_ptr(), n, b.data_ptr(), n, out.data_ptr(), st), 8 * n),
+            ("norm_l2", lambda: L.trn_norm_l2_f32_dev(a.data_ptr(), n, out.data_ptr(), st), 4 * n),
+            ("argmax", lambda: L.trn_argmax_f32_dev(a.data_ptr(), n, oidx.data_ptr(), out.data_ptr(), st), 4 * n),
+            ("max", lambda: L.trn_max_f32_dev(a.data_ptr(), n, out.data_ptr(), st), 4 * n),
+            ("torch.sum (ref)", lambda: torch.sum(a), 4 * n),
+        ]:
+            med, best = timeit(fn)
+            print(f"reduce {name:16s} n=2^30 median {med:.3f} ms best {best:.3f} ms  {nbytes / med / 1e6:.0f} GB/s "
+                  f"({nbytes / med / 1e6 / HBM:.2%} of measured HBM)")
+        del a, b
+
+    if "map" in which:
+        n = 4096 * 32000
+        a = torch.randn(n, device="cuda")
+        b = torch.randn(n, device="cuda")
+        o = torch.empty(n, device="cuda")
+        for name, fn, nbytes in [
+            ("add", lambda: L.trn_add_f32_dev(a.data_ptr(), n, b.data_ptr(), n, o.data_ptr(), st), 12 * n),
+            ("mul", lambda: L.trn_mul_f32_dev(a.data_ptr(), n, b.data_ptr(), n, o.data_ptr(), st), 12 * n),
+            ("sigmoid", lambda: L.trn_sigmoid_f32_dev(a.data_ptr(), n, o.data_ptr(), st), 8 * n),
+            ("gelu", lambda: L.trn_gelu_f32_dev(a.data_ptr(), n, o.data_ptr(), st), 8 * n),
+            ("torch.add (ref)", lambda: torch.add(a, b, out=o), 12 * n),
+        ]:
+            med, best = timeit(fn)
+            print(f"map {name:16s} n=131M median {med:.3f} ms best {best:.3f} ms  {nbytes / med / 1e6:.0f} GB/s "
+                  f"({nbytes / med / 1e6 / HBM:.2%})")
+        del a, b, o
+
+    if "softmax" in which:
+        rows, cols = 4096, 32000
+        a = torch.randn(rows, cols, device="cuda") * 4
+        o = torch.empty_like(a)
+        nbytes = 8 * rows * cols
+        for name, fn in [
+            ("softmax", lambda: L.trn_softmax_rows_f32_dev(a.data_ptr(), o.data_ptr(), rows, cols, st)),
+            ("log_softmax", lambda: L.trn_log_softmax_rows_f32_dev(a.data_ptr(), o.data_ptr(), rows, cols, st)),
+            ("torch.softmax (ref)", lambda: torch.softmax(a, dim=1, out=o)),
+        ]:
+            med, best = timeit(fn)
+            print(f"softmax {name:20s} 4096x32000 median {med:.3f} ms best {best:.3f} ms  {nbytes / med / 1e6:.0f} GB/s "
+                  f"({nbytes / med / 1e6 / HBM:.2%})")
+        del a, o
+
+    if "gemm" in which:
+        for size in (2048, 4096, 8192):
+            m = k = n = size
+            a = torch.rand(m, k, device="cuda")
+            b = torch.rand(k, n, device="cuda")
+            c = torch.empty(m, n, device="cuda")
+            flop = 2.0 * m * n * k
+            for name, eng in [("simt", 1), ("tc 3xTF32", 2), ("tc 1xTF32", 3)]:
+                if eng == 1 and size > 4096:
+                    continue
+                trn.set_gemm_engine(eng)
+                fn = lambda: trn.check(L.trn_matmul_f32_dev(a.data_ptr(), m, k, b.data_ptr(), k, n, c.data_ptr(), st))
+                med, best = timeit(fn, iters=10)
+                print(f"gemm {size}^3 {name:10s} median {med:.3f} ms best {best:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
+                if eng == 2:
+                    ref = (a.double() @ b.double())
+                    err = ((c.double() - ref).abs() / (a.double().abs() @ b.double().abs())).max().item()
+                    print(f"      3xTF32 max err / sum|a||b| = {err:.3e}")
+            trn.set_gemm_engine(0)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            med, best = timeit(lambda: torch.matmul(a, b, out=c), iters=10)
+            print(f"gemm {size}^3 cuBLAS TF32  median {med:.3f} ms best {best:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s  (peak probe)")
+            torch.backends.cuda.matmul.allow_tf32 = False
+            med, best = timeit(lambda: torch.matmul(a, b, out=c), iters=5)
+            print(f"gemm {size}^3 cuBLAS FP32  median {med:.3f} ms best {best:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
+            del a, b, c
+
+    if "batched" in which:
+        B, H, m, k, n = 8, 32, 2048, 128, 2048
+        a = torch.rand(B * H * m * k, device="cuda")
+        b = torch.rand(B * H * k * n, device="cuda")
+        c = torch.empty(B * H * m * n, device="cuda")
+        flop = 2.0 * B * H * m * n * k
+        nbytes = 4.0 * (a.numel() + b.numel() + c.numel())
+        for name, eng in [("tc 3xTF32", 2)]:
+            trn.set_gemm_engine(eng)
+            fn = lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(),
+                                                                   c.data_ptr(), B, H, m, k, n, st))
+            med, best = timeit(fn, iters=10)
+            print(f"batched4d {name} median {med:.3f} ms best {best:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s  "
+                  f"{nbytes / med / 1e6:.0f} GB/s algorithmic")
+        trn.set_gemm_engine(0)
+        a3, b3 = a.view(B * H, m, k), b.view(B * H, k, n)
+        med, best = timeit(lambda: torch.bmm(a3, b3, out=c.view(B * H, m, n)), iters=5)
+        print(f"batched4d cuBLAS FP32 median {med:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
+        del a, b, c
+
+    if "matvec" in which:
+        rows = cols = 16384
+        a = torch.randn(rows, cols, device="cuda")
+        v = torch.randn(cols, device="cuda")
+        y = torch.empty(rows, device="cuda")
+        med, best = timeit(lambda: L.trn_matvec_f32_dev(a.data_ptr(), rows, cols, v.data_ptr(), cols, y.data_ptr(), st))
+        print(f"matvec 16384^2 median {med:.3f} ms  {4.0 * rows * cols / med / 1e6:.0f} GB/s ({4.0 * rows * cols / med / 1e6 / HBM:.2%})")
+    print("launches:", trn.launch_count())
+
+
+if __name__ == "__main__":
+    main()

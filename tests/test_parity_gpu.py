@@ -1,0 +1,434 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, the reference's KATs and
+size-independent properties.  Needs a B200: run with `-m gpu`.
+
+Stated tolerances:
+  * argmax/argmin indices, add, mul, vecmat (rows == 1 matmul)      : bit-exact
+  * dot / sum / norm_l2            : |gpu - f64 truth| <= 1e-5 * sum|terms|   (condition-aware "1e-5 rel")
+  * matmul family                  : |gpu - f64 truth| <= 1e-5 * sum_k |a_ik||b_kj|
+  * softmax / log_softmax          : <= 1e-6 abs vs the scalar-libm oracle (tests/pixel_fkr.rs:30) for
+                                     softmax; 4e-6 abs for log_softmax (values are O(10), 1 ulp = 1e-6)
+  * sigmoid                        : <= 4 ulp vs the scalar-libm oracle
+  * gelu                           : <= 4 ulp(|y|) + 4 * 2^-24 * |x| (the 1 + tanh cancellation term)
+"""
+import numpy as np
+import pytest
+
+import kats
+from oracle import AVX2, SCALAR
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def ulp(x):
+    return np.spacing(np.abs(x).astype(f32)).astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------------------
+# reductions
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kat", kats.REDUCTION_KATS, ids=[k[0] for k in kats.REDUCTION_KATS])
+def test_reduction_kats(trn, kat):
+    _, op, args, expected, tol, _ = kat
+    vs = [trn.Vector.from_slice(a) for a in args]
+    got = getattr(vs[0], op)(*vs[1:])
+    assert abs(float(got) - expected) <= tol
+
+
+@pytest.mark.parametrize("kat", kats.ARG_KATS, ids=[k[0] for k in kats.ARG_KATS])
+def test_arg_kats(trn, kat):
+    _, op, v, expected, _ = kat
+    assert getattr(trn.Vector.from_slice(v), op)() == expected
+
+
+def test_planted_extrema(trn):
+    v, at = kats.planted32("max")
+    assert trn.Vector.from_slice(v).argmax() == at
+    v, at = kats.planted32("min")
+    assert trn.Vector.from_slice(v).argmin() == at
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 4099, 65537, 1 << 20, (1 << 22) + 3])
+def test_reductions_vs_oracle(trn, oracle, n):
+    rng = np.random.default_rng(n)
+    a = rng.uniform(-1, 1, n).astype(f32)
+    b = rng.uniform(-1, 1, n).astype(f32)
+    va, vb = trn.Vector.from_slice(a), trn.Vector.from_slice(b)
+    truth_dot, abs_dot = oracle.f64_dot(a, b)
+    truth_sum, abs_sum = oracle.f64_sum(a)
+    truth_sq, _ = oracle.f64_dot(a, a)
+    assert abs(float(va.dot(vb)) - truth_dot) <= 1e-5 * abs_dot
+    assert abs(float(va.sum()) - truth_sum) <= 1e-5 * abs_sum
+    assert abs(float(va.norm_l2()) - np.sqrt(truth_sq)) <= 1e-5 * np.sqrt(truth_sq)
+    # and the reference's own result sits inside the same band around ours at these sizes
+    assert abs(float(va.dot(vb)) - float(oracle.dot(a, b))) <= 2e-5 * abs_dot
+    assert abs(float(va.sum()) - float(oracle.sum(a))) <= 2e-5 * abs_sum
+    # max/min/argmax/argmin: exact against the scalar backend
+    assert va.max() == oracle.max(a, backend=SCALAR)
+    assert va.min() == oracle.min(a, backend=SCALAR)
+    assert va.argmax() == oracle.argmax(a, backend=SCALAR)
+    assert va.argmin() == oracle.argmin(a, backend=SCALAR)
+
+
+def test_arg_first_occurrence_with_heavy_ties(trn, oracle):
+    rng = np.random.default_rng(7)
+    for n in (17, 1000, 100_003, (1 << 21) + 11):
+        a = rng.integers(-3, 4, n).astype(f32)  # 7 distinct values -> massive ties across threads/blocks
+        v = trn.Vector.from_slice(a)
+        assert v.argmax() == oracle.argmax(a, backend=SCALAR) == int(np.argmax(a))
+        assert v.argmin() == oracle.argmin(a, backend=SCALAR) == int(np.argmin(a))
+    # the cross-lane tie the AVX2 path gets wrong — we follow the scalar rule
+    a = np.zeros(16, f32); a[9] = 5; a[3] = 5
+    assert trn.Vector.from_slice(a).argmax() == 3
+
+
+def test_nan_and_signed_zero_semantics_follow_scalar_backend(trn, oracle):
+    cases = [
+        kats.arr(1, np.nan, 3, 2), kats.arr(np.nan, 1, 2), kats.arr(-np.inf, np.nan, -np.inf),
+        kats.arr(-np.inf, -np.inf), kats.arr(np.inf, np.inf, 1), kats.arr(-0.0, 0.0, -0.0), kats.arr(0.0, -0.0),
+        np.concatenate([np.full(5000, np.nan, f32), kats.arr(2, 7, 7)]).astype(f32),
+    ]
+    for a in cases:
+        v = trn.Vector.from_slice(a)
+        assert v.argmax() == oracle.argmax(a, backend=SCALAR)
+        assert v.argmin() == oracle.argmin(a, backend=SCALAR)
+        for op in ("max", "min"):
+            got, want = getattr(v, op)(), getattr(oracle, op)(a, backend=SCALAR)
+            assert (np.isnan(got) and np.isnan(want)) or (got == want and np.signbit(got) == np.signbit(want))
+
+
+def test_reduction_determinism(trn):
+    a = np.random.default_rng(3).standard_normal((1 << 20) + 5).astype(f32)
+    v = trn.Vector.from_slice(a)
+    first = (v.sum().tobytes(), v.dot(v).tobytes(), v.norm_l2().tobytes())
+    for _ in range(5):
+        assert (v.sum().tobytes(), v.dot(v).tobytes(), v.norm_l2().tobytes()) == first
+
+
+def test_sum_does_not_stagnate_like_avx2(trn, oracle):
+    # AVX2 sum of 8*(2^24+4096) ones returns 2^27; the CUDA path returns n
+    n = 8 * ((1 << 24) + 4096)
+    a = np.ones(n, f32)
+    assert float(trn.Vector.from_slice(a).sum()) == float(n)
+    assert float(oracle.sum(a, backend=AVX2)) == float(1 << 27)
+
+
+def test_smoke_e2e_dot_norm(trn):
+    # tests/smoke_e2e.rs:54-91
+    n = 10_000
+    i = np.arange(n, dtype=f32)
+    a, b = np.sin(i).astype(f32), np.cos(i).astype(f32)
+    expect = np.sum(a.astype(np.float64) * b.astype(np.float64))
+    assert abs(float(trn.Vector.from_slice(a).dot(trn.Vector.from_slice(b))) - expect) < 1e-5 * n
+    c = np.sin(i * f32(0.01)).astype(f32)
+    assert abs(float(trn.Vector.from_slice(c).norm_l2()) - np.sqrt(np.sum(c.astype(np.float64) ** 2))) < 1e-5 * np.sqrt(n)
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 1024, 4097, 100_000, (1 << 22) + 1])
+def test_add_mul_bit_exact(trn, oracle, n):
+    rng = np.random.default_rng(n)
+    a = (rng.standard_normal(n) * 10 ** rng.uniform(-20, 20, n)).astype(f32)
+    b = (rng.standard_normal(n) * 10 ** rng.uniform(-20, 20, n)).astype(f32)
+    if n > 4:
+        a[1], b[2], a[3] = np.nan, np.inf, -np.inf
+    va, vb = trn.Vector.from_slice(a), trn.Vector.from_slice(b)
+    with np.errstate(all="ignore"):
+        for op in ("add", "mul"):
+            got = getattr(va, op)(vb).as_slice()
+            want = getattr(oracle, op)(a, b)
+            assert np.array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)])
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+
+
+def test_sigmoid_parity(trn, oracle):
+    x = np.concatenate([np.linspace(-60, 60, 200_001), kats.arr(0, 2, -2, -100, 100, 50, -50, 50.0001, -50.0001)]).astype(f32)
+    got = trn.Vector.from_slice(x).sigmoid().as_slice()
+    want = oracle.sigmoid(x, backend=SCALAR)
+    assert np.max(np.abs(got.astype(np.float64) - want) / ulp(want)) <= 4
+    assert got[200_001] == f32(0.5) and got[200_004] == 0.0 and got[200_005] == 1.0   # src/vector.rs:8087-8160
+    poly = oracle.sigmoid(x, backend=AVX2)   # what trueno's default AVX2 path returns: degree-6 Taylor exp
+    assert np.max(np.abs(got - poly)) < 2e-6
+
+
+def test_gelu_parity(trn, oracle):
+    x = np.concatenate([np.linspace(-12, 12, 200_001), kats.arr(-2, -1, -0.5, 0, 0.5, 1, 2)]).astype(f32)
+    got = trn.Vector.from_slice(x).gelu().as_slice()
+    want = oracle.gelu(x, backend=SCALAR)
+    tol = 4 * ulp(want) + 4 * 2.0 ** -24 * np.abs(x)
+    assert np.all(np.abs(got.astype(np.float64) - want) <= tol)
+    assert got[200_001 + 3] == 0.0                                                      # src/vector.rs:8352-8360
+    ref = 0.5 * x.astype(np.float64) * (1 + np.tanh(0.7978845608 * (x + 0.044715 * x.astype(np.float64) ** 3)))
+    assert np.max(np.abs(got - ref)) < 1e-4                                             # falsification_tests.rs:1020
+    assert np.max(np.abs(got - oracle.gelu(x, backend=AVX2))) < 1e-5 * np.maximum(1, np.abs(x)).max()
+
+
+def test_map_nan_propagation(trn):
+    x = kats.arr(1, np.nan, np.inf, -np.inf, 0)
+    s = trn.Vector.from_slice(x).sigmoid().as_slice()
+    assert np.isnan(s[1]) and s[2] == 1.0 and s[3] == 0.0
+    g = trn.Vector.from_slice(x).gelu().as_slice()
+    assert np.isnan(g[1]) and g[2] == np.inf
+
+
+# ------------------------------------------------------------------------------------------------
+# softmax / log_softmax
+# ------------------------------------------------------------------------------------------------
+def test_softmax_kats(trn):
+    r = trn.Vector.from_slice([1, 1, 1, 1]).softmax().as_slice()
+    assert np.all(np.abs(r - 0.25) < 1e-5)                                # src/vector.rs:7866-7875
+    r = trn.Vector.from_slice([1000, 1001, 1002]).softmax().as_slice()
+    assert np.all(np.isfinite(r)) and abs(r.sum() - 1) < 1e-5            # src/vector.rs:7890-7905
+    r = trn.Vector.from_slice([1, 2, 3]).softmax().as_slice()
+    assert r[0] < r[1] < r[2] and abs(r.sum() - 1) < 1e-6
+
+
+def test_pixel_fkr_softmax(trn, oracle):
+    x = kats.SimpleRng(22222).gen_vec(2048)                               # tests/pixel_fkr.rs:401-419
+    got = trn.Vector.from_slice(x).softmax().as_slice()
+    assert np.max(np.abs(got - oracle.softmax(x, backend=SCALAR))) <= 1e-6
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 4), (5, 7), (4, 1000), (7, 1001), (3, 1024), (2, 2048), (5, 4096),
+                                       (3, 8192), (4, 16384), (6, 32000), (2, 32768), (3, 40000), (2, 65536),
+                                       (2, 70000), (1, 200_003), (300, 32000)])
+def test_softmax_rows_vs_oracle(trn, oracle, rows, cols):
+    rng = np.random.default_rng(rows * 131 + cols)
+    x = (rng.standard_normal((rows, cols)) * 4).astype(f32)
+    got = trn.softmax_rows(x, rows, cols)
+    want = oracle.softmax_rows(x, rows, cols, backend=SCALAR)
+    assert np.max(np.abs(got - want)) <= 1e-6
+    assert np.max(np.abs(got.astype(np.float64).sum(1) - 1)) < 1e-5       # proptest: sums to 1 (src/vector.rs:13461)
+    glog = trn.softmax_rows(x, rows, cols, log=True)
+    wlog = oracle.softmax_rows(x, rows, cols, log=True, backend=SCALAR)
+    assert np.max(np.abs(glog - wlog)) <= 4e-6
+    # translation invariance (src/vector.rs:13490-13530)
+    shifted = trn.softmax_rows((x + f32(3)).astype(f32), rows, cols)
+    assert np.max(np.abs(shifted - got)) <= 2e-6
+
+
+def test_softmax_determinism_and_nan_row(trn):
+    x = (np.random.default_rng(5).standard_normal((4, 32000)) * 4).astype(f32)
+    a = trn.softmax_rows(x, 4, 32000)
+    assert np.array_equal(a, trn.softmax_rows(x, 4, 32000))
+    x[2, 17] = np.nan
+    b = trn.softmax_rows(x, 4, 32000)
+    assert np.isnan(b[2]).all() and np.array_equal(b[[0, 1, 3]], a[[0, 1, 3]])
+
+
+# ------------------------------------------------------------------------------------------------
+# matmul family
+# ------------------------------------------------------------------------------------------------
+ENGINES = [("simt", 1), ("tc3", 2), ("auto", 0)]
+
+
+@pytest.fixture(params=ENGINES, ids=[e[0] for e in ENGINES])
+def engine(request, trn):
+    trn.set_gemm_engine(request.param[1])
+    yield request.param[0]
+    trn.set_gemm_engine(0)
+
+
+@pytest.mark.parametrize("kat", kats.MATMUL_KATS, ids=[k[0] for k in kats.MATMUL_KATS])
+def test_matmul_kats(trn, engine, kat):
+    _, A, B, expected, tol, _ = kat
+    if A.shape[0] == 1 and engine != "auto":
+        pytest.skip("rows == 1 always takes the vecmat path")
+    C = trn.Matrix.from_vec(*A.shape, A).matmul(trn.Matrix.from_vec(*B.shape, B)).to_numpy()
+    assert np.max(np.abs(C - expected)) <= tol
+
+
+def matmul_check(trn, oracle, A, B, rtol=1e-5, samples=4096, seed=0):
+    m, k = A.shape
+    n = B.shape[1]
+    C = trn.Matrix.from_vec(m, k, A).matmul(trn.Matrix.from_vec(k, n, B)).to_numpy()
+    rng = np.random.default_rng(seed)
+    if m * n <= samples:
+        rows, cols = np.divmod(np.arange(m * n), n)
+    else:
+        rows, cols = rng.integers(0, m, samples), rng.integers(0, n, samples)
+        rows[:4], cols[:4] = [0, m - 1, 0, m - 1], [0, 0, n - 1, n - 1]
+    truth, scale = oracle.f64_matmul_samples(A, B, k, n, rows, cols)
+    err = np.abs(C[rows, cols].astype(np.float64) - truth)
+    assert np.all(err <= rtol * np.maximum(scale, 1e-30)), float(np.max(err / np.maximum(scale, 1e-30)))
+    return C
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (8, 8, 8), (16, 16, 16), (33, 33, 33), (64, 64, 64), (65, 65, 65),
+                                   (100, 100, 100), (127, 127, 127), (128, 128, 128), (67, 89, 71), (384, 74, 384),
+                                   (64, 128, 32), (256, 256, 256), (129, 257, 513), (512, 512, 512), (300, 1000, 700)])
+def test_matmul_shapes_vs_truth(trn, oracle, engine, shape):
+    m, k, n = shape
+    rng = np.random.default_rng(m * 7 + k * 3 + n)
+    A = rng.uniform(-1, 1, (m, k)).astype(f32)
+    B = rng.uniform(-1, 1, (k, n)).astype(f32)
+    matmul_check(trn, oracle, A, B)
+
+
+@pytest.mark.parametrize("size", [256, 512, 1024])
+def test_matmul_reference_fixture(trn, oracle, engine, size):
+    # src/matrix.rs:2540-2714: A[i]=(i%100)/10, B[i]=((i*7)%100)/10; reference tolerance 1e-2 rel, ours 1e-5
+    A, B = kats.fixture_mod(size, size, size, 100, 10, 7, 100, 10)
+    C = matmul_check(trn, oracle, A, B)
+    if size <= 512:
+        want = oracle.matmul(A, A.shape, B, B.shape)      # what trueno's AVX2 path returns
+        assert np.max(np.abs(C - want) / np.maximum(np.abs(want), 1)) < 1e-5
+
+
+def test_matmul_bench_data_512(trn, oracle, engine):
+    # benches/matrix_ops.rs:23-25 — config 1's exact workload: integers, products exact in f32 up to 2^24
+    i = np.arange(512 * 512)
+    A = (i % 100).astype(f32).reshape(512, 512)
+    B = ((i * 2) % 100).astype(f32).reshape(512, 512)
+    C = trn.Matrix.from_vec(512, 512, A).matmul(trn.Matrix.from_vec(512, 512, B)).to_numpy()
+    want = A.astype(np.float64) @ B.astype(np.float64)    # < 2^24 -> exactly representable
+    assert np.array_equal(C.astype(np.float64), want)
+    assert np.array_equal(C, oracle.matmul(A, A.shape, B, B.shape))
+
+
+def test_matmul_identity_zero_and_transpose(trn, engine):
+    rng = np.random.default_rng(11)
+    for n in (4, 64, 200):
+        A = rng.standard_normal((n, n)).astype(f32)
+        Am = trn.Matrix.from_vec(n, n, A)
+        assert np.max(np.abs(Am.matmul(trn.Matrix.identity(n)).to_numpy() - A)) < 1e-5   # src/matrix.rs:3290
+        assert not Am.matmul(trn.Matrix.zeros(n, n)).to_numpy().any()
+    A = rng.standard_normal((37, 91)).astype(f32)
+    B = rng.standard_normal((91, 53)).astype(f32)
+    Am, Bm = trn.Matrix.from_vec(37, 91, A), trn.Matrix.from_vec(91, 53, B)
+    assert np.array_equal(Am.transpose().to_numpy(), A.T)
+    lhs = Am.matmul(Bm).transpose().to_numpy()                                            # (AB)^T = B^T A^T
+    rhs = Bm.transpose().matmul(Am.transpose()).to_numpy()
+    assert np.max(np.abs(lhs - rhs) / np.maximum(np.abs(lhs), 1)) < 1e-3                  # src/matrix.rs:3330
+
+
+def test_matmul_nan_inf_propagation(trn, engine):
+    # tests/wasm_optimization_tests.rs:160-196
+    for n in (4, 160):
+        A = np.ones((n, n), f32); A[2, 3] = np.nan
+        C = trn.Matrix.from_vec(n, n, A).matmul(trn.Matrix.from_vec(n, n, np.ones((n, n), f32))).to_numpy()
+        assert np.isnan(C[2]).all() and np.isfinite(np.delete(C, 2, 0)).all()
+        big = np.full((n, n), np.finfo(f32).max, f32)
+        C = trn.Matrix.from_vec(n, n, big).matmul(trn.Matrix.from_vec(n, n, np.full((n, n), 2, f32))).to_numpy()
+        assert (np.isinf(C) | np.isnan(C)).all()
+        A = np.ones((n, n), f32); A[1, 1] = np.inf
+        C = trn.Matrix.from_vec(n, n, A).matmul(trn.Matrix.from_vec(n, n, np.ones((n, n), f32))).to_numpy()
+        assert np.isposinf(C[1]).all() and np.isfinite(np.delete(C, 1, 0)).all()
+
+
+def test_matmul_deterministic_100_runs(trn, engine):
+    # tests/wasm_optimization_tests.rs:200-230
+    A = ((np.arange(128 * 128) % 97).astype(f32) * f32(0.01))
+    B = ((np.arange(128 * 128) % 83).astype(f32) * f32(0.01))
+    Am, Bm = trn.Matrix.from_vec(128, 128, A), trn.Matrix.from_vec(128, 128, B)
+    first = Am.matmul(Bm).as_slice().tobytes()
+    for _ in range(100):
+        assert Am.matmul(Bm).as_slice().tobytes() == first
+
+
+def test_matmul_empty(trn):
+    # tests/wasm_optimization_tests.rs:234-250 — 0x0 must not crash
+    C = trn.Matrix.zeros(0, 0).matmul(trn.Matrix.zeros(0, 0))
+    assert C.shape() == (0, 0)
+    C = trn.Matrix.zeros(3, 0).matmul(trn.Matrix.zeros(0, 4))
+    assert C.shape() == (3, 4) and not C.to_numpy().any()
+
+
+def test_row_vector_path_is_bit_exact_with_reference(trn, oracle):
+    # src/matrix.rs:540-569: same order, same rounding, same skip-zero rule => identical bits
+    rng = np.random.default_rng(13)
+    for k, n in ((2, 2), (384, 5186), (1000, 33)):
+        a = rng.standard_normal((1, k)).astype(f32)
+        a[0, ::7] = 0
+        B = rng.standard_normal((k, n)).astype(f32)
+        got = trn.Matrix.from_vec(1, k, a).matmul(trn.Matrix.from_vec(k, n, B)).to_numpy()
+        assert np.array_equal(got, oracle.matmul(a, a.shape, B, B.shape))
+    a = kats.arr(0, 1).reshape(1, 2)
+    B = np.array([[np.nan, np.nan], [2, 3]], f32)
+    assert np.array_equal(trn.Matrix.from_vec(1, 2, a).matmul(trn.Matrix.from_vec(2, 2, B)).to_numpy(), [[2, 3]])
+
+
+def test_batched_kats(trn, engine):
+    k = kats.BATCHED_KAT
+    got = trn.Matrix.batched_matmul(k["a"], k["b"], k["batch"], k["m"], k["k"], k["n"])
+    assert np.max(np.abs(got - k["expected"])) < 1e-5
+    k = kats.BATCHED4D_KAT
+    got = trn.Matrix.batched_matmul_4d(k["a"], k["b"], k["batch"], k["heads"], k["m"], k["k"], k["n"])
+    assert np.max(np.abs(got - k["expected"])) < 1e-5
+
+
+@pytest.mark.parametrize("dims", [(2, 3, 64, 32, 64), (1, 4, 256, 128, 256), (2, 2, 130, 70, 257)])
+def test_batched_4d_vs_oracle(trn, oracle, engine, dims):
+    # attention pattern Q @ K^T (src/matrix.rs:3985-4005): every head equals the single-matrix product
+    batch, heads, m, k, n = dims
+    rng = np.random.default_rng(sum(dims))
+    A = rng.uniform(-1, 1, batch * heads * m * k).astype(f32)
+    B = rng.uniform(-1, 1, batch * heads * k * n).astype(f32)
+    got = trn.Matrix.batched_matmul_4d(A, B, batch, heads, m, k, n).reshape(batch * heads, m, n)
+    for h in range(batch * heads):
+        Ah, Bh = A.reshape(-1, m, k)[h], B.reshape(-1, k, n)[h]
+        truth = Ah.astype(np.float64) @ Bh.astype(np.float64)
+        scale = np.abs(Ah).astype(np.float64) @ np.abs(Bh).astype(np.float64)
+        assert np.all(np.abs(got[h] - truth) <= 1e-5 * scale)
+        single = trn.Matrix.from_vec(m, k, Ah).matmul(trn.Matrix.from_vec(k, n, Bh)).to_numpy()
+        assert np.array_equal(single, got[h])
+
+
+def test_matvec(trn, oracle):
+    k = kats.MATVEC_KAT
+    got = trn.Matrix.from_vec(k["rows"], k["cols"], k["a"]).matvec(trn.Vector.from_slice(k["v"])).as_slice()
+    assert np.array_equal(got, k["expected"])
+    rng = np.random.default_rng(17)
+    for rows, cols in ((4096, 512), (33, 1001), (1, 7), (1000, 4096), (5, 100_000)):   # src/matrix.rs:2719-2776
+        A = rng.standard_normal((rows, cols)).astype(f32)
+        v = rng.standard_normal(cols).astype(f32)
+        got = trn.Matrix.from_vec(rows, cols, A).matvec(trn.Vector.from_slice(v)).as_slice()
+        truth = A.astype(np.float64) @ v.astype(np.float64)
+        scale = np.abs(A).astype(np.float64) @ np.abs(v).astype(np.float64)
+        assert np.all(np.abs(got - truth) <= 1e-5 * scale)
+        assert np.all(np.abs(got - oracle.matvec(A, rows, cols, v)) <= 2e-5 * scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident chain and pinned staging
+# ------------------------------------------------------------------------------------------------
+def test_device_resident_chain(trn, oracle):
+    import ctypes as C
+    n = 1 << 20
+    rng = np.random.default_rng(19)
+    a, b = rng.standard_normal(n).astype(f32), rng.standard_normal(n).astype(f32)
+    da, db, dc, dd = (trn.DeviceBuffer.from_host(a), trn.DeviceBuffer.from_host(b), trn.DeviceBuffer(n), trn.DeviceBuffer(n))
+    ds = trn.DeviceBuffer(4)
+    # d = gelu(a * b + a); s = dot(d, b) — four kernels, nothing leaves HBM until the end
+    trn.check(trn.lib.trn_mul_f32_dev(da.ptr, n, db.ptr, n, dc.ptr, None))
+    trn.check(trn.lib.trn_add_f32_dev(dc.ptr, n, da.ptr, n, dc.ptr, None))
+    trn.check(trn.lib.trn_gelu_f32_dev(dc.ptr, n, dd.ptr, None))
+    trn.check(trn.lib.trn_dot_f32_dev(dd.ptr, n, db.ptr, n, ds.ptr, None))
+    trn.synchronize()
+    d = dd.to_host()
+    want = oracle.gelu((a * b + a).astype(f32), backend=SCALAR)
+    assert np.all(np.abs(d - want) <= 4 * ulp(want) + 4 * 2.0 ** -24 * np.abs(a * b + a))
+    truth, scale = oracle.f64_dot(d, b)
+    assert abs(float(ds.to_host()[0]) - truth) <= 1e-5 * scale
+
+
+def test_pinned_host_memory_roundtrip(trn):
+    n = 1 << 18
+    a = trn.pinned_empty(n)
+    a[:] = np.arange(n, dtype=f32)
+    v = trn.Vector(a)
+    assert float(v.sum()) == float(np.arange(n, dtype=np.float64).sum())
+    out = v.add(v).as_slice()
+    assert np.array_equal(out, 2 * np.arange(n, dtype=f32))
+
+
+def test_large_pageable_staging(trn):
+    # > 2 staging chunks (32 MiB each) through the pageable path
+    n = (80 << 20) // 4 + 13
+    a = np.ones(n, f32)
+    v = trn.Vector.from_slice(a)
+    assert float(v.sum()) == float(n)
+    out = v.add(v).as_slice()
+    assert out[0] == 2 and out[-1] == 2 and float(out.sum(dtype=np.float64)) == 2.0 * n

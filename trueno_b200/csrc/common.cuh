@@ -1,0 +1,136 @@
+// common.cuh — shared device helpers and the host-side context interface (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "trueno_cuda.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "trueno_b200 kernels are written for sm_100a only"
+#endif
+
+namespace trn {
+
+// ---------------------------------------------------------------------------------------------
+// Host-side context (context.cu)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxReduceBlocks = 148 * 8;   // persistent reduction grid upper bound (B200: 148 SMs)
+
+struct Workspace {            // one per stream: scratch for the single-launch reductions
+    float*    partial_val;    // [kMaxReduceBlocks] per-block partial values
+    uint64_t* partial_idx;    // [kMaxReduceBlocks] per-block partial indices (arg reductions)
+    unsigned* ticket;         // last-block-done counter; self-resetting
+    float*    scalar_f32;     // device slot for host-slice scalar results
+    uint64_t* scalar_u64;
+    float*    host_f32;       // pinned mirrors of the two scalar slots
+    uint64_t* host_u64;
+};
+
+struct Context {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    size_t hbm_bytes;
+    char name[256];
+    cudaStream_t stream;      // the backend's own stream (host-slice calls, default for *_dev)
+    cudaStream_t copy_stream; // second stream for staged H2D/D2H overlap
+};
+
+// Lazily binds the process to a device (LOCAL_RANK or 0); returns nullptr and sets the
+// thread-local error if no sm_100 device is usable.  NEVER falls back to the CPU.
+Context* ctx();
+Workspace* workspace(cudaStream_t s);
+cudaStream_t resolve_stream(void* s);
+void count_launch(unsigned n = 1);
+
+// thread-local error state -------------------------------------------------------------------
+int fail(int status, const char* fmt, ...);
+int fail_mismatch(size_t expected, size_t actual);
+int fail_cuda(cudaError_t e, const char* what);
+
+#define TRN_CUDA(expr)                                                     \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) return ::trn::fail_cuda(_e, #expr);         \
+    } while (0)
+
+#define TRN_TRY(expr)                                                      \
+    do {                                                                   \
+        int _s = (expr);                                                   \
+        if (_s != TRN_OK) return _s;                                       \
+    } while (0)
+
+// stream-ordered scratch (cudaMallocAsync pool with an unlimited release threshold)
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s);
+int scratch_free(void* p, cudaStream_t s);
+
+// host <-> device transfers with pinned staging (context.cu)
+int upload(float* dst_dev, const float* src_host, size_t n, cudaStream_t s);
+int download(float* dst_host, const float* src_dev, size_t n, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (one translation unit per family)
+// ---------------------------------------------------------------------------------------------
+enum class Reduce { Sum, Dot, SumSq, NormL2 };
+int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s);
+// is_max: 1 argmax / 0 argmin.  out_idx / out_val may be null.
+int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s);
+
+enum class Map { Add, Mul, Sigmoid, Gelu };
+int launch_map(Map op, const float* a, const float* b, float* out, size_t n, cudaStream_t s);
+
+int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows, size_t cols, cudaStream_t s);
+
+int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaStream_t s);
+int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, float* y, cudaStream_t s);
+int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s);
+// C[b] = A[b] * B[b], b in [0,batch); strides in elements
+int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
+                     cudaStream_t s);
+// tcgen05 path; terms = 3 (3xTF32, fp32-accurate) or 1 (plain TF32, probe only)
+int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
+                   int terms, cudaStream_t s);
+bool gemm_tc_supported(size_t m, size_t k, size_t n);
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (data is touched once)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// 128-bit streaming store (evict-first: the output is not re-read by this kernel)
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace trn

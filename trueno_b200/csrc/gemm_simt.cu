@@ -1,0 +1,272 @@
+// gemm_simt.cu — SIMT FFMA kernels: GEMM for small/ragged shapes, matvec, row-vector x matrix,
+// and transpose.
+//
+// gemm_simt replaces matmul_naive / matmul_wasm_tiled / matmul_simd_simple (src/matrix.rs:572,
+// :1476, :1407) for shapes that do not fill a tcgen05 tile, and is the "SIMT FFMA" arm of
+// BASELINE.json config 2.  Each C element is ONE FMA chain over ascending k (deterministic, and
+// exact for the small-integer KATs).  matvec replaces Matrix::matvec (src/matrix.rs:1657: one
+// Avx2 dot per row); vecmat replaces matmul_vector_matrix (src/matrix.rs:540) INCLUDING its
+// `a_k == 0.0 -> skip` rule, so 0*NaN contributes nothing on that path exactly as in the reference.
+#include "common.cuh"
+
+namespace trn {
+
+// ---------------------------------------------------------------------------------------------
+// transpose: 32x32 shared-memory tiles (+1 padding), coalesced on both sides.  8 B / element.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
+    __shared__ float tile[32][33];
+    const size_t tiles_x = (cols + 31) / 32, tiles_y = (rows + 31) / 32;
+    const size_t ntiles = tiles_x * tiles_y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t by = t / tiles_x, bx = t % tiles_x;
+#pragma unroll
+        for (int r = 0; r < 32; r += 8) {
+            size_t i = by * 32 + ty + r, j = bx * 32 + tx;
+            if (i < rows && j < cols) tile[ty + r][tx] = in[i * cols + j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 32; r += 8) {
+            size_t j = bx * 32 + ty + r, i = by * 32 + tx;
+            if (i < rows && j < cols) out[j * rows + i] = tile[tx][ty + r];
+        }
+        __syncthreads();
+    }
+}
+
+int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    if (rows == 0 || cols == 0) return TRN_OK;
+    size_t ntiles = ((cols + 31) / 32) * ((rows + 31) / 32);
+    size_t cap = (size_t)c->sm_count * 8;
+    transpose_kernel<<<(unsigned)(ntiles < cap ? ntiles : cap), 256, 0, s>>>(a, out, rows, cols);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// matvec: y = A v.  One warp per row, 128-bit coalesced loads along the row, 4 FMA chains,
+// shuffle fold.  Streams A once: 4 B per matrix element, HBM-bound.
+// ---------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+matvec_kernel(const float* __restrict__ a, const float* __restrict__ v, float* __restrict__ y, size_t rows, size_t cols) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp; r < rows; r += nwarps) {
+        const float* row = a + r * cols;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        if (VEC) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            const float4* v4 = reinterpret_cast<const float4*>(v);
+            const size_t nvec = cols >> 2;
+            size_t i = lane;
+            for (; i + 96 < nvec; i += 128) {
+                float4 x0 = ld_stream(row4 + i), x1 = ld_stream(row4 + i + 32), x2 = ld_stream(row4 + i + 64),
+                       x3 = ld_stream(row4 + i + 96);
+                float4 w0 = __ldg(v4 + i), w1 = __ldg(v4 + i + 32), w2 = __ldg(v4 + i + 64), w3 = __ldg(v4 + i + 96);
+                c0 = fmaf(x0.x, w0.x, c0); c0 = fmaf(x0.y, w0.y, c0); c0 = fmaf(x0.z, w0.z, c0); c0 = fmaf(x0.w, w0.w, c0);
+                c1 = fmaf(x1.x, w1.x, c1); c1 = fmaf(x1.y, w1.y, c1); c1 = fmaf(x1.z, w1.z, c1); c1 = fmaf(x1.w, w1.w, c1);
+                c2 = fmaf(x2.x, w2.x, c2); c2 = fmaf(x2.y, w2.y, c2); c2 = fmaf(x2.z, w2.z, c2); c2 = fmaf(x2.w, w2.w, c2);
+                c3 = fmaf(x3.x, w3.x, c3); c3 = fmaf(x3.y, w3.y, c3); c3 = fmaf(x3.z, w3.z, c3); c3 = fmaf(x3.w, w3.w, c3);
+            }
+            for (; i < nvec; i += 32) {
+                float4 x0 = ld_stream(row4 + i);
+                float4 w0 = __ldg(v4 + i);
+                c0 = fmaf(x0.x, w0.x, c0); c0 = fmaf(x0.y, w0.y, c0); c0 = fmaf(x0.z, w0.z, c0); c0 = fmaf(x0.w, w0.w, c0);
+            }
+        } else {
+            for (size_t i = lane; i < cols; i += 32) c0 = fmaf(row[i], __ldg(v + i), c0);
+        }
+        float sum = warp_sum((c0 + c1) + (c2 + c3));
+        if (lane == 0) y[r] = sum;
+    }
+}
+
+int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, float* y, cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    if (rows == 0) return TRN_OK;
+    const bool vec = cols % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
+    size_t blocks = (rows + 7) / 8;
+    size_t cap = (size_t)c->sm_count * 8;
+    unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    if (vec) matvec_kernel<true><<<grid, 256, 0, s>>>(a, v, y, rows, cols);
+    else     matvec_kernel<false><<<grid, 256, 0, s>>>(a, v, y, rows, cols);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vecmat: y[1 x n] = x[1 x k] * B[k x n]  (Matrix::matmul with rows == 1).
+// The reference accumulates y[j] += x[p] * B[p][j] for ascending p with separate mul and add and
+// SKIPS p when x[p] == 0.0 (src/matrix.rs:552-566).  Same order and rounding here: one thread per
+// output column, p ascending, __fmul_rn + __fadd_rn => bit-identical to the reference's path.
+// B is streamed once with coalesced rows: 4 B per element of B.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vecmat_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, size_t k, size_t n) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        size_t p = 0;
+        for (; p + 4 <= k; p += 4) {
+            const float x0 = __ldg(x + p), x1 = __ldg(x + p + 1), x2 = __ldg(x + p + 2), x3 = __ldg(x + p + 3);
+            const float b0 = ld_stream(b + p * n + j), b1 = ld_stream(b + (p + 1) * n + j),
+                        b2 = ld_stream(b + (p + 2) * n + j), b3 = ld_stream(b + (p + 3) * n + j);
+            if (x0 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x0, b0));
+            if (x1 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x1, b1));
+            if (x2 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x2, b2));
+            if (x3 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x3, b3));
+        }
+        for (; p < k; ++p) {
+            const float xp = __ldg(x + p);
+            if (xp != 0.0f) acc = __fadd_rn(acc, __fmul_rn(xp, ld_stream(b + p * n + j)));
+        }
+        y[j] = acc;
+    }
+}
+
+int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    if (n == 0) return TRN_OK;
+    size_t blocks = (n + 127) / 128;
+    size_t cap = (size_t)c->sm_count * 16;
+    vecmat_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, s>>>(x, b, y, k, n);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT FFMA GEMM: 128x128 CTA tile, BK = 16, 256 threads, 8x8 register micro-tile (split 4+4 so
+// shared-memory reads are conflict-free float4), register-staged double buffering.  Arbitrary
+// m, k, n via guarded loads/stores.  Bound by the FP32 FMA pipe (~2 flop/lane/clk), not HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 16;
+
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                 size_t m, size_t k, size_t n, size_t tiles_m, size_t tiles_n) {
+    __shared__ __align__(16) float sA[2][BK][BM + 4];  // k-major: sA[kk][i]
+    __shared__ __align__(16) float sB[2][BK][BN + 4];  // sB[kk][j]
+
+    const size_t batch = blockIdx.y;
+    A += batch * m * k;
+    B += batch * k * n;
+    C += batch * m * n;
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads; thread owns rows {ty*4..+3, 64+ty*4..+3} x cols likewise
+
+    for (size_t tile = blockIdx.x; tile < tiles_m * tiles_n; tile += gridDim.x) {
+        const size_t bm = (tile / tiles_n) * BM, bn = (tile % tiles_n) * BN;
+
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+        // global -> register staging: A tile 128x16 (each thread: 8 elements), B tile 16x128 (8 elements)
+        float ra[8], rb[8];
+        auto load_tiles = [&](size_t k0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                // A: element index l = e*256 + tid -> row l/16, kk l%16 (16 consecutive k per row: 64 B segments)
+                const int l = e * 256 + tid;
+                const size_t i = bm + (l >> 4), p = k0 + (l & 15);
+                ra[e] = (i < m && p < k) ? A[i * k + p] : 0.f;
+                // B: row kk = l/128, col l%128 (coalesced 512 B rows)
+                const size_t q = k0 + (l >> 7), j = bn + (l & 127);
+                rb[e] = (q < k && j < n) ? B[q * n + j] : 0.f;
+            }
+        };
+        auto store_tiles = [&](int buf) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int l = e * 256 + tid;
+                sA[buf][l & 15][l >> 4] = ra[e];
+                sB[buf][l >> 7][l & 127] = rb[e];
+            }
+        };
+
+        load_tiles(0);
+        store_tiles(0);
+        __syncthreads();
+        int buf = 0;
+        for (size_t k0 = 0; k0 < k; k0 += BK) {
+            const bool more = k0 + BK < k;
+            if (more) load_tiles(k0 + BK);
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                const float4 a_lo = *reinterpret_cast<const float4*>(&sA[buf][kk][ty * 4]);
+                const float4 a_hi = *reinterpret_cast<const float4*>(&sA[buf][kk][64 + ty * 4]);
+                const float4 b_lo = *reinterpret_cast<const float4*>(&sB[buf][kk][tx * 4]);
+                const float4 b_hi = *reinterpret_cast<const float4*>(&sB[buf][kk][64 + tx * 4]);
+                const float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+                const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            if (more) {
+                store_tiles(buf ^ 1);
+                __syncthreads();
+                buf ^= 1;
+            }
+        }
+        __syncthreads();  // all reads of the last buffer are done before the next tile refills it
+
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const size_t row = bm + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (row >= m) continue;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const size_t col = bn + half * 64 + tx * 4;
+                float* dst = C + row * n + col;
+                if (col + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                    *reinterpret_cast<float4*>(dst) =
+                        make_float4(acc[i][half * 4], acc[i][half * 4 + 1], acc[i][half * 4 + 2], acc[i][half * 4 + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < n) dst[j] = acc[i][half * 4 + j];
+                }
+            }
+        }
+    }
+}
+
+int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
+                     cudaStream_t s) {
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
+    if (batch == 0 || m == 0 || n == 0) return TRN_OK;
+    if (k == 0) {  // empty inner dimension: C = 0 (the reference's zero-initialised result)
+        TRN_CUDA(cudaMemsetAsync(c, 0, batch * m * n * sizeof(float), s));
+        return TRN_OK;
+    }
+    const size_t tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+    size_t tiles = tiles_m * tiles_n;
+    size_t cap = (size_t)cx->sm_count * 2;
+    for (size_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.y limit
+        size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)nb);
+        gemm_simt_kernel<<<grid, 256, 0, s>>>(a + b0 * m * k, b + b0 * k * n, c + b0 * m * n, m, k, n, tiles_m, tiles_n);
+        count_launch();
+    }
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+}  // namespace trn

@@ -1,0 +1,496 @@
+// gemm_tc.cu — f32 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), 3xTF32.
+//
+// Replaces Matrix::matmul's blocked AVX2 path (matmul_simd + matmul_microkernel_4x1_avx2,
+// src/matrix.rs:912-1401, :615-688) and the wgpu MATMUL_SHADER (src/backends/gpu/shaders.rs:11-49)
+// for shapes that fill a tensor-core tile; batched_matmul / batched_matmul_4d (src/matrix.rs:383,
+// :464) are the same kernel with a batch coordinate in the tile scheduler.
+//
+// Numerics (3xTF32): every f32 operand x is split once, in a streaming pre-pass, into
+//   hi = tf32_round(x),  lo = tf32_round(x - hi)        (x - hi is exact in f32)
+// and the product is accumulated as  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  in an f32 TMEM
+// accumulator — three kind::tf32 MMAs per logical product.  The dropped lo*lo term is <= 2^-22
+// relative per product.  Non-finite inputs keep hi = x, lo = 0 so Inf/NaN propagate as IEEE.
+// The same pre-pass re-lays B (k x n, row-major) out K-major (n x k), so both operands use the
+// canonical K-major SWIZZLE_128B shared-memory layout, and pads K to a multiple of 32 with
+// zeros so the main loop has no remainder and TMA strides are 16-byte aligned.
+//
+// Kernel: persistent, warp-specialised, one CTA per SM.
+//   warp 0 : TMA producer   (cp.async.bulk.tensor.3d -> smem ring, mbarrier complete_tx)
+//   warp 1 : MMA issuer     (one elected lane; tcgen05.mma.cta_group::1.kind::tf32, 128x256x8),
+//            also owns the TMEM allocation (512 columns = two 128x256 f32 accumulators)
+//   warps 2-5 : epilogue    (tcgen05.ld 32x32b -> registers -> global), overlapped with the next
+//            tile's main loop through the two accumulator stages.
+// Accumulation order is fixed (k ascending, no split-K, no atomics) => bit-identical reruns
+// (tests/wasm_optimization_tests.rs:200-230).
+//
+// Roofline: tensor pipe.  Algorithmic work 2*m*n*k flop; the pipe executes 3x that in TF32.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace trn {
+namespace tc {
+
+constexpr int BM = 128;   // UMMA M (cta_group::1)
+constexpr int BN = 256;   // UMMA N
+constexpr int BK = 32;    // floats per stage row = 128 bytes = one SWIZZLE_128B span
+constexpr int UMMA_K = 8; // kind::tf32: 32 bytes of K per instruction
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 4;  // 16 KiB
+constexpr uint32_t kBBytes = BN * BK * 4;  // 32 KiB
+constexpr uint32_t kTmemCols = 512;        // 2 accumulator stages x 256 columns
+
+template <int TERMS>
+struct Cfg {
+    static constexpr int kOperands = TERMS == 3 ? 2 : 1;  // hi (+ lo)
+    static constexpr uint32_t kStageBytes = kOperands * (kABytes + kBBytes);
+    static constexpr int kStages = TERMS == 3 ? 2 : 4;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread t of the warp receives row (lane base + t), 32 consecutive columns
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups)
+//   [46,48) version = 1 (sm_100)   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+
+struct Params {
+    float* c;
+    uint32_t m, n;            // C rows / cols per batch
+    uint32_t num_kb;          // Kpad / BK
+    uint32_t tiles_m, tiles_n, batch;
+};
+
+// Tile order: batch-major, then groups of 16 m-tiles, n fastest-but-one inside a group, so CTAs
+// that run concurrently share A row-panels and B column-panels in L2.
+__device__ __forceinline__ void tile_coords(uint32_t t, const Params& p, uint32_t& b, uint32_t& mt, uint32_t& nt) {
+    const uint32_t per_batch = p.tiles_m * p.tiles_n;
+    b = t / per_batch;
+    uint32_t r = t % per_batch;
+    constexpr uint32_t G = 16;
+    const uint32_t group = r / (G * p.tiles_n);
+    const uint32_t first_m = group * G;
+    const uint32_t gsize = min(G, p.tiles_m - first_m);
+    const uint32_t in_group = r - group * G * p.tiles_n;
+    mt = first_m + in_group % gsize;
+    nt = in_group / gsize;
+}
+
+template <int TERMS>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const Params p) {
+    using C = Cfg<TERMS>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles must sit on 1024-byte boundaries
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + C::kStages * C::kStageBytes);
+    // barrier slots: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t total_tiles = p.tiles_m * p.tiles_n * p.batch;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_b_hi);
+        if (TERMS == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                uint32_t b, mt, nt;
+                tile_coords(t, p, b, mt, nt);
+                const int m0 = (int)(mt * BM), n0 = (int)(nt * BN);
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * C::kStageBytes;
+                    mbar_expect_tx(full_bar(stage), C::kStageBytes);
+                    const int k0 = (int)(kb * BK);
+                    tma_load_3d(sa, &map_a_hi, full_bar(stage), k0, m0, (int)b);
+                    tma_load_3d(sa + kABytes, &map_b_hi, full_bar(stage), k0, n0, (int)b);
+                    if (TERMS == 3) {
+                        tma_load_3d(sa + kABytes + kBBytes, &map_a_lo, full_bar(stage), k0, m0, (int)b);
+                        tma_load_3d(sa + 2 * kABytes + kBBytes, &map_b_lo, full_bar(stage), k0, n0, (int)b);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem_base + acc * BN;
+            for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_base + stage * C::kStageBytes;
+                    const uint32_t a_hi = sa, b_hi = sa + kABytes;
+                    const uint32_t a_lo = sa + kABytes + kBBytes, b_lo = sa + 2 * kABytes + kBBytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 4;  // 32 bytes along K inside the swizzle span
+                        const uint32_t first = (kb | (uint32_t)k) != 0;
+                        if (TERMS == 3) {
+                            umma_tf32(d, make_desc_k_sw128(a_lo + koff), make_desc_k_sw128(b_hi + koff), idesc, first);
+                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_lo + koff), idesc, 1u);
+                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_hi + koff), idesc, 1u);
+                        } else {
+                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_hi + koff), idesc, first);
+                        }
+                    }
+                    umma_commit(empty_bar(stage));                       // smem slot free once these MMAs retire
+                    if (kb == p.num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const uint32_t quad = warp & 3;  // TMEM lane quadrant this warp may access
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            uint32_t b, mt, nt;
+            tile_coords(t, p, b, mt, nt);
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t row = mt * BM + quad * 32 + lane;
+            float* crow = p.c + ((size_t)b * p.m + row) * p.n + (size_t)nt * BN;
+            const bool row_ok = row < p.m;
+            const bool vec_ok = (p.n % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15u) == 0;  // 16-byte aligned rows
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + acc * BN + chunk * 32, r);
+                tmem_ld_wait();
+                const uint32_t col0 = nt * BN + chunk * 32;
+                if (row_ok && col0 < p.n) {
+                    if (vec_ok && col0 + 32 <= p.n) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(crow + chunk * 32 + 4 * j) =
+                                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.n) crow[chunk * 32 + j] = __uint_as_float(r[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- operand pre-pass: split into tf32 hi/lo, pad K, lay B out K-major ------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    if (!isfinite(x)) { hi = x; lo = 0.f; return; }     // Inf/NaN propagate through hi alone
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    float fh = __uint_as_float(h);
+    if (isinf(fh)) fh = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // rounding overflowed: truncate instead
+    const float r = x - fh;                              // exact
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+    hi = fh;
+    lo = __uint_as_float(l);
+}
+
+// rows x k (row-major, per batch) -> hi/lo [rows x kpad]
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
+                  size_t rows_total, size_t k, size_t kpad) {
+    const size_t total = rows_total * kpad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / kpad, c = i - r * kpad;
+        float h = 0.f, l = 0.f;
+        if (c < k) split_tf32(ld_stream(in + r * k + c), h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+// 4-wide variant for k % 4 == 0 (kpad is always a multiple of 32)
+__global__ void __launch_bounds__(256)
+split_rows_vec_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
+                      size_t rows_total, size_t k, size_t kpad) {
+    const size_t kv = k >> 2, kpv = kpad >> 2;
+    const size_t total = rows_total * kpv;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / kpv, c = i - r * kpv;
+        float4 h = make_float4(0, 0, 0, 0), l = h;
+        if (c < kv) {
+            const float4 x = ld_stream(reinterpret_cast<const float4*>(in + r * k) + c);
+            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+        }
+        reinterpret_cast<float4*>(hi)[i] = h;
+        reinterpret_cast<float4*>(lo)[i] = l;
+    }
+}
+// B [batch][k][n] row-major -> hi/lo [batch][n][kpad] (transposed through a 32x33 smem tile)
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
+                       size_t batch, size_t k, size_t n, size_t kpad) {
+    __shared__ float tile[32][33];
+    const size_t tiles_n = (n + 31) / 32, tiles_k = kpad / 32;
+    const size_t per_batch = tiles_n * tiles_k;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (size_t t = blockIdx.x; t < per_batch * batch; t += gridDim.x) {
+        const size_t b = t / per_batch, r = t % per_batch;
+        const size_t tk = r / tiles_n, tn = r % tiles_n;
+        const float* src = in + b * k * n;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            const size_t kk = tk * 32 + ty + i, nn = tn * 32 + tx;
+            tile[ty + i][tx] = (kk < k && nn < n) ? ld_stream(src + kk * n + nn) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            const size_t nn = tn * 32 + ty + i, kk = tk * 32 + tx;
+            if (nn < n) {
+                float h, l;
+                split_tf32(tile[tx][ty + i], h, l);
+                const size_t o = (b * n + nn) * kpad + kk;
+                hi[o] = h;
+                lo[o] = l;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+// [batch][rows][kpad] f32, box = {BK, box_rows, 1}, SWIZZLE_128B
+static int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t dims[3] = {kpad, rows, batch};
+    cuuint64_t strides[2] = {kpad * sizeof(float), rows * kpad * sizeof(float)};
+    cuuint32_t box[3] = {BK, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return TRN_OK;
+}
+
+template <int TERMS>
+static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                  const Params& p, int sm_count, cudaStream_t s) {
+    using C = Cfg<TERMS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TRN_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        attr_set = true;
+    }
+    const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
+    const uint32_t grid = total < (uint32_t)sm_count ? total : (uint32_t)sm_count;
+    gemm_tf32_kernel<TERMS><<<grid, kThreads, C::kSmemBytes, s>>>(ah, al, bh, bl, p);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+}  // namespace tc
+
+bool gemm_tc_supported(size_t m, size_t k, size_t n) {
+    // 32-bit tile coordinates and TMA dimension limits; any m, n, k >= 1 otherwise
+    return m >= 1 && n >= 1 && k >= 1 && m < (1u << 30) && n < (1u << 30) && k < (1u << 30);
+}
+
+int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int terms,
+                   cudaStream_t s) {
+    using namespace tc;
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
+    if (batch == 0 || m == 0 || n == 0) return TRN_OK;
+    const size_t kpad = (k + BK - 1) / BK * BK;
+    const size_t a_elems = batch * m * kpad, b_elems = batch * n * kpad;
+
+    // scratch: A_hi, A_lo, Bt_hi, Bt_lo (stream-ordered pool; stays cached between calls)
+    float* scratch = nullptr;
+    TRN_TRY(scratch_alloc((void**)&scratch, (2 * a_elems + 2 * b_elems) * sizeof(float), s));
+    float* a_hi = scratch;
+    float* a_lo = a_hi + a_elems;
+    float* b_hi = a_lo + a_elems;
+    float* b_lo = b_hi + b_elems;
+
+    const unsigned cap = (unsigned)cx->sm_count * 8;
+    const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
+    if (vec) {
+        size_t work = batch * m * (kpad / 4);
+        size_t blocks = (work + 255) / 256;
+        split_rows_vec_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad);
+    } else {
+        size_t blocks = (a_elems + 255) / 256;
+        split_rows_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad);
+    }
+    {
+        size_t tiles = batch * ((n + 31) / 32) * (kpad / 32);
+        split_transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad);
+    }
+    count_launch(2);
+    TRN_CUDA(cudaGetLastError());
+
+    CUtensorMap map_ah, map_al, map_bh, map_bl;
+    TRN_TRY(make_map(&map_ah, a_hi, batch, m, kpad, BM));
+    TRN_TRY(make_map(&map_al, a_lo, batch, m, kpad, BM));
+    TRN_TRY(make_map(&map_bh, b_hi, batch, n, kpad, BN));
+    TRN_TRY(make_map(&map_bl, b_lo, batch, n, kpad, BN));
+
+    Params p;
+    p.c = c;
+    p.m = (uint32_t)m;
+    p.n = (uint32_t)n;
+    p.num_kb = (uint32_t)(kpad / BK);
+    p.tiles_m = (uint32_t)((m + BM - 1) / BM);
+    p.tiles_n = (uint32_t)((n + BN - 1) / BN);
+    p.batch = (uint32_t)batch;
+    int st = terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s)
+                        : launch<1>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s);
+    scratch_free(scratch, s);
+    return st;
+}
+
+}  // namespace trn

@@ -1,0 +1,293 @@
+// reduce.cu — single-launch, deterministic, HBM-streaming reductions for sm_100a.
+//
+// Replaces Avx2Backend::{dot,sum,max,min,argmax,argmin,norm_l2} (src/backends/avx2.rs:159-489)
+// with the SEMANTICS of the scalar backend (src/backends/scalar.rs:66-200) — see DESIGN.md for why
+// the AVX2 accumulation defects (single-accumulator sum, f32-lane indices) are not reproduced.
+//
+// Shape of every kernel:
+//   * persistent grid of (SMs x resident CTAs) blocks, 256 threads; each block walks 16 KiB
+//     (sum/arg) or 2x16 KiB (dot) tiles grid-strided, 4 independent 128-bit loads per thread per
+//     array per step (ld.global.nc.L1::no_allocate) so >= 64 KiB/SM is in flight;
+//   * per-thread accumulators -> warp shuffle tree -> shared-memory tree -> one partial per block;
+//   * the LAST block to finish (ticket counter, self-resetting) folds the per-block partials in a
+//     fixed order and writes the result.  No float atomics, fixed grid => bit-identical reruns
+//     (the reference pins run-to-run determinism: tests/falsification_tests.rs:415-500).
+//
+// Algorithmic bytes per element: sum/max/min/argmax/argmin/norm_l2 4 B, dot 8 B; HBM-bound.
+#include <cfloat>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace trn {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;                           // float4 loads in flight per thread per array
+constexpr int kTileVec = kThreads * kUnroll;         // float4 per tile (16 KiB)
+
+__device__ __forceinline__ bool last_block_done(unsigned* ticket) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *ticket = 0;  // self-reset for the next launch on this stream
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+__device__ __forceinline__ float block_sum(float v) {
+    __shared__ float s_w[kThreads / 32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < kThreads / 32 ? s_w[threadIdx.x] : 0.f;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;  // valid in warp 0
+}
+
+// ---- sum / dot / sum of squares ---------------------------------------------------------------------
+template <int OP>  // 0 sum, 1 dot, 2 sumsq
+__device__ __forceinline__ void accum4(float& acc, const float4& x, const float4& y) {
+    if (OP == 0) {
+        acc += (x.x + x.y) + (x.z + x.w);
+    } else if (OP == 1) {
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+        acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    } else {
+        acc = fmaf(x.x, x.x, acc); acc = fmaf(x.y, x.y, acc);
+        acc = fmaf(x.z, x.z, acc); acc = fmaf(x.w, x.w, acc);
+    }
+}
+template <int OP>
+__device__ __forceinline__ void accum1(float& acc, float x, float y) {
+    if (OP == 0) acc += x;
+    else if (OP == 1) acc = fmaf(x, y, acc);
+    else acc = fmaf(x, x, acc);
+}
+
+// VEC: pointers are 16-byte aligned -> 128-bit path over n/4 vectors, scalar tail by block 0.
+template <int OP, bool VEC, bool SQRT>
+__global__ void __launch_bounds__(kThreads)
+reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                  float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out) {
+    float acc[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) acc[u] = 0.f;
+
+    if (VEC) {
+        const size_t nvec = n >> 2;
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        const size_t full_tiles = nvec / kTileVec;
+        for (size_t t = blockIdx.x; t < full_tiles; t += gridDim.x) {
+            const size_t base = t * kTileVec + threadIdx.x;
+            float4 x[kUnroll], y[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(a4 + base + u * kThreads);
+            if (OP == 1) {
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) y[u] = ld_stream(b4 + base + u * kThreads);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) accum4<OP>(acc[u], x[u], OP == 1 ? y[u] : x[u]);
+        }
+        // ragged vector tail + scalar tail: spread over the grid, one element stride
+        const size_t tail0 = full_tiles * kTileVec;
+        for (size_t v = tail0 + (size_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += (size_t)gridDim.x * kThreads) {
+            float4 x = ld_stream(a4 + v);
+            float4 y = OP == 1 ? ld_stream(b4 + v) : x;
+            accum4<OP>(acc[0], x, y);
+        }
+        if (blockIdx.x == 0) {
+            size_t i = (nvec << 2) + threadIdx.x;
+            if (i < n) accum1<OP>(acc[1], a[i], OP == 1 ? b[i] : 0.f);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+            accum1<OP>(acc[0], ld_stream(a + i), OP == 1 ? ld_stream(b + i) : 0.f);
+    }
+
+    float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    v = block_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+
+    if (last_block_done(ticket)) {
+        // fixed-order fold of the per-block partials (gridDim.x <= kMaxReduceBlocks)
+        float r = 0.f;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) r += __ldcg(partial + i);
+        r = block_sum(r);
+        if (threadIdx.x == 0) *out = SQRT ? sqrtf(r) : r;
+    }
+}
+
+// ---- argmax / argmin (also serves max / min: value at the winning index) ------------------------------
+// Scalar-backend rule (src/backends/scalar.rs:112-166): seed with a[0], strict compare, first
+// occurrence.  A NaN element never wins; a NaN seed never loses.  Within a thread indices are
+// visited in increasing order, so a strict compare keeps the first occurrence; across threads the
+// combine prefers the better value, then the lower index.
+struct Best {
+    float v;
+    uint64_t i;
+};
+constexpr uint64_t kNoIndex = ~0ull;
+
+template <bool MAX>
+__device__ __forceinline__ bool better(float x, float v) { return MAX ? (x > v) : (x < v); }
+
+template <bool MAX>
+__device__ __forceinline__ Best combine(Best p, Best q) {
+    if (better<MAX>(q.v, p.v) || (q.v == p.v && q.i < p.i)) return q;
+    return p;
+}
+template <bool MAX>
+__device__ __forceinline__ Best warp_best(Best p) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best q;
+        q.v = __shfl_xor_sync(0xffffffffu, p.v, o);
+        q.i = __shfl_xor_sync(0xffffffffu, p.i, o);
+        p = combine<MAX>(p, q);
+    }
+    return p;
+}
+template <bool MAX>
+__device__ __forceinline__ Best block_best(Best p) {
+    __shared__ float s_v[kThreads / 32];
+    __shared__ uint64_t s_i[kThreads / 32];
+    p = warp_best<MAX>(p);
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = p.v; s_i[threadIdx.x >> 5] = p.i; }
+    __syncthreads();
+    Best r{MAX ? -INFINITY : INFINITY, kNoIndex};
+    if (threadIdx.x < 32) {
+        if (threadIdx.x < kThreads / 32) { r.v = s_v[threadIdx.x]; r.i = s_i[threadIdx.x]; }
+        r = warp_best<MAX>(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+template <bool MAX, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ partial_v,
+                 uint64_t* __restrict__ partial_i, unsigned* __restrict__ ticket,
+                 uint64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    Best best{MAX ? -INFINITY : INFINITY, kNoIndex};
+    auto visit = [&](float x, uint64_t i) { if (better<MAX>(x, best.v)) { best.v = x; best.i = i; } };
+
+    if (VEC) {
+        const size_t nvec = n >> 2;
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const size_t full_tiles = nvec / kTileVec;
+        for (size_t t = blockIdx.x; t < full_tiles; t += gridDim.x) {
+            const size_t base = t * kTileVec + threadIdx.x;
+            float4 x[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(a4 + base + u * kThreads);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint64_t e = (uint64_t)(base + u * kThreads) << 2;
+                visit(x[u].x, e); visit(x[u].y, e + 1); visit(x[u].z, e + 2); visit(x[u].w, e + 3);
+            }
+        }
+        const size_t tail0 = full_tiles * kTileVec;
+        for (size_t v = tail0 + (size_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += (size_t)gridDim.x * kThreads) {
+            float4 x = ld_stream(a4 + v);
+            const uint64_t e = (uint64_t)v << 2;
+            visit(x.x, e); visit(x.y, e + 1); visit(x.z, e + 2); visit(x.w, e + 3);
+        }
+        if (blockIdx.x == 0) {
+            size_t i = (nvec << 2) + threadIdx.x;
+            if (i < n) visit(a[i], i);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+            visit(ld_stream(a + i), i);
+    }
+
+    best = block_best<MAX>(best);
+    if (threadIdx.x == 0) { partial_v[blockIdx.x] = best.v; partial_i[blockIdx.x] = best.i; }
+
+    if (last_block_done(ticket)) {
+        Best r{MAX ? -INFINITY : INFINITY, kNoIndex};
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads)
+            r = combine<MAX>(r, Best{__ldcg(partial_v + i), __ldcg(partial_i + i)});
+        r = block_best<MAX>(r);
+        if (threadIdx.x == 0) {
+            const float seed = a[0];
+            // NaN seed never loses; and if nothing beat the identity, every element is the identity
+            // value or NaN, so nothing is strictly better than a[0] either: the answer is index 0.
+            if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
+            if (out_idx) *out_idx = r.i;
+            if (out_val) *out_val = r.v;
+        }
+    }
+}
+
+// ---- launchers ------------------------------------------------------------------------------------------
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int reduce_grid(size_t n, int sm_count) {
+    // enough blocks to cover the data once with 16 KiB tiles, capped at 8 resident CTAs per SM
+    size_t tiles = (n / 4 + kTileVec - 1) / kTileVec;
+    size_t cap = (size_t)sm_count * 8;
+    if (cap > (size_t)kMaxReduceBlocks) cap = kMaxReduceBlocks;
+    size_t g = tiles < cap ? tiles : cap;
+    return (int)(g ? g : 1);
+}
+
+int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    if (n == 0) {  // empty -> 0.0 (src/vector.rs:635, :2602-2604; dot of empty slices is 0)
+        TRN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+        return TRN_OK;
+    }
+    Workspace* w = workspace(s);
+    if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
+    const int grid = reduce_grid(n, c->sm_count);
+    const bool vec = aligned16(a) && (op != Reduce::Dot || aligned16(b));
+#define LAUNCH(OP, SQRT)                                                                                   \
+    do {                                                                                                   \
+        if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out); \
+        else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out); \
+    } while (0)
+    switch (op) {
+        case Reduce::Sum:    LAUNCH(0, false); break;
+        case Reduce::Dot:    LAUNCH(1, false); break;
+        case Reduce::SumSq:  LAUNCH(2, false); break;
+        case Reduce::NormL2: LAUNCH(2, true); break;
+    }
+#undef LAUNCH
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    Workspace* w = workspace(s);
+    if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
+    const int grid = reduce_grid(n, c->sm_count);
+    const bool vec = aligned16(a);
+    if (is_max) {
+        if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
+        else     argreduce_kernel<true, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
+    } else {
+        if (vec) argreduce_kernel<false, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
+        else     argreduce_kernel<false, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
+    }
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+}  // namespace trn
