@@ -37,7 +37,11 @@ def main():
     which = set(sys.argv[1:]) or {"reduce", "map", "softmax", "gemm", "batched", "matvec"}
     torch.cuda.set_device(0)
     trn.check(trn.lib.trn_cuda_init(0))
-    st = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: torch events and our launches must share it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
+    assert st != 0
     L = trn.lib
     print(trn.device_info(), "HBM peak (measured)", HBM)
 
@@ -48,11 +52,11 @@ def main():
         out = torch.zeros(4, device="cuda")
         oidx = torch.zeros(2, device="cuda", dtype=torch.int64)
         for name, fn, nbytes in [
-            ("sum", lambda: L.trn_sum_f32_dev(a.data_ptr(), n, out.data_ptr(), st), 4 * n),
-            ("dot", lambda: L.trn_dot_f32_dev(a.data_ptr(), n, b.data_ptr(), n, out.data_ptr(), st), 8 * n),
-            ("norm_l2", lambda: L.trn_norm_l2_f32_dev(a.data_ptr(), n, out.data_ptr(), st), 4 * n),
-            ("argmax", lambda: L.trn_argmax_f32_dev(a.data_ptr(), n, oidx.data_ptr(), out.data_ptr(), st), 4 * n),
-            ("max", lambda: L.trn_max_f32_dev(a.data_ptr(), n, out.data_ptr(), st), 4 * n),
+            ("sum", lambda: trn.check(L.trn_sum_f32_dev(a.data_ptr(), n, out.data_ptr(), st)), 4 * n),
+            ("dot", lambda: trn.check(L.trn_dot_f32_dev(a.data_ptr(), n, b.data_ptr(), n, out.data_ptr(), st)), 8 * n),
+            ("norm_l2", lambda: trn.check(L.trn_norm_l2_f32_dev(a.data_ptr(), n, out.data_ptr(), st)), 4 * n),
+            ("argmax", lambda: trn.check(L.trn_argmax_f32_dev(a.data_ptr(), n, oidx.data_ptr(), out.data_ptr(), st)), 4 * n),
+            ("max", lambda: trn.check(L.trn_max_f32_dev(a.data_ptr(), n, out.data_ptr(), st)), 4 * n),
             ("torch.sum (ref)", lambda: torch.sum(a), 4 * n),
         ]:
             med, best = timeit(fn)
@@ -66,10 +70,10 @@ def main():
         b = torch.randn(n, device="cuda")
         o = torch.empty(n, device="cuda")
         for name, fn, nbytes in [
-            ("add", lambda: L.trn_add_f32_dev(a.data_ptr(), n, b.data_ptr(), n, o.data_ptr(), st), 12 * n),
-            ("mul", lambda: L.trn_mul_f32_dev(a.data_ptr(), n, b.data_ptr(), n, o.data_ptr(), st), 12 * n),
-            ("sigmoid", lambda: L.trn_sigmoid_f32_dev(a.data_ptr(), n, o.data_ptr(), st), 8 * n),
-            ("gelu", lambda: L.trn_gelu_f32_dev(a.data_ptr(), n, o.data_ptr(), st), 8 * n),
+            ("add", lambda: trn.check(L.trn_add_f32_dev(a.data_ptr(), n, b.data_ptr(), n, o.data_ptr(), st)), 12 * n),
+            ("mul", lambda: trn.check(L.trn_mul_f32_dev(a.data_ptr(), n, b.data_ptr(), n, o.data_ptr(), st)), 12 * n),
+            ("sigmoid", lambda: trn.check(L.trn_sigmoid_f32_dev(a.data_ptr(), n, o.data_ptr(), st)), 8 * n),
+            ("gelu", lambda: trn.check(L.trn_gelu_f32_dev(a.data_ptr(), n, o.data_ptr(), st)), 8 * n),
             ("torch.add (ref)", lambda: torch.add(a, b, out=o), 12 * n),
         ]:
             med, best = timeit(fn)
@@ -83,8 +87,8 @@ def main():
         o = torch.empty_like(a)
         nbytes = 8 * rows * cols
         for name, fn in [
-            ("softmax", lambda: L.trn_softmax_rows_f32_dev(a.data_ptr(), o.data_ptr(), rows, cols, st)),
-            ("log_softmax", lambda: L.trn_log_softmax_rows_f32_dev(a.data_ptr(), o.data_ptr(), rows, cols, st)),
+            ("softmax", lambda: trn.check(L.trn_softmax_rows_f32_dev(a.data_ptr(), o.data_ptr(), rows, cols, st))),
+            ("log_softmax", lambda: trn.check(L.trn_log_softmax_rows_f32_dev(a.data_ptr(), o.data_ptr(), rows, cols, st))),
             ("torch.softmax (ref)", lambda: torch.softmax(a, dim=1, out=o)),
         ]:
             med, best = timeit(fn)
@@ -144,7 +148,7 @@ def main():
         a = torch.randn(rows, cols, device="cuda")
         v = torch.randn(cols, device="cuda")
         y = torch.empty(rows, device="cuda")
-        med, best = timeit(lambda: L.trn_matvec_f32_dev(a.data_ptr(), rows, cols, v.data_ptr(), cols, y.data_ptr(), st))
+        med, best = timeit(lambda: trn.check(L.trn_matvec_f32_dev(a.data_ptr(), rows, cols, v.data_ptr(), cols, y.data_ptr(), st)))
         print(f"matvec 16384^2 median {med:.3f} ms  {4.0 * rows * cols / med / 1e6:.0f} GB/s ({4.0 * rows * cols / med / 1e6 / HBM:.2%})")
     print("launches:", trn.launch_count())
 

@@ -84,8 +84,10 @@ int gemm_dispatch(const float* a, const float* b, float* c, size_t batch, size_t
             return fail(TRN_INVALID_INPUT, "tcgen05 GEMM engine forced for an unsupported shape %zux%zux%zu", m, k, n);
         return launch_gemm_tc(a, b, c, batch, m, k, n, engine == 2 ? 3 : 1, s);
     }
-    // auto: the tensor-core tile is 128x256; below ~1 tile of work per few SMs the SIMT kernel wins
-    if (gemm_tc_supported(m, k, n) && m >= 128 && n >= 128 && k >= 32 && batch * m * n * k >= (size_t)1 << 24)
+    // auto: the tensor-core tile is 128x256; below that the SIMT kernel wins.  The choice depends on
+    // (m, k, n) only — never on batch — so a batched product is bit-identical to the loop of single
+    // products the reference runs (src/matrix.rs:507-524).
+    if (gemm_tc_supported(m, k, n) && m >= 128 && n >= 128 && k >= 32 && m * n * k >= (size_t)1 << 24)
         return launch_gemm_tc(a, b, c, batch, m, k, n, 3, s);
     return launch_gemm_simt(a, b, c, batch, m, k, n, s);
 }

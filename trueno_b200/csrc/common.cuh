@@ -87,8 +87,9 @@ int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaS
 int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, float* y, cudaStream_t s);
 int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s);
 // C[b] = A[b] * B[b], b in [0,batch); strides in elements
+// only_if_flag != nullptr: the kernel returns immediately unless *only_if_flag != 0 (device-side fallback)
 int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
-                     cudaStream_t s);
+                     cudaStream_t s, const int* only_if_flag = nullptr);
 // tcgen05 path; terms = 3 (3xTF32, fp32-accurate) or 1 (plain TF32, probe only)
 int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
                    int terms, cudaStream_t s);

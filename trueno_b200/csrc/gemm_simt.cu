@@ -154,7 +154,9 @@ constexpr int BM = 128, BN = 128, BK = 16;
 
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
-                 size_t m, size_t k, size_t n, size_t tiles_m, size_t tiles_n) {
+                 size_t m, size_t k, size_t n, size_t tiles_m, size_t tiles_n, const int* __restrict__ only_if_flag) {
+    // fallback mode (gemm_tc.cu): run only when the pre-pass saw a non-finite input; grid-uniform exit
+    if (only_if_flag != nullptr && *only_if_flag == 0) return;
     __shared__ __align__(16) float sA[2][BK][BM + 4];  // k-major: sA[kk][i]
     __shared__ __align__(16) float sB[2][BK][BN + 4];  // sB[kk][j]
 
@@ -248,7 +250,7 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
 }
 
 int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
-                     cudaStream_t s) {
+                     cudaStream_t s, const int* only_if_flag) {
     Context* cx = ctx();
     if (!cx) return TRN_GPU_ERROR;
     if (batch == 0 || m == 0 || n == 0) return TRN_OK;
@@ -262,7 +264,7 @@ int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, siz
     for (size_t b0 = 0; b0 < batch; b0 += 65535) {  // gridDim.y limit
         size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
         dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)nb);
-        gemm_simt_kernel<<<grid, 256, 0, s>>>(a + b0 * m * k, b + b0 * k * n, c + b0 * m * n, m, k, n, tiles_m, tiles_n);
+        gemm_simt_kernel<<<grid, 256, 0, s>>>(a + b0 * m * k, b + b0 * k * n, c + b0 * m * n, m, k, n, tiles_m, tiles_n, only_if_flag);
         count_launch();
     }
     TRN_CUDA(cudaGetLastError());

@@ -9,7 +9,20 @@
 //   hi = tf32_round(x),  lo = tf32_round(x - hi)        (x - hi is exact in f32)
 // and the product is accumulated as  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  in an f32 TMEM
 // accumulator — three kind::tf32 MMAs per logical product.  The dropped lo*lo term is <= 2^-22
-// relative per product.  Non-finite inputs keep hi = x, lo = 0 so Inf/NaN propagate as IEEE.
+// relative per product.
+//
+// Two-level accumulation: the tensor core adds into its f32 accumulator with truncation, which
+// is a BIASED rounding — measured on B200 the relative error of an all-positive product grows
+// linearly with K (2.5e-5 at K=2048, 9.3e-5 at K=8192) when a whole tile is accumulated in TMEM.
+// So TMEM only ever holds a partial sum over kChunkKB k-blocks (K = 128): the MMA warp alternates
+// between the two accumulator stages, and the epilogue warps drain each finished partial into f32
+// REGISTER accumulators with round-to-nearest adds while the next partial is being computed.  The
+// bias is then bounded by the chunk length (48 accumulate steps, ~1.5e-6 relative) instead of K.
+//
+// Non-finite inputs: hi*lo would manufacture Inf*0 = NaN where IEEE gives Inf, so the split
+// pre-pass raises a device flag when it meets an Inf/NaN; the tensor-core kernel then exits at
+// once and the SIMT FFMA kernel (exact IEEE semantics) computes the product instead.  Both
+// kernels are always enqueued, the flag is read on the device: no host round trip.
 // The same pre-pass re-lays B (k x n, row-major) out K-major (n x k), so both operands use the
 // canonical K-major SWIZZLE_128B shared-memory layout, and pads K to a multiple of 32 with
 // zeros so the main loop has no remainder and TMA strides are 16-byte aligned.
@@ -18,8 +31,8 @@
 //   warp 0 : TMA producer   (cp.async.bulk.tensor.3d -> smem ring, mbarrier complete_tx)
 //   warp 1 : MMA issuer     (one elected lane; tcgen05.mma.cta_group::1.kind::tf32, 128x256x8),
 //            also owns the TMEM allocation (512 columns = two 128x256 f32 accumulators)
-//   warps 2-5 : epilogue    (tcgen05.ld 32x32b -> registers -> global), overlapped with the next
-//            tile's main loop through the two accumulator stages.
+//   warps 2-9 : epilogue    (tcgen05.ld 32x32b -> f32 register accumulators -> global); warp w owns
+//            TMEM lane quadrant w%4 and column half (w-2)/4 of the 128x256 tile.
 // Accumulation order is fixed (k ascending, no split-K, no atomics) => bit-identical reruns
 // (tests/wasm_optimization_tests.rs:200-230).
 //
@@ -35,7 +48,9 @@ constexpr int BM = 128;   // UMMA M (cta_group::1)
 constexpr int BN = 256;   // UMMA N
 constexpr int BK = 32;    // floats per stage row = 128 bytes = one SWIZZLE_128B span
 constexpr int UMMA_K = 8; // kind::tf32: 32 bytes of K per instruction
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kChunkKB = 4;  // k-blocks (of 32) accumulated in TMEM before draining to registers
 constexpr uint32_t kABytes = BM * BK * 4;  // 16 KiB
 constexpr uint32_t kBBytes = BN * BK * 4;  // 32 KiB
 constexpr uint32_t kTmemCols = 512;        // 2 accumulator stages x 256 columns
@@ -143,6 +158,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 
 struct Params {
     float* c;
+    const int* nonfinite_flag;  // set by the split pre-pass; non-zero => this kernel must not run
     uint32_t m, n;            // C rows / cols per batch
     uint32_t num_kb;          // Kpad / BK
     uint32_t tiles_m, tiles_n, batch;
@@ -169,6 +185,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const Params p) {
     using C = Cfg<TERMS>;
+    if (*p.nonfinite_flag != 0) return;  // Inf/NaN in the inputs: the SIMT kernel takes over (grid-uniform)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -191,7 +208,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         tma_prefetch_desc(&map_b_hi);
         if (TERMS == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
         for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -228,12 +245,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t d = tmem_base + acc * BN;
             for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                const uint32_t in_chunk = kb % kChunkKB;
+                if (in_chunk == 0) {
+                    mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+                    tc_fence_after();
+                }
+                const uint32_t d = tmem_base + acc * BN;
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
+                const bool chunk_end = in_chunk == kChunkKB - 1 || kb == p.num_kb - 1;
                 if (elect_one()) {
                     const uint32_t sa = smem_base + stage * C::kStageBytes;
                     const uint32_t a_hi = sa, b_hi = sa + kABytes;
@@ -241,60 +262,72 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint32_t koff = k * UMMA_K * 4;  // 32 bytes along K inside the swizzle span
-                        const uint32_t first = (kb | (uint32_t)k) != 0;
+                        const uint32_t accum = (in_chunk | (uint32_t)k) != 0;  // first MMA of a chunk overwrites
                         if (TERMS == 3) {
-                            umma_tf32(d, make_desc_k_sw128(a_lo + koff), make_desc_k_sw128(b_hi + koff), idesc, first);
+                            umma_tf32(d, make_desc_k_sw128(a_lo + koff), make_desc_k_sw128(b_hi + koff), idesc, accum);
                             umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_lo + koff), idesc, 1u);
                             umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_hi + koff), idesc, 1u);
                         } else {
-                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_hi + koff), idesc, first);
+                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_hi + koff), idesc, accum);
                         }
                     }
-                    umma_commit(empty_bar(stage));                       // smem slot free once these MMAs retire
-                    if (kb == p.num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete
+                    umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                    if (chunk_end) umma_commit(tmem_full_bar(acc));  // partial sum complete
                 }
                 __syncwarp();
                 if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                if (chunk_end && ++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const uint32_t quad = warp & 3;  // TMEM lane quadrant this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may access
+        const uint32_t half = (warp - 2) >> 2;   // which 128 of the 256 accumulator columns
+        const uint32_t num_chunks = (p.num_kb + kChunkKB - 1) / kChunkKB;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             uint32_t b, mt, nt;
             tile_coords(t, p, b, mt, nt);
-            mbar_wait(tmem_full_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t row = mt * BM + quad * 32 + lane;
-            float* crow = p.c + ((size_t)b * p.m + row) * p.n + (size_t)nt * BN;
-            const bool row_ok = row < p.m;
-            const bool vec_ok = (p.n % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15u) == 0;  // 16-byte aligned rows
-#pragma unroll 1
-            for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + acc * BN + chunk * 32, r);
-                tmem_ld_wait();
-                const uint32_t col0 = nt * BN + chunk * 32;
-                if (row_ok && col0 < p.n) {
-                    if (vec_ok && col0 + 32 <= p.n) {
+            float sum[128];  // this thread's row, 128 consecutive columns: the second accumulation level
+            for (uint32_t ch = 0; ch < num_chunks; ++ch) {
+                mbar_wait(tmem_full_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * BN + half * 128;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(crow + chunk * 32 + 4 * j) =
-                                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + j * 32, r);
+                    tmem_ld_wait();
+                    if (ch == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __uint_as_float(r[i]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.n) crow[chunk * 32 + j] = __uint_as_float(r[j]);
+                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __fadd_rn(sum[j * 32 + i], __uint_as_float(r[i]));
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            // ---- store this thread's 128 columns
+            const uint32_t row = mt * BM + quad * 32 + lane;
+            const uint32_t col_base = nt * BN + half * 128;
+            if (row < p.m && col_base < p.n) {
+                float* crow = p.c + ((size_t)b * p.m + row) * p.n + col_base;
+                const bool vec_ok = (p.n % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15u) == 0;
+                if (vec_ok && col_base + 128 <= p.n) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        *reinterpret_cast<float4*>(crow + 4 * j) =
+                            make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 128; ++j)
+                        if (col_base + j < p.n) crow[j] = sum[j];
+                }
+            }
         }
     }
 
@@ -307,8 +340,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 }
 
 // ---- operand pre-pass: split into tf32 hi/lo, pad K, lay B out K-major ------------------------------
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    if (!isfinite(x)) { hi = x; lo = 0.f; return; }     // Inf/NaN propagate through hi alone
+// returns true when x is Inf/NaN (the caller raises the fallback flag)
+__device__ __forceinline__ bool split_tf32(float x, float& hi, float& lo) {
+    if (!isfinite(x)) { hi = x; lo = 0.f; return true; }
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
     float fh = __uint_as_float(h);
@@ -318,43 +352,50 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
     hi = fh;
     lo = __uint_as_float(l);
+    return false;
 }
 
 // rows x k (row-major, per batch) -> hi/lo [rows x kpad]
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
-                  size_t rows_total, size_t k, size_t kpad) {
+                  size_t rows_total, size_t k, size_t kpad, int* __restrict__ flag) {
     const size_t total = rows_total * kpad;
+    bool bad = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / kpad, c = i - r * kpad;
         float h = 0.f, l = 0.f;
-        if (c < k) split_tf32(ld_stream(in + r * k + c), h, l);
+        if (c < k) bad |= split_tf32(ld_stream(in + r * k + c), h, l);
         hi[i] = h;
         lo[i] = l;
     }
+    if (bad) *flag = 1;
 }
 // 4-wide variant for k % 4 == 0 (kpad is always a multiple of 32)
 __global__ void __launch_bounds__(256)
 split_rows_vec_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
-                      size_t rows_total, size_t k, size_t kpad) {
+                      size_t rows_total, size_t k, size_t kpad, int* __restrict__ flag) {
     const size_t kv = k >> 2, kpv = kpad >> 2;
     const size_t total = rows_total * kpv;
+    bool bad = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / kpv, c = i - r * kpv;
         float4 h = make_float4(0, 0, 0, 0), l = h;
         if (c < kv) {
             const float4 x = ld_stream(reinterpret_cast<const float4*>(in + r * k) + c);
-            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+            bad |= split_tf32(x.x, h.x, l.x); bad |= split_tf32(x.y, h.y, l.y);
+            bad |= split_tf32(x.z, h.z, l.z); bad |= split_tf32(x.w, h.w, l.w);
         }
         reinterpret_cast<float4*>(hi)[i] = h;
         reinterpret_cast<float4*>(lo)[i] = l;
     }
+    if (bad) *flag = 1;
 }
 // B [batch][k][n] row-major -> hi/lo [batch][n][kpad] (transposed through a 32x33 smem tile)
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
-                       size_t batch, size_t k, size_t n, size_t kpad) {
+                       size_t batch, size_t k, size_t n, size_t kpad, int* __restrict__ flag) {
     __shared__ float tile[32][33];
+    bool bad = false;
     const size_t tiles_n = (n + 31) / 32, tiles_k = kpad / 32;
     const size_t per_batch = tiles_n * tiles_k;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -373,7 +414,7 @@ split_transpose_kernel(const float* __restrict__ in, float* __restrict__ hi, flo
             const size_t nn = tn * 32 + ty + i, kk = tk * 32 + tx;
             if (nn < n) {
                 float h, l;
-                split_tf32(tile[tx][ty + i], h, l);
+                bad |= split_tf32(tile[tx][ty + i], h, l);
                 const size_t o = (b * n + nn) * kpad + kk;
                 hi[o] = h;
                 lo[o] = l;
@@ -381,6 +422,7 @@ split_transpose_kernel(const float* __restrict__ in, float* __restrict__ hi, flo
         }
         __syncthreads();
     }
+    if (bad) *flag = 1;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -450,25 +492,27 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
 
     // scratch: A_hi, A_lo, Bt_hi, Bt_lo (stream-ordered pool; stays cached between calls)
     float* scratch = nullptr;
-    TRN_TRY(scratch_alloc((void**)&scratch, (2 * a_elems + 2 * b_elems) * sizeof(float), s));
+    TRN_TRY(scratch_alloc((void**)&scratch, (2 * a_elems + 2 * b_elems) * sizeof(float) + 256, s));
     float* a_hi = scratch;
     float* a_lo = a_hi + a_elems;
     float* b_hi = a_lo + a_elems;
     float* b_lo = b_hi + b_elems;
+    int* flag = reinterpret_cast<int*>(b_lo + b_elems);   // non-finite-input flag (see header)
+    TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
 
     const unsigned cap = (unsigned)cx->sm_count * 8;
     const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
     if (vec) {
         size_t work = batch * m * (kpad / 4);
         size_t blocks = (work + 255) / 256;
-        split_rows_vec_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad);
+        split_rows_vec_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
     } else {
         size_t blocks = (a_elems + 255) / 256;
-        split_rows_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad);
+        split_rows_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
     }
     {
         size_t tiles = batch * ((n + 31) / 32) * (kpad / 32);
-        split_transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad);
+        split_transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad, flag);
     }
     count_launch(2);
     TRN_CUDA(cudaGetLastError());
@@ -481,6 +525,7 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
 
     Params p;
     p.c = c;
+    p.nonfinite_flag = flag;
     p.m = (uint32_t)m;
     p.n = (uint32_t)n;
     p.num_kb = (uint32_t)(kpad / BK);
@@ -489,6 +534,8 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     p.batch = (uint32_t)batch;
     int st = terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s)
                         : launch<1>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s);
+    // IEEE fallback for Inf/NaN inputs: runs only when the flag is set (checked on the device)
+    if (st == TRN_OK) st = launch_gemm_simt(a, b, c, batch, m, k, n, s, flag);
     scratch_free(scratch, s);
     return st;
 }

@@ -139,8 +139,14 @@ softmax_rows_generic_kernel(const float* __restrict__ in, float* __restrict__ ou
         float m = -INFINITY;
         for (size_t i = threadIdx.x; i < cols; i += kThreads) m = fmaxf(m, src[i]);
         m = block_max_256(m, s_w);
-        float part = 0.f;
-        for (size_t i = threadIdx.x; i < cols; i += kThreads) part += expf(src[i] - m);
+        // long per-thread chains: compensated (Kahan) summation keeps the row sum within ~1 ulp
+        float part = 0.f, comp = 0.f;
+        for (size_t i = threadIdx.x; i < cols; i += kThreads) {
+            const float y = __fsub_rn(expf(src[i] - m), comp);
+            const float t = __fadd_rn(part, y);
+            comp = __fsub_rn(__fsub_rn(t, part), y);
+            part = t;
+        }
         const float sum = block_sum_256(part, s_w);
         const float lse = LOG ? logf(sum) : 0.f;
         for (size_t i = threadIdx.x; i < cols; i += kThreads)
