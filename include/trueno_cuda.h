@@ -157,6 +157,11 @@ TRN_API int trn_max_f32_dev(const float* a, size_t n, float* out, void* stream);
 TRN_API int trn_min_f32_dev(const float* a, size_t n, float* out, void* stream);
 TRN_API int trn_argmax_f32_dev(const float* a, size_t n, uint64_t* out, float* out_value, void* stream);
 TRN_API int trn_argmin_f32_dev(const float* a, size_t n, uint64_t* out, float* out_value, void* stream);
+/* One contiguous slice of a vector sharded across GPUs (trueno_b200/parallel.py).  first_slice != 0:
+ * the slice starts at global index 0 and carries the a[0] seed rule; otherwise the slice has no seed
+ * and reports "no candidate" (all elements NaN or the identity) as index UINT64_MAX. */
+TRN_API int trn_argmax_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t* out, float* out_value, void* stream);
+TRN_API int trn_argmin_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t* out, float* out_value, void* stream);
 TRN_API int trn_norm_l2_f32_dev(const float* a, size_t n, float* out, void* stream);
 /* sum of squares without the sqrt: the per-slice partial of a sharded norm_l2 (allreduce, then sqrt) */
 TRN_API int trn_sumsq_f32_dev(const float* a, size_t n, float* out, void* stream);
@@ -183,6 +188,13 @@ TRN_API int trn_transpose_f32_dev(const float* a, size_t rows, size_t cols, floa
  * 2 = tcgen05 3xTF32, 3 = tcgen05 1xTF32 (peak probe only; NOT fp32-accurate, never auto-selected). */
 TRN_API int trn_set_gemm_engine(int engine);
 TRN_API int trn_get_gemm_engine(void);
+
+/* ---- live kernel timing (bench.py's roofline leg) -------------------------------------------
+ * When enabled, the GEMM launcher brackets its operand pre-pass and its main tensor-core kernel
+ * with CUDA events on the launching stream.  trn_profile_last_gemm() synchronises on those events
+ * and returns the two durations of the most recent GEMM call (milliseconds).  Off by default. */
+TRN_API int trn_profile_enable(int on);
+TRN_API int trn_profile_last_gemm(float* prepass_ms, float* kernel_ms);
 
 #ifdef __cplusplus
 }

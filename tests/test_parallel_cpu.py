@@ -1,0 +1,131 @@
+"""Host-side logic of the multi-GPU layer (trueno_b200/parallel.py) on CPU: the partitioner and
+the cross-slice exchange steps over a world_size-2 (and 3) gloo group.  Per-slice partials are
+produced here by the ORACLE (it stands in for the slice kernels, whose own parity is covered by
+the -m gpu tests); what is under test is the combine rule and the collectives."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+f32 = np.float32
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_range_partitions_exactly():
+    from trueno_b200.parallel import shard_range
+    for total in (0, 1, 5, 255, 256, 1000, 1 << 20, (1 << 30)):
+        for world in (1, 2, 3, 4, 8):
+            for align in (1, 4):
+                shards = [shard_range(total, r, world, align) for r in range(world)]
+                assert shards[0].start == 0 and sum(s.count for s in shards) == total
+                for a, b in zip(shards, shards[1:]):
+                    assert a.start + a.count == b.start
+                    assert b.start % align == 0 or b.count == 0
+                assert max(s.count for s in shards) - min(s.count for s in shards) < 2 * align
+    # BASELINE config 4: 2^30 over 8 GPUs -> 2^27 each; config 3: 256 heads -> 32 each
+    assert [shard_range(1 << 30, r, 8, 4).count for r in range(8)] == [1 << 27] * 8
+    assert [shard_range(256, r, 8).count for r in range(8)] == [32] * 8
+
+
+def _slice_partial(orc, a, start, is_max):
+    """What trn_arg{max,min}_slice_f32_dev reports for one slice (see reduce.cu / parallel.py)."""
+    from oracle import SCALAR
+    from trueno_b200.parallel import NO_CANDIDATE
+    ident = -np.inf if is_max else np.inf
+    if start == 0:
+        i = orc.argmax(a, backend=SCALAR) if is_max else orc.argmin(a, backend=SCALAR)
+        return f32(a[i]), i
+    ok = ~np.isnan(a) & (a != ident)
+    if not ok.any():
+        return f32(ident), NO_CANDIDATE
+    v = a[ok].max() if is_max else a[ok].min()
+    return f32(v), start + int(np.flatnonzero(a == v)[0])
+
+
+def _worker(rank, world, port, cases, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import oracle
+    from trueno_b200 import parallel as par
+    r, _, w = par.init_distributed("gloo")
+    assert (r, w) == (rank, world) and par.world_size() == world
+    orc = oracle.get()
+    out = []
+    for a, b in cases:
+        sh = par.shard_range(a.size, rank, world, align=4)
+        la, lb = a[sh.start:sh.start + sh.count], b[sh.start:sh.start + sh.count]
+        # sum-type partials -> all_reduce(SUM)
+        dot = par.combine_sum(torch.tensor([float(orc.dot(la, lb)) if sh.count else 0.0], dtype=torch.float32))
+        ssq = par.combine_sum(torch.tensor([float(orc.dot(la, la)) if sh.count else 0.0], dtype=torch.float32)).sqrt()
+        mx = par.combine_extreme(torch.tensor([la.max() if sh.count else -np.inf], dtype=torch.float32), True)
+        res = [float(dot), float(ssq), float(mx)]
+        for is_max in (True, False):
+            if sh.count:
+                v, i = _slice_partial(orc, la, sh.start, is_max)
+            else:
+                v, i = f32(-np.inf if is_max else np.inf), par.NO_CANDIDATE
+            gv, gi = par.combine_arg(torch.tensor([v], dtype=torch.float32), torch.tensor([i], dtype=torch.int64), is_max)
+            res += [float(gv), int(gi)]
+        out.append(res)
+    if rank == 0:
+        results.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _cases():
+    rng = np.random.default_rng(42)
+    cases = []
+    for n in (8, 9, 1000, 4097):
+        a = rng.integers(-3, 4, n).astype(f32)          # heavy ties across slices
+        cases.append((a, rng.standard_normal(n).astype(f32)))
+    a = rng.standard_normal(64).astype(f32); a[0] = np.nan                       # NaN seed: index 0 wins
+    cases.append((a, np.ones(64, f32)))
+    a = rng.standard_normal(64).astype(f32); a[32] = np.nan; a[40] = 9; a[50] = 9  # NaN heads slice 1, max behind it
+    cases.append((a, np.ones(64, f32)))
+    a = np.full(64, -np.inf, f32); a[33:40] = np.nan                              # nothing beats the identity -> 0
+    cases.append((a, np.ones(64, f32)))
+    a = np.zeros(64, f32); a[5] = 7; a[37] = 7                                    # equal maxima in two slices
+    cases.append((a, np.ones(64, f32)))
+    return cases
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_steps_over_gloo(world):
+    import oracle
+    from oracle import SCALAR
+    orc = oracle.get()
+    cases = _cases()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for (a, b), res in zip(cases, got):
+        dot, nrm, mx, vmax, imax, vmin, imin = res
+        tdot, adot = orc.f64_dot(a, b)
+        if np.isfinite(tdot):
+            assert abs(dot - tdot) <= 1e-5 * adot + 1e-30
+        with np.errstate(invalid="ignore"):
+            tn = np.sqrt(np.sum(a.astype(np.float64) ** 2))
+        if np.isfinite(tn):
+            assert abs(nrm - tn) <= 1e-5 * tn + 1e-30
+        assert imax == orc.argmax(a, backend=SCALAR), (a, imax)
+        assert imin == orc.argmin(a, backend=SCALAR), (a, imin)
+        wmax, wmin = orc.max(a, backend=SCALAR), orc.min(a, backend=SCALAR)
+        assert (np.isnan(vmax) and np.isnan(wmax)) or vmax == wmax
+        assert (np.isnan(vmin) and np.isnan(wmin)) or vmin == wmin

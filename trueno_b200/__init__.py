@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libtrueno_cuda.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} is missing: build it with `python -m trueno_b200.build` (nvcc, sm_100a). "
+        f"{LIB_PATH} is missing: build it with `python trueno_b200/build.py` (nvcc, sm_100a). "
         "trueno_b200 has no CPU or PyTorch fallback."
     )
 
@@ -59,6 +59,8 @@ _SIGNATURES = {
     "trn_dot_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp], "trn_sum_f32_dev": [_vp, _sz, _vp, _vp],
     "trn_max_f32_dev": [_vp, _sz, _vp, _vp], "trn_min_f32_dev": [_vp, _sz, _vp, _vp],
     "trn_argmax_f32_dev": [_vp, _sz, _vp, _vp, _vp], "trn_argmin_f32_dev": [_vp, _sz, _vp, _vp, _vp],
+    "trn_argmax_slice_f32_dev": [_vp, _sz, C.c_int, _vp, _vp, _vp],
+    "trn_argmin_slice_f32_dev": [_vp, _sz, C.c_int, _vp, _vp, _vp],
     "trn_norm_l2_f32_dev": [_vp, _sz, _vp, _vp], "trn_sumsq_f32_dev": [_vp, _sz, _vp, _vp],
     "trn_add_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp], "trn_mul_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp],
     "trn_sigmoid_f32_dev": [_vp, _sz, _vp, _vp], "trn_gelu_f32_dev": [_vp, _sz, _vp, _vp],
@@ -69,6 +71,7 @@ _SIGNATURES = {
     "trn_matvec_f32_dev": [_vp, _sz, _sz, _vp, _sz, _vp, _vp],
     "trn_transpose_f32_dev": [_vp, _sz, _sz, _vp, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
+    "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }
 _RESTYPES = {"trn_last_error": _sz, "trn_last_mismatch": None, "trn_launch_count": C.c_uint64,
              "trn_buf_len": _sz, "trn_buf_ptr": _vp}

@@ -1,7 +1,8 @@
 """Builds trueno_b200/libtrueno_cuda.so (the C-ABI library) with nvcc for sm_100a only.
 
 In-tree build so the .so travels to the GPU box with the repo snapshot.  nvcc cross-compiles
-without a GPU.  Usage: python -m trueno_b200.build [--force] [--verbose]
+without a GPU.  Usage: python trueno_b200/build.py [--force] [--verbose]   (run as a script: importing the package
+first would need the library this script is about to build)
 """
 from __future__ import annotations
 

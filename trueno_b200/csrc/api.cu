@@ -199,6 +199,18 @@ int trn_argmin_f32_dev(const float* a, size_t n, uint64_t* out, float* out_value
     TRN_TRY(need_ctx());
     return launch_argreduce(0, a, n, out, out_value, resolve_stream(stream));
 }
+// Slice variants for sharded vectors: first_slice != 0 applies the a[0] seed rule,
+// interior slices report "no candidate" as index UINT64_MAX / value = identity (-inf / +inf).
+int trn_argmax_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t* out, float* out_value, void* stream) {
+    TRN_TRY(check_nonempty_invalid(n));
+    TRN_TRY(need_ctx());
+    return launch_argreduce(1, a, n, out, out_value, resolve_stream(stream), first_slice != 0);
+}
+int trn_argmin_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t* out, float* out_value, void* stream) {
+    TRN_TRY(check_nonempty_invalid(n));
+    TRN_TRY(need_ctx());
+    return launch_argreduce(0, a, n, out, out_value, resolve_stream(stream), first_slice != 0);
+}
 int trn_add_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream) {
     TRN_TRY(check_same_len(na, nb));
     TRN_TRY(need_ctx());

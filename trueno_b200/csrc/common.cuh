@@ -75,8 +75,10 @@ int download(float* dst_host, const float* src_dev, size_t n, cudaStream_t s);
 // ---------------------------------------------------------------------------------------------
 enum class Reduce { Sum, Dot, SumSq, NormL2 };
 int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s);
-// is_max: 1 argmax / 0 argmin.  out_idx / out_val may be null.
-int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s);
+// is_max: 1 argmax / 0 argmin.  out_idx / out_val may be null.  seed_rule 0: interior slice of a
+// sharded vector (no a[0] seed; "no candidate" -> index ~0).
+int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s,
+                     int seed_rule = 1);
 
 enum class Map { Add, Mul, Sigmoid, Gelu };
 int launch_map(Map op, const float* a, const float* b, float* out, size_t n, cudaStream_t s);

@@ -476,6 +476,11 @@ static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMa
 
 }  // namespace tc
 
+// ---- optional live timing of the pre-pass and the main kernel (trn_profile_*) -------------------------
+static bool g_profile = false;
+static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+static bool g_ev_valid = false;
+
 bool gemm_tc_supported(size_t m, size_t k, size_t n) {
     // 32-bit tile coordinates and TMA dimension limits; any m, n, k >= 1 otherwise
     return m >= 1 && n >= 1 && k >= 1 && m < (1u << 30) && n < (1u << 30) && k < (1u << 30);
@@ -500,6 +505,10 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     int* flag = reinterpret_cast<int*>(b_lo + b_elems);   // non-finite-input flag (see header)
     TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
 
+    if (g_profile) {
+        if (!g_ev[0]) for (auto& e : g_ev) TRN_CUDA(cudaEventCreate(&e));
+        TRN_CUDA(cudaEventRecord(g_ev[0], s));
+    }
     const unsigned cap = (unsigned)cx->sm_count * 8;
     const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
     if (vec) {
@@ -532,8 +541,13 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     p.tiles_m = (uint32_t)((m + BM - 1) / BM);
     p.tiles_n = (uint32_t)((n + BN - 1) / BN);
     p.batch = (uint32_t)batch;
+    if (g_profile) TRN_CUDA(cudaEventRecord(g_ev[1], s));
     int st = terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s)
                         : launch<1>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s);
+    if (g_profile) {
+        TRN_CUDA(cudaEventRecord(g_ev[2], s));
+        g_ev_valid = true;
+    }
     // IEEE fallback for Inf/NaN inputs: runs only when the flag is set (checked on the device)
     if (st == TRN_OK) st = launch_gemm_simt(a, b, c, batch, m, k, n, s, flag);
     scratch_free(scratch, s);
@@ -541,3 +555,21 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
 }
 
 }  // namespace trn
+
+extern "C" {
+int trn_profile_enable(int on) {
+    trn::g_profile = on != 0;
+    return TRN_OK;
+}
+int trn_profile_last_gemm(float* prepass_ms, float* kernel_ms) {
+    using namespace trn;
+    if (!g_ev_valid) return fail(TRN_INVALID_INPUT, "no profiled GEMM call has been made");
+    TRN_CUDA(cudaEventSynchronize(g_ev[2]));
+    float a = 0.f, b = 0.f;
+    TRN_CUDA(cudaEventElapsedTime(&a, g_ev[0], g_ev[1]));
+    TRN_CUDA(cudaEventElapsedTime(&b, g_ev[1], g_ev[2]));
+    if (prepass_ms) *prepass_ms = a;
+    if (kernel_ms) *kernel_ms = b;
+    return TRN_OK;
+}
+}

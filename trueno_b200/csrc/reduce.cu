@@ -178,7 +178,7 @@ template <bool MAX, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ partial_v,
                  uint64_t* __restrict__ partial_i, unsigned* __restrict__ ticket,
-                 uint64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+                 uint64_t* __restrict__ out_idx, float* __restrict__ out_val, int seed_rule) {
     Best best{MAX ? -INFINITY : INFINITY, kNoIndex};
     auto visit = [&](float x, uint64_t i) { if (better<MAX>(x, best.v)) { best.v = x; best.i = i; } };
 
@@ -221,10 +221,15 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             r = combine<MAX>(r, Best{__ldcg(partial_v + i), __ldcg(partial_i + i)});
         r = block_best<MAX>(r);
         if (threadIdx.x == 0) {
-            const float seed = a[0];
-            // NaN seed never loses; and if nothing beat the identity, every element is the identity
+            // seed_rule == 1: this is a whole Vector (or its first slice) and a[0] seeds the scan.
+            // A NaN seed never loses; and if nothing beat the identity, every element is the identity
             // value or NaN, so nothing is strictly better than a[0] either: the answer is index 0.
-            if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
+            // seed_rule == 0: an interior slice of a sharded vector — no seed; "no candidate" is
+            // reported as index ~0 so the cross-slice combine can skip it (trueno_b200/parallel.py).
+            if (seed_rule) {
+                const float seed = a[0];
+                if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
+            }
             if (out_idx) *out_idx = r.i;
             if (out_val) *out_val = r.v;
         }
@@ -271,7 +276,8 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
     return TRN_OK;
 }
 
-int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s) {
+int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s,
+                     int seed_rule) {
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
     Workspace* w = workspace(s);
@@ -279,11 +285,11 @@ int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, fl
     const int grid = reduce_grid(n, c->sm_count);
     const bool vec = aligned16(a);
     if (is_max) {
-        if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
-        else     argreduce_kernel<true, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
+        if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
+        else     argreduce_kernel<true, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
     } else {
-        if (vec) argreduce_kernel<false, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
-        else     argreduce_kernel<false, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val);
+        if (vec) argreduce_kernel<false, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
+        else     argreduce_kernel<false, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
     }
     count_launch();
     TRN_CUDA(cudaGetLastError());

@@ -1,0 +1,182 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed (NCCL over
+NVLink 5 / NVSwitch) for the plumbing, the C-ABI kernels for the work.
+
+The reference has no multi-GPU code at all; this module implements SURVEY.md §8e:
+
+  op                                   partitioning                         exchange step
+  -----------------------------------  -----------------------------------  ---------------------------------
+  dot / sum / norm_l2                  contiguous slices of the vector      all_reduce(SUM) of one f32 partial
+  min / max                            contiguous slices                    all_reduce(MIN/MAX) of one f32
+  argmin / argmax                      contiguous slices, global u64 index  all_gather of (value, index) pairs,
+                                                                            best value then LOWEST index wins
+  softmax / log_softmax rows, maps     row / slice blocks                   none
+  batched_matmul_4d                    contiguous ranges of batch*head      none
+  matmul (large)                       C / A row blocks, B replicated       none
+
+Partials are produced by the `_dev` kernels on the CURRENT torch stream and the collective is
+enqueued on the same stream right behind them (no host synchronisation in between).  Tensors are
+torch CUDA tensors used purely as device memory.  The combine functions accept CPU tensors too,
+which is how the world_size-2 gloo tests exercise the exchange logic without a GPU; nothing here
+ever computes a hot-path op on the CPU.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class Shard:
+    """Contiguous share [start, start + count) of `total` units owned by `rank` of `world`."""
+    start: int
+    count: int
+    total: int
+    rank: int
+    world: int
+
+
+def shard_range(total: int, rank: int, world: int, align: int = 1) -> Shard:
+    """Even contiguous partition; every shard start is a multiple of `align` (128-bit loads want
+    align=4 for f32 slices).  The first `rem` ranks get one extra aligned block."""
+    blocks = (total + align - 1) // align
+    base, rem = divmod(blocks, world)
+    b0 = rank * base + min(rank, rem)
+    nb = base + (1 if rank < rem else 0)
+    start = min(b0 * align, total)
+    end = min((b0 + nb) * align, total)
+    return Shard(start, end - start, total, rank, world)
+
+
+def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
+    """Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun) and joins the process group.
+    Returns (rank, local_rank, world).  world == 1 without env vars: no process group."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def current_stream_handle() -> int:
+    """cudaStream_t of torch's current stream for the C ABI.  torch reports its default stream as 0,
+    but 0 / NULL means "the backend's own stream" to the C ABI, so the legacy default stream is
+    passed as cudaStreamLegacy (0x1)."""
+    return torch.cuda.current_stream().cuda_stream or 1
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+# ---- exchange steps (device-agnostic: CUDA tensors over NCCL, CPU tensors over gloo) ------------
+def combine_sum(partial: torch.Tensor) -> torch.Tensor:
+    """all_reduce(SUM) of per-slice partials (dot, sum, sum of squares), in place."""
+    if world_size() > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM)
+    return partial
+
+
+def combine_extreme(partial: torch.Tensor, is_max: bool) -> torch.Tensor:
+    if world_size() > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.MAX if is_max else dist.ReduceOp.MIN)
+    return partial
+
+
+NO_CANDIDATE = torch.iinfo(torch.int64).max
+
+
+def combine_arg(value: torch.Tensor, index: torch.Tensor, is_max: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    """(value, GLOBAL index) pairs from every slice -> the scalar-backend answer for the whole vector
+    (src/backends/scalar.rs:140-166).  Slice 0 carries the a[0] seed rule, so a NaN value from it is
+    final (a NaN seed never loses).  Interior slices report NO_CANDIDATE when they hold nothing but
+    NaNs / identity values (a NaN element never wins).  Otherwise: best value, and among equal
+    values the LOWEST global index.  NCCL has no arg-reduce: this is an all_gather of `world` pairs."""
+    w = world_size()
+    if w == 1:
+        return value, index
+    vals = torch.empty(w, dtype=value.dtype, device=value.device)
+    idxs = torch.empty(w, dtype=index.dtype, device=index.device)
+    dist.all_gather_into_tensor(vals, value.reshape(1))
+    dist.all_gather_into_tensor(idxs, index.reshape(1))
+    return pick_arg(vals, idxs, is_max)
+
+
+def pick_arg(vals: torch.Tensor, idxs: torch.Tensor, is_max: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    """The selection rule of combine_arg on already-gathered pairs (pure tensor ops, no host sync)."""
+    nan0 = torch.isnan(vals[0])
+    usable = (idxs != NO_CANDIDATE) & ~torch.isnan(vals)
+    worst = -float("inf") if is_max else float("inf")
+    key = torch.where(usable, vals, torch.full_like(vals, worst))
+    best = key.max() if is_max else key.min()
+    cand = torch.where(usable & (key == best), idxs, torch.full_like(idxs, NO_CANDIDATE))
+    out_v = torch.where(nan0, vals[0], best)
+    out_i = torch.where(nan0, idxs[0], cand.min())
+    return out_v.reshape(1), out_i.reshape(1)
+
+
+# ---- sharded ops on device-resident slices --------------------------------------------------------
+class ShardedVector:
+    """This rank's contiguous slice of a global f32 vector, resident in HBM."""
+
+    def __init__(self, local: torch.Tensor, shard: Shard):
+        assert local.is_cuda and local.dtype == torch.float32 and local.is_contiguous()
+        self.local, self.shard = local, shard
+        self._f32 = torch.zeros(1, dtype=torch.float32, device=local.device)
+        self._i64 = torch.zeros(1, dtype=torch.int64, device=local.device)
+
+    def _stream(self) -> int:
+        return current_stream_handle()
+
+    def _partial(self, fn_name: str, other: "ShardedVector | None" = None) -> torch.Tensor:
+        import trueno_b200 as trn
+        fn = getattr(trn.lib, fn_name)
+        n = self.local.numel()
+        if other is None:
+            trn.check(fn(self.local.data_ptr(), n, self._f32.data_ptr(), self._stream()))
+        else:
+            trn.check(fn(self.local.data_ptr(), n, other.local.data_ptr(), other.local.numel(),
+                         self._f32.data_ptr(), self._stream()))
+        return self._f32
+
+    def sum(self) -> torch.Tensor:
+        return combine_sum(self._partial("trn_sum_f32_dev"))
+
+    def dot(self, other: "ShardedVector") -> torch.Tensor:
+        return combine_sum(self._partial("trn_dot_f32_dev", other))
+
+    def norm_l2(self) -> torch.Tensor:
+        return combine_sum(self._partial("trn_sumsq_f32_dev")).sqrt_()
+
+    def _arg(self, is_max: bool) -> tuple[torch.Tensor, torch.Tensor]:
+        import trueno_b200 as trn
+        fn = trn.lib.trn_argmax_slice_f32_dev if is_max else trn.lib.trn_argmin_slice_f32_dev
+        trn.check(fn(self.local.data_ptr(), self.local.numel(), int(self.shard.start == 0), self._i64.data_ptr(),
+                     self._f32.data_ptr(), self._stream()))
+        # local -> global index; the kernel's "no candidate" (u64 ~0 == int64 -1) maps to NO_CANDIDATE
+        gidx = torch.where(self._i64 < 0, torch.full_like(self._i64, NO_CANDIDATE), self._i64 + self.shard.start)
+        return combine_arg(self._f32, gidx, is_max)
+
+    def argmax(self) -> torch.Tensor:
+        return self._arg(True)[1]
+
+    def argmin(self) -> torch.Tensor:
+        return self._arg(False)[1]
+
+    def max(self) -> torch.Tensor:
+        return self._arg(True)[0]
+
+    def min(self) -> torch.Tensor:
+        return self._arg(False)[0]
