@@ -6,10 +6,10 @@ Stated tolerances:
   * dot / sum / norm_l2            : |gpu - f64 truth| <= 1e-5 * sum|terms|   (condition-aware "1e-5 rel")
   * matmul family                  : |gpu - f64 truth| <= 1e-5 * sum_k |a_ik||b_kj|
   * softmax                        : <= 1e-6 abs AND <= 8 ulp vs the f64 truth; vs the scalar-libm oracle
-                                     <= 1e-6 abs (tests/pixel_fkr.rs:30) + 8*sqrt(cols)*2^-24 relative — the
-                                     second term is the rounding noise of the REFERENCE's own left-to-right
-                                     f32 sum of `cols` exponentials (src/vector.rs:1548), which ours (a tree)
-                                     does not share
+                                     <= 1e-6 abs (tests/pixel_fkr.rs:30) + the REFERENCE's own measured relative
+                                     deviation from the truth (its left-to-right f32 sum of `cols`
+                                     exponentials, src/vector.rs:1548, loses up to 2.4e-4 at 200 003 columns;
+                                     asserted < 1e-3), which ours (register tree / Kahan) does not share
   * log_softmax                    : <= 4 ulp(|y|) + 2^-22 vs the f64 truth; vs the oracle the same plus the
                                      reference's sum noise
   * sigmoid                        : <= 4 ulp vs the scalar-libm oracle
@@ -209,7 +209,11 @@ def test_softmax_rows_vs_oracle(trn, oracle, rows, cols):
     arg = (x - x.max(1, keepdims=True)).astype(f32).astype(np.float64)
     e64 = np.exp(arg)
     truth = e64 / e64.sum(1, keepdims=True)
-    ref_noise = 8 * np.sqrt(cols) * 2.0 ** -24   # observed up to 3.6e-5 at cols = 32000 (the REFERENCE's error)
+    # the REFERENCE's own deviation from the truth: its left-to-right f32 sum of `cols` exponentials
+    # (src/vector.rs:1548) drops every term below half an ulp of the running sum — measured 9.3e-5
+    # relative at cols = 32 000 and 2.4e-4 at 200 003.  Ours (register tree / Kahan) stays within ulps.
+    ref_noise = float(np.max(np.abs(want - truth) / np.maximum(truth, 1e-300))) + 1e-6
+    assert ref_noise < 1e-3
     assert np.all(np.abs(got - truth) <= np.minimum(1e-6, 8 * ulp(truth) + 1e-45))
     assert np.all(np.abs(got.astype(np.float64) - want) <= 1e-6 + ref_noise * want)
     assert np.max(np.abs(got.astype(np.float64).sum(1) - 1)) < 1e-5       # proptest: sums to 1 (src/vector.rs:13461)
