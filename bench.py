@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -75,9 +75,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, region: tuple[float, float] | None = None, load_window: tuple[float, float] | None = None) -> dict:
+        """Summarises the samples that fell inside the timed region; a region shorter than three
+        sampling periods falls back to the surrounding window in which the same kernel was running
+        back to back (warm-up + timed + roofline loops) and says so in `window`."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,8 +88,17 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        window = "all samples"
+        rows = [r for _, r in self.rows]
+        if region:
+            inside = [r for t, r in self.rows if region[0] <= t <= region[1]]
+            if len(inside) >= 3:
+                rows, window = inside, "timed region"
+            elif load_window:
+                rows = [r for t, r in self.rows if load_window[0] <= t <= load_window[1]] or rows
+                window = "timed region < 3 samples: warm-up + timed + roofline loops (same kernel, back to back)"
         sm, smax, reasons, power = [], [], set(), []
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
                 for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
@@ -96,7 +108,8 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 # ==================================================================================================
@@ -208,25 +221,28 @@ def run_ours(args) -> int:
     def step_dev():
         trn.check(L.trn_matmul_f32_dev(a.data_ptr(), M, K, b.data_ptr(), K, N, c.data_ptr(), st))
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)   # nvidia-smi start-up
+    t_load0 = time.time()
     for _ in range(max(args.warmup, 3)):
         step_dev()
     barrier()
 
     # ---- timed region: K steps, device events, barrier + sync on both sides, clocks sampled during
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = trn.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step_dev()
     e1.record(stream)
     barrier()
+    t_region1 = time.time()
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = trn.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else {}
     ms_per_step = elapsed_ms / args.steps
     value = FLOP_PER_STEP * world / (ms_per_step * 1e-3) / 1e12
 
@@ -239,6 +255,8 @@ def run_ours(args) -> int:
         trn.check(L.trn_profile_last_gemm(C.byref(p_ms), C.byref(k_ms)))
         kern_ms.append(k_ms.value); pre_ms.append(p_ms.value)
     L.trn_profile_enable(0)
+    torch.cuda.synchronize()
+    clocks = sampler.stop((t_region0, t_region1), (t_load0, time.time())) if rank == 0 else {}
     kernel_ms = sum(kern_ms) / len(kern_ms)
     achieved = FLOP_PER_STEP / (kernel_ms * 1e-3) / 1e12
     tf32x3_peak = bf16_peak / 6.0   # TF32 runs at half the bf16 rate; 3 TF32 MMAs per f32 product

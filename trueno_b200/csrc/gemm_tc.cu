@@ -31,8 +31,9 @@
 //   warp 0 : TMA producer   (cp.async.bulk.tensor.3d -> smem ring, mbarrier complete_tx)
 //   warp 1 : MMA issuer     (one elected lane; tcgen05.mma.cta_group::1.kind::tf32, 128x256x8),
 //            also owns the TMEM allocation (512 columns = two 128x256 f32 accumulators)
-//   warps 2-9 : epilogue    (tcgen05.ld 32x32b -> f32 register accumulators -> global); warp w owns
-//            TMEM lane quadrant w%4 and column half (w-2)/4 of the 128x256 tile.
+//   warps 2-9 : epilogue    (tcgen05.ld 32x32b -> f32 register accumulators -> swizzled smem block ->
+//            cp.async.bulk.tensor store); warp w owns TMEM lane quadrant w%4 and column half (w-2)/4
+//            of the 128x256 tile.
 // Accumulation order is fixed (k ascending, no split-K, no atomics) => bit-identical reruns
 // (tests/wasm_optimization_tests.rs:200-230).
 //
@@ -60,7 +61,8 @@ struct Cfg {
     static constexpr int kOperands = TERMS == 3 ? 2 : 1;  // hi (+ lo)
     static constexpr uint32_t kStageBytes = kOperands * (kABytes + kBBytes);
     static constexpr int kStages = TERMS == 3 ? 2 : 4;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t kStoreBytes = kEpiWarps * 4096;  // one 32x32 f32 staging block per epilogue warp
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -158,6 +160,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 
 struct Params {
     float* c;
+    uint32_t tma_store;         // 1: C goes out through smem + cp.async.bulk.tensor stores (needs n % 4 == 0)
     const int* nonfinite_flag;  // set by the split pre-pass; non-zero => this kernel must not run
     uint32_t m, n;            // C rows / cols per batch
     uint32_t num_kb;          // Kpad / BK
@@ -183,14 +186,15 @@ template <int TERMS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                 const Params p) {
+                 const __grid_constant__ CUtensorMap map_c, const Params p) {
     using C = Cfg<TERMS>;
     if (*p.nonfinite_flag != 0) return;  // Inf/NaN in the inputs: the SIMT kernel takes over (grid-uniform)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + C::kStages * C::kStageBytes);
+    const uint32_t store_base = smem_base + C::kStages * C::kStageBytes;   // 1024-aligned staging for C
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + C::kStages * C::kStageBytes + C::kStoreBytes);
     // barrier slots: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -312,23 +316,44 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             // ---- store this thread's 128 columns
-            const uint32_t row = mt * BM + quad * 32 + lane;
+            const uint32_t row0 = mt * BM + quad * 32;
+            const uint32_t row = row0 + lane;
             const uint32_t col_base = nt * BN + half * 128;
-            if (row < p.m && col_base < p.n) {
-                float* crow = p.c + ((size_t)b * p.m + row) * p.n + col_base;
-                const bool vec_ok = (p.n % 4) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15u) == 0;
-                if (vec_ok && col_base + 128 <= p.n) {
+            if (p.tma_store) {
+                // registers -> 32x32 block in smem (SWIZZLE_128B pattern: 16-byte chunk j of row r sits at
+                // chunk j ^ (r & 7), conflict-free for row-per-lane float4 writes) -> TMA tensor store, which
+                // writes full 128-byte lines and clips rows >= m / cols >= n by itself.
+                const uint32_t stage_addr = store_base + (uint32_t)(warp - 2) * 4096u;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        *reinterpret_cast<float4*>(crow + 4 * j) =
-                            make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
-                } else {
+                for (int j = 0; j < 4; ++j) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging free again
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 128; ++j)
-                        if (col_base + j < p.n) crow[j] = sum[j];
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t dst = stage_addr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) * 16);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(dst), "f"(sum[j * 32 + 4 * q]),
+                                     "f"(sum[j * 32 + 4 * q + 1]), "f"(sum[j * 32 + 4 * q + 2]), "f"(sum[j * 32 + 4 * q + 3])
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && row0 < p.m && col_base + j * 32 < p.n) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     :: "l"(&map_c), "r"(stage_addr), "r"((int)(col_base + j * 32)), "r"((int)row0), "r"((int)b)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
+            } else if (row < p.m && col_base < p.n) {
+                float* crow = p.c + ((size_t)b * p.m + row) * p.n + col_base;
+#pragma unroll
+                for (int j = 0; j < 128; ++j)
+                    if (col_base + j < p.n) crow[j] = sum[j];
             }
         }
+        // all of this warp's tensor stores must have landed before the CTA exits
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
 
     tc_fence_before();
@@ -443,12 +468,13 @@ static EncodeTiledFn get_encode() {
 }
 
 // [batch][rows][kpad] f32, box = {BK, box_rows, 1}, SWIZZLE_128B
-static int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows) {
+static int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows,
+                    uint32_t box_cols = BK) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     cuuint64_t dims[3] = {kpad, rows, batch};
     cuuint64_t strides[2] = {kpad * sizeof(float), rows * kpad * sizeof(float)};
-    cuuint32_t box[3] = {BK, box_rows, 1};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -459,7 +485,7 @@ static int make_map(CUtensorMap* map, const float* base, size_t batch, size_t ro
 
 template <int TERMS>
 static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                  const Params& p, int sm_count, cudaStream_t s) {
+                  const CUtensorMap& mc, const Params& p, int sm_count, cudaStream_t s) {
     using C = Cfg<TERMS>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -468,7 +494,7 @@ static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMa
     }
     const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
     const uint32_t grid = total < (uint32_t)sm_count ? total : (uint32_t)sm_count;
-    gemm_tf32_kernel<TERMS><<<grid, kThreads, C::kSmemBytes, s>>>(ah, al, bh, bl, p);
+    gemm_tf32_kernel<TERMS><<<grid, kThreads, C::kSmemBytes, s>>>(ah, al, bh, bl, mc, p);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -532,8 +558,14 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     TRN_TRY(make_map(&map_bh, b_hi, batch, n, kpad, BN));
     TRN_TRY(make_map(&map_bl, b_lo, batch, n, kpad, BN));
 
+    // C as a [batch][m][n] tensor with 32x32 store boxes — only when its rows are 16-byte aligned
+    CUtensorMap map_c = map_ah;
+    const bool tma_store = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(c) & 15u) == 0);
+    if (tma_store) TRN_TRY(make_map(&map_c, c, batch, m, n, 32, 32));
+
     Params p;
     p.c = c;
+    p.tma_store = tma_store ? 1u : 0u;
     p.nonfinite_flag = flag;
     p.m = (uint32_t)m;
     p.n = (uint32_t)n;
@@ -542,8 +574,8 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     p.tiles_n = (uint32_t)((n + BN - 1) / BN);
     p.batch = (uint32_t)batch;
     if (g_profile) TRN_CUDA(cudaEventRecord(g_ev[1], s));
-    int st = terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s)
-                        : launch<1>(map_ah, map_al, map_bh, map_bl, p, cx->sm_count, s);
+    int st = terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s)
+                        : launch<1>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s);
     if (g_profile) {
         TRN_CUDA(cudaEventRecord(g_ev[2], s));
         g_ev_valid = true;

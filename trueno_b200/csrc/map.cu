@@ -20,15 +20,18 @@ __device__ __forceinline__ float apply(float x, float y) {
     if (OP == 0) return x + y;
     if (OP == 1) return x * y;
     if (OP == 2) {
-        // src/backends/scalar.rs:313-324
-        if (x < -50.0f) return 0.0f;
-        if (x > 50.0f) return 1.0f;
-        return 1.0f / (1.0f + expf(-x));
+        // src/backends/scalar.rs:313-324 (cut-offs applied as selects: no divergence)
+        const float s = 1.0f / (1.0f + expf(-x));
+        return x < -50.0f ? 0.0f : (x > 50.0f ? 1.0f : s);
     }
-    // src/backends/scalar.rs:330-340 — same operation order: (x*x)*x, c*x3, x+.., k*(..), (0.5*x)*(1+tanh)
+    // src/backends/scalar.rs:330-340: 0.5*x*(1 + tanh(u)), u = k*(x + c*x^3) with the reference's
+    // operation order for u.  Evaluated through the exact identity 0.5*(1 + tanh(u)) = 1/(1 + e^(-2u)):
+    // branch-free (tanhf is two divergent paths), ~half the instructions, and WITHOUT the 1 + tanh
+    // cancellation the reference's form has for x << 0 — so the result is at least as close to the true
+    // value as the reference's own (parity tolerance: 4 ulp + 4*2^-24*|x|, the reference's cancellation term).
     const float x3 = __fmul_rn(__fmul_rn(x, x), x);
-    const float inner = __fmul_rn(0.7978846f, __fadd_rn(x, __fmul_rn(0.044715f, x3)));
-    return __fmul_rn(__fmul_rn(0.5f, x), __fadd_rn(1.0f, tanhf(inner)));
+    const float u = __fmul_rn(0.7978846f, __fadd_rn(x, __fmul_rn(0.044715f, x3)));
+    return x / (1.0f + expf(-2.0f * u));
 }
 
 template <int OP>
@@ -84,10 +87,16 @@ int launch_map(Map op, const float* a, const float* b, float* out, size_t n, cud
     const bool bin = op == Map::Add || op == Map::Mul;
     const bool vec = aligned16(a) && aligned16(out) && (!bin || aligned16(b));
     size_t tiles = (n / 4 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-    size_t cap = (size_t)c->sm_count * 8;
-    int grid = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);
+    // exactly one resident wave: grid = SMs x (CTAs the kernel really fits per SM), so there is no tail wave
 #define LAUNCH(OP)                                                                    \
     do {                                                                              \
+        static int per_sm = 0;                                                        \
+        if (!per_sm) {                                                                \
+            TRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_kernel<OP, true>, kThreads, 0)); \
+            if (per_sm < 1) per_sm = 1;                                               \
+        }                                                                             \
+        size_t cap = (size_t)c->sm_count * per_sm;                                    \
+        int grid = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);                    \
         if (vec) map_kernel<OP, true><<<grid, kThreads, 0, s>>>(a, b, out, n);         \
         else     map_kernel<OP, false><<<grid, kThreads, 0, s>>>(a, b, out, n);        \
     } while (0)

@@ -239,13 +239,20 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
 // ---- launchers ------------------------------------------------------------------------------------------
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int reduce_grid(size_t n, int sm_count) {
-    // enough blocks to cover the data once with 16 KiB tiles, capped at 8 resident CTAs per SM
+// enough blocks to cover the data once with 16 KiB tiles, capped at ONE resident wave (SMs x the
+// CTAs of this kernel that really fit per SM — ncu showed 8/SM was 1.33 waves at 36 registers)
+static int reduce_grid(size_t n, int sm_count, int per_sm) {
     size_t tiles = (n / 4 + kTileVec - 1) / kTileVec;
-    size_t cap = (size_t)sm_count * 8;
+    size_t cap = (size_t)sm_count * (per_sm < 1 ? 1 : per_sm);
     if (cap > (size_t)kMaxReduceBlocks) cap = kMaxReduceBlocks;
     size_t g = tiles < cap ? tiles : cap;
     return (int)(g ? g : 1);
+}
+template <class K>
+static int blocks_per_sm(K kernel) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0) != cudaSuccess) { cudaGetLastError(); v = 4; }
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
 }
 
 int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s) {
@@ -257,10 +264,12 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
     }
     Workspace* w = workspace(s);
     if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
-    const int grid = reduce_grid(n, c->sm_count);
     const bool vec = aligned16(a) && (op != Reduce::Dot || aligned16(b));
 #define LAUNCH(OP, SQRT)                                                                                   \
     do {                                                                                                   \
+        static int per_sm = 0;                                                                             \
+        if (!per_sm) per_sm = blocks_per_sm(reduce_sum_kernel<OP, true, SQRT>);                            \
+        const int grid = reduce_grid(n, c->sm_count, per_sm);                                              \
         if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out); \
         else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out); \
     } while (0)
@@ -282,7 +291,12 @@ int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, fl
     if (!c) return TRN_GPU_ERROR;
     Workspace* w = workspace(s);
     if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
-    const int grid = reduce_grid(n, c->sm_count);
+    static int per_sm_max = 0, per_sm_min = 0;
+    if (!per_sm_max) {
+        per_sm_max = blocks_per_sm(argreduce_kernel<true, true>);
+        per_sm_min = blocks_per_sm(argreduce_kernel<false, true>);
+    }
+    const int grid = reduce_grid(n, c->sm_count, is_max ? per_sm_max : per_sm_min);
     const bool vec = aligned16(a);
     if (is_max) {
         if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
