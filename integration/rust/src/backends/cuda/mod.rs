@@ -1,0 +1,152 @@
+//! `src/backends/cuda/mod.rs` — the B200 (sm_100a) backend of trueno's data-parallel hot path.
+//!
+//! Drop this directory into the trueno tree as `src/backends/cuda/`, add
+//! `trueno-cuda-sys = { path = "...", optional = true }` and `cuda = ["trueno-cuda-sys"]` to
+//! Cargo.toml, and apply the dispatcher edits listed in INTEGRATION.md.  With the `cuda` feature
+//! on, `Backend::Auto`/`Backend::GPU` route the hot-path ops here UNCONDITIONALLY: there is no
+//! size threshold, no wgpu fallback and no CPU fallback — a CUDA failure surfaces as
+//! `TruenoError::GpuError`.
+//!
+//! The public `Vector` / `Matrix` API and its `Result` semantics do not change: shape validation
+//! stays in `src/vector.rs` / `src/matrix.rs` (so the error values and message text are produced by
+//! the same Rust code as today), and this backend only replaces the arithmetic.
+//!
+//! This file cannot be compiled in the build image of the CUDA sources (no cargo there); it is kept
+//! trivially thin on purpose — every function is one FFI call plus status mapping.
+use crate::{Backend, TruenoError};
+use trueno_cuda_sys as sys;
+
+pub mod buffer;
+pub use buffer::DeviceBuffer;
+
+/// Maps a non-zero `trn_status` to the `TruenoError` variant it stands for (src/error.rs:8-41).
+#[cold]
+pub(crate) fn status_to_error(status: i32) -> TruenoError {
+    let mut buf = [0u8; 1024];
+    // SAFETY: buf is writable for its whole length; the library NUL-terminates.
+    let len = unsafe { sys::trn_last_error(buf.as_mut_ptr().cast(), buf.len()) }.min(buf.len() - 1);
+    let msg = String::from_utf8_lossy(&buf[..len]).into_owned();
+    match status {
+        sys::TRN_SIZE_MISMATCH => {
+            let (mut expected, mut actual) = (0u64, 0u64);
+            unsafe { sys::trn_last_mismatch(&mut expected, &mut actual) };
+            TruenoError::SizeMismatch { expected: expected as usize, actual: actual as usize }
+        }
+        sys::TRN_INVALID_INPUT => TruenoError::InvalidInput(msg),
+        sys::TRN_EMPTY_VECTOR => TruenoError::EmptyVector,
+        sys::TRN_DIVISION_BY_ZERO => TruenoError::DivisionByZero,
+        sys::TRN_UNSUPPORTED_BACKEND => TruenoError::UnsupportedBackend(Backend::GPU),
+        _ => TruenoError::GpuError(msg),
+    }
+}
+
+#[inline]
+pub(crate) fn check(status: i32) -> Result<(), TruenoError> {
+    if status == sys::TRN_OK { Ok(()) } else { Err(status_to_error(status)) }
+}
+
+/// Stateless operator set with the shape of `trait VectorBackend` (src/backends/mod.rs:52-385),
+/// but fallible: a CUDA error cannot be swallowed into a plain value.
+pub struct CudaBackend;
+
+macro_rules! reduce_f32 {
+    ($name:ident, $ffi:ident) => {
+        #[inline]
+        pub fn $name(a: &[f32]) -> Result<f32, TruenoError> {
+            let mut out = 0.0f32;
+            check(unsafe { sys::$ffi(a.as_ptr(), a.len(), &mut out) })?;
+            Ok(out)
+        }
+    };
+}
+macro_rules! unary_map {
+    ($name:ident, $ffi:ident) => {
+        #[inline]
+        pub fn $name(a: &[f32], result: &mut [f32]) -> Result<(), TruenoError> {
+            debug_assert_eq!(a.len(), result.len());
+            check(unsafe { sys::$ffi(a.as_ptr(), a.len(), result.as_mut_ptr()) })
+        }
+    };
+}
+macro_rules! binary_map {
+    ($name:ident, $ffi:ident) => {
+        #[inline]
+        pub fn $name(a: &[f32], b: &[f32], result: &mut [f32]) -> Result<(), TruenoError> {
+            debug_assert_eq!(a.len(), result.len());
+            check(unsafe { sys::$ffi(a.as_ptr(), a.len(), b.as_ptr(), b.len(), result.as_mut_ptr()) })
+        }
+    };
+}
+
+impl CudaBackend {
+    /// `GpuBackend::is_available()` (src/backends/gpu/mod.rs:75)
+    pub fn is_available() -> bool {
+        unsafe { sys::trn_cuda_is_available() != 0 }
+    }
+
+    pub fn dot(a: &[f32], b: &[f32]) -> Result<f32, TruenoError> {
+        let mut out = 0.0f32;
+        check(unsafe { sys::trn_dot_f32(a.as_ptr(), a.len(), b.as_ptr(), b.len(), &mut out) })?;
+        Ok(out)
+    }
+    reduce_f32!(sum, trn_sum_f32);
+    reduce_f32!(max, trn_max_f32);
+    reduce_f32!(min, trn_min_f32);
+    reduce_f32!(norm_l2, trn_norm_l2_f32);
+
+    pub fn argmax(a: &[f32]) -> Result<usize, TruenoError> {
+        let mut out = 0u64;
+        check(unsafe { sys::trn_argmax_f32(a.as_ptr(), a.len(), &mut out) })?;
+        Ok(out as usize)
+    }
+    pub fn argmin(a: &[f32]) -> Result<usize, TruenoError> {
+        let mut out = 0u64;
+        check(unsafe { sys::trn_argmin_f32(a.as_ptr(), a.len(), &mut out) })?;
+        Ok(out as usize)
+    }
+
+    binary_map!(add, trn_add_f32);
+    binary_map!(mul, trn_mul_f32);
+    unary_map!(sigmoid, trn_sigmoid_f32);
+    unary_map!(gelu, trn_gelu_f32);
+
+    /// One row (`rows == 1`) is exactly `Vector::softmax` (src/vector.rs:1516).
+    pub fn softmax_rows(a: &[f32], result: &mut [f32], rows: usize, cols: usize) -> Result<(), TruenoError> {
+        check(unsafe { sys::trn_softmax_rows_f32(a.as_ptr(), result.as_mut_ptr(), rows, cols) })
+    }
+    pub fn log_softmax_rows(a: &[f32], result: &mut [f32], rows: usize, cols: usize) -> Result<(), TruenoError> {
+        check(unsafe { sys::trn_log_softmax_rows_f32(a.as_ptr(), result.as_mut_ptr(), rows, cols) })
+    }
+
+    /// `GpuBackend::matmul(a, b, m, k, n)` (src/backends/gpu/mod.rs:434) — same argument meaning.
+    pub fn matmul(a: &[f32], b: &[f32], m: usize, k: usize, n: usize) -> Result<Vec<f32>, TruenoError> {
+        let mut c = vec![0.0f32; m * n];
+        check(unsafe { sys::trn_matmul_f32(a.as_ptr(), m, k, b.as_ptr(), k, n, c.as_mut_ptr()) })?;
+        Ok(c)
+    }
+    pub fn batched_matmul(a: &[f32], b: &[f32], batch: usize, m: usize, k: usize, n: usize) -> Result<Vec<f32>, TruenoError> {
+        let mut c = vec![0.0f32; batch * m * n];
+        check(unsafe {
+            sys::trn_batched_matmul_f32(a.as_ptr(), a.len(), b.as_ptr(), b.len(), c.as_mut_ptr(), batch, m, k, n)
+        })?;
+        Ok(c)
+    }
+    pub fn batched_matmul_4d(a: &[f32], b: &[f32], batch: usize, heads: usize, m: usize, k: usize, n: usize)
+        -> Result<Vec<f32>, TruenoError> {
+        let mut c = vec![0.0f32; batch * heads * m * n];
+        check(unsafe {
+            sys::trn_batched_matmul_4d_f32(a.as_ptr(), a.len(), b.as_ptr(), b.len(), c.as_mut_ptr(), batch, heads, m, k, n)
+        })?;
+        Ok(c)
+    }
+    pub fn matvec(a: &[f32], rows: usize, cols: usize, v: &[f32]) -> Result<Vec<f32>, TruenoError> {
+        let mut y = vec![0.0f32; rows];
+        check(unsafe { sys::trn_matvec_f32(a.as_ptr(), rows, cols, v.as_ptr(), v.len(), y.as_mut_ptr()) })?;
+        Ok(y)
+    }
+    pub fn transpose(a: &[f32], rows: usize, cols: usize) -> Result<Vec<f32>, TruenoError> {
+        let mut out = vec![0.0f32; rows * cols];
+        check(unsafe { sys::trn_transpose_f32(a.as_ptr(), rows, cols, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+}

@@ -1,0 +1,96 @@
+//! Raw bindings to include/trueno_cuda.h — one declaration per exported symbol, nothing else.
+//! Status codes: 0 OK, 1 SizeMismatch, 2 InvalidInput, 3 EmptyVector, 4 DivisionByZero,
+//! 5 GpuError, 6 UnsupportedBackend (the variants of `TruenoError`, src/error.rs:8-41).
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct trn_buf {
+    _private: [u8; 0],
+}
+
+pub const TRN_OK: c_int = 0;
+pub const TRN_SIZE_MISMATCH: c_int = 1;
+pub const TRN_INVALID_INPUT: c_int = 2;
+pub const TRN_EMPTY_VECTOR: c_int = 3;
+pub const TRN_DIVISION_BY_ZERO: c_int = 4;
+pub const TRN_GPU_ERROR: c_int = 5;
+pub const TRN_UNSUPPORTED_BACKEND: c_int = 6;
+
+extern "C" {
+    // context
+    pub fn trn_cuda_init(device: c_int) -> c_int;
+    pub fn trn_cuda_shutdown() -> c_int;
+    pub fn trn_cuda_is_available() -> c_int;
+    pub fn trn_device_count(count: *mut c_int) -> c_int;
+    pub fn trn_device_info(name: *mut c_char, cap: usize, sm_count: *mut c_int, hbm_bytes: *mut u64) -> c_int;
+    pub fn trn_last_error(buf: *mut c_char, cap: usize) -> usize;
+    pub fn trn_last_mismatch(expected: *mut u64, actual: *mut u64);
+    pub fn trn_synchronize(stream: *mut c_void) -> c_int;
+    pub fn trn_launch_count() -> u64;
+    // device buffers + pinned host memory
+    pub fn trn_buf_alloc(len: usize, out: *mut *mut trn_buf) -> c_int;
+    pub fn trn_buf_free(buf: *mut trn_buf) -> c_int;
+    pub fn trn_buf_upload(buf: *mut trn_buf, host: *const f32, len: usize) -> c_int;
+    pub fn trn_buf_download(buf: *const trn_buf, host: *mut f32, len: usize) -> c_int;
+    pub fn trn_buf_len(buf: *const trn_buf) -> usize;
+    pub fn trn_buf_ptr(buf: *const trn_buf) -> *mut f32;
+    pub fn trn_host_alloc(len: usize, out: *mut *mut f32) -> c_int;
+    pub fn trn_host_free(ptr: *mut f32) -> c_int;
+    // host-slice operators (trait VectorBackend, src/backends/mod.rs:52-385; GpuBackend::matmul, gpu/mod.rs:434)
+    pub fn trn_dot_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_sum_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_max_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_min_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_argmax_f32(a: *const f32, n: usize, out: *mut u64) -> c_int;
+    pub fn trn_argmin_f32(a: *const f32, n: usize, out: *mut u64) -> c_int;
+    pub fn trn_norm_l2_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_add_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_mul_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_sigmoid_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_gelu_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_softmax_rows_f32(a: *const f32, out: *mut f32, rows: usize, cols: usize) -> c_int;
+    pub fn trn_log_softmax_rows_f32(a: *const f32, out: *mut f32, rows: usize, cols: usize) -> c_int;
+    pub fn trn_matmul_f32(a: *const f32, a_rows: usize, a_cols: usize, b: *const f32, b_rows: usize, b_cols: usize,
+                          c: *mut f32) -> c_int;
+    pub fn trn_batched_matmul_f32(a: *const f32, a_len: usize, b: *const f32, b_len: usize, c: *mut f32,
+                                  batch: usize, m: usize, k: usize, n: usize) -> c_int;
+    pub fn trn_batched_matmul_4d_f32(a: *const f32, a_len: usize, b: *const f32, b_len: usize, c: *mut f32,
+                                     batch: usize, heads: usize, m: usize, k: usize, n: usize) -> c_int;
+    pub fn trn_matvec_f32(a: *const f32, rows: usize, cols: usize, v: *const f32, v_len: usize, y: *mut f32) -> c_int;
+    pub fn trn_transpose_f32(a: *const f32, rows: usize, cols: usize, out: *mut f32) -> c_int;
+    // device-resident twins (stream-ordered; scalar outputs are device pointers)
+    pub fn trn_dot_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sum_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_max_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_min_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_argmax_f32_dev(a: *const f32, n: usize, out: *mut u64, out_value: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_argmin_f32_dev(a: *const f32, n: usize, out: *mut u64, out_value: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_argmax_slice_f32_dev(a: *const f32, n: usize, first_slice: c_int, out: *mut u64, out_value: *mut f32,
+                                    stream: *mut c_void) -> c_int;
+    pub fn trn_argmin_slice_f32_dev(a: *const f32, n: usize, first_slice: c_int, out: *mut u64, out_value: *mut f32,
+                                    stream: *mut c_void) -> c_int;
+    pub fn trn_norm_l2_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sumsq_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_add_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_mul_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sigmoid_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_gelu_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_softmax_rows_f32_dev(a: *const f32, out: *mut f32, rows: usize, cols: usize, stream: *mut c_void) -> c_int;
+    pub fn trn_log_softmax_rows_f32_dev(a: *const f32, out: *mut f32, rows: usize, cols: usize, stream: *mut c_void) -> c_int;
+    pub fn trn_matmul_f32_dev(a: *const f32, a_rows: usize, a_cols: usize, b: *const f32, b_rows: usize, b_cols: usize,
+                              c: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_batched_matmul_f32_dev(a: *const f32, a_len: usize, b: *const f32, b_len: usize, c: *mut f32,
+                                      batch: usize, m: usize, k: usize, n: usize, stream: *mut c_void) -> c_int;
+    pub fn trn_batched_matmul_4d_f32_dev(a: *const f32, a_len: usize, b: *const f32, b_len: usize, c: *mut f32,
+                                         batch: usize, heads: usize, m: usize, k: usize, n: usize,
+                                         stream: *mut c_void) -> c_int;
+    pub fn trn_matvec_f32_dev(a: *const f32, rows: usize, cols: usize, v: *const f32, v_len: usize, y: *mut f32,
+                              stream: *mut c_void) -> c_int;
+    pub fn trn_transpose_f32_dev(a: *const f32, rows: usize, cols: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    // engine selection / live timing (benches only)
+    pub fn trn_set_gemm_engine(engine: c_int) -> c_int;
+    pub fn trn_get_gemm_engine() -> c_int;
+    pub fn trn_profile_enable(on: c_int) -> c_int;
+    pub fn trn_profile_last_gemm(prepass_ms: *mut f32, kernel_ms: *mut f32) -> c_int;
+}

@@ -4,14 +4,21 @@
 // -> sum -> divide, i.e. 3 reads + 2 writes per element on the CPU, 4 dispatches with a host round
 // trip each in the wgpu path, src/backends/gpu/device.rs:956-971).
 //
-// Layout: a row lives entirely in REGISTERS, spread over a thread-block CLUSTER: CS CTAs x 256
-// threads x VPT float4 (CS in {1,2,4,8}, VPT in {1,2,4,8}); config 5's 32 000-float rows use
-// CS=4, VPT=8 (32 768 slots).  Row max and exp-sum are combined across the cluster through
-// distributed shared memory in a fixed rank order, so every CTA computes bit-identical
-// statistics and reruns are bit-identical.  Several clusters are resident per SM, so one row's
-// load phase overlaps another row's exp/store phase.  Rows longer than 65 536 elements (or rows
-// that are not 16-byte aligned) take the three-pass fallback kernel, which re-reads the row from
-// L2.  Math: accurate expf / logf and IEEE division — no fast-math intrinsics.
+// Three kernels, chosen by row length (cols % 4 == 0, 16-byte aligned rows):
+//   * cols <= 8192: a row lives in the REGISTERS of one 256-thread CTA (VPT float4 per thread).
+//   * 8192 < cols <= 32768 (config 5: 32 000): the TMA RING kernel.  One persistent CTA per SM;
+//     a producer warp streams rows into a 14-slot x 16 KiB shared-memory ring with 1-D bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), 16 consumer warps pull each slot into registers
+//     (a row = <= 8 slots = 16 float4 per thread), release the slot at once, and compute
+//     max -> exp -> sum -> scale out of registers.  Because slots are released as soon as they are
+//     in registers, the next row's bulk copies (up to 224 KiB in flight per SM) run underneath the
+//     current row's exp and store phases — HBM reads never stop, with no register cost.
+//   * cols <= 65536: a row spread over a thread-block CLUSTER (CS CTAs x 256 threads x VPT float4);
+//     row max and exp-sum are combined through distributed shared memory in a fixed rank order.
+// Rows longer than that (or rows that are not 16-byte aligned) take the three-pass fallback kernel,
+// which re-reads the row from L2.  All reductions use fixed trees, so reruns are bit-identical.
+// Math: accurate expf / logf; softmax scales by the correctly rounded reciprocal of the row sum
+// (<= 1 ulp from the reference's e / sum) — no fast-math intrinsics.
 //
 // Algorithmic bytes per element: 8 B (4 read + 4 written).  HBM-bound.
 #include <cooperative_groups.h>
@@ -127,6 +134,153 @@ softmax_rows_cluster_kernel(const float* __restrict__ in, float* __restrict__ ou
     }
 }
 
+// ---- TMA ring kernel -----------------------------------------------------------------------------------
+namespace ring {
+constexpr int kConsumers = 512;                 // 16 consumer warps
+constexpr int kRingThreads = kConsumers + 32;   // + 1 producer warp
+constexpr int kChunkVec = 2 * kConsumers;       // float4 per slot: two per consumer thread
+constexpr uint32_t kChunkBytes = kChunkVec * 16;  // 16 KiB
+constexpr int kMaxChunks = 8;                   // row <= 8 slots = 32 768 floats
+constexpr int kSlots = 14;                      // 224 KiB ring
+constexpr uint32_t kSmemBytes = kSlots * kChunkBytes + 2 * kSlots * 8 + 2 * 16 * 4 + 128;
+}  // namespace ring
+
+template <bool LOG>
+__global__ void __launch_bounds__(ring::kRingThreads, 1)
+softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
+    using namespace ring;
+    extern __shared__ uint8_t ring_smem_raw[];
+    const uint32_t base = (smem_u32(ring_smem_raw) + 127u) & ~127u;
+    uint8_t* gen = ring_smem_raw + (base - smem_u32(ring_smem_raw));
+    const uint32_t bar_base = base + kSlots * kChunkBytes;
+    auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (kSlots + s); };
+    float* s_max = reinterpret_cast<float*>(gen + kSlots * kChunkBytes + 2 * kSlots * 8);
+    float* s_sum = s_max + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned nvec = (unsigned)(cols >> 2);
+    const unsigned nchunks = (nvec + kChunkVec - 1) / kChunkVec;
+    const uint32_t row_bytes = nvec * 16u;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < (uint32_t)kSlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kConsumers / 32); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumers / 32) {
+        // ===================== producer: one elected lane streams rows into the ring =====================
+        if (elect_one()) {
+            uint32_t slot = 0, phase = 0;
+            for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+                const char* src = reinterpret_cast<const char*>(in + row * cols);
+                for (unsigned j = 0; j < nchunks; ++j) {
+                    mbar_wait(empty_bar(slot), phase ^ 1);
+                    const uint32_t off = j * kChunkBytes;
+                    const uint32_t bytes = row_bytes - off < kChunkBytes ? row_bytes - off : kChunkBytes;
+                    mbar_expect_tx(full_bar(slot), bytes);
+                    bulk_load_1d(base + slot * kChunkBytes, src + off, bytes, full_bar(slot));
+                    if (++slot == (uint32_t)kSlots) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const int t = threadIdx.x;
+    uint32_t slot = 0, phase = 0;
+    for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        float4 x[2 * kMaxChunks];
+        // ---- ring -> registers; each slot goes back to the producer as soon as it has been read
+#pragma unroll
+        for (int j = 0; j < kMaxChunks; ++j) {
+            if ((unsigned)j < nchunks) {
+                mbar_wait(full_bar(slot), phase);
+                const uint32_t sb = base + slot * kChunkBytes;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned v = j * kChunkVec + h * kConsumers + t;
+                    float4 r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    if (v < nvec)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sb + (h * kConsumers + t) * 16u));
+                    x[2 * j + h] = r;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(slot));
+                if (++slot == (uint32_t)kSlots) { slot = 0; phase ^= 1; }
+            } else {
+                x[2 * j] = x[2 * j + 1] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+        }
+
+        // ---- row max: warp tree, then a fixed-order fold of the 16 warp values in every thread
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 2 * kMaxChunks; ++j) m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+        m = warp_max(m);
+        if (lane == 0) s_max[warp] = m;
+        named_bar_sync(1, kConsumers);
+        m = s_max[0];
+#pragma unroll
+        for (int w = 1; w < kConsumers / 32; ++w) m = fmaxf(m, s_max[w]);
+
+        // ---- exponentials and their sum.  Padding slots hold -inf -> expf(-inf) = 0 exactly.
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2 * kMaxChunks; ++j) {
+            float4 e;
+            e.x = expf(x[j].x - m); e.y = expf(x[j].y - m); e.z = expf(x[j].z - m); e.w = expf(x[j].w - m);
+            part += (e.x + e.y) + (e.z + e.w);
+            if (!LOG) x[j] = e;
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_sum[warp] = part;
+        named_bar_sync(1, kConsumers);
+        float sum = s_sum[0];
+#pragma unroll
+        for (int w = 1; w < kConsumers / 32; ++w) sum += s_sum[w];
+        // (s_max is rewritten only after the next row's first barrier... no: after THIS barrier every
+        //  thread has read s_max; s_sum is rewritten after the next row's max barrier.)
+
+        // ---- scale and store straight from registers (512 contiguous bytes per warp per store)
+        const float lse = LOG ? logf(sum) : 0.f;
+        const float inv = LOG ? 0.f : __frcp_rn(sum);
+        float4* dst = reinterpret_cast<float4*>(out + row * cols);
+#pragma unroll
+        for (int j = 0; j < 2 * kMaxChunks; ++j) {
+            const unsigned v = (j >> 1) * kChunkVec + (j & 1) * kConsumers + t;
+            if (v < nvec) {
+                float4 y;
+                if (LOG) {  // (x - max) - ln(sum), evaluated in that order (src/vector.rs:1617-1621)
+                    y.x = (x[j].x - m) - lse; y.y = (x[j].y - m) - lse;
+                    y.z = (x[j].z - m) - lse; y.w = (x[j].w - m) - lse;
+                } else {
+                    y.x = x[j].x * inv; y.y = x[j].y * inv; y.z = x[j].z * inv; y.w = x[j].w * inv;
+                }
+                st_stream(dst + v, y);
+            }
+        }
+    }
+}
+
+template <bool LOG>
+static int launch_ring(const float* a, float* out, size_t rows, size_t cols, int sm_count, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        TRN_CUDA(cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ring::kSmemBytes));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)(rows < (size_t)sm_count ? rows : (size_t)sm_count);
+    softmax_rows_ring_kernel<LOG><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
 // Fallback: any cols / alignment.  One CTA per row, three passes (max, exp-sum, write); passes 2
 // and 3 hit L2 for rows that fit there.
 template <bool LOG>
@@ -187,6 +341,7 @@ static int dispatch(const float* a, float* out, size_t rows, size_t cols, int sm
         if (nvec <= kThreads * 2)      return launch_cluster<1, 2, LOG>(a, out, rows, cols, sm_count, s);
         if (nvec <= kThreads * 4)      return launch_cluster<1, 4, LOG>(a, out, rows, cols, sm_count, s);
         if (nvec <= kThreads * 8)      return launch_cluster<1, 8, LOG>(a, out, rows, cols, sm_count, s);
+        if (nvec <= (size_t)ring::kChunkVec * ring::kMaxChunks) return launch_ring<LOG>(a, out, rows, cols, sm_count, s);
         if (nvec <= kThreads * 8 * 2)  return launch_cluster<2, 8, LOG>(a, out, rows, cols, sm_count, s);
         if (nvec <= kThreads * 8 * 4)  return launch_cluster<4, 8, LOG>(a, out, rows, cols, sm_count, s);
         return launch_cluster<8, 8, LOG>(a, out, rows, cols, sm_count, s);
