@@ -453,3 +453,50 @@ def test_large_pageable_staging(trn):
     assert float(v.sum()) == float(n)
     out = v.add(v).as_slice()
     assert out[0] == 2 and out[-1] == 2 and float(out.sum(dtype=np.float64)) == 2.0 * n
+
+
+@pytest.mark.parametrize("shape", [(1, 4096, 2048, 2048), (1, 4100, 1028, 2052), (32, 1024, 128, 1024), (3, 2048, 200, 1536)],
+                         ids=["rowblocks", "rowblocks-ragged", "head-groups", "head-groups-ragged"])
+def test_pipelined_host_gemm_matches_resident(trn, shape):
+    """Pinned host slices take the transfer-overlapped path (api.cu host_gemm_pipelined): row blocks of one
+    product / groups of heads.  It must be bit-identical to the resident call on the same inputs (same
+    kernels, same k order) and inside the matmul tolerance against the f64 truth on sampled rows."""
+    batch, m, k, n = shape
+    rng = np.random.default_rng(m + k + n)
+    ha, hb, hc = trn.pinned_empty(batch * m * k), trn.pinned_empty(batch * k * n), trn.pinned_empty(batch * m * n)
+    ha[:] = rng.uniform(-1, 1, ha.size).astype(f32)
+    hb[:] = rng.uniform(-1, 1, hb.size).astype(f32)
+    hc[:] = np.nan
+    launches0 = trn.launch_count()
+    if batch == 1:
+        trn.check(trn.lib.trn_matmul_f32(ha.ctypes.data, m, k, hb.ctypes.data, k, n, hc.ctypes.data))
+    else:
+        trn.check(trn.lib.trn_batched_matmul_f32(ha.ctypes.data, ha.size, hb.ctypes.data, hb.size, hc.ctypes.data, batch, m, k, n))
+    assert trn.launch_count() - launches0 > 4          # several blocks => the pipelined path really ran
+    da, db, dc = trn.DeviceBuffer.from_host(ha), trn.DeviceBuffer.from_host(hb), trn.DeviceBuffer(batch * m * n)
+    trn.check(trn.lib.trn_batched_matmul_f32_dev(da.ptr, ha.size, db.ptr, hb.size, dc.ptr, batch, m, k, n, None))
+    trn.synchronize()
+    assert np.array_equal(np.asarray(hc), dc.to_host())
+    A = np.asarray(ha).reshape(batch, m, k).astype(np.float64)
+    B = np.asarray(hb).reshape(batch, k, n).astype(np.float64)
+    Cg = np.asarray(hc).reshape(batch, m, n)
+    for bi in {0, batch - 1}:
+        rows = rng.integers(0, m, 16)
+        truth = A[bi, rows] @ B[bi]
+        scale = np.abs(A[bi, rows]) @ np.abs(B[bi])
+        assert np.all(np.abs(Cg[bi, rows] - truth) <= 1e-5 * scale)
+
+
+def test_pipelined_host_gemm_nonfinite_block(trn):
+    """An Inf in ONE row block must give IEEE results (SIMT fallback, raised on the device) for that block
+    and leave the others exact."""
+    m, k, n = 4096, 2048, 2048
+    rng = np.random.default_rng(77)
+    ha, hb, hc = trn.pinned_empty(m * k), trn.pinned_empty(k * n), trn.pinned_empty(m * n)
+    ha[:] = rng.uniform(0, 1, ha.size).astype(f32)
+    hb[:] = rng.uniform(0, 1, hb.size).astype(f32)
+    ha[(m // 2 + 5) * k + 17] = np.inf
+    trn.check(trn.lib.trn_matmul_f32(ha.ctypes.data, m, k, hb.ctypes.data, k, n, hc.ctypes.data))
+    Cg = np.asarray(hc).reshape(m, n)
+    assert np.isposinf(Cg[m // 2 + 5]).all()
+    assert np.isfinite(np.delete(Cg, m // 2 + 5, 0)).all()

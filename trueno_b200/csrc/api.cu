@@ -3,6 +3,7 @@
 // stage through HBM.  No entry point ever computes on the CPU.
 #include <atomic>
 #include <cstdio>
+#include <vector>
 
 #include "common.cuh"
 
@@ -65,6 +66,17 @@ int check_matvec(size_t cols, size_t v_len) {  // src/matrix.rs:1658-1664
 }
 #undef X
 
+}  // namespace
+
+// auto: the tensor-core tile is 128x256; below that the SIMT kernel wins.  The choice depends on
+// (m, k, n) only — never on batch or on how the host path blocks the rows — so a batched product is
+// bit-identical to the loop of single products the reference runs (src/matrix.rs:507-524).
+bool trn::gemm_auto_uses_tc(size_t m, size_t k, size_t n) {
+    return gemm_tc_supported(m, k, n) && m >= 128 && n >= 128 && k >= 32 && m * n * k >= (size_t)1 << 24;
+}
+
+namespace {
+
 // ---- GEMM engine dispatch -----------------------------------------------------------------------
 // Matrix::matmul routes by shape (src/matrix.rs:293-356); the CUDA backend routes every shape to
 // the device (north star: unconditional, no thresholds that fall back to the CPU) and only picks
@@ -84,11 +96,7 @@ int gemm_dispatch(const float* a, const float* b, float* c, size_t batch, size_t
             return fail(TRN_INVALID_INPUT, "tcgen05 GEMM engine forced for an unsupported shape %zux%zux%zu", m, k, n);
         return launch_gemm_tc(a, b, c, batch, m, k, n, engine == 2 ? 3 : 1, s);
     }
-    // auto: the tensor-core tile is 128x256; below that the SIMT kernel wins.  The choice depends on
-    // (m, k, n) only — never on batch — so a batched product is bit-identical to the loop of single
-    // products the reference runs (src/matrix.rs:507-524).
-    if (gemm_tc_supported(m, k, n) && m >= 128 && n >= 128 && k >= 32 && m * n * k >= (size_t)1 << 24)
-        return launch_gemm_tc(a, b, c, batch, m, k, n, 3, s);
+    if (gemm_auto_uses_tc(m, k, n)) return launch_gemm_tc(a, b, c, batch, m, k, n, 3, s);
     return launch_gemm_simt(a, b, c, batch, m, k, n, s);
 }
 
@@ -370,10 +378,117 @@ int trn_log_softmax_rows_f32(const float* a, float* out, size_t rows, size_t col
     return host_softmax(1, a, out, rows, cols);
 }
 
+// ---- pipelined host-slice GEMM -----------------------------------------------------------------------
+// The host-slice call is bound by PCIe, not by the tensor cores (8192^3: 768 MiB over the link vs
+// ~4.5 ms of math), so the transfers are overlapped with the math instead of bracketing it:
+//   copy stream : H2D of B, then of A in row blocks (single product) / of A and B per group of heads (batched)
+//   main stream : split B once (or per group), then per block: split A block -> tcgen05 GEMM -> (IEEE fallback)
+//   d2h stream  : D2H of each finished C block while the next block is uploaded and computed
+// H2D and D2H run on different copy engines in opposite directions of the link.  Every block runs the same
+// kernels with the same k-order as the unblocked call: results are bit-identical to trn_matmul_f32_dev.
+struct Event {
+    cudaEvent_t e = nullptr;
+    int create() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess ? TRN_OK : fail(TRN_GPU_ERROR, "cudaEventCreate failed"); }
+    ~Event() { if (e) cudaEventDestroy(e); }
+};
+
+static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n) {
+    Context* cx = ctx();
+    cudaStream_t s_main = cx->stream, s_up = cx->copy_stream, s_down = cx->d2h_stream;
+    const size_t kpad = gemm_tc_kpad(k);
+    const bool single = batch == 1;
+    // work units: row blocks of one product, or groups of whole (batch*head) products
+    size_t unit_rows = m, units = batch, per_block = 1;
+    if (single) {
+        unit_rows = 128 * ((m / 8 + 127) / 128);          // ~8 blocks, multiples of the 128-row tile
+        if (unit_rows < 128) unit_rows = 128;
+        units = (m + unit_rows - 1) / unit_rows;
+    } else {
+        const size_t bytes_per = (m * k + k * n + m * n) * sizeof(float);
+        per_block = ((size_t)64 << 20) / (bytes_per ? bytes_per : 1);   // ~64 MiB of traffic per group
+        if (per_block < 1) per_block = 1;
+        if (per_block > batch) per_block = batch;
+        units = (batch + per_block - 1) / per_block;
+    }
+
+    const size_t na = batch * m * k, nb = batch * k * n, nc = batch * m * n;
+    const size_t a_split = batch * m * kpad, b_split = batch * n * kpad;
+    float* dev = nullptr;
+    TRN_TRY(scratch_alloc((void**)&dev, (na + nb + nc + 2 * a_split + 2 * b_split) * sizeof(float) + 256, s_main));
+    float* da = dev;
+    float* db = da + na;
+    float* dc = db + nb;
+    float* a_hi = dc + nc;
+    float* a_lo = a_hi + a_split;
+    float* b_hi = a_lo + a_split;
+    float* b_lo = b_hi + b_split;
+    int* flag = reinterpret_cast<int*>(b_lo + b_split);
+    TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s_main));
+
+    std::vector<Event> up(units + 1), done(units);
+    Event ready, drained;
+    TRN_TRY(ready.create());
+    TRN_TRY(drained.create());
+    for (auto& e : up) TRN_TRY(e.create());
+    for (auto& e : done) TRN_TRY(e.create());
+    // the allocation (stream-ordered on s_main) must be complete before the copy stream writes into it
+    TRN_CUDA(cudaEventRecord(ready.e, s_main));
+    TRN_CUDA(cudaStreamWaitEvent(s_up, ready.e, 0));
+    TRN_CUDA(cudaStreamWaitEvent(s_down, ready.e, 0));
+
+    int st = TRN_OK;
+    if (single) {
+        TRN_CUDA(cudaMemcpyAsync(db, b, nb * sizeof(float), cudaMemcpyHostToDevice, s_up));
+        TRN_CUDA(cudaEventRecord(up[units].e, s_up));
+        TRN_CUDA(cudaStreamWaitEvent(s_main, up[units].e, 0));
+        st = gemm_tc_split_b(db, b_hi, b_lo, 1, k, n, flag, s_main);
+    }
+    for (size_t u = 0; u < units && st == TRN_OK; ++u) {
+        if (single) {
+            const size_t r0 = u * unit_rows, rows = m - r0 < unit_rows ? m - r0 : unit_rows;
+            TRN_CUDA(cudaMemcpyAsync(da + r0 * k, a + r0 * k, rows * k * sizeof(float), cudaMemcpyHostToDevice, s_up));
+            TRN_CUDA(cudaEventRecord(up[u].e, s_up));
+            TRN_CUDA(cudaStreamWaitEvent(s_main, up[u].e, 0));
+            st = gemm_tc_split_a(da + r0 * k, a_hi + r0 * kpad, a_lo + r0 * kpad, 1, rows, k, flag, s_main);
+            if (st == TRN_OK) st = gemm_tc_main(a_hi + r0 * kpad, a_lo + r0 * kpad, b_hi, b_lo, dc + r0 * n, 1, rows, k, n, 3, flag, s_main);
+            if (st == TRN_OK) st = launch_gemm_simt(da + r0 * k, db, dc + r0 * n, 1, rows, k, n, s_main, flag);
+            TRN_CUDA(cudaEventRecord(done[u].e, s_main));
+            TRN_CUDA(cudaStreamWaitEvent(s_down, done[u].e, 0));
+            TRN_CUDA(cudaMemcpyAsync(c + r0 * n, dc + r0 * n, rows * n * sizeof(float), cudaMemcpyDeviceToHost, s_down));
+        } else {
+            const size_t b0 = u * per_block, cnt = batch - b0 < per_block ? batch - b0 : per_block;
+            TRN_CUDA(cudaMemcpyAsync(da + b0 * m * k, a + b0 * m * k, cnt * m * k * sizeof(float), cudaMemcpyHostToDevice, s_up));
+            TRN_CUDA(cudaMemcpyAsync(db + b0 * k * n, b + b0 * k * n, cnt * k * n * sizeof(float), cudaMemcpyHostToDevice, s_up));
+            TRN_CUDA(cudaEventRecord(up[u].e, s_up));
+            TRN_CUDA(cudaStreamWaitEvent(s_main, up[u].e, 0));
+            st = gemm_tc_split_a(da + b0 * m * k, a_hi + b0 * m * kpad, a_lo + b0 * m * kpad, cnt, m, k, flag, s_main);
+            if (st == TRN_OK) st = gemm_tc_split_b(db + b0 * k * n, b_hi + b0 * n * kpad, b_lo + b0 * n * kpad, cnt, k, n, flag, s_main);
+            if (st == TRN_OK) st = gemm_tc_main(a_hi + b0 * m * kpad, a_lo + b0 * m * kpad, b_hi + b0 * n * kpad, b_lo + b0 * n * kpad,
+                                                dc + b0 * m * n, cnt, m, k, n, 3, flag, s_main);
+            if (st == TRN_OK) st = launch_gemm_simt(da + b0 * m * k, db + b0 * k * n, dc + b0 * m * n, cnt, m, k, n, s_main, flag);
+            TRN_CUDA(cudaEventRecord(done[u].e, s_main));
+            TRN_CUDA(cudaStreamWaitEvent(s_down, done[u].e, 0));
+            TRN_CUDA(cudaMemcpyAsync(c + b0 * m * n, dc + b0 * m * n, cnt * m * n * sizeof(float), cudaMemcpyDeviceToHost, s_down));
+        }
+    }
+    // the host slices are borrowed: everything must have landed before the call returns
+    cudaError_t e1 = cudaStreamSynchronize(s_up), e2 = cudaStreamSynchronize(s_main), e3 = cudaStreamSynchronize(s_down);
+    scratch_free(dev, s_main);
+    if (st != TRN_OK) return st;
+    TRN_CUDA(e1);
+    TRN_CUDA(e2);
+    TRN_CUDA(e3);
+    return TRN_OK;
+}
+
 static int host_gemm(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n) {
     Context* cx = ctx();
     const size_t na = batch * m * k, nb = batch * k * n, nc = batch * m * n;
     if (nc == 0) return TRN_OK;
+    // large tensor-core products from pinned host memory: overlap the PCIe transfers with the math
+    if (g_engine.load() == 0 && k > 0 && m > 1 && gemm_auto_uses_tc(m, k, n) && (na + nb + nc) * sizeof(float) >= ((size_t)64 << 20) &&
+        (batch > 1 || m >= 1024) && is_pinned_host(a) && is_pinned_host(b) && is_pinned_host(c))
+        return host_gemm_pipelined(a, b, c, batch, m, k, n);
     DevTemp da(cx->stream), db(cx->stream), dc(cx->stream);
     TRN_TRY(da.alloc(na));
     TRN_TRY(db.alloc(nb));

@@ -35,7 +35,8 @@ struct Context {
     size_t hbm_bytes;
     char name[256];
     cudaStream_t stream;      // the backend's own stream (host-slice calls, default for *_dev)
-    cudaStream_t copy_stream; // second stream for staged H2D/D2H overlap
+    cudaStream_t copy_stream; // H2D leg of the pipelined host-slice GEMM
+    cudaStream_t d2h_stream;  // D2H leg of the pipelined host-slice GEMM
 };
 
 // Lazily binds the process to a device (LOCAL_RANK or 0); returns nullptr and sets the
@@ -96,6 +97,15 @@ int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, siz
 int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
                    int terms, cudaStream_t s);
 bool gemm_tc_supported(size_t m, size_t k, size_t n);
+// the three phases of launch_gemm_tc, exposed so the host-slice path can pipeline them with transfers
+size_t gemm_tc_kpad(size_t k);
+int gemm_tc_split_a(const float* a, float* a_hi, float* a_lo, size_t batch, size_t m, size_t k, int* flag, cudaStream_t s);
+int gemm_tc_split_b(const float* b, float* b_hi, float* b_lo, size_t batch, size_t k, size_t n, int* flag, cudaStream_t s);
+int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* c, size_t batch,
+                 size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s);
+// auto-dispatch rule shared by the resident and the pipelined host paths (api.cu)
+bool gemm_auto_uses_tc(size_t m, size_t k, size_t n);
+bool is_pinned_host(const void* p);
 
 // ---------------------------------------------------------------------------------------------
 // Device helpers

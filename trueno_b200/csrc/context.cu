@@ -94,6 +94,7 @@ static int init_locked(int device) {
     snprintf(c->name, sizeof c->name, "%s", prop.name);
     TRN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     TRN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    TRN_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     // keep freed scratch in the pool: GEMM operand splits are re-used call after call
     cudaMemPool_t pool;
     TRN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -156,6 +157,8 @@ int scratch_free(void* p, cudaStream_t s) {
 }
 
 // ---- transfers ------------------------------------------------------------------------------------
+static bool is_pinned(const void* p);
+bool is_pinned_host(const void* p) { return is_pinned(p); }
 static bool is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -270,6 +273,7 @@ int trn_cuda_shutdown(void) {
         }
     cudaStreamDestroy(g_ctx->stream);
     cudaStreamDestroy(g_ctx->copy_stream);
+    cudaStreamDestroy(g_ctx->d2h_stream);
     delete g_ctx;
     g_ctx = nullptr;
     return TRN_OK;

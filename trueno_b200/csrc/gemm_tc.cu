@@ -478,29 +478,17 @@ bool gemm_tc_supported(size_t m, size_t k, size_t n) {
     return m >= 1 && n >= 1 && k >= 1 && m < (1u << 30) && n < (1u << 30) && k < (1u << 30);
 }
 
-int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int terms,
-                   cudaStream_t s) {
+size_t gemm_tc_kpad(size_t k) { return (k + tc::BK - 1) / tc::BK * tc::BK; }
+
+// A [batch][m][k] row-major -> hi/lo [batch][m][kpad]; raises *flag on Inf/NaN
+int gemm_tc_split_a(const float* a, float* a_hi, float* a_lo, size_t batch, size_t m, size_t k, int* flag,
+                    cudaStream_t s) {
     using namespace tc;
     Context* cx = ctx();
     if (!cx) return TRN_GPU_ERROR;
-    if (batch == 0 || m == 0 || n == 0) return TRN_OK;
-    const size_t kpad = (k + BK - 1) / BK * BK;
-    const size_t a_elems = batch * m * kpad, b_elems = batch * n * kpad;
-
-    // scratch: A_hi, A_lo, Bt_hi, Bt_lo (stream-ordered pool; stays cached between calls)
-    float* scratch = nullptr;
-    TRN_TRY(scratch_alloc((void**)&scratch, (2 * a_elems + 2 * b_elems) * sizeof(float) + 256, s));
-    float* a_hi = scratch;
-    float* a_lo = a_hi + a_elems;
-    float* b_hi = a_lo + a_elems;
-    float* b_lo = b_hi + b_elems;
-    int* flag = reinterpret_cast<int*>(b_lo + b_elems);   // non-finite-input flag (see header)
-    TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
-
-    if (g_profile) {
-        if (!g_ev[0]) for (auto& e : g_ev) TRN_CUDA(cudaEventCreate(&e));
-        TRN_CUDA(cudaEventRecord(g_ev[0], s));
-    }
+    const size_t kpad = gemm_tc_kpad(k);
+    const size_t a_elems = batch * m * kpad;
+    if (a_elems == 0) return TRN_OK;
     const unsigned cap = (unsigned)cx->sm_count * 8;
     const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
     if (vec) {
@@ -511,13 +499,35 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
         size_t blocks = (a_elems + 255) / 256;
         split_rows_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
     }
-    {
-        size_t tiles = batch * ((n + 31) / 32) * (kpad / 32);
-        split_transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad, flag);
-    }
-    count_launch(2);
+    count_launch();
     TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
 
+// B [batch][k][n] row-major -> hi/lo [batch][n][kpad] (K-major); raises *flag on Inf/NaN
+int gemm_tc_split_b(const float* b, float* b_hi, float* b_lo, size_t batch, size_t k, size_t n, int* flag,
+                    cudaStream_t s) {
+    using namespace tc;
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
+    const size_t kpad = gemm_tc_kpad(k);
+    if (batch * n * kpad == 0) return TRN_OK;
+    const unsigned cap = (unsigned)cx->sm_count * 8;
+    size_t tiles = batch * ((n + 31) / 32) * (kpad / 32);
+    split_transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad, flag);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+// C[b] = A[b] * B[b] from pre-split operands.  The tensor-core kernel returns at once when *flag != 0.
+int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* c, size_t batch,
+                 size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s) {
+    using namespace tc;
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
+    if (batch == 0 || m == 0 || n == 0) return TRN_OK;
+    const size_t kpad = gemm_tc_kpad(k);
     CUtensorMap map_ah, map_al, map_bh, map_bl;
     TRN_TRY(make_map(&map_ah, a_hi, batch, m, kpad, BM));
     TRN_TRY(make_map(&map_al, a_lo, batch, m, kpad, BM));
@@ -539,9 +549,36 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     p.tiles_m = (uint32_t)((m + BM - 1) / BM);
     p.tiles_n = (uint32_t)((n + BN - 1) / BN);
     p.batch = (uint32_t)batch;
+    return terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s)
+                      : launch<1>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s);
+}
+
+int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int terms,
+                   cudaStream_t s) {
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
+    if (batch == 0 || m == 0 || n == 0) return TRN_OK;
+    const size_t kpad = gemm_tc_kpad(k);
+    const size_t a_elems = batch * m * kpad, b_elems = batch * n * kpad;
+
+    // scratch: A_hi, A_lo, Bt_hi, Bt_lo (stream-ordered pool; stays cached between calls)
+    float* scratch = nullptr;
+    TRN_TRY(scratch_alloc((void**)&scratch, (2 * a_elems + 2 * b_elems) * sizeof(float) + 256, s));
+    float* a_hi = scratch;
+    float* a_lo = a_hi + a_elems;
+    float* b_hi = a_lo + a_elems;
+    float* b_lo = b_hi + b_elems;
+    int* flag = reinterpret_cast<int*>(b_lo + b_elems);   // non-finite-input flag (see header)
+    TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+
+    if (g_profile) {
+        if (!g_ev[0]) for (auto& e : g_ev) TRN_CUDA(cudaEventCreate(&e));
+        TRN_CUDA(cudaEventRecord(g_ev[0], s));
+    }
+    int st = gemm_tc_split_a(a, a_hi, a_lo, batch, m, k, flag, s);
+    if (st == TRN_OK) st = gemm_tc_split_b(b, b_hi, b_lo, batch, k, n, flag, s);
     if (g_profile) TRN_CUDA(cudaEventRecord(g_ev[1], s));
-    int st = terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s)
-                        : launch<1>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s);
+    if (st == TRN_OK) st = gemm_tc_main(a_hi, a_lo, b_hi, b_lo, c, batch, m, k, n, terms, flag, s);
     if (g_profile) {
         TRN_CUDA(cudaEventRecord(g_ev[2], s));
         g_ev_valid = true;
