@@ -185,6 +185,8 @@ def run_ours(args) -> int:
     import trueno_b200 as trn
     from trueno_b200 import parallel as par
 
+    # NCCL's version banner goes to stdout by default: keep stdout to the ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, local_rank, world = par.init_distributed()
     if world != args.gpus and world > 1:
         args.gpus = world

@@ -1,0 +1,113 @@
+"""Multi-GPU parity worker: run under torchrun (one rank per GPU, NCCL).  Every rank regenerates the
+SAME global inputs from a seed, computes its shard through the C-ABI `_dev` kernels + the exchange
+steps of trueno_b200/parallel.py, and checks the result against the CPU oracle on the global input
+(slices + all_reduce / all_gather; head ranges; row blocks).  Exit code 0 == pass."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+f32 = np.float32
+
+
+def main() -> int:
+    import oracle
+    import trueno_b200 as trn
+    from oracle import SCALAR
+    from trueno_b200 import parallel as par
+
+    rank, local_rank, world = par.init_distributed("nccl")
+    torch.cuda.set_device(local_rank)
+    trn.check(trn.lib.trn_cuda_init(local_rank))
+    dev = torch.device("cuda", local_rank)
+    orc = oracle.get()
+    st = par.current_stream_handle()
+    rng = np.random.default_rng(2026)
+
+    # ---- config 4 (scaled to what the oracle finishes in seconds): sliced reductions -------------------
+    for n in (1 << 22, (1 << 22) + 37, 1001):
+        a = rng.uniform(-1, 1, n).astype(f32)
+        b = rng.uniform(-1, 1, n).astype(f32)
+        # planted maximum in the LAST rank's slice and an equal duplicate later in the same slice,
+        # plus an equal value in slice 0 at a lower index: the lowest global index must win
+        sh_last = par.shard_range(n, world - 1, world, align=4)
+        big = f32(a.max() + 1)
+        a[sh_last.start + 3] = big
+        a[min(sh_last.start + 11, n - 1)] = big
+        a[5] = big
+        a[7] = f32(a.min() - 1)
+        sh = par.shard_range(n, rank, world, align=4)
+        va = par.ShardedVector(torch.from_numpy(a[sh.start:sh.start + sh.count]).to(dev), sh)
+        vb = par.ShardedVector(torch.from_numpy(b[sh.start:sh.start + sh.count]).to(dev), sh)
+        tdot, adot = orc.f64_dot(a, b)
+        tsum, asum = orc.f64_sum(a)
+        assert abs(float(va.dot(vb)) - tdot) <= 1e-5 * adot
+        assert abs(float(va.sum()) - tsum) <= 1e-5 * asum
+        tn = float(np.sqrt(np.sum(a.astype(np.float64) ** 2)))
+        assert abs(float(va.norm_l2()) - tn) <= 1e-5 * tn
+        assert int(va.argmax()) == orc.argmax(a, backend=SCALAR) == 5
+        assert int(va.argmin()) == orc.argmin(a, backend=SCALAR) == 7
+        assert float(va.max()) == float(big)
+
+    # ---- config 3 (scaled): batch x head ranges, no collective; every rank checks its own heads ---------
+    B, H, m, k, n = 2, 8, 256, 128, 384
+    A = rng.uniform(-1, 1, (B * H, m, k)).astype(f32)
+    Bm = rng.uniform(-1, 1, (B * H, k, n)).astype(f32)
+    hs = par.shard_range(B * H, rank, world)
+    dA = torch.from_numpy(A[hs.start:hs.start + hs.count]).to(dev).contiguous()
+    dB = torch.from_numpy(Bm[hs.start:hs.start + hs.count]).to(dev).contiguous()
+    dC = torch.empty(hs.count, m, n, device=dev)
+    trn.check(trn.lib.trn_batched_matmul_f32_dev(dA.data_ptr(), dA.numel(), dB.data_ptr(), dB.numel(), dC.data_ptr(),
+                                                 hs.count, m, k, n, st))
+    torch.cuda.synchronize()
+    got = dC.cpu().numpy()
+    for i in range(hs.count):
+        h = hs.start + i
+        truth = A[h].astype(np.float64) @ Bm[h].astype(np.float64)
+        scale = np.abs(A[h]).astype(np.float64) @ np.abs(Bm[h]).astype(np.float64)
+        assert np.all(np.abs(got[i] - truth) <= 1e-5 * scale)
+
+    # ---- config 5 (scaled): row-sharded softmax / log_softmax / gelu, and row-block matmul with B replicated
+    rows, cols = 64, 32000
+    X = (rng.standard_normal((rows, cols)) * 4).astype(f32)
+    rs = par.shard_range(rows, rank, world)
+    dX = torch.from_numpy(X[rs.start:rs.start + rs.count]).to(dev).contiguous()
+    dY = torch.empty_like(dX)
+    trn.check(trn.lib.trn_softmax_rows_f32_dev(dX.data_ptr(), dY.data_ptr(), rs.count, cols, st))
+    torch.cuda.synchronize()
+    want = orc.softmax_rows(X[rs.start:rs.start + rs.count], rs.count, cols, backend=SCALAR)
+    assert np.all(np.abs(dY.cpu().numpy() - want) <= 1e-6 + 2e-4 * want)
+    trn.check(trn.lib.trn_gelu_f32_dev(dX.data_ptr(), dX.numel(), dY.data_ptr(), st))
+    torch.cuda.synchronize()
+    gw = orc.gelu(X[rs.start:rs.start + rs.count].reshape(-1), backend=SCALAR)
+    assert np.max(np.abs(dY.cpu().numpy().reshape(-1) - gw)) <= 2e-6
+
+    M, K, N = 1024, 512, 768
+    A2 = rng.uniform(-1, 1, (M, K)).astype(f32)
+    B2 = rng.uniform(-1, 1, (K, N)).astype(f32)
+    ms = par.shard_range(M, rank, world, align=128)
+    dA2 = torch.from_numpy(A2[ms.start:ms.start + ms.count]).to(dev).contiguous()
+    dB2 = torch.from_numpy(B2).to(dev)
+    dC2 = torch.empty(ms.count, N, device=dev)
+    trn.check(trn.lib.trn_matmul_f32_dev(dA2.data_ptr(), ms.count, K, dB2.data_ptr(), K, N, dC2.data_ptr(), st))
+    # gather the row blocks (optional step of §8e) and compare the WHOLE product on every rank
+    blocks = [torch.empty(par.shard_range(M, r, world, align=128).count, N, device=dev) for r in range(world)]
+    dist.all_gather(blocks, dC2)
+    full = torch.cat(blocks).cpu().numpy()
+    truth = A2.astype(np.float64) @ B2.astype(np.float64)
+    scale = np.abs(A2).astype(np.float64) @ np.abs(B2).astype(np.float64)
+    assert np.all(np.abs(full - truth) <= 1e-5 * scale)
+
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_worker ok: world={world}, launches={trn.launch_count()}")
+    dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

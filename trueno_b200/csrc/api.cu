@@ -413,16 +413,18 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
 
     const size_t na = batch * m * k, nb = batch * k * n, nc = batch * m * n;
     const size_t a_split = batch * m * kpad, b_split = batch * n * kpad;
+    // every sub-buffer starts on a 256-byte boundary (TMA needs 16-byte aligned tensor bases)
+    auto pad64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
     float* dev = nullptr;
-    TRN_TRY(scratch_alloc((void**)&dev, (na + nb + nc + 2 * a_split + 2 * b_split) * sizeof(float) + 256, s_main));
+    TRN_TRY(scratch_alloc((void**)&dev, (pad64(na) + pad64(nb) + pad64(nc) + 2 * pad64(a_split) + 2 * pad64(b_split)) * sizeof(float) + 256, s_main));
     float* da = dev;
-    float* db = da + na;
-    float* dc = db + nb;
-    float* a_hi = dc + nc;
-    float* a_lo = a_hi + a_split;
-    float* b_hi = a_lo + a_split;
-    float* b_lo = b_hi + b_split;
-    int* flag = reinterpret_cast<int*>(b_lo + b_split);
+    float* db = da + pad64(na);
+    float* dc = db + pad64(nb);
+    float* a_hi = dc + pad64(nc);
+    float* a_lo = a_hi + pad64(a_split);
+    float* b_hi = a_lo + pad64(a_split);
+    float* b_lo = b_hi + pad64(b_split);
+    int* flag = reinterpret_cast<int*>(b_lo + pad64(b_split));
     TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s_main));
 
     std::vector<Event> up(units + 1), done(units);

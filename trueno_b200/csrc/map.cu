@@ -6,14 +6,17 @@
 // tanh-form GELU with libm tanhf) using CUDA's accurate expf/tanhf and IEEE division — no
 // fast-math intrinsics on the parity path.
 //
-// HBM-bound streaming: 128-bit loads/stores, 4 vectors in flight per thread per input, grid-stride
-// over a persistent grid.  Algorithmic bytes per element: add/mul 12 B, sigmoid/gelu 8 B.
+// HBM-bound streaming: 128-bit loads/stores, ONE 8 KiB tile per CTA on a flat (non-persistent) grid.
+// Measured on B200 (scripts/exp/exp_map.cu, 131 M elements): flat grids reach 6.6-6.9 TB/s where a
+// persistent one-wave grid-stride loop of the same body reaches 5.0-6.5 TB/s — the block scheduler
+// keeps every SM's load queue full while persistent CTAs drift into lock-step load/compute phases.
+// Algorithmic bytes per element: add/mul 12 B, sigmoid/gelu 8 B.
 #include "common.cuh"
 
 namespace trn {
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 2;   // float4 per thread per input: 8 KiB tiles
 
 template <int OP>
 __device__ __forceinline__ float apply(float x, float y) {
@@ -48,10 +51,8 @@ map_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
         const float4* a4 = reinterpret_cast<const float4*>(a);
         const float4* b4 = reinterpret_cast<const float4*>(b);
         float4* o4 = reinterpret_cast<float4*>(out);
-        constexpr int tile = kThreads * kUnroll;
-        const size_t full_tiles = nvec / tile;
-        for (size_t t = blockIdx.x; t < full_tiles; t += gridDim.x) {
-            const size_t base = t * tile + threadIdx.x;
+        const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+        if (base + (kUnroll - 1) * kThreads < nvec) {   // full tile (all but the last CTA)
             float4 x[kUnroll], y[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(a4 + base + u * kThreads);
@@ -61,20 +62,27 @@ map_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) st_stream(o4 + base + u * kThreads, apply4<OP>(x[u], BIN ? y[u] : x[u]));
+        } else {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const size_t v = base + u * kThreads;
+                if (v < nvec) {
+                    const float4 x = ld_stream(a4 + v);
+                    st_stream(o4 + v, apply4<OP>(x, BIN ? ld_stream(b4 + v) : x));
+                }
+            }
         }
-        const size_t tail0 = full_tiles * tile;
-        for (size_t v = tail0 + (size_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += (size_t)gridDim.x * kThreads) {
-            float4 x = ld_stream(a4 + v);
-            float4 y = BIN ? ld_stream(b4 + v) : x;
-            st_stream(o4 + v, apply4<OP>(x, y));
-        }
-        if (blockIdx.x == 0) {
-            size_t i = (nvec << 2) + threadIdx.x;
+        if (blockIdx.x == 0) {   // scalar tail (n % 4 elements)
+            const size_t i = (nvec << 2) + threadIdx.x;
             if (i < n) out[i] = apply<OP>(a[i], BIN ? b[i] : 0.f);
         }
     } else {
-        for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
-            out[i] = apply<OP>(ld_stream(a + i), BIN ? ld_stream(b + i) : 0.f);
+        const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll * 4) + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < kUnroll * 4; ++u) {
+            const size_t i = base + (size_t)u * kThreads;
+            if (i < n) out[i] = apply<OP>(ld_stream(a + i), BIN ? ld_stream(b + i) : 0.f);
+        }
     }
 }
 
@@ -86,17 +94,13 @@ int launch_map(Map op, const float* a, const float* b, float* out, size_t n, cud
     if (n == 0) return TRN_OK;
     const bool bin = op == Map::Add || op == Map::Mul;
     const bool vec = aligned16(a) && aligned16(out) && (!bin || aligned16(b));
-    size_t tiles = (n / 4 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-    // exactly one resident wave: grid = SMs x (CTAs the kernel really fits per SM), so there is no tail wave
+    // one CTA per 8 KiB tile; the scalar path covers the same 2048 elements per CTA
+    const size_t per_cta = (size_t)kThreads * kUnroll * 4;
+    const size_t tiles = (n + per_cta - 1) / per_cta;
+    if (tiles > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "vector of %zu elements exceeds the launch grid", n);
+    const unsigned grid = (unsigned)tiles;
 #define LAUNCH(OP)                                                                    \
     do {                                                                              \
-        static int per_sm = 0;                                                        \
-        if (!per_sm) {                                                                \
-            TRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_kernel<OP, true>, kThreads, 0)); \
-            if (per_sm < 1) per_sm = 1;                                               \
-        }                                                                             \
-        size_t cap = (size_t)c->sm_count * per_sm;                                    \
-        int grid = (int)(tiles < cap ? (tiles ? tiles : 1) : cap);                    \
         if (vec) map_kernel<OP, true><<<grid, kThreads, 0, s>>>(a, b, out, n);         \
         else     map_kernel<OP, false><<<grid, kThreads, 0, s>>>(a, b, out, n);        \
     } while (0)
