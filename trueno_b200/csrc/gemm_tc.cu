@@ -40,6 +40,8 @@
 // Roofline: tensor pipe.  Algorithmic work 2*m*n*k flop; the pipe executes 3x that in TF32.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace trn {
@@ -47,20 +49,24 @@ namespace tc {
 
 constexpr int BM = 128;   // UMMA M (cta_group::1)
 constexpr int BN = 256;   // UMMA N
-constexpr int BK = 32;    // floats per stage row = 128 bytes = one SWIZZLE_128B span
+constexpr int BK = 32;    // K padding granularity of the split operands (Kpad % 32 == 0)
 constexpr int UMMA_K = 8; // kind::tf32: 32 bytes of K per instruction
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kEpiWarps = 8;
-constexpr uint32_t kChunkKB = 4;  // k-blocks (of 32) accumulated in TMEM before draining to registers
-constexpr uint32_t kABytes = BM * BK * 4;  // 16 KiB
-constexpr uint32_t kBBytes = BN * BK * 4;  // 32 KiB
+constexpr uint32_t kChunkK = 128;  // K extent accumulated in TMEM before draining to registers
 constexpr uint32_t kTmemCols = 512;        // 2 accumulator stages x 256 columns
 
-template <int TERMS>
+// SBK = floats of K per pipeline stage: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B).
+// 3xTF32 moves hi+lo of both operands per stage, so SBK = 16 buys a 4-deep ring (4 x 48 KiB) where SBK = 32
+// only fits 2 x 96 KiB: with 3 stages in flight instead of 1 the ring tolerates ~2300 cycles of load latency.
+template <int TERMS, int SBK>
 struct Cfg {
     static constexpr int kOperands = TERMS == 3 ? 2 : 1;  // hi (+ lo)
+    static constexpr uint32_t kABytes = BM * SBK * 4;
+    static constexpr uint32_t kBBytes = BN * SBK * 4;
     static constexpr uint32_t kStageBytes = kOperands * (kABytes + kBBytes);
-    static constexpr int kStages = TERMS == 3 ? 2 : 4;
+    static constexpr int kStages = (TERMS == 3 ? 2 : 4) * (32 / SBK);
+    static constexpr uint32_t kChunkKB = kChunkK / SBK;       // k-blocks per TMEM partial sum
     static constexpr uint32_t kStoreBytes = kEpiWarps * 4096;  // one 32x32 f32 staging block per epilogue warp
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -112,11 +118,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
-//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups)
-//   [46,48) version = 1 (sm_100)   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
+//   [32,46) stride byte offset >> 4 (bytes between 8-row groups)
+//   [46,48) version = 1 (sm_100)   [61,64) layout type
+// SBK = 32: rows of 128 B, SWIZZLE_128B (type 2), 1024 B between 8-row groups;
+// SBK = 16: rows of  64 B, SWIZZLE_64B  (type 4),  512 B between 8-row groups.
+template <int SBK>
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
+    constexpr uint64_t sbo = (8 * SBK * 4) >> 4;
+    constexpr uint64_t type = SBK == 32 ? 2ull : 4ull;
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
@@ -148,12 +158,13 @@ __device__ __forceinline__ void tile_coords(uint32_t t, const Params& p, uint32_
     nt = in_group / gsize;
 }
 
-template <int TERMS>
+template <int TERMS, int SBK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const __grid_constant__ CUtensorMap map_c, const Params p) {
-    using C = Cfg<TERMS>;
+    using C = Cfg<TERMS, SBK>;
+    constexpr uint32_t kABytes = C::kABytes, kBBytes = C::kBBytes, kChunkKB = C::kChunkKB;
     if (*p.nonfinite_flag != 0) return;  // Inf/NaN in the inputs: the SIMT kernel takes over (grid-uniform)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries
@@ -199,7 +210,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::kStageBytes;
                     mbar_expect_tx(full_bar(stage), C::kStageBytes);
-                    const int k0 = (int)(kb * BK);
+                    const int k0 = (int)(kb * SBK);
                     tma_load_3d(sa, &map_a_hi, full_bar(stage), k0, m0, (int)b);
                     tma_load_3d(sa + kABytes, &map_b_hi, full_bar(stage), k0, n0, (int)b);
                     if (TERMS == 3) {
@@ -230,15 +241,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     const uint32_t a_hi = sa, b_hi = sa + kABytes;
                     const uint32_t a_lo = sa + kABytes + kBBytes, b_lo = sa + 2 * kABytes + kBBytes;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                    for (int k = 0; k < SBK / UMMA_K; ++k) {
                         const uint32_t koff = k * UMMA_K * 4;  // 32 bytes along K inside the swizzle span
                         const uint32_t accum = (in_chunk | (uint32_t)k) != 0;  // first MMA of a chunk overwrites
                         if (TERMS == 3) {
-                            umma_tf32(d, make_desc_k_sw128(a_lo + koff), make_desc_k_sw128(b_hi + koff), idesc, accum);
-                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_lo + koff), idesc, 1u);
-                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_hi + koff), idesc, 1u);
+                            umma_tf32(d, make_desc_k<SBK>(a_lo + koff), make_desc_k<SBK>(b_hi + koff), idesc, accum);
+                            umma_tf32(d, make_desc_k<SBK>(a_hi + koff), make_desc_k<SBK>(b_lo + koff), idesc, 1u);
+                            umma_tf32(d, make_desc_k<SBK>(a_hi + koff), make_desc_k<SBK>(b_hi + koff), idesc, 1u);
                         } else {
-                            umma_tf32(d, make_desc_k_sw128(a_hi + koff), make_desc_k_sw128(b_hi + koff), idesc, accum);
+                            umma_tf32(d, make_desc_k<SBK>(a_hi + koff), make_desc_k<SBK>(b_hi + koff), idesc, accum);
                         }
                     }
                     umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
@@ -433,9 +444,9 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// [batch][rows][kpad] f32, box = {BK, box_rows, 1}, SWIZZLE_128B
+// [batch][rows][kpad] f32, box = {box_cols, box_rows, 1}; swizzle span = box_cols * 4 bytes (128 or 64)
 static int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows,
-                    uint32_t box_cols = BK) {
+                    uint32_t box_cols) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     cuuint64_t dims[3] = {kpad, rows, batch};
@@ -443,24 +454,25 @@ static int make_map(CUtensorMap* map, const float* base, size_t batch, size_t ro
     cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return TRN_OK;
 }
 
-template <int TERMS>
+template <int TERMS, int SBK>
 static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                   const CUtensorMap& mc, const Params& p, int sm_count, cudaStream_t s) {
-    using C = Cfg<TERMS>;
+    using C = Cfg<TERMS, SBK>;
     static bool attr_set = false;
     if (!attr_set) {
-        TRN_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        TRN_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<TERMS, SBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         attr_set = true;
     }
     const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
     const uint32_t grid = total < (uint32_t)sm_count ? total : (uint32_t)sm_count;
-    gemm_tf32_kernel<TERMS><<<grid, kThreads, C::kSmemBytes, s>>>(ah, al, bh, bl, mc, p);
+    gemm_tf32_kernel<TERMS, SBK><<<grid, kThreads, C::kSmemBytes, s>>>(ah, al, bh, bl, mc, p);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -528,11 +540,15 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
     if (!cx) return TRN_GPU_ERROR;
     if (batch == 0 || m == 0 || n == 0) return TRN_OK;
     const size_t kpad = gemm_tc_kpad(k);
+    // K extent of one pipeline stage (see Cfg): 16 for 3xTF32 (4-deep ring), 32 for the 1xTF32 probe.
+    // TRN_GEMM_STAGE_K=32 restores the 2 x 96 KiB ring for A/B measurements.
+    static const int stage_k_3x = [] { const char* e = getenv("TRN_GEMM_STAGE_K"); return (e && atoi(e) == 32) ? 32 : 16; }();
+    const uint32_t sbk = terms == 3 ? (uint32_t)stage_k_3x : 32u;
     CUtensorMap map_ah, map_al, map_bh, map_bl;
-    TRN_TRY(make_map(&map_ah, a_hi, batch, m, kpad, BM));
-    TRN_TRY(make_map(&map_al, a_lo, batch, m, kpad, BM));
-    TRN_TRY(make_map(&map_bh, b_hi, batch, n, kpad, BN));
-    TRN_TRY(make_map(&map_bl, b_lo, batch, n, kpad, BN));
+    TRN_TRY(make_map(&map_ah, a_hi, batch, m, kpad, BM, sbk));
+    TRN_TRY(make_map(&map_al, a_lo, batch, m, kpad, BM, sbk));
+    TRN_TRY(make_map(&map_bh, b_hi, batch, n, kpad, BN, sbk));
+    TRN_TRY(make_map(&map_bl, b_lo, batch, n, kpad, BN, sbk));
 
     // C as a [batch][m][n] tensor with 32x32 store boxes — only when its rows are 16-byte aligned
     CUtensorMap map_c = map_ah;
@@ -545,12 +561,14 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
     p.nonfinite_flag = flag;
     p.m = (uint32_t)m;
     p.n = (uint32_t)n;
-    p.num_kb = (uint32_t)(kpad / BK);
+    p.num_kb = (uint32_t)(kpad / sbk);
     p.tiles_m = (uint32_t)((m + BM - 1) / BM);
     p.tiles_n = (uint32_t)((n + BN - 1) / BN);
     p.batch = (uint32_t)batch;
-    return terms == 3 ? launch<3>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s)
-                      : launch<1>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s);
+    if (terms == 3)
+        return sbk == 16 ? launch<3, 16>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s)
+                         : launch<3, 32>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s);
+    return launch<1, 32>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s);
 }
 
 int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int terms,
