@@ -357,72 +357,107 @@ __device__ __forceinline__ bool split_tf32(float x, float& hi, float& lo) {
     return false;
 }
 
-// rows x k (row-major, per batch) -> hi/lo [rows x kpad]
+// The split kernels run on flat grids (one tile per CTA): measured on B200, flat streaming grids reach the
+// HBM roofline where persistent grid-stride loops of the same body stay 10-25 % below it (scripts/exp/exp_map.cu).
+
+// rows x k (row-major, per batch) -> hi/lo [rows x kpad]; 2048 elements per CTA
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
                   size_t rows_total, size_t k, size_t kpad, int* __restrict__ flag) {
     const size_t total = rows_total * kpad;
     bool bad = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / kpad, c = i - r * kpad;
-        float h = 0.f, l = 0.f;
-        if (c < k) bad |= split_tf32(ld_stream(in + r * k + c), h, l);
-        hi[i] = h;
-        lo[i] = l;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const size_t i = (size_t)blockIdx.x * 2048 + u * 256 + threadIdx.x;
+        if (i < total) {
+            const size_t r = i / kpad, c = i - r * kpad;
+            float h = 0.f, l = 0.f;
+            if (c < k) bad |= split_tf32(ld_stream(in + r * k + c), h, l);
+            hi[i] = h;
+            lo[i] = l;
+        }
     }
     if (bad) *flag = 1;
 }
-// 4-wide variant for k % 4 == 0 (kpad is always a multiple of 32)
+// 4-wide variant for k % 4 == 0 (kpad is always a multiple of 32); 512 float4 per CTA
 __global__ void __launch_bounds__(256)
 split_rows_vec_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
                       size_t rows_total, size_t k, size_t kpad, int* __restrict__ flag) {
     const size_t kv = k >> 2, kpv = kpad >> 2;
     const size_t total = rows_total * kpv;
     bool bad = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / kpv, c = i - r * kpv;
-        float4 h = make_float4(0, 0, 0, 0), l = h;
-        if (c < kv) {
-            const float4 x = ld_stream(reinterpret_cast<const float4*>(in + r * k) + c);
-            bad |= split_tf32(x.x, h.x, l.x); bad |= split_tf32(x.y, h.y, l.y);
-            bad |= split_tf32(x.z, h.z, l.z); bad |= split_tf32(x.w, h.w, l.w);
+    float4 x[2];
+    size_t idx[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        idx[u] = (size_t)blockIdx.x * 512 + u * 256 + threadIdx.x;
+        const size_t r = idx[u] / kpv, c = idx[u] - r * kpv;
+        live[u] = idx[u] < total && c < kv;
+        x[u] = live[u] ? ld_stream(reinterpret_cast<const float4*>(in + r * k) + c) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        if (idx[u] < total) {
+            float4 h = make_float4(0, 0, 0, 0), l = h;
+            if (live[u]) {
+                bad |= split_tf32(x[u].x, h.x, l.x); bad |= split_tf32(x[u].y, h.y, l.y);
+                bad |= split_tf32(x[u].z, h.z, l.z); bad |= split_tf32(x[u].w, h.w, l.w);
+            }
+            st_stream(reinterpret_cast<float4*>(hi) + idx[u], h);
+            st_stream(reinterpret_cast<float4*>(lo) + idx[u], l);
         }
-        reinterpret_cast<float4*>(hi)[i] = h;
-        reinterpret_cast<float4*>(lo)[i] = l;
     }
     if (bad) *flag = 1;
 }
-// B [batch][k][n] row-major -> hi/lo [batch][n][kpad] (transposed through a 32x33 smem tile)
+// B [batch][k][n] row-major -> hi/lo [batch][n][kpad]: one 64(k) x 64(n) tile per CTA through shared memory,
+// 128-bit accesses on the write side always and on the read side when rows of B are 16-byte aligned (VEC).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
                        size_t batch, size_t k, size_t n, size_t kpad, int* __restrict__ flag) {
-    __shared__ float tile[32][33];
-    bool bad = false;
-    const size_t tiles_n = (n + 31) / 32, tiles_k = kpad / 32;
+    __shared__ float tile[64][65];   // [k][n]
+    const size_t tiles_n = (n + 63) / 64, tiles_k = (kpad + 63) / 64;
     const size_t per_batch = tiles_n * tiles_k;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (size_t t = blockIdx.x; t < per_batch * batch; t += gridDim.x) {
-        const size_t b = t / per_batch, r = t % per_batch;
-        const size_t tk = r / tiles_n, tn = r % tiles_n;
-        const float* src = in + b * k * n;
+    const size_t t = blockIdx.x;
+    const size_t b = t / per_batch, r = t % per_batch;
+    const size_t tk = r / tiles_n, tn = r % tiles_n;
+    const float* src = in + b * k * n;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            const size_t kk = tk * 32 + ty + i, nn = tn * 32 + tx;
-            tile[ty + i][tx] = (kk < k && nn < n) ? ld_stream(src + kk * n + nn) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            const size_t nn = tn * 32 + ty + i, kk = tk * 32 + tx;
-            if (nn < n) {
-                float h, l;
-                bad |= split_tf32(tile[tx][ty + i], h, l);
-                const size_t o = (b * n + nn) * kpad + kk;
-                hi[o] = h;
-                lo[o] = l;
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        const int kr = idx >> 4, c4 = (idx & 15) * 4;
+        const size_t kk = tk * 64 + kr, nn = tn * 64 + c4;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (kk < k) {
+            if (VEC) {
+                if (nn < n) v = ld_stream(reinterpret_cast<const float4*>(src + kk * n + nn));
+            } else {
+                if (nn < n) v.x = ld_stream(src + kk * n + nn);
+                if (nn + 1 < n) v.y = ld_stream(src + kk * n + nn + 1);
+                if (nn + 2 < n) v.z = ld_stream(src + kk * n + nn + 2);
+                if (nn + 3 < n) v.w = ld_stream(src + kk * n + nn + 3);
             }
         }
-        __syncthreads();
+        tile[kr][c4] = v.x; tile[kr][c4 + 1] = v.y; tile[kr][c4 + 2] = v.z; tile[kr][c4 + 3] = v.w;
+    }
+    __syncthreads();
+    bool bad = false;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        const int nr = idx >> 4, k4 = (idx & 15) * 4;
+        const size_t nn = tn * 64 + nr, kk = tk * 64 + k4;
+        if (nn < n && kk < kpad) {
+            float4 h, l;
+            bad |= split_tf32(tile[k4][nr], h.x, l.x);
+            bad |= split_tf32(tile[k4 + 1][nr], h.y, l.y);
+            bad |= split_tf32(tile[k4 + 2][nr], h.z, l.z);
+            bad |= split_tf32(tile[k4 + 3][nr], h.w, l.w);
+            const size_t o = (b * n + nn) * kpad + kk;
+            st_stream(reinterpret_cast<float4*>(hi + o), h);
+            st_stream(reinterpret_cast<float4*>(lo + o), l);
+        }
     }
     if (bad) *flag = 1;
 }
@@ -501,16 +536,11 @@ int gemm_tc_split_a(const float* a, float* a_hi, float* a_lo, size_t batch, size
     const size_t kpad = gemm_tc_kpad(k);
     const size_t a_elems = batch * m * kpad;
     if (a_elems == 0) return TRN_OK;
-    const unsigned cap = (unsigned)cx->sm_count * 8;
     const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0);
-    if (vec) {
-        size_t work = batch * m * (kpad / 4);
-        size_t blocks = (work + 255) / 256;
-        split_rows_vec_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
-    } else {
-        size_t blocks = (a_elems + 255) / 256;
-        split_rows_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
-    }
+    const size_t blocks = vec ? (a_elems / 4 + 511) / 512 : (a_elems + 2047) / 2048;
+    if (blocks > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "operand of %zu elements exceeds the launch grid", a_elems);
+    if (vec) split_rows_vec_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
+    else     split_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -524,9 +554,11 @@ int gemm_tc_split_b(const float* b, float* b_hi, float* b_lo, size_t batch, size
     if (!cx) return TRN_GPU_ERROR;
     const size_t kpad = gemm_tc_kpad(k);
     if (batch * n * kpad == 0) return TRN_OK;
-    const unsigned cap = (unsigned)cx->sm_count * 8;
-    size_t tiles = batch * ((n + 31) / 32) * (kpad / 32);
-    split_transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad, flag);
+    const size_t tiles = batch * ((n + 63) / 64) * ((kpad + 63) / 64);
+    if (tiles > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "operand of %zu tiles exceeds the launch grid", tiles);
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(b) & 15u) == 0);
+    if (vec) split_transpose_kernel<true><<<(unsigned)tiles, 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad, flag);
+    else     split_transpose_kernel<false><<<(unsigned)tiles, 256, 0, s>>>(b, b_hi, b_lo, batch, k, n, kpad, flag);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
