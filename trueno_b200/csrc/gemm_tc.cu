@@ -145,11 +145,11 @@ struct Params {
 
 // Tile order: batch-major, then groups of 16 m-tiles, n fastest-but-one inside a group, so CTAs
 // that run concurrently share A row-panels and B column-panels in L2.
+template <uint32_t G = 16>
 __device__ __forceinline__ void tile_coords(uint32_t t, const Params& p, uint32_t& b, uint32_t& mt, uint32_t& nt) {
     const uint32_t per_batch = p.tiles_m * p.tiles_n;
     b = t / per_batch;
     uint32_t r = t % per_batch;
-    constexpr uint32_t G = 16;
     const uint32_t group = r / (G * p.tiles_n);
     const uint32_t first_m = group * G;
     const uint32_t gsize = min(G, p.tiles_m - first_m);
@@ -338,6 +338,237 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// =====================================================================================================
+// CTA-pair kernel: tcgen05.mma.cta_group::2 — two SMs of one TPC compute one 256 x 256 tile.
+//
+// Each CTA of the 2-CTA cluster loads ITS 128 rows of A and ITS 128 of the tile's 256 B rows (n), i.e.
+// 32 KiB per 16-wide k-block instead of 48 KiB: one third less L2->SM traffic and a 6-deep ring in the
+// same shared memory (5 stages = 3840 MMA-cycles of loads in flight).  The leader CTA (cluster rank 0)
+// issues every MMA (M = 256, N = 256, K = 8; A/B descriptors name the leader's shared memory, the tensor
+// core reads the peer's at the same offsets) and the accumulator rows land in each CTA's own TMEM, so
+// both CTAs run the same two-level epilogue on their own 128 rows.
+// Synchronisation: TMA loads of both CTAs complete_tx on the LEADER's full barrier; tcgen05.commit
+// multicasts the "stage free" / "accumulator full" arrivals to both CTAs; the epilogue warps of both CTAs
+// arrive on the leader's "accumulator empty" barrier through the cluster shared window.
+// =====================================================================================================
+namespace pair {
+constexpr int SBK = 16;
+constexpr uint32_t kABytes = BM * SBK * 4;        // 8 KiB: this CTA's 128 rows of A
+constexpr uint32_t kBBytes = (BN / 2) * SBK * 4;  // 8 KiB: this CTA's 128 of the 256 B rows
+constexpr uint32_t kStageBytes = 2 * (kABytes + kBBytes);   // hi + lo: 32 KiB per CTA
+constexpr int kStages = 6;
+constexpr uint32_t kChunkKB = kChunkK / SBK;
+constexpr uint32_t kStoreBytes = kEpiWarps * 4096;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 + 256;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;       // clears the CTA-rank bit of a cluster shared address: the leader's copy
+}  // namespace pair
+
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrival delivered to the barrier at this offset in BOTH CTAs of the pair once the prior MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                        const __grid_constant__ CUtensorMap map_c, const Params p) {
+    using namespace pair;
+    if (*p.nonfinite_flag != 0) return;  // grid-uniform: both CTAs of every pair leave together
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t store_base = smem_base + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * kStageBytes + kStoreBytes);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const uint32_t pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const uint32_t total_tiles = p.tiles_m * p.tiles_n * p.batch;   // tiles_m counts 256-row pair tiles here
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 2 * kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {   // the same warp in both CTAs allocates the pair's TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();     // barriers of BOTH CTAs are initialised before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
+                uint32_t b, mt, nt;
+                tile_coords<8>(t, p, b, mt, nt);
+                const int m0 = (int)(mt * 2 * BM + rank * BM), n0 = (int)(nt * BN + rank * (BN / 2));
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * kStageBytes;
+                    const uint32_t lead_full = full_bar(stage) & kPeerMask;
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);   // both CTAs' bytes
+                    const int k0 = (int)(kb * SBK);
+                    tma_load_3d_pair(sa, &map_a_hi, lead_full, k0, m0, (int)b);
+                    tma_load_3d_pair(sa + kABytes, &map_b_hi, lead_full, k0, n0, (int)b);
+                    tma_load_3d_pair(sa + kABytes + kBBytes, &map_a_lo, lead_full, k0, m0, (int)b);
+                    tma_load_3d_pair(sa + 2 * kABytes + kBBytes, &map_b_lo, lead_full, k0, n0, (int)b);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(2 * BM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    const uint32_t in_chunk = kb % kChunkKB;
+                    if (in_chunk == 0) {
+                        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);   // both CTAs' epilogues have drained it
+                        tc_fence_after();
+                    }
+                    const uint32_t d = tmem_base + acc * BN;
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const bool chunk_end = in_chunk == kChunkKB - 1 || kb == p.num_kb - 1;
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint32_t a_hi = sa, b_hi = sa + kABytes;
+                        const uint32_t a_lo = sa + kABytes + kBBytes, b_lo = sa + 2 * kABytes + kBBytes;
+#pragma unroll
+                        for (int k = 0; k < SBK / UMMA_K; ++k) {
+                            const uint32_t koff = k * UMMA_K * 4;
+                            const uint32_t accum = (in_chunk | (uint32_t)k) != 0;
+                            umma_tf32_pair(d, make_desc_k<SBK>(a_lo + koff), make_desc_k<SBK>(b_hi + koff), idesc, accum);
+                            umma_tf32_pair(d, make_desc_k<SBK>(a_hi + koff), make_desc_k<SBK>(b_lo + koff), idesc, 1u);
+                            umma_tf32_pair(d, make_desc_k<SBK>(a_hi + koff), make_desc_k<SBK>(b_hi + koff), idesc, 1u);
+                        }
+                        umma_commit_pair(empty_bar(stage));
+                        if (chunk_end) umma_commit_pair(tmem_full_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (chunk_end && ++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9, both CTAs, own 128 rows) =====================
+        const uint32_t quad = warp & 3;
+        const uint32_t half = (warp - 2) >> 2;
+        const uint32_t num_chunks = (p.num_kb + kChunkKB - 1) / kChunkKB;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
+            uint32_t b, mt, nt;
+            tile_coords<8>(t, p, b, mt, nt);
+            float sum[128];
+            for (uint32_t ch = 0; ch < num_chunks; ++ch) {
+                mbar_wait(tmem_full_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * BN + half * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + j * 32, r);
+                    tmem_ld_wait();
+                    if (ch == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __uint_as_float(r[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __fadd_rn(sum[j * 32 + i], __uint_as_float(r[i]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(acc) & kPeerMask);   // on the leader's barrier
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            const uint32_t row0 = mt * 2 * BM + rank * BM + quad * 32;
+            const uint32_t row = row0 + lane;
+            const uint32_t col_base = nt * BN + half * 128;
+            if (p.tma_store) {
+                const uint32_t stage_addr = store_base + (uint32_t)(warp - 2) * 4096u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t dst = stage_addr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) * 16);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(dst), "f"(sum[j * 32 + 4 * q]),
+                                     "f"(sum[j * 32 + 4 * q + 1]), "f"(sum[j * 32 + 4 * q + 2]), "f"(sum[j * 32 + 4 * q + 3])
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && row0 < p.m && col_base + j * 32 < p.n) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     :: "l"(&map_c), "r"(stage_addr), "r"((int)(col_base + j * 32)), "r"((int)row0), "r"((int)b)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else if (row < p.m && col_base < p.n) {
+                float* crow = p.c + ((size_t)b * p.m + row) * p.n + col_base;
+#pragma unroll
+                for (int j = 0; j < 128; ++j)
+                    if (col_base + j < p.n) crow[j] = sum[j];
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+
+    // neither CTA may leave (or free TMEM) while its partner can still signal it or read its shared memory
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -572,6 +803,52 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
     if (!cx) return TRN_GPU_ERROR;
     if (batch == 0 || m == 0 || n == 0) return TRN_OK;
     const size_t kpad = gemm_tc_kpad(k);
+    // CTA-pair kernel (cta_group::2) for 3xTF32 whenever there are at least two 128-row tiles of C;
+    // TRN_GEMM_PAIR=0 forces the single-CTA kernel (A/B measurements, and its own parity tests).
+    static const int use_pair = [] { const char* e = getenv("TRN_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    if (terms == 3 && use_pair && m > (size_t)BM) {
+        CUtensorMap pa_h, pa_l, pb_h, pb_l, pc;
+        TRN_TRY(make_map(&pa_h, a_hi, batch, m, kpad, BM, pair::SBK));
+        TRN_TRY(make_map(&pa_l, a_lo, batch, m, kpad, BM, pair::SBK));
+        TRN_TRY(make_map(&pb_h, b_hi, batch, n, kpad, BN / 2, pair::SBK));
+        TRN_TRY(make_map(&pb_l, b_lo, batch, n, kpad, BN / 2, pair::SBK));
+        pc = pa_h;
+        const bool tma_store = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(c) & 15u) == 0);
+        if (tma_store) TRN_TRY(make_map(&pc, c, batch, m, n, 32, 32));
+        Params p;
+        p.c = c;
+        p.tma_store = tma_store ? 1u : 0u;
+        p.nonfinite_flag = flag;
+        p.m = (uint32_t)m;
+        p.n = (uint32_t)n;
+        p.num_kb = (uint32_t)(kpad / pair::SBK);
+        p.tiles_m = (uint32_t)((m + 2 * BM - 1) / (2 * BM));
+        p.tiles_n = (uint32_t)((n + BN - 1) / BN);
+        p.batch = (uint32_t)batch;
+        static bool attr_set = false;
+        if (!attr_set) {
+            TRN_CUDA(cudaFuncSetAttribute(gemm_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytes));
+            attr_set = true;
+        }
+        const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
+        const uint32_t max_pairs = (uint32_t)cx->sm_count / 2;
+        const uint32_t pairs = total < max_pairs ? total : max_pairs;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = pair::kSmemBytes;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TRN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_pair_kernel, pa_h, pa_l, pb_h, pb_l, pc, p));
+        count_launch();
+        return TRN_OK;
+    }
     // K extent of one pipeline stage (see Cfg): 16 for 3xTF32 (4-deep ring), 32 for the 1xTF32 probe.
     // TRN_GEMM_STAGE_K=32 restores the 2 x 96 KiB ring for A/B measurements.
     static const int stage_k_3x = [] { const char* e = getenv("TRN_GEMM_STAGE_K"); return (e && atoi(e) == 32) ? 32 : 16; }();
