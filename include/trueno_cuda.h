@@ -191,8 +191,10 @@ TRN_API int trn_get_gemm_engine(void);
 
 /* ---- live kernel timing (bench.py's roofline leg) -------------------------------------------
  * When enabled, the GEMM launcher brackets its operand pre-pass and its main tensor-core kernel
- * with CUDA events on the launching stream.  trn_profile_last_gemm() synchronises on those events
- * and returns the two durations of the most recent GEMM call (milliseconds).  Off by default. */
+ * with CUDA events on the launching stream (a ring of 64 event triples: no host synchronisation
+ * between calls).  trn_profile_enable(1) restarts the ring; trn_profile_last_gemm() synchronises
+ * on the newest event and returns the MEAN pre-pass / kernel durations (milliseconds) over the
+ * (at most 64 newest) GEMM calls recorded since.  Off by default. */
 TRN_API int trn_profile_enable(int on);
 TRN_API int trn_profile_last_gemm(float* prepass_ms, float* kernel_ms);
 

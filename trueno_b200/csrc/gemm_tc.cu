@@ -747,9 +747,13 @@ static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMa
 }  // namespace tc
 
 // ---- optional live timing of the pre-pass and the main kernel (trn_profile_*) -------------------------
+// A ring of event triples so a whole timed region of back-to-back calls can be profiled without a host sync
+// between them; trn_profile_last_gemm() averages over the calls recorded since trn_profile_enable(1).
+constexpr int kProfRing = 64;
 static bool g_profile = false;
-static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
-static bool g_ev_valid = false;
+static cudaEvent_t g_ev[kProfRing][3];
+static bool g_ev_created = false;
+static unsigned g_ev_count = 0;
 
 bool gemm_tc_supported(size_t m, size_t k, size_t n) {
     // 32-bit tile coordinates and TMA dimension limits; any m, n, k >= 1 otherwise
@@ -898,17 +902,22 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     int* flag = reinterpret_cast<int*>(b_lo + b_elems);   // non-finite-input flag (see header)
     TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
 
+    cudaEvent_t* ev = nullptr;
     if (g_profile) {
-        if (!g_ev[0]) for (auto& e : g_ev) TRN_CUDA(cudaEventCreate(&e));
-        TRN_CUDA(cudaEventRecord(g_ev[0], s));
+        if (!g_ev_created) {
+            for (auto& t : g_ev) for (auto& e : t) TRN_CUDA(cudaEventCreate(&e));
+            g_ev_created = true;
+        }
+        ev = g_ev[g_ev_count % kProfRing];
+        TRN_CUDA(cudaEventRecord(ev[0], s));
     }
     int st = gemm_tc_split_a(a, a_hi, a_lo, batch, m, k, flag, s);
     if (st == TRN_OK) st = gemm_tc_split_b(b, b_hi, b_lo, batch, k, n, flag, s);
-    if (g_profile) TRN_CUDA(cudaEventRecord(g_ev[1], s));
+    if (ev) TRN_CUDA(cudaEventRecord(ev[1], s));
     if (st == TRN_OK) st = gemm_tc_main(a_hi, a_lo, b_hi, b_lo, c, batch, m, k, n, terms, flag, s);
-    if (g_profile) {
-        TRN_CUDA(cudaEventRecord(g_ev[2], s));
-        g_ev_valid = true;
+    if (ev) {
+        TRN_CUDA(cudaEventRecord(ev[2], s));
+        ++g_ev_count;
     }
     // IEEE fallback for Inf/NaN inputs: runs only when the flag is set (checked on the device)
     if (st == TRN_OK) st = launch_gemm_simt(a, b, c, batch, m, k, n, s, flag);
@@ -921,15 +930,24 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
 extern "C" {
 int trn_profile_enable(int on) {
     trn::g_profile = on != 0;
+    if (on) trn::g_ev_count = 0;
     return TRN_OK;
 }
 int trn_profile_last_gemm(float* prepass_ms, float* kernel_ms) {
     using namespace trn;
-    if (!g_ev_valid) return fail(TRN_INVALID_INPUT, "no profiled GEMM call has been made");
-    TRN_CUDA(cudaEventSynchronize(g_ev[2]));
+    if (g_ev_count == 0) return fail(TRN_INVALID_INPUT, "no profiled GEMM call has been made");
+    const unsigned cnt = g_ev_count < (unsigned)kProfRing ? g_ev_count : (unsigned)kProfRing;
+    TRN_CUDA(cudaEventSynchronize(g_ev[(g_ev_count - 1) % kProfRing][2]));
     float a = 0.f, b = 0.f;
-    TRN_CUDA(cudaEventElapsedTime(&a, g_ev[0], g_ev[1]));
-    TRN_CUDA(cudaEventElapsedTime(&b, g_ev[1], g_ev[2]));
+    for (unsigned i = 0; i < cnt; ++i) {
+        float x = 0.f, y = 0.f;
+        TRN_CUDA(cudaEventElapsedTime(&x, g_ev[i][0], g_ev[i][1]));
+        TRN_CUDA(cudaEventElapsedTime(&y, g_ev[i][1], g_ev[i][2]));
+        a += x;
+        b += y;
+    }
+    a /= (float)cnt;
+    b /= (float)cnt;
     if (prepass_ms) *prepass_ms = a;
     if (kernel_ms) *kernel_ms = b;
     return TRN_OK;

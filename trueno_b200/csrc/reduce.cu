@@ -191,10 +191,22 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             float4 x[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(a4 + base + u * kThreads);
+            // fast path: one min/max tree over the 16 values (fmaxf/fminf drop NaNs, like the strict compare)
+            // and ONE test against the running best; the index bookkeeping runs only when a new best
+            // appears, which becomes rare after the first few tiles.
+            float m = MAX ? -INFINITY : INFINITY;
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const uint64_t e = (uint64_t)(base + u * kThreads) << 2;
-                visit(x[u].x, e); visit(x[u].y, e + 1); visit(x[u].z, e + 2); visit(x[u].w, e + 3);
+                const float m2 = MAX ? fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w))
+                                     : fminf(fminf(x[u].x, x[u].y), fminf(x[u].z, x[u].w));
+                m = MAX ? fmaxf(m, m2) : fminf(m, m2);
+            }
+            if (better<MAX>(m, best.v)) {
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {   // ascending index order: the first occurrence wins
+                    const uint64_t e = (uint64_t)(base + u * kThreads) << 2;
+                    visit(x[u].x, e); visit(x[u].y, e + 1); visit(x[u].z, e + 2); visit(x[u].w, e + 3);
+                }
             }
         }
         const size_t tail0 = full_tiles * kTileVec;
