@@ -37,6 +37,9 @@ FLOP_PER_STEP = 2.0 * M * K * N
 WORKLOAD = "Matrix::matmul 8192x8192x8192 f32 (BASELINE.json configs[1])"
 
 
+line_holder: list[str] = []   # the JSON line, emitted by main() once fd 1 points at the real stdout again
+
+
 def load_peaks() -> dict:
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -170,7 +173,7 @@ def run_reference(args) -> int:
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    line_holder.append(json.dumps(line))
     return 0
 
 
@@ -185,8 +188,6 @@ def run_ours(args) -> int:
     import trueno_b200 as trn
     from trueno_b200 import parallel as par
 
-    # NCCL's version banner goes to stdout by default: keep stdout to the ONE JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, local_rank, world = par.init_distributed()
     if world != args.gpus and world > 1:
         args.gpus = world
@@ -373,7 +374,7 @@ def run_ours(args) -> int:
             "clocks": clocks, "secondary": secondary,
             "device": trn.device_info()["name"],
         }
-        print(json.dumps(line))
+        line_holder.append(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -388,9 +389,22 @@ def main() -> int:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 behind Python's back (NCCL prints its
+    # version banner there) are pointed at stderr for the duration of the run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line_holder.clear()
+        rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in line_holder:
+        print(line)
+    sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":
