@@ -162,6 +162,14 @@ TRN_API int trn_argmin_f32_dev(const float* a, size_t n, uint64_t* out, float* o
  * and reports "no candidate" (all elements NaN or the identity) as index UINT64_MAX. */
 TRN_API int trn_argmax_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t* out, float* out_value, void* stream);
 TRN_API int trn_argmin_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t* out, float* out_value, void* stream);
+/* Same, packed for ONE all_gather: writes {value, GLOBAL index = slice_start + local index} (index UINT64_MAX =
+ * "no candidate"); slice_start == 0 carries the a[0] seed rule.  trn_arg_combine_f32_dev folds `count` gathered
+ * pairs (slice 0 first) into the whole-vector answer: NaN seed wins, else best value then lowest global index
+ * (NCCL has no arg-reduce: SURVEY.md 8e).  One kernel each; no host synchronisation. */
+typedef struct trn_arg_pair { float value; uint32_t reserved; uint64_t index; } trn_arg_pair;
+TRN_API int trn_argmax_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream);
+TRN_API int trn_argmin_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream);
+TRN_API int trn_arg_combine_f32_dev(const trn_arg_pair* pairs, size_t count, int is_max, uint64_t* out_idx, float* out_value, void* stream);
 TRN_API int trn_norm_l2_f32_dev(const float* a, size_t n, float* out, void* stream);
 /* sum of squares without the sqrt: the per-slice partial of a sharded norm_l2 (allreduce, then sqrt) */
 TRN_API int trn_sumsq_f32_dev(const float* a, size_t n, float* out, void* stream);

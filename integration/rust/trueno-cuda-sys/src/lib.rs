@@ -9,6 +9,15 @@ pub struct trn_buf {
     _private: [u8; 0],
 }
 
+/// (value, global index) of one slice of a sharded vector; index == u64::MAX means "no candidate"
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct trn_arg_pair {
+    pub value: f32,
+    pub reserved: u32,
+    pub index: u64,
+}
+
 pub const TRN_OK: c_int = 0;
 pub const TRN_SIZE_MISMATCH: c_int = 1;
 pub const TRN_INVALID_INPUT: c_int = 2;
@@ -70,6 +79,10 @@ extern "C" {
                                     stream: *mut c_void) -> c_int;
     pub fn trn_argmin_slice_f32_dev(a: *const f32, n: usize, first_slice: c_int, out: *mut u64, out_value: *mut f32,
                                     stream: *mut c_void) -> c_int;
+    pub fn trn_argmax_slice_pair_f32_dev(a: *const f32, n: usize, slice_start: u64, out: *mut trn_arg_pair, stream: *mut c_void) -> c_int;
+    pub fn trn_argmin_slice_pair_f32_dev(a: *const f32, n: usize, slice_start: u64, out: *mut trn_arg_pair, stream: *mut c_void) -> c_int;
+    pub fn trn_arg_combine_f32_dev(pairs: *const trn_arg_pair, count: usize, is_max: c_int, out_idx: *mut u64, out_value: *mut f32,
+                                   stream: *mut c_void) -> c_int;
     pub fn trn_norm_l2_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn trn_sumsq_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn trn_add_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;

@@ -500,3 +500,36 @@ def test_pipelined_host_gemm_nonfinite_block(trn):
     Cg = np.asarray(hc).reshape(m, n)
     assert np.isposinf(Cg[m // 2 + 5]).all()
     assert np.isfinite(np.delete(Cg, m // 2 + 5, 0)).all()
+
+
+def test_arg_combine_kernel_matches_rule(trn):
+    """trn_arg_combine_f32_dev (the device-side cross-slice pick) against the tensor statement of the same rule
+    (parallel.pick_arg, which the gloo tests pin against the scalar-backend oracle)."""
+    import torch
+    from trueno_b200 import parallel as par
+    NC = (1 << 64) - 1
+    cases = [
+        ([1.0, 5.0, 5.0, 2.0], [3, 70, 40, 90]),                 # tie -> lowest global index
+        ([float("nan"), 9.0, 1.0], [0, 50, 99]),                 # NaN seed from slice 0 wins
+        ([2.0, float("nan"), 7.0], [1, NC, 64]),                 # NaN / no-candidate entries never win
+        ([-float("inf"), -float("inf")], [0, NC]),               # nothing beats the identity -> slice 0's answer
+        ([3.0], [17]),
+        ([0.5] * 40, list(range(1000, 1040))),                    # more pairs than one warp pass
+    ]
+    for is_max in (True, False):
+        for vals, idxs in cases:
+            n = len(vals)
+            buf = np.zeros(n, dtype=[("v", "<f4"), ("r", "<u4"), ("i", "<u8")])
+            buf["v"], buf["i"] = vals, idxs
+            dp = torch.from_numpy(buf.view(np.int64).copy()).cuda()
+            oi = torch.zeros(1, dtype=torch.int64, device="cuda")
+            ov = torch.zeros(1, dtype=torch.float32, device="cuda")
+            trn.check(trn.lib.trn_arg_combine_f32_dev(dp.data_ptr(), n, int(is_max), oi.data_ptr(), ov.data_ptr(),
+                                                      par.current_stream_handle()))
+            torch.cuda.synchronize()
+            ti = torch.tensor([par.NO_CANDIDATE if i == NC else i for i in idxs], dtype=torch.int64)
+            wv, wi = par.pick_arg(torch.tensor(vals, dtype=torch.float32), ti, is_max)
+            got_i = int(oi.item()) & ((1 << 64) - 1)
+            want_i = NC if int(wi) == par.NO_CANDIDATE else int(wi)
+            assert got_i == want_i, (is_max, vals, idxs, got_i, want_i)
+            assert (np.isnan(float(ov)) and np.isnan(float(wv))) or float(ov) == float(wv)

@@ -61,6 +61,9 @@ _SIGNATURES = {
     "trn_argmax_f32_dev": [_vp, _sz, _vp, _vp, _vp], "trn_argmin_f32_dev": [_vp, _sz, _vp, _vp, _vp],
     "trn_argmax_slice_f32_dev": [_vp, _sz, C.c_int, _vp, _vp, _vp],
     "trn_argmin_slice_f32_dev": [_vp, _sz, C.c_int, _vp, _vp, _vp],
+    "trn_argmax_slice_pair_f32_dev": [_vp, _sz, C.c_uint64, _vp, _vp],
+    "trn_argmin_slice_pair_f32_dev": [_vp, _sz, C.c_uint64, _vp, _vp],
+    "trn_arg_combine_f32_dev": [_vp, _sz, C.c_int, _vp, _vp, _vp],
     "trn_norm_l2_f32_dev": [_vp, _sz, _vp, _vp], "trn_sumsq_f32_dev": [_vp, _sz, _vp, _vp],
     "trn_add_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp], "trn_mul_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp],
     "trn_sigmoid_f32_dev": [_vp, _sz, _vp, _vp], "trn_gelu_f32_dev": [_vp, _sz, _vp, _vp],

@@ -219,6 +219,21 @@ int trn_argmin_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t
     TRN_TRY(need_ctx());
     return launch_argreduce(0, a, n, out, out_value, resolve_stream(stream), first_slice != 0);
 }
+int trn_argmax_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream) {
+    TRN_TRY(check_nonempty_invalid(n));
+    TRN_TRY(need_ctx());
+    return launch_argreduce(1, a, n, nullptr, nullptr, resolve_stream(stream), slice_start == 0, slice_start, out);
+}
+int trn_argmin_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream) {
+    TRN_TRY(check_nonempty_invalid(n));
+    TRN_TRY(need_ctx());
+    return launch_argreduce(0, a, n, nullptr, nullptr, resolve_stream(stream), slice_start == 0, slice_start, out);
+}
+int trn_arg_combine_f32_dev(const trn_arg_pair* pairs, size_t count, int is_max, uint64_t* out_idx, float* out_value,
+                            void* stream) {
+    TRN_TRY(need_ctx());
+    return launch_arg_combine(pairs, count, is_max, out_idx, out_value, resolve_stream(stream));
+}
 int trn_add_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream) {
     TRN_TRY(check_same_len(na, nb));
     TRN_TRY(need_ctx());

@@ -79,7 +79,9 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
 // is_max: 1 argmax / 0 argmin.  out_idx / out_val may be null.  seed_rule 0: interior slice of a
 // sharded vector (no a[0] seed; "no candidate" -> index ~0).
 int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s,
-                     int seed_rule = 1);
+                     int seed_rule = 1, uint64_t index_base = 0, trn_arg_pair* out_pair = nullptr);
+int launch_arg_combine(const trn_arg_pair* pairs, size_t count, int is_max, uint64_t* out_idx, float* out_val,
+                       cudaStream_t s);
 
 enum class Map { Add, Mul, Sigmoid, Gelu };
 int launch_map(Map op, const float* a, const float* b, float* out, size_t n, cudaStream_t s);

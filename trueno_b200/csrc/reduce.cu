@@ -178,7 +178,8 @@ template <bool MAX, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ partial_v,
                  uint64_t* __restrict__ partial_i, unsigned* __restrict__ ticket,
-                 uint64_t* __restrict__ out_idx, float* __restrict__ out_val, int seed_rule) {
+                 uint64_t* __restrict__ out_idx, float* __restrict__ out_val, int seed_rule,
+                 uint64_t index_base, trn_arg_pair* __restrict__ out_pair) {
     Best best{MAX ? -INFINITY : INFINITY, kNoIndex};
     auto visit = [&](float x, uint64_t i) { if (better<MAX>(x, best.v)) { best.v = x; best.i = i; } };
 
@@ -244,8 +245,54 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             }
             if (out_idx) *out_idx = r.i;
             if (out_val) *out_val = r.v;
+            if (out_pair) {   // (value, GLOBAL index) for the cross-slice combine; "no candidate" stays ~0
+                out_pair->value = r.v;
+                out_pair->reserved = 0;
+                out_pair->index = r.i == kNoIndex ? kNoIndex : r.i + index_base;
+            }
         }
     }
+}
+
+// Cross-slice combine of `count` (value, global index) pairs (one per slice, slice 0 first) into the
+// scalar-backend answer for the whole vector (src/backends/scalar.rs:140-166): a NaN from slice 0 is the
+// NaN seed and wins outright; otherwise best value, then LOWEST global index; NaN values and "no
+// candidate" entries never win.  One warp; replaces ~10 framework ops behind the all_gather.
+__global__ void arg_combine_kernel(const trn_arg_pair* __restrict__ pairs, unsigned count, int is_max,
+                                   uint64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    const float seed_v = pairs[0].value;
+    const bool nan_seed = seed_v != seed_v;
+    float bv = is_max ? -INFINITY : INFINITY;
+    uint64_t bi = kNoIndex;
+    for (unsigned i = threadIdx.x; i < count; i += 32) {
+        const float v = pairs[i].value;
+        const uint64_t ix = pairs[i].index;
+        if (ix == kNoIndex || v != v) continue;
+        const bool win = bi == kNoIndex || (is_max ? v > bv : v < bv) || (v == bv && ix < bi);
+        if (win) { bv = v; bi = ix; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const uint64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const bool win = oi != kNoIndex && (bi == kNoIndex || (is_max ? ov > bv : ov < bv) || (ov == bv && oi < bi));
+        if (win) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+        if (nan_seed) { bv = seed_v; bi = pairs[0].index; }
+        if (out_idx) *out_idx = bi;
+        if (out_val) *out_val = bv;
+    }
+}
+
+int launch_arg_combine(const trn_arg_pair* pairs, size_t count, int is_max, uint64_t* out_idx, float* out_val,
+                       cudaStream_t s) {
+    if (!ctx()) return TRN_GPU_ERROR;
+    if (count == 0) return fail(TRN_INVALID_INPUT, "Empty vector");
+    arg_combine_kernel<<<1, 32, 0, s>>>(pairs, (unsigned)count, is_max, out_idx, out_val);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------
@@ -298,7 +345,7 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
 }
 
 int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s,
-                     int seed_rule) {
+                     int seed_rule, uint64_t index_base, trn_arg_pair* out_pair) {
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
     Workspace* w = workspace(s);
@@ -311,11 +358,11 @@ int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, fl
     const int grid = reduce_grid(n, c->sm_count, is_max ? per_sm_max : per_sm_min);
     const bool vec = aligned16(a);
     if (is_max) {
-        if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
-        else     argreduce_kernel<true, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
+        if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
+        else     argreduce_kernel<true, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
     } else {
-        if (vec) argreduce_kernel<false, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
-        else     argreduce_kernel<false, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule);
+        if (vec) argreduce_kernel<false, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
+        else     argreduce_kernel<false, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
     }
     count_launch();
     TRN_CUDA(cudaGetLastError());

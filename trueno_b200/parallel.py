@@ -103,7 +103,9 @@ def combine_arg(value: torch.Tensor, index: torch.Tensor, is_max: bool) -> tuple
     (src/backends/scalar.rs:140-166).  Slice 0 carries the a[0] seed rule, so a NaN value from it is
     final (a NaN seed never loses).  Interior slices report NO_CANDIDATE when they hold nothing but
     NaNs / identity values (a NaN element never wins).  Otherwise: best value, and among equal
-    values the LOWEST global index.  NCCL has no arg-reduce: this is an all_gather of `world` pairs."""
+    values the LOWEST global index.  NCCL has no arg-reduce: this is an all_gather of `world` pairs.
+    Tensor-op statement of the rule, used over gloo on CPU; on GPUs ShardedVector._arg runs the same rule as
+    one kernel (trn_arg_combine_f32_dev) behind a single packed all_gather."""
     w = world_size()
     if w == 1:
         return value, index
@@ -136,6 +138,8 @@ class ShardedVector:
         self.local, self.shard = local, shard
         self._f32 = torch.zeros(1, dtype=torch.float32, device=local.device)
         self._i64 = torch.zeros(1, dtype=torch.int64, device=local.device)
+        self._pair = torch.zeros(2, dtype=torch.int64, device=local.device)   # one trn_arg_pair (16 bytes)
+        self._gathered = None
 
     def _stream(self) -> int:
         return current_stream_handle()
@@ -161,13 +165,23 @@ class ShardedVector:
         return combine_sum(self._partial("trn_sumsq_f32_dev")).sqrt_()
 
     def _arg(self, is_max: bool) -> tuple[torch.Tensor, torch.Tensor]:
+        """slice kernel -> ONE all_gather of 16-byte (value, global index) pairs -> ONE combine kernel; all three are
+        enqueued on the current stream with no host synchronisation (NCCL has no arg-reduce)."""
         import trueno_b200 as trn
-        fn = trn.lib.trn_argmax_slice_f32_dev if is_max else trn.lib.trn_argmin_slice_f32_dev
-        trn.check(fn(self.local.data_ptr(), self.local.numel(), int(self.shard.start == 0), self._i64.data_ptr(),
-                     self._f32.data_ptr(), self._stream()))
-        # local -> global index; the kernel's "no candidate" (u64 ~0 == int64 -1) maps to NO_CANDIDATE
-        gidx = torch.where(self._i64 < 0, torch.full_like(self._i64, NO_CANDIDATE), self._i64 + self.shard.start)
-        return combine_arg(self._f32, gidx, is_max)
+        L = trn.lib
+        w = world_size()
+        fn = L.trn_argmax_slice_pair_f32_dev if is_max else L.trn_argmin_slice_pair_f32_dev
+        trn.check(fn(self.local.data_ptr(), self.local.numel(), self.shard.start, self._pair.data_ptr(), self._stream()))
+        if w > 1:
+            if self._gathered is None or self._gathered.numel() != 2 * w:
+                self._gathered = torch.empty(2 * w, dtype=torch.int64, device=self.local.device)
+            dist.all_gather_into_tensor(self._gathered, self._pair)
+            pairs = self._gathered
+        else:
+            pairs = self._pair
+        trn.check(L.trn_arg_combine_f32_dev(pairs.data_ptr(), w, int(is_max), self._i64.data_ptr(), self._f32.data_ptr(),
+                                            self._stream()))
+        return self._f32, self._i64
 
     def argmax(self) -> torch.Tensor:
         return self._arg(True)[1]
