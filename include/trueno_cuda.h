@@ -189,6 +189,75 @@ TRN_API int trn_matvec_f32_dev(const float* a, size_t rows, size_t cols, const f
                                float* y, void* stream);
 TRN_API int trn_transpose_f32_dev(const float* a, size_t rows, size_t cols, float* out, void* stream);
 
+/* ---- remaining VectorBackend surface ----------------------------------
+ * trait VectorBackend::{sub,div,scale,abs,clamp,lerp,fma,relu,exp,swish,tanh,sqrt,recip,ln,log2,log10,
+ * sin,cos,tan,floor,ceil,round,sum_kahan,norm_l1,norm_linf} (src/backends/mod.rs:67-385) behind the Vector
+ * methods of the same names (src/vector.rs:423-4182); scalar-backend definitions (src/backends/scalar.rs).
+ * Host-slice form `trn_<op>_f32(...)`, device-resident twin `trn_<op>_f32_dev(..., stream)`.
+ *   sub, div, lerp, fma : operand lengths differ -> TRN_SIZE_MISMATCH{expected = len(a), actual}
+ *   relu, swish, tanh   : empty input -> TRN_EMPTY_VECTOR (src/vector.rs:1670, :2293, :3950)
+ *   other maps          : empty input -> OK, empty result
+ *   clamp               : min > max -> TRN_INVALID_INPUT "Invalid clamp range: min ({}) > max ({})"
+ *   sum_kahan, norm_l1, norm_linf : empty -> 0
+ *   mean, variance, stddev : empty -> TRN_EMPTY_VECTOR; variance = E[x^2] - mean^2 (src/vector.rs:973-990)
+ * Bit-exact vs the scalar backend: sub, div, scale, abs, clamp, lerp, fma (unfused), relu, sqrt, recip,
+ * floor, ceil, round.  Transcendentals: <= 4 ulp vs libm (tan: 8 ulp). */
+TRN_API int trn_abs_f32(const float* a, size_t n, float* out);
+TRN_API int trn_abs_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_relu_f32(const float* a, size_t n, float* out);
+TRN_API int trn_relu_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_exp_f32(const float* a, size_t n, float* out);
+TRN_API int trn_exp_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_swish_f32(const float* a, size_t n, float* out);
+TRN_API int trn_swish_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_tanh_f32(const float* a, size_t n, float* out);
+TRN_API int trn_tanh_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_sqrt_f32(const float* a, size_t n, float* out);
+TRN_API int trn_sqrt_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_recip_f32(const float* a, size_t n, float* out);
+TRN_API int trn_recip_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_ln_f32(const float* a, size_t n, float* out);
+TRN_API int trn_ln_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_log2_f32(const float* a, size_t n, float* out);
+TRN_API int trn_log2_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_log10_f32(const float* a, size_t n, float* out);
+TRN_API int trn_log10_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_sin_f32(const float* a, size_t n, float* out);
+TRN_API int trn_sin_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_cos_f32(const float* a, size_t n, float* out);
+TRN_API int trn_cos_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_tan_f32(const float* a, size_t n, float* out);
+TRN_API int trn_tan_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_floor_f32(const float* a, size_t n, float* out);
+TRN_API int trn_floor_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_ceil_f32(const float* a, size_t n, float* out);
+TRN_API int trn_ceil_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_round_f32(const float* a, size_t n, float* out);
+TRN_API int trn_round_f32_dev(const float* a, size_t n, float* out, void* stream);
+/* reductions: `out` is one f32 (host pointer / device pointer for the _dev twin) */
+TRN_API int trn_sum_kahan_f32(const float* a, size_t n, float* out);
+TRN_API int trn_sum_kahan_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_norm_l1_f32(const float* a, size_t n, float* out);
+TRN_API int trn_norm_l1_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_norm_linf_f32(const float* a, size_t n, float* out);
+TRN_API int trn_norm_linf_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_sub_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_sub_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_div_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_div_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_scale_f32(const float* a, size_t n, float scalar, float* out);
+TRN_API int trn_scale_f32_dev(const float* a, size_t n, float scalar, float* out, void* stream);
+TRN_API int trn_clamp_f32(const float* a, size_t n, float min_val, float max_val, float* out);
+TRN_API int trn_clamp_f32_dev(const float* a, size_t n, float min_val, float max_val, float* out, void* stream);
+TRN_API int trn_lerp_f32(const float* a, size_t na, const float* b, size_t nb, float t, float* out);
+TRN_API int trn_lerp_f32_dev(const float* a, size_t na, const float* b, size_t nb, float t, float* out, void* stream);
+TRN_API int trn_fma_f32(const float* a, size_t na, const float* b, size_t nb, const float* c, size_t nc, float* out);
+TRN_API int trn_fma_f32_dev(const float* a, size_t na, const float* b, size_t nb, const float* c, size_t nc, float* out,
+                            void* stream);
+TRN_API int trn_mean_f32(const float* a, size_t n, float* out);
+TRN_API int trn_variance_f32(const float* a, size_t n, float* out);
+TRN_API int trn_stddev_f32(const float* a, size_t n, float* out);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

@@ -101,6 +101,61 @@ extern "C" {
     pub fn trn_matvec_f32_dev(a: *const f32, rows: usize, cols: usize, v: *const f32, v_len: usize, y: *mut f32,
                               stream: *mut c_void) -> c_int;
     pub fn trn_transpose_f32_dev(a: *const f32, rows: usize, cols: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    // remaining VectorBackend surface (src/backends/mod.rs:67-385)
+    pub fn trn_abs_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_abs_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_relu_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_relu_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_exp_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_exp_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_swish_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_swish_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_tanh_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_tanh_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sqrt_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_sqrt_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_recip_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_recip_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_ln_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_ln_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_log2_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_log2_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_log10_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_log10_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sin_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_sin_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_cos_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_cos_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_tan_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_tan_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_floor_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_floor_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_ceil_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_ceil_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_round_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_round_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sum_kahan_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_sum_kahan_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_norm_l1_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_norm_l1_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_norm_linf_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_norm_linf_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sub_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_sub_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_div_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_div_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_scale_f32(a: *const f32, n: usize, scalar: f32, out: *mut f32) -> c_int;
+    pub fn trn_scale_f32_dev(a: *const f32, n: usize, scalar: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_clamp_f32(a: *const f32, n: usize, min_val: f32, max_val: f32, out: *mut f32) -> c_int;
+    pub fn trn_clamp_f32_dev(a: *const f32, n: usize, min_val: f32, max_val: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_lerp_f32(a: *const f32, na: usize, b: *const f32, nb: usize, t: f32, out: *mut f32) -> c_int;
+    pub fn trn_lerp_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, t: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_fma_f32(a: *const f32, na: usize, b: *const f32, nb: usize, c: *const f32, nc: usize, out: *mut f32) -> c_int;
+    pub fn trn_fma_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, c: *const f32, nc: usize, out: *mut f32,
+                           stream: *mut c_void) -> c_int;
+    pub fn trn_mean_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_variance_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_stddev_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     // engine selection / live timing (benches only)
     pub fn trn_set_gemm_engine(engine: c_int) -> c_int;
     pub fn trn_get_gemm_engine() -> c_int;

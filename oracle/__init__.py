@@ -93,6 +93,10 @@ class Oracle:
         L.orc_f64_dot.argtypes = [_f32p, _f32p, C.c_size_t, _f64p, _f64p]
         L.orc_f64_matmul_samples.restype = None
         L.orc_f64_matmul_samples.argtypes = [_f32p, _f32p, C.c_size_t, C.c_size_t, _u64p, _u64p, C.c_size_t, _f64p, _f64p]
+        L.orc_scalar_map.restype = None
+        L.orc_scalar_map.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
+        for name in ("scalar_sum_kahan", "scalar_norm_l1", "scalar_norm_linf"):
+            f = getattr(L, "orc_" + name); f.restype = C.c_float; f.argtypes = [_f32p, C.c_size_t]
         L.orc_last_mismatch.restype = None
         L.orc_last_mismatch.argtypes = [_u64p, _u64p]
         L.orc_set_threads.argtypes = [C.c_int]
@@ -161,6 +165,23 @@ class Oracle:
     def gelu(self, a, backend=SCALAR): return self._map("gelu", a, backend)
     def softmax(self, a, backend=AVX2): return self._map("softmax", a, backend)
     def log_softmax(self, a, backend=AVX2): return self._map("log_softmax", a, backend)
+
+    # ---- remaining VectorBackend surface, scalar backend (src/backends/scalar.rs) ----
+    MAP_OPS = {"sub": 0, "div": 1, "scale": 2, "abs": 3, "clamp": 4, "lerp": 5, "fma": 6, "relu": 7, "exp": 8, "swish": 9,
+               "tanh": 10, "sqrt": 11, "recip": 12, "ln": 13, "log2": 14, "log10": 15, "sin": 16, "cos": 17, "tan": 18,
+               "floor": 19, "ceil": 20, "round": 21}
+
+    def scalar_map(self, op: str, a, b=None, c=None, p0: float = 0.0, p1: float = 0.0) -> np.ndarray:
+        a = _f32(a)
+        b = _f32(b) if b is not None else a
+        c = _f32(c) if c is not None else a
+        out = np.empty(a.size, np.float32)
+        self.lib.orc_scalar_map(self.MAP_OPS[op], _p(a), _p(b), _p(c), p0, p1, _p(out), a.size)
+        return out
+
+    def sum_kahan(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_sum_kahan(_p(a), a.size))
+    def norm_l1(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_norm_l1(_p(a), a.size))
+    def norm_linf(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_norm_linf(_p(a), a.size))
 
     def exp_avx2(self, a):
         a = _f32(a)

@@ -748,3 +748,72 @@ ORC_API void orc_set_threads(int t) {
     (void)t;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Remaining VectorBackend surface, scalar backend: one restatement per
+ * function of src/backends/scalar.rs, same operation order, libm for transcendentals.
+ * op codes are private to the oracle (oracle/__init__.py holds the name table).
+ * ---------------------------------------------------------------------------------------- */
+/* scalar.rs:32-60 (sub, div), :250-260 (scale), :262-266 (abs), :268-272 (clamp: val.max(min).min(max)),
+ * :274-279 (lerp: a + t*(b-a)), :281-286 (fma: a*b + c, NOT fused), :288-294 (relu), :296-300 (exp),
+ * :342-353 (swish), :355-480 (tanh, sqrt, recip, ln, log2, log10, sin, cos, tan, floor, ceil, round) */
+ORC_API void orc_scalar_map(int op, const float* a, const float* b, const float* c, float p0, float p1,
+                            float* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        const float x = a[i];
+        float r;
+        switch (op) {
+            case 0: r = x - b[i]; break;                                  /* sub */
+            case 1: r = x / b[i]; break;                                  /* div */
+            case 2: r = x * p0; break;                                    /* scale */
+            case 3: r = fabsf(x); break;                                  /* abs */
+            case 4: r = fminf(fmaxf(x, p0), p1); break;                   /* clamp (f32::max/min ignore NaN like fmaxf/fminf) */
+            case 5: { float d = b[i] - x; float t = p0 * d; r = x + t; } break;   /* lerp */
+            case 6: { float m = x * b[i]; r = m + c[i]; } break;          /* fma (unfused; -ffp-contract=off) */
+            case 7: r = x > 0.0f ? x : 0.0f; break;                       /* relu */
+            case 8: r = expf(x); break;
+            case 9: r = x < -50.0f ? 0.0f : (x > 50.0f ? x : x * (1.0f / (1.0f + expf(-x)))); break;   /* swish */
+            case 10: r = tanhf(x); break;
+            case 11: r = sqrtf(x); break;
+            case 12: r = 1.0f / x; break;                                 /* recip */
+            case 13: r = logf(x); break;
+            case 14: r = log2f(x); break;
+            case 15: r = log10f(x); break;
+            case 16: r = sinf(x); break;
+            case 17: r = cosf(x); break;
+            case 18: r = tanf(x); break;
+            case 19: r = floorf(x); break;
+            case 20: r = ceilf(x); break;
+            case 21: r = roundf(x); break;                                /* half away from zero == f32::round */
+            default: r = x;
+        }
+        out[i] = r;
+    }
+}
+
+/* scalar.rs:170-183 — Kahan-compensated sequential sum */
+ORC_API float orc_scalar_sum_kahan(const float* a, size_t n) {
+    float sum = 0.f, c = 0.f;
+    for (size_t i = 0; i < n; ++i) {
+        float y = a[i] - c;
+        float t = sum + y;
+        c = (t - sum) - y;
+        sum = t;
+    }
+    return sum;
+}
+/* scalar.rs:218-228 */
+ORC_API float orc_scalar_norm_l1(const float* a, size_t n) {
+    float s = 0.f;
+    for (size_t i = 0; i < n; ++i) s += fabsf(a[i]);
+    return s;
+}
+/* scalar.rs:234-247 — starts at 0.0, strict compare: a NaN never wins */
+ORC_API float orc_scalar_norm_linf(const float* a, size_t n) {
+    float m = 0.f;
+    for (size_t i = 0; i < n; ++i) {
+        float v = fabsf(a[i]);
+        if (v > m) m = v;
+    }
+    return m;
+}

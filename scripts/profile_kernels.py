@@ -1,0 +1,77 @@
+"""One launch of every hot-path kernel at its BASELINE size between cudaProfilerStart/Stop, for
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_all python scripts/profile_kernels.py
+Warm-up launches run before the profiler range so the captured launch is steady-state (apart from ncu's own
+cache control).  usage: python scripts/profile_kernels.py [gemm] [batched] [reduce] [map] [softmax] [matvec]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import trueno_b200 as trn  # noqa: E402
+
+
+def main():
+    which = set(sys.argv[1:]) or {"gemm", "batched", "reduce", "map", "softmax", "matvec"}
+    torch.cuda.set_device(0)
+    trn.check(trn.lib.trn_cuda_init(0))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
+    L = trn.lib
+    ops = []
+    keep = []
+    if "gemm" in which:
+        n = 8192
+        a, b, c = torch.rand(n, n, device="cuda"), torch.rand(n, n, device="cuda"), torch.empty(n, n, device="cuda")
+        keep += [a, b, c]
+        ops.append(lambda: trn.check(L.trn_matmul_f32_dev(a.data_ptr(), n, n, b.data_ptr(), n, n, c.data_ptr(), st)))
+    if "batched" in which:
+        B, H, m, k, nn = 8, 32, 2048, 128, 2048
+        qa, qb = torch.rand(B * H * m * k, device="cuda"), torch.rand(B * H * k * nn, device="cuda")
+        qc = torch.empty(B * H * m * nn, device="cuda")
+        keep += [qa, qb, qc]
+        ops.append(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(qa.data_ptr(), qa.numel(), qb.data_ptr(), qb.numel(),
+                                                                     qc.data_ptr(), B, H, m, k, nn, st)))
+    if "reduce" in which:
+        n1 = 1 << 30
+        x, y = torch.rand(n1, device="cuda") * 2 - 1, torch.rand(n1, device="cuda") * 2 - 1
+        out = torch.zeros(4, device="cuda")
+        oi = torch.zeros(2, dtype=torch.int64, device="cuda")
+        keep += [x, y, out, oi]
+        ops += [lambda: trn.check(L.trn_sum_f32_dev(x.data_ptr(), n1, out.data_ptr(), st)),
+                lambda: trn.check(L.trn_dot_f32_dev(x.data_ptr(), n1, y.data_ptr(), n1, out.data_ptr(), st)),
+                lambda: trn.check(L.trn_norm_l2_f32_dev(x.data_ptr(), n1, out.data_ptr(), st)),
+                lambda: trn.check(L.trn_argmax_f32_dev(x.data_ptr(), n1, oi.data_ptr(), out.data_ptr(), st))]
+    if "map" in which or "softmax" in which:
+        rows, cols = 4096, 32000
+        z = torch.randn(rows, cols, device="cuda") * 4
+        z2 = torch.randn(rows, cols, device="cuda")
+        o = torch.empty_like(z)
+        keep += [z, z2, o]
+        if "map" in which:
+            ops += [lambda: trn.check(L.trn_add_f32_dev(z.data_ptr(), z.numel(), z2.data_ptr(), z2.numel(), o.data_ptr(), st)),
+                    lambda: trn.check(L.trn_sigmoid_f32_dev(z.data_ptr(), z.numel(), o.data_ptr(), st)),
+                    lambda: trn.check(L.trn_gelu_f32_dev(z.data_ptr(), z.numel(), o.data_ptr(), st))]
+        if "softmax" in which:
+            ops += [lambda: trn.check(L.trn_softmax_rows_f32_dev(z.data_ptr(), o.data_ptr(), rows, cols, st)),
+                    lambda: trn.check(L.trn_log_softmax_rows_f32_dev(z.data_ptr(), o.data_ptr(), rows, cols, st))]
+    if "matvec" in which:
+        r = 16384
+        ma, mv, my = torch.randn(r, r, device="cuda"), torch.randn(r, device="cuda"), torch.empty(r, device="cuda")
+        keep += [ma, mv, my]
+        ops.append(lambda: trn.check(L.trn_matvec_f32_dev(ma.data_ptr(), r, r, mv.data_ptr(), r, my.data_ptr(), st)))
+    for _ in range(3):
+        for f in ops:
+            f()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    for f in ops:
+        f()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print("profiled", len(ops), "ops;", trn.launch_count(), "launches")
+
+
+if __name__ == "__main__":
+    main()

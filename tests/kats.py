@@ -105,3 +105,46 @@ def splitmix_u01(seed, start, count):
     z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
     z = z ^ (z >> np.uint64(31))
     return ((z >> np.uint64(40)).astype(np.float32) * f32(1.0 / (1 << 24))).astype(f32)
+
+
+# ---- remaining VectorBackend surface: exact-value KATs of the reference's own tests -----
+# (op, inputs, params, expected, tolerance (0 = exact), reference test location)
+MAP_EXT_KATS = [
+    ("sub", [[5, 7, 9], [1, 2, 3]], (), [4, 5, 6], 0, "src/vector.rs:4567"),
+    ("div", [[10, 20, 30], [2, 4, 5]], (), [5, 5, 6], 0, "src/vector.rs:4640"),
+    ("abs", [[3, -4, 5, -2]], (), [3, 4, 5, 2], 0, "src/vector.rs:5072"),
+    ("scale", [[1, 2, 3, 4]], (2.0,), [2, 4, 6, 8], 0, "src/vector.rs:5108"),
+    ("scale", [[1, 2, 3]], (0.0,), [0, 0, 0], 0, "src/vector.rs:5116"),
+    ("clamp", [[-5, 0, 5, 10, 15]], (0.0, 10.0), [0, 0, 5, 10, 10], 0, "src/vector.rs:5151"),
+    ("lerp", [[0, 10, 20], [100, 110, 120]], (0.5,), [50, 60, 70], 0, "src/vector.rs:5208"),
+    ("lerp", [[1, 2, 3], [4, 5, 6]], (0.0,), [1, 2, 3], 0, "src/vector.rs:5216"),
+    ("fma", [[2, 3, 4], [5, 6, 7], [1, 2, 3]], (), [11, 20, 31], 0, "src/vector.rs:5265"),
+    ("sqrt", [[4, 9, 16, 25]], (), [2, 3, 4, 5], 0, "src/vector.rs:5333"),
+    ("recip", [[2, 4, 5, 10]], (), [0.5, 0.25, 0.2, 0.1], 0, "src/vector.rs:5379"),
+    ("floor", [[3.7, -2.3, 5.0]], (), [3, -3, 5], 0, "src/vector.rs:6689"),
+    ("ceil", [[3.2, -2.7, 5.0]], (), [4, -2, 5], 0, "src/vector.rs:6731"),
+    ("round", [[3.2, 3.7, -2.3, -2.8, 5.0]], (), [3, 4, -2, -3, 5], 0, "src/vector.rs:6773"),
+    ("round", [[1.4, 1.5, 1.6, 2.5]], (), [1, 2, 2, 3], 0, "src/vector.rs:6780"),
+    ("round", [[-1.4, -1.5, -1.6, -2.5]], (), [-1, -2, -2, -3], 0, "src/vector.rs:6787"),
+    ("round", [[0.5, 1.5, 2.5, 3.5, 4.5]], (), [1, 2, 3, 4, 5], 0, "src/vector.rs:6795"),
+    ("relu", [[-2, -1, 0, 1, 2]], (), [0, 0, 0, 1, 2], 0, "src/vector.rs:8018"),
+    ("swish", [[-2, -1, 0, 1, 2]], (), [-0.238, -0.269, 0.0, 0.731, 1.762], 0.01, "src/vector.rs:8424"),
+    ("exp", [[0, 1, 2]], (), [1.0, 2.718281828, 7.389056099], 1e-5, "src/vector.rs:5475"),
+    ("tanh", [[0.0]], (), [0.0], 0, "src/vector.rs:6472"),
+    ("sin", [[0.0]], (), [0.0], 0, "src/vector.rs:5813"),
+    ("cos", [[0.0]], (), [1.0], 0, "src/vector.rs:5905"),
+]
+REDUCE_EXT_KATS = [
+    ("sum_kahan", [1, 2, 3, 4], 10.0, 0, "src/vector.rs:4733"),
+    ("sum_kahan", [], 0.0, 0, "src/vector.rs:4739"),
+    ("sum_kahan", [42], 42.0, 0, "src/vector.rs:4744"),
+    ("norm_l1", [3, -4, 5], 12.0, 1e-5, "src/vector.rs:4987"),
+    ("norm_l1", [1, 2, 3, 4], 10.0, 1e-5, "src/vector.rs:4994"),
+    ("norm_linf", [3, -7, 5, -2], 7.0, 1e-5, "src/vector.rs:5026"),
+    ("norm_linf", [1, 2, 5, 3], 5.0, 1e-5, "src/vector.rs:5033"),
+    ("mean", [1, 2, 3, 4], 2.5, 1e-5, "src/vector.rs:7238"),
+    ("mean", [-2, -4, -6], -4.0, 1e-5, "src/vector.rs:7245"),
+    ("variance", [1, 2, 3, 4, 5], 2.0, 1e-5, "src/vector.rs:7284"),
+    ("variance", [7, 7, 7, 7], 0.0, 1e-5, "src/vector.rs:7291"),
+    ("stddev", [1, 2, 3, 4, 5], 2.0 ** 0.5, 1e-5, "src/vector.rs:7335"),
+]

@@ -1,0 +1,47 @@
+"""Oracle pin for the remaining VectorBackend surface: the scalar-backend restatement in
+oracle/trueno_oracle.c against the exact-value KATs of the reference's own tests (tests/kats.py)."""
+import numpy as np
+import pytest
+
+import kats
+
+f32 = np.float32
+
+
+@pytest.mark.parametrize("kat", kats.MAP_EXT_KATS, ids=[f"{k[0]}-{i}" for i, k in enumerate(kats.MAP_EXT_KATS)])
+def test_oracle_map_kats(oracle, kat):
+    op, inputs, params, expected, tol, _ = kat
+    args = [np.asarray(x, f32) for x in inputs]
+    p0 = params[0] if len(params) > 0 else 0.0
+    p1 = params[1] if len(params) > 1 else 0.0
+    got = oracle.scalar_map(op, args[0], args[1] if len(args) > 1 else None, args[2] if len(args) > 2 else None, p0, p1)
+    want = np.asarray(expected, f32)
+    if tol == 0:
+        assert np.array_equal(got, want), (op, got, want)
+    else:
+        assert np.max(np.abs(got - want)) <= tol
+
+
+@pytest.mark.parametrize("kat", [k for k in kats.REDUCE_EXT_KATS if k[0] in ("sum_kahan", "norm_l1", "norm_linf")],
+                         ids=lambda k: k[0])
+def test_oracle_reduce_kats(oracle, kat):
+    op, v, expected, tol, _ = kat
+    got = float(getattr(oracle, op)(np.asarray(v, f32)))
+    assert abs(got - expected) <= tol
+
+
+def test_oracle_semantics_corner_cases(oracle):
+    nan = np.nan
+    # relu: NaN and -0.0 -> +0.0 (strict `val > 0.0`, src/backends/scalar.rs:293)
+    r = oracle.scalar_map("relu", [nan, -0.0, 3.0])
+    assert r[0] == 0 and not np.signbit(r[1]) and r[2] == 3
+    # clamp: f32::max / min ignore a NaN operand -> NaN clamps to min
+    assert oracle.scalar_map("clamp", [nan], p0=1.0, p1=2.0)[0] == 1.0
+    # norm_linf: NaN never wins
+    assert float(oracle.norm_linf(np.array([1, nan, -3], f32))) == 3.0
+    # fma is NOT fused in the scalar backend: a*b rounds before the add
+    a, b, c = f32(1 + 2 ** -12), f32(1 + 2 ** -12), f32(-1)
+    assert oracle.scalar_map("fma", [a], [b], [c])[0] == f32(f32(a * b) + c)
+    # Kahan keeps what the plain left-to-right sum loses
+    v = np.array([1e8] + [1.0] * 1000, f32)
+    assert float(oracle.sum_kahan(v)) == 1e8 + 1000

@@ -1,0 +1,126 @@
+"""CUDA path of the remaining VectorBackend surface against the reference's KATs and the
+scalar-backend oracle.  Stated tolerances: single-operation and unfused two-operation maps bit-exact; exp / tanh /
+ln / log2 / log10 / sin / cos / swish <= 4 ulp, tan <= 8 ulp vs glibc; sum_kahan / norm_l1 within 1e-5 * sum|x| of
+the f64 truth (sum_kahan additionally within 2 ulp of it); norm_linf exact."""
+import numpy as np
+import pytest
+
+import kats
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+EXACT = ("sub", "div", "scale", "abs", "clamp", "lerp", "fma", "relu", "sqrt", "recip", "floor", "ceil", "round")
+ULPS = {"exp": 4, "swish": 4, "tanh": 4, "ln": 4, "log2": 4, "log10": 4, "sin": 4, "cos": 4, "tan": 8}
+
+
+def ulp(x):
+    return np.spacing(np.abs(x).astype(f32)).astype(np.float64)
+
+
+def run_map(trn, op, args, params):
+    vs = [trn.Vector.from_slice(a) for a in args]
+    return getattr(vs[0], op)(*vs[1:], *params).as_slice()
+
+
+@pytest.mark.parametrize("kat", kats.MAP_EXT_KATS, ids=[f"{k[0]}-{i}" for i, k in enumerate(kats.MAP_EXT_KATS)])
+def test_map_kats(trn, kat):
+    op, inputs, params, expected, tol, _ = kat
+    got = run_map(trn, op, [np.asarray(x, f32) for x in inputs], params)
+    want = np.asarray(expected, f32)
+    if tol == 0:
+        assert np.array_equal(got, want), (op, got, want)
+    else:
+        assert np.max(np.abs(got - want)) <= tol
+
+
+@pytest.mark.parametrize("kat", kats.REDUCE_EXT_KATS, ids=[f"{k[0]}-{i}" for i, k in enumerate(kats.REDUCE_EXT_KATS)])
+def test_reduce_kats(trn, kat):
+    op, v, expected, tol, _ = kat
+    got = float(getattr(trn.Vector.from_slice(np.asarray(v, f32)), op)())
+    assert abs(got - expected) <= tol
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 2048, 2049, 100_003, (1 << 20) + 1])
+def test_maps_vs_oracle(trn, oracle, n):
+    rng = np.random.default_rng(n)
+    a = (rng.standard_normal(n) * 3).astype(f32)
+    b = (rng.standard_normal(n) * 3).astype(f32)
+    c = rng.standard_normal(n).astype(f32)
+    b[b == 0] = 1
+    pos = np.abs(a) + f32(1e-3)
+    cases = {
+        "sub": ([a, b], ()), "div": ([a, b], ()), "scale": ([a], (1.7,)), "abs": ([a], ()), "clamp": ([a], (-1.5, 2.25)),
+        "lerp": ([a, b], (0.3,)), "fma": ([a, b, c], ()), "relu": ([a], ()), "exp": ([a], ()), "swish": ([a * 20], ()),
+        "tanh": ([a], ()), "sqrt": ([pos], ()), "recip": ([b], ()), "ln": ([pos], ()), "log2": ([pos], ()),
+        "log10": ([pos], ()), "sin": ([a * 100], ()), "cos": ([a * 100], ()), "tan": ([a], ()), "floor": ([a], ()),
+        "ceil": ([a], ()), "round": ([a], ()),
+    }
+    for op, (args, params) in cases.items():
+        got = run_map(trn, op, args, params)
+        p0 = params[0] if len(params) > 0 else 0.0
+        p1 = params[1] if len(params) > 1 else 0.0
+        want = oracle.scalar_map(op, args[0], args[1] if len(args) > 1 else None, args[2] if len(args) > 2 else None, p0, p1)
+        if op in EXACT:
+            assert np.array_equal(got, want), (op, n)
+        else:
+            assert np.all(np.abs(got.astype(np.float64) - want) <= ULPS[op] * ulp(want) + 1e-45), (op, n)
+
+
+def test_map_special_values(trn, oracle):
+    nan, inf = np.nan, np.inf
+    x = np.array([nan, -0.0, 0.0, inf, -inf, 1e-45, -1e-45, 3.4e38, -3.4e38, 60.0, -60.0, 0.5, -0.5, 2.5, -2.5], f32)
+    for op in ("abs", "relu", "sqrt", "recip", "floor", "ceil", "round", "exp", "tanh", "swish"):
+        got = run_map(trn, op, [x], ())
+        want = oracle.scalar_map(op, x)
+        with np.errstate(invalid="ignore"):
+            same = (got == want) | (np.isnan(got) & np.isnan(want)) | (np.abs(got.astype(np.float64) - want) <= 4 * ulp(want))
+        assert same.all(), (op, got, want)
+        if op in EXACT:
+            assert np.array_equal(np.signbit(got), np.signbit(want)), op
+    assert run_map(trn, "clamp", [np.array([nan, 5, -5], f32)], (1.0, 2.0)).tolist() == [1.0, 2.0, 1.0]
+
+
+def test_ext_error_contract(trn):
+    V, E = trn.Vector, trn.TruenoError
+    for op in ("sub", "div"):
+        with pytest.raises(E) as e:
+            getattr(V.from_slice([1, 2, 3]), op)(V.from_slice([1, 2]))
+        assert e.value == E.SizeMismatch(3, 2)
+    with pytest.raises(E) as e:
+        V.from_slice([1, 2, 3]).fma(V.from_slice([1, 2, 3]), V.from_slice([1]))
+    assert e.value == E.SizeMismatch(3, 1)
+    with pytest.raises(E) as e:
+        V.from_slice([1, 2, 3]).clamp(10.0, 0.0)                     # src/vector.rs:5200
+    assert e.value == E.InvalidInput("Invalid clamp range: min (10) > max (0)")
+    for op in ("relu", "swish", "tanh", "mean", "variance", "stddev"):
+        with pytest.raises(E) as e:
+            getattr(V.from_slice([]), op)()
+        assert e.value == E.EmptyVector
+    for op in ("abs", "sqrt", "exp", "floor"):
+        assert getattr(V.from_slice([]), op)().len() == 0
+    assert float(V.from_slice([]).sum_kahan()) == 0 and float(V.from_slice([]).norm_l1()) == 0
+    with pytest.raises(E) as e:
+        V.from_slice([0, 0, 0]).normalize()                          # src/vector.rs:2670
+    assert e.value.variant == "DivisionByZero"
+    r = V.from_slice([3, 4]).normalize().as_slice()                  # src/vector.rs:4946
+    assert abs(r[0] - 0.6) < 1e-5 and abs(r[1] - 0.8) < 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 65537, (1 << 22) + 3])
+def test_ext_reductions_vs_oracle(trn, oracle, n):
+    rng = np.random.default_rng(n + 1)
+    a = rng.uniform(-1, 1, n).astype(f32)
+    v = trn.Vector.from_slice(a)
+    tsum, asum = oracle.f64_sum(a)
+    assert abs(float(v.sum_kahan()) - tsum) <= min(1e-5 * asum, 2 * float(ulp(np.float32(tsum))) + 1e-6 * asum / max(n, 1) ** 0.5 + 1e-30 + 2e-7 * abs(tsum) + 4e-8 * asum ** 0.5)
+    assert abs(float(v.norm_l1()) - asum) <= 1e-5 * asum
+    assert float(v.norm_linf()) == float(np.max(np.abs(a))) == float(oracle.norm_linf(a))
+    assert abs(float(v.mean()) - tsum / n) <= 1e-5 * asum / n
+    m2 = float(np.mean(a.astype(np.float64) ** 2))
+    assert abs(float(v.variance()) - (m2 - (tsum / n) ** 2)) <= 1e-5 * (m2 + (tsum / n) ** 2) + 1e-7
+
+
+def test_kahan_keeps_small_terms(trn, oracle):
+    """The reference's own motivation for sum_kahan (src/vector.rs:848 doc): 1e8 followed by ones."""
+    v = np.array([1e8] + [1.0] * 100_000, f32)
+    assert float(trn.Vector.from_slice(v).sum_kahan()) == float(oracle.sum_kahan(v)) == 1e8 + 100_000

@@ -33,6 +33,10 @@ _u64p = C.POINTER(C.c_uint64)
 _sz = C.c_size_t
 _vp = C.c_void_p
 
+_UNARY_EXT = ("abs", "relu", "exp", "swish", "tanh", "sqrt", "recip", "ln", "log2", "log10", "sin", "cos", "tan",
+              "floor", "ceil", "round")
+_REDUCE_EXT = ("sum_kahan", "norm_l1", "norm_linf", "mean", "variance", "stddev")
+
 # name -> argtypes; every function returns int (trn_status) unless listed in _RESTYPES
 _SIGNATURES = {
     "trn_cuda_init": [C.c_int], "trn_cuda_shutdown": [], "trn_cuda_is_available": [],
@@ -73,6 +77,16 @@ _SIGNATURES = {
     "trn_batched_matmul_4d_f32_dev": [_vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, _sz, _sz, _vp],
     "trn_matvec_f32_dev": [_vp, _sz, _sz, _vp, _sz, _vp, _vp],
     "trn_transpose_f32_dev": [_vp, _sz, _sz, _vp, _vp],
+    **{f"trn_{n}_f32": [_vp, _sz, _vp] for n in _UNARY_EXT},
+    **{f"trn_{n}_f32_dev": [_vp, _sz, _vp, _vp] for n in _UNARY_EXT},
+    **{f"trn_{n}_f32": [_vp, _sz, _f32p] for n in _REDUCE_EXT},
+    **{f"trn_{n}_f32_dev": [_vp, _sz, _vp, _vp] for n in _REDUCE_EXT[:3]},
+    "trn_sub_f32": [_vp, _sz, _vp, _sz, _vp], "trn_sub_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp],
+    "trn_div_f32": [_vp, _sz, _vp, _sz, _vp], "trn_div_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp],
+    "trn_scale_f32": [_vp, _sz, C.c_float, _vp], "trn_scale_f32_dev": [_vp, _sz, C.c_float, _vp, _vp],
+    "trn_clamp_f32": [_vp, _sz, C.c_float, C.c_float, _vp], "trn_clamp_f32_dev": [_vp, _sz, C.c_float, C.c_float, _vp, _vp],
+    "trn_lerp_f32": [_vp, _sz, _vp, _sz, C.c_float, _vp], "trn_lerp_f32_dev": [_vp, _sz, _vp, _sz, C.c_float, _vp, _vp],
+    "trn_fma_f32": [_vp, _sz, _vp, _sz, _vp, _sz, _vp], "trn_fma_f32_dev": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }
@@ -314,6 +328,44 @@ class Vector:
     def sigmoid(self): return self._map(lib.trn_sigmoid_f32)
     def gelu(self): return self._map(lib.trn_gelu_f32)
 
+    # ---- remaining VectorBackend surface (src/vector.rs:423-4182) ----
+    def sub(self, other): return self._binary(lib.trn_sub_f32, other)
+    def div(self, other): return self._binary(lib.trn_div_f32, other)
+
+    def scale(self, scalar: float) -> "Vector":
+        out = np.empty(self.data.size, np.float32)
+        check(lib.trn_scale_f32(_ptr(self.data), self.data.size, scalar, _ptr(out)))
+        return Vector(out)
+
+    def clamp(self, min_val: float, max_val: float) -> "Vector":
+        out = np.empty(self.data.size, np.float32)
+        check(lib.trn_clamp_f32(_ptr(self.data), self.data.size, min_val, max_val, _ptr(out)))
+        return Vector(out)
+
+    def lerp(self, other: "Vector", t: float) -> "Vector":
+        out = np.empty(self.data.size, np.float32)
+        check(lib.trn_lerp_f32(_ptr(self.data), self.data.size, _ptr(other.data), other.data.size, t, _ptr(out)))
+        return Vector(out)
+
+    def fma(self, b: "Vector", c: "Vector") -> "Vector":
+        out = np.empty(self.data.size, np.float32)
+        check(lib.trn_fma_f32(_ptr(self.data), self.data.size, _ptr(b.data), b.data.size, _ptr(c.data), c.data.size, _ptr(out)))
+        return Vector(out)
+
+    def sum_kahan(self): return self._reduce(lib.trn_sum_kahan_f32)
+    def norm_l1(self): return self._reduce(lib.trn_norm_l1_f32)
+    def norm_linf(self): return self._reduce(lib.trn_norm_linf_f32)
+    def mean(self): return self._reduce(lib.trn_mean_f32)
+    def variance(self): return self._reduce(lib.trn_variance_f32)
+    def stddev(self): return self._reduce(lib.trn_stddev_f32)
+
+    def normalize(self) -> "Vector":
+        """src/vector.rs:2665-2678: norm_l2, |norm| < 1e-10 -> DivisionByZero, else scale(1 / norm)."""
+        norm = self.norm_l2()
+        if abs(float(norm)) < 1e-10:
+            raise TruenoError("DivisionByZero")
+        return self.scale(float(np.float32(1.0) / norm))
+
     # ---- softmax family (src/vector.rs:1516, 1581): a Vector is one row ----
     def softmax(self) -> "Vector":
         out = np.empty(self.data.size, np.float32)
@@ -399,3 +451,19 @@ def softmax_rows(a, rows: int, cols: int, log: bool = False) -> np.ndarray:
     fn = lib.trn_log_softmax_rows_f32 if log else lib.trn_softmax_rows_f32
     check(fn(_ptr(a), _ptr(out), rows, cols))
     return out.reshape(rows, cols)
+
+
+def _install_unary_maps():
+    def make(name):
+        fn = getattr(lib, f"trn_{name}_f32")
+
+        def method(self):
+            return self._map(fn)
+        method.__name__ = name
+        method.__doc__ = f"Vector::{name} (src/vector.rs) -> trn_{name}_f32"
+        return method
+    for name in _UNARY_EXT:
+        setattr(Vector, name, make(name))
+
+
+_install_unary_maps()

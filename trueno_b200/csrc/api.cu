@@ -2,7 +2,10 @@
 // reference's exact error values/messages, engine dispatch, and the host-slice wrappers that
 // stage through HBM.  No entry point ever computes on the CPU.
 #include <atomic>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -10,6 +13,22 @@
 using namespace trn;
 
 namespace {
+
+// Rust's `{}` for f32: shortest representation that round-trips, integers without a fraction ("1", "0.5", "-2.25")
+std::string fmt_f32(float v) {
+    char buf[64];
+    for (int prec = 1; prec <= 9; ++prec) {
+        snprintf(buf, sizeof buf, "%.*g", prec, (double)v);
+        if (strtof(buf, nullptr) == v) break;
+    }
+    std::string r(buf);
+    if (r.find('e') != std::string::npos) {   // Rust never prints exponents for f32 Display
+        snprintf(buf, sizeof buf, "%.9f", (double)v);
+        r = buf;
+        while (r.find('.') != std::string::npos && (r.back() == '0' || r.back() == '.')) { const bool dot = r.back() == '.'; r.pop_back(); if (dot) break; }
+    }
+    return r;
+}
 
 std::atomic<int> g_engine{0};
 
@@ -144,9 +163,10 @@ int host_arg(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out
     return TRN_OK;
 }
 
-int host_map(Map op, const float* a, const float* b, float* out, size_t n) {
+int host_map(Map op, const float* a, const float* b, const float* c3, float* out, size_t n, float p0 = 0.f, float p1 = 0.f) {
     Context* c = ctx();
-    DevTemp da(c->stream), db(c->stream), dout(c->stream);
+    if (n == 0) return TRN_OK;
+    DevTemp da(c->stream), db(c->stream), dc(c->stream), dout(c->stream);
     TRN_TRY(da.alloc(n));
     TRN_TRY(dout.alloc(n));
     TRN_TRY(upload(da.p, a, n, c->stream));
@@ -154,8 +174,17 @@ int host_map(Map op, const float* a, const float* b, float* out, size_t n) {
         TRN_TRY(db.alloc(n));
         TRN_TRY(upload(db.p, b, n, c->stream));
     }
-    TRN_TRY(launch_map(op, da.p, db.p, dout.p, n, c->stream));
+    if (c3) {
+        TRN_TRY(dc.alloc(n));
+        TRN_TRY(upload(dc.p, c3, n, c->stream));
+    }
+    TRN_TRY(launch_map(op, da.p, db.p, dc.p, dout.p, n, p0, p1, c->stream));
     return download(out, dout.p, n, c->stream);
+}
+
+int check_clamp(float lo, float hi) {  // src/vector.rs:2964-2969
+    if (lo > hi) return fail(TRN_INVALID_INPUT, "Invalid clamp range: min (%s) > max (%s)", fmt_f32(lo).c_str(), fmt_f32(hi).c_str());
+    return TRN_OK;
 }
 
 }  // namespace
@@ -237,22 +266,22 @@ int trn_arg_combine_f32_dev(const trn_arg_pair* pairs, size_t count, int is_max,
 int trn_add_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream) {
     TRN_TRY(check_same_len(na, nb));
     TRN_TRY(need_ctx());
-    return launch_map(Map::Add, a, b, out, na, resolve_stream(stream));
+    return launch_map(Map::Add, a, b, nullptr, out, na, 0.f, 0.f, resolve_stream(stream));
 }
 int trn_mul_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream) {
     TRN_TRY(check_same_len(na, nb));
     TRN_TRY(need_ctx());
-    return launch_map(Map::Mul, a, b, out, na, resolve_stream(stream));
+    return launch_map(Map::Mul, a, b, nullptr, out, na, 0.f, 0.f, resolve_stream(stream));
 }
 int trn_sigmoid_f32_dev(const float* a, size_t n, float* out, void* stream) {
     TRN_TRY(check_nonempty_emptyvec(n));
     TRN_TRY(need_ctx());
-    return launch_map(Map::Sigmoid, a, nullptr, out, n, resolve_stream(stream));
+    return launch_map(Map::Sigmoid, a, nullptr, nullptr, out, n, 0.f, 0.f, resolve_stream(stream));
 }
 int trn_gelu_f32_dev(const float* a, size_t n, float* out, void* stream) {
     TRN_TRY(check_nonempty_emptyvec(n));
     TRN_TRY(need_ctx());
-    return launch_map(Map::Gelu, a, nullptr, out, n, resolve_stream(stream));
+    return launch_map(Map::Gelu, a, nullptr, nullptr, out, n, 0.f, 0.f, resolve_stream(stream));
 }
 int trn_softmax_rows_f32_dev(const float* a, float* out, size_t rows, size_t cols, void* stream) {
     TRN_TRY(check_nonempty_emptyvec(rows * cols));
@@ -356,22 +385,22 @@ int trn_argmin_f32(const float* a, size_t n, uint64_t* out) {
 int trn_add_f32(const float* a, size_t na, const float* b, size_t nb, float* out) {
     TRN_TRY(check_same_len(na, nb));
     TRN_TRY(need_ctx());
-    return host_map(Map::Add, a, b, out, na);
+    return host_map(Map::Add, a, b, nullptr, out, na);
 }
 int trn_mul_f32(const float* a, size_t na, const float* b, size_t nb, float* out) {
     TRN_TRY(check_same_len(na, nb));
     TRN_TRY(need_ctx());
-    return host_map(Map::Mul, a, b, out, na);
+    return host_map(Map::Mul, a, b, nullptr, out, na);
 }
 int trn_sigmoid_f32(const float* a, size_t n, float* out) {
     TRN_TRY(check_nonempty_emptyvec(n));
     TRN_TRY(need_ctx());
-    return host_map(Map::Sigmoid, a, nullptr, out, n);
+    return host_map(Map::Sigmoid, a, nullptr, nullptr, out, n);
 }
 int trn_gelu_f32(const float* a, size_t n, float* out) {
     TRN_TRY(check_nonempty_emptyvec(n));
     TRN_TRY(need_ctx());
-    return host_map(Map::Gelu, a, nullptr, out, n);
+    return host_map(Map::Gelu, a, nullptr, nullptr, out, n);
 }
 
 static int host_softmax(int log_variant, const float* a, float* out, size_t rows, size_t cols) {
@@ -560,6 +589,148 @@ int trn_transpose_f32(const float* a, size_t rows, size_t cols, float* out) {
     TRN_TRY(upload(da.p, a, n, c->stream));
     TRN_TRY(launch_transpose(da.p, rows, cols, dout.p, c->stream));
     return download(out, dout.p, n, c->stream);
+}
+
+// ===================== remaining VectorBackend surface =====================
+// Validation per op follows src/vector.rs: sub/div/lerp/fma -> SizeMismatch; relu/swish/tanh on an empty vector ->
+// EmptyVector (:1670, :2293, :3950); the other maps return an empty result for an empty input (:2827-4182);
+// clamp with min > max -> InvalidInput("Invalid clamp range: min ({}) > max ({})") (:2964-2969).
+#define TRN_UNARY(NAME, OP, EMPTY_IS_ERROR)                                                              \
+    int trn_##NAME##_f32_dev(const float* a, size_t n, float* out, void* stream) {                       \
+        if (EMPTY_IS_ERROR) TRN_TRY(check_nonempty_emptyvec(n));                                         \
+        TRN_TRY(need_ctx());                                                                             \
+        return launch_map(Map::OP, a, nullptr, nullptr, out, n, 0.f, 0.f, resolve_stream(stream));       \
+    }                                                                                                    \
+    int trn_##NAME##_f32(const float* a, size_t n, float* out) {                                         \
+        if (EMPTY_IS_ERROR) TRN_TRY(check_nonempty_emptyvec(n));                                         \
+        TRN_TRY(need_ctx());                                                                             \
+        return host_map(Map::OP, a, nullptr, nullptr, out, n);                                           \
+    }
+TRN_UNARY(abs, Abs, false)
+TRN_UNARY(relu, Relu, true)
+TRN_UNARY(exp, Exp, false)
+TRN_UNARY(swish, Swish, true)
+TRN_UNARY(tanh, Tanh, true)
+TRN_UNARY(sqrt, Sqrt, false)
+TRN_UNARY(recip, Recip, false)
+TRN_UNARY(ln, Ln, false)
+TRN_UNARY(log2, Log2, false)
+TRN_UNARY(log10, Log10, false)
+TRN_UNARY(sin, Sin, false)
+TRN_UNARY(cos, Cos, false)
+TRN_UNARY(tan, Tan, false)
+TRN_UNARY(floor, Floor, false)
+TRN_UNARY(ceil, Ceil, false)
+TRN_UNARY(round, Round, false)
+#undef TRN_UNARY
+
+#define TRN_BINARY(NAME, OP)                                                                             \
+    int trn_##NAME##_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream) { \
+        TRN_TRY(check_same_len(na, nb));                                                                 \
+        TRN_TRY(need_ctx());                                                                             \
+        return launch_map(Map::OP, a, b, nullptr, out, na, 0.f, 0.f, resolve_stream(stream));            \
+    }                                                                                                    \
+    int trn_##NAME##_f32(const float* a, size_t na, const float* b, size_t nb, float* out) {             \
+        TRN_TRY(check_same_len(na, nb));                                                                 \
+        TRN_TRY(need_ctx());                                                                             \
+        return host_map(Map::OP, a, b, nullptr, out, na);                                                \
+    }
+TRN_BINARY(sub, Sub)
+TRN_BINARY(div, Div)
+#undef TRN_BINARY
+
+int trn_scale_f32_dev(const float* a, size_t n, float scalar, float* out, void* stream) {
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Scale, a, nullptr, nullptr, out, n, scalar, 0.f, resolve_stream(stream));
+}
+int trn_scale_f32(const float* a, size_t n, float scalar, float* out) {
+    TRN_TRY(need_ctx());
+    return host_map(Map::Scale, a, nullptr, nullptr, out, n, scalar);
+}
+int trn_clamp_f32_dev(const float* a, size_t n, float min_val, float max_val, float* out, void* stream) {
+    TRN_TRY(check_clamp(min_val, max_val));
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Clamp, a, nullptr, nullptr, out, n, min_val, max_val, resolve_stream(stream));
+}
+int trn_clamp_f32(const float* a, size_t n, float min_val, float max_val, float* out) {
+    TRN_TRY(check_clamp(min_val, max_val));
+    TRN_TRY(need_ctx());
+    return host_map(Map::Clamp, a, nullptr, nullptr, out, n, min_val, max_val);
+}
+int trn_lerp_f32_dev(const float* a, size_t na, const float* b, size_t nb, float t, float* out, void* stream) {
+    TRN_TRY(check_same_len(na, nb));
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Lerp, a, b, nullptr, out, na, t, 0.f, resolve_stream(stream));
+}
+int trn_lerp_f32(const float* a, size_t na, const float* b, size_t nb, float t, float* out) {
+    TRN_TRY(check_same_len(na, nb));
+    TRN_TRY(need_ctx());
+    return host_map(Map::Lerp, a, b, nullptr, out, na, t);
+}
+int trn_fma_f32_dev(const float* a, size_t na, const float* b, size_t nb, const float* c, size_t nc, float* out, void* stream) {
+    TRN_TRY(check_same_len(na, nb));
+    TRN_TRY(check_same_len(na, nc));
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Fma, a, b, c, out, na, 0.f, 0.f, resolve_stream(stream));
+}
+int trn_fma_f32(const float* a, size_t na, const float* b, size_t nb, const float* c, size_t nc, float* out) {
+    TRN_TRY(check_same_len(na, nb));
+    TRN_TRY(check_same_len(na, nc));
+    TRN_TRY(need_ctx());
+    return host_map(Map::Fma, a, b, c, out, na);
+}
+
+// ---- reductions: sum_kahan, norm_l1, norm_linf (empty -> 0, src/vector.rs:848, :2708, :2770) ----------------
+#define TRN_REDUCE(NAME, OP)                                                                             \
+    int trn_##NAME##_f32_dev(const float* a, size_t n, float* out, void* stream) {                       \
+        TRN_TRY(need_ctx());                                                                             \
+        return launch_reduce(Reduce::OP, a, nullptr, n, out, resolve_stream(stream));                    \
+    }                                                                                                    \
+    int trn_##NAME##_f32(const float* a, size_t n, float* out) {                                         \
+        TRN_TRY(need_ctx());                                                                             \
+        return host_reduce_f32(a, n, nullptr, 0, out, [&](const float* da, const float*, float* o, cudaStream_t s) { \
+            return launch_reduce(Reduce::OP, da, nullptr, n, o, s);                                      \
+        });                                                                                              \
+    }
+TRN_REDUCE(sum_kahan, SumKahan)
+TRN_REDUCE(norm_l1, SumAbs)
+TRN_REDUCE(norm_linf, MaxAbs)
+#undef TRN_REDUCE
+
+// mean / variance / stddev (src/vector.rs:935-1030): empty -> EmptyVector; mean = sum / n;
+// variance = E[x^2] - mean^2 with both moments from the device reductions; stddev = sqrt(variance)
+static int host_moments(const float* a, size_t n, float* mean, float* var) {
+    TRN_TRY(check_nonempty_emptyvec(n));
+    TRN_TRY(need_ctx());
+    Context* c = ctx();
+    Workspace* w = workspace(c->stream);
+    if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
+    DevTemp da(c->stream);
+    TRN_TRY(da.alloc(n));
+    TRN_TRY(upload(da.p, a, n, c->stream));
+    float sum = 0.f, sumsq = 0.f;
+    TRN_TRY(launch_reduce(Reduce::Sum, da.p, nullptr, n, w->scalar_f32, c->stream));
+    TRN_CUDA(cudaMemcpyAsync(w->host_f32, w->scalar_f32, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    TRN_CUDA(cudaStreamSynchronize(c->stream));
+    sum = *w->host_f32;
+    if (var) {
+        TRN_TRY(launch_reduce(Reduce::SumSq, da.p, nullptr, n, w->scalar_f32, c->stream));
+        TRN_CUDA(cudaMemcpyAsync(w->host_f32, w->scalar_f32, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        TRN_CUDA(cudaStreamSynchronize(c->stream));
+        sumsq = *w->host_f32;
+    }
+    const float m = sum / (float)n;
+    if (mean) *mean = m;
+    if (var) *var = sumsq / (float)n - m * m;
+    return TRN_OK;
+}
+int trn_mean_f32(const float* a, size_t n, float* out) { return host_moments(a, n, out, nullptr); }
+int trn_variance_f32(const float* a, size_t n, float* out) { return host_moments(a, n, nullptr, out); }
+int trn_stddev_f32(const float* a, size_t n, float* out) {
+    float v = 0.f;
+    TRN_TRY(host_moments(a, n, nullptr, &v));
+    *out = sqrtf(v);
+    return TRN_OK;
 }
 
 }  // extern "C"

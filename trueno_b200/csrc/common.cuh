@@ -74,7 +74,7 @@ int download(float* dst_host, const float* src_dev, size_t n, cudaStream_t s);
 // ---------------------------------------------------------------------------------------------
 // kernel launchers (one translation unit per family)
 // ---------------------------------------------------------------------------------------------
-enum class Reduce { Sum, Dot, SumSq, NormL2 };
+enum class Reduce { Sum, Dot, SumSq, NormL2, SumAbs, MaxAbs, SumKahan };
 int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s);
 // is_max: 1 argmax / 0 argmin.  out_idx / out_val may be null.  seed_rule 0: interior slice of a
 // sharded vector (no a[0] seed; "no candidate" -> index ~0).
@@ -83,8 +83,12 @@ int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, fl
 int launch_arg_combine(const trn_arg_pair* pairs, size_t count, int is_max, uint64_t* out_idx, float* out_val,
                        cudaStream_t s);
 
-enum class Map { Add, Mul, Sigmoid, Gelu };
-int launch_map(Map op, const float* a, const float* b, float* out, size_t n, cudaStream_t s);
+enum class Map { Add, Sub, Mul, Div, Scale, Abs, Clamp, Lerp, Fma, Relu, Exp, Sigmoid, Gelu, Swish, Tanh, Sqrt, Recip,
+                 Ln, Log2, Log10, Sin, Cos, Tan, Floor, Ceil, Round };
+// out[i] = op(a[i], b[i], c[i]; p0, p1): b / c are read only by binary / ternary ops, p0 / p1 only by scale
+// (p0 = scalar), clamp (p0 = min, p1 = max) and lerp (p0 = t)
+int launch_map(Map op, const float* a, const float* b, const float* c, float* out, size_t n, float p0, float p1,
+               cudaStream_t s);
 
 int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows, size_t cols, cudaStream_t s);
 

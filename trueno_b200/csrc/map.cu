@@ -1,16 +1,20 @@
-// map.cu — elementwise kernels: add, mul (bit-exact), sigmoid, gelu (scalar-backend definitions).
+// map.cu — elementwise kernels: the whole `VectorBackend` map surface (src/backends/mod.rs:52-385).
 //
-// Replaces Avx2Backend::{add,mul,sigmoid,gelu} (src/backends/avx2.rs:32-117, :875-1047).  add/mul
-// are one IEEE operation per element, so they match the reference bit for bit.  sigmoid/gelu follow
-// the scalar backend's definitions (src/backends/scalar.rs:313-340: libm expf with +-50 cut-offs;
-// tanh-form GELU with libm tanhf) using CUDA's accurate expf/tanhf and IEEE division — no
-// fast-math intrinsics on the parity path.
+// Replaces Avx2Backend::{add,sub,mul,div,scale,abs,clamp,lerp,fma,relu,exp,sigmoid,gelu,swish,tanh,sqrt,
+// recip,ln,log2,log10,sin,cos,tan,floor,ceil,round} (src/backends/avx2.rs) with the SEMANTICS of the scalar
+// backend (src/backends/scalar.rs:20-60, 266-480).  Single-operation maps (add, sub, mul, div, scale, abs,
+// clamp, relu, sqrt, recip, floor, ceil, round) and the unfused two-operation maps (lerp = a + t*(b-a),
+// fma = a*b + c — Rust never contracts them, scalar.rs:271, :283) are spelled with explicitly rounded
+// intrinsics, so they match the reference bit for bit.  Transcendentals use CUDA's accurate libm-class
+// functions (expf, logf, sinf, ... <= 2 ulp; tanf <= 4 ulp) — no fast-math intrinsics on the parity path.
+// sigmoid / swish keep the scalar backend's +-50 cut-offs as selects; gelu evaluates the reference's
+// u = k*(x + c*x^3) in its operation order and then the exact identity 0.5*(1 + tanh u) = 1/(1 + e^(-2u)).
 //
 // HBM-bound streaming: 128-bit loads/stores, ONE 8 KiB tile per CTA on a flat (non-persistent) grid.
 // Measured on B200 (scripts/exp/exp_map.cu, 131 M elements): flat grids reach 6.6-6.9 TB/s where a
 // persistent one-wave grid-stride loop of the same body reaches 5.0-6.5 TB/s — the block scheduler
 // keeps every SM's load queue full while persistent CTAs drift into lock-step load/compute phases.
-// Algorithmic bytes per element: add/mul 12 B, sigmoid/gelu 8 B.
+// Algorithmic bytes per element: 4 B per input + 4 B output (unary 8 B, binary 12 B, fma 16 B).
 #include "common.cuh"
 
 namespace trn {
@@ -18,99 +22,147 @@ namespace trn {
 constexpr int kThreads = 256;
 constexpr int kUnroll = 2;   // float4 per thread per input: 8 KiB tiles
 
-template <int OP>
-__device__ __forceinline__ float apply(float x, float y) {
-    if (OP == 0) return x + y;
-    if (OP == 1) return x * y;
-    if (OP == 2) {
-        // src/backends/scalar.rs:313-324 (cut-offs applied as selects: no divergence)
-        const float s = 1.0f / (1.0f + expf(-x));
-        return x < -50.0f ? 0.0f : (x > 50.0f ? 1.0f : s);
+__host__ __device__ constexpr int map_arity(Map op) {
+    return (op == Map::Add || op == Map::Sub || op == Map::Mul || op == Map::Div || op == Map::Lerp) ? 2
+           : op == Map::Fma ? 3 : 1;
+}
+
+template <Map OP>
+__device__ __forceinline__ float apply(float x, float y, float z, float p0, float p1) {
+    switch (OP) {
+        case Map::Add: return __fadd_rn(x, y);
+        case Map::Sub: return __fsub_rn(x, y);
+        case Map::Mul: return __fmul_rn(x, y);
+        case Map::Div: return __fdiv_rn(x, y);
+        case Map::Scale: return __fmul_rn(x, p0);
+        case Map::Abs: return fabsf(x);
+        case Map::Clamp: return fminf(fmaxf(x, p0), p1);                 // val.max(min).min(max): NaN -> min
+        case Map::Lerp: return __fadd_rn(x, __fmul_rn(p0, __fsub_rn(y, x)));   // a + t*(b - a), unfused
+        case Map::Fma: return __fadd_rn(__fmul_rn(x, y), z);             // a*b + c, unfused (scalar.rs:283)
+        case Map::Relu: return x > 0.0f ? x : 0.0f;                       // NaN and -0.0 -> +0.0 (scalar.rs:293)
+        case Map::Exp: return expf(x);
+        case Map::Sigmoid: {
+            // src/backends/scalar.rs:313-324 (cut-offs applied as selects: no divergence)
+            const float s = 1.0f / (1.0f + expf(-x));
+            return x < -50.0f ? 0.0f : (x > 50.0f ? 1.0f : s);
+        }
+        case Map::Gelu: {
+            // src/backends/scalar.rs:330-340: 0.5*x*(1 + tanh(u)), u = k*(x + c*x^3) with the reference's
+            // operation order for u, then 0.5*(1 + tanh(u)) = 1/(1 + e^(-2u)): branch-free and WITHOUT the
+            // 1 + tanh cancellation the reference's form has for x << 0 (tolerance: 4 ulp + 4*2^-24*|x|).
+            const float x3 = __fmul_rn(__fmul_rn(x, x), x);
+            const float u = __fmul_rn(0.7978846f, __fadd_rn(x, __fmul_rn(0.044715f, x3)));
+            return x / (1.0f + expf(-2.0f * u));
+        }
+        case Map::Swish: {
+            // src/backends/scalar.rs:342-353: x * sigmoid(x), x < -50 -> 0, x > 50 -> x
+            const float s = __fmul_rn(x, 1.0f / (1.0f + expf(-x)));
+            return x < -50.0f ? 0.0f : (x > 50.0f ? x : s);
+        }
+        case Map::Tanh: return tanhf(x);
+        case Map::Sqrt: return sqrtf(x);
+        case Map::Recip: return __frcp_rn(x);
+        case Map::Ln: return logf(x);
+        case Map::Log2: return log2f(x);
+        case Map::Log10: return log10f(x);
+        case Map::Sin: return sinf(x);
+        case Map::Cos: return cosf(x);
+        case Map::Tan: return tanf(x);
+        case Map::Floor: return floorf(x);
+        case Map::Ceil: return ceilf(x);
+        case Map::Round: return roundf(x);                                // half away from zero == f32::round
     }
-    // src/backends/scalar.rs:330-340: 0.5*x*(1 + tanh(u)), u = k*(x + c*x^3) with the reference's
-    // operation order for u.  Evaluated through the exact identity 0.5*(1 + tanh(u)) = 1/(1 + e^(-2u)):
-    // branch-free (tanhf is two divergent paths), ~half the instructions, and WITHOUT the 1 + tanh
-    // cancellation the reference's form has for x << 0 — so the result is at least as close to the true
-    // value as the reference's own (parity tolerance: 4 ulp + 4*2^-24*|x|, the reference's cancellation term).
-    const float x3 = __fmul_rn(__fmul_rn(x, x), x);
-    const float u = __fmul_rn(0.7978846f, __fadd_rn(x, __fmul_rn(0.044715f, x3)));
-    return x / (1.0f + expf(-2.0f * u));
+    return x;
 }
 
-template <int OP>
-__device__ __forceinline__ float4 apply4(const float4& x, const float4& y) {
-    return make_float4(apply<OP>(x.x, y.x), apply<OP>(x.y, y.y), apply<OP>(x.z, y.z), apply<OP>(x.w, y.w));
+template <Map OP>
+__device__ __forceinline__ float4 apply4(const float4& x, const float4& y, const float4& z, float p0, float p1) {
+    return make_float4(apply<OP>(x.x, y.x, z.x, p0, p1), apply<OP>(x.y, y.y, z.y, p0, p1),
+                       apply<OP>(x.z, y.z, z.z, p0, p1), apply<OP>(x.w, y.w, z.w, p0, p1));
 }
 
-template <int OP, bool VEC>
+template <Map OP, bool VEC>
 __global__ void __launch_bounds__(kThreads)
-map_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n) {
-    constexpr bool BIN = OP < 2;
+map_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+           float* __restrict__ out, size_t n, float p0, float p1) {
+    constexpr int AR = map_arity(OP);
     if (VEC) {
         const size_t nvec = n >> 2;
         const float4* a4 = reinterpret_cast<const float4*>(a);
         const float4* b4 = reinterpret_cast<const float4*>(b);
+        const float4* c4 = reinterpret_cast<const float4*>(c);
         float4* o4 = reinterpret_cast<float4*>(out);
         const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
         if (base + (kUnroll - 1) * kThreads < nvec) {   // full tile (all but the last CTA)
-            float4 x[kUnroll], y[kUnroll];
+            float4 x[kUnroll], y[kUnroll], z[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(a4 + base + u * kThreads);
-            if (BIN) {
+            if (AR >= 2) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) y[u] = ld_stream(b4 + base + u * kThreads);
             }
+            if (AR >= 3) {
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) st_stream(o4 + base + u * kThreads, apply4<OP>(x[u], BIN ? y[u] : x[u]));
+                for (int u = 0; u < kUnroll; ++u) z[u] = ld_stream(c4 + base + u * kThreads);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                st_stream(o4 + base + u * kThreads, apply4<OP>(x[u], AR >= 2 ? y[u] : x[u], AR >= 3 ? z[u] : x[u], p0, p1));
         } else {
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const size_t v = base + u * kThreads;
                 if (v < nvec) {
                     const float4 x = ld_stream(a4 + v);
-                    st_stream(o4 + v, apply4<OP>(x, BIN ? ld_stream(b4 + v) : x));
+                    const float4 y = AR >= 2 ? ld_stream(b4 + v) : x;
+                    const float4 z = AR >= 3 ? ld_stream(c4 + v) : x;
+                    st_stream(o4 + v, apply4<OP>(x, y, z, p0, p1));
                 }
             }
         }
         if (blockIdx.x == 0) {   // scalar tail (n % 4 elements)
             const size_t i = (nvec << 2) + threadIdx.x;
-            if (i < n) out[i] = apply<OP>(a[i], BIN ? b[i] : 0.f);
+            if (i < n) out[i] = apply<OP>(a[i], AR >= 2 ? b[i] : 0.f, AR >= 3 ? c[i] : 0.f, p0, p1);
         }
     } else {
         const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll * 4) + threadIdx.x;
 #pragma unroll
         for (int u = 0; u < kUnroll * 4; ++u) {
             const size_t i = base + (size_t)u * kThreads;
-            if (i < n) out[i] = apply<OP>(ld_stream(a + i), BIN ? ld_stream(b + i) : 0.f);
+            if (i < n)
+                out[i] = apply<OP>(ld_stream(a + i), AR >= 2 ? ld_stream(b + i) : 0.f, AR >= 3 ? ld_stream(c + i) : 0.f, p0, p1);
         }
     }
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int launch_map(Map op, const float* a, const float* b, float* out, size_t n, cudaStream_t s) {
-    Context* c = ctx();
-    if (!c) return TRN_GPU_ERROR;
+template <Map OP>
+static void launch_one(bool vec, unsigned grid, const float* a, const float* b, const float* c, float* out, size_t n,
+                       float p0, float p1, cudaStream_t s) {
+    if (vec) map_kernel<OP, true><<<grid, kThreads, 0, s>>>(a, b, c, out, n, p0, p1);
+    else     map_kernel<OP, false><<<grid, kThreads, 0, s>>>(a, b, c, out, n, p0, p1);
+}
+
+int launch_map(Map op, const float* a, const float* b, const float* c3, float* out, size_t n, float p0, float p1,
+               cudaStream_t s) {
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
     if (n == 0) return TRN_OK;
-    const bool bin = op == Map::Add || op == Map::Mul;
-    const bool vec = aligned16(a) && aligned16(out) && (!bin || aligned16(b));
+    const int ar = map_arity(op);
+    const bool vec = aligned16(a) && aligned16(out) && (ar < 2 || aligned16(b)) && (ar < 3 || aligned16(c3));
     // one CTA per 8 KiB tile; the scalar path covers the same 2048 elements per CTA
     const size_t per_cta = (size_t)kThreads * kUnroll * 4;
     const size_t tiles = (n + per_cta - 1) / per_cta;
     if (tiles > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "vector of %zu elements exceeds the launch grid", n);
     const unsigned grid = (unsigned)tiles;
-#define LAUNCH(OP)                                                                    \
-    do {                                                                              \
-        if (vec) map_kernel<OP, true><<<grid, kThreads, 0, s>>>(a, b, out, n);         \
-        else     map_kernel<OP, false><<<grid, kThreads, 0, s>>>(a, b, out, n);        \
-    } while (0)
+#define CASE(OP) case Map::OP: launch_one<Map::OP>(vec, grid, a, b, c3, out, n, p0, p1, s); break
     switch (op) {
-        case Map::Add:     LAUNCH(0); break;
-        case Map::Mul:     LAUNCH(1); break;
-        case Map::Sigmoid: LAUNCH(2); break;
-        case Map::Gelu:    LAUNCH(3); break;
+        CASE(Add); CASE(Sub); CASE(Mul); CASE(Div); CASE(Scale); CASE(Abs); CASE(Clamp); CASE(Lerp); CASE(Fma);
+        CASE(Relu); CASE(Exp); CASE(Sigmoid); CASE(Gelu); CASE(Swish); CASE(Tanh); CASE(Sqrt); CASE(Recip);
+        CASE(Ln); CASE(Log2); CASE(Log10); CASE(Sin); CASE(Cos); CASE(Tan); CASE(Floor); CASE(Ceil); CASE(Round);
     }
-#undef LAUNCH
+#undef CASE
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;

@@ -53,24 +53,57 @@ __device__ __forceinline__ float block_sum(float v) {
     return r;  // valid in warp 0
 }
 
-// ---- sum / dot / sum of squares ---------------------------------------------------------------------
-template <int OP>  // 0 sum, 1 dot, 2 sumsq
-__device__ __forceinline__ void accum4(float& acc, const float4& x, const float4& y) {
+__device__ __forceinline__ float block_max(float v) {
+    __shared__ float s_m[kThreads / 32];
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < kThreads / 32 ? s_m[threadIdx.x] : 0.f;
+        r = warp_max(r);
+    }
+    __syncthreads();
+    return r;  // valid in warp 0
+}
+
+// ---- sum / dot / sum of squares / sum of |x| / max of |x| / compensated sum --------------------------------
+// OP: 0 sum, 1 dot, 2 sumsq, 3 sum|x| (norm_l1, scalar.rs:218-228), 4 max|x| (norm_linf, scalar.rs:234-247:
+//     starts at 0.0 and a NaN never wins, exactly fmaxf), 5 Kahan-compensated sum (sum_kahan, scalar.rs:170-183:
+//     every thread runs the reference's compensation recurrence on its own elements; the per-thread results
+//     then go through the same fixed tree as the plain sum)
+template <int OP>
+__device__ __forceinline__ void accum1(float& acc, float& comp, float x, float y) {
+    if (OP == 0) acc += x;
+    else if (OP == 1) acc = fmaf(x, y, acc);
+    else if (OP == 2) acc = fmaf(x, x, acc);
+    else if (OP == 3) acc += fabsf(x);
+    else if (OP == 4) acc = fmaxf(acc, fabsf(x));
+    else {
+        const float yk = __fsub_rn(x, comp);
+        const float t = __fadd_rn(acc, yk);
+        comp = __fsub_rn(__fsub_rn(t, acc), yk);
+        acc = t;
+    }
+}
+template <int OP>
+__device__ __forceinline__ void accum4(float& acc, float& comp, const float4& x, const float4& y) {
     if (OP == 0) {
         acc += (x.x + x.y) + (x.z + x.w);
     } else if (OP == 1) {
         acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
         acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-    } else {
+    } else if (OP == 2) {
         acc = fmaf(x.x, x.x, acc); acc = fmaf(x.y, x.y, acc);
         acc = fmaf(x.z, x.z, acc); acc = fmaf(x.w, x.w, acc);
+    } else if (OP == 3) {
+        acc += (fabsf(x.x) + fabsf(x.y)) + (fabsf(x.z) + fabsf(x.w));
+    } else if (OP == 4) {
+        acc = fmaxf(acc, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+    } else {
+        accum1<OP>(acc, comp, x.x, 0.f); accum1<OP>(acc, comp, x.y, 0.f);
+        accum1<OP>(acc, comp, x.z, 0.f); accum1<OP>(acc, comp, x.w, 0.f);
     }
-}
-template <int OP>
-__device__ __forceinline__ void accum1(float& acc, float x, float y) {
-    if (OP == 0) acc += x;
-    else if (OP == 1) acc = fmaf(x, y, acc);
-    else acc = fmaf(x, x, acc);
 }
 
 // VEC: pointers are 16-byte aligned -> 128-bit path over n/4 vectors, scalar tail by block 0.
@@ -78,9 +111,9 @@ template <int OP, bool VEC, bool SQRT>
 __global__ void __launch_bounds__(kThreads)
 reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
                   float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out) {
-    float acc[kUnroll];
+    float acc[kUnroll], comp[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) acc[u] = 0.f;
+    for (int u = 0; u < kUnroll; ++u) acc[u] = comp[u] = 0.f;
 
     if (VEC) {
         const size_t nvec = n >> 2;
@@ -97,33 +130,37 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
                 for (int u = 0; u < kUnroll; ++u) y[u] = ld_stream(b4 + base + u * kThreads);
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) accum4<OP>(acc[u], x[u], OP == 1 ? y[u] : x[u]);
+            for (int u = 0; u < kUnroll; ++u) accum4<OP>(acc[u], comp[u], x[u], OP == 1 ? y[u] : x[u]);
         }
         // ragged vector tail + scalar tail: spread over the grid, one element stride
         const size_t tail0 = full_tiles * kTileVec;
         for (size_t v = tail0 + (size_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += (size_t)gridDim.x * kThreads) {
             float4 x = ld_stream(a4 + v);
             float4 y = OP == 1 ? ld_stream(b4 + v) : x;
-            accum4<OP>(acc[0], x, y);
+            accum4<OP>(acc[0], comp[0], x, y);
         }
         if (blockIdx.x == 0) {
             size_t i = (nvec << 2) + threadIdx.x;
-            if (i < n) accum1<OP>(acc[1], a[i], OP == 1 ? b[i] : 0.f);
+            if (i < n) accum1<OP>(acc[1], comp[1], a[i], OP == 1 ? b[i] : 0.f);
         }
     } else {
         for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
-            accum1<OP>(acc[0], ld_stream(a + i), OP == 1 ? ld_stream(b + i) : 0.f);
+            accum1<OP>(acc[0], comp[0], ld_stream(a + i), OP == 1 ? ld_stream(b + i) : 0.f);
     }
 
-    float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    v = block_sum(v);
+    constexpr bool ISMAX = OP == 4;
+    float v = ISMAX ? fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3])) : (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    v = ISMAX ? block_max(v) : block_sum(v);
     if (threadIdx.x == 0) partial[blockIdx.x] = v;
 
     if (last_block_done(ticket)) {
         // fixed-order fold of the per-block partials (gridDim.x <= kMaxReduceBlocks)
         float r = 0.f;
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) r += __ldcg(partial + i);
-        r = block_sum(r);
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) {
+            const float q = __ldcg(partial + i);
+            r = ISMAX ? fmaxf(r, q) : r + q;
+        }
+        r = ISMAX ? block_max(r) : block_sum(r);
         if (threadIdx.x == 0) *out = SQRT ? sqrtf(r) : r;
     }
 }
@@ -337,6 +374,9 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
         case Reduce::Dot:    LAUNCH(1, false); break;
         case Reduce::SumSq:  LAUNCH(2, false); break;
         case Reduce::NormL2: LAUNCH(2, true); break;
+        case Reduce::SumAbs: LAUNCH(3, false); break;
+        case Reduce::MaxAbs: LAUNCH(4, false); break;
+        case Reduce::SumKahan: LAUNCH(5, false); break;
     }
 #undef LAUNCH
     count_launch();
