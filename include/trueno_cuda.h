@@ -201,7 +201,7 @@ TRN_API int trn_transpose_f32_dev(const float* a, size_t rows, size_t cols, floa
  *   sum_kahan, norm_l1, norm_linf : empty -> 0
  *   mean, variance, stddev : empty -> TRN_EMPTY_VECTOR; variance = E[x^2] - mean^2 (src/vector.rs:973-990)
  * Bit-exact vs the scalar backend: sub, div, scale, abs, clamp, lerp, fma (unfused), relu, sqrt, recip,
- * floor, ceil, round.  Transcendentals: <= 4 ulp vs libm (tan: 8 ulp). */
+ * floor, ceil, round.  Transcendentals: <= 4 ulp vs libm (swish: 6 ulp, tan: 8 ulp). */
 TRN_API int trn_abs_f32(const float* a, size_t n, float* out);
 TRN_API int trn_abs_f32_dev(const float* a, size_t n, float* out, void* stream);
 TRN_API int trn_relu_f32(const float* a, size_t n, float* out);

@@ -1,7 +1,8 @@
 """CUDA path of the remaining VectorBackend surface against the reference's KATs and the
 scalar-backend oracle.  Stated tolerances: single-operation and unfused two-operation maps bit-exact; exp / tanh /
-ln / log2 / log10 / sin / cos / swish <= 4 ulp, tan <= 8 ulp vs glibc; sum_kahan / norm_l1 within 1e-5 * sum|x| of
-the f64 truth (sum_kahan additionally within 2 ulp of it); norm_linf exact."""
+ln / log2 / log10 / sin / cos <= 4 ulp, tan <= 8 ulp vs glibc; swish <= 6 ulp (expf 2 ulp on the device + 1 ulp in
+glibc, then 1 + e, the division and the product round in BOTH implementations); sum_kahan / norm_l1 within 1e-5 * sum|x| of
+the f64 truth; sum_kahan within 2 ulp of the f64 truth (compensated per thread AND through the tree); norm_linf exact."""
 import numpy as np
 import pytest
 
@@ -10,7 +11,7 @@ import kats
 pytestmark = pytest.mark.gpu
 f32 = np.float32
 EXACT = ("sub", "div", "scale", "abs", "clamp", "lerp", "fma", "relu", "sqrt", "recip", "floor", "ceil", "round")
-ULPS = {"exp": 4, "swish": 4, "tanh": 4, "ln": 4, "log2": 4, "log10": 4, "sin": 4, "cos": 4, "tan": 8}
+ULPS = {"exp": 4, "swish": 6, "tanh": 4, "ln": 4, "log2": 4, "log10": 4, "sin": 4, "cos": 4, "tan": 8}
 
 
 def ulp(x):
@@ -73,10 +74,11 @@ def test_map_special_values(trn, oracle):
         got = run_map(trn, op, [x], ())
         want = oracle.scalar_map(op, x)
         with np.errstate(invalid="ignore"):
-            same = (got == want) | (np.isnan(got) & np.isnan(want)) | (np.abs(got.astype(np.float64) - want) <= 4 * ulp(want))
+            same = (got == want) | (np.isnan(got) & np.isnan(want)) | (np.abs(got.astype(np.float64) - want) <= 6 * ulp(want))
         assert same.all(), (op, got, want)
-        if op in EXACT:
-            assert np.array_equal(np.signbit(got), np.signbit(want)), op
+        if op in EXACT:   # signed zeros / infinities must agree too (the sign of a NaN carries no meaning)
+            ok = ~np.isnan(want)
+            assert np.array_equal(np.signbit(got[ok]), np.signbit(want[ok])), op
     assert run_map(trn, "clamp", [np.array([nan, 5, -5], f32)], (1.0, 2.0)).tolist() == [1.0, 2.0, 1.0]
 
 
@@ -112,7 +114,7 @@ def test_ext_reductions_vs_oracle(trn, oracle, n):
     a = rng.uniform(-1, 1, n).astype(f32)
     v = trn.Vector.from_slice(a)
     tsum, asum = oracle.f64_sum(a)
-    assert abs(float(v.sum_kahan()) - tsum) <= min(1e-5 * asum, 2 * float(ulp(np.float32(tsum))) + 1e-6 * asum / max(n, 1) ** 0.5 + 1e-30 + 2e-7 * abs(tsum) + 4e-8 * asum ** 0.5)
+    assert abs(float(v.sum_kahan()) - tsum) <= 2 * float(ulp(np.float32(tsum))) + 1e-30   # compensated end to end
     assert abs(float(v.norm_l1()) - asum) <= 1e-5 * asum
     assert float(v.norm_linf()) == float(np.max(np.abs(a))) == float(oracle.norm_linf(a))
     assert abs(float(v.mean()) - tsum / n) <= 1e-5 * asum / n

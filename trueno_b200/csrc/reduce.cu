@@ -70,8 +70,8 @@ __device__ __forceinline__ float block_max(float v) {
 // ---- sum / dot / sum of squares / sum of |x| / max of |x| / compensated sum --------------------------------
 // OP: 0 sum, 1 dot, 2 sumsq, 3 sum|x| (norm_l1, scalar.rs:218-228), 4 max|x| (norm_linf, scalar.rs:234-247:
 //     starts at 0.0 and a NaN never wins, exactly fmaxf), 5 Kahan-compensated sum (sum_kahan, scalar.rs:170-183:
-//     every thread runs the reference's compensation recurrence on its own elements; the per-thread results
-//     then go through the same fixed tree as the plain sum)
+//     every thread runs the reference's compensation recurrence on its own elements; the per-thread
+//     (sum, compensation) pairs then go through a fixed tree of error-free two-sums)
 template <int OP>
 __device__ __forceinline__ void accum1(float& acc, float& comp, float x, float y) {
     if (OP == 0) acc += x;
@@ -106,11 +106,39 @@ __device__ __forceinline__ void accum4(float& acc, float& comp, const float4& x,
     }
 }
 
+// ---- compensated (hi, lo) pairs: the sum_kahan tree ---------------------------------------------------------
+// (hi, lo) += (bh, bl) with Knuth's error-free two-sum: the rounding error of hi + bh moves into lo, so the
+// cross-thread / cross-block tree keeps what the per-thread Kahan recurrences kept.
+__device__ __forceinline__ void pair_add(float& hi, float& lo, float bh, float bl) {
+    const float s = __fadd_rn(hi, bh);
+    const float bb = __fsub_rn(s, hi);
+    const float err = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(bh, bb));
+    hi = s;
+    lo = __fadd_rn(__fadd_rn(lo, bl), err);
+}
+__device__ __forceinline__ void block_pair_sum(float& hi, float& lo) {   // result valid in thread 0
+    __shared__ float s_h[kThreads / 32], s_l[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oh = __shfl_xor_sync(0xffffffffu, hi, o), ol = __shfl_xor_sync(0xffffffffu, lo, o);
+        pair_add(hi, lo, oh, ol);
+    }
+    if ((threadIdx.x & 31) == 0) { s_h[threadIdx.x >> 5] = hi; s_l[threadIdx.x >> 5] = lo; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        hi = s_h[0]; lo = s_l[0];
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w) pair_add(hi, lo, s_h[w], s_l[w]);
+    }
+    __syncthreads();
+}
+
 // VEC: pointers are 16-byte aligned -> 128-bit path over n/4 vectors, scalar tail by block 0.
 template <int OP, bool VEC, bool SQRT>
 __global__ void __launch_bounds__(kThreads)
 reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
-                  float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out) {
+                  float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out,
+                  float* __restrict__ partial_lo) {
     float acc[kUnroll], comp[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) acc[u] = comp[u] = 0.f;
@@ -148,6 +176,21 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
             accum1<OP>(acc[0], comp[0], ld_stream(a + i), OP == 1 ? ld_stream(b + i) : 0.f);
     }
 
+    if (OP == 5) {
+        // Kahan's c is the NEGATIVE of the part the running sum lost: thread total = acc - comp
+        float hi = acc[0], lo = -comp[0];
+#pragma unroll
+        for (int u = 1; u < kUnroll; ++u) pair_add(hi, lo, acc[u], -comp[u]);
+        block_pair_sum(hi, lo);
+        if (threadIdx.x == 0) { partial[blockIdx.x] = hi; partial_lo[blockIdx.x] = lo; }
+        if (last_block_done(ticket)) {
+            float rh = 0.f, rl = 0.f;
+            for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) pair_add(rh, rl, __ldcg(partial + i), __ldcg(partial_lo + i));
+            block_pair_sum(rh, rl);
+            if (threadIdx.x == 0) *out = __fadd_rn(rh, rl);
+        }
+        return;
+    }
     constexpr bool ISMAX = OP == 4;
     float v = ISMAX ? fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3])) : (acc[0] + acc[1]) + (acc[2] + acc[3]);
     v = ISMAX ? block_max(v) : block_sum(v);
@@ -366,8 +409,8 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
         static int per_sm = 0;                                                                             \
         if (!per_sm) per_sm = blocks_per_sm(reduce_sum_kernel<OP, true, SQRT>);                            \
         const int grid = reduce_grid(n, c->sm_count, per_sm);                                              \
-        if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out); \
-        else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out); \
+        if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx)); \
+        else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx)); \
     } while (0)
     switch (op) {
         case Reduce::Sum:    LAUNCH(0, false); break;
