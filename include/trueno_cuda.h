@@ -258,6 +258,25 @@ TRN_API int trn_mean_f32(const float* a, size_t n, float* out);
 TRN_API int trn_variance_f32(const float* a, size_t n, float* out);
 TRN_API int trn_stddev_f32(const float* a, size_t n, float* out);
 
+/* ---- device-resident op chaining --------------------------------------
+ * The CUDA counterpart of GpuCommandBatch (src/backends/gpu/batch.rs:118-1019): queue uploads and ops, run
+ * them with ONE graph launch, read results back.  Every BufferId is a slice of one device arena; execute()
+ * uploads the inputs and launches the op sequence as a CUDA graph captured from the same launchers the `_dev`
+ * entry points use (bit-identical results); calling execute() again (after trn_batch_update) replays it.
+ * ops: 0 relu, 1 scale(scalar), 2 add, 3 mul, 4 dot (1-element result), 5 sigmoid, 6 tanh, 7 swish, 8 gelu, 9 sub.
+ * Binary ops on buffers of different sizes: TRN_INVALID_INPUT "Buffer size mismatch: {} vs {}" (the reference
+ * panics with the same text, batch.rs:215-232). */
+typedef struct trn_batch trn_batch;
+TRN_API int trn_batch_create(trn_batch** out);
+TRN_API int trn_batch_destroy(trn_batch* batch);
+TRN_API int trn_batch_upload(trn_batch* batch, const float* data, size_t len, uint32_t* id);
+TRN_API int trn_batch_update(trn_batch* batch, uint32_t id, const float* data, size_t len);
+TRN_API int trn_batch_op(trn_batch* batch, int op, uint32_t a_id, uint32_t b_id, float scalar, uint32_t* out_id);
+TRN_API int trn_batch_execute(trn_batch* batch);
+TRN_API int trn_batch_read(trn_batch* batch, uint32_t id, float* out, size_t len);
+TRN_API size_t trn_batch_num_operations(const trn_batch* batch);
+TRN_API size_t trn_batch_num_buffers(const trn_batch* batch);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

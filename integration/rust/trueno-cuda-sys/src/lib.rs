@@ -18,6 +18,11 @@ pub struct trn_arg_pair {
     pub index: u64,
 }
 
+#[repr(C)]
+pub struct trn_batch {
+    _private: [u8; 0],
+}
+
 pub const TRN_OK: c_int = 0;
 pub const TRN_SIZE_MISMATCH: c_int = 1;
 pub const TRN_INVALID_INPUT: c_int = 2;
@@ -156,6 +161,16 @@ extern "C" {
     pub fn trn_mean_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     pub fn trn_variance_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     pub fn trn_stddev_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    // device-resident op chaining (GpuCommandBatch counterpart, src/backends/gpu/batch.rs)
+    pub fn trn_batch_create(out: *mut *mut trn_batch) -> c_int;
+    pub fn trn_batch_destroy(batch: *mut trn_batch) -> c_int;
+    pub fn trn_batch_upload(batch: *mut trn_batch, data: *const f32, len: usize, id: *mut u32) -> c_int;
+    pub fn trn_batch_update(batch: *mut trn_batch, id: u32, data: *const f32, len: usize) -> c_int;
+    pub fn trn_batch_op(batch: *mut trn_batch, op: c_int, a_id: u32, b_id: u32, scalar: f32, out_id: *mut u32) -> c_int;
+    pub fn trn_batch_execute(batch: *mut trn_batch) -> c_int;
+    pub fn trn_batch_read(batch: *mut trn_batch, id: u32, out: *mut f32, len: usize) -> c_int;
+    pub fn trn_batch_num_operations(batch: *const trn_batch) -> usize;
+    pub fn trn_batch_num_buffers(batch: *const trn_batch) -> usize;
     // engine selection / live timing (benches only)
     pub fn trn_set_gemm_engine(engine: c_int) -> c_int;
     pub fn trn_get_gemm_engine() -> c_int;

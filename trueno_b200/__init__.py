@@ -87,11 +87,16 @@ _SIGNATURES = {
     "trn_clamp_f32": [_vp, _sz, C.c_float, C.c_float, _vp], "trn_clamp_f32_dev": [_vp, _sz, C.c_float, C.c_float, _vp, _vp],
     "trn_lerp_f32": [_vp, _sz, _vp, _sz, C.c_float, _vp], "trn_lerp_f32_dev": [_vp, _sz, _vp, _sz, C.c_float, _vp, _vp],
     "trn_fma_f32": [_vp, _sz, _vp, _sz, _vp, _sz, _vp], "trn_fma_f32_dev": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp],
+    "trn_batch_create": [C.POINTER(_vp)], "trn_batch_destroy": [_vp],
+    "trn_batch_upload": [_vp, _vp, _sz, C.POINTER(C.c_uint32)], "trn_batch_update": [_vp, C.c_uint32, _vp, _sz],
+    "trn_batch_op": [_vp, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_uint32)],
+    "trn_batch_execute": [_vp], "trn_batch_read": [_vp, C.c_uint32, _vp, _sz],
+    "trn_batch_num_operations": [_vp], "trn_batch_num_buffers": [_vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }
 _RESTYPES = {"trn_last_error": _sz, "trn_last_mismatch": None, "trn_launch_count": C.c_uint64,
-             "trn_buf_len": _sz, "trn_buf_ptr": _vp}
+             "trn_buf_len": _sz, "trn_buf_ptr": _vp, "trn_batch_num_operations": _sz, "trn_batch_num_buffers": _sz}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 for _name, _args in _SIGNATURES.items():
@@ -442,6 +447,66 @@ class Matrix:
         out = np.empty(batch * heads * m * n, np.float32)
         check(lib.trn_batched_matmul_4d_f32(_ptr(a), a.size, _ptr(b), b.size, _ptr(out), batch, heads, m, k, n))
         return out
+
+
+class CommandBatch:
+    """Mirror of `GpuCommandBatch` (src/backends/gpu/batch.rs:118-1019): queue uploads and ops, `execute()` them as
+    one CUDA graph launch on the B200, `read()` results back.  BufferIds are plain ints."""
+    _OPS = {"relu": 0, "scale": 1, "add": 2, "mul": 3, "dot": 4, "sigmoid": 5, "tanh": 6, "swish": 7, "gelu": 8, "sub": 9}
+
+    def __init__(self):
+        h = _vp()
+        check(lib.trn_batch_create(C.byref(h)))
+        self._h = h
+        self._sizes: list[int] = []
+
+    def upload(self, data) -> int:
+        a = _as_f32(data)
+        bid = C.c_uint32()
+        check(lib.trn_batch_upload(self._h, _ptr(a), a.size, C.byref(bid)))
+        self._sizes.append(a.size)
+        return bid.value
+
+    def update(self, buffer_id: int, data) -> None:
+        a = _as_f32(data)
+        check(lib.trn_batch_update(self._h, buffer_id, _ptr(a), a.size))
+
+    def _op(self, name: str, a: int, b: int = 0, scalar: float = 0.0) -> int:
+        out = C.c_uint32()
+        check(lib.trn_batch_op(self._h, self._OPS[name], a, b, scalar, C.byref(out)))
+        self._sizes.append(1 if name == "dot" else self._sizes[a])
+        return out.value
+
+    def relu(self, x): return self._op("relu", x)
+    def scale(self, x, scalar: float): return self._op("scale", x, 0, scalar)
+    def add(self, a, b): return self._op("add", a, b)
+    def mul(self, a, b): return self._op("mul", a, b)
+    def dot(self, a, b): return self._op("dot", a, b)
+    def sigmoid(self, x): return self._op("sigmoid", x)
+    def tanh(self, x): return self._op("tanh", x)
+    def swish(self, x): return self._op("swish", x)
+    def gelu(self, x): return self._op("gelu", x)
+    def sub(self, a, b): return self._op("sub", a, b)
+
+    def execute(self) -> None:
+        check(lib.trn_batch_execute(self._h))
+
+    def read(self, buffer_id: int) -> np.ndarray:
+        n = self._sizes[buffer_id] if buffer_id < len(self._sizes) else 0
+        out = np.empty(n, np.float32)
+        check(lib.trn_batch_read(self._h, buffer_id, _ptr(out), n))
+        return out
+
+    def num_operations(self) -> int: return int(lib.trn_batch_num_operations(self._h))
+    def num_buffers(self) -> int: return int(lib.trn_batch_num_buffers(self._h))
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                lib.trn_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def softmax_rows(a, rows: int, cols: int, log: bool = False) -> np.ndarray:
