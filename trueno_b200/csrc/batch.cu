@@ -163,7 +163,9 @@ int trn_batch_execute(trn_batch* b) {   // batch.rs:362
             if (!workspace(s)) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
             cudaGraph_t graph = nullptr;
             TRN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+            const uint64_t before = trn_launch_count();
             const int st = enqueue_ops(b, s);
+            uncount_launch((unsigned)(trn_launch_count() - before));   // captured nodes are not launches yet
             const cudaError_t e = cudaStreamEndCapture(s, &graph);
             if (st != TRN_OK) { if (graph) cudaGraphDestroy(graph); return st; }
             TRN_CUDA(e);

@@ -45,6 +45,7 @@ Context* ctx();
 Workspace* workspace(cudaStream_t s);
 cudaStream_t resolve_stream(void* s);
 void count_launch(unsigned n = 1);
+void uncount_launch(unsigned n);   // launchers called under stream capture record nodes, not launches
 
 // thread-local error state -------------------------------------------------------------------
 int fail(int status, const char* fmt, ...);

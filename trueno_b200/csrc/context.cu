@@ -54,6 +54,7 @@ static char* g_stage[2] = {nullptr, nullptr};
 static cudaEvent_t g_stage_ev[2];
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void uncount_launch(unsigned n) { g_launches.fetch_sub(n, std::memory_order_relaxed); }
 
 static int init_locked(int device) {
     if (g_ctx) {
