@@ -277,6 +277,20 @@ TRN_API int trn_batch_read(trn_batch* batch, uint32_t id, float* out, size_t len
 TRN_API size_t trn_batch_num_operations(const trn_batch* batch);
 TRN_API size_t trn_batch_num_buffers(const trn_batch* batch);
 
+/* ---- callers next to the path -----------------------------------------
+ * Matrix::vecmat (src/matrix.rs:1782): y[cols] = v^T A, accumulated row by row exactly like the reference
+ * (result += row_i * v[i], unfused, ascending i) -> bit-exact.  v_len != rows -> TRN_INVALID_INPUT
+ * "Vector length {} does not match matrix rows {} for vector-matrix multiplication".
+ * Vector::layer_norm (src/vector.rs:1316): `rows` vectors of `cols` elements sharing gamma / beta
+ * (rows == 1 is the reference call): y = gamma * (x - mean) * inv_std + beta.  Empty -> TRN_EMPTY_VECTOR;
+ * gamma / beta length != cols -> TRN_SIZE_MISMATCH{expected = cols, actual}. */
+TRN_API int trn_vecmat_f32(const float* v, size_t v_len, const float* a, size_t rows, size_t cols, float* y);
+TRN_API int trn_vecmat_f32_dev(const float* v, size_t v_len, const float* a, size_t rows, size_t cols, float* y, void* stream);
+TRN_API int trn_layer_norm_rows_f32(const float* a, const float* gamma, size_t gamma_len, const float* beta, size_t beta_len,
+                                    float eps, float* out, size_t rows, size_t cols);
+TRN_API int trn_layer_norm_rows_f32_dev(const float* a, const float* gamma, size_t gamma_len, const float* beta,
+                                        size_t beta_len, float eps, float* out, size_t rows, size_t cols, void* stream);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

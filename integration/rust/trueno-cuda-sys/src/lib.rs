@@ -161,6 +161,12 @@ extern "C" {
     pub fn trn_mean_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     pub fn trn_variance_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     pub fn trn_stddev_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_vecmat_f32(v: *const f32, v_len: usize, a: *const f32, rows: usize, cols: usize, y: *mut f32) -> c_int;
+    pub fn trn_vecmat_f32_dev(v: *const f32, v_len: usize, a: *const f32, rows: usize, cols: usize, y: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_layer_norm_rows_f32(a: *const f32, gamma: *const f32, gamma_len: usize, beta: *const f32, beta_len: usize,
+                                   eps: f32, out: *mut f32, rows: usize, cols: usize) -> c_int;
+    pub fn trn_layer_norm_rows_f32_dev(a: *const f32, gamma: *const f32, gamma_len: usize, beta: *const f32, beta_len: usize,
+                                       eps: f32, out: *mut f32, rows: usize, cols: usize, stream: *mut c_void) -> c_int;
     // device-resident op chaining (GpuCommandBatch counterpart, src/backends/gpu/batch.rs)
     pub fn trn_batch_create(out: *mut *mut trn_batch) -> c_int;
     pub fn trn_batch_destroy(batch: *mut trn_batch) -> c_int;

@@ -97,6 +97,10 @@ class Oracle:
         L.orc_scalar_map.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
         for name in ("scalar_sum_kahan", "scalar_norm_l1", "scalar_norm_linf"):
             f = getattr(L, "orc_" + name); f.restype = C.c_float; f.argtypes = [_f32p, C.c_size_t]
+        L.orc_vecmat.restype = None
+        L.orc_vecmat.argtypes = [_f32p, _f32p, C.c_size_t, C.c_size_t, _f32p]
+        L.orc_layer_norm.restype = None
+        L.orc_layer_norm.argtypes = [_f32p, _f32p, _f32p, C.c_float, _f32p, C.c_size_t]
         L.orc_last_mismatch.restype = None
         L.orc_last_mismatch.argtypes = [_u64p, _u64p]
         L.orc_set_threads.argtypes = [C.c_int]
@@ -182,6 +186,18 @@ class Oracle:
     def sum_kahan(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_sum_kahan(_p(a), a.size))
     def norm_l1(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_norm_l1(_p(a), a.size))
     def norm_linf(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_norm_linf(_p(a), a.size))
+
+    def vecmat(self, v, A, rows, cols):
+        v, A = _f32(v), _f32(A)
+        out = np.empty(cols, np.float32)
+        self.lib.orc_vecmat(_p(v), _p(A), rows, cols, _p(out))
+        return out
+
+    def layer_norm(self, x, gamma, beta, eps):
+        x, gamma, beta = _f32(x), _f32(gamma), _f32(beta)
+        out = np.empty(x.size, np.float32)
+        self.lib.orc_layer_norm(_p(x), _p(gamma), _p(beta), eps, _p(out), x.size)
+        return out
 
     def exp_avx2(self, a):
         a = _f32(a)

@@ -817,3 +817,32 @@ ORC_API float orc_scalar_norm_linf(const float* a, size_t n) {
     }
     return m;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Callers next to the path
+ * ---------------------------------------------------------------------------------------- */
+/* src/matrix.rs:1782-1816 — result = sum_i row_i.scale(v[i]) accumulated in order: unfused mul then add */
+ORC_API void orc_vecmat(const float* v, const float* a, size_t rows, size_t cols, float* y) {
+    for (size_t j = 0; j < cols; ++j) y[j] = 0.f;
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t j = 0; j < cols; ++j) {
+            float s = a[i * cols + j] * v[i];
+            y[j] = y[j] + s;
+        }
+}
+/* src/vector.rs:1316-1362 — mean = sum/n (sequential f32 sum here: the scalar backend's sum), variance =
+ * sequential sum of (x-mean)^2 / n, inv_std = 1/sqrt(var+eps), y = g*(x-mean)*inv_std + b (unfused) */
+ORC_API void orc_layer_norm(const float* x, const float* g, const float* b, float eps, float* y, size_t n) {
+    float sum = 0.f;
+    for (size_t i = 0; i < n; ++i) sum += x[i];
+    const float mean = sum / (float)n;
+    float var = 0.f;
+    for (size_t i = 0; i < n; ++i) { float d = x[i] - mean; var += d * d; }
+    var = var / (float)n;
+    const float inv_std = 1.0f / sqrtf(var + eps);
+    for (size_t i = 0; i < n; ++i) {
+        float t = g[i] * (x[i] - mean);
+        t = t * inv_std;
+        y[i] = t + b[i];
+    }
+}

@@ -45,3 +45,15 @@ def test_oracle_semantics_corner_cases(oracle):
     # Kahan keeps what the plain left-to-right sum loses
     v = np.array([1e8] + [1.0] * 1000, f32)
     assert float(oracle.sum_kahan(v)) == 1e8 + 1000
+
+
+def test_oracle_vecmat_and_layer_norm_kats(oracle):
+    # src/matrix.rs:3543-3555: [1,2,3] x [[1,2],[3,4],[5,6]] = [22, 28]
+    assert oracle.vecmat([1, 2, 3], [1, 2, 3, 4, 5, 6], 3, 2).tolist() == [22.0, 28.0]
+    # src/vector.rs:7656-7703: normalised output has mean ~0 / variance ~1, then scale 2 / shift 1
+    y = oracle.layer_norm([1, 2, 3, 4], [1] * 4, [0] * 4, 1e-5)
+    assert abs(y.mean()) < 1e-5 and abs(y.var() - 1) < 1e-3
+    y = oracle.layer_norm([1, 2, 3, 4], [2] * 4, [1] * 4, 1e-5)
+    assert abs(y.mean() - 1) < 1e-3 and abs(y.std() - 2) < 1e-3
+    assert np.all(np.abs(oracle.layer_norm([5] * 4, [1] * 4, [0] * 4, 1e-5)) < 1e-3)   # :7745
+    assert abs(oracle.layer_norm([42], [1], [0], 1e-5)[0]) < 1e-3                       # :7760

@@ -126,3 +126,60 @@ def test_kahan_keeps_small_terms(trn, oracle):
     """The reference's own motivation for sum_kahan (src/vector.rs:848 doc): 1e8 followed by ones."""
     v = np.array([1e8] + [1.0] * 100_000, f32)
     assert float(trn.Vector.from_slice(v).sum_kahan()) == float(oracle.sum_kahan(v)) == 1e8 + 100_000
+
+
+def test_vecmat_bit_exact_and_errors(trn, oracle):
+    V, M = trn.Vector, trn.Matrix
+    r = M.vecmat(V.from_slice([1, 2, 3]), M.from_vec(3, 2, [1, 2, 3, 4, 5, 6])).as_slice()     # src/matrix.rs:3543
+    assert r.tolist() == [22.0, 28.0]
+    with pytest.raises(trn.TruenoError) as e:                                                  # src/matrix.rs:3567
+        M.vecmat(V.from_slice([1, 2]), M.from_vec(3, 2, [1, 2, 3, 4, 5, 6]))
+    assert e.value.message == "Vector length 2 does not match matrix rows 3 for vector-matrix multiplication"
+    rng = np.random.default_rng(8)
+    for rows, cols in ((1, 1), (7, 5), (300, 1001), (1025, 4096)):
+        v = rng.standard_normal(rows).astype(f32)
+        v[::3] = 0                                   # unlike matmul's rows == 1 path, zeros are NOT skipped
+        A = rng.standard_normal((rows, cols)).astype(f32)
+        if rows > 2:
+            A[0, 0] = np.inf                         # 0 * inf = NaN must propagate here
+        got = M.vecmat(V.from_slice(v), M.from_vec(rows, cols, A)).as_slice()
+        want = oracle.vecmat(v, A, rows, cols)
+        assert np.array_equal(got, want, equal_nan=True), (rows, cols)
+
+
+def test_layer_norm_reference_tests_and_oracle(trn, oracle):
+    V, E = trn.Vector, trn.TruenoError
+    y = V.from_slice([1, 2, 3, 4]).layer_norm(V.from_slice([1] * 4), V.from_slice([0] * 4), 1e-5).as_slice()
+    assert abs(y.mean()) < 1e-5 and abs(y.var() - 1) < 1e-3                                     # src/vector.rs:7656
+    y = V.from_slice([1, 2, 3, 4]).layer_norm(V.from_slice([2] * 4), V.from_slice([1] * 4), 1e-5).as_slice()
+    assert abs(y.mean() - 1) < 1e-3 and abs(y.std() - 2) < 1e-3                                 # :7682
+    with pytest.raises(E) as e:
+        V.from_slice([]).layer_norm(V.from_slice([]), V.from_slice([]), 1e-5)                   # :7705
+    assert e.value == E.EmptyVector
+    with pytest.raises(E) as e:
+        V.from_slice([1, 2, 3]).layer_norm(V.from_slice([1, 1]), V.from_slice([0, 0, 0]), 1e-5)  # :7715
+    assert e.value == E.SizeMismatch(3, 2)
+    with pytest.raises(E) as e:
+        V.from_slice([1, 2, 3]).layer_norm(V.from_slice([1, 1, 1]), V.from_slice([0, 0]), 1e-5)  # :7725
+    assert e.value == E.SizeMismatch(3, 2)
+    assert np.all(np.abs(V.from_slice([5] * 4).layer_norm(V.from_slice([1] * 4), V.from_slice([0] * 4), 1e-5).as_slice()) < 1e-3)
+    rng = np.random.default_rng(12)
+    for n in (1, 5, 1000, 4097, 100_003):
+        x = (rng.standard_normal(n) * 3 + 1).astype(f32)
+        g, b = rng.standard_normal(n).astype(f32), rng.standard_normal(n).astype(f32)
+        got = V.from_slice(x).layer_norm(V.from_slice(g), V.from_slice(b), 1e-5).as_slice()
+        want = oracle.layer_norm(x, g, b, 1e-5)
+        xd = x.astype(np.float64)
+        truth = g * (xd - xd.mean()) / np.sqrt(xd.var() + 1e-5) + b
+        # stated tolerance: 1e-5 relative to |gamma| * |x - mean| / std + |beta| (mean / variance are f32 sums)
+        scale = np.abs(g) * np.abs(xd - xd.mean()) / np.sqrt(xd.var() + 1e-5) + np.abs(b) + 1e-6
+        assert np.all(np.abs(got - truth) <= 1e-5 * scale + 2e-6 * np.abs(g)), n
+        assert np.all(np.abs(got - want) <= 2e-5 * scale + 4e-6 * np.abs(g)), n
+    # rows sharing gamma / beta: every row equals the single-vector call
+    rows, cols = 33, 2048
+    X = rng.standard_normal((rows, cols)).astype(f32)
+    g, b = rng.standard_normal(cols).astype(f32), rng.standard_normal(cols).astype(f32)
+    out = np.empty_like(X)
+    trn.check(trn.lib.trn_layer_norm_rows_f32(X.ctypes.data, g.ctypes.data, cols, b.ctypes.data, cols, 1e-5, out.ctypes.data, rows, cols))
+    for r in (0, 17, 32):
+        assert np.array_equal(out[r], V.from_slice(X[r]).layer_norm(V.from_slice(g), V.from_slice(b), 1e-5).as_slice())

@@ -92,6 +92,9 @@ _SIGNATURES = {
     "trn_batch_op": [_vp, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_uint32)],
     "trn_batch_execute": [_vp], "trn_batch_read": [_vp, C.c_uint32, _vp, _sz],
     "trn_batch_num_operations": [_vp], "trn_batch_num_buffers": [_vp],
+    "trn_vecmat_f32": [_vp, _sz, _vp, _sz, _sz, _vp], "trn_vecmat_f32_dev": [_vp, _sz, _vp, _sz, _sz, _vp, _vp],
+    "trn_layer_norm_rows_f32": [_vp, _vp, _sz, _vp, _sz, C.c_float, _vp, _sz, _sz],
+    "trn_layer_norm_rows_f32_dev": [_vp, _vp, _sz, _vp, _sz, C.c_float, _vp, _sz, _sz, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }
@@ -371,6 +374,13 @@ class Vector:
             raise TruenoError("DivisionByZero")
         return self.scale(float(np.float32(1.0) / norm))
 
+    def layer_norm(self, gamma: "Vector", beta: "Vector", eps: float) -> "Vector":
+        """Vector::layer_norm (src/vector.rs:1316)."""
+        out = np.empty(self.data.size, np.float32)
+        check(lib.trn_layer_norm_rows_f32(_ptr(self.data), _ptr(gamma.data), gamma.data.size, _ptr(beta.data), beta.data.size,
+                                          eps, _ptr(out), 1 if self.data.size else 0, self.data.size))
+        return Vector(out)
+
     # ---- softmax family (src/vector.rs:1516, 1581): a Vector is one row ----
     def softmax(self) -> "Vector":
         out = np.empty(self.data.size, np.float32)
@@ -433,6 +443,13 @@ class Matrix:
         out = np.empty(self.data.size, np.float32)
         check(lib.trn_transpose_f32(_ptr(self.data), self._rows, self._cols, _ptr(out)))
         return Matrix(self._cols, self._rows, out)
+
+    @staticmethod
+    def vecmat(v: Vector, m: "Matrix") -> Vector:
+        """Matrix::vecmat (src/matrix.rs:1782): v^T * m."""
+        out = np.empty(m._cols, np.float32)
+        check(lib.trn_vecmat_f32(_ptr(v.data), v.data.size, _ptr(m.data), m._rows, m._cols, _ptr(out)))
+        return Vector(out)
 
     @staticmethod
     def batched_matmul(a, b, batch: int, m: int, k: int, n: int) -> np.ndarray:

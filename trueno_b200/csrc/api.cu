@@ -733,4 +733,68 @@ int trn_stddev_f32(const float* a, size_t n, float* out) {
     return TRN_OK;
 }
 
+// ===================== callers next to the path =====================
+// Matrix::vecmat (src/matrix.rs:1782): y = v^T A; v_len != rows -> InvalidInput
+int trn_vecmat_f32_dev(const float* v, size_t v_len, const float* a, size_t rows, size_t cols, float* y, void* stream) {
+    if (v_len != rows)
+        return fail(TRN_INVALID_INPUT, "Vector length %zu does not match matrix rows %zu for vector-matrix multiplication",
+                    v_len, rows);
+    TRN_TRY(need_ctx());
+    cudaStream_t s = resolve_stream(stream);
+    if (rows == 0 && cols > 0) {
+        TRN_CUDA(cudaMemsetAsync(y, 0, cols * sizeof(float), s));
+        return TRN_OK;
+    }
+    return launch_vecmat(v, a, rows, cols, y, s, false);
+}
+int trn_vecmat_f32(const float* v, size_t v_len, const float* a, size_t rows, size_t cols, float* y) {
+    if (v_len != rows)
+        return fail(TRN_INVALID_INPUT, "Vector length %zu does not match matrix rows %zu for vector-matrix multiplication",
+                    v_len, rows);
+    TRN_TRY(need_ctx());
+    Context* c = ctx();
+    if (cols == 0) return TRN_OK;
+    DevTemp da(c->stream), dv(c->stream), dy(c->stream);
+    TRN_TRY(da.alloc(rows * cols));
+    TRN_TRY(dv.alloc(rows));
+    TRN_TRY(dy.alloc(cols));
+    TRN_TRY(upload(da.p, a, rows * cols, c->stream));
+    TRN_TRY(upload(dv.p, v, rows, c->stream));
+    if (rows == 0) TRN_CUDA(cudaMemsetAsync(dy.p, 0, cols * sizeof(float), c->stream));
+    else TRN_TRY(launch_vecmat(dv.p, da.p, rows, cols, dy.p, c->stream, false));
+    return download(y, dy.p, cols, c->stream);
+}
+
+// Vector::layer_norm (src/vector.rs:1316): `rows` vectors of `cols` elements sharing gamma / beta (rows == 1 is
+// exactly the reference call).  Empty -> EmptyVector; gamma / beta length != cols -> SizeMismatch{cols, len}.
+static int check_layer_norm(size_t rows, size_t cols, size_t ng, size_t nb) {
+    TRN_TRY(check_nonempty_emptyvec(rows * cols));
+    if (ng != cols) return fail_mismatch(cols, ng);
+    if (nb != cols) return fail_mismatch(cols, nb);
+    return TRN_OK;
+}
+int trn_layer_norm_rows_f32_dev(const float* a, const float* gamma, size_t gamma_len, const float* beta, size_t beta_len,
+                                float eps, float* out, size_t rows, size_t cols, void* stream) {
+    TRN_TRY(check_layer_norm(rows, cols, gamma_len, beta_len));
+    TRN_TRY(need_ctx());
+    return launch_layer_norm_rows(a, gamma, beta, eps, out, rows, cols, resolve_stream(stream));
+}
+int trn_layer_norm_rows_f32(const float* a, const float* gamma, size_t gamma_len, const float* beta, size_t beta_len,
+                            float eps, float* out, size_t rows, size_t cols) {
+    TRN_TRY(check_layer_norm(rows, cols, gamma_len, beta_len));
+    TRN_TRY(need_ctx());
+    Context* c = ctx();
+    const size_t n = rows * cols;
+    DevTemp da(c->stream), dg(c->stream), db(c->stream), dout(c->stream);
+    TRN_TRY(da.alloc(n));
+    TRN_TRY(dg.alloc(cols));
+    TRN_TRY(db.alloc(cols));
+    TRN_TRY(dout.alloc(n));
+    TRN_TRY(upload(da.p, a, n, c->stream));
+    TRN_TRY(upload(dg.p, gamma, cols, c->stream));
+    TRN_TRY(upload(db.p, beta, cols, c->stream));
+    TRN_TRY(launch_layer_norm_rows(da.p, dg.p, db.p, eps, dout.p, rows, cols, c->stream));
+    return download(out, dout.p, n, c->stream);
+}
+
 }  // extern "C"

@@ -95,7 +95,9 @@ int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows
 
 int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaStream_t s);
 int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, float* y, cudaStream_t s);
-int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s);
+int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s, bool skip_zero = true);
+int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta, float eps, float* out, size_t rows,
+                           size_t cols, cudaStream_t s);
 // C[b] = A[b] * B[b], b in [0,batch); strides in elements
 // only_if_flag != nullptr: the kernel returns immediately unless *only_if_flag != 0 (device-side fallback)
 int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,

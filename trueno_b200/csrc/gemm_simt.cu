@@ -111,6 +111,9 @@ int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, floa
 // output column, p ascending, __fmul_rn + __fadd_rn => bit-identical to the reference's path.
 // B is streamed once with coalesced rows: 4 B per element of B.
 // ---------------------------------------------------------------------------------------------
+// SKIP_ZERO = true : Matrix::matmul with rows == 1 (src/matrix.rs:552-566 skips x[p] == 0.0)
+// SKIP_ZERO = false: Matrix::vecmat (src/matrix.rs:1782-1816: result += row_p.scale(v[p]), every p, unfused)
+template <bool SKIP_ZERO>
 __global__ void __launch_bounds__(256)
 vecmat_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, size_t k, size_t n) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
@@ -120,26 +123,27 @@ vecmat_kernel(const float* __restrict__ x, const float* __restrict__ b, float* _
             const float x0 = __ldg(x + p), x1 = __ldg(x + p + 1), x2 = __ldg(x + p + 2), x3 = __ldg(x + p + 3);
             const float b0 = ld_stream(b + p * n + j), b1 = ld_stream(b + (p + 1) * n + j),
                         b2 = ld_stream(b + (p + 2) * n + j), b3 = ld_stream(b + (p + 3) * n + j);
-            if (x0 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x0, b0));
-            if (x1 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x1, b1));
-            if (x2 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x2, b2));
-            if (x3 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x3, b3));
+            if (!SKIP_ZERO || x0 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x0, b0));
+            if (!SKIP_ZERO || x1 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x1, b1));
+            if (!SKIP_ZERO || x2 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x2, b2));
+            if (!SKIP_ZERO || x3 != 0.0f) acc = __fadd_rn(acc, __fmul_rn(x3, b3));
         }
         for (; p < k; ++p) {
             const float xp = __ldg(x + p);
-            if (xp != 0.0f) acc = __fadd_rn(acc, __fmul_rn(xp, ld_stream(b + p * n + j)));
+            if (!SKIP_ZERO || xp != 0.0f) acc = __fadd_rn(acc, __fmul_rn(xp, ld_stream(b + p * n + j)));
         }
         y[j] = acc;
     }
 }
 
-int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s) {
+int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s, bool skip_zero) {
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
     if (n == 0) return TRN_OK;
     size_t blocks = (n + 127) / 128;
     size_t cap = (size_t)c->sm_count * 16;
-    vecmat_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, s>>>(x, b, y, k, n);
+    if (skip_zero) vecmat_kernel<true><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, s>>>(x, b, y, k, n);
+    else           vecmat_kernel<false><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, s>>>(x, b, y, k, n);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;

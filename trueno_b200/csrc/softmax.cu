@@ -361,4 +361,44 @@ int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows
                        : dispatch<false>(a, out, rows, cols, c->sm_count, s);
 }
 
+// ---- layer_norm rows --------------------------------------------------------------
+// Vector::layer_norm (src/vector.rs:1316-1362): mean = sum / n; variance = sum((x - mean)^2) / n;
+// inv_std = 1 / sqrt(variance + eps); y = gamma * (x - mean) * inv_std + beta, evaluated per element in exactly
+// that (unfused) order.  `rows` independent vectors share gamma / beta.  One CTA per row: the first pass
+// streams the row from HBM, the second and third hit L1/L2 (a row is <= a few hundred KiB), so HBM sees one
+// read and one write per element.  Fixed trees -> deterministic.
+__global__ void __launch_bounds__(kThreads)
+layer_norm_rows_kernel(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float eps, float* __restrict__ out, size_t rows, size_t cols) {
+    __shared__ float s_w[kThreads / 32];
+    for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float* src = in + row * cols;
+        float* dst = out + row * cols;
+        float part = 0.f;
+        for (size_t i = threadIdx.x; i < cols; i += kThreads) part += src[i];
+        const float mean = block_sum_256(part, s_w) / (float)cols;
+        part = 0.f;
+        for (size_t i = threadIdx.x; i < cols; i += kThreads) {
+            const float d = __fsub_rn(src[i], mean);
+            part = __fadd_rn(part, __fmul_rn(d, d));
+        }
+        const float var = block_sum_256(part, s_w) / (float)cols;
+        const float inv_std = 1.0f / sqrtf(var + eps);
+        for (size_t i = threadIdx.x; i < cols; i += kThreads)
+            dst[i] = __fadd_rn(__fmul_rn(__fmul_rn(gamma[i], __fsub_rn(src[i], mean)), inv_std), beta[i]);
+    }
+}
+
+int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta, float eps, float* out, size_t rows,
+                           size_t cols, cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    if (rows == 0 || cols == 0) return TRN_OK;
+    const size_t cap = (size_t)c->sm_count * 8;
+    layer_norm_rows_kernel<<<(unsigned)(rows < cap ? rows : cap), kThreads, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
 }  // namespace trn
