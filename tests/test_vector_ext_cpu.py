@@ -48,8 +48,8 @@ def test_oracle_semantics_corner_cases(oracle):
 
 
 def test_oracle_vecmat_and_layer_norm_kats(oracle):
-    # src/matrix.rs:3543-3555: [1,2,3] x [[1,2],[3,4],[5,6]] = [22, 28]
-    assert oracle.vecmat([1, 2, 3], [1, 2, 3, 4, 5, 6], 3, 2).tolist() == [22.0, 28.0]
+    # src/matrix.rs:3543-3555: [1,2] x [[1,2,3],[4,5,6]] = [9, 12, 15]
+    assert oracle.vecmat([1, 2], [1, 2, 3, 4, 5, 6], 2, 3).tolist() == [9.0, 12.0, 15.0]
     # src/vector.rs:7656-7703: normalised output has mean ~0 / variance ~1, then scale 2 / shift 1
     y = oracle.layer_norm([1, 2, 3, 4], [1] * 4, [0] * 4, 1e-5)
     assert abs(y.mean()) < 1e-5 and abs(y.var() - 1) < 1e-3

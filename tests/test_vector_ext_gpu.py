@@ -130,8 +130,8 @@ def test_kahan_keeps_small_terms(trn, oracle):
 
 def test_vecmat_bit_exact_and_errors(trn, oracle):
     V, M = trn.Vector, trn.Matrix
-    r = M.vecmat(V.from_slice([1, 2, 3]), M.from_vec(3, 2, [1, 2, 3, 4, 5, 6])).as_slice()     # src/matrix.rs:3543
-    assert r.tolist() == [22.0, 28.0]
+    r = M.vecmat(V.from_slice([1, 2]), M.from_vec(2, 3, [1, 2, 3, 4, 5, 6])).as_slice()        # src/matrix.rs:3543
+    assert r.tolist() == [9.0, 12.0, 15.0]
     with pytest.raises(trn.TruenoError) as e:                                                  # src/matrix.rs:3567
         M.vecmat(V.from_slice([1, 2]), M.from_vec(3, 2, [1, 2, 3, 4, 5, 6]))
     assert e.value.message == "Vector length 2 does not match matrix rows 3 for vector-matrix multiplication"
