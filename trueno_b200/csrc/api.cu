@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,12 @@ std::string fmt_f32(float v) {
 }
 
 std::atomic<int> g_engine{0};
+
+// Host-slice calls stage through the ONE backend stream and its per-stream scalar slots / pinned staging ring,
+// so concurrent callers (the reference's rayon workers may call a backend from several threads) are serialised
+// here.  `_dev` calls take caller-owned memory and streams and need no lock.
+std::mutex g_host_mu;
+#define TRN_HOST_LOCK() std::lock_guard<std::mutex> _host_lock(g_host_mu)
 
 // U+00D7 MULTIPLICATION SIGN, as the reference's format strings use (src/matrix.rs:288, :398, :484)
 #define X "\xC3\x97"
@@ -130,6 +137,7 @@ struct DevTemp {
 
 template <class F>
 int host_reduce_f32(const float* a, size_t na, const float* b, size_t nb, float* out, F&& launch) {
+    TRN_HOST_LOCK();
     Context* c = ctx();
     Workspace* w = workspace(c->stream);
     if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
@@ -148,6 +156,7 @@ int host_reduce_f32(const float* a, size_t na, const float* b, size_t nb, float*
 }
 
 int host_arg(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val) {
+    TRN_HOST_LOCK();
     Context* c = ctx();
     Workspace* w = workspace(c->stream);
     if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
@@ -164,6 +173,7 @@ int host_arg(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out
 }
 
 int host_map(Map op, const float* a, const float* b, const float* c3, float* out, size_t n, float p0 = 0.f, float p1 = 0.f) {
+    TRN_HOST_LOCK();
     Context* c = ctx();
     if (n == 0) return TRN_OK;
     DevTemp da(c->stream), db(c->stream), dc(c->stream), dout(c->stream);
@@ -406,6 +416,7 @@ int trn_gelu_f32(const float* a, size_t n, float* out) {
 static int host_softmax(int log_variant, const float* a, float* out, size_t rows, size_t cols) {
     TRN_TRY(check_nonempty_emptyvec(rows * cols));
     TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
     Context* c = ctx();
     const size_t n = rows * cols;
     DevTemp da(c->stream), dout(c->stream);
@@ -442,11 +453,25 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     const size_t kpad = gemm_tc_kpad(k);
     const bool single = batch == 1;
     // work units: row blocks of one product, or groups of whole (batch*head) products
-    size_t unit_rows = m, units = batch, per_block = 1;
+    size_t units = batch, per_block = 1;
+    std::vector<size_t> row_start;   // single product: start row of every block, plus m as the sentinel
     if (single) {
-        unit_rows = 128 * ((m / 8 + 127) / 128);          // ~8 blocks, multiples of the 128-row tile
-        if (unit_rows < 128) unit_rows = 128;
-        units = (m + unit_rows - 1) / unit_rows;
+        // ~8 blocks of whole 256-row pair tiles; the LAST block is cut into 1/2 + 1/4 + 1/4 so the tail that
+        // cannot overlap anything (last split + GEMM + D2H) is a quarter block instead of a whole one
+        size_t unit_rows = 256 * ((m / 8 + 255) / 256);
+        if (unit_rows < 256) unit_rows = 256;
+        size_t r = 0;
+        while (m - r > unit_rows) { row_start.push_back(r); r += unit_rows; }
+        const size_t last = m - r, q = 256 * ((last / 4 + 255) / 256);
+        if (last >= 1024 && 3 * q < last) {
+            row_start.push_back(r);
+            row_start.push_back(r + last - 2 * q);
+            row_start.push_back(r + last - q);
+        } else {
+            row_start.push_back(r);
+        }
+        units = row_start.size();
+        row_start.push_back(m);
     } else {
         const size_t bytes_per = (m * k + k * n + m * n) * sizeof(float);
         per_block = ((size_t)64 << 20) / (bytes_per ? bytes_per : 1);   // ~64 MiB of traffic per group
@@ -491,7 +516,7 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     }
     for (size_t u = 0; u < units && st == TRN_OK; ++u) {
         if (single) {
-            const size_t r0 = u * unit_rows, rows = m - r0 < unit_rows ? m - r0 : unit_rows;
+            const size_t r0 = row_start[u], rows = row_start[u + 1] - r0;
             TRN_CUDA(cudaMemcpyAsync(da + r0 * k, a + r0 * k, rows * k * sizeof(float), cudaMemcpyHostToDevice, s_up));
             TRN_CUDA(cudaEventRecord(up[u].e, s_up));
             TRN_CUDA(cudaStreamWaitEvent(s_main, up[u].e, 0));
@@ -528,6 +553,7 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
 }
 
 static int host_gemm(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n) {
+    TRN_HOST_LOCK();
     Context* cx = ctx();
     const size_t na = batch * m * k, nb = batch * k * n, nc = batch * m * n;
     if (nc == 0) return TRN_OK;
@@ -566,6 +592,7 @@ int trn_batched_matmul_4d_f32(const float* a, size_t a_len, const float* b, size
 int trn_matvec_f32(const float* a, size_t rows, size_t cols, const float* v, size_t v_len, float* y) {
     TRN_TRY(check_matvec(cols, v_len));
     TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
     Context* c = ctx();
     if (rows == 0) return TRN_OK;
     DevTemp da(c->stream), dv(c->stream), dy(c->stream);
@@ -580,6 +607,7 @@ int trn_matvec_f32(const float* a, size_t rows, size_t cols, const float* v, siz
 }
 int trn_transpose_f32(const float* a, size_t rows, size_t cols, float* out) {
     TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
     Context* c = ctx();
     const size_t n = rows * cols;
     if (n == 0) return TRN_OK;
@@ -700,6 +728,7 @@ TRN_REDUCE(norm_linf, MaxAbs)
 // mean / variance / stddev (src/vector.rs:935-1030): empty -> EmptyVector; mean = sum / n;
 // variance = E[x^2] - mean^2 with both moments from the device reductions; stddev = sqrt(variance)
 static int host_moments(const float* a, size_t n, float* mean, float* var) {
+    TRN_HOST_LOCK();
     TRN_TRY(check_nonempty_emptyvec(n));
     TRN_TRY(need_ctx());
     Context* c = ctx();
@@ -752,6 +781,7 @@ int trn_vecmat_f32(const float* v, size_t v_len, const float* a, size_t rows, si
         return fail(TRN_INVALID_INPUT, "Vector length %zu does not match matrix rows %zu for vector-matrix multiplication",
                     v_len, rows);
     TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
     Context* c = ctx();
     if (cols == 0) return TRN_OK;
     DevTemp da(c->stream), dv(c->stream), dy(c->stream);
@@ -783,6 +813,7 @@ int trn_layer_norm_rows_f32(const float* a, const float* gamma, size_t gamma_len
                             float eps, float* out, size_t rows, size_t cols) {
     TRN_TRY(check_layer_norm(rows, cols, gamma_len, beta_len));
     TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
     Context* c = ctx();
     const size_t n = rows * cols;
     DevTemp da(c->stream), dg(c->stream), db(c->stream), dout(c->stream);

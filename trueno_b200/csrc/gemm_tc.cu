@@ -731,11 +731,9 @@ template <int TERMS, int SBK>
 static int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                   const CUtensorMap& mc, const Params& p, int sm_count, cudaStream_t s) {
     using C = Cfg<TERMS, SBK>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TRN_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<TERMS, SBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        attr_set = true;
-    }
+    // thread-safe one-time opt-in to > 48 KiB of dynamic shared memory
+    static const cudaError_t attr = cudaFuncSetAttribute(gemm_tf32_kernel<TERMS, SBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    TRN_CUDA(attr);
     const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
     const uint32_t grid = total < (uint32_t)sm_count ? total : (uint32_t)sm_count;
     gemm_tf32_kernel<TERMS, SBK><<<grid, kThreads, C::kSmemBytes, s>>>(ah, al, bh, bl, mc, p);
@@ -829,11 +827,8 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
         p.tiles_m = (uint32_t)((m + 2 * BM - 1) / (2 * BM));
         p.tiles_n = (uint32_t)((n + BN - 1) / BN);
         p.batch = (uint32_t)batch;
-        static bool attr_set = false;
-        if (!attr_set) {
-            TRN_CUDA(cudaFuncSetAttribute(gemm_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytes));
-            attr_set = true;
-        }
+        static const cudaError_t smem_optin = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytes);
+        TRN_CUDA(smem_optin);
         const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
         const uint32_t max_pairs = (uint32_t)cx->sm_count / 2;
         const uint32_t pairs = total < max_pairs ? total : max_pairs;

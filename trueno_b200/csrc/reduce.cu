@@ -406,8 +406,7 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
     const bool vec = aligned16(a) && (op != Reduce::Dot || aligned16(b));
 #define LAUNCH(OP, SQRT)                                                                                   \
     do {                                                                                                   \
-        static int per_sm = 0;                                                                             \
-        if (!per_sm) per_sm = blocks_per_sm(reduce_sum_kernel<OP, true, SQRT>);                            \
+        static const int per_sm = blocks_per_sm(reduce_sum_kernel<OP, true, SQRT>);   /* thread-safe, once */ \
         const int grid = reduce_grid(n, c->sm_count, per_sm);                                              \
         if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx)); \
         else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx)); \
@@ -433,11 +432,8 @@ int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, fl
     if (!c) return TRN_GPU_ERROR;
     Workspace* w = workspace(s);
     if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
-    static int per_sm_max = 0, per_sm_min = 0;
-    if (!per_sm_max) {
-        per_sm_max = blocks_per_sm(argreduce_kernel<true, true>);
-        per_sm_min = blocks_per_sm(argreduce_kernel<false, true>);
-    }
+    static const int per_sm_max = blocks_per_sm(argreduce_kernel<true, true>);    // thread-safe, once
+    static const int per_sm_min = blocks_per_sm(argreduce_kernel<false, true>);
     const int grid = reduce_grid(n, c->sm_count, is_max ? per_sm_max : per_sm_min);
     const bool vec = aligned16(a);
     if (is_max) {

@@ -268,12 +268,9 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
 
 template <bool LOG>
 static int launch_ring(const float* a, float* out, size_t rows, size_t cols, int sm_count, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        TRN_CUDA(cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)ring::kSmemBytes));
-        attr_set = true;
-    }
+    static const cudaError_t attr = cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)ring::kSmemBytes);   // thread-safe, once
+    TRN_CUDA(attr);
     const unsigned grid = (unsigned)(rows < (size_t)sm_count ? rows : (size_t)sm_count);
     softmax_rows_ring_kernel<LOG><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols);
     count_launch();
