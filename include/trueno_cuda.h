@@ -291,6 +291,26 @@ TRN_API int trn_layer_norm_rows_f32(const float* a, const float* gamma, size_t g
 TRN_API int trn_layer_norm_rows_f32_dev(const float* a, const float* gamma, size_t gamma_len, const float* beta,
                                         size_t beta_len, float eps, float* out, size_t rows, size_t cols, void* stream);
 
+/* ---- fused slice reduction + exchange over NVLink peer memory -----------------
+ * One process per GPU.  Each process exports a small mailbox (trn_comm_local_handle: a 64-byte CUDA IPC
+ * handle), the host all-gathers the handles once, trn_comm_create maps the peers' mailboxes.  The
+ * `_allreduce` / `_allgather` reductions then need no separate collective: the last block of the slice kernel
+ * writes its result into every peer's mailbox with P2P stores and folds all ranks' results in rank order, so
+ * every rank gets the bit-identical whole-vector answer from ONE launch.  Collective rules: same calls, same
+ * order, one stream per process; world <= 8.  The argmax/argmin variants apply the scalar-backend rule across
+ * slices (NaN seed of slice 0 wins, else best value then lowest global index). */
+typedef struct trn_comm trn_comm;
+TRN_API int trn_comm_local_handle(void* handle64);
+TRN_API int trn_comm_create(int rank, int world, const void* handles, trn_comm** out);
+TRN_API int trn_comm_destroy(trn_comm* comm);
+TRN_API int trn_sum_allreduce_f32_dev(trn_comm* comm, const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_dot_allreduce_f32_dev(trn_comm* comm, const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_norm_l2_allreduce_f32_dev(trn_comm* comm, const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_argmax_allgather_f32_dev(trn_comm* comm, const float* a, size_t n, uint64_t slice_start, uint64_t* out_idx,
+                                         float* out_value, void* stream);
+TRN_API int trn_argmin_allgather_f32_dev(trn_comm* comm, const float* a, size_t n, uint64_t slice_start, uint64_t* out_idx,
+                                         float* out_value, void* stream);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

@@ -19,6 +19,11 @@ pub struct trn_arg_pair {
 }
 
 #[repr(C)]
+pub struct trn_comm {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
 pub struct trn_batch {
     _private: [u8; 0],
 }
@@ -167,6 +172,18 @@ extern "C" {
                                    eps: f32, out: *mut f32, rows: usize, cols: usize) -> c_int;
     pub fn trn_layer_norm_rows_f32_dev(a: *const f32, gamma: *const f32, gamma_len: usize, beta: *const f32, beta_len: usize,
                                        eps: f32, out: *mut f32, rows: usize, cols: usize, stream: *mut c_void) -> c_int;
+    // fused slice reduction + exchange over NVLink peer memory
+    pub fn trn_comm_local_handle(handle64: *mut c_void) -> c_int;
+    pub fn trn_comm_create(rank: c_int, world: c_int, handles: *const c_void, out: *mut *mut trn_comm) -> c_int;
+    pub fn trn_comm_destroy(comm: *mut trn_comm) -> c_int;
+    pub fn trn_sum_allreduce_f32_dev(comm: *mut trn_comm, a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_dot_allreduce_f32_dev(comm: *mut trn_comm, a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32,
+                                     stream: *mut c_void) -> c_int;
+    pub fn trn_norm_l2_allreduce_f32_dev(comm: *mut trn_comm, a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_argmax_allgather_f32_dev(comm: *mut trn_comm, a: *const f32, n: usize, slice_start: u64, out_idx: *mut u64,
+                                        out_value: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_argmin_allgather_f32_dev(comm: *mut trn_comm, a: *const f32, n: usize, slice_start: u64, out_idx: *mut u64,
+                                        out_value: *mut f32, stream: *mut c_void) -> c_int;
     // device-resident op chaining (GpuCommandBatch counterpart, src/backends/gpu/batch.rs)
     pub fn trn_batch_create(out: *mut *mut trn_batch) -> c_int;
     pub fn trn_batch_destroy(batch: *mut trn_batch) -> c_int;

@@ -28,8 +28,10 @@ def main() -> int:
     st = par.current_stream_handle()
     rng = np.random.default_rng(2026)
 
-    # ---- config 4 (scaled to what the oracle finishes in seconds): sliced reductions -------------------
-    for n in (1 << 22, (1 << 22) + 37, 1001):
+    # ---- config 4 (scaled to what the oracle finishes in seconds): sliced reductions, exchanged (a) by NCCL
+    #      behind the slice kernel and (b) inside the slice kernel over NVLink peer memory (csrc/peer.cu)
+    comm = par.PeerComm()
+    for n, use_comm in [(x, c) for x in (1 << 22, (1 << 22) + 37, 1001) for c in (None, comm)]:
         a = rng.uniform(-1, 1, n).astype(f32)
         b = rng.uniform(-1, 1, n).astype(f32)
         # planted maximum in the LAST rank's slice and an equal duplicate later in the same slice,
@@ -41,8 +43,8 @@ def main() -> int:
         a[5] = big
         a[7] = f32(a.min() - 1)
         sh = par.shard_range(n, rank, world, align=4)
-        va = par.ShardedVector(torch.from_numpy(a[sh.start:sh.start + sh.count]).to(dev), sh)
-        vb = par.ShardedVector(torch.from_numpy(b[sh.start:sh.start + sh.count]).to(dev), sh)
+        va = par.ShardedVector(torch.from_numpy(a[sh.start:sh.start + sh.count]).to(dev), sh, use_comm)
+        vb = par.ShardedVector(torch.from_numpy(b[sh.start:sh.start + sh.count]).to(dev), sh, use_comm)
         tdot, adot = orc.f64_dot(a, b)
         tsum, asum = orc.f64_sum(a)
         assert abs(float(va.dot(vb)) - tdot) <= 1e-5 * adot
@@ -52,6 +54,17 @@ def main() -> int:
         assert int(va.argmax()) == orc.argmax(a, backend=SCALAR) == 5
         assert int(va.argmin()) == orc.argmin(a, backend=SCALAR) == 7
         assert float(va.max()) == float(big)
+        if use_comm is not None:
+            # every rank folds the slice results in rank order: the fused answers are bit-identical everywhere
+            mine = torch.stack([va.dot(vb).clone(), va.sum().clone(), va.norm_l2().clone()]).reshape(-1)
+            everyone = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(everyone, mine)
+            assert all(torch.equal(everyone[0], e) for e in everyone)
+            # NaN seed in slice 0 wins across ranks; repeated calls stay in step (sequence numbers)
+            a2 = a.copy(); a2[0] = np.nan
+            vn = par.ShardedVector(torch.from_numpy(a2[sh.start:sh.start + sh.count]).to(dev), sh, use_comm)
+            for _ in range(5):
+                assert int(vn.argmax()) == 0 and int(vn.argmin()) == 0
 
     # ---- config 3 (scaled): batch x head ranges, no collective; every rank checks its own heads ---------
     B, H, m, k, n = 2, 8, 256, 128, 384

@@ -95,6 +95,11 @@ _SIGNATURES = {
     "trn_vecmat_f32": [_vp, _sz, _vp, _sz, _sz, _vp], "trn_vecmat_f32_dev": [_vp, _sz, _vp, _sz, _sz, _vp, _vp],
     "trn_layer_norm_rows_f32": [_vp, _vp, _sz, _vp, _sz, C.c_float, _vp, _sz, _sz],
     "trn_layer_norm_rows_f32_dev": [_vp, _vp, _sz, _vp, _sz, C.c_float, _vp, _sz, _sz, _vp],
+    "trn_comm_local_handle": [_vp], "trn_comm_create": [C.c_int, C.c_int, _vp, C.POINTER(_vp)], "trn_comm_destroy": [_vp],
+    "trn_sum_allreduce_f32_dev": [_vp, _vp, _sz, _vp, _vp], "trn_dot_allreduce_f32_dev": [_vp, _vp, _sz, _vp, _sz, _vp, _vp],
+    "trn_norm_l2_allreduce_f32_dev": [_vp, _vp, _sz, _vp, _vp],
+    "trn_argmax_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
+    "trn_argmin_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }

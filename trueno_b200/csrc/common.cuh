@@ -75,12 +75,22 @@ int download(float* dst_host, const float* src_dev, size_t n, cudaStream_t s);
 // ---------------------------------------------------------------------------------------------
 // kernel launchers (one translation unit per family)
 // ---------------------------------------------------------------------------------------------
+// Peer-memory exchange context of a fused reduction (peer.cu builds it; world <= 1 disables the exchange).
+constexpr int kMaxPeers = 8;
+struct PeerCtx {
+    unsigned long long* box[kMaxPeers];   // mailbox of every rank, mapped into this process (box[rank] is local)
+    int rank, world;
+    unsigned seq;                         // collective call number: identical on every rank
+};
+
 enum class Reduce { Sum, Dot, SumSq, NormL2, SumAbs, MaxAbs, SumKahan };
-int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s);
+int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s,
+                  const PeerCtx* pc = nullptr);
 // is_max: 1 argmax / 0 argmin.  out_idx / out_val may be null.  seed_rule 0: interior slice of a
 // sharded vector (no a[0] seed; "no candidate" -> index ~0).
 int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s,
-                     int seed_rule = 1, uint64_t index_base = 0, trn_arg_pair* out_pair = nullptr);
+                     int seed_rule = 1, uint64_t index_base = 0, trn_arg_pair* out_pair = nullptr,
+                     const PeerCtx* pc = nullptr);
 int launch_arg_combine(const trn_arg_pair* pairs, size_t count, int is_max, uint64_t* out_idx, float* out_val,
                        cudaStream_t s);
 

@@ -39,6 +39,38 @@ __device__ __forceinline__ bool last_block_done(unsigned* ticket) {
     return s_last;
 }
 
+// ---- fused exchange over NVLink peer memory (slice partials + one exchange step) -------------
+// Instead of a separate NCCL collective behind the kernel, the LAST block of every rank's reduction writes its
+// slice result straight into every peer's mailbox (P2P stores through NVLink / NVSwitch) and then reads the
+// results of all ranks from its own mailbox.  Payload and sequence number travel in ONE 64-bit store, so there
+// is no flag/data ordering to get wrong; slots are double-buffered by call parity (a rank can only be one call
+// ahead of its slowest peer, because finishing a call needs every peer's message of that call).  Every rank
+// folds the values in rank order -> all ranks return the bit-identical result, run after run.
+constexpr int kPeerWords = 4;   // 32-bit payload words per rank per call
+__device__ __forceinline__ unsigned long long* peer_slot(unsigned long long* box, unsigned parity, int src, int word) {
+    return box + ((parity * kMaxPeers + src) * kPeerWords + word);
+}
+template <int NW>
+__device__ __forceinline__ void peer_exchange(const PeerCtx& pc, const uint32_t (&mine)[NW], uint32_t (*all)[kPeerWords]) {
+    const unsigned parity = pc.seq & 1u;
+    const int t = threadIdx.x;
+    if (t < pc.world * NW) {
+        const int dst = t / NW, w = t % NW;
+        const unsigned long long msg = ((unsigned long long)pc.seq << 32) | mine[w];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peer_slot(pc.box[dst], parity, pc.rank, w)), "l"(msg) : "memory");
+    }
+    if (t < pc.world * NW) {
+        const int src = t / NW, w = t % NW;
+        const unsigned long long* slot = peer_slot(pc.box[pc.rank], parity, src, w);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+        } while ((unsigned)(v >> 32) != pc.seq);
+        all[src][w] = (uint32_t)v;
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ float block_sum(float v) {
     __shared__ float s_w[kThreads / 32];
     v = warp_sum(v);
@@ -138,7 +170,8 @@ template <int OP, bool VEC, bool SQRT>
 __global__ void __launch_bounds__(kThreads)
 reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
                   float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out,
-                  float* __restrict__ partial_lo) {
+                  float* __restrict__ partial_lo, const PeerCtx pc) {
+    __shared__ uint32_t s_all[kMaxPeers][kPeerWords];
     float acc[kUnroll], comp[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) acc[u] = comp[u] = 0.f;
@@ -187,6 +220,15 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
             float rh = 0.f, rl = 0.f;
             for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) pair_add(rh, rl, __ldcg(partial + i), __ldcg(partial_lo + i));
             block_pair_sum(rh, rl);
+            if (pc.world > 1) {   // (hi, lo) pairs of every slice, folded in rank order
+                __shared__ float s_pair[2];
+                if (threadIdx.x == 0) { s_pair[0] = rh; s_pair[1] = rl; }
+                __syncthreads();
+                const uint32_t mine[2] = {__float_as_uint(s_pair[0]), __float_as_uint(s_pair[1])};
+                peer_exchange<2>(pc, mine, s_all);
+                rh = 0.f; rl = 0.f;
+                for (int r = 0; r < pc.world; ++r) pair_add(rh, rl, __uint_as_float(s_all[r][0]), __uint_as_float(s_all[r][1]));
+            }
             if (threadIdx.x == 0) *out = __fadd_rn(rh, rl);
         }
         return;
@@ -204,6 +246,15 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
             r = ISMAX ? fmaxf(r, q) : r + q;
         }
         r = ISMAX ? block_max(r) : block_sum(r);
+        if (pc.world > 1) {   // slice totals of every rank, folded in rank order
+            __shared__ float s_tot;
+            if (threadIdx.x == 0) s_tot = r;
+            __syncthreads();
+            const uint32_t mine[1] = {__float_as_uint(s_tot)};
+            peer_exchange<1>(pc, mine, s_all);
+            r = 0.f;
+            for (int q = 0; q < pc.world; ++q) r = ISMAX ? fmaxf(r, __uint_as_float(s_all[q][0])) : r + __uint_as_float(s_all[q][0]);
+        }
         if (threadIdx.x == 0) *out = SQRT ? sqrtf(r) : r;
     }
 }
@@ -254,12 +305,20 @@ __device__ __forceinline__ Best block_best(Best p) {
     return r;
 }
 
+// Cross-slice rule (slice 0 first): a NaN from slice 0 is the NaN seed and wins outright; otherwise best value,
+// then LOWEST global index; NaN values and "no candidate" entries never win (src/backends/scalar.rs:140-166).
+__device__ __forceinline__ bool pair_wins(int is_max, float v, uint64_t ix, float bv, uint64_t bi) {
+    if (ix == kNoIndex || v != v) return false;
+    return bi == kNoIndex || (is_max ? v > bv : v < bv) || (v == bv && ix < bi);
+}
+
 template <bool MAX, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ partial_v,
                  uint64_t* __restrict__ partial_i, unsigned* __restrict__ ticket,
                  uint64_t* __restrict__ out_idx, float* __restrict__ out_val, int seed_rule,
-                 uint64_t index_base, trn_arg_pair* __restrict__ out_pair) {
+                 uint64_t index_base, trn_arg_pair* __restrict__ out_pair, const PeerCtx pc) {
+    __shared__ uint32_t s_all[kMaxPeers][kPeerWords];
     Best best{MAX ? -INFINITY : INFINITY, kNoIndex};
     auto visit = [&](float x, uint64_t i) { if (better<MAX>(x, best.v)) { best.v = x; best.i = i; } };
 
@@ -313,6 +372,36 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
         for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads)
             r = combine<MAX>(r, Best{__ldcg(partial_v + i), __ldcg(partial_i + i)});
         r = block_best<MAX>(r);
+        if (pc.world > 1) {
+            // fused cross-slice pick: exchange (value, global index) with every rank, then apply the rule
+            __shared__ float s_v;
+            __shared__ uint64_t s_i;
+            if (threadIdx.x == 0) {
+                if (seed_rule) {
+                    const float seed = a[0];
+                    if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
+                }
+                s_v = r.v;
+                s_i = r.i == kNoIndex ? kNoIndex : r.i + index_base;
+            }
+            __syncthreads();
+            const uint32_t mine[3] = {__float_as_uint(s_v), (uint32_t)s_i, (uint32_t)(s_i >> 32)};
+            peer_exchange<3>(pc, mine, s_all);
+            if (threadIdx.x == 0) {
+                const float v0 = __uint_as_float(s_all[0][0]);
+                float bv = MAX ? -INFINITY : INFINITY;
+                uint64_t bi = kNoIndex;
+                for (int q = 0; q < pc.world; ++q) {
+                    const float v = __uint_as_float(s_all[q][0]);
+                    const uint64_t ix = (uint64_t)s_all[q][1] | ((uint64_t)s_all[q][2] << 32);
+                    if (pair_wins(MAX ? 1 : 0, v, ix, bv, bi)) { bv = v; bi = ix; }
+                }
+                if (v0 != v0) { bv = v0; bi = (uint64_t)s_all[0][1] | ((uint64_t)s_all[0][2] << 32); }
+                if (out_idx) *out_idx = bi;
+                if (out_val) *out_val = bv;
+            }
+            return;
+        }
         if (threadIdx.x == 0) {
             // seed_rule == 1: this is a whole Vector (or its first slice) and a[0] seeds the scan.
             // A NaN seed never loses; and if nothing beat the identity, every element is the identity
@@ -394,10 +483,12 @@ static int blocks_per_sm(K kernel) {
     return v < 1 ? 1 : (v > 8 ? 8 : v);
 }
 
-int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s) {
+int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s, const PeerCtx* pc) {
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
-    if (n == 0) {  // empty -> 0.0 (src/vector.rs:635, :2602-2604; dot of empty slices is 0)
+    PeerCtx pcv = {};
+    if (pc) pcv = *pc;
+    if (n == 0 && pcv.world <= 1) {  // empty -> 0.0 (src/vector.rs:635, :2602-2604; dot of empty slices is 0)
         TRN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
         return TRN_OK;
     }
@@ -408,8 +499,8 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
     do {                                                                                                   \
         static const int per_sm = blocks_per_sm(reduce_sum_kernel<OP, true, SQRT>);   /* thread-safe, once */ \
         const int grid = reduce_grid(n, c->sm_count, per_sm);                                              \
-        if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx)); \
-        else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx)); \
+        if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx), pcv); \
+        else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx), pcv); \
     } while (0)
     switch (op) {
         case Reduce::Sum:    LAUNCH(0, false); break;
@@ -427,9 +518,11 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
 }
 
 int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out_val, cudaStream_t s,
-                     int seed_rule, uint64_t index_base, trn_arg_pair* out_pair) {
+                     int seed_rule, uint64_t index_base, trn_arg_pair* out_pair, const PeerCtx* pc) {
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
+    PeerCtx pcv = {};
+    if (pc) pcv = *pc;
     Workspace* w = workspace(s);
     if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
     static const int per_sm_max = blocks_per_sm(argreduce_kernel<true, true>);    // thread-safe, once
@@ -437,11 +530,11 @@ int launch_argreduce(int is_max, const float* a, size_t n, uint64_t* out_idx, fl
     const int grid = reduce_grid(n, c->sm_count, is_max ? per_sm_max : per_sm_min);
     const bool vec = aligned16(a);
     if (is_max) {
-        if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
-        else     argreduce_kernel<true, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
+        if (vec) argreduce_kernel<true, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair, pcv);
+        else     argreduce_kernel<true, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair, pcv);
     } else {
-        if (vec) argreduce_kernel<false, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
-        else     argreduce_kernel<false, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair);
+        if (vec) argreduce_kernel<false, true><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair, pcv);
+        else     argreduce_kernel<false, false><<<grid, kThreads, 0, s>>>(a, n, w->partial_val, w->partial_idx, w->ticket, out_idx, out_val, seed_rule, index_base, out_pair, pcv);
     }
     count_launch();
     TRN_CUDA(cudaGetLastError());

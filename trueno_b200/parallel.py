@@ -129,13 +129,58 @@ def pick_arg(vals: torch.Tensor, idxs: torch.Tensor, is_max: bool) -> tuple[torc
     return out_v.reshape(1), out_i.reshape(1)
 
 
+# ---- fused exchange over NVLink peer memory ------------------------------------------------------------
+class PeerComm:
+    """Peer mailboxes for the fused "slice reduction + exchange" kernels (csrc/peer.cu, csrc/reduce.cu).
+    Every rank exports a 64-byte CUDA IPC handle; ONE all_gather of those handles at construction is all the
+    collective plumbing the fused path needs — afterwards dot / sum / norm_l2 / argmax / argmin of a sharded
+    vector are a single kernel launch per rank (P2P stores over NVLink, no NCCL call per reduction)."""
+
+    def __init__(self):
+        import ctypes as C
+
+        import trueno_b200 as trn
+        if not (dist.is_initialized() and dist.get_world_size() > 1):
+            raise RuntimeError("PeerComm needs an initialised process group with world_size > 1")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_ubyte * 64)()
+        trn.check(trn.lib.trn_comm_local_handle(buf))
+        mine = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        gathered = torch.empty(64 * world, dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine)
+        handles = bytes(gathered.cpu().numpy().tobytes())
+        h = C.c_void_p()
+        trn.check(trn.lib.trn_comm_create(rank, world, handles, C.byref(h)))
+        self._h, self.rank, self.world = h, rank, world
+        dist.barrier()   # every rank has mapped every mailbox before the first fused call
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        import trueno_b200 as trn
+        if self._h is not None:
+            trn.lib.trn_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- sharded ops on device-resident slices --------------------------------------------------------
 class ShardedVector:
     """This rank's contiguous slice of a global f32 vector, resident in HBM."""
 
-    def __init__(self, local: torch.Tensor, shard: Shard):
+    def __init__(self, local: torch.Tensor, shard: Shard, comm: "PeerComm | None" = None):
+        """`comm`: use the fused peer-memory exchange (one launch per reduction) instead of kernel + NCCL."""
         assert local.is_cuda and local.dtype == torch.float32 and local.is_contiguous()
-        self.local, self.shard = local, shard
+        self.local, self.shard, self.comm = local, shard, comm
         self._f32 = torch.zeros(1, dtype=torch.float32, device=local.device)
         self._i64 = torch.zeros(1, dtype=torch.int64, device=local.device)
         self._pair = torch.zeros(2, dtype=torch.int64, device=local.device)   # one trn_arg_pair (16 bytes)
@@ -155,13 +200,30 @@ class ShardedVector:
                          self._f32.data_ptr(), self._stream()))
         return self._f32
 
+    def _fused(self, fn_name: str, other: "ShardedVector | None" = None) -> torch.Tensor:
+        import trueno_b200 as trn
+        fn = getattr(trn.lib, fn_name)
+        n = self.local.numel()
+        if other is None:
+            trn.check(fn(self.comm.handle, self.local.data_ptr(), n, self._f32.data_ptr(), self._stream()))
+        else:
+            trn.check(fn(self.comm.handle, self.local.data_ptr(), n, other.local.data_ptr(), other.local.numel(),
+                         self._f32.data_ptr(), self._stream()))
+        return self._f32
+
     def sum(self) -> torch.Tensor:
+        if self.comm is not None:
+            return self._fused("trn_sum_allreduce_f32_dev")
         return combine_sum(self._partial("trn_sum_f32_dev"))
 
     def dot(self, other: "ShardedVector") -> torch.Tensor:
+        if self.comm is not None:
+            return self._fused("trn_dot_allreduce_f32_dev", other)
         return combine_sum(self._partial("trn_dot_f32_dev", other))
 
     def norm_l2(self) -> torch.Tensor:
+        if self.comm is not None:
+            return self._fused("trn_norm_l2_allreduce_f32_dev")
         return combine_sum(self._partial("trn_sumsq_f32_dev")).sqrt_()
 
     def _arg(self, is_max: bool) -> tuple[torch.Tensor, torch.Tensor]:
@@ -170,6 +232,11 @@ class ShardedVector:
         import trueno_b200 as trn
         L = trn.lib
         w = world_size()
+        if self.comm is not None:   # fused: the slice kernel exchanges the pairs itself and applies the rule
+            fused = L.trn_argmax_allgather_f32_dev if is_max else L.trn_argmin_allgather_f32_dev
+            trn.check(fused(self.comm.handle, self.local.data_ptr(), self.local.numel(), self.shard.start,
+                            self._i64.data_ptr(), self._f32.data_ptr(), self._stream()))
+            return self._f32, self._i64
         fn = L.trn_argmax_slice_pair_f32_dev if is_max else L.trn_argmin_slice_pair_f32_dev
         trn.check(fn(self.local.data_ptr(), self.local.numel(), self.shard.start, self._pair.data_ptr(), self._stream()))
         if w > 1:
