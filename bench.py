@@ -325,14 +325,23 @@ def run_ours(args) -> int:
     sh = par.shard_range(n_total, rank, world, align=4)
     x = (splitmix_u01_torch(torch, 0x5EED0005 + rank, sh.count, dev) * 2 - 1)
     y = (splitmix_u01_torch(torch, 0x5EED0006 + rank, sh.count, dev) * 2 - 1)
-    vx, vy = par.ShardedVector(x, sh), par.ShardedVector(y, sh)
-    for name, fn, nbytes in (("dot", lambda: vx.dot(vy), 8 * n_total), ("sum", lambda: vx.sum(), 4 * n_total),
-                             ("argmax", lambda: vx.argmax(), 4 * n_total), ("norm_l2", lambda: vx.norm_l2(), 4 * n_total)):
-        ms = timed(fn)
-        gbs = nbytes / ms / 1e6
-        secondary.append({"metric": f"{name} 2^30 f32 GB/s", "value": gbs, "ms": ms,
-                          "roofline_frac": gbs / (hbm_peak * world), "bound": "hbm"})
+    # N > 1: the exchange step runs INSIDE the slice kernel over NVLink peer memory (csrc/peer.cu); the
+    # kernel + NCCL variant is timed beside it for comparison
+    comm = par.PeerComm() if world > 1 else None
+    variants = [("", comm)] + ([(" [kernel + NCCL exchange]", None)] if world > 1 else [])
+    for suffix, cm in variants:
+        vx, vy = par.ShardedVector(x, sh, cm), par.ShardedVector(y, sh, cm)
+        for name, fn, nbytes in (("dot", lambda: vx.dot(vy), 8 * n_total), ("sum", lambda: vx.sum(), 4 * n_total),
+                                 ("argmax", lambda: vx.argmax(), 4 * n_total), ("norm_l2", lambda: vx.norm_l2(), 4 * n_total)):
+            ms = timed(fn)
+            gbs = nbytes / ms / 1e6
+            secondary.append({"metric": f"{name} 2^30 f32 GB/s{suffix}", "value": gbs, "ms": ms,
+                              "roofline_frac": gbs / (hbm_peak * world), "bound": "hbm",
+                              "exchange": "none (1 GPU)" if world == 1 else ("fused P2P over NVLink" if cm else "NCCL")})
     del x, y, vx, vy
+    if comm is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
     rows_total, cols = 4096, 32000
     rsh = par.shard_range(rows_total, rank, world)
     logits = torch.randn(rsh.count, cols, device=dev) * 4
