@@ -533,3 +533,32 @@ def test_arg_combine_kernel_matches_rule(trn):
             want_i = NC if int(wi) == par.NO_CANDIDATE else int(wi)
             assert got_i == want_i, (is_max, vals, idxs, got_i, want_i)
             assert (np.isnan(float(ov)) and np.isnan(float(wv))) or float(ov) == float(wv)
+
+
+def test_cuda_path_against_committed_golden(trn):
+    """CUDA path vs the frozen golden file (tests/golden/seeded_fixtures.npz, oracle outputs on the reference's
+    seeded fixtures) — no oracle call here, so an oracle change cannot mask a kernel change."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seeded_fixtures.npz"))
+    for seed in (22222, 34567):
+        x = g[f"xorshift_{seed}_x"]
+        v = trn.Vector.from_slice(x)
+        assert np.max(np.abs(v.softmax().as_slice() - g[f"xorshift_{seed}_softmax"])) <= 1e-6      # tests/pixel_fkr.rs:30
+        want = g[f"xorshift_{seed}_log_softmax"]
+        assert np.all(np.abs(v.log_softmax().as_slice() - want) <= 4 * ulp(want) + 2.0 ** -20)
+        want = g[f"xorshift_{seed}_sigmoid"]
+        assert np.all(np.abs(v.sigmoid().as_slice() - want) <= 4 * ulp(want))
+        want = g[f"xorshift_{seed}_gelu"]
+        assert np.all(np.abs(v.gelu().as_slice() - want) <= 4 * ulp(want) + 4 * 2.0 ** -24 * np.abs(x))
+    A, B = kats.fixture_mod(256, 256, 256, 100, 10.0, 7, 100, 10.0)
+    got = trn.Matrix.from_vec(256, 256, A).matmul(trn.Matrix.from_vec(256, 256, B)).to_numpy()
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)
+    assert np.all(np.abs(got - g["matmul_mod100_256"]) <= 2e-5 * scale)
+    s = kats.splitmix_u01(0x5EED0005, 0, 1 << 16) * f32(2) - f32(1)
+    t = kats.splitmix_u01(0x5EED0006, 0, 1 << 16) * f32(2) - f32(1)
+    vs, vt = trn.Vector.from_slice(s), trn.Vector.from_slice(t)
+    gs = g["splitmix_slice_sum_dot_norm"]
+    asum = float(np.abs(s).astype(np.float64).sum())
+    assert abs(float(vs.sum()) - gs[0]) <= 2e-5 * asum and abs(float(vs.dot(vt)) - gs[1]) <= 2e-5 * asum
+    assert abs(float(vs.norm_l2()) - gs[2]) <= 2e-5 * gs[2]
+    assert [vs.argmax(), vs.argmin()] == g["splitmix_slice_argmax_argmin"].tolist()
