@@ -1,0 +1,143 @@
+// C++ parity tests over include/trueno.hpp, written to read like the reference's own Rust tests (each block cites
+// the reference test it restates).  Built and run by tests/test_cpp_mirror.py:
+//   ./test_trueno_hpp validation   — error contract only: every check fails BEFORE the device is touched (CPU box)
+//   ./test_trueno_hpp all          — the KATs on the B200 as well
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "trueno.hpp"
+
+using namespace trueno;
+
+static int g_failed = 0, g_run = 0;
+#define CHECK(cond)                                                                          \
+    do {                                                                                     \
+        ++g_run;                                                                             \
+        if (!(cond)) { ++g_failed; fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); } \
+    } while (0)
+#define CHECK_NEAR(a, b, tol) CHECK(std::fabs((double)(a) - (double)(b)) <= (tol))
+
+static Vector V(std::initializer_list<float> l) { return Vector::from_slice(std::vector<float>(l)); }
+
+static void validation_tests() {
+    // src/vector.rs:4695-4711 test_dot_size_mismatch
+    auto r = V({1, 2, 3}).dot(V({1, 2}));
+    CHECK(r.is_err() && r.unwrap_err() == TruenoError::size_mismatch(3, 2));
+    CHECK(r.unwrap_err().to_string() == "Size mismatch: expected 3, got 2");                 // src/error.rs:58-66
+    // src/vector.rs:4849-4857: max of an empty vector is InvalidInput("Empty vector")
+    auto e = Vector().max();
+    CHECK(e.is_err() && e.unwrap_err() == TruenoError::invalid_input("Empty vector"));
+    CHECK(Vector().argmax().is_err() && Vector().argmin().unwrap_err() == TruenoError::invalid_input("Empty vector"));
+    // src/vector.rs:7908, 8152, 8413: activations on an empty vector are EmptyVector
+    CHECK(Vector().softmax().unwrap_err() == TruenoError::empty_vector());
+    CHECK(Vector().sigmoid().unwrap_err() == TruenoError::empty_vector());
+    CHECK(Vector().gelu().unwrap_err() == TruenoError::empty_vector());
+    CHECK(Vector().relu().unwrap_err().to_string() == "Empty vector");
+    // src/vector.rs:5200-5205 test_clamp_invalid_range
+    auto c = V({1, 2, 3}).clamp(10.0f, 0.0f);
+    CHECK(c.is_err() && c.unwrap_err() == TruenoError::invalid_input("Invalid clamp range: min (10) > max (0)"));
+    // src/vector.rs:7715-7733 layer_norm size mismatches
+    CHECK(V({1, 2, 3}).layer_norm(V({1, 1}), V({0, 0, 0}), 1e-5f).unwrap_err() == TruenoError::size_mismatch(3, 2));
+    // src/matrix.rs:108-117
+    auto m = Matrix::from_vec(2, 2, {1, 2, 3});
+    CHECK(m.is_err() && m.unwrap_err().message == "Data length 3 does not match matrix dimensions 2x2 (expected 4)");
+    // src/matrix.rs:2246-2256 test_matmul_dimension_mismatch
+    auto a = Matrix::from_vec(2, 3, {1, 2, 3, 4, 5, 6}).unwrap();
+    auto b = Matrix::from_vec(2, 2, {1, 2, 3, 4}).unwrap();
+    auto p = a.matmul(b);
+    CHECK(p.is_err() && p.unwrap_err().kind == TruenoError::InvalidInput);
+    CHECK(p.unwrap_err().message ==
+          "Matrix dimension mismatch for multiplication: 2\xC3\x97" "3 \xC3\x97 2\xC3\x97" "2 (inner dimensions 3 and 2 must match)");
+    // src/matrix.rs:3912-3945 batched size checks
+    auto bm = Matrix::batched_matmul(std::vector<float>(10, 1.f), std::vector<float>(12, 1.f), 2, 2, 3, 2);
+    CHECK(bm.is_err() && bm.unwrap_err().message == "A data size mismatch: expected 12 (2\xC3\x97" "2\xC3\x97" "3), got 10");
+    // src/matrix.rs:3567-3572 test_vecmat_dimension_mismatch
+    CHECK(Matrix::vecmat(V({1, 2}), Matrix::from_vec(3, 2, {1, 2, 3, 4, 5, 6}).unwrap()).is_err());
+    // src/matrix.rs:1658-1664
+    CHECK(a.matvec(V({1, 2})).unwrap_err().message ==
+          "Vector length 2 does not match matrix columns 3 for matrix-vector multiplication");
+}
+
+static void device_tests() {
+    // src/vector.rs:4689-4694 test_dot
+    CHECK(V({1, 2, 3}).dot(V({4, 5, 6})).unwrap() == 32.0f);
+    // src/vector.rs:4714-4730 test_sum / empty / single
+    CHECK(V({1, 2, 3, 4}).sum().unwrap() == 10.0f);
+    CHECK(Vector().sum().unwrap() == 0.0f);
+    CHECK(V({42}).sum().unwrap() == 42.0f);
+    // src/vector.rs:4837-4906 argmax / argmin, first occurrence on ties
+    CHECK(V({1, 5, 3, 2}).argmax().unwrap() == 1);
+    CHECK(V({-5, -1, -3, -2}).argmax().unwrap() == 1);
+    CHECK(V({1, 5, 3, 5, 2}).argmax().unwrap() == 1);
+    CHECK(V({5, 1, 3, 1, 2}).argmin().unwrap() == 1);
+    // src/vector.rs:2586-2588 norm_l2
+    CHECK(V({3, 4}).norm_l2().unwrap() == 5.0f);
+    // src/vector.rs:4567 / 4640 sub, div; 5151 clamp; 5208 lerp; 5265 fma; 6773 round
+    CHECK(V({5, 7, 9}).sub(V({1, 2, 3})).unwrap() == V({4, 5, 6}));
+    CHECK(V({10, 20, 30}).div(V({2, 4, 5})).unwrap() == V({5, 5, 6}));
+    CHECK(V({-5, 0, 5, 10, 15}).clamp(0, 10).unwrap() == V({0, 0, 5, 10, 10}));
+    CHECK(V({0, 10, 20}).lerp(V({100, 110, 120}), 0.5f).unwrap() == V({50, 60, 70}));
+    CHECK(V({2, 3, 4}).fma(V({5, 6, 7}), V({1, 2, 3})).unwrap() == V({11, 20, 31}));
+    CHECK(V({3.2f, 3.7f, -2.3f, -2.8f, 5.0f}).round().unwrap() == V({3, 4, -2, -3, 5}));
+    CHECK(V({-2, -1, 0, 1, 2}).relu().unwrap() == V({0, 0, 0, 1, 2}));                        // src/vector.rs:8018
+    // src/vector.rs:8087-8096 sigmoid; 8352-8360 gelu(0) == 0; 7866-7875 uniform softmax
+    auto s = V({0, 2, -2}).sigmoid().unwrap().as_slice();
+    CHECK(s[0] == 0.5f);
+    CHECK_NEAR(s[1], 0.8808, 1e-3);
+    CHECK_NEAR(s[2], 0.1192, 1e-3);
+    CHECK(V({0}).gelu().unwrap().as_slice()[0] == 0.0f);
+    for (float p : V({1, 1, 1, 1}).softmax().unwrap().as_slice()) CHECK_NEAR(p, 0.25, 1e-5);
+    // src/vector.rs:4946-4960 normalize; zero vector -> DivisionByZero
+    auto n = V({3, 4}).normalize().unwrap().as_slice();
+    CHECK_NEAR(n[0], 0.6, 1e-5);
+    CHECK_NEAR(n[1], 0.8, 1e-5);
+    CHECK(V({0, 0, 0}).normalize().unwrap_err() == TruenoError::division_by_zero());
+    // src/matrix.rs:2166-2196 matmul 2x2 and 2x3 * 3x2
+    auto a = Matrix::from_vec(2, 2, {1, 2, 3, 4}).unwrap();
+    auto b = Matrix::from_vec(2, 2, {5, 6, 7, 8}).unwrap();
+    CHECK(a.matmul(b).unwrap().as_slice() == std::vector<float>({19, 22, 43, 50}));
+    auto c = Matrix::from_vec(2, 3, {1, 2, 3, 4, 5, 6}).unwrap();
+    auto d = Matrix::from_vec(3, 2, {7, 8, 9, 10, 11, 12}).unwrap();
+    CHECK(c.matmul(d).unwrap().as_slice() == std::vector<float>({58, 64, 139, 154}));
+    CHECK(a.matmul(Matrix::identity(2)).unwrap().as_slice() == a.as_slice());                // src/matrix.rs:2224-2232
+    // a product big enough for the tcgen05 path (src/matrix.rs:2540-2600 fixture family, tolerance 1e-2 relative)
+    {
+        const size_t sz = 256;
+        std::vector<float> fa(sz * sz), fb(sz * sz);
+        for (size_t i = 0; i < sz * sz; ++i) { fa[i] = (float)(i % 100) / 10.0f; fb[i] = (float)((i * 7) % 100) / 10.0f; }
+        auto big = Matrix::from_vec(sz, sz, fa).unwrap().matmul(Matrix::from_vec(sz, sz, fb).unwrap()).unwrap();
+        double worst = 0;
+        for (size_t i = 0; i < sz; i += 37)
+            for (size_t j = 0; j < sz; j += 41) {
+                double ref = 0;
+                for (size_t k = 0; k < sz; ++k) ref += (double)fa[i * sz + k] * fb[k * sz + j];
+                worst = std::fmax(worst, std::fabs(big.as_slice()[i * sz + j] - ref) / std::fabs(ref));
+            }
+        CHECK(worst < 1e-5);
+    }
+    // src/matrix.rs:3853-3889 batched 3-D; :1648-1655 matvec; :3543-3555 vecmat
+    std::vector<float> seq12(12);
+    for (int i = 0; i < 12; ++i) seq12[i] = (float)(i + 1);
+    CHECK(Matrix::batched_matmul(seq12, seq12, 2, 2, 3, 2).unwrap() == std::vector<float>({22, 28, 49, 64, 220, 244, 301, 334}));
+    CHECK(c.matvec(V({1, 2, 3})).unwrap() == V({14, 32}));
+    CHECK(Matrix::vecmat(V({1, 2}), c).unwrap() == V({9, 12, 15}));
+    // src/backends/gpu/batch.rs:1120-1180 relu -> scale -> add in one batch
+    CommandBatch batch;
+    auto in = batch.upload({1, 2, -3, 4});
+    auto out = batch.add(batch.scale(batch.relu(in), 2.0f), batch.upload({0.5f, 0.5f, 0.5f, 0.5f}));
+    CHECK(batch.num_operations() == 3 && batch.num_buffers() == 5);
+    CHECK(batch.execute().is_ok());
+    CHECK(batch.read(out).unwrap() == std::vector<float>({2.5f, 4.5f, 0.5f, 8.5f}));
+    // device buffer round trip
+    auto buf = DeviceBuffer::from_slice({1, 2, 3, 4, 5});
+    CHECK(buf.is_ok() && buf.unwrap().to_vec().unwrap() == std::vector<float>({1, 2, 3, 4, 5}));
+}
+
+int main(int argc, char** argv) {
+    const bool all = argc > 1 && strcmp(argv[1], "all") == 0;
+    validation_tests();
+    if (all) device_tests();
+    printf("%s: %d checks, %d failed\n", all ? "all" : "validation", g_run, g_failed);
+    return g_failed ? 1 : 0;
+}
