@@ -87,7 +87,8 @@ static void device_tests() {
     CHECK_NEAR(s[1], 0.8808, 1e-3);
     CHECK_NEAR(s[2], 0.1192, 1e-3);
     CHECK(V({0}).gelu().unwrap().as_slice()[0] == 0.0f);
-    for (float p : V({1, 1, 1, 1}).softmax().unwrap().as_slice()) CHECK_NEAR(p, 0.25, 1e-5);
+    const std::vector<float> uniform = V({1, 1, 1, 1}).softmax().unwrap().as_slice();   // copy: the Result is a temporary
+    for (float p : uniform) CHECK_NEAR(p, 0.25, 1e-5);
     // src/vector.rs:4946-4960 normalize; zero vector -> DivisionByZero
     auto n = V({3, 4}).normalize().unwrap().as_slice();
     CHECK_NEAR(n[0], 0.6, 1e-5);
