@@ -12,28 +12,53 @@
 namespace trn {
 
 // ---------------------------------------------------------------------------------------------
-// transpose: 32x32 shared-memory tiles (+1 padding), coalesced on both sides.  8 B / element.
+// transpose: 64x64 shared-memory tiles (+1 padding), coalesced 128-bit accesses on both sides.  8 B / element.
 // ---------------------------------------------------------------------------------------------
+// One 64 x 64 tile per CTA on a flat grid; 128-bit accesses on both sides when rows and cols are multiples of 4
+// and the pointers are 16-byte aligned (VEC), scalar otherwise.  tile[r][c] holds in[r][c]; the +1 padding keeps the
+// transposed reads at most 2-way conflicted.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
-    __shared__ float tile[32][33];
-    const size_t tiles_x = (cols + 31) / 32, tiles_y = (rows + 31) / 32;
-    const size_t ntiles = tiles_x * tiles_y;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const size_t by = t / tiles_x, bx = t % tiles_x;
+    __shared__ float tile[64][65];
+    const size_t tiles_x = (cols + 63) / 64;
+    const size_t by = blockIdx.x / tiles_x, bx = blockIdx.x % tiles_x;
 #pragma unroll
-        for (int r = 0; r < 32; r += 8) {
-            size_t i = by * 32 + ty + r, j = bx * 32 + tx;
-            if (i < rows && j < cols) tile[ty + r][tx] = in[i * cols + j];
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        const int r = idx >> 4, c4 = (idx & 15) * 4;
+        const size_t i = by * 64 + r, j = bx * 64 + c4;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (i < rows) {
+            if (VEC) {
+                if (j < cols) v = ld_stream(reinterpret_cast<const float4*>(in + i * cols + j));
+            } else {
+                if (j < cols) v.x = in[i * cols + j];
+                if (j + 1 < cols) v.y = in[i * cols + j + 1];
+                if (j + 2 < cols) v.z = in[i * cols + j + 2];
+                if (j + 3 < cols) v.w = in[i * cols + j + 3];
+            }
         }
-        __syncthreads();
+        tile[r][c4] = v.x; tile[r][c4 + 1] = v.y; tile[r][c4 + 2] = v.z; tile[r][c4 + 3] = v.w;
+    }
+    __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 32; r += 8) {
-            size_t j = bx * 32 + ty + r, i = by * 32 + tx;
-            if (i < rows && j < cols) out[j * rows + i] = tile[tx][ty + r];
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        const int c = idx >> 4, r4 = (idx & 15) * 4;      // output row = input column c, 4 consecutive input rows
+        const size_t j = bx * 64 + c, i = by * 64 + r4;
+        if (j < cols && i < rows) {
+            const float4 v = make_float4(tile[r4][c], tile[r4 + 1][c], tile[r4 + 2][c], tile[r4 + 3][c]);
+            float* dst = out + j * rows + i;
+            if (VEC) {
+                st_stream(reinterpret_cast<float4*>(dst), v);
+            } else {
+                dst[0] = v.x;
+                if (i + 1 < rows) dst[1] = v.y;
+                if (i + 2 < rows) dst[2] = v.z;
+                if (i + 3 < rows) dst[3] = v.w;
+            }
         }
-        __syncthreads();
     }
 }
 
@@ -41,9 +66,12 @@ int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaS
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
     if (rows == 0 || cols == 0) return TRN_OK;
-    size_t ntiles = ((cols + 31) / 32) * ((rows + 31) / 32);
-    size_t cap = (size_t)c->sm_count * 8;
-    transpose_kernel<<<(unsigned)(ntiles < cap ? ntiles : cap), 256, 0, s>>>(a, out, rows, cols);
+    const size_t ntiles = ((cols + 63) / 64) * ((rows + 63) / 64);
+    if (ntiles > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "matrix of %zu tiles exceeds the launch grid", ntiles);
+    const bool vec = rows % 4 == 0 && cols % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    if (vec) transpose_kernel<true><<<(unsigned)ntiles, 256, 0, s>>>(a, out, rows, cols);
+    else     transpose_kernel<false><<<(unsigned)ntiles, 256, 0, s>>>(a, out, rows, cols);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
