@@ -34,7 +34,7 @@ def timeit(fn, iters=20, warmup=3):
 
 
 def main():
-    which = set(sys.argv[1:]) or {"reduce", "map", "softmax", "gemm", "batched", "matvec"}
+    which = set(sys.argv[1:]) or {"reduce", "map", "softmax", "gemm", "batched", "matvec"}   # + rowblock, hostbatched on request
     torch.cuda.set_device(0)
     trn.check(trn.lib.trn_cuda_init(0))
     # a real (non-default) stream: torch events and our launches must share it
@@ -142,6 +142,34 @@ def main():
         med, best = timeit(lambda: torch.bmm(a3, b3, out=c.view(B * H, m, n)), iters=5)
         print(f"batched4d cuBLAS FP32 median {med:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
         del a, b, c
+
+    if "rowblock" in which:
+        # BASELINE config 5b: one GPU's share of the 32768^3 product at 8 GPUs (A-block 4096 x 32768, full B)
+        n, mb = 32768, 4096
+        a = torch.rand(mb, n, device="cuda")
+        b = torch.rand(n, n, device="cuda")
+        c = torch.empty(mb, n, device="cuda")
+        flop = 2.0 * mb * n * n
+        fn = lambda: trn.check(L.trn_matmul_f32_dev(a.data_ptr(), mb, n, b.data_ptr(), n, n, c.data_ptr(), st))
+        med, best = timeit(fn, iters=5)
+        print(f"rowblock 4096x32768x32768 tc 3xTF32 median {med:.3f} ms best {best:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
+        del a, b, c
+
+    if "hostbatched" in which:
+        # BASELINE config 3 through the host-slice API (pinned): 512 MiB up, 4 GiB down, pipelined by head groups
+        B, H, m, k, n = 8, 32, 2048, 128, 2048
+        ha, hb, hc = trn.pinned_empty(B * H * m * k), trn.pinned_empty(B * H * k * n), trn.pinned_empty(B * H * m * n)
+        ha[:] = 0.5
+        hb[:] = 0.25
+        import time
+        fn = lambda: trn.check(L.trn_batched_matmul_4d_f32(ha.ctypes.data, ha.size, hb.ctypes.data, hb.size, hc.ctypes.data, B, H, m, k, n))
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        dt = (time.perf_counter() - t0) / 3
+        print(f"host batched4d (pinned, pipelined) {dt * 1e3:.1f} ms  {2.0 * B * H * m * n * k / dt / 1e12:.1f} TFLOP/s e2e  D2H {4.0 * hc.size / dt / 1e9:.1f} GB/s  check {float(hc[12345]):.3f}")
+        del ha, hb, hc
 
     if "matvec" in which:
         rows = cols = 16384
