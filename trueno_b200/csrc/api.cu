@@ -456,19 +456,23 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     size_t units = batch, per_block = 1;
     std::vector<size_t> row_start;   // single product: start row of every block, plus m as the sentinel
     if (single) {
-        // ~8 blocks of whole 256-row pair tiles; the LAST block is cut into 1/2 + 1/4 + 1/4 so the tail that
-        // cannot overlap anything (last split + GEMM + D2H) is a quarter block instead of a whole one
-        size_t unit_rows = 256 * ((m / 8 + 255) / 256);
+        // Row blocks of whole 256-row pair tiles.  After B has arrived the three stages of a block — upload of its A
+        // rows, split + GEMM, download of its C rows — run as a pipeline over three streams; the end-to-end time is
+        // B upload + (blocks + 2) x the slowest stage, so blocks should be as small as the GEMM stays efficient.
+        // Measured on 8192^3 (TRN_PIPE_ROWS): 256-row blocks 13.0 ms, 512 11.4, 768 11.15, 1024 11.5, 2304 12.6 —
+        // about eleven blocks; the PCIe floor (512 MiB up + 256 MiB down concurrently) is 10.3 ms.
+        static const size_t forced_rows = [] { const char* e = getenv("TRN_PIPE_ROWS"); return e ? (size_t)atol(e) : (size_t)0; }();
+        size_t unit_rows = forced_rows ? (forced_rows + 255) / 256 * 256 : 256 * ((m / 11 + 255) / 256);
         if (unit_rows < 256) unit_rows = 256;
         size_t r = 0;
         while (m - r > unit_rows) { row_start.push_back(r); r += unit_rows; }
-        const size_t last = m - r, q = 256 * ((last / 4 + 255) / 256);
-        if (last >= 1024 && 3 * q < last) {
-            row_start.push_back(r);
-            row_start.push_back(r + last - 2 * q);
-            row_start.push_back(r + last - q);
-        } else {
-            row_start.push_back(r);
+        // the tail: [rest, 256, 256] rows — after the last upload only a 256-row GEMM and its 8 MiB D2H remain
+        const size_t last = m - r;
+        row_start.push_back(r);
+        if (last >= 768) {
+            const size_t rest = (last - 512 + 255) / 256 * 256;
+            row_start.push_back(r + rest);
+            if (last - rest > 256) row_start.push_back(r + rest + 256);
         }
         units = row_start.size();
         row_start.push_back(m);
