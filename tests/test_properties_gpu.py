@@ -1,0 +1,107 @@
+"""The reference's proptest suite (100 cases each) restated with hypothesis against the CUDA path:
+src/vector.rs:9030-14280 (vector properties), src/matrix.rs:3251-3507 (matrix properties).  Same generators
+(values in -1000..1000 / -100..100, lengths 1..100, small matrix dims), same tolerances."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+from hypothesis.extra import numpy as hnp
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+CASES = settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+
+
+def vec(lo=-1000.0, hi=1000.0, min_len=1, max_len=100):
+    return hnp.arrays(f32, st.integers(min_len, max_len), elements=st.floats(lo, hi, width=32, allow_nan=False))
+
+
+@CASES
+@given(data=st.data())
+def test_dot_commutative_and_norm_is_sqrt_dot(trn, data):       # src/vector.rs:9100-9180, :11830-11870
+    n = data.draw(st.integers(1, 100))
+    a = data.draw(hnp.arrays(f32, n, elements=st.floats(-100, 100, width=32)))
+    b = data.draw(hnp.arrays(f32, n, elements=st.floats(-100, 100, width=32)))
+    va, vb = trn.Vector(a), trn.Vector(b)
+    assert va.dot(vb) == vb.dot(va)
+    assert abs(float(va.norm_l2()) - float(np.sqrt(va.dot(va)))) <= 1e-3 * max(1.0, float(va.norm_l2()))
+
+
+@CASES
+@given(a=vec())
+def test_sum_max_min_match_manual(trn, a):                        # src/vector.rs:9200-9330
+    v = trn.Vector(a)
+    manual = float(np.sum(a.astype(np.float64)))
+    assert abs(float(v.sum()) - manual) <= 1e-3 * max(1.0, float(np.abs(a).sum()))
+    assert float(v.max()) == float(a.max()) and float(v.min()) == float(a.min())
+
+
+@CASES
+@given(a=hnp.arrays(f32, st.integers(1, 100), elements=st.integers(-1000, 1000).map(float)))
+def test_argmax_argmin_first_occurrence(trn, a):                  # src/vector.rs:9434-9477
+    v = trn.Vector(a)
+    assert v.argmax() == int(np.argmax(a)) and v.argmin() == int(np.argmin(a))   # numpy also returns the first
+
+
+@CASES
+@given(a=vec(-50.0, 50.0), shift=st.floats(-10, 10, width=32))
+def test_softmax_sums_to_one_and_translation_invariant(trn, a, shift):   # src/vector.rs:13461-13530
+    s = trn.Vector(a).softmax().as_slice()
+    assert abs(float(s.sum(dtype=np.float64)) - 1.0) < 1e-5
+    assert ((s >= 0) & (s <= 1)).all()
+    s2 = trn.Vector((a + f32(shift)).astype(f32)).softmax().as_slice()
+    assert np.max(np.abs(s - s2)) < 1e-4
+
+
+@CASES
+@given(a=vec(-100.0, 100.0))
+def test_sigmoid_bounded_and_monotone_relu_gelu(trn, a):           # src/vector.rs:13668-13714, :13240-13300
+    s = trn.Vector(a).sigmoid().as_slice()
+    assert ((s >= 0) & (s <= 1)).all()
+    order = np.argsort(a, kind="stable")
+    assert np.all(np.diff(s[order]) >= 0)
+    r = trn.Vector(a).relu().as_slice()
+    assert np.array_equal(r, np.maximum(a, 0).astype(f32) + f32(0))
+    g = trn.Vector(a).gelu().as_slice()
+    big = a > 10
+    assert np.all(np.abs(g[big] - a[big]) <= 1e-3 * np.abs(a[big]))          # linear for large x (src/vector.rs:8397)
+
+
+def small_matrix(rows, cols, lo=-10.0, hi=10.0):
+    return hnp.arrays(f32, (rows, cols), elements=st.floats(lo, hi, width=32))
+
+
+@CASES
+@given(data=st.data())
+def test_matmul_identity_associativity_transpose(trn, data):      # src/matrix.rs:3267-3420
+    m, k, n, p = (data.draw(st.integers(1, 8)) for _ in range(4))
+    A, B, C = data.draw(small_matrix(m, k)), data.draw(small_matrix(k, n)), data.draw(small_matrix(n, p))
+    M = trn.Matrix
+    mA, mB, mC = M.from_vec(m, k, A), M.from_vec(k, n, B), M.from_vec(n, p, C)
+    assert np.max(np.abs(mA.matmul(M.identity(k)).to_numpy() - A)) <= 1e-5                      # A * I = A
+    lhs = mA.matmul(mB).matmul(mC).to_numpy()
+    rhs = mA.matmul(mB.matmul(mC)).to_numpy()
+    scale = np.abs(A).astype(np.float64) @ np.abs(B) @ np.abs(C) + 1e-6
+    assert np.all(np.abs(lhs - rhs) <= 0.05 * scale)                                            # (AB)C = A(BC), 5 %
+    t1 = mA.matmul(mB).transpose().to_numpy()
+    t2 = mB.transpose().matmul(mA.transpose()).to_numpy()
+    assert np.all(np.abs(t1 - t2) <= 1e-3 * np.maximum(np.abs(t1), 1))                          # (AB)^T = B^T A^T
+
+
+@CASES
+@given(data=st.data())
+def test_matvec_and_vecmat_associativity(trn, data):               # src/matrix.rs:3430-3507
+    m, k, n = (data.draw(st.integers(1, 8)) for _ in range(3))
+    A, B = data.draw(small_matrix(m, k)), data.draw(small_matrix(k, n))
+    v = data.draw(hnp.arrays(f32, n, elements=st.floats(-10, 10, width=32)))
+    w = data.draw(hnp.arrays(f32, m, elements=st.floats(-10, 10, width=32)))
+    M, V = trn.Matrix, trn.Vector
+    mA, mB = M.from_vec(m, k, A), M.from_vec(k, n, B)
+    scale = np.abs(A).astype(np.float64) @ np.abs(B) @ np.abs(v) + 1e-6
+    lhs = mA.matmul(mB).matvec(V(v)).as_slice()
+    rhs = mA.matvec(mB.matvec(V(v))).as_slice()
+    assert np.all(np.abs(lhs - rhs) <= 2e-2 * scale)                                            # (AB)v = A(Bv)
+    scale2 = np.abs(w).astype(np.float64) @ np.abs(A) @ np.abs(B) + 1e-6
+    l2 = M.vecmat(V(w), mA.matmul(mB)).as_slice()
+    r2 = M.vecmat(M.vecmat(V(w), mA), mB).as_slice()
+    assert np.all(np.abs(l2 - r2) <= 2e-2 * scale2)                                             # w(AB) = (wA)B
