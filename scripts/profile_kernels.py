@@ -1,7 +1,7 @@
 """One launch of every hot-path kernel at its BASELINE size between cudaProfilerStart/Stop, for
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_all python scripts/profile_kernels.py
 Warm-up launches run before the profiler range so the captured launch is steady-state (apart from ncu's own
-cache control).  usage: python scripts/profile_kernels.py [gemm] [batched] [reduce] [map] [softmax] [matvec]"""
+cache control).  usage: python scripts/profile_kernels.py [gemm] [batched] [reduce] [map] [softmax] [rows] [matvec]"""
 import os
 import sys
 
@@ -12,7 +12,7 @@ import trueno_b200 as trn  # noqa: E402
 
 
 def main():
-    which = set(sys.argv[1:]) or {"gemm", "batched", "reduce", "map", "softmax", "matvec"}
+    which = set(sys.argv[1:]) or {"gemm", "batched", "reduce", "map", "softmax", "rows", "matvec"}
     torch.cuda.set_device(0)
     trn.check(trn.lib.trn_cuda_init(0))
     stream = torch.cuda.Stream()
@@ -56,6 +56,19 @@ def main():
         if "softmax" in which:
             ops += [lambda: trn.check(L.trn_softmax_rows_f32_dev(z.data_ptr(), o.data_ptr(), rows, cols, st)),
                     lambda: trn.check(L.trn_log_softmax_rows_f32_dev(z.data_ptr(), o.data_ptr(), rows, cols, st))]
+    if "rows" in which:
+        # the other row-kernel families: warp-per-row (cols 1024), CTA-per-row registers (cols 8192), layer_norm, transpose
+        for rr, cc in ((131072, 1024), (16384, 8192)):
+            w = torch.randn(rr, cc, device="cuda")
+            wo = torch.empty_like(w)
+            g, bb = torch.randn(cc, device="cuda"), torch.randn(cc, device="cuda")
+            keep += [w, wo, g, bb]
+            ops += [lambda w=w, wo=wo, rr=rr, cc=cc: trn.check(L.trn_softmax_rows_f32_dev(w.data_ptr(), wo.data_ptr(), rr, cc, st)),
+                    lambda w=w, wo=wo, g=g, bb=bb, rr=rr, cc=cc: trn.check(L.trn_layer_norm_rows_f32_dev(w.data_ptr(), g.data_ptr(), cc, bb.data_ptr(), cc, 1e-5, wo.data_ptr(), rr, cc, st))]
+        t_in = torch.randn(16384, 8192, device="cuda")
+        t_out = torch.empty(8192, 16384, device="cuda")
+        keep += [t_in, t_out]
+        ops.append(lambda: trn.check(L.trn_transpose_f32_dev(t_in.data_ptr(), 16384, 8192, t_out.data_ptr(), st)))
     if "matvec" in which:
         r = 16384
         ma, mv, my = torch.randn(r, r, device="cuda"), torch.randn(r, device="cuda"), torch.empty(r, device="cuda")
