@@ -271,6 +271,14 @@ public:
         if (st != TRN_OK) return detail::from_status(st);
         return out;
     }
+    Result<Matrix> convolve2d(const Matrix& k) const {                                       // src/matrix.rs:1868
+        const bool ok = k.rows_ <= rows_ && k.cols_ <= cols_;
+        Matrix out(ok ? rows_ - k.rows_ + 1 : 0, ok ? cols_ - k.cols_ + 1 : 0, {});
+        out.data_.resize(out.rows_ * out.cols_);
+        const int st = trn_convolve2d_f32(data_.data(), rows_, cols_, k.data_.data(), k.rows_, k.cols_, out.data_.data());
+        if (st != TRN_OK) return detail::from_status(st);
+        return out;
+    }
     static Result<Vector> vecmat(const Vector& v, const Matrix& m) {                        // src/matrix.rs:1782
         Vector out{std::vector<float>(m.cols_)};
         const int st = trn_vecmat_f32(v.data_.data(), v.data_.size(), m.data_.data(), m.rows_, m.cols_, out.data_.data());

@@ -311,6 +311,14 @@ TRN_API int trn_argmax_allgather_f32_dev(trn_comm* comm, const float* a, size_t 
 TRN_API int trn_argmin_allgather_f32_dev(trn_comm* comm, const float* a, size_t n, uint64_t slice_start, uint64_t* out_idx,
                                          float* out_value, void* stream);
 
+/* Matrix::convolve2d (src/matrix.rs:1868): valid-padding 2-D cross-correlation, out is
+ * (rows - k_rows + 1) x (cols - k_cols + 1); accumulated in the reference's order, unfused -> bit-exact.  Kernel larger
+ * than the input -> TRN_INVALID_INPUT "Kernel size ({}x{}) larger than input ({}x{})". */
+TRN_API int trn_convolve2d_f32(const float* in, size_t rows, size_t cols, const float* kernel, size_t k_rows, size_t k_cols,
+                               float* out);
+TRN_API int trn_convolve2d_f32_dev(const float* in, size_t rows, size_t cols, const float* kernel, size_t k_rows,
+                                   size_t k_cols, float* out, void* stream);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

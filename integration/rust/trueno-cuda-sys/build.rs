@@ -9,7 +9,7 @@ use std::path::PathBuf;
 use std::process::Command;
 
 const SOURCES: &[&str] = &[
-    "context.cu", "reduce.cu", "map.cu", "softmax.cu", "gemm_simt.cu", "gemm_tc.cu", "batch.cu", "peer.cu", "api.cu",
+    "context.cu", "reduce.cu", "map.cu", "softmax.cu", "gemm_simt.cu", "gemm_tc.cu", "batch.cu", "peer.cu", "conv.cu", "api.cu",
 ];
 
 fn main() {

@@ -172,6 +172,10 @@ extern "C" {
                                    eps: f32, out: *mut f32, rows: usize, cols: usize) -> c_int;
     pub fn trn_layer_norm_rows_f32_dev(a: *const f32, gamma: *const f32, gamma_len: usize, beta: *const f32, beta_len: usize,
                                        eps: f32, out: *mut f32, rows: usize, cols: usize, stream: *mut c_void) -> c_int;
+    pub fn trn_convolve2d_f32(input: *const f32, rows: usize, cols: usize, kernel: *const f32, k_rows: usize, k_cols: usize,
+                              out: *mut f32) -> c_int;
+    pub fn trn_convolve2d_f32_dev(input: *const f32, rows: usize, cols: usize, kernel: *const f32, k_rows: usize, k_cols: usize,
+                                  out: *mut f32, stream: *mut c_void) -> c_int;
     // fused slice reduction + exchange over NVLink peer memory
     pub fn trn_comm_local_handle(handle64: *mut c_void) -> c_int;
     pub fn trn_comm_create(rank: c_int, world: c_int, handles: *const c_void, out: *mut *mut trn_comm) -> c_int;

@@ -97,6 +97,8 @@ class Oracle:
         L.orc_scalar_map.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
         for name in ("scalar_sum_kahan", "scalar_norm_l1", "scalar_norm_linf"):
             f = getattr(L, "orc_" + name); f.restype = C.c_float; f.argtypes = [_f32p, C.c_size_t]
+        L.orc_convolve2d.restype = None
+        L.orc_convolve2d.argtypes = [_f32p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t, C.c_size_t, _f32p]
         L.orc_vecmat.restype = None
         L.orc_vecmat.argtypes = [_f32p, _f32p, C.c_size_t, C.c_size_t, _f32p]
         L.orc_layer_norm.restype = None
@@ -186,6 +188,12 @@ class Oracle:
     def sum_kahan(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_sum_kahan(_p(a), a.size))
     def norm_l1(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_norm_l1(_p(a), a.size))
     def norm_linf(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_norm_linf(_p(a), a.size))
+
+    def convolve2d(self, A, rows, cols, K, kr, kc):
+        A, K = _f32(A), _f32(K)
+        out = np.empty((rows - kr + 1) * (cols - kc + 1), np.float32)
+        self.lib.orc_convolve2d(_p(A), rows, cols, _p(K), kr, kc, _p(out))
+        return out.reshape(rows - kr + 1, cols - kc + 1)
 
     def vecmat(self, v, A, rows, cols):
         v, A = _f32(v), _f32(A)

@@ -846,3 +846,18 @@ ORC_API void orc_layer_norm(const float* x, const float* g, const float* b, floa
         y[i] = t + b[i];
     }
 }
+
+/* src/matrix.rs:1868-1950 — valid-padding cross-correlation, scalar loop: sum += input * kernel (unfused) */
+ORC_API void orc_convolve2d(const float* in, size_t rows, size_t cols, const float* k, size_t kr, size_t kc, float* out) {
+    const size_t orows = rows - kr + 1, ocols = cols - kc + 1;
+    for (size_t r = 0; r < orows; ++r)
+        for (size_t c = 0; c < ocols; ++c) {
+            float sum = 0.f;
+            for (size_t a = 0; a < kr; ++a)
+                for (size_t b = 0; b < kc; ++b) {
+                    float p = in[(r + a) * cols + (c + b)] * k[a * kc + b];
+                    sum = sum + p;
+                }
+            out[r * ocols + c] = sum;
+        }
+}

@@ -52,6 +52,9 @@ static void validation_tests() {
     // src/matrix.rs:3912-3945 batched size checks
     auto bm = Matrix::batched_matmul(std::vector<float>(10, 1.f), std::vector<float>(12, 1.f), 2, 2, 3, 2);
     CHECK(bm.is_err() && bm.unwrap_err().message == "A data size mismatch: expected 12 (2\xC3\x97" "2\xC3\x97" "3), got 10");
+    // src/matrix.rs:3715-3722 test_convolve2d_invalid_kernel
+    CHECK(Matrix::from_vec(3, 3, std::vector<float>(9, 1.f)).unwrap().convolve2d(Matrix::from_vec(4, 4, std::vector<float>(16, 1.f)).unwrap())
+              .unwrap_err() == TruenoError::invalid_input("Kernel size (4x4) larger than input (3x3)"));
     // src/matrix.rs:3567-3572 test_vecmat_dimension_mismatch
     CHECK(Matrix::vecmat(V({1, 2}), Matrix::from_vec(3, 2, {1, 2, 3, 4, 5, 6}).unwrap()).is_err());
     // src/matrix.rs:1658-1664
@@ -123,6 +126,12 @@ static void device_tests() {
     CHECK(Matrix::batched_matmul(seq12, seq12, 2, 2, 3, 2).unwrap() == std::vector<float>({22, 28, 49, 64, 220, 244, 301, 334}));
     CHECK(c.matvec(V({1, 2, 3})).unwrap() == V({14, 32}));
     CHECK(Matrix::vecmat(V({1, 2}), c).unwrap() == V({9, 12, 15}));
+    // src/matrix.rs:3624-3638 convolve2d with the 1x1 identity kernel preserves the input
+    {
+        auto img = Matrix::from_vec(3, 3, {1, 2, 3, 4, 5, 6, 7, 8, 9}).unwrap();
+        auto res = img.convolve2d(Matrix::from_vec(1, 1, {1.0f}).unwrap()).unwrap();
+        CHECK(res.rows() == 3 && res.cols() == 3 && res.as_slice() == img.as_slice());
+    }
     // src/backends/gpu/batch.rs:1120-1180 relu -> scale -> add in one batch
     CommandBatch batch;
     auto in = batch.upload({1, 2, -3, 4});

@@ -57,3 +57,16 @@ def test_oracle_vecmat_and_layer_norm_kats(oracle):
     assert abs(y.mean() - 1) < 1e-3 and abs(y.std() - 2) < 1e-3
     assert np.all(np.abs(oracle.layer_norm([5] * 4, [1] * 4, [0] * 4, 1e-5)) < 1e-3)   # :7745
     assert abs(oracle.layer_norm([42], [1], [0], 1e-5)[0]) < 1e-3                       # :7760
+
+
+def test_oracle_convolve2d_kats(oracle):
+    # src/matrix.rs:3624-3638: 1x1 identity kernel preserves the input
+    inp = np.arange(1, 10, dtype=f32)
+    assert np.array_equal(oracle.convolve2d(inp, 3, 3, [1.0], 1, 1).reshape(-1), inp)
+    # src/matrix.rs:3676-3712: 3x3 averaging of a centred 9 -> centre 1.0
+    img = np.zeros(25, f32); img[12] = 9
+    out = oracle.convolve2d(img, 5, 5, np.full(9, f32(1.0) / f32(9.0), f32), 3, 3)
+    assert out.shape == (3, 3) and abs(out[1, 1] - 1.0) < 1e-5
+    # src/matrix.rs:3641-3673: horizontal edge kernel on the 4x4 plateau -> 2x2
+    edge = oracle.convolve2d([1, 1, 1, 1, 1, 2, 2, 1, 1, 2, 2, 1, 1, 1, 1, 1], 4, 4, [-1, -1, -1, 0, 0, 0, 1, 1, 1], 3, 3)
+    assert edge.shape == (2, 2) and edge.tolist() == [[1.0, 1.0], [-1.0, -1.0]]

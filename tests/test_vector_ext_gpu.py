@@ -183,3 +183,27 @@ def test_layer_norm_reference_tests_and_oracle(trn, oracle):
     trn.check(trn.lib.trn_layer_norm_rows_f32(X.ctypes.data, g.ctypes.data, cols, b.ctypes.data, cols, 1e-5, out.ctypes.data, rows, cols))
     for r in (0, 17, 32):
         assert np.array_equal(out[r], V.from_slice(X[r]).layer_norm(V.from_slice(g), V.from_slice(b), 1e-5).as_slice())
+
+
+def test_convolve2d_reference_tests_and_bit_exact(trn, oracle):
+    M = trn.Matrix
+    inp = M.from_vec(3, 3, np.arange(1, 10))
+    r = inp.convolve2d(M.from_vec(1, 1, [1.0]))                                           # src/matrix.rs:3624-3638
+    assert r.shape() == (3, 3) and np.array_equal(r.as_slice(), inp.as_slice())
+    img = np.zeros(25, f32); img[12] = 9
+    r = M.from_vec(5, 5, img).convolve2d(M.from_vec(3, 3, np.full(9, f32(1.0) / f32(9.0), f32)))   # :3676-3712
+    assert r.shape() == (3, 3) and abs(r.get(1, 1) - 1.0) < 1e-5
+    with pytest.raises(trn.TruenoError) as e:                                             # :3715-3722
+        M.from_vec(3, 3, np.ones(9)).convolve2d(M.from_vec(4, 4, np.ones(16)))
+    assert e.value == trn.TruenoError.InvalidInput("Kernel size (4x4) larger than input (3x3)")
+    # zero kernel -> zero output; scalar multiplication (src/matrix.rs:4092-4135)
+    z = M.from_vec(7, 9, np.full(63, 5.0)).convolve2d(M.zeros(3, 2))
+    assert not z.as_slice().any()
+    rng = np.random.default_rng(21)
+    for rows, cols, kr, kc in ((3, 3, 3, 3), (10, 12, 1, 1), (64, 64, 3, 3), (200, 333, 5, 7), (1024, 1000, 9, 9), (130, 70, 11, 1),
+                               (300, 300, 80, 80), (97, 4096, 3, 3)):
+        A = rng.standard_normal((rows, cols)).astype(f32)
+        K = rng.standard_normal((kr, kc)).astype(f32)
+        got = M.from_vec(rows, cols, A).convolve2d(M.from_vec(kr, kc, K)).to_numpy()
+        want = oracle.convolve2d(A, rows, cols, K, kr, kc)
+        assert got.shape == want.shape and np.array_equal(got, want), (rows, cols, kr, kc)   # same order, unfused: bit-exact

@@ -100,6 +100,7 @@ _SIGNATURES = {
     "trn_norm_l2_allreduce_f32_dev": [_vp, _vp, _sz, _vp, _vp],
     "trn_argmax_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
     "trn_argmin_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
+    "trn_convolve2d_f32": [_vp, _sz, _sz, _vp, _sz, _sz, _vp], "trn_convolve2d_f32_dev": [_vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }
@@ -448,6 +449,14 @@ class Matrix:
         out = np.empty(self.data.size, np.float32)
         check(lib.trn_transpose_f32(_ptr(self.data), self._rows, self._cols, _ptr(out)))
         return Matrix(self._cols, self._rows, out)
+
+    def convolve2d(self, kernel: "Matrix") -> "Matrix":
+        """Matrix::convolve2d (src/matrix.rs:1868): valid-padding cross-correlation."""
+        ok = kernel._rows <= self._rows and kernel._cols <= self._cols
+        orows, ocols = (self._rows - kernel._rows + 1, self._cols - kernel._cols + 1) if ok else (0, 0)
+        out = np.empty(orows * ocols, np.float32)
+        check(lib.trn_convolve2d_f32(_ptr(self.data), self._rows, self._cols, _ptr(kernel.data), kernel._rows, kernel._cols, _ptr(out)))
+        return Matrix(orows, ocols, out)
 
     @staticmethod
     def vecmat(v: Vector, m: "Matrix") -> Vector:

@@ -832,4 +832,33 @@ int trn_layer_norm_rows_f32(const float* a, const float* gamma, size_t gamma_len
     return download(out, dout.p, n, c->stream);
 }
 
+// Matrix::convolve2d (src/matrix.rs:1868): valid padding; kernel larger than the input -> InvalidInput
+static int check_conv(size_t rows, size_t cols, size_t kr, size_t kc) {   // src/matrix.rs:1870-1875
+    if (kr > rows || kc > cols)
+        return fail(TRN_INVALID_INPUT, "Kernel size (%zux%zu) larger than input (%zux%zu)", kr, kc, rows, cols);
+    return TRN_OK;
+}
+int trn_convolve2d_f32_dev(const float* in, size_t rows, size_t cols, const float* kernel, size_t k_rows, size_t k_cols,
+                           float* out, void* stream) {
+    TRN_TRY(check_conv(rows, cols, k_rows, k_cols));
+    TRN_TRY(need_ctx());
+    return launch_convolve2d(in, rows, cols, kernel, k_rows, k_cols, out, resolve_stream(stream));
+}
+int trn_convolve2d_f32(const float* in, size_t rows, size_t cols, const float* kernel, size_t k_rows, size_t k_cols, float* out) {
+    TRN_TRY(check_conv(rows, cols, k_rows, k_cols));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Context* c = ctx();
+    const size_t n_out = (rows - k_rows + 1) * (cols - k_cols + 1);
+    if (n_out == 0 || k_rows * k_cols == 0) return TRN_OK;
+    DevTemp din(c->stream), dk(c->stream), dout(c->stream);
+    TRN_TRY(din.alloc(rows * cols));
+    TRN_TRY(dk.alloc(k_rows * k_cols));
+    TRN_TRY(dout.alloc(n_out));
+    TRN_TRY(upload(din.p, in, rows * cols, c->stream));
+    TRN_TRY(upload(dk.p, kernel, k_rows * k_cols, c->stream));
+    TRN_TRY(launch_convolve2d(din.p, rows, cols, dk.p, k_rows, k_cols, dout.p, c->stream));
+    return download(out, dout.p, n_out, c->stream);
+}
+
 }  // extern "C"

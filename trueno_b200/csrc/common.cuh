@@ -104,6 +104,8 @@ int launch_map(Map op, const float* a, const float* b, const float* c, float* ou
 int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows, size_t cols, cudaStream_t s);
 
 int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaStream_t s);
+int launch_convolve2d(const float* in, size_t rows, size_t cols, const float* kernel, size_t kr, size_t kc, float* out,
+                      cudaStream_t s);
 int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, float* y, cudaStream_t s);
 int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s, bool skip_zero = true);
 int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta, float eps, float* out, size_t rows,
