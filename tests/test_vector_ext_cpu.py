@@ -69,4 +69,4 @@ def test_oracle_convolve2d_kats(oracle):
     assert out.shape == (3, 3) and abs(out[1, 1] - 1.0) < 1e-5
     # src/matrix.rs:3641-3673: horizontal edge kernel on the 4x4 plateau -> 2x2
     edge = oracle.convolve2d([1, 1, 1, 1, 1, 2, 2, 1, 1, 2, 2, 1, 1, 1, 1, 1], 4, 4, [-1, -1, -1, 0, 0, 0, 1, 1, 1], 3, 3)
-    assert edge.shape == (2, 2) and edge.tolist() == [[1.0, 1.0], [-1.0, -1.0]]
+    assert edge.shape == (2, 2) and edge.tolist() == [[2.0, 2.0], [-2.0, -2.0]]   # shape pinned by the reference; values by hand: -(1+1+1) + (1+2+2)
