@@ -319,6 +319,20 @@ TRN_API int trn_convolve2d_f32(const float* in, size_t rows, size_t cols, const 
 TRN_API int trn_convolve2d_f32_dev(const float* in, size_t rows, size_t cols, const float* kernel, size_t k_rows,
                                    size_t k_cols, float* out, void* stream);
 
+/* Fused scaled-dot-product attention: out = softmax(scale * Q K^T [causal]) V per head.
+ * Replaces trueno-gpu's AttentionKernel (trueno-gpu/src/kernels/attention.rs:27-125: q/k/v/o are
+ * [num_heads][seq_len][head_dim] f32, `scale` defaults to 1/sqrt(head_dim) there, `causal` masks keys after the
+ * query) and the CPU composition batched_matmul_4d(Q, K^T) -> scale -> softmax -> batched_matmul_4d(P, V)
+ * (src/matrix.rs:464, :3985; src/vector.rs:1516).  The score matrix is never written to memory.  head_dim <= 128
+ * runs on the tensor cores (3xTF32, same accuracy contract as matmul); 128 < head_dim <= 1024 on the SIMT kernel;
+ * larger -> TRN_INVALID_INPUT.  Size errors: "Q data size mismatch: expected {} (heads*seq*head_dim), got {}"
+ * (likewise K, V) in the style of src/matrix.rs:481-502.  Engine follows trn_set_gemm_engine (1 = SIMT, 2 = tensor). */
+TRN_API int trn_attention_f32(const float* q, size_t q_len, const float* k, size_t k_len, const float* v, size_t v_len,
+                              float* out, size_t heads, size_t seq_len, size_t head_dim, float scale, int causal);
+TRN_API int trn_attention_f32_dev(const float* q, size_t q_len, const float* k, size_t k_len, const float* v, size_t v_len,
+                                  float* out, size_t heads, size_t seq_len, size_t head_dim, float scale, int causal,
+                                  void* stream);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

@@ -263,6 +263,27 @@ class Oracle:
         self._check(self.lib.orc_batched_matmul_4d(_p(A), A.size, _p(B), B.size, _p(out), batch, heads, m, k, n, int(parallel)))
         return out
 
+    def attention(self, q, k, v, heads, seq, d, scale=None, causal=False):
+        """TEST ORACLE for the fused attention: the composition the reference spells with its own CPU operators —
+        Matrix::transpose (src/matrix.rs:1590) + Matrix::matmul (src/matrix.rs:285) for Q K^T (the "attention
+        pattern" of src/matrix.rs:3985), ScalarBackend::scale, Vector::softmax per row (src/vector.rs:1516), matmul
+        with V — with trueno-gpu's AttentionKernel conventions (trueno-gpu/src/kernels/attention.rs:46-112):
+        layout [heads][seq][d], scale = 1/sqrt(d) by default, causal = keys after the query are masked."""
+        q = _f32(q).reshape(heads, seq, d); k = _f32(k).reshape(heads, seq, d); v = _f32(v).reshape(heads, seq, d)
+        if scale is None:
+            scale = np.float32(1.0) / np.sqrt(np.float32(d))
+        scale = np.float32(scale)
+        out = np.empty((heads, seq, d), np.float32)
+        for h in range(heads):
+            kt = self.transpose(k[h].ravel(), seq, d)
+            s = self.matmul(q[h].ravel(), (seq, d), kt, (d, seq)).reshape(seq, seq)
+            s = self.scalar_map("scale", s.ravel(), p0=float(scale)).reshape(seq, seq)
+            if causal:
+                s = np.where(np.arange(seq)[None, :] > np.arange(seq)[:, None], np.float32(-np.inf), s).astype(np.float32)
+            p = self.softmax_rows(s.ravel(), seq, seq)
+            out[h] = self.matmul(p, (seq, seq), v[h].ravel(), (seq, d)).reshape(seq, d)
+        return out.ravel()
+
     def matvec(self, A, rows, cols, v, parallel=False):
         A, v = _f32(A), _f32(v)
         out = np.empty(rows, np.float32)

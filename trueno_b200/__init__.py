@@ -101,6 +101,8 @@ _SIGNATURES = {
     "trn_argmax_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
     "trn_argmin_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
     "trn_convolve2d_f32": [_vp, _sz, _sz, _vp, _sz, _sz, _vp], "trn_convolve2d_f32_dev": [_vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp],
+    "trn_attention_f32": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, C.c_float, C.c_int],
+    "trn_attention_f32_dev": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, C.c_float, C.c_int, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }
@@ -478,6 +480,19 @@ class Matrix:
         out = np.empty(batch * heads * m * n, np.float32)
         check(lib.trn_batched_matmul_4d_f32(_ptr(a), a.size, _ptr(b), b.size, _ptr(out), batch, heads, m, k, n))
         return out
+
+
+def attention(q, k, v, heads: int, seq_len: int, head_dim: int, scale: float | None = None, causal: bool = False) -> np.ndarray:
+    """Fused attention out = softmax(scale * Q K^T [causal]) V per head; q, k, v are [heads][seq_len][head_dim].
+    Mirrors trueno-gpu's `AttentionKernel::new(seq_len, head_dim)[.with_causal()][.with_scale(s)]`
+    (trueno-gpu/src/kernels/attention.rs:46-112): `scale` defaults to 1/sqrt(head_dim)."""
+    q, k, v = _as_f32(q), _as_f32(k), _as_f32(v)
+    if scale is None:
+        scale = 1.0 / float(np.sqrt(np.float32(head_dim))) if head_dim else 1.0
+    out = np.empty(heads * seq_len * head_dim, np.float32)
+    check(lib.trn_attention_f32(_ptr(q), q.size, _ptr(k), k.size, _ptr(v), v.size, _ptr(out), heads, seq_len, head_dim,
+                                float(scale), int(bool(causal))))
+    return out
 
 
 class CommandBatch:

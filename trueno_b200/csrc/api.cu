@@ -861,4 +861,50 @@ int trn_convolve2d_f32(const float* in, size_t rows, size_t cols, const float* k
     return download(out, dout.p, n_out, c->stream);
 }
 
+// ---- fused attention (trueno-gpu/src/kernels/attention.rs:27-125) ---------------------------------------------
+static int check_attention(size_t q_len, size_t k_len, size_t v_len, size_t heads, size_t seq, size_t d) {
+    const size_t want = heads * seq * d;   // size checks in the style of src/matrix.rs:481-502
+    const char* names[3] = {"Q", "K", "V"};
+    const size_t lens[3] = {q_len, k_len, v_len};
+    for (int i = 0; i < 3; ++i)
+        if (lens[i] != want)
+            return fail(TRN_INVALID_INPUT, "%s data size mismatch: expected %zu (%zu\xC3\x97%zu\xC3\x97%zu), got %zu", names[i], want,
+                        heads, seq, d, lens[i]);
+    if (d > attention_max_head_dim())
+        return fail(TRN_INVALID_INPUT, "head_dim %zu exceeds the supported maximum %zu", d, attention_max_head_dim());
+    return TRN_OK;
+}
+static int attention_engine() {
+    const int e = g_engine.load();
+    return e == 1 ? 1 : (e == 2 ? 2 : 0);
+}
+int trn_attention_f32_dev(const float* q, size_t q_len, const float* k, size_t k_len, const float* v, size_t v_len, float* out,
+                          size_t heads, size_t seq_len, size_t head_dim, float scale, int causal, void* stream) {
+    TRN_TRY(check_attention(q_len, k_len, v_len, heads, seq_len, head_dim));
+    TRN_TRY(need_ctx());
+    // engine 2 on a head_dim the tensor kernel cannot take falls back to auto rather than failing a forced test sweep
+    const int engine = (attention_engine() == 2 && head_dim > 128) ? 0 : attention_engine();
+    return launch_attention(q, k, v, out, heads, seq_len, head_dim, scale, causal, engine, resolve_stream(stream));
+}
+int trn_attention_f32(const float* q, size_t q_len, const float* k, size_t k_len, const float* v, size_t v_len, float* out,
+                      size_t heads, size_t seq_len, size_t head_dim, float scale, int causal) {
+    TRN_TRY(check_attention(q_len, k_len, v_len, heads, seq_len, head_dim));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Context* c = ctx();
+    const size_t n = heads * seq_len * head_dim;
+    if (n == 0) return TRN_OK;
+    DevTemp dq(c->stream), dk(c->stream), dv(c->stream), dout(c->stream);
+    TRN_TRY(dq.alloc(n));
+    TRN_TRY(dk.alloc(n));
+    TRN_TRY(dv.alloc(n));
+    TRN_TRY(dout.alloc(n));
+    TRN_TRY(upload(dq.p, q, n, c->stream));
+    TRN_TRY(upload(dk.p, k, n, c->stream));
+    TRN_TRY(upload(dv.p, v, n, c->stream));
+    const int engine = (attention_engine() == 2 && head_dim > 128) ? 0 : attention_engine();
+    TRN_TRY(launch_attention(dq.p, dk.p, dv.p, dout.p, heads, seq_len, head_dim, scale, causal, engine, c->stream));
+    return download(out, dout.p, n, c->stream);
+}
+
 }  // extern "C"

@@ -1,0 +1,461 @@
+// attention.cu — fused scaled-dot-product attention, O = softmax(scale * Q K^T [+ causal mask]) V, f32 in / f32 out.
+//
+// Replaces: trueno-gpu's `AttentionKernel` (trueno-gpu/src/kernels/attention.rs:27-125,
+// parameters q/k/v/o [num_heads][seq_len][head_dim], `scale` = 1/sqrt(head_dim) by default, `causal`), i.e. the
+// fusion of the composition the reference spells on the CPU as batched_matmul_4d(Q, K^T) (src/matrix.rs:464,
+// the "attention pattern" test at :3985) -> Vector::scale -> Vector::softmax (src/vector.rs:1516) ->
+// batched_matmul_4d(P, V).  The seq x seq score matrix never exists in HBM.
+//
+// attention_tf32x3_kernel (head_dim <= 128): one CTA per (head, 128 query rows), 320 threads:
+//   warp 0   TMA producer: 6 x 32 KiB ring of 16-wide k-blocks of the pre-split (hi, lo) operands
+//   warp 1   MMA issuer (one elected lane), tcgen05.mma kind::tf32, 3xTF32 (lo*hi + hi*lo + hi*hi):
+//              S  = Q K_j^T        A, B from shared memory            -> TMEM columns [0,128)
+//              O' = P_j V_j        A = P (hi, lo) from TENSOR MEMORY  -> TMEM columns [384,512)
+//   warps 2-9  softmax: thread = (query row, 64-column half).  Per 128-key tile: tcgen05.ld the scores, free the
+//              S buffer at once (so S_{j+1} runs on the tensor pipe while this tile's exponentials run on the
+//              CUDA cores), scale, mask, running max (halves exchange through shared memory), p = expf(x - m),
+//              split p into tf32 hi/lo and tcgen05.st them to TMEM columns [128,256) / [256,384); then drain the
+//              previous tile's O' into register accumulators: O = O * exp(m_old - m_new) + O'.
+//   Like the GEMM (gemm_tc.cu), TMEM only ever holds partial sums over 128 terms; the second accumulation level is
+//   round-to-nearest in registers, which is also where the online-softmax rescaling happens — no TMEM rescale pass.
+//   Issue order S_0, S_1, PV_0, S_2, PV_1, ...: the tensor pipe always has the next S queued behind a PV.
+// attention_simt_kernel: one warp per query row, any head_dim <= 1024; the IEEE path for Inf/NaN inputs (gated on
+//   the split pre-pass's device flag, as in the GEMM) and for head_dim > 128.
+//
+// Tensor-bound: 4 * seq^2 * head_dim flop per head (2 * seq^2 * head_dim for causal), executed 3x in TF32.
+// HBM traffic is O(seq * head_dim) per head; K and V tiles are re-read from L2 by the seq/128 query tiles.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace trn {
+namespace attn {
+
+using namespace tc;
+
+constexpr int BQ = 128;        // query rows per CTA (UMMA M)
+constexpr int BKV = 128;       // keys per tile (UMMA N of S, K extent of one TMEM partial of O)
+constexpr int SBK = 16;        // floats of K per ring stage (SWIZZLE_64B rows)
+constexpr int kStages = 6;
+constexpr uint32_t kTile = 128 * SBK * 4;            // 8 KiB: 128 rows x 64 B
+constexpr uint32_t kStageBytes = 4 * kTile;          // S phase: Q_hi, K_hi, Q_lo, K_lo; PV phase: V_hi, -, V_lo, -
+constexpr int kThreads = 320;
+constexpr int kSoftmaxWarps = 8;
+constexpr uint32_t kColS = 0, kColPhi = 128, kColPlo = 256, kColO = 384, kTmemCols = 512;
+constexpr uint32_t kXchgBytes = 3 * 2 * 128 * 4;     // [buffer][half][row]
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kXchgBytes + 256 + 1024;
+
+struct Params {
+    float* out;
+    const int* nonfinite_flag;
+    uint32_t heads, seq, d;
+    uint32_t dn;          // UMMA N of the PV product: head_dim rounded up to 16
+    uint32_t num_kb_s;    // dpad / SBK
+    uint32_t q_tiles;
+    float scale;
+    uint32_t causal;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                        const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
+                        const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
+                        const Params p) {
+    if (*p.nonfinite_flag != 0) return;   // Inf/NaN in the inputs: the SIMT kernel takes over (grid-uniform)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    float* xchg = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * kStageBytes + kXchgBytes);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    const uint32_t s_full = bar_base + 8u * (2 * kStages), s_free = s_full + 8, p_full = s_full + 16,
+                   o_full = s_full + 24, o_free = s_full + 32;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // heavy (late, for causal) query tiles first
+    const uint32_t head = blockIdx.x / p.q_tiles;
+    const uint32_t qt = p.q_tiles - 1 - blockIdx.x % p.q_tiles;
+    const uint32_t q0 = qt * BQ;
+    const uint32_t kv_tiles = p.causal ? qt + 1 : (p.seq + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q_hi); tma_prefetch_desc(&map_k_hi); tma_prefetch_desc(&map_v_hi);
+        tma_prefetch_desc(&map_q_lo); tma_prefetch_desc(&map_k_lo); tma_prefetch_desc(&map_v_lo);
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, kSoftmaxWarps);
+        mbar_init(p_full, kSoftmaxWarps);
+        mbar_init(o_full, 1);
+        mbar_init(o_free, kSoftmaxWarps);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: the MMA warp's order S_0, S_1, PV_0, S_2, PV_1, ... =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t step = 0; step <= kv_tiles; ++step) {
+                if (step < kv_tiles) {
+                    const int key0 = (int)(step * BKV);
+                    for (uint32_t kb = 0; kb < p.num_kb_s; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        mbar_expect_tx(full_bar(stage), 4 * kTile);
+                        const int k0 = (int)(kb * SBK);
+                        tma_load_3d(sa, &map_q_hi, full_bar(stage), k0, (int)q0, (int)head);
+                        tma_load_3d(sa + kTile, &map_k_hi, full_bar(stage), k0, key0, (int)head);
+                        tma_load_3d(sa + 2 * kTile, &map_q_lo, full_bar(stage), k0, (int)q0, (int)head);
+                        tma_load_3d(sa + 3 * kTile, &map_k_lo, full_bar(stage), k0, key0, (int)head);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                if (step >= 1) {
+                    const int key0 = (int)((step - 1) * BKV);
+                    for (uint32_t kb = 0; kb < BKV / SBK; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        mbar_expect_tx(full_bar(stage), 2 * p.dn * SBK * 4);
+                        tma_load_3d(sa, &map_v_hi, full_bar(stage), key0 + (int)(kb * SBK), 0, (int)head);
+                        tma_load_3d(sa + 2 * kTile, &map_v_lo, full_bar(stage), key0 + (int)(kb * SBK), 0, (int)head);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_s = make_idesc_tf32(BQ, BKV);
+        const uint32_t idesc_o = make_idesc_tf32(BQ, (int)p.dn);
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t step = 0; step <= kv_tiles; ++step) {
+            if (step < kv_tiles) {
+                // ---- S_step = Q K^T over head_dim
+                if (step >= 1) {
+                    mbar_wait(s_free, (step - 1) & 1);   // the softmax warps have read S_{step-1}
+                    tc_fence_after();
+                }
+                for (uint32_t kb = 0; kb < p.num_kb_s; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint32_t q_hi = sa, k_hi = sa + kTile, q_lo = sa + 2 * kTile, k_lo = sa + 3 * kTile;
+                        const uint32_t dst = tmem_base + kColS;
+#pragma unroll
+                        for (int k = 0; k < SBK / UMMA_K; ++k) {
+                            const uint32_t koff = k * UMMA_K * 4;
+                            const uint32_t accum = (kb | (uint32_t)k) != 0;
+                            umma_tf32(dst, make_desc_k<SBK>(q_lo + koff), make_desc_k<SBK>(k_hi + koff), idesc_s, accum);
+                            umma_tf32(dst, make_desc_k<SBK>(q_hi + koff), make_desc_k<SBK>(k_lo + koff), idesc_s, 1u);
+                            umma_tf32(dst, make_desc_k<SBK>(q_hi + koff), make_desc_k<SBK>(k_hi + koff), idesc_s, 1u);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (kb == p.num_kb_s - 1) umma_commit(s_full);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (step >= 1) {
+                // ---- O'_{t} = P_t V_t over the tile's 128 keys, t = step - 1
+                const uint32_t t = step - 1;
+                mbar_wait(p_full, t & 1);                      // P_t is in tensor memory
+                if (t >= 1) mbar_wait(o_free, (t - 1) & 1);    // O'_{t-1} has been drained
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < BKV / SBK; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint32_t v_hi = sa, v_lo = sa + 2 * kTile;
+                        const uint32_t dst = tmem_base + kColO;
+#pragma unroll
+                        for (int k = 0; k < SBK / UMMA_K; ++k) {
+                            const uint32_t koff = k * UMMA_K * 4;
+                            const uint32_t pcol = kb * SBK + k * UMMA_K;
+                            const uint32_t accum = (kb | (uint32_t)k) != 0;
+                            umma_tf32_ts(dst, tmem_base + kColPlo + pcol, make_desc_k<SBK>(v_hi + koff), idesc_o, accum);
+                            umma_tf32_ts(dst, tmem_base + kColPhi + pcol, make_desc_k<SBK>(v_lo + koff), idesc_o, 1u);
+                            umma_tf32_ts(dst, tmem_base + kColPhi + pcol, make_desc_k<SBK>(v_hi + koff), idesc_o, 1u);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (kb == BKV / SBK - 1) umma_commit(o_full);   // O'_t complete; P_t no longer needed
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== softmax / accumulation warps =====================
+        const uint32_t quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const uint32_t half = (uint32_t)(warp - 2) >> 2;  // which 64 of the tile's 128 keys / of the output columns
+        const uint32_t row_in_tile = quad * 32 + lane;
+        const uint32_t qrow = q0 + row_in_tile;
+        const uint32_t lane_addr = tmem_base + ((quad * 32u) << 16);
+        const uint32_t ocols = p.dn > 64 * half ? min(64u, p.dn - 64 * half) : 0u;   // this thread's O columns
+        float o_acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o_acc[i] = 0.0f;
+        float m_run = -INFINITY, l_part = 0.0f, alpha_prev = 0.0f;
+
+        auto drain_o = [&](uint32_t t, float alpha) {
+            // O = O * alpha + O'_t  (second accumulation level, round-to-nearest)
+            mbar_wait(o_full, t & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if ((uint32_t)(j * 32) < ocols) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(lane_addr + kColO + 64 * half + j * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o_acc[j * 32 + i] = __fmaf_rn(o_acc[j * 32 + i], alpha, __uint_as_float(r[i]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
+        };
+
+        for (uint32_t t = 0; t < kv_tiles; ++t) {
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+            float x[64];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t r[32];
+                tmem_ld_32x32(lane_addr + kColS + 64 * half + j * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[j * 32 + i] = __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);   // S_{t+1} may overwrite the buffer
+
+            // scale, mask (keys past the sequence, keys after the query when causal), tile maximum
+            const uint32_t key0 = t * BKV + 64 * half;
+            float m_loc = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const uint32_t key = key0 + i;
+                const bool valid = key < p.seq && (!p.causal || key <= qrow);
+                x[i] = valid ? __fmul_rn(x[i], p.scale) : -INFINITY;
+                m_loc = fmaxf(m_loc, x[i]);
+            }
+            float* xb = xchg + (t & 1) * 256;
+            xb[half * 128 + row_in_tile] = m_loc;
+            named_bar_sync(1 + quad, 64);
+            const float m_new = fmaxf(m_run, fmaxf(m_loc, xb[(half ^ 1) * 128 + row_in_tile]));
+            const float m_use = m_new == -INFINITY ? 0.0f : m_new;            // row with no valid key yet
+            const float alpha = m_run == -INFINITY ? 0.0f : expf(m_run - m_use);
+            m_run = m_new;
+
+            // p = exp(x - m) in place, row-sum partial
+            float l_tile = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                x[i] = expf(x[i] - m_use);
+                l_tile += x[i];
+            }
+            l_part = __fmaf_rn(l_part, alpha, l_tile);
+
+            // the previous tile's PV product must have retired before P is overwritten; drain its O' first
+            if (t >= 1) drain_o(t - 1, alpha_prev);
+            alpha_prev = alpha;
+            // tf32 split: hi = rna(p), lo = rna(p - hi)  (p - hi is exact), written where the MMA reads its A operand
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[i]) : "f"(x[j * 32 + i]));
+                tmem_st_32x32(lane_addr + kColPhi + 64 * half + j * 32, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float rest = x[j * 32 + i] - __uint_as_float(r[i]);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[i]) : "f"(rest));
+                }
+                tmem_st_32x32(lane_addr + kColPlo + 64 * half + j * 32, r);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        drain_o(kv_tiles - 1, alpha_prev);
+
+        // row sum: half 0 + half 1 (fixed order), then normalise and store this thread's columns
+        float* xb = xchg + 2 * 256;
+        xb[half * 128 + row_in_tile] = l_part;
+        named_bar_sync(1 + quad, 64);
+        const float l = xb[row_in_tile] + xb[128 + row_in_tile];
+        if (qrow < p.seq && ocols > 0) {
+            float* orow = p.out + ((size_t)head * p.seq + qrow) * p.d + 64 * half;
+            const uint32_t ncol = min(ocols, p.d > 64 * half ? p.d - 64 * half : 0u);
+            const bool vec = (p.d & 3u) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+                if ((uint32_t)i + 3 < ncol && vec) {
+                    *reinterpret_cast<float4*>(orow + i) = make_float4(o_acc[i] / l, o_acc[i + 1] / l, o_acc[i + 2] / l, o_acc[i + 3] / l);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((uint32_t)(i + e) < ncol) orow[i + e] = o_acc[i + e] / l;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- IEEE path: one warp per query row, online softmax key by key -------------------------------------------
+constexpr int kSimtMaxC = 32;   // head_dim <= 1024
+
+__global__ void __launch_bounds__(128)
+attention_simt_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                      float* __restrict__ out, uint32_t heads, uint32_t seq, uint32_t d, float scale, uint32_t causal,
+                      const int* __restrict__ only_if_flag) {
+    if (only_if_flag != nullptr && *only_if_flag == 0) return;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t row_id = (size_t)blockIdx.x * 4 + warp;
+    if (row_id >= (size_t)heads * seq) return;
+    const uint32_t head = (uint32_t)(row_id / seq), qrow = (uint32_t)(row_id % seq);
+    const float* qr = q + row_id * d;
+    const float* kh = k + (size_t)head * seq * d;
+    const float* vh = v + (size_t)head * seq * d;
+    float qv[kSimtMaxC], o[kSimtMaxC];
+#pragma unroll
+    for (int c = 0; c < kSimtMaxC; ++c) {
+        const uint32_t col = c * 32 + lane;
+        qv[c] = col < d ? qr[col] : 0.0f;
+        o[c] = 0.0f;
+    }
+    const uint32_t nc = (d + 31) / 32;
+    float m = -INFINITY, l = 0.0f;
+    const uint32_t last = causal ? qrow + 1 : seq;
+    for (uint32_t j = 0; j < last; ++j) {
+        float part = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kSimtMaxC; ++c) {
+            if ((uint32_t)c < nc) {
+                const uint32_t col = c * 32 + lane;
+                if (col < d) part = fmaf(qv[c], kh[(size_t)j * d + col], part);
+            }
+        }
+        const float x = warp_sum(part) * scale;
+        const float m_new = fmaxf(m, x);
+        // NaN scores propagate through fmaxf-free arithmetic below: keep m finite-or-NaN consistent
+        const float alpha = m == -INFINITY ? 0.0f : expf(m - m_new);
+        const float pv = expf(x - m_new);
+        l = fmaf(l, alpha, pv);
+#pragma unroll
+        for (int c = 0; c < kSimtMaxC; ++c) {
+            if ((uint32_t)c < nc) {
+                const uint32_t col = c * 32 + lane;
+                if (col < d) o[c] = fmaf(o[c], alpha, pv * vh[(size_t)j * d + col]);
+            }
+        }
+        m = m_new;
+    }
+#pragma unroll
+    for (int c = 0; c < kSimtMaxC; ++c) {
+        const uint32_t col = c * 32 + lane;
+        if ((uint32_t)c < nc && col < d) out[row_id * d + col] = o[c] / l;
+    }
+}
+
+}  // namespace attn
+
+size_t attention_max_head_dim() { return (size_t)attn::kSimtMaxC * 32; }
+
+// q, k, v, out: [heads][seq][d] row-major f32 on the device.  engine: 0 auto, 1 SIMT, 2 tensor cores.
+int launch_attention(const float* q, const float* k, const float* v, float* out, size_t heads, size_t seq, size_t d,
+                     float scale, int causal, int engine, cudaStream_t s) {
+    using namespace attn;
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
+    if (heads == 0 || seq == 0 || d == 0) return TRN_OK;
+    const size_t rows = heads * seq;
+    const size_t simt_blocks = (rows + 3) / 4;
+    if (simt_blocks > 0x7FFFFFFFull || seq >= (1u << 30)) return fail(TRN_INVALID_INPUT, "attention over %zu rows exceeds the launch grid", rows);
+    const bool tc_ok = d <= 128 && heads * ((seq + BQ - 1) / BQ) <= 0x7FFFFFFFull;
+    if (engine == 2 && !tc_ok) return fail(TRN_INVALID_INPUT, "tensor-core attention needs head_dim <= 128, got %zu", d);
+    if (engine == 1 || !tc_ok) {
+        attention_simt_kernel<<<(unsigned)simt_blocks, 128, 0, s>>>(q, k, v, out, (uint32_t)heads, (uint32_t)seq, (uint32_t)d,
+                                                                   scale, causal ? 1u : 0u, nullptr);
+        count_launch();
+        TRN_CUDA(cudaGetLastError());
+        return TRN_OK;
+    }
+
+    // split pre-pass: Q, K -> hi/lo [heads][seq][dpad] (K-major as they are); V -> hi/lo [heads][d][seqpad] (transposed)
+    const size_t dpad = gemm_tc_kpad(d), seqpad = gemm_tc_kpad(seq);
+    const size_t qk_elems = heads * seq * dpad, v_elems = heads * d * seqpad;
+    float* scratch = nullptr;
+    TRN_TRY(scratch_alloc((void**)&scratch, (4 * qk_elems + 2 * v_elems) * sizeof(float) + 256, s));
+    float* q_hi = scratch;
+    float* q_lo = q_hi + qk_elems;
+    float* k_hi = q_lo + qk_elems;
+    float* k_lo = k_hi + qk_elems;
+    float* v_hi = k_lo + qk_elems;
+    float* v_lo = v_hi + v_elems;
+    int* flag = reinterpret_cast<int*>(v_lo + v_elems);
+    int st = TRN_OK;
+    auto run = [&]() -> int {
+        TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+        TRN_TRY(gemm_tc_split_a(q, q_hi, q_lo, heads, seq, d, flag, s));
+        TRN_TRY(gemm_tc_split_a(k, k_hi, k_lo, heads, seq, d, flag, s));
+        TRN_TRY(gemm_tc_split_b(v, v_hi, v_lo, heads, seq, d, flag, s));
+        Params p;
+        p.out = out;
+        p.nonfinite_flag = flag;
+        p.heads = (uint32_t)heads;
+        p.seq = (uint32_t)seq;
+        p.d = (uint32_t)d;
+        p.dn = (uint32_t)((d + 15) / 16 * 16);
+        p.num_kb_s = (uint32_t)(dpad / SBK);
+        p.q_tiles = (uint32_t)((seq + BQ - 1) / BQ);
+        p.scale = scale;
+        p.causal = causal ? 1u : 0u;
+        CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
+        TRN_TRY(make_map(&mq_h, q_hi, heads, seq, dpad, BQ, SBK));
+        TRN_TRY(make_map(&mq_l, q_lo, heads, seq, dpad, BQ, SBK));
+        TRN_TRY(make_map(&mk_h, k_hi, heads, seq, dpad, BKV, SBK));
+        TRN_TRY(make_map(&mk_l, k_lo, heads, seq, dpad, BKV, SBK));
+        TRN_TRY(make_map(&mv_h, v_hi, heads, d, seqpad, p.dn, SBK));
+        TRN_TRY(make_map(&mv_l, v_lo, heads, d, seqpad, p.dn, SBK));
+        static const cudaError_t optin = cudaFuncSetAttribute(attention_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        TRN_CUDA(optin);
+        attention_tf32x3_kernel<<<(unsigned)(heads * p.q_tiles), kThreads, kSmemBytes, s>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+        count_launch();
+        TRN_CUDA(cudaGetLastError());
+        // IEEE path for Inf/NaN inputs: runs only when the split pre-pass raised the flag (checked on the device)
+        attention_simt_kernel<<<(unsigned)simt_blocks, 128, 0, s>>>(q, k, v, out, (uint32_t)heads, (uint32_t)seq, (uint32_t)d,
+                                                                   scale, causal ? 1u : 0u, flag);
+        count_launch();
+        TRN_CUDA(cudaGetLastError());
+        return TRN_OK;
+    };
+    st = run();
+    scratch_free(scratch, s);
+    return st;
+}
+
+}  // namespace trn

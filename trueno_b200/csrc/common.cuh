@@ -106,6 +106,10 @@ int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows
 int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaStream_t s);
 int launch_convolve2d(const float* in, size_t rows, size_t cols, const float* kernel, size_t kr, size_t kc, float* out,
                       cudaStream_t s);
+// fused attention (attention.cu): q, k, v, out [heads][seq][d]; engine 0 auto, 1 SIMT, 2 tcgen05
+int launch_attention(const float* q, const float* k, const float* v, float* out, size_t heads, size_t seq, size_t d,
+                     float scale, int causal, int engine, cudaStream_t s);
+size_t attention_max_head_dim();
 int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, float* y, cudaStream_t s);
 int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s, bool skip_zero = true);
 int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta, float eps, float* out, size_t rows,

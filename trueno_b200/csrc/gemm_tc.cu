@@ -43,6 +43,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace trn {
 namespace tc {
@@ -50,7 +51,6 @@ namespace tc {
 constexpr int BM = 128;   // UMMA M (cta_group::1)
 constexpr int BN = 256;   // UMMA N
 constexpr int BK = 32;    // K padding granularity of the split operands (Kpad % 32 == 0)
-constexpr int UMMA_K = 8; // kind::tf32: 32 bytes of K per instruction
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kChunkK = 128;  // K extent accumulated in TMEM before draining to registers
@@ -70,69 +70,6 @@ struct Cfg {
     static constexpr uint32_t kStoreBytes = kEpiWarps * 4096;  // one 32x32 f32 staging block per epilogue warp
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
-
-// ---- PTX wrappers (mbarrier / smem helpers are in common.cuh) ----------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 columns of 32-bit: thread t of the warp receives row (lane base + t), 32 consecutive columns
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
-//   [32,46) stride byte offset >> 4 (bytes between 8-row groups)
-//   [46,48) version = 1 (sm_100)   [61,64) layout type
-// SBK = 32: rows of 128 B, SWIZZLE_128B (type 2), 1024 B between 8-row groups;
-// SBK = 16: rows of  64 B, SWIZZLE_64B  (type 4),  512 B between 8-row groups.
-template <int SBK>
-__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
-    constexpr uint64_t sbo = (8 * SBK * 4) >> 4;
-    constexpr uint64_t type = SBK == 32 ? 2ull : 4ull;
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
-}
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(m >> 4) << 24);
-}
 
 struct Params {
     float* c;
@@ -711,8 +648,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // [batch][rows][kpad] f32, box = {box_cols, box_rows, 1}; swizzle span = box_cols * 4 bytes (128 or 64)
-static int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows,
-                    uint32_t box_cols) {
+int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows,
+             uint32_t box_cols) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     cuuint64_t dims[3] = {kpad, rows, batch};
