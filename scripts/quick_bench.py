@@ -143,6 +143,36 @@ def main():
         print(f"batched4d cuBLAS FP32 median {med:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
         del a, b, c
 
+    if "attention" in which:
+        # BASELINE config 3's head shape, now fused: out = softmax(scale * Q K^T) V per head
+        import os
+        H, seq, d = int(os.environ.get("ATT_HEADS", 256)), int(os.environ.get("ATT_SEQ", 2048)), int(os.environ.get("ATT_D", 128))
+        q = torch.randn(H * seq * d, device="cuda"); k = torch.randn(H * seq * d, device="cuda"); v = torch.randn(H * seq * d, device="cuda")
+        o = torch.empty(H * seq * d, device="cuda")
+        scale = 1.0 / d ** 0.5
+        for causal in (0, 1):
+            flop = 4.0 * H * seq * seq * d * (0.5 if causal else 1.0)
+            fn = lambda: trn.check(L.trn_attention_f32_dev(q.data_ptr(), q.numel(), k.data_ptr(), k.numel(), v.data_ptr(), v.numel(),
+                                                           o.data_ptr(), H, seq, d, scale, causal, st))
+            med, best = timeit(fn, iters=10)
+            print(f"attention H={H} seq={seq} d={d} causal={causal} fused 3xTF32 median {med:.3f} ms best {best:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
+            q4, k4, v4 = (t.view(1, H, seq, d) for t in (q, k, v))
+            torch.backends.cuda.matmul.allow_tf32 = False
+            med, best = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4, is_causal=bool(causal)), iters=5)
+            print(f"   torch SDPA fp32 median {med:.3f} ms  {flop / med / 1e9:.1f} TFLOP/s")
+        # unfused composition on this library's own kernels (needs the seq x seq scores in HBM)
+        if H * seq * seq * 4 <= (8 << 30):
+            s_buf = torch.empty(H * seq * seq, device="cuda")
+            p_buf = torch.empty(H * seq * seq, device="cuda")
+            kt = k.view(H, seq, d).transpose(1, 2).contiguous().view(-1)
+            def unfused():
+                trn.check(L.trn_batched_matmul_f32_dev(q.data_ptr(), q.numel(), kt.data_ptr(), kt.numel(), s_buf.data_ptr(), H, seq, d, seq, st))
+                trn.check(L.trn_scale_f32_dev(s_buf.data_ptr(), s_buf.numel(), scale, s_buf.data_ptr(), st))
+                trn.check(L.trn_softmax_rows_f32_dev(s_buf.data_ptr(), p_buf.data_ptr(), H * seq, seq, st))
+                trn.check(L.trn_batched_matmul_f32_dev(p_buf.data_ptr(), p_buf.numel(), v.data_ptr(), v.numel(), o.data_ptr(), H, seq, seq, d, st))
+            med, best = timeit(unfused, iters=5)
+            print(f"   unfused (bmm -> scale -> softmax -> bmm, K^T given) median {med:.3f} ms  {4.0 * H * seq * seq * d / med / 1e9:.1f} TFLOP/s")
+
     if "rowblock" in which:
         # BASELINE config 5b: one GPU's share of the 32768^3 product at 8 GPUs (A-block 4096 x 32768, full B)
         n, mb = 32768, 4096

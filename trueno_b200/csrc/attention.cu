@@ -13,7 +13,7 @@
 //              O' = P_j V_j        A = P (hi, lo) from TENSOR MEMORY  -> TMEM columns [384,512)
 //   warps 2-9  softmax: thread = (query row, 64-column half).  Per 128-key tile: tcgen05.ld the scores, free the
 //              S buffer at once (so S_{j+1} runs on the tensor pipe while this tile's exponentials run on the
-//              CUDA cores), scale, mask, running max (halves exchange through shared memory), p = expf(x - m),
+//              CUDA cores), scale, mask, running max (halves exchange through shared memory), p = 2^(x - m),
 //              split p into tf32 hi/lo and tcgen05.st them to TMEM columns [128,256) / [256,384); then drain the
 //              previous tile's O' into register accumulators: O = O * exp(m_old - m_new) + O'.
 //   Like the GEMM (gemm_tc.cu), TMEM only ever holds partial sums over 128 terms; the second accumulation level is
@@ -45,6 +45,12 @@ constexpr int kSoftmaxWarps = 8;
 constexpr uint32_t kColS = 0, kColPhi = 128, kColPlo = 256, kColO = 384, kTmemCols = 512;
 constexpr uint32_t kXchgBytes = 3 * 2 * 128 * 4;     // [buffer][half][row]
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + kXchgBytes + 256 + 1024;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct Params {
     float* out;
@@ -208,6 +214,7 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
 #pragma unroll
         for (int i = 0; i < 64; ++i) o_acc[i] = 0.0f;
         float m_run = -INFINITY, l_part = 0.0f, alpha_prev = 0.0f;
+        const float scale2 = __fmul_rn(p.scale, 1.4426950408889634f);   // scale * log2(e)
 
         auto drain_o = [&](uint32_t t, float alpha) {
             // O = O * alpha + O'_t  (second accumulation level, round-to-nearest)
@@ -244,29 +251,41 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(s_free);   // S_{t+1} may overwrite the buffer
 
-            // scale, mask (keys past the sequence, keys after the query when causal), tile maximum
+            // Scores in the base-2 domain: x = s * (scale * log2 e), so that exp(scale*s - m) = 2^(x - m2) is one FADD
+            // and one MUFU.EX2 per element (ex2.approx: 2 ulp; the product rounding moves a score by <= 0.5 ulp —
+            // both far inside the matmul contract's 1e-5 * sum|q||k| allowance on the scores).
+            // Masking (keys past the sequence, keys after the query when causal) only on the tiles that need it.
             const uint32_t key0 = t * BKV + 64 * half;
+            const bool mask_tile = (t + 1) * BKV > p.seq || (p.causal && t == qt);   // CTA-uniform
             float m_loc = -INFINITY;
+            if (mask_tile) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const uint32_t key = key0 + i;
-                const bool valid = key < p.seq && (!p.causal || key <= qrow);
-                x[i] = valid ? __fmul_rn(x[i], p.scale) : -INFINITY;
-                m_loc = fmaxf(m_loc, x[i]);
+                for (int i = 0; i < 64; ++i) {
+                    const uint32_t key = key0 + i;
+                    const bool valid = key < p.seq && (!p.causal || key <= qrow);
+                    x[i] = valid ? __fmul_rn(x[i], scale2) : -INFINITY;
+                    m_loc = fmaxf(m_loc, x[i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    x[i] = __fmul_rn(x[i], scale2);
+                    m_loc = fmaxf(m_loc, x[i]);
+                }
             }
             float* xb = xchg + (t & 1) * 256;
             xb[half * 128 + row_in_tile] = m_loc;
             named_bar_sync(1 + quad, 64);
             const float m_new = fmaxf(m_run, fmaxf(m_loc, xb[(half ^ 1) * 128 + row_in_tile]));
             const float m_use = m_new == -INFINITY ? 0.0f : m_new;            // row with no valid key yet
-            const float alpha = m_run == -INFINITY ? 0.0f : expf(m_run - m_use);
+            const float alpha = m_run == -INFINITY ? 0.0f : ex2_approx(m_run - m_use);
             m_run = m_new;
 
-            // p = exp(x - m) in place, row-sum partial
+            // p = 2^(x - m) in place, row-sum partial
             float l_tile = 0.0f;
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
-                x[i] = expf(x[i] - m_use);
+                x[i] = ex2_approx(x[i] - m_use);
                 l_tile += x[i];
             }
             l_part = __fmaf_rn(l_part, alpha, l_tile);

@@ -84,7 +84,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // SBK = 32: rows of 128 B, SWIZZLE_128B (type 2), 1024 B between 8-row groups;
 // SBK = 16: rows of  64 B, SWIZZLE_64B  (type 4),  512 B between 8-row groups.
 template <int SBK>
-__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
+__host__ __device__ constexpr uint64_t make_desc_k(uint32_t smem_addr) {
     constexpr uint64_t sbo = (8 * SBK * 4) >> 4;
     constexpr uint64_t type = SBK == 32 ? 2ull : 4ull;
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
