@@ -52,6 +52,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// round-to-nearest, ties away, to the 10-bit tf32 mantissa — cvt.rna.tf32.f32 for finite inputs (the PTX
+// instruction is emulated with an extra Inf/NaN select on sm_100)
+__device__ __forceinline__ uint32_t tf32_rna_finite(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
+
 struct Params {
     float* out;
     const int* nonfinite_flag;
@@ -298,13 +302,10 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
             for (int j = 0; j < 2; ++j) {
                 uint32_t r[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[i]) : "f"(x[j * 32 + i]));
+                for (int i = 0; i < 32; ++i) r[i] = tf32_rna_finite(x[j * 32 + i]);
                 tmem_st_32x32(lane_addr + kColPhi + 64 * half + j * 32, r);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float rest = x[j * 32 + i] - __uint_as_float(r[i]);
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[i]) : "f"(rest));
-                }
+                for (int i = 0; i < 32; ++i) r[i] = tf32_rna_finite(x[j * 32 + i] - __uint_as_float(r[i]));
                 tmem_st_32x32(lane_addr + kColPlo + 64 * half + j * 32, r);
             }
             tmem_st_wait();
@@ -318,7 +319,7 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
         float* xb = xchg + 2 * 256;
         xb[half * 128 + row_in_tile] = l_part;
         named_bar_sync(1 + quad, 64);
-        const float l = xb[row_in_tile] + xb[128 + row_in_tile];
+        const float inv_l = 1.0f / (xb[row_in_tile] + xb[128 + row_in_tile]);
         if (qrow < p.seq && ocols > 0) {
             float* orow = p.out + ((size_t)head * p.seq + qrow) * p.d + 64 * half;
             const uint32_t ncol = min(ocols, p.d > 64 * half ? p.d - 64 * half : 0u);
@@ -326,11 +327,11 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {
                 if ((uint32_t)i + 3 < ncol && vec) {
-                    *reinterpret_cast<float4*>(orow + i) = make_float4(o_acc[i] / l, o_acc[i + 1] / l, o_acc[i + 2] / l, o_acc[i + 3] / l);
+                    *reinterpret_cast<float4*>(orow + i) = make_float4(o_acc[i] * inv_l, o_acc[i + 1] * inv_l, o_acc[i + 2] * inv_l, o_acc[i + 3] * inv_l);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if ((uint32_t)(i + e) < ncol) orow[i + e] = o_acc[i + e] / l;
+                        if ((uint32_t)(i + e) < ncol) orow[i + e] = o_acc[i + e] * inv_l;
                 }
             }
         }
