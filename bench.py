@@ -357,6 +357,31 @@ def run_ours(args) -> int:
                       "roofline_frac": gbs / (hbm_peak * world), "bound": "hbm"})
     del logits, out
 
+    # ---- secondary: BASELINE config 3 (Q K^T, batch 8 x heads 32, seq 2048, head_dim 128, heads sharded over the
+    # ranks, no collective) and the same heads through the fused attention kernel (scores never leave the SM)
+    B3, H3, S3, D3 = 8, 32, 2048, 128
+    hsh = par.shard_range(B3 * H3, rank, world)
+    q3 = torch.randn(hsh.count * S3 * D3, device=dev)
+    k3 = torch.randn(hsh.count * S3 * D3, device=dev)
+    v3 = torch.randn(hsh.count * S3 * D3, device=dev)
+    kt3 = k3.view(hsh.count, S3, D3).transpose(1, 2).contiguous().view(-1)
+    c3 = torch.empty(hsh.count * S3 * S3, device=dev)
+    ms = timed(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(q3.data_ptr(), q3.numel(), kt3.data_ptr(), kt3.numel(),
+                                                                 c3.data_ptr(), 1, hsh.count, S3, D3, S3, st)), iters=10)
+    secondary.append({"metric": "batched_matmul_4d Q K^T 8x32x2048x128 TFLOP/s", "value": 2.0 * B3 * H3 * S3 * S3 * D3 / ms / 1e9,
+                      "ms": ms, "roofline_frac": 2.0 * B3 * H3 * S3 * S3 * D3 / ms / 1e9 / (tf32x3_peak * world), "bound": "tensor"})
+    del c3, kt3
+    o3 = torch.empty_like(q3)
+    for causal in (0, 1):
+        flop = 4.0 * B3 * H3 * S3 * S3 * D3 * (0.5 if causal else 1.0)
+        ms = timed(lambda: trn.check(L.trn_attention_f32_dev(q3.data_ptr(), q3.numel(), k3.data_ptr(), k3.numel(), v3.data_ptr(),
+                                                             v3.numel(), o3.data_ptr(), hsh.count, S3, D3, 1.0 / D3 ** 0.5, causal, st)),
+                   iters=10)
+        secondary.append({"metric": f"fused attention 256 heads x 2048 x 128{' causal' if causal else ''} TFLOP/s",
+                          "value": flop / ms / 1e9, "ms": ms, "roofline_frac": flop / ms / 1e9 / (tf32x3_peak * world),
+                          "bound": "tensor"})
+    del q3, k3, v3, o3
+
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

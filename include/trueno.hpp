@@ -301,6 +301,33 @@ public:
     }
 };
 
+// ---- fused attention: the counterpart of trueno-gpu's AttentionKernel (trueno-gpu/src/kernels/attention.rs:27-125) ----
+// AttentionKernel::new(seq_len, head_dim) [.with_causal()] [.with_scale(s)]; run(q, k, v, heads) with q/k/v laid out
+// [heads][seq_len][head_dim] returns softmax(scale * Q K^T [causal]) V per head.
+class AttentionKernel {
+    size_t seq_len_, head_dim_;
+    float scale_;
+    bool causal_ = false;
+
+public:
+    AttentionKernel(size_t seq_len, size_t head_dim)
+        : seq_len_(seq_len), head_dim_(head_dim), scale_(1.0f / std::sqrt(static_cast<float>(head_dim))) {}
+    AttentionKernel with_causal() const { AttentionKernel k = *this; k.causal_ = true; return k; }
+    AttentionKernel with_scale(float s) const { AttentionKernel k = *this; k.scale_ = s; return k; }
+    size_t seq_len() const { return seq_len_; }
+    size_t head_dim() const { return head_dim_; }
+    float scale() const { return scale_; }
+    bool causal() const { return causal_; }
+    Result<std::vector<float>> run(const std::vector<float>& q, const std::vector<float>& k, const std::vector<float>& v,
+                                   size_t heads) const {
+        std::vector<float> out(heads * seq_len_ * head_dim_);
+        const int st = trn_attention_f32(q.data(), q.size(), k.data(), k.size(), v.data(), v.size(), out.data(), heads, seq_len_,
+                                         head_dim_, scale_, causal_ ? 1 : 0);
+        if (st != TRN_OK) return detail::from_status(st);
+        return out;
+    }
+};
+
 // ---- device-buffer type: f32 storage resident in HBM (trn_buf_*) --------------------------------------------
 class DeviceBuffer {
     trn_buf* raw_ = nullptr;

@@ -139,6 +139,17 @@ impl CudaBackend {
         })?;
         Ok(c)
     }
+    /// Fused attention, the device counterpart of `trueno_gpu::kernels::AttentionKernel`
+    /// (trueno-gpu/src/kernels/attention.rs:27-125): q, k, v are `[heads][seq_len][head_dim]`.
+    pub fn attention(q: &[f32], k: &[f32], v: &[f32], heads: usize, seq_len: usize, head_dim: usize, scale: f32, causal: bool)
+        -> Result<Vec<f32>, TruenoError> {
+        let mut out = vec![0.0f32; heads * seq_len * head_dim];
+        check(unsafe {
+            sys::trn_attention_f32(q.as_ptr(), q.len(), k.as_ptr(), k.len(), v.as_ptr(), v.len(), out.as_mut_ptr(), heads, seq_len,
+                                   head_dim, scale, causal as i32)
+        })?;
+        Ok(out)
+    }
     pub fn matvec(a: &[f32], rows: usize, cols: usize, v: &[f32]) -> Result<Vec<f32>, TruenoError> {
         let mut y = vec![0.0f32; rows];
         check(unsafe { sys::trn_matvec_f32(a.as_ptr(), rows, cols, v.as_ptr(), v.len(), y.as_mut_ptr()) })?;

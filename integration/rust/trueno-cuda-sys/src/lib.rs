@@ -176,6 +176,12 @@ extern "C" {
                               out: *mut f32) -> c_int;
     pub fn trn_convolve2d_f32_dev(input: *const f32, rows: usize, cols: usize, kernel: *const f32, k_rows: usize, k_cols: usize,
                                   out: *mut f32, stream: *mut c_void) -> c_int;
+    // fused attention (trueno-gpu AttentionKernel): q, k, v, out are [heads][seq_len][head_dim]
+    pub fn trn_attention_f32(q: *const f32, q_len: usize, k: *const f32, k_len: usize, v: *const f32, v_len: usize, out: *mut f32,
+                             heads: usize, seq_len: usize, head_dim: usize, scale: f32, causal: c_int) -> c_int;
+    pub fn trn_attention_f32_dev(q: *const f32, q_len: usize, k: *const f32, k_len: usize, v: *const f32, v_len: usize,
+                                 out: *mut f32, heads: usize, seq_len: usize, head_dim: usize, scale: f32, causal: c_int,
+                                 stream: *mut c_void) -> c_int;
     // fused slice reduction + exchange over NVLink peer memory
     pub fn trn_comm_local_handle(handle64: *mut c_void) -> c_int;
     pub fn trn_comm_create(rank: c_int, world: c_int, handles: *const c_void, out: *mut *mut trn_comm) -> c_int;

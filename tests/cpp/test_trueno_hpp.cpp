@@ -52,6 +52,11 @@ static void validation_tests() {
     // src/matrix.rs:3912-3945 batched size checks
     auto bm = Matrix::batched_matmul(std::vector<float>(10, 1.f), std::vector<float>(12, 1.f), 2, 2, 3, 2);
     CHECK(bm.is_err() && bm.unwrap_err().message == "A data size mismatch: expected 12 (2\xC3\x97" "2\xC3\x97" "3), got 10");
+    // attention size checks (style of src/matrix.rs:481-502)
+    {
+        auto r = AttentionKernel(4, 8).run(std::vector<float>(50), std::vector<float>(64), std::vector<float>(64), 2);
+        CHECK(r.is_err() && r.unwrap_err().to_string().find("Q data size mismatch: expected 64") != std::string::npos);
+    }
     // src/matrix.rs:3715-3722 test_convolve2d_invalid_kernel
     CHECK(Matrix::from_vec(3, 3, std::vector<float>(9, 1.f)).unwrap().convolve2d(Matrix::from_vec(4, 4, std::vector<float>(16, 1.f)).unwrap())
               .unwrap_err() == TruenoError::invalid_input("Kernel size (4x4) larger than input (3x3)"));
@@ -131,6 +136,24 @@ static void device_tests() {
         auto img = Matrix::from_vec(3, 3, {1, 2, 3, 4, 5, 6, 7, 8, 9}).unwrap();
         auto res = img.convolve2d(Matrix::from_vec(1, 1, {1.0f}).unwrap()).unwrap();
         CHECK(res.rows() == 3 && res.cols() == 3 && res.as_slice() == img.as_slice());
+    }
+    // trueno-gpu/src/kernels/attention.rs:1172-1200: defaults (scale = 1/sqrt(head_dim), not causal), builders;
+    // zero queries weigh every key alike: out = mean of V, prefix means when causal
+    {
+        AttentionKernel att(5, 2);
+        CHECK(std::fabs(att.scale() - 1.0f / std::sqrt(2.0f)) < 1e-6f && !att.causal());
+        CHECK(att.with_causal().causal() && att.with_scale(0.5f).scale() == 0.5f);
+        std::vector<float> z(10, 0.0f), v(10);
+        for (int i = 0; i < 10; ++i) v[i] = (float)i;
+        auto o = att.run(z, z, v, 1).unwrap();
+        auto oc = att.with_causal().run(z, z, v, 1).unwrap();
+        bool ok = true;
+        for (int r = 0; r < 5; ++r)
+            for (int c = 0; c < 2; ++c) {
+                ok = ok && std::fabs(o[r * 2 + c] - (4.0f + c)) < 1e-5f;
+                ok = ok && std::fabs(oc[r * 2 + c] - ((float)r + c)) < 1e-5f;
+            }
+        CHECK(ok);
     }
     // src/backends/gpu/batch.rs:1120-1180 relu -> scale -> add in one batch
     CommandBatch batch;
