@@ -333,6 +333,18 @@ TRN_API int trn_attention_f32_dev(const float* q, size_t q_len, const float* k, 
                                   float* out, size_t heads, size_t seq_len, size_t head_dim, float scale, int causal,
                                   void* stream);
 
+/* SymmetricEigen::new (src/eigen.rs:108-141; GPU hook GpuBackend::symmetric_eigen src/backends/gpu/mod.rs:466; SURVEY.md
+ * 8f rank 4): eigendecomposition of a symmetric rows x cols matrix by Jacobi rotations with the reference's rotation
+ * formulas, threshold (1e-7 * max(||A||_F, 1)) and sweep limit (50); the device applies the n/2 disjoint rotations of a
+ * round-robin round at once.  eigenvalues[rows] come back in descending order, eigenvectors[rows*rows] row-major with
+ * the eigenvectors as COLUMNS in the same order (src/eigen.rs:183-203).  Errors (TRN_INVALID_INPUT, the reference's
+ * text): "Matrix must be square for eigendecomposition, got {}x{}", "Cannot compute eigendecomposition of empty
+ * matrix", "Jacobi algorithm failed to converge after 50 sweeps"; rows > 8192 is rejected.  The _dev variant takes
+ * and returns device pointers but synchronises the stream (the stopping rule is read back once per sweep). */
+TRN_API int trn_symmetric_eigen_f32(const float* a, size_t rows, size_t cols, float* eigenvalues, float* eigenvectors);
+TRN_API int trn_symmetric_eigen_f32_dev(const float* a, size_t rows, size_t cols, float* eigenvalues, float* eigenvectors,
+                                        void* stream);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

@@ -97,6 +97,8 @@ class Oracle:
         L.orc_scalar_map.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
         for name in ("scalar_sum_kahan", "scalar_norm_l1", "scalar_norm_linf"):
             f = getattr(L, "orc_" + name); f.restype = C.c_float; f.argtypes = [_f32p, C.c_size_t]
+        L.orc_symmetric_eigen.restype = C.c_int
+        L.orc_symmetric_eigen.argtypes = [_f32p, C.c_size_t, _f32p, _f32p]
         L.orc_convolve2d.restype = None
         L.orc_convolve2d.argtypes = [_f32p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t, C.c_size_t, _f32p]
         L.orc_vecmat.restype = None
@@ -194,6 +196,20 @@ class Oracle:
         out = np.empty((rows - kr + 1) * (cols - kc + 1), np.float32)
         self.lib.orc_convolve2d(_p(A), rows, cols, _p(K), kr, kc, _p(out))
         return out.reshape(rows - kr + 1, cols - kc + 1)
+
+    def symmetric_eigen(self, A, rows, cols):
+        """SymmetricEigen::new (src/eigen.rs:108-141) on the CPU Jacobi path (src/eigen.rs:143-221): returns
+        (eigenvalues descending, eigenvectors as the COLUMNS of a rows x rows matrix)."""
+        if rows != cols:
+            raise OracleError("InvalidInput", f"Matrix must be square for eigendecomposition, got {rows}x{cols}")
+        if rows == 0:
+            raise OracleError("InvalidInput", "Cannot compute eigendecomposition of empty matrix")
+        A = _f32(A)
+        vals = np.empty(rows, np.float32)
+        vecs = np.empty(rows * rows, np.float32)
+        if self.lib.orc_symmetric_eigen(_p(A), rows, _p(vals), _p(vecs)) != 0:
+            raise OracleError("InvalidInput", "Jacobi algorithm failed to converge after 50 sweeps")
+        return vals, vecs.reshape(rows, rows)
 
     def vecmat(self, v, A, rows, cols):
         v, A = _f32(v), _f32(A)

@@ -861,3 +861,77 @@ ORC_API void orc_convolve2d(const float* in, size_t rows, size_t cols, const flo
             out[r * ocols + c] = sum;
         }
 }
+
+/* src/eigen.rs:143-306 — SymmetricEigen::compute_jacobi: cyclic Jacobi, row-cyclic pair order, rotations applied one
+ * after the other (src/eigen.rs:248-306: tau, t, c, s by the Golub & Van Loan formulas; a_pp -= t*a_pq, a_qq += t*a_pq,
+ * a_pq = 0; columns p, q of A mirrored into rows; columns p, q of V), threshold CONVERGENCE_THRESHOLD (1e-7) *
+ * max(||A||_F, 1) (src/eigen.rs:150-151), at most MAX_JACOBI_SWEEPS = 50 sweeps; eigenvalues sorted descending with
+ * a stable sort and the eigenvector COLUMNS permuted alike (src/eigen.rs:183-203).
+ * Returns 0, or 2 when it does not converge ("Jacobi algorithm failed to converge after 50 sweeps"). */
+ORC_API int orc_symmetric_eigen(const float* matrix, size_t n, float* eigenvalues, float* eigenvectors) {
+    float* a = (float*)malloc(sizeof(float) * n * n);
+    float* v = (float*)calloc(n * n, sizeof(float));
+    size_t* idx = (size_t*)malloc(sizeof(size_t) * n);
+    memcpy(a, matrix, sizeof(float) * n * n);
+    float frob = 0.f;
+    for (size_t i = 0; i < n * n; ++i) { float sq = a[i] * a[i]; frob = frob + sq; }
+    float root = sqrtf(frob);
+    const float tolerance = 1e-7f * (root > 1.0f ? root : 1.0f);
+    for (size_t i = 0; i < n; ++i) v[i * n + i] = 1.0f;
+    int status = 2;
+    for (int sweep = 0; sweep < 50 && status != 0; ++sweep) {
+        int converged = 1;
+        for (size_t p = 0; p < n; ++p)
+            for (size_t q = p + 1; q < n; ++q) {
+                if (fabsf(a[p * n + q]) < tolerance) continue;
+                converged = 0;
+                const float app = a[p * n + p], aqq = a[q * n + q], apq = a[p * n + q];
+                if (fabsf(apq) < 1e-15f) continue;
+                const float two_apq = 2.0f * apq;
+                const float tau = (aqq - app) / two_apq;
+                float tt = tau * tau;
+                float root1 = sqrtf(1.0f + tt);
+                float t = tau >= 0.0f ? 1.0f / (tau + root1) : -1.0f / (-tau + root1);
+                float t2 = t * t;
+                const float c = 1.0f / sqrtf(1.0f + t2);
+                const float s = t * c;
+                float tapq = t * apq;
+                a[p * n + p] = app - tapq;
+                a[q * n + q] = aqq + tapq;
+                a[p * n + q] = 0.0f;
+                a[q * n + p] = 0.0f;
+                for (size_t k = 0; k < n; ++k) {
+                    if (k == p || k == q) continue;
+                    const float akp = a[k * n + p], akq = a[k * n + q];
+                    float x0 = c * akp, x1 = s * akq, y0 = s * akp, y1 = c * akq;
+                    a[k * n + p] = x0 - x1;
+                    a[p * n + k] = a[k * n + p];
+                    a[k * n + q] = y0 + y1;
+                    a[q * n + k] = a[k * n + q];
+                }
+                for (size_t k = 0; k < n; ++k) {
+                    const float vkp = v[k * n + p], vkq = v[k * n + q];
+                    float x0 = c * vkp, x1 = s * vkq, y0 = s * vkp, y1 = c * vkq;
+                    v[k * n + p] = x0 - x1;
+                    v[k * n + q] = y0 + y1;
+                }
+            }
+        if (converged) status = 0;
+    }
+    if (status == 0) {
+        /* stable descending sort of the diagonal (insertion sort == any stable sort) */
+        for (size_t i = 0; i < n; ++i) idx[i] = i;
+        for (size_t i = 1; i < n; ++i) {
+            size_t key = idx[i];
+            size_t j = i;
+            while (j > 0 && a[idx[j - 1] * n + idx[j - 1]] < a[key * n + key]) { idx[j] = idx[j - 1]; --j; }
+            idx[j] = key;
+        }
+        for (size_t c2 = 0; c2 < n; ++c2) {
+            eigenvalues[c2] = a[idx[c2] * n + idx[c2]];
+            for (size_t r = 0; r < n; ++r) eigenvectors[r * n + c2] = v[r * n + idx[c2]];
+        }
+    }
+    free(a); free(v); free(idx);
+    return status;
+}

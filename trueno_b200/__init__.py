@@ -103,6 +103,7 @@ _SIGNATURES = {
     "trn_convolve2d_f32": [_vp, _sz, _sz, _vp, _sz, _sz, _vp], "trn_convolve2d_f32_dev": [_vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp],
     "trn_attention_f32": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, C.c_float, C.c_int],
     "trn_attention_f32_dev": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, C.c_float, C.c_int, _vp],
+    "trn_symmetric_eigen_f32": [_vp, _sz, _sz, _vp, _vp], "trn_symmetric_eigen_f32_dev": [_vp, _sz, _sz, _vp, _vp, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }
@@ -480,6 +481,53 @@ class Matrix:
         out = np.empty(batch * heads * m * n, np.float32)
         check(lib.trn_batched_matmul_4d_f32(_ptr(a), a.size, _ptr(b), b.size, _ptr(out), batch, heads, m, k, n))
         return out
+
+
+class SymmetricEigen:
+    """Mirror of `SymmetricEigen` (src/eigen.rs:56-516): eigenvalues in descending order, eigenvectors as the columns
+    of a Matrix, computed by parallel Jacobi rotations on the device (`trn_symmetric_eigen_f32`)."""
+
+    def __init__(self, matrix: "Matrix"):
+        n = matrix.rows()
+        vals = np.empty(n if matrix.rows() == matrix.cols() else 0, np.float32)
+        vecs = np.empty(vals.size * vals.size, np.float32)
+        check(lib.trn_symmetric_eigen_f32(_ptr(matrix.data), matrix.rows(), matrix.cols(), _ptr(vals), _ptr(vecs)))
+        self._values = vals
+        self._vectors = Matrix(n, n, vecs)
+
+    @staticmethod
+    def new(matrix: "Matrix") -> "SymmetricEigen":
+        return SymmetricEigen(matrix)
+
+    def eigenvalues(self) -> np.ndarray:
+        return self._values
+
+    def eigenvectors(self) -> "Matrix":
+        return self._vectors
+
+    def __len__(self) -> int:
+        return int(self._values.size)
+
+    def is_empty(self) -> bool:
+        return self._values.size == 0
+
+    def eigenvector(self, i: int):
+        """src/eigen.rs:434: column i as a Vector, None when out of range."""
+        n = len(self)
+        if not 0 <= i < n:
+            return None
+        return Vector.from_slice(self._vectors.data.reshape(n, n)[:, i].copy())
+
+    def __iter__(self):
+        """src/eigen.rs:403: (eigenvalue, eigenvector) pairs in descending order."""
+        return ((float(self._values[i]), self.eigenvector(i)) for i in range(len(self)))
+
+    def reconstruct(self) -> "Matrix":
+        """src/eigen.rs:468: V * diag(lambda) * V^T on the device GEMM."""
+        n = len(self)
+        v = self._vectors.data.reshape(n, n)
+        scaled = Matrix(n, n, (v * self._values[None, :]).astype(np.float32).ravel())
+        return scaled.matmul(self._vectors.transpose())
 
 
 def attention(q, k, v, heads: int, seq_len: int, head_dim: int, scale: float | None = None, causal: bool = False) -> np.ndarray:

@@ -907,4 +907,32 @@ int trn_attention_f32(const float* q, size_t q_len, const float* k, size_t k_len
     return download(out, dout.p, n, c->stream);
 }
 
+// ---- SymmetricEigen (src/eigen.rs:108-141) ----------------------------------------------------------------------
+static int check_eigen(size_t rows, size_t cols) {
+    if (rows != cols) return fail(TRN_INVALID_INPUT, "Matrix must be square for eigendecomposition, got %zux%zu", rows, cols);
+    if (rows == 0) return fail(TRN_INVALID_INPUT, "Cannot compute eigendecomposition of empty matrix");
+    if (rows > eigen_max_n())
+        return fail(TRN_INVALID_INPUT, "matrix dimension %zu exceeds the supported maximum %zu", rows, eigen_max_n());
+    return TRN_OK;
+}
+int trn_symmetric_eigen_f32_dev(const float* a, size_t rows, size_t cols, float* eigenvalues, float* eigenvectors, void* stream) {
+    TRN_TRY(check_eigen(rows, cols));
+    TRN_TRY(need_ctx());
+    return launch_symmetric_eigen(a, rows, eigenvalues, eigenvectors, nullptr, resolve_stream(stream));
+}
+int trn_symmetric_eigen_f32(const float* a, size_t rows, size_t cols, float* eigenvalues, float* eigenvectors) {
+    TRN_TRY(check_eigen(rows, cols));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Context* c = ctx();
+    DevTemp da(c->stream), dvals(c->stream), dvecs(c->stream);
+    TRN_TRY(da.alloc(rows * rows));
+    TRN_TRY(dvals.alloc(rows));
+    TRN_TRY(dvecs.alloc(rows * rows));
+    TRN_TRY(upload(da.p, a, rows * rows, c->stream));
+    TRN_TRY(launch_symmetric_eigen(da.p, rows, dvals.p, dvecs.p, nullptr, c->stream));
+    TRN_TRY(download(eigenvalues, dvals.p, rows, c->stream));
+    return download(eigenvectors, dvecs.p, rows * rows, c->stream);
+}
+
 }  // extern "C"

@@ -110,6 +110,9 @@ int launch_convolve2d(const float* in, size_t rows, size_t cols, const float* ke
 int launch_attention(const float* q, const float* k, const float* v, float* out, size_t heads, size_t seq, size_t d,
                      float scale, int causal, int engine, cudaStream_t s);
 size_t attention_max_head_dim();
+// SymmetricEigen (eigen.cu): parallel Jacobi; values descending, vectors as columns; synchronises the stream
+int launch_symmetric_eigen(const float* a, size_t n, float* values, float* vectors, int* sweeps_out, cudaStream_t s);
+size_t eigen_max_n();
 int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, float* y, cudaStream_t s);
 int launch_vecmat(const float* x, const float* b, size_t k, size_t n, float* y, cudaStream_t s, bool skip_zero = true);
 int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta, float eps, float* out, size_t rows,
