@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cmath>
+#include <optional>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -298,6 +299,34 @@ public:
         const int st = trn_batched_matmul_4d_f32(a.data(), a.size(), b.data(), b.size(), c.data(), batch, heads, m, k, n);
         if (st != TRN_OK) return detail::from_status(st);
         return c;
+    }
+};
+
+// ---- SymmetricEigen (src/eigen.rs:56-516): eigenvalues descending, eigenvectors as the columns of a Matrix ----
+class SymmetricEigen {
+    std::vector<float> values_;
+    Matrix vectors_;
+    SymmetricEigen(std::vector<float> v, Matrix m) : values_(std::move(v)), vectors_(std::move(m)) {}
+
+public:
+    static Result<SymmetricEigen> create(const Matrix& m) {                                 // SymmetricEigen::new, src/eigen.rs:108
+        const size_t n = m.rows() == m.cols() ? m.rows() : 0;
+        std::vector<float> vals(n), vecs(n * n);
+        const int st = trn_symmetric_eigen_f32(m.as_slice().data(), m.rows(), m.cols(), vals.data(), vecs.data());
+        if (st != TRN_OK) return detail::from_status(st);
+        auto mat = Matrix::from_vec(n, n, std::move(vecs));
+        if (mat.is_err()) return mat.unwrap_err();
+        return SymmetricEigen(std::move(vals), mat.unwrap());
+    }
+    const std::vector<float>& eigenvalues() const { return values_; }                       // src/eigen.rs:363
+    const Matrix& eigenvectors() const { return vectors_; }                                 // src/eigen.rs:385
+    size_t len() const { return values_.size(); }
+    bool is_empty() const { return values_.empty(); }
+    std::optional<Vector> eigenvector(size_t i) const {                                     // src/eigen.rs:434
+        if (i >= len()) return std::nullopt;
+        std::vector<float> col(len());
+        for (size_t r = 0; r < len(); ++r) col[r] = vectors_.as_slice()[r * len() + i];
+        return Vector{std::move(col)};
     }
 };
 

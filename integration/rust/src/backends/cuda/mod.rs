@@ -139,6 +139,14 @@ impl CudaBackend {
         })?;
         Ok(c)
     }
+    /// `GpuBackend::symmetric_eigen` (src/backends/gpu/mod.rs:466) for `SymmetricEigen::compute_gpu` (src/eigen.rs:309):
+    /// returns (eigenvalues, eigenvectors as columns), already in descending order.
+    pub fn symmetric_eigen(matrix: &[f32], n: usize) -> Result<(Vec<f32>, Vec<f32>), TruenoError> {
+        let mut values = vec![0.0f32; n];
+        let mut vectors = vec![0.0f32; n * n];
+        check(unsafe { sys::trn_symmetric_eigen_f32(matrix.as_ptr(), n, n, values.as_mut_ptr(), vectors.as_mut_ptr()) })?;
+        Ok((values, vectors))
+    }
     /// Fused attention, the device counterpart of `trueno_gpu::kernels::AttentionKernel`
     /// (trueno-gpu/src/kernels/attention.rs:27-125): q, k, v are `[heads][seq_len][head_dim]`.
     pub fn attention(q: &[f32], k: &[f32], v: &[f32], heads: usize, seq_len: usize, head_dim: usize, scale: f32, causal: bool)

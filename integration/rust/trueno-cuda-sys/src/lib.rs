@@ -176,6 +176,10 @@ extern "C" {
                               out: *mut f32) -> c_int;
     pub fn trn_convolve2d_f32_dev(input: *const f32, rows: usize, cols: usize, kernel: *const f32, k_rows: usize, k_cols: usize,
                                   out: *mut f32, stream: *mut c_void) -> c_int;
+    // SymmetricEigen (src/eigen.rs:108): eigenvalues descending, eigenvectors as columns
+    pub fn trn_symmetric_eigen_f32(a: *const f32, rows: usize, cols: usize, eigenvalues: *mut f32, eigenvectors: *mut f32) -> c_int;
+    pub fn trn_symmetric_eigen_f32_dev(a: *const f32, rows: usize, cols: usize, eigenvalues: *mut f32, eigenvectors: *mut f32,
+                                       stream: *mut c_void) -> c_int;
     // fused attention (trueno-gpu AttentionKernel): q, k, v, out are [heads][seq_len][head_dim]
     pub fn trn_attention_f32(q: *const f32, q_len: usize, k: *const f32, k_len: usize, v: *const f32, v_len: usize, out: *mut f32,
                              heads: usize, seq_len: usize, head_dim: usize, scale: f32, causal: c_int) -> c_int;

@@ -173,6 +173,26 @@ def main():
             med, best = timeit(unfused, iters=5)
             print(f"   unfused (bmm -> scale -> softmax -> bmm, K^T given) median {med:.3f} ms  {4.0 * H * seq * seq * d / med / 1e9:.1f} TFLOP/s")
 
+    if "eigen" in which:
+        import time
+        import numpy as np
+        for n in (64, 256, 1024, 2048, 4096):
+            rng = np.random.default_rng(n)
+            x = rng.standard_normal((n, n)).astype(np.float32)
+            m = torch.from_numpy(((x + x.T) / 2).astype(np.float32)).cuda()
+            vals = torch.empty(n, device="cuda"); vecs = torch.empty(n * n, device="cuda")
+            fn = lambda: trn.check(L.trn_symmetric_eigen_f32_dev(m.data_ptr(), n, n, vals.data_ptr(), vecs.data_ptr(), st))
+            fn(); torch.cuda.synchronize()
+            l0 = trn.launch_count() if hasattr(trn, "launch_count") else 0
+            t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            l1 = trn.launch_count() if hasattr(trn, "launch_count") else 0
+            t1 = time.perf_counter(); w = torch.linalg.eigvalsh(m.double()); torch.cuda.synchronize(); dt_t = time.perf_counter() - t1
+            t1 = time.perf_counter(); w32, v32 = torch.linalg.eigh(m); torch.cuda.synchronize(); dt_t32 = time.perf_counter() - t1
+            err = float((vals.double().flip(0) - w).abs().max() / m.double().norm())
+            rounds = (l1 - l0) / 2 / max(1, n - 1 + n % 2)
+            print(f"symmetric_eigen n={n}: {dt * 1e3:.1f} ms  (~{rounds:.1f} sweeps, {l1 - l0} launches)  max eigenvalue error {err:.2e} * ||A||_F   "
+                  f"torch eigh f32 (cuSOLVER) {dt_t32 * 1e3:.1f} ms")
+
     if "rowblock" in which:
         # BASELINE config 5b: one GPU's share of the 32768^3 product at 8 GPUs (A-block 4096 x 32768, full B)
         n, mb = 32768, 4096

@@ -52,6 +52,11 @@ static void validation_tests() {
     // src/matrix.rs:3912-3945 batched size checks
     auto bm = Matrix::batched_matmul(std::vector<float>(10, 1.f), std::vector<float>(12, 1.f), 2, 2, 3, 2);
     CHECK(bm.is_err() && bm.unwrap_err().message == "A data size mismatch: expected 12 (2\xC3\x97" "2\xC3\x97" "3), got 10");
+    // src/eigen.rs:672-690 non-square and empty inputs
+    {
+        auto r = SymmetricEigen::create(Matrix::from_vec(2, 3, {1, 2, 3, 4, 5, 6}).unwrap());
+        CHECK(r.is_err() && r.unwrap_err().to_string().find("Matrix must be square for eigendecomposition, got 2x3") != std::string::npos);
+    }
     // attention size checks (style of src/matrix.rs:481-502)
     {
         auto r = AttentionKernel(4, 8).run(std::vector<float>(50), std::vector<float>(64), std::vector<float>(64), 2);
@@ -136,6 +141,14 @@ static void device_tests() {
         auto img = Matrix::from_vec(3, 3, {1, 2, 3, 4, 5, 6, 7, 8, 9}).unwrap();
         auto res = img.convolve2d(Matrix::from_vec(1, 1, {1.0f}).unwrap()).unwrap();
         CHECK(res.rows() == 3 && res.cols() == 3 && res.as_slice() == img.as_slice());
+    }
+    // src/eigen.rs:527-551 [[2,1],[1,2]] -> 3, 1; :754-769 [[0,1],[1,0]] -> 1, -1; :726-735 eigenvector accessor
+    {
+        auto e = SymmetricEigen::create(Matrix::from_vec(2, 2, {2, 1, 1, 2}).unwrap()).unwrap();
+        CHECK(e.len() == 2 && std::fabs(e.eigenvalues()[0] - 3.0f) < 1e-5f && std::fabs(e.eigenvalues()[1] - 1.0f) < 1e-5f);
+        auto e2 = SymmetricEigen::create(Matrix::from_vec(2, 2, {0, 1, 1, 0}).unwrap()).unwrap();
+        CHECK(std::fabs(e2.eigenvalues()[0] - 1.0f) < 1e-5f && std::fabs(e2.eigenvalues()[1] + 1.0f) < 1e-5f);
+        CHECK(e.eigenvector(0).has_value() && e.eigenvector(0)->len() == 2 && !e.eigenvector(10).has_value());
     }
     // trueno-gpu/src/kernels/attention.rs:1172-1200: defaults (scale = 1/sqrt(head_dim), not causal), builders;
     // zero queries weigh every key alike: out = mean of V, prefix means when causal
