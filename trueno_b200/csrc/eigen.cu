@@ -11,11 +11,13 @@
 // parity tests state the tolerance (tests/test_eigen_gpu.py).
 //
 // One round = A' = J^T A J for the block-diagonal J of that round's rotations, and V' = V J:
-//   jacobi_params_kernel   one thread per pair: (c, s, t) from the current A; per COLUMN j it leaves (partner, c_j,
-//                          ss_j) with ss_j = -s for the first index of a pair, +s for the second, so that a rotated
-//                          column is c_j * col_j + ss_j * col_partner for both roles
-//   jacobi_apply_kernel    one CTA per pair: rows p and q of A staged in shared memory (coalesced), every new element
-//                          of rows p and q from the four old ones it depends on,
+//   jacobi_round_kernel    ONE launch per round, one CTA per pair.  A round's rotations depend on A only through its
+//                          diagonal and one off-diagonal element per pair; every CTA leaves those of its two rows
+//                          for the NEXT round's pairing and the last CTA to finish (ticket) turns them into that
+//                          round's per-COLUMN parameters (c_j, ss_j), ss_j = -s for the first index of a pair, +s
+//                          for the second, so a rotated column is c_j * col_j + ss_j * col_partner in both roles.
+//                          Rows p and q of A are staged in shared memory (coalesced), every new element
+//                          of rows p and q comes from the four old ones it depends on,
 //                              A'[i][j] = c2 * (c1 * a00 + ss1 * a10) + ss2 * (c1 * a01 + ss1 * a11),
 //                          always evaluated with the SMALLER index as "1" — the transposed element is computed by
 //                          another CTA from the same four numbers (A is symmetric) in the same order, so A stays
@@ -34,14 +36,8 @@ namespace eig {
 
 constexpr int kThreads = 256;
 
-struct ColParam {      // how column (and, by symmetry, row) j is rotated this round
-    float c, ss;       // new_j = c * old_j + ss * old_partner
-    uint32_t partner;  // == j when j sits out (odd n) — then c = 1, ss = 0
-    float tdelta;      // t * a_pq of j's pair: a_pp -= tdelta, a_qq += tdelta
-    uint32_t rotated;  // 0: the pair was skipped (|a_pq| under the threshold) or j sits out
-};
-
-// round-robin ("circle") schedule over m = n rounded up to even players: pair 0 = (m - 1, r), pair i = (r + i, r - i)
+// round-robin ("circle") schedule over m = n rounded up to even players, round r in [0, m - 1):
+// pair 0 = (m - 1, r), pair i = (r + i, r - i) mod (m - 1); so the partner of index i is a closed form
 __device__ __forceinline__ void round_pair(uint32_t m, uint32_t r, uint32_t i, uint32_t& p, uint32_t& q) {
     uint32_t a, b;
     if (i == 0) { a = m - 1; b = r; }
@@ -49,34 +45,24 @@ __device__ __forceinline__ void round_pair(uint32_t m, uint32_t r, uint32_t i, u
     p = min(a, b);
     q = max(a, b);
 }
+__device__ __forceinline__ uint32_t partner_of(uint32_t m, uint32_t r, uint32_t i) {
+    if (i == m - 1) return r;
+    if (i == r) return m - 1;
+    return (2 * r + (m - 1) - i) % (m - 1);
+}
 
-__global__ void jacobi_params_kernel(const float* __restrict__ a, uint32_t n, uint32_t m, uint32_t round, float tol,
-                                     ColParam* __restrict__ prm, unsigned* __restrict__ rotations) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m / 2) return;
-    uint32_t p, q;
-    round_pair(m, round, i, p, q);
-    if (q >= n) {   // p's partner is the padding player: p sits out
-        if (p < n) prm[p] = ColParam{1.0f, 0.0f, p, 0.0f, 0u};
-        return;
-    }
-    const float app = a[(size_t)p * n + p], aqq = a[(size_t)q * n + q], apq = a[(size_t)p * n + q];
-    float c = 1.0f, s = 0.0f, td = 0.0f;
-    if (!(fabsf(apq) < tol) && !(fabsf(apq) < 1e-15f)) {   // src/eigen.rs:166, :262
-        const float tau = __fdiv_rn(__fsub_rn(aqq, app), __fmul_rn(2.0f, apq));
-        const float root = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(tau, tau)));
-        const float t = tau >= 0.0f ? __fdiv_rn(1.0f, __fadd_rn(tau, root)) : __fdiv_rn(-1.0f, __fadd_rn(-tau, root));
-        c = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(t, t))));
-        s = __fmul_rn(t, c);
-        td = __fmul_rn(t, apq);
-        atomicAdd(rotations, 1u);
-        prm[p] = ColParam{c, -s, q, td, 1u};
-        prm[q] = ColParam{c, s, p, td, 1u};
-    } else {
-        // skipped pair: identity rotation, the pair's 2x2 block stays as it is
-        prm[p] = ColParam{1.0f, 0.0f, q, 0.0f, 0u};
-        prm[q] = ColParam{1.0f, 0.0f, p, 0.0f, 0u};
-    }
+// One rotation with the reference's expressions (src/eigen.rs:262-279); false when the pair is skipped
+// (|a_pq| under the threshold, src/eigen.rs:166, or under 1e-15, :262)
+__device__ __forceinline__ bool rotation(float app, float aqq, float apq, float tol, float& c, float& s, float& td) {
+    c = 1.0f; s = 0.0f; td = 0.0f;
+    if (fabsf(apq) < tol || fabsf(apq) < 1e-15f) return false;
+    const float tau = __fdiv_rn(__fsub_rn(aqq, app), __fmul_rn(2.0f, apq));
+    const float root = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(tau, tau)));
+    const float t = tau >= 0.0f ? __fdiv_rn(1.0f, __fadd_rn(tau, root)) : __fdiv_rn(-1.0f, __fadd_rn(-tau, root));
+    c = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(t, t))));
+    s = __fmul_rn(t, c);
+    td = __fmul_rn(t, apq);
+    return true;
 }
 
 // c2 * (c1 * a00 + ss1 * a10) + ss2 * (c1 * a01 + ss1 * a11), every operation rounded on its own (no contraction):
@@ -87,74 +73,126 @@ __device__ __forceinline__ float rot2(float c1, float ss1, float c2, float ss2, 
     return __fadd_rn(__fmul_rn(c2, u), __fmul_rn(ss2, w));
 }
 
+struct ColParam {      // how column (and, by symmetry, row) j is rotated in a round: new_j = c * old_j + ss * old_partner
+    float c, ss;       // ss = -s for the first index of a pair, +s for the second; (1, 0) when j's pair is skipped / j sits out
+    float tdelta;      // t * a_pq of j's pair: a_pp -= tdelta, a_qq += tdelta
+    uint32_t rotated;
+};
+
+// (c, ss) of every column for `round`, from the diagonal and offd[i] = A[i][partner(i, round)]; one thread per pair
+__device__ __forceinline__ void pair_params(const volatile float* diag, const volatile float* offd, uint32_t n, uint32_t m,
+                                            uint32_t round, uint32_t i, float tol, ColParam* __restrict__ prm) {
+    uint32_t p, q;
+    round_pair(m, round, i, p, q);
+    if (p >= n) return;
+    if (q >= n) { prm[p] = ColParam{1.0f, 0.0f, 0.0f, 0u}; return; }   // p sits out this round
+    float c, s, td;
+    const bool rot = rotation(diag[p], diag[q], offd[p], tol, c, s, td);
+    prm[p] = ColParam{c, -s, td, rot ? 1u : 0u};
+    prm[q] = ColParam{c, s, td, rot ? 1u : 0u};
+}
+
+__global__ void jacobi_first_params_kernel(const float* diag, const float* offd, uint32_t n, uint32_t m, float tol, ColParam* prm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m / 2) pair_params(diag, offd, n, m, 0, i, tol, prm);
+}
+
+// One round, ONE launch, one CTA per pair.  The rotations of a round depend on A only through its diagonal and one
+// off-diagonal element per pair; every CTA leaves those of its two rows for the NEXT round's pairing (diag, offd[i] =
+// A'[i][partner(i, next round)]), and the last CTA to finish (ticket) turns them into the next round's per-column
+// parameters — so there is no separate parameter launch and no grid-wide wait inside the round.
 __global__ void __launch_bounds__(kThreads)
-jacobi_apply_kernel(const float* __restrict__ a_in, float* __restrict__ a_out, float* __restrict__ vt, uint32_t n, uint32_t m,
-                    uint32_t round, const ColParam* __restrict__ prm) {
-    extern __shared__ float rows[];   // [2][n]: row p, row q of the old A
+jacobi_round_kernel(const float* __restrict__ a_in, float* __restrict__ a_out, float* __restrict__ vt,
+                    const ColParam* __restrict__ prm_in, ColParam* __restrict__ prm_out, float* diag, float* offd,
+                    unsigned* __restrict__ ticket, uint32_t n, uint32_t m, uint32_t round, float tol,
+                    unsigned* __restrict__ rotations) {
+    extern __shared__ float smem[];   // row p [n], row q [n] of the old A
+    __shared__ bool s_last;
+    float* row_p = smem;
+    float* row_q = smem + n;
     uint32_t p, q;
     round_pair(m, round, blockIdx.x, p, q);
-    if (p >= n) return;
-    const bool alone = q >= n;
-    float* row_p = rows;
-    float* row_q = rows + n;
-    for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
-        row_p[j] = a_in[(size_t)p * n + j];
-        row_q[j] = alone ? 0.0f : a_in[(size_t)q * n + j];
-    }
-    __syncthreads();
-    const ColParam pp = prm[p];
-    const ColParam pq = alone ? ColParam{1.0f, 0.0f, p, 0.0f, 0u} : prm[q];
-    const bool rotated = pp.rotated != 0u;
-    for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
-        const ColParam pj = prm[j];
-        float new_p, new_q;
-        if (!alone && (j == p || j == q)) {
-            // the pair's own 2x2 block (src/eigen.rs:283-287); untouched when the pair was skipped
-            if (rotated) {
-                new_p = j == p ? __fsub_rn(row_p[p], pp.tdelta) : 0.0f;
-                new_q = j == q ? __fadd_rn(row_q[q], pp.tdelta) : 0.0f;
+    const uint32_t next_round = round + 1 == m - 1 ? 0 : round + 1;
+    if (p < n) {
+        const bool alone = q >= n;
+        for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
+            row_p[j] = a_in[(size_t)p * n + j];
+            row_q[j] = alone ? 0.0f : a_in[(size_t)q * n + j];
+        }
+        __syncthreads();
+        const ColParam pp = prm_in[p];
+        const ColParam pq = alone ? ColParam{1.0f, 0.0f, 0.0f, 0u} : prm_in[q];
+        const bool rotated = !alone && pp.rotated != 0u;
+        if (rotated && threadIdx.x == 0) atomicAdd(rotations, 1u);
+        const uint32_t next_p = partner_of(m, next_round, p), next_q = alone ? 0xFFFFFFFFu : partner_of(m, next_round, q);
+        for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
+            float new_p, new_q = 0.0f;
+            if (!alone && (j == p || j == q)) {
+                // the pair's own 2x2 block (src/eigen.rs:283-287); untouched when the pair was skipped
+                if (rotated) {
+                    new_p = j == p ? __fsub_rn(row_p[p], pp.tdelta) : 0.0f;
+                    new_q = j == q ? __fadd_rn(row_q[q], pp.tdelta) : 0.0f;
+                } else {
+                    new_p = row_p[j];
+                    new_q = row_q[j];
+                }
             } else {
-                new_p = row_p[j];
-                new_q = row_q[j];
+                const ColParam pj = prm_in[j];
+                const uint32_t jpart = partner_of(m, round, j);
+                const uint32_t jq = jpart < n ? jpart : j;    // j sits out: its "partner" column is itself (c = 1, ss = 0)
+                // row i of the pair against column j: "first" = the smaller of (i, j); old elements of rows i, partner(i)
+                if (p < j) new_p = rot2(pp.c, pp.ss, pj.c, pj.ss, row_p[j], row_q[j], row_p[jq], row_q[jq]);
+                else       new_p = rot2(pj.c, pj.ss, pp.c, pp.ss, row_p[j], row_p[jq], row_q[j], row_q[jq]);
+                if (!alone) {
+                    if (q < j) new_q = rot2(pq.c, pq.ss, pj.c, pj.ss, row_q[j], row_p[j], row_q[jq], row_p[jq]);
+                    else       new_q = rot2(pj.c, pj.ss, pq.c, pq.ss, row_q[j], row_q[jq], row_p[j], row_p[jq]);
+                }
             }
-        } else {
-            const uint32_t jp = pj.partner;
-            // row i of the pair against column j: "first" = the smaller of (i, j); old elements of rows i and partner(i)
-            // row p: partner row is q
-            if (p < j) new_p = rot2(pp.c, pp.ss, pj.c, pj.ss, row_p[j], row_q[j], row_p[jp], row_q[jp]);
-            else       new_p = rot2(pj.c, pj.ss, pp.c, pp.ss, row_p[j], row_p[jp], row_q[j], row_q[jp]);
+            a_out[(size_t)p * n + j] = new_p;
+            if (j == p) diag[p] = new_p;
+            if (j == next_p) offd[p] = new_p;
             if (!alone) {
-                // row q: partner row is p
-                if (q < j) new_q = rot2(pq.c, pq.ss, pj.c, pj.ss, row_q[j], row_p[j], row_q[jp], row_p[jp]);
-                else       new_q = rot2(pj.c, pj.ss, pq.c, pq.ss, row_q[j], row_q[jp], row_p[j], row_p[jp]);
-            } else {
-                new_q = 0.0f;
+                a_out[(size_t)q * n + j] = new_q;
+                if (j == q) diag[q] = new_q;
+                if (j == next_q) offd[q] = new_q;
             }
         }
-        a_out[(size_t)p * n + j] = new_p;
-        if (!alone) a_out[(size_t)q * n + j] = new_q;
-    }
-    // eigenvectors: columns p, q of V = rows p, q of V^T (src/eigen.rs:299-305)
-    if (!alone && rotated) {
-        const float c = pp.c, s = pq.ss;
-        float* vp = vt + (size_t)p * n;
-        float* vq = vt + (size_t)q * n;
-        for (uint32_t k = threadIdx.x; k < n; k += kThreads) {
-            const float x = vp[k], y = vq[k];
-            vp[k] = __fsub_rn(__fmul_rn(c, x), __fmul_rn(s, y));
-            vq[k] = __fadd_rn(__fmul_rn(s, x), __fmul_rn(c, y));
+        // eigenvectors: columns p, q of V = rows p, q of V^T (src/eigen.rs:299-305)
+        if (rotated) {
+            const float c = pp.c, sn = pq.ss;
+            float* vp = vt + (size_t)p * n;
+            float* vq = vt + (size_t)q * n;
+            for (uint32_t k = threadIdx.x; k < n; k += kThreads) {
+                const float x = vp[k], y = vq[k];
+                vp[k] = __fsub_rn(__fmul_rn(c, x), __fmul_rn(sn, y));
+                vq[k] = __fadd_rn(__fmul_rn(sn, x), __fmul_rn(c, y));
+            }
         }
+    }
+    // last CTA of the round: the next round's parameters
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (uint32_t i = threadIdx.x; i < m / 2; i += kThreads) pair_params(diag, offd, n, m, next_round, i, tol, prm_out);
+        if (threadIdx.x == 0) *ticket = 0;
     }
 }
 
 // working copy of A read through its UPPER triangle (the rotation decisions of src/eigen.rs:165 read a[i][j], i < j),
 // so the copy is exactly symmetric whatever the caller's lower triangle holds; V^T = I
-__global__ void init_kernel(const float* __restrict__ a, float* __restrict__ a0, float* __restrict__ vt, uint32_t n) {
+__global__ void init_kernel(const float* __restrict__ a, float* __restrict__ a0, float* __restrict__ vt, float* __restrict__ diag,
+                            float* __restrict__ offd, uint32_t n, uint32_t m) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)n * n) return;
     const uint32_t r = (uint32_t)(i / n), c = (uint32_t)(i % n);
-    a0[i] = r <= c ? a[i] : a[(size_t)c * n + r];
+    const float v = r <= c ? a[i] : a[(size_t)c * n + r];
+    a0[i] = v;
     vt[i] = r == c ? 1.0f : 0.0f;
+    if (r == c) diag[r] = v;
+    if (c == partner_of(m, 0, r)) offd[r] = v;   // what round 0 needs
 }
 
 __global__ void diagonal_kernel(const float* __restrict__ a, uint32_t n, float* __restrict__ diag) {
@@ -197,20 +235,24 @@ int launch_symmetric_eigen(const float* a, size_t n_, float* values, float* vect
     const uint32_t m = (n + 1) & ~1u;
     const size_t nn = (size_t)n * n;
     float* scratch = nullptr;
-    // A ping, A pong, V^T, diag[n], norm slot, params[n], order[n], rotation counter
-    const size_t floats = 3 * nn + n + 4;
-    const size_t bytes = floats * sizeof(float) + (size_t)n * sizeof(ColParam) + (size_t)n * sizeof(uint32_t) + 64;
+    // A ping, A pong, V^T, diag, offd, sorted-diag scratch, norm slot, params x2, order[n], rotation counter, ticket
+    const size_t floats = 3 * nn + 3 * (size_t)n + 4;
+    const size_t bytes = floats * sizeof(float) + 2 * (size_t)n * sizeof(ColParam) + (size_t)n * sizeof(uint32_t) + 64;
     TRN_TRY(scratch_alloc((void**)&scratch, bytes, s));
     float* a0 = scratch;
     float* a1 = a0 + nn;
     float* vt = a1 + nn;
-    float* diag = vt + nn;
+    float* dg = vt + nn;
+    float* od = dg + n;
+    float* diag = od + n;
     float* norm_slot = diag + n;
-    ColParam* prm = reinterpret_cast<ColParam*>(norm_slot + 4);
-    uint32_t* order = reinterpret_cast<uint32_t*>(prm + n);
+    ColParam* prm[2] = {reinterpret_cast<ColParam*>(norm_slot + 4), reinterpret_cast<ColParam*>(norm_slot + 4) + n};
+    uint32_t* order = reinterpret_cast<uint32_t*>(prm[1] + n);
     unsigned* counter = reinterpret_cast<unsigned*>(order + n);
+    unsigned* ticket = counter + 1;
     auto run = [&]() -> int {
-        init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(a, a0, vt, n);
+        TRN_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned), s));
+        init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(a, a0, vt, dg, od, n, m);
         count_launch();
         // tolerance = 1e-7 * max(||A||_F, 1)   (src/eigen.rs:150-151)
         TRN_TRY(launch_reduce(Reduce::NormL2, a0, nullptr, nn, norm_slot, s));
@@ -218,21 +260,23 @@ int launch_symmetric_eigen(const float* a, size_t n_, float* values, float* vect
         TRN_CUDA(cudaMemcpyAsync(&frob, norm_slot, sizeof(float), cudaMemcpyDeviceToHost, s));
         TRN_CUDA(cudaStreamSynchronize(s));
         const float tol = 1e-7f * (frob > 1.0f ? frob : 1.0f);
+        jacobi_first_params_kernel<<<(m / 2 + 127) / 128, 128, 0, s>>>(dg, od, n, m, tol, prm[0]);
+        count_launch();
         const size_t smem = 2 * (size_t)n * sizeof(float);
         if (smem > 48 * 1024) {
-            static const cudaError_t optin = cudaFuncSetAttribute(jacobi_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            static const cudaError_t optin = cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             TRN_CUDA(optin);
         }
         float* cur = a0;
         float* nxt = a1;
+        unsigned g = 0;   // rounds done: the parameter vectors ping-pong with it
         bool converged = n == 1;
         int sweep = 0;
         for (; sweep < 50 && !converged; ++sweep) {   // MAX_JACOBI_SWEEPS (src/eigen.rs:37)
             TRN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), s));
-            for (uint32_t r = 0; r + 1 < m; ++r) {
-                jacobi_params_kernel<<<(m / 2 + 127) / 128, 128, 0, s>>>(cur, n, m, r, tol, prm, counter);
-                jacobi_apply_kernel<<<m / 2, kThreads, smem, s>>>(cur, nxt, vt, n, m, r, prm);
-                count_launch();
+            for (uint32_t r = 0; r + 1 < m; ++r, ++g) {
+                jacobi_round_kernel<<<m / 2, kThreads, smem, s>>>(cur, nxt, vt, prm[g & 1], prm[(g + 1) & 1], dg, od, ticket, n, m, r,
+                                                                 tol, counter);
                 count_launch();
                 std::swap(cur, nxt);
             }
