@@ -7,7 +7,8 @@
 // batched_matmul_4d(P, V).  The seq x seq score matrix never exists in HBM.
 //
 // attention_tf32x3_kernel (head_dim <= 128): one CTA per (head, 128 query rows), 320 threads:
-//   warp 0   TMA producer: 6 x 32 KiB ring of 16-wide k-blocks of the pre-split (hi, lo) operands
+//   warp 0   TMA producer: the query tile (hi, lo) once, resident in shared memory; then a ring of 16 KiB stages
+//            (5 at head_dim 128, up to 12 below) of 16-wide k-blocks of the pre-split K and V^T (hi, lo)
 //   warp 1   MMA issuer (one elected lane), tcgen05.mma kind::tf32, 3xTF32 (lo*hi + hi*lo + hi*hi):
 //              S  = Q K_j^T        A, B from shared memory            -> TMEM columns [0,128)
 //              O' = P_j V_j        A = P (hi, lo) from TENSOR MEMORY  -> TMEM columns [384,512)
@@ -37,14 +38,23 @@ using namespace tc;
 constexpr int BQ = 128;        // query rows per CTA (UMMA M)
 constexpr int BKV = 128;       // keys per tile (UMMA N of S, K extent of one TMEM partial of O)
 constexpr int SBK = 16;        // floats of K per ring stage (SWIZZLE_64B rows)
-constexpr int kStages = 6;
+constexpr int kMaxStages = 12;
 constexpr uint32_t kTile = 128 * SBK * 4;            // 8 KiB: 128 rows x 64 B
-constexpr uint32_t kStageBytes = 4 * kTile;          // S phase: Q_hi, K_hi, Q_lo, K_lo; PV phase: V_hi, -, V_lo, -
+constexpr uint32_t kStageBytes = 2 * kTile;          // S phase: K_hi, K_lo; PV phase: V_hi, V_lo
+constexpr uint32_t kQBlockBytes = 2 * kTile;         // one resident k-block of the query tile: Q_hi, Q_lo
 constexpr int kThreads = 320;
 constexpr int kSoftmaxWarps = 8;
 constexpr uint32_t kColS = 0, kColPhi = 128, kColPlo = 256, kColO = 384, kTmemCols = 512;
 constexpr uint32_t kXchgBytes = 3 * 2 * 128 * 4;     // [buffer][half][row]
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + kXchgBytes + 256 + 1024;
+constexpr uint32_t kSmemBudget = 227 * 1024;
+constexpr uint32_t kFixedBytes = kXchgBytes + 256 + 1024;   // exchange area, barriers, 1 KiB alignment slack
+__host__ __device__ constexpr uint32_t ring_stages(uint32_t num_kb_s) {   // what is left after the resident Q tile
+    const uint32_t n = (kSmemBudget - kFixedBytes - num_kb_s * kQBlockBytes) / kStageBytes;
+    return n < (uint32_t)kMaxStages ? n : (uint32_t)kMaxStages;
+}
+__host__ __device__ constexpr uint32_t smem_bytes(uint32_t num_kb_s) {
+    return num_kb_s * kQBlockBytes + ring_stages(num_kb_s) * kStageBytes + kFixedBytes;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -76,14 +86,18 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    float* xchg = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * kStageBytes + kXchgBytes);
+    // [Q tile: num_kb_s x (hi 8 KiB, lo 8 KiB), resident] [ring: kStages x (hi 8 KiB, lo 8 KiB)] [exchange] [barriers]
+    const uint32_t kStages = ring_stages(p.num_kb_s);
+    const uint32_t q_bytes = p.num_kb_s * kQBlockBytes;
+    const uint32_t ring_base = smem_base + q_bytes;
+    float* xchg = reinterpret_cast<float*>(smem_gen + q_bytes + kStages * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + q_bytes + kStages * kStageBytes + kXchgBytes);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    const uint32_t s_full = bar_base + 8u * (2 * kStages), s_free = s_full + 8, p_full = s_full + 16,
-                   o_full = s_full + 24, o_free = s_full + 32;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    const uint32_t s_full = bar_base + 8u * (2 * kMaxStages), s_free = s_full + 8, p_full = s_full + 16,
+                   o_full = s_full + 24, o_free = s_full + 32, q_full = s_full + 40;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -96,7 +110,8 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q_hi); tma_prefetch_desc(&map_k_hi); tma_prefetch_desc(&map_v_hi);
         tma_prefetch_desc(&map_q_lo); tma_prefetch_desc(&map_k_lo); tma_prefetch_desc(&map_v_lo);
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(q_full, 1);
         mbar_init(s_full, 1);
         mbar_init(s_free, kSoftmaxWarps);
         mbar_init(p_full, kSoftmaxWarps);
@@ -113,19 +128,23 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
     if (warp == 0) {
         // ===================== TMA producer: the MMA warp's order S_0, S_1, PV_0, S_2, PV_1, ... =====================
         if (elect_one()) {
+            // the query tile, once: every k-block of Q_hi and Q_lo stays in shared memory for all key tiles
+            mbar_expect_tx(q_full, q_bytes);
+            for (uint32_t kb = 0; kb < p.num_kb_s; ++kb) {
+                tma_load_3d(smem_base + kb * kQBlockBytes, &map_q_hi, q_full, (int)(kb * SBK), (int)q0, (int)head);
+                tma_load_3d(smem_base + kb * kQBlockBytes + kTile, &map_q_lo, q_full, (int)(kb * SBK), (int)q0, (int)head);
+            }
             uint32_t stage = 0, phase = 0;
             for (uint32_t step = 0; step <= kv_tiles; ++step) {
                 if (step < kv_tiles) {
                     const int key0 = (int)(step * BKV);
                     for (uint32_t kb = 0; kb < p.num_kb_s; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        mbar_expect_tx(full_bar(stage), 4 * kTile);
+                        const uint32_t sa = ring_base + stage * kStageBytes;
+                        mbar_expect_tx(full_bar(stage), 2 * kTile);
                         const int k0 = (int)(kb * SBK);
-                        tma_load_3d(sa, &map_q_hi, full_bar(stage), k0, (int)q0, (int)head);
-                        tma_load_3d(sa + kTile, &map_k_hi, full_bar(stage), k0, key0, (int)head);
-                        tma_load_3d(sa + 2 * kTile, &map_q_lo, full_bar(stage), k0, (int)q0, (int)head);
-                        tma_load_3d(sa + 3 * kTile, &map_k_lo, full_bar(stage), k0, key0, (int)head);
+                        tma_load_3d(sa, &map_k_hi, full_bar(stage), k0, key0, (int)head);
+                        tma_load_3d(sa + kTile, &map_k_lo, full_bar(stage), k0, key0, (int)head);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -133,10 +152,10 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
                     const int key0 = (int)((step - 1) * BKV);
                     for (uint32_t kb = 0; kb < BKV / SBK; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
-                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint32_t sa = ring_base + stage * kStageBytes;
                         mbar_expect_tx(full_bar(stage), 2 * p.dn * SBK * 4);
                         tma_load_3d(sa, &map_v_hi, full_bar(stage), key0 + (int)(kb * SBK), 0, (int)head);
-                        tma_load_3d(sa + 2 * kTile, &map_v_lo, full_bar(stage), key0 + (int)(kb * SBK), 0, (int)head);
+                        tma_load_3d(sa + kTile, &map_v_lo, full_bar(stage), key0 + (int)(kb * SBK), 0, (int)head);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -146,7 +165,17 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_s = make_idesc_tf32(BQ, BKV);
         const uint32_t idesc_o = make_idesc_tf32(BQ, (int)p.dn);
+        // A k-block's six MMAs execute in 384 cycles, so the issue path between them must be a handful of instructions
+        // (scripts/exp/exp_mma_rate.cu: 64 cycles per N = 128 MMA with descriptors at hand, 93 when each is rebuilt from
+        // its address).  Every shared-memory address >> 4 fits the descriptor's 14-bit field, so a descriptor is a
+        // constant high word and ONE add on the low word.
+        constexpr uint32_t kDescHi = (uint32_t)(make_desc_k<SBK>(0) >> 32);
+        constexpr uint32_t kT4 = kTile >> 4, kK4 = (UMMA_K * 4) >> 4;
+        const uint32_t desc_q0 = (uint32_t)make_desc_k<SBK>(0) + (smem_base >> 4);      // resident Q tile
+        const uint32_t desc_lo0 = (uint32_t)make_desc_k<SBK>(0) + (ring_base >> 4);     // ring
+        auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
         uint32_t stage = 0, phase = 0;
+        mbar_wait(q_full, 0);
         for (uint32_t step = 0; step <= kv_tiles; ++step) {
             if (step < kv_tiles) {
                 // ---- S_step = Q K^T over head_dim
@@ -158,16 +187,16 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        const uint32_t q_hi = sa, k_hi = sa + kTile, q_lo = sa + 2 * kTile, k_lo = sa + 3 * kTile;
+                        // descriptor low words: one add each (see desc_lo0 above)
+                        const uint32_t q_hi = desc_q0 + kb * (kQBlockBytes >> 4), q_lo = q_hi + kT4;
+                        const uint32_t k_hi = desc_lo0 + stage * (kStageBytes >> 4), k_lo = k_hi + kT4;
                         const uint32_t dst = tmem_base + kColS;
 #pragma unroll
                         for (int k = 0; k < SBK / UMMA_K; ++k) {
-                            const uint32_t koff = k * UMMA_K * 4;
                             const uint32_t accum = (kb | (uint32_t)k) != 0;
-                            umma_tf32(dst, make_desc_k<SBK>(q_lo + koff), make_desc_k<SBK>(k_hi + koff), idesc_s, accum);
-                            umma_tf32(dst, make_desc_k<SBK>(q_hi + koff), make_desc_k<SBK>(k_lo + koff), idesc_s, 1u);
-                            umma_tf32(dst, make_desc_k<SBK>(q_hi + koff), make_desc_k<SBK>(k_hi + koff), idesc_s, 1u);
+                            umma_tf32(dst, desc(q_lo + k * kK4), desc(k_hi + k * kK4), idesc_s, accum);
+                            umma_tf32(dst, desc(q_hi + k * kK4), desc(k_lo + k * kK4), idesc_s, 1u);
+                            umma_tf32(dst, desc(q_hi + k * kK4), desc(k_hi + k * kK4), idesc_s, 1u);
                         }
                         umma_commit(empty_bar(stage));
                         if (kb == p.num_kb_s - 1) umma_commit(s_full);
@@ -186,17 +215,15 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t sa = smem_base + stage * kStageBytes;
-                        const uint32_t v_hi = sa, v_lo = sa + 2 * kTile;
+                        const uint32_t v_hi = desc_lo0 + stage * (kStageBytes >> 4), v_lo = v_hi + kT4;
                         const uint32_t dst = tmem_base + kColO;
+                        const uint32_t p_hi = tmem_base + kColPhi + kb * SBK, p_lo = tmem_base + kColPlo + kb * SBK;
 #pragma unroll
                         for (int k = 0; k < SBK / UMMA_K; ++k) {
-                            const uint32_t koff = k * UMMA_K * 4;
-                            const uint32_t pcol = kb * SBK + k * UMMA_K;
                             const uint32_t accum = (kb | (uint32_t)k) != 0;
-                            umma_tf32_ts(dst, tmem_base + kColPlo + pcol, make_desc_k<SBK>(v_hi + koff), idesc_o, accum);
-                            umma_tf32_ts(dst, tmem_base + kColPhi + pcol, make_desc_k<SBK>(v_lo + koff), idesc_o, 1u);
-                            umma_tf32_ts(dst, tmem_base + kColPhi + pcol, make_desc_k<SBK>(v_hi + koff), idesc_o, 1u);
+                            umma_tf32_ts(dst, p_lo + k * UMMA_K, desc(v_hi + k * kK4), idesc_o, accum);
+                            umma_tf32_ts(dst, p_hi + k * UMMA_K, desc(v_lo + k * kK4), idesc_o, 1u);
+                            umma_tf32_ts(dst, p_hi + k * UMMA_K, desc(v_hi + k * kK4), idesc_o, 1u);
                         }
                         umma_commit(empty_bar(stage));
                         if (kb == BKV / SBK - 1) umma_commit(o_full);   // O'_t complete; P_t no longer needed
@@ -461,9 +488,9 @@ int launch_attention(const float* q, const float* k, const float* v, float* out,
         TRN_TRY(make_map(&mk_l, k_lo, heads, seq, dpad, BKV, SBK));
         TRN_TRY(make_map(&mv_h, v_hi, heads, d, seqpad, p.dn, SBK));
         TRN_TRY(make_map(&mv_l, v_lo, heads, d, seqpad, p.dn, SBK));
-        static const cudaError_t optin = cudaFuncSetAttribute(attention_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        static const cudaError_t optin = cudaFuncSetAttribute(attention_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         TRN_CUDA(optin);
-        attention_tf32x3_kernel<<<(unsigned)(heads * p.q_tiles), kThreads, kSmemBytes, s>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+        attention_tf32x3_kernel<<<(unsigned)(heads * p.q_tiles), kThreads, smem_bytes(p.num_kb_s), s>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
         count_launch();
         TRN_CUDA(cudaGetLastError());
         // IEEE path for Inf/NaN inputs: runs only when the split pre-pass raised the flag (checked on the device)
