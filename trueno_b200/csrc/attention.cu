@@ -43,6 +43,7 @@ constexpr uint32_t kTile = 128 * SBK * 4;            // 8 KiB: 128 rows x 64 B
 constexpr uint32_t kStageBytes = 2 * kTile;          // S phase: K_hi, K_lo; PV phase: V_hi, V_lo
 constexpr uint32_t kQBlockBytes = 2 * kTile;         // one resident k-block of the query tile: Q_hi, Q_lo
 constexpr int kThreads = 320;
+constexpr int kPairThreads = 384;   // pair kernel: warpgroup 0 = TMA, MMA, 2 idle warps; warpgroups 1-2 = softmax
 constexpr int kSoftmaxWarps = 8;
 constexpr uint32_t kColS = 0, kColPhi = 128, kColPlo = 256, kColO = 384, kTmemCols = 512;
 constexpr uint32_t kXchgBytes = 3 * 2 * 128 * 4;     // [buffer][half][row]
@@ -51,6 +52,15 @@ constexpr uint32_t kFixedBytes = kXchgBytes + 256 + 1024;   // exchange area, ba
 __host__ __device__ constexpr uint32_t ring_stages(uint32_t num_kb_s) {   // what is left after the resident Q tile
     const uint32_t n = (kSmemBudget - kFixedBytes - num_kb_s * kQBlockBytes) / kStageBytes;
     return n < (uint32_t)kMaxStages ? n : (uint32_t)kMaxStages;
+}
+constexpr uint32_t kHalfTile = kTile / 2;             // 64 rows x 64 B
+constexpr uint32_t kPairStageBytes = 2 * kHalfTile;   // hi, lo of this CTA's half tile: 8 KiB
+__host__ __device__ constexpr uint32_t pair_ring_stages(uint32_t num_kb_s) {
+    const uint32_t n = (kSmemBudget - kFixedBytes - num_kb_s * kQBlockBytes) / kPairStageBytes;
+    return n < (uint32_t)kMaxStages ? n : (uint32_t)kMaxStages;
+}
+__host__ __device__ constexpr uint32_t pair_smem_bytes(uint32_t num_kb_s) {
+    return num_kb_s * kQBlockBytes + pair_ring_stages(num_kb_s) * kPairStageBytes + kFixedBytes;
 }
 __host__ __device__ constexpr uint32_t smem_bytes(uint32_t num_kb_s) {
     return num_kb_s * kQBlockBytes + ring_stages(num_kb_s) * kStageBytes + kFixedBytes;
@@ -372,6 +382,332 @@ attention_tf32x3_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __gr
     }
 }
 
+// ---- CTA-pair variant (cta_group::2): the two CTAs of a cluster take two consecutive query tiles of one head and share
+// every K and V^T tile — each loads HALF of it (64 keys, or 64 of V^T's rows) and the pair's MMAs (M = 256, issued by the
+// leader) read both halves.  Per SM the score product then fetches 4 KiB of A + 2 KiB of B per MMA (96 B/clk instead of
+// 128) and TMA writes half as much (21 B/clk instead of 43): under the shared-memory port's 128 B/clk, where the
+// single-CTA kernel is over it; L2 -> SM traffic for K and V halves as well.  Synchronisation as in the CTA-pair GEMM:
+// TMA loads of both CTAs complete_tx on the leader's barriers, tcgen05.commit multicasts "stage free" / "S ready" /
+// "O' ready" to both CTAs, both CTAs' softmax warps arrive on the leader's s_free / p_full / o_free.
+__global__ void __launch_bounds__(kPairThreads, 1)
+attention_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                        const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
+                        const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
+                        const Params p) {
+    if (*p.nonfinite_flag != 0) return;   // Inf/NaN in the inputs: the SIMT kernel takes over (grid-uniform)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    // [Q tile: num_kb_s x (hi 8 KiB, lo 8 KiB), resident] [ring: kStages x (hi 8 KiB, lo 8 KiB)] [exchange] [barriers]
+    const uint32_t kStages = pair_ring_stages(p.num_kb_s);
+    constexpr uint32_t kStageBytes = kPairStageBytes;   // this CTA's 64 of the tile's 128 keys (or 64 of V^T's rows): hi, lo
+    const uint32_t q_bytes = p.num_kb_s * kQBlockBytes;
+    const uint32_t ring_base = smem_base + q_bytes;
+    float* xchg = reinterpret_cast<float*>(smem_gen + q_bytes + kStages * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + q_bytes + kStages * kStageBytes + kXchgBytes);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    const uint32_t s_full = bar_base + 8u * (2 * kMaxStages), s_free = s_full + 8, p_full = s_full + 16,
+                   o_full = s_full + 24, o_free = s_full + 32, q_full = s_full + 40;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // one 2-CTA cluster per (head, PAIR of query tiles); heavy (late, for causal) pairs first; rank 0 leads
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t q_pairs = (p.q_tiles + 1) / 2;
+    const uint32_t pair_id = blockIdx.x >> 1;
+    const uint32_t head = pair_id / q_pairs;
+    const uint32_t qp = q_pairs - 1 - pair_id % q_pairs;
+    const uint32_t qt = 2 * qp + rank;          // may be one past the last tile (odd tile count): rows masked, nothing stored
+    const uint32_t q0 = qt * BQ;
+    const uint32_t kv_tiles = p.causal ? min(2 * qp + 2, (p.seq + BKV - 1) / BKV) : (p.seq + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q_hi); tma_prefetch_desc(&map_k_hi); tma_prefetch_desc(&map_v_hi);
+        tma_prefetch_desc(&map_q_lo); tma_prefetch_desc(&map_k_lo); tma_prefetch_desc(&map_v_lo);
+        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(q_full, 1);
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 2 * kSoftmaxWarps);   // the leader's copies collect both CTAs' softmax warps
+        mbar_init(p_full, 2 * kSoftmaxWarps);
+        mbar_init(o_full, 1);
+        mbar_init(o_free, 2 * kSoftmaxWarps);
+        fence_barrier_init();
+    }
+    if (warp == 1) {   // the same warp in both CTAs allocates the pair's TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();     // barriers of BOTH CTAs are initialised before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // Register budget by role (setmaxnreg is per warpgroup): warpgroup 0 = TMA warp, MMA warp and two idle warps gives
+    // registers up; the softmax warpgroups take them — a softmax thread holds a 64-wide probability row AND a 64-wide
+    // output accumulator, and at the uniform 168-register limit the accumulator spilled (the drain of O' took ~2700 cycles
+    // per key tile and sat on the critical path between two value products).
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+    if (warp == 0) {
+        // ===================== TMA producer: the MMA warp's order S_0, S_1, PV_0, S_2, PV_1, ... =====================
+        if (elect_one()) {
+            // the query tile, once: every k-block of Q_hi and Q_lo stays in shared memory for all key tiles.
+            // All loads of both CTAs complete_tx on the LEADER's barriers.
+            const uint32_t lead_q = q_full & kPeerMask;
+            if (rank == 0) mbar_expect_tx(q_full, 2 * q_bytes);
+            for (uint32_t kb = 0; kb < p.num_kb_s; ++kb) {
+                tma_load_3d_pair(smem_base + kb * kQBlockBytes, &map_q_hi, lead_q, (int)(kb * SBK), (int)q0, (int)head);
+                tma_load_3d_pair(smem_base + kb * kQBlockBytes + kTile, &map_q_lo, lead_q, (int)(kb * SBK), (int)q0, (int)head);
+            }
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t step = 0; step <= kv_tiles; ++step) {
+                if (step < kv_tiles) {
+                    const int key0 = (int)(step * BKV + rank * (BKV / 2));   // this CTA's 64 keys of the tile
+                    for (uint32_t kb = 0; kb < p.num_kb_s; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = ring_base + stage * kStageBytes;
+                        const uint32_t lead_full = full_bar(stage) & kPeerMask;
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+                        const int k0 = (int)(kb * SBK);
+                        tma_load_3d_pair(sa, &map_k_hi, lead_full, k0, key0, (int)head);
+                        tma_load_3d_pair(sa + kHalfTile, &map_k_lo, lead_full, k0, key0, (int)head);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                if (step >= 1) {
+                    const int key0 = (int)((step - 1) * BKV);
+                    const int row0 = (int)(rank * (p.dn / 2));               // this CTA's half of V^T's rows (output columns)
+                    for (uint32_t kb = 0; kb < BKV / SBK; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = ring_base + stage * kStageBytes;
+                        const uint32_t lead_full = full_bar(stage) & kPeerMask;
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * 2 * (p.dn / 2) * SBK * 4);
+                        tma_load_3d_pair(sa, &map_v_hi, lead_full, key0 + (int)(kb * SBK), row0, (int)head);
+                        tma_load_3d_pair(sa + kHalfTile, &map_v_lo, lead_full, key0 + (int)(kb * SBK), row0, (int)head);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only): M = 256 = both CTAs' query tiles =====================
+        if (rank == 0) {
+        constexpr uint32_t idesc_s = make_idesc_tf32(2 * BQ, BKV);
+        const uint32_t idesc_o = make_idesc_tf32(2 * BQ, (int)p.dn);
+        // A k-block's six MMAs execute in 384 cycles, so the issue path between them must be a handful of instructions
+        // (scripts/exp/exp_mma_rate.cu: 64 cycles per N = 128 MMA with descriptors at hand, 93 when each is rebuilt from
+        // its address).  Every shared-memory address >> 4 fits the descriptor's 14-bit field, so a descriptor is a
+        // constant high word and ONE add on the low word.
+        constexpr uint32_t kDescHi = (uint32_t)(make_desc_k<SBK>(0) >> 32);
+        constexpr uint32_t kT4 = kTile >> 4, kH4 = kHalfTile >> 4, kK4 = (UMMA_K * 4) >> 4;
+        const uint32_t desc_q0 = (uint32_t)make_desc_k<SBK>(0) + (smem_base >> 4);      // resident Q tile
+        const uint32_t desc_lo0 = (uint32_t)make_desc_k<SBK>(0) + (ring_base >> 4);     // ring
+        auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+        uint32_t stage = 0, phase = 0;
+        mbar_wait(q_full, 0);
+        for (uint32_t step = 0; step <= kv_tiles; ++step) {
+            if (step < kv_tiles) {
+                // ---- S_step = Q K^T over head_dim
+                if (step >= 1) {
+                    mbar_wait(s_free, (step - 1) & 1);   // the softmax warps have read S_{step-1}
+                    tc_fence_after();
+                }
+                for (uint32_t kb = 0; kb < p.num_kb_s; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // descriptor low words: one add each (see desc_lo0 above)
+                        const uint32_t q_hi = desc_q0 + kb * (kQBlockBytes >> 4), q_lo = q_hi + kT4;
+                        const uint32_t k_hi = desc_lo0 + stage * (kStageBytes >> 4), k_lo = k_hi + kH4;
+                        const uint32_t dst = tmem_base + kColS;
+#pragma unroll
+                        for (int k = 0; k < SBK / UMMA_K; ++k) {
+                            const uint32_t accum = (kb | (uint32_t)k) != 0;
+                            umma_tf32_pair(dst, desc(q_lo + k * kK4), desc(k_hi + k * kK4), idesc_s, accum);
+                            umma_tf32_pair(dst, desc(q_hi + k * kK4), desc(k_lo + k * kK4), idesc_s, 1u);
+                            umma_tf32_pair(dst, desc(q_hi + k * kK4), desc(k_hi + k * kK4), idesc_s, 1u);
+                        }
+                        umma_commit_pair(empty_bar(stage));
+                        if (kb == p.num_kb_s - 1) umma_commit_pair(s_full);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (step >= 1) {
+                // ---- O'_{t} = P_t V_t over the tile's 128 keys, t = step - 1
+                const uint32_t t = step - 1;
+                mbar_wait(p_full, t & 1);                      // P_t is in tensor memory
+                if (t >= 1) mbar_wait(o_free, (t - 1) & 1);    // O'_{t-1} has been drained
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < BKV / SBK; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t v_hi = desc_lo0 + stage * (kStageBytes >> 4), v_lo = v_hi + kH4;
+                        const uint32_t dst = tmem_base + kColO;
+                        const uint32_t p_hi = tmem_base + kColPhi + kb * SBK, p_lo = tmem_base + kColPlo + kb * SBK;
+#pragma unroll
+                        for (int k = 0; k < SBK / UMMA_K; ++k) {
+                            const uint32_t accum = (kb | (uint32_t)k) != 0;
+                            umma_tf32_ts_pair(dst, p_lo + k * UMMA_K, desc(v_hi + k * kK4), idesc_o, accum);
+                            umma_tf32_ts_pair(dst, p_hi + k * UMMA_K, desc(v_lo + k * kK4), idesc_o, 1u);
+                            umma_tf32_ts_pair(dst, p_hi + k * UMMA_K, desc(v_hi + k * kK4), idesc_o, 1u);
+                        }
+                        umma_commit_pair(empty_bar(stage));
+                        if (kb == BKV / SBK - 1) umma_commit_pair(o_full);   // O'_t complete; P_t no longer needed
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        }
+    }
+    } else {
+        // ===================== softmax / accumulation warps (4..11) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+        const uint32_t quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const uint32_t half = (uint32_t)(warp - 4) >> 2;  // which 64 of the tile's 128 keys / of the output columns
+        const uint32_t row_in_tile = quad * 32 + lane;
+        const uint32_t qrow = q0 + row_in_tile;
+        const uint32_t lane_addr = tmem_base + ((quad * 32u) << 16);
+        const uint32_t ocols = p.dn > 64 * half ? min(64u, p.dn - 64 * half) : 0u;   // this thread's O columns
+        float o_acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o_acc[i] = 0.0f;
+        float m_run = -INFINITY, l_part = 0.0f, alpha_prev = 0.0f;
+        const float scale2 = __fmul_rn(p.scale, 1.4426950408889634f);   // scale * log2(e)
+
+        auto drain_o = [&](uint32_t t, float alpha) {
+            // O = O * alpha + O'_t  (second accumulation level, round-to-nearest)
+            mbar_wait(o_full, t & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if ((uint32_t)(j * 32) < ocols) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(lane_addr + kColO + 64 * half + j * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o_acc[j * 32 + i] = __fmaf_rn(o_acc[j * 32 + i], alpha, __uint_as_float(r[i]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(o_free & kPeerMask);
+        };
+
+        for (uint32_t t = 0; t < kv_tiles; ++t) {
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+            float x[64];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t r[32];
+                tmem_ld_32x32(lane_addr + kColS + 64 * half + j * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[j * 32 + i] = __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(s_free & kPeerMask);   // S_{t+1} may overwrite the buffer
+
+            // Scores in the base-2 domain: x = s * (scale * log2 e), so that exp(scale*s - m) = 2^(x - m2) is one FADD
+            // and one MUFU.EX2 per element (ex2.approx: 2 ulp; the product rounding moves a score by <= 0.5 ulp —
+            // both far inside the matmul contract's 1e-5 * sum|q||k| allowance on the scores).
+            // Masking (keys past the sequence, keys after the query when causal) only on the tiles that need it.
+            const uint32_t key0 = t * BKV + 64 * half;
+            const bool mask_tile = (t + 1) * BKV > p.seq || (p.causal && t >= qt);   // CTA-uniform; t > qt: wholly masked
+            float m_loc = -INFINITY;
+            if (mask_tile) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const uint32_t key = key0 + i;
+                    const bool valid = key < p.seq && (!p.causal || key <= qrow);
+                    x[i] = valid ? __fmul_rn(x[i], scale2) : -INFINITY;
+                    m_loc = fmaxf(m_loc, x[i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    x[i] = __fmul_rn(x[i], scale2);
+                    m_loc = fmaxf(m_loc, x[i]);
+                }
+            }
+            float* xb = xchg + (t & 1) * 256;
+            xb[half * 128 + row_in_tile] = m_loc;
+            named_bar_sync(1 + quad, 64);
+            const float m_new = fmaxf(m_run, fmaxf(m_loc, xb[(half ^ 1) * 128 + row_in_tile]));
+            const float m_use = m_new == -INFINITY ? 0.0f : m_new;            // row with no valid key yet
+            const float alpha = m_run == -INFINITY ? 0.0f : ex2_approx(m_run - m_use);
+            m_run = m_new;
+
+            // p = 2^(x - m) in place, row-sum partial
+            float l_tile = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                x[i] = ex2_approx(x[i] - m_use);
+                l_tile += x[i];
+            }
+            l_part = __fmaf_rn(l_part, alpha, l_tile);
+
+            // the previous tile's PV product must have retired before P is overwritten; drain its O' first
+            if (t >= 1) drain_o(t - 1, alpha_prev);
+            alpha_prev = alpha;
+            // tf32 split: hi = rna(p), lo = rna(p - hi)  (p - hi is exact), written where the MMA reads its A operand
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = tf32_rna_finite(x[j * 32 + i]);
+                tmem_st_32x32(lane_addr + kColPhi + 64 * half + j * 32, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = tf32_rna_finite(x[j * 32 + i] - __uint_as_float(r[i]));
+                tmem_st_32x32(lane_addr + kColPlo + 64 * half + j * 32, r);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(p_full & kPeerMask);
+        }
+        drain_o(kv_tiles - 1, alpha_prev);
+
+        // row sum: half 0 + half 1 (fixed order), then normalise and store this thread's columns
+        float* xb = xchg + 2 * 256;
+        xb[half * 128 + row_in_tile] = l_part;
+        named_bar_sync(1 + quad, 64);
+        const float inv_l = 1.0f / (xb[row_in_tile] + xb[128 + row_in_tile]);
+        if (qrow < p.seq && ocols > 0) {
+            float* orow = p.out + ((size_t)head * p.seq + qrow) * p.d + 64 * half;
+            const uint32_t ncol = min(ocols, p.d > 64 * half ? p.d - 64 * half : 0u);
+            const bool vec = (p.d & 3u) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+                if ((uint32_t)i + 3 < ncol && vec) {
+                    *reinterpret_cast<float4*>(orow + i) = make_float4(o_acc[i] * inv_l, o_acc[i + 1] * inv_l, o_acc[i + 2] * inv_l, o_acc[i + 3] * inv_l);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((uint32_t)(i + e) < ncol) orow[i + e] = o_acc[i + e] * inv_l;
+                }
+            }
+        }
+    }
+
+    // neither CTA may leave (or free TMEM) while its partner can still signal it or read its shared memory
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ---- IEEE path: one warp per query row, online softmax key by key -------------------------------------------
 constexpr int kSimtMaxC = 32;   // head_dim <= 1024
 
@@ -484,13 +820,39 @@ int launch_attention(const float* q, const float* k, const float* v, float* out,
         CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
         TRN_TRY(make_map(&mq_h, q_hi, heads, seq, dpad, BQ, SBK));
         TRN_TRY(make_map(&mq_l, q_lo, heads, seq, dpad, BQ, SBK));
-        TRN_TRY(make_map(&mk_h, k_hi, heads, seq, dpad, BKV, SBK));
-        TRN_TRY(make_map(&mk_l, k_lo, heads, seq, dpad, BKV, SBK));
-        TRN_TRY(make_map(&mv_h, v_hi, heads, d, seqpad, p.dn, SBK));
-        TRN_TRY(make_map(&mv_l, v_lo, heads, d, seqpad, p.dn, SBK));
-        static const cudaError_t optin = cudaFuncSetAttribute(attention_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-        TRN_CUDA(optin);
-        attention_tf32x3_kernel<<<(unsigned)(heads * p.q_tiles), kThreads, smem_bytes(p.num_kb_s), s>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+        // CTA pairs (two query tiles share every K / V tile) whenever a head has at least two query tiles;
+        // TRN_ATT_PAIR=0 forces the single-CTA kernel (A/B measurements and its own parity tests)
+        static const int use_pair = [] { const char* e = getenv("TRN_ATT_PAIR"); return e ? atoi(e) : 1; }();
+        const size_t q_pairs = (p.q_tiles + 1) / 2;
+        if (use_pair && p.q_tiles >= 2 && heads * q_pairs * 2 <= 0x7FFFFFFFull) {
+            TRN_TRY(make_map(&mk_h, k_hi, heads, seq, dpad, BKV / 2, SBK));
+            TRN_TRY(make_map(&mk_l, k_lo, heads, seq, dpad, BKV / 2, SBK));
+            TRN_TRY(make_map(&mv_h, v_hi, heads, d, seqpad, p.dn / 2, SBK));
+            TRN_TRY(make_map(&mv_l, v_lo, heads, d, seqpad, p.dn / 2, SBK));
+            static const cudaError_t optin2 = cudaFuncSetAttribute(attention_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+            TRN_CUDA(optin2);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(heads * q_pairs * 2));
+            cfg.blockDim = dim3(kPairThreads);
+            cfg.dynamicSmemBytes = pair_smem_bytes(p.num_kb_s);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            TRN_CUDA(cudaLaunchKernelEx(&cfg, attention_tf32x3_pair_kernel, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
+        } else {
+            TRN_TRY(make_map(&mk_h, k_hi, heads, seq, dpad, BKV, SBK));
+            TRN_TRY(make_map(&mk_l, k_lo, heads, seq, dpad, BKV, SBK));
+            TRN_TRY(make_map(&mv_h, v_hi, heads, d, seqpad, p.dn, SBK));
+            TRN_TRY(make_map(&mv_l, v_lo, heads, d, seqpad, p.dn, SBK));
+            static const cudaError_t optin = cudaFuncSetAttribute(attention_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+            TRN_CUDA(optin);
+            attention_tf32x3_kernel<<<(unsigned)(heads * p.q_tiles), kThreads, smem_bytes(p.num_kb_s), s>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+        }
         count_launch();
         TRN_CUDA(cudaGetLastError());
         // IEEE path for Inf/NaN inputs: runs only when the split pre-pass raised the flag (checked on the device)
