@@ -163,3 +163,31 @@ def test_attention_full_size_rows_sum_to_one(trn):
     for causal in (False, True):
         out = trn.attention(q, k, v, heads, seq, d, causal=causal)
         assert np.max(np.abs(out - 1.0)) <= 4e-6
+
+
+@pytest.mark.parametrize("mode", ["0", "2"], ids=["single-cta", "forced-pairs"])
+def test_attention_kernel_variants_in_subprocess(trn, mode):
+    """The launcher picks the CTA-pair kernel or the single-CTA kernel by shape; TRN_ATT_PAIR (read once per process)
+    forces either, so both run the multi-tile, ragged and causal shapes here, each in its own process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import trueno_b200 as trn
+from test_attention_gpu import make, truth64
+for heads, seq, d in [(2, 200, 128), (1, 384, 32), (2, 129, 5), (1, 640, 64), (3, 300, 96)]:
+    for causal in (False, True):
+        q, k, v = make(heads, seq, d, seed=seq + d)
+        scale = np.float32(1.0) / np.sqrt(np.float32(d))
+        got = trn.attention(q, k, v, heads, seq, d, causal=causal)
+        want, bound, kappa = truth64(q, k, v, heads, seq, d, scale, causal)
+        tol = (1e-5 + 2e-5 * kappa) * bound + 1e-30
+        assert np.all(np.abs(got - want) <= tol), (heads, seq, d, causal, float(np.max(np.abs(got - want) / tol)))
+print("variants ok")
+'''
+    env = dict(os.environ, TRN_ATT_PAIR=mode)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "variants ok" in r.stdout, r.stdout + r.stderr

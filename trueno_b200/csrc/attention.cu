@@ -6,6 +6,8 @@
 // the "attention pattern" test at :3985) -> Vector::scale -> Vector::softmax (src/vector.rs:1516) ->
 // batched_matmul_4d(P, V).  The seq x seq score matrix never exists in HBM.
 //
+// attention_tf32x3_pair_kernel is the kernel that normally runs (two CTAs = two query tiles of a head, see below);
+// attention_tf32x3_kernel is its single-CTA form (one query tile per head, short causal sequences, A/B runs).
 // attention_tf32x3_kernel (head_dim <= 128): one CTA per (head, 128 query rows), 320 threads:
 //   warp 0   TMA producer: the query tile (hi, lo) once, resident in shared memory; then a ring of 16 KiB stages
 //            (5 at head_dim 128, up to 12 below) of 16-wide k-blocks of the pre-split K and V^T (hi, lo)
@@ -820,11 +822,14 @@ int launch_attention(const float* q, const float* k, const float* v, float* out,
         CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
         TRN_TRY(make_map(&mq_h, q_hi, heads, seq, dpad, BQ, SBK));
         TRN_TRY(make_map(&mq_l, q_lo, heads, seq, dpad, BQ, SBK));
-        // CTA pairs (two query tiles share every K / V tile) whenever a head has at least two query tiles;
-        // TRN_ATT_PAIR=0 forces the single-CTA kernel (A/B measurements and its own parity tests)
+        // CTA pairs (two query tiles share every K / V tile) whenever a head has at least two query tiles.  With a causal
+        // mask the pair also runs the earlier tile through the later tile's last key tile (wholly masked for it): 1/(T+1)
+        // extra work at T query tiles against the pair kernel's ~18 % gain, so short causal sequences stay single.
+        // TRN_ATT_PAIR=0 forces the single-CTA kernel (A/B measurements and its own parity tests), 2 forces pairs.
         static const int use_pair = [] { const char* e = getenv("TRN_ATT_PAIR"); return e ? atoi(e) : 1; }();
         const size_t q_pairs = (p.q_tiles + 1) / 2;
-        if (use_pair && p.q_tiles >= 2 && heads * q_pairs * 2 <= 0x7FFFFFFFull) {
+        const bool pair_pays = use_pair == 2 || !causal || p.q_tiles >= 6;
+        if (use_pair && pair_pays && p.q_tiles >= 2 && heads * q_pairs * 2 <= 0x7FFFFFFFull) {
             TRN_TRY(make_map(&mk_h, k_hi, heads, seq, dpad, BKV / 2, SBK));
             TRN_TRY(make_map(&mk_l, k_lo, heads, seq, dpad, BKV / 2, SBK));
             TRN_TRY(make_map(&mv_h, v_hi, heads, d, seqpad, p.dn / 2, SBK));
