@@ -52,6 +52,7 @@ constexpr int BM = 128;   // UMMA M (cta_group::1)
 constexpr int BN = 256;   // UMMA N
 constexpr int BK = 32;    // K padding granularity of the split operands (Kpad % 32 == 0)
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kPairThreads = 384;  // pair kernel: warpgroup 0 = TMA, MMA, 2 idle warps; warpgroups 1-2 = 8 epilogue warps
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kChunkK = 128;  // K extent accumulated in TMEM before draining to registers
 constexpr uint32_t kTmemCols = 512;        // 2 accumulator stages x 256 columns
@@ -302,7 +303,7 @@ constexpr uint32_t kStoreBytes = kEpiWarps * 4096;
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 + 256;
 }  // namespace pair
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kPairThreads, 1)
 gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                         const __grid_constant__ CUtensorMap map_c, const Params p) {
@@ -342,6 +343,11 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register budget by role (setmaxnreg is per warpgroup, and ptxas honours it only as the first statement of the role's
+    // branch): warpgroup 0 = TMA warp, MMA warp, two idle warps; warpgroups 1-2 = the epilogue warps, whose 128 register
+    // accumulators of the second accumulation level do not fit the uniform 168-register limit.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
         if (elect_one()) {
@@ -401,10 +407,12 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 }
             }
         }
+    }
     } else {
-        // ===================== epilogue (warps 2..9, both CTAs, own 128 rows) =====================
+        // ===================== epilogue (warps 4..11, both CTAs, own 128 rows) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
         const uint32_t quad = warp & 3;
-        const uint32_t half = (warp - 2) >> 2;
+        const uint32_t half = (warp - 4) >> 2;
         const uint32_t num_chunks = (p.num_kb + kChunkKB - 1) / kChunkKB;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
@@ -437,7 +445,7 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             const uint32_t row = row0 + lane;
             const uint32_t col_base = nt * BN + half * 128;
             if (p.tma_store) {
-                const uint32_t stage_addr = store_base + (uint32_t)(warp - 2) * 4096u;
+                const uint32_t stage_addr = store_base + (uint32_t)(warp - 4) * 4096u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -740,7 +748,7 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
         const uint32_t pairs = total < max_pairs ? total : max_pairs;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(kPairThreads);
         cfg.dynamicSmemBytes = pair::kSmemBytes;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
