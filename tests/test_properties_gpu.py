@@ -105,3 +105,51 @@ def test_matvec_and_vecmat_associativity(trn, data):               # src/matrix.
     l2 = M.vecmat(V(w), mA.matmul(mB)).as_slice()
     r2 = M.vecmat(M.vecmat(V(w), mA), mB).as_slice()
     assert np.all(np.abs(l2 - r2) <= 2e-2 * scale2)                                             # w(AB) = (wA)B
+
+
+# ---- widened rows: SymmetricEigen (the reference's proptests, src/eigen.rs:805-870) and the fused attention -----------
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(data=st.data())
+def test_eigen_properties(trn, data):
+    """prop_eigenvalues_descending (n in 2..6), prop_eigenvector_count_matches_dimension (1..8),
+    prop_reconstruction_accuracy — here for n in 1..24 and arbitrary symmetric matrices."""
+    n = data.draw(st.integers(1, 24))
+    a = data.draw(hnp.arrays(f32, (n, n), elements=st.floats(-10, 10, width=32)))
+    m = ((a + a.T) / 2).astype(f32)
+    eig = trn.SymmetricEigen.new(trn.Matrix.from_vec(n, n, m.ravel()))
+    vals = eig.eigenvalues().astype(np.float64)
+    vecs = eig.eigenvectors().as_slice().reshape(n, n).astype(np.float64)
+    frob = max(1.0, float(np.linalg.norm(m.astype(np.float64))))
+    assert len(eig) == n and vecs.shape == (n, n)
+    assert np.all(np.diff(vals) <= 0)
+    assert np.max(np.abs(vecs @ np.diag(vals) @ vecs.T - m)) <= 1e-5 * frob * max(1.0, n ** 0.5)
+    assert np.max(np.abs(vals - np.linalg.eigvalsh(np.triu(m).astype(np.float64) + np.triu(m, 1).T.astype(np.float64))[::-1])) <= 4e-6 * frob
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(data=st.data())
+def test_attention_properties(trn, data):
+    """Rows of the output are convex combinations of the value rows (inside their min/max per column), and the result
+    matches the f64 truth within the stated contract — random ragged shapes, both masks, both kernel forms' ranges."""
+    heads = data.draw(st.integers(1, 3))
+    seq = data.draw(st.integers(1, 300))
+    d = data.draw(st.sampled_from([1, 3, 8, 16, 24, 40, 64, 72, 128, 136]))
+    causal = data.draw(st.booleans())
+    seed = data.draw(st.integers(0, 2 ** 31))
+    rng = np.random.default_rng(seed)
+    q, k, v = (rng.standard_normal(heads * seq * d).astype(f32) * f32(1.5) for _ in range(3))
+    scale = f32(1.0) / np.sqrt(f32(d))
+    got = trn.attention(q, k, v, heads, seq, d, causal=causal).reshape(heads, seq, d)
+    q64, k64, v64 = (x.reshape(heads, seq, d).astype(np.float64) for x in (q, k, v))
+    s = np.einsum("hid,hjd->hij", q64, k64) * float(scale)
+    if causal:
+        s = np.where(np.arange(seq)[None, None, :] > np.arange(seq)[None, :, None], -np.inf, s)
+    p = np.exp(s - s.max(axis=-1, keepdims=True))
+    p /= p.sum(axis=-1, keepdims=True)
+    want = np.einsum("hij,hjd->hid", p, v64)
+    bound = np.einsum("hij,hjd->hid", p, np.abs(v64))
+    kappa = float(scale) * np.einsum("hid,hjd->hij", np.abs(q64), np.abs(k64)).max()
+    assert np.all(np.abs(got - want) <= (1e-5 + 2e-5 * kappa) * bound + 1e-30)
+    lo, hi = v64.min(axis=1, keepdims=True), v64.max(axis=1, keepdims=True)
+    span = (hi - lo) + np.abs(hi) + np.abs(lo)
+    assert np.all(got >= lo - 1e-5 * span) and np.all(got <= hi + 1e-5 * span)
