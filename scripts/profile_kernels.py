@@ -1,7 +1,7 @@
 """One launch of every hot-path kernel at its BASELINE size between cudaProfilerStart/Stop, for
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_all python scripts/profile_kernels.py
 Warm-up launches run before the profiler range so the captured launch is steady-state (apart from ncu's own
-cache control).  usage: python scripts/profile_kernels.py [gemm] [batched] [reduce] [map] [softmax] [rows] [matvec]"""
+cache control).  usage: python scripts/profile_kernels.py [gemm] [batched] [reduce] [map] [softmax] [rows] [matvec] [attention] [conv]"""
 import os
 import sys
 
@@ -12,7 +12,7 @@ import trueno_b200 as trn  # noqa: E402
 
 
 def main():
-    which = set(sys.argv[1:]) or {"gemm", "batched", "reduce", "map", "softmax", "rows", "matvec"}
+    which = set(sys.argv[1:]) or {"gemm", "batched", "reduce", "map", "softmax", "rows", "matvec", "attention", "conv"}
     torch.cuda.set_device(0)
     trn.check(trn.lib.trn_cuda_init(0))
     stream = torch.cuda.Stream()
@@ -74,6 +74,20 @@ def main():
         ma, mv, my = torch.randn(r, r, device="cuda"), torch.randn(r, device="cuda"), torch.empty(r, device="cuda")
         keep += [ma, mv, my]
         ops.append(lambda: trn.check(L.trn_matvec_f32_dev(ma.data_ptr(), r, r, mv.data_ptr(), r, my.data_ptr(), st)))
+    if "attention" in which:
+        aH, aseq, ad = 256, 2048, 128
+        aq, ak, av = (torch.randn(aH * aseq * ad, device="cuda") for _ in range(3))
+        ao = torch.empty_like(aq)
+        keep += [aq, ak, av, ao]
+        for causal in (0, 1):
+            ops.append(lambda causal=causal: trn.check(L.trn_attention_f32_dev(aq.data_ptr(), aq.numel(), ak.data_ptr(), ak.numel(),
+                                                                               av.data_ptr(), av.numel(), ao.data_ptr(), aH, aseq, ad,
+                                                                               1.0 / ad ** 0.5, causal, st)))
+    if "conv" in which:
+        img, ker = torch.randn(8192, 8192, device="cuda"), torch.randn(5, 5, device="cuda")
+        co = torch.empty(8188 * 8188, device="cuda")
+        keep += [img, ker, co]
+        ops.append(lambda: trn.check(L.trn_convolve2d_f32_dev(img.data_ptr(), 8192, 8192, ker.data_ptr(), 5, 5, co.data_ptr(), st)))
     for _ in range(3):
         for f in ops:
             f()

@@ -27,6 +27,7 @@
 //
 // Tensor-bound: 4 * seq^2 * head_dim flop per head (2 * seq^2 * head_dim for causal), executed 3x in TF32.
 // HBM traffic is O(seq * head_dim) per head; K and V tiles are re-read from L2 by the seq/128 query tiles.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -719,8 +720,7 @@ attention_simt_kernel(const float* __restrict__ q, const float* __restrict__ k, 
                       const int* __restrict__ only_if_flag) {
     if (only_if_flag != nullptr && *only_if_flag == 0) return;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t row_id = (size_t)blockIdx.x * 4 + warp;
-    if (row_id >= (size_t)heads * seq) return;
+    for (size_t row_id = (size_t)blockIdx.x * 4 + warp; row_id < (size_t)heads * seq; row_id += (size_t)gridDim.x * 4) {
     const uint32_t head = (uint32_t)(row_id / seq), qrow = (uint32_t)(row_id % seq);
     const float* qr = q + row_id * d;
     const float* kh = k + (size_t)head * seq * d;
@@ -763,6 +763,7 @@ attention_simt_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     for (int c = 0; c < kSimtMaxC; ++c) {
         const uint32_t col = c * 32 + lane;
         if ((uint32_t)c < nc && col < d) out[row_id * d + col] = o[c] / l;
+    }
     }
 }
 
@@ -860,8 +861,10 @@ int launch_attention(const float* q, const float* k, const float* v, float* out,
         }
         count_launch();
         TRN_CUDA(cudaGetLastError());
-        // IEEE path for Inf/NaN inputs: runs only when the split pre-pass raised the flag (checked on the device)
-        attention_simt_kernel<<<(unsigned)simt_blocks, 128, 0, s>>>(q, k, v, out, (uint32_t)heads, (uint32_t)seq, (uint32_t)d,
+        // IEEE path for Inf/NaN inputs: runs only when the split pre-pass raised the flag (checked on the device).  A
+        // grid of a few blocks per SM striding over the rows: as a no-op it costs ~3 us (131 072 empty blocks cost 76 us)
+        const size_t gated_blocks = std::min(simt_blocks, (size_t)cx->sm_count * 16);
+        attention_simt_kernel<<<(unsigned)gated_blocks, 128, 0, s>>>(q, k, v, out, (uint32_t)heads, (uint32_t)seq, (uint32_t)d,
                                                                    scale, causal ? 1u : 0u, flag);
         count_launch();
         TRN_CUDA(cudaGetLastError());
