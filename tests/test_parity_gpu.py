@@ -201,7 +201,12 @@ def test_pixel_fkr_softmax(trn, oracle):
 @pytest.mark.parametrize("rows,cols", [(1, 1), (3, 4), (5, 7), (4, 1000), (7, 1001), (3, 1024), (2, 2048), (5, 4096),
                                        (3, 8192), (4, 16384), (6, 32000), (2, 32768), (3, 40000), (2, 65536),
                                        (2, 70000), (1, 200_003), (300, 32000),
-                                       (700, 9000), (450, 32768), (149, 8196), (3, 20000)])
+                                       (700, 9000), (450, 32768), (149, 8196), (3, 20000),
+                                       # window form (rows not 16-byte aligned) of every kernel, and the long kernel
+                                       (9, 77), (64, 1018), (5, 1019), (5, 1023), (3, 4099), (5, 16387), (5, 32001),
+                                       (33, 50257), (3, 65530), (3, 65531), (3, 65537), (4, 128256), (2, 151936),
+                                       (2, 262144), (1, 1_000_003), (40, 131072), (19, 66666), (20, 65537), (20, 65540),
+                                       (1, 4_194_304 + 4), (2, 3_000_001)])
 def test_softmax_rows_vs_oracle(trn, oracle, rows, cols):
     rng = np.random.default_rng(rows * 131 + cols)
     x = (rng.standard_normal((rows, cols)) * 4).astype(f32)
@@ -237,6 +242,95 @@ def test_softmax_determinism_and_nan_row(trn):
     x[2, 17] = np.nan
     b = trn.softmax_rows(x, 4, 32000)
     assert np.isnan(b[2]).all() and np.array_equal(b[[0, 1, 3]], a[[0, 1, 3]])
+
+
+def _softmax_ref(x, log=False):
+    """the reference's expressions on f32 data, f64 accumulation of the sum (src/vector.rs:1540-1553, :1605-1623)"""
+    with np.errstate(all="ignore"):
+        m = np.max(x, axis=1, keepdims=True)     # rows here hold no NaN
+        arg = (x - m).astype(f32).astype(np.float64)
+        e = np.exp(arg)
+        ssum = e.sum(1, keepdims=True)
+        return arg - np.log(ssum) if log else e / ssum
+
+
+@pytest.mark.parametrize("rows", [6, 24], ids=["few_rows", "many_rows"])   # few long rows: split kernels; many: cluster
+@pytest.mark.parametrize("cols", [77, 5001, 50257, 70000, 70001, 131072, 300_001])
+def test_softmax_special_rows(trn, rows, cols):
+    """-inf prefixes / blocks (online max must not manufacture NaN), an all -inf row and a +inf row (NaN, as the
+    reference's x - max gives), a NaN row — through the window, cluster and long kernels."""
+    rng = np.random.default_rng(cols)
+    x = (rng.standard_normal((rows, cols)) * 4).astype(f32)
+    x[0, : cols - 3] = -np.inf                      # finite values only at the very end
+    x[1, cols // 3: 2 * cols // 3] = -np.inf        # a -inf block in the middle
+    x[2, :] = -np.inf                               # reference: -inf - -inf = NaN everywhere
+    x[3, cols // 2] = np.inf                        # reference: inf - inf = NaN in the sum -> NaN row
+    x[4, cols - 1] = np.nan
+    for log in (False, True):
+        got = trn.softmax_rows(x, rows, cols, log=log)
+        ok = [0, 1] + list(range(5, rows))
+        want = _softmax_ref(x[ok], log=log)
+        g = got[ok].astype(np.float64)
+        if log:
+            fin = np.isfinite(want)
+            assert np.array_equal(np.isneginf(g), np.isneginf(want))
+            assert np.all(np.abs(g[fin] - want[fin]) <= 4 * ulp(want[fin]) + 2.0 ** -20)
+        else:
+            assert np.all(np.abs(g - want) <= np.minimum(1e-6, 8 * ulp(want) + 1e-45))
+        assert np.isnan(got[2]).all() and np.isnan(got[3]).all() and np.isnan(got[4]).all()
+
+
+@pytest.mark.parametrize("rows,cols", [(7, 77), (5, 1000), (3, 5000), (3, 40000), (2, 50257), (2, 70000), (2, 140001)])
+@pytest.mark.parametrize("mis_in,mis_out", [(1, 1), (2, 2), (3, 3), (0, 0), (1, 2), (0, 3)])
+def test_softmax_rows_misaligned_base(trn, rows, cols, mis_in, mis_out):
+    """`_dev` entry points on base pointers that are only 4-byte aligned: equal misalignment of input and output
+    takes the window kernels, different misalignment the three-pass fallback; guard words around the output stay."""
+    torch = pytest.importorskip("torch")
+    trn.check(trn.lib.trn_cuda_init(0))
+    dev = torch.device("cuda", 0)
+    n = rows * cols
+    g = torch.Generator(device="cpu").manual_seed(rows * 1000 + cols)
+    host = (torch.randn(n, generator=g) * 4).float()
+    xin = torch.zeros(n + 8, device=dev)
+    xin[mis_in: mis_in + n] = host.to(dev)
+    st = torch.cuda.current_stream().cuda_stream or 1
+    for log in (False, True):
+        yout = torch.full((n + 8,), 123.0, device=dev)
+        fn = trn.lib.trn_log_softmax_rows_f32_dev if log else trn.lib.trn_softmax_rows_f32_dev
+        trn.check(fn(xin.data_ptr() + 4 * mis_in, yout.data_ptr() + 4 * mis_out, rows, cols, st))
+        torch.cuda.synchronize()
+        y = yout.cpu().numpy()
+        assert np.all(y[:mis_out] == 123.0) and np.all(y[mis_out + n:] == 123.0)
+        got = y[mis_out: mis_out + n].reshape(rows, cols).astype(np.float64)
+        want = _softmax_ref(host.numpy().reshape(rows, cols), log=log)
+        if log:
+            assert np.all(np.abs(got - want) <= 4 * ulp(want) + 2.0 ** -20)
+        else:
+            assert np.all(np.abs(got - want) <= np.minimum(1e-6, 8 * ulp(want) + 1e-45))
+
+
+def test_softmax_window_kernels_match_fallback():
+    """A/B: the vector / window / long kernels against the three-pass fallback (TRN_ROWS_GENERIC=1) in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import os, numpy as np, trueno_b200 as trn
+rng = np.random.default_rng(7)
+for rows, cols in [(3, 77), (3, 5001), (2, 50257), (2, 128256), (2, 262147)]:
+    x = (rng.standard_normal((rows, cols)) * 4).astype(np.float32)
+    np.save(f"/tmp/_trn_sm_{cols}_{int(os.environ.get('TRN_ROWS_GENERIC', '0'))}.npy",
+            np.stack([trn.softmax_rows(x, rows, cols), trn.softmax_rows(x, rows, cols, log=True)]))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for flag in ("0", "1"):
+        env = dict(os.environ, TRN_ROWS_GENERIC=flag, PYTHONPATH=root)
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=root)
+    for cols in (77, 5001, 50257, 128256, 262147):
+        a = np.load(f"/tmp/_trn_sm_{cols}_0.npy").astype(np.float64)
+        b = np.load(f"/tmp/_trn_sm_{cols}_1.npy").astype(np.float64)
+        assert np.all(np.abs(a[0] - b[0]) <= np.minimum(2e-6, 16 * ulp(b[0]) + 1e-45))
+        assert np.all(np.abs(a[1] - b[1]) <= 8 * ulp(b[1]) + 2.0 ** -19)
 
 
 # ------------------------------------------------------------------------------------------------

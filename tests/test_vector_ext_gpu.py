@@ -164,7 +164,7 @@ def test_layer_norm_reference_tests_and_oracle(trn, oracle):
     assert e.value == E.SizeMismatch(3, 2)
     assert np.all(np.abs(V.from_slice([5] * 4).layer_norm(V.from_slice([1] * 4), V.from_slice([0] * 4), 1e-5).as_slice()) < 1e-3)
     rng = np.random.default_rng(12)
-    for n in (1, 5, 1000, 4097, 100_003):
+    for n in (1, 5, 1000, 4097, 8192, 8196, 12288, 16384, 16388, 100_003):
         x = (rng.standard_normal(n) * 3 + 1).astype(f32)
         g, b = rng.standard_normal(n).astype(f32), rng.standard_normal(n).astype(f32)
         got = V.from_slice(x).layer_norm(V.from_slice(g), V.from_slice(b), 1e-5).as_slice()

@@ -18,13 +18,24 @@
 //     current row's exp and store phases — HBM reads never stop, with no register cost.  6.0 TB/s (0.91).
 //   * cols <= 65536: a row spread over a thread-block CLUSTER (CS CTAs x 256 threads x VPT float4);
 //     row max and exp-sum are combined through distributed shared memory in a fixed rank order (4.7 TB/s).
-// Rows longer than that (or rows that are not 16-byte aligned) take the three-pass fallback kernel,
-// which re-reads the row from L2.  All reductions use fixed trees, so reruns are bit-identical.
+//   * cols > 65536 (LLM-vocabulary rows: 128 256, 151 936, 262 144 ...): the LONG kernel — a row spread over an
+//     8-CTA cluster, two passes: pass 1 streams the row from HBM keeping an online (max, sum) pair per thread
+//     (one rescale per 16 elements), the pairs are folded through the block and through distributed shared
+//     memory in a fixed order; pass 2 re-reads the row (an L2 hit: a row is a few MB at most against 126 MB)
+//     and writes the result.  HBM still sees one read and one write per element.
+//   * rows that are not 16-byte aligned (cols % 4 != 0: 77, 1001, 50 257 ...; or a base pointer that is only
+//     4-byte aligned): the same warp / CTA / cluster / long kernels in their WINDOW form — a row is addressed
+//     through the 16-byte-aligned window that contains it, interior vectors move as 128-bit accesses and only
+//     the (up to) two edge vectors of a row fall back to predicated scalar accesses; nothing outside the row
+//     is ever read or written.
+// Only input / output pointers whose misalignment differs take the three-pass fallback kernel (TRN_ROWS_GENERIC=1
+// forces it, for A/B tests).  All reductions use fixed trees, so reruns are bit-identical.
 // Math: accurate expf / logf; softmax scales by the correctly rounded reciprocal of the row sum
 // (<= 1 ulp from the reference's e / sum) — no fast-math intrinsics.
 //
 // Algorithmic bytes per element: 8 B (4 read + 4 written).  HBM-bound.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -55,10 +66,50 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_w) {
     return r;
 }
 
-// One cluster per row (grid-strided over rows).  cols % 4 == 0 and 16-byte aligned rows.
-template <int CS, int VPT, bool LOG>
+
+// A row seen as 128-bit vectors.  WIN = false: the row starts on a 16-byte boundary and cols % 4 == 0 (vector v is
+// elements 4v .. 4v+3).  WIN = true: the row starts `mis` elements (0..3) past a 16-byte boundary; vector v of the
+// aligned window covers elements 4v - mis .. 4v + 3 - mis.  Vectors that lie wholly inside the row move as one
+// 128-bit access; the first / last vector of a row may be partial and is handled element by element, so no byte
+// outside [row, row + cols) is touched.  Input and output share `mis` (checked by the dispatcher).
+template <bool WIN>
+struct RowView {
+    const float* src;
+    float* dst;
+    size_t cols;
+    int mis;
+    __device__ __forceinline__ RowView(const float* in, float* out, size_t row, size_t cols_, unsigned mis0)
+        : src(in + row * cols_), dst(out + row * cols_), cols(cols_),
+          mis(WIN ? (int)((mis0 + row * cols_) & 3u) : 0) {}
+    __device__ __forceinline__ size_t nvec() const { return WIN ? (cols + (size_t)mis + 3) >> 2 : cols >> 2; }
+    // caller guarantees v < nvec()
+    __device__ __forceinline__ float4 load(size_t v, float fill) const {
+        if (!WIN) return ld_stream(reinterpret_cast<const float4*>(src) + v);
+        const long long e0 = 4ll * (long long)v - mis;
+        if (e0 >= 0 && e0 + 4 <= (long long)cols) return ld_stream(reinterpret_cast<const float4*>(src + e0));
+        float4 r = make_float4(fill, fill, fill, fill);
+        if (e0 + 0 >= 0 && e0 + 0 < (long long)cols) r.x = ld_stream(src + e0 + 0);
+        if (e0 + 1 >= 0 && e0 + 1 < (long long)cols) r.y = ld_stream(src + e0 + 1);
+        if (e0 + 2 >= 0 && e0 + 2 < (long long)cols) r.z = ld_stream(src + e0 + 2);
+        if (e0 + 3 >= 0 && e0 + 3 < (long long)cols) r.w = ld_stream(src + e0 + 3);
+        return r;
+    }
+    __device__ __forceinline__ void store(size_t v, const float4& y) const {
+        if (!WIN) { st_stream(reinterpret_cast<float4*>(dst) + v, y); return; }
+        const long long e0 = 4ll * (long long)v - mis;
+        if (e0 >= 0 && e0 + 4 <= (long long)cols) { st_stream(reinterpret_cast<float4*>(dst + e0), y); return; }
+        if (e0 + 0 >= 0 && e0 + 0 < (long long)cols) st_stream(dst + e0 + 0, y.x);
+        if (e0 + 1 >= 0 && e0 + 1 < (long long)cols) st_stream(dst + e0 + 1, y.y);
+        if (e0 + 2 >= 0 && e0 + 2 < (long long)cols) st_stream(dst + e0 + 2, y.z);
+        if (e0 + 3 >= 0 && e0 + 3 < (long long)cols) st_stream(dst + e0 + 3, y.w);
+    }
+};
+
+// One cluster per row (grid-strided over rows); the row in the registers of the cluster.
+template <int CS, int VPT, bool LOG, bool WIN>
 __global__ void __launch_bounds__(kThreads)
-softmax_rows_cluster_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
+softmax_rows_cluster_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols,
+                            unsigned mis0) {
     __shared__ float s_w[kThreads / 32];
     __shared__ float s_stat[2];  // [0] CTA max, [1] CTA exp-sum — read by cluster peers through DSMEM
 
@@ -66,11 +117,10 @@ softmax_rows_cluster_kernel(const float* __restrict__ in, float* __restrict__ ou
     if (CS > 1) rank = cg::this_cluster().block_rank();
     const size_t cluster_id = blockIdx.x / CS;
     const size_t num_clusters = gridDim.x / CS;
-    const unsigned nvec = (unsigned)(cols >> 2);
 
     for (size_t row = cluster_id; row < rows; row += num_clusters) {
-        const float4* src = reinterpret_cast<const float4*>(in + row * cols);
-        float4* dst = reinterpret_cast<float4*>(out + row * cols);
+        const RowView<WIN> rv(in, out, row, cols, mis0);
+        const unsigned nvec = (unsigned)rv.nvec();
 
         // ---- load: VPT independent 128-bit loads per thread; chunk j of the row is split
         //      contiguously over the CS CTAs so every warp reads 512 contiguous bytes
@@ -78,7 +128,7 @@ softmax_rows_cluster_kernel(const float* __restrict__ in, float* __restrict__ ou
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
             const unsigned v = (j * CS + rank) * kThreads + threadIdx.x;
-            x[j] = v < nvec ? ld_stream(src + v) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            x[j] = v < nvec ? rv.load(v, -INFINITY) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
 
         // ---- row max
@@ -129,7 +179,7 @@ softmax_rows_cluster_kernel(const float* __restrict__ in, float* __restrict__ ou
                 } else {
                     y.x = x[j].x / sum; y.y = x[j].y / sum; y.z = x[j].z / sum; y.w = x[j].w / sum;
                 }
-                st_stream(dst + v, y);
+                rv.store(v, y);
             }
         }
         // peers must be done reading this CTA's s_stat before the next row overwrites it
@@ -163,19 +213,18 @@ __device__ __forceinline__ float block_sum_t(float v, float* s_w) {
     return r;
 }
 
-template <int T, int VPT, bool LOG>
+template <int T, int VPT, bool LOG, bool WIN>
 __global__ void __launch_bounds__(T)
-softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
+softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
     __shared__ float s_w[T / 32];
-    const unsigned nvec = (unsigned)(cols >> 2);
     const size_t row = blockIdx.x;
-    const float4* src = reinterpret_cast<const float4*>(in + row * cols);
-    float4* dst = reinterpret_cast<float4*>(out + row * cols);
+    const RowView<WIN> rv(in, out, row, cols, mis0);
+    const unsigned nvec = (unsigned)rv.nvec();
     float4 x[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
         const unsigned v = j * T + threadIdx.x;
-        x[j] = v < nvec ? ld_stream(src + v) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        x[j] = v < nvec ? rv.load(v, -INFINITY) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
     float m = -INFINITY;
 #pragma unroll
@@ -202,15 +251,15 @@ softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, s
             } else {
                 y.x = x[j].x * inv; y.y = x[j].y * inv; y.z = x[j].z * inv; y.w = x[j].w * inv;
             }
-            st_stream(dst + v, y);
+            rv.store(v, y);
         }
     }
 }
 
-template <int T, int VPT, bool LOG>
-static int launch_cta(const float* a, float* out, size_t rows, size_t cols, cudaStream_t s) {
+template <int T, int VPT, bool LOG, bool WIN>
+static int launch_cta(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, cudaStream_t s) {
     if (rows > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "%zu rows exceed the launch grid", rows);
-    softmax_rows_cta_kernel<T, VPT, LOG><<<(unsigned)rows, T, 0, s>>>(a, out, rows, cols);
+    softmax_rows_cta_kernel<T, VPT, LOG, WIN><<<(unsigned)rows, T, 0, s>>>(a, out, rows, cols, mis0);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -365,31 +414,33 @@ static int launch_ring(const float* a, float* out, size_t rows, size_t cols, int
 // (RPW * VPT = 8 independent 128-bit loads in flight per lane), all statistics are warp shuffles — no block
 // barrier at all — and a CTA of 8 warps moves 8 * RPW rows.  Flat grid.  MODE 0 softmax, 1 log_softmax,
 // 2 layer_norm (gamma / beta shared by all rows, src/vector.rs:1316-1362).
-template <int VPT, int MODE>
+template <int VPT, int MODE, bool WIN>
 __global__ void __launch_bounds__(kThreads)
 rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols,
-                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, unsigned mis0) {
+    static_assert(!(WIN && MODE == 2), "layer_norm has no window form");
     constexpr int RPW = 8 / VPT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned nvec = (unsigned)(cols >> 2);
     const size_t row0 = ((size_t)blockIdx.x * (kThreads / 32) + warp) * RPW;
     const float fill = MODE == 2 ? 0.f : -INFINITY;
     float4 x[RPW][VPT];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const size_t row = row0 + r;
-        const float4* src = reinterpret_cast<const float4*>(in + row * cols);
+        const RowView<WIN> rv(in, out, row < rows ? row : 0, cols, mis0);
+        const unsigned nvec = (unsigned)rv.nvec();
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
             const unsigned v = j * 32 + lane;
-            x[r][j] = (row < rows && v < nvec) ? ld_stream(src + v) : make_float4(fill, fill, fill, fill);
+            x[r][j] = (row < rows && v < nvec) ? rv.load(v, fill) : make_float4(fill, fill, fill, fill);
         }
     }
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const size_t row = row0 + r;
         if (row >= rows) break;   // warp-uniform
-        float4* dst = reinterpret_cast<float4*>(out + row * cols);
+        const RowView<WIN> rv(in, out, row, cols, mis0);
+        const unsigned nvec = (unsigned)rv.nvec();
         if (MODE == 2) {
             float part = 0.f;
 #pragma unroll
@@ -416,7 +467,7 @@ rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t r
                     y.y = __fadd_rn(__fmul_rn(__fmul_rn(g.y, __fsub_rn(x[r][j].y, mean)), inv_std), bt.y);
                     y.z = __fadd_rn(__fmul_rn(__fmul_rn(g.z, __fsub_rn(x[r][j].z, mean)), inv_std), bt.z);
                     y.w = __fadd_rn(__fmul_rn(__fmul_rn(g.w, __fsub_rn(x[r][j].w, mean)), inv_std), bt.w);
-                    st_stream(dst + v, y);
+                    rv.store(v, y);
                 }
             }
         } else {
@@ -446,38 +497,38 @@ rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t r
                     } else {
                         y.x = x[r][j].x * inv; y.y = x[r][j].y * inv; y.z = x[r][j].z * inv; y.w = x[r][j].w * inv;
                     }
-                    st_stream(dst + v, y);
+                    rv.store(v, y);
                 }
             }
         }
     }
 }
 
-template <int MODE>
+template <int MODE, bool WIN>
 static int launch_rows_warp(const float* a, float* out, size_t rows, size_t cols, const float* gamma, const float* beta,
-                            float eps, cudaStream_t s) {
-    const size_t nvec = cols / 4;
+                            float eps, unsigned mis0, cudaStream_t s) {
+    const size_t nvec = WIN ? (cols + 6) / 4 : cols / 4;   // window form: the longest window any row can need
     const int vpt = nvec <= 32 ? 1 : nvec <= 64 ? 2 : nvec <= 128 ? 4 : 8;
     const size_t rows_per_cta = (size_t)(kThreads / 32) * (8 / vpt);
     const size_t grid = (rows + rows_per_cta - 1) / rows_per_cta;
     if (grid > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "%zu rows exceed the launch grid", rows);
     switch (vpt) {
-        case 1: rows_warp_kernel<1, MODE><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps); break;
-        case 2: rows_warp_kernel<2, MODE><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps); break;
-        case 4: rows_warp_kernel<4, MODE><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps); break;
-        default: rows_warp_kernel<8, MODE><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps); break;
+        case 1: rows_warp_kernel<1, MODE, WIN><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps, mis0); break;
+        case 2: rows_warp_kernel<2, MODE, WIN><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps, mis0); break;
+        case 4: rows_warp_kernel<4, MODE, WIN><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps, mis0); break;
+        default: rows_warp_kernel<8, MODE, WIN><<<(unsigned)grid, kThreads, 0, s>>>(a, out, rows, cols, gamma, beta, eps, mis0); break;
     }
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
 }
 
-// layer_norm with the row in the registers of one CTA (1024 < cols <= 8192): one read, one write
-template <int VPT>
-__global__ void __launch_bounds__(kThreads)
+// layer_norm with the row in the registers of one CTA (1024 < cols <= 16384): one read, one write
+template <int T, int VPT>
+__global__ void __launch_bounds__(T)
 layer_norm_rows_reg_kernel(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
                            float eps, float* __restrict__ out, size_t rows, size_t cols) {
-    __shared__ float s_w[kThreads / 32];
+    __shared__ float s_w[T / 32];
     const unsigned nvec = (unsigned)(cols >> 2);
     for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const float4* src = reinterpret_cast<const float4*>(in + row * cols);
@@ -485,26 +536,26 @@ layer_norm_rows_reg_kernel(const float* __restrict__ in, const float* __restrict
         float4 x[VPT];
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
-            const unsigned v = j * kThreads + threadIdx.x;
+            const unsigned v = j * T + threadIdx.x;
             x[j] = v < nvec ? ld_stream(src + v) : make_float4(0, 0, 0, 0);
         }
         float part = 0.f;
 #pragma unroll
         for (int j = 0; j < VPT; ++j) part += (x[j].x + x[j].y) + (x[j].z + x[j].w);
-        const float mean = block_sum_256(part, s_w) / (float)cols;
+        const float mean = block_sum_t<T>(part, s_w) / (float)cols;
         part = 0.f;
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
-            if (j * kThreads + threadIdx.x < nvec) {
+            if (j * T + threadIdx.x < nvec) {
                 const float a = __fsub_rn(x[j].x, mean), b = __fsub_rn(x[j].y, mean);
                 const float c = __fsub_rn(x[j].z, mean), d = __fsub_rn(x[j].w, mean);
                 part += (__fmul_rn(a, a) + __fmul_rn(b, b)) + (__fmul_rn(c, c) + __fmul_rn(d, d));
             }
         }
-        const float inv_std = 1.0f / sqrtf(block_sum_256(part, s_w) / (float)cols + eps);
+        const float inv_std = 1.0f / sqrtf(block_sum_t<T>(part, s_w) / (float)cols + eps);
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
-            const unsigned v = j * kThreads + threadIdx.x;
+            const unsigned v = j * T + threadIdx.x;
             if (v < nvec) {
                 const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
                 const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
@@ -517,6 +568,239 @@ layer_norm_rows_reg_kernel(const float* __restrict__ in, const float* __restrict
             }
         }
     }
+}
+
+// ---- LONG rows: a row over an 8-CTA cluster, two passes, online (max, sum) ---------------------------------
+// cols > 65 536 (or any length in the window form).  Pass 1: every thread walks its share of the row in steps of
+// U independent 128-bit loads and keeps a running (m, s) pair, s = sum of exp(x - m) over what it has seen;
+// a step costs one rescale exp(m_old - m_new) per 16 elements.  The pairs fold to one (M, S) per CTA through a
+// fixed block tree and to the row's (M, S) through distributed shared memory in rank order -> deterministic.
+// Pass 2 re-reads the row (L2) and writes exp(x - M) / S or (x - M) - ln S, the reference's expressions
+// (src/vector.rs:1540-1553, :1605-1623).  An all -inf prefix keeps s = 0 (reference: exp(-inf - max) = 0); an
+// all -inf ROW gives NaN as the reference does (x - max = -inf - -inf).
+template <int CS, bool LOG, bool WIN>
+__global__ void __launch_bounds__(kThreads)
+softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
+    constexpr int U = 4;
+    __shared__ float s_w[kThreads / 32];
+    __shared__ float s_stat[2];  // [0] CTA max, [1] CTA exp-sum relative to it — read by cluster peers through DSMEM
+
+    unsigned rank = 0;
+    if (CS > 1) rank = cg::this_cluster().block_rank();
+    const size_t cluster_id = blockIdx.x / CS;
+    const size_t num_clusters = gridDim.x / CS;
+    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+
+    for (size_t row = cluster_id; row < rows; row += num_clusters) {
+        const RowView<WIN> rv(in, out, row, cols, mis0);
+        const size_t nvec = rv.nvec();
+        const size_t step = (size_t)CS * kThreads * U;   // vectors the cluster consumes per step
+
+        // ---- pass 1: online (max, sum)
+        float m = -INFINITY, s = 0.f;
+        for (size_t base = 0; base < nvec; base += step) {
+            float4 x[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
+                x[j] = v < nvec ? rv.load(v, -INFINITY) : ninf4;
+            }
+            float tm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < U; ++j) tm = fmaxf(tm, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+            const float mn = fmaxf(m, tm);
+            const float ref = mn == -INFINITY ? 0.f : mn;   // nothing finite seen yet: every term is exp(-inf) = 0
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                acc += (expf(x[j].x - ref) + expf(x[j].y - ref)) + (expf(x[j].z - ref) + expf(x[j].w - ref));
+            s = s * expf(m - ref) + acc;
+            m = mn;
+        }
+
+        // ---- fold the pairs: block tree, then the cluster in rank order
+        float M = block_max_256(m, s_w);
+        {
+            const float ref = M == -INFINITY ? 0.f : M;
+            s = s * expf(m - ref);
+        }
+        float S = block_sum_256(s, s_w);
+        if (CS > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (threadIdx.x == 0) { s_stat[0] = M; s_stat[1] = S; }
+            cluster.sync();
+            float pm[CS], ps[CS];
+#pragma unroll
+            for (int p = 0; p < CS; ++p) {
+                pm[p] = *cluster.map_shared_rank(&s_stat[0], p);
+                ps[p] = *cluster.map_shared_rank(&s_stat[1], p);
+            }
+            float gm = pm[0];
+#pragma unroll
+            for (int p = 1; p < CS; ++p) gm = fmaxf(gm, pm[p]);
+            const float ref = gm == -INFINITY ? 0.f : gm;
+            float gs = 0.f;
+#pragma unroll
+            for (int p = 0; p < CS; ++p) gs += ps[p] * expf(pm[p] - ref);
+            M = gm;
+            S = gs;
+        }
+
+        // ---- pass 2: re-read (L2), normalise, store
+        const float lse = LOG ? logf(S) : 0.f;
+        const float inv = LOG ? 0.f : __frcp_rn(S);
+        for (size_t base = 0; base < nvec; base += step) {
+            float4 x[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
+                x[j] = v < nvec ? rv.load(v, -INFINITY) : ninf4;
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
+                if (v < nvec) {
+                    float4 y;
+                    if (LOG) {  // (x - max) - ln(sum), evaluated in that order (src/vector.rs:1617-1621)
+                        y.x = (x[j].x - M) - lse; y.y = (x[j].y - M) - lse;
+                        y.z = (x[j].z - M) - lse; y.w = (x[j].w - M) - lse;
+                    } else {
+                        y.x = expf(x[j].x - M) * inv; y.y = expf(x[j].y - M) * inv;
+                        y.z = expf(x[j].z - M) * inv; y.w = expf(x[j].w - M) * inv;
+                    }
+                    rv.store(v, y);
+                }
+            }
+        }
+        // peers must be done reading this CTA's s_stat before the next row overwrites it
+        if (CS > 1) cg::this_cluster().sync();
+    }
+}
+
+// ---- FEW long rows (Vector::softmax on one large vector): a row split over many CTAs, two launches ---------
+// With fewer rows than SM-eighths the cluster kernel above would leave most of the machine idle (one 4 GiB vector =
+// one cluster = 8 SMs).  Here every row is cut into P segments, grid (P, rows): launch 1 folds each segment to an
+// online (max, sum) pair in the workspace; launch 2 has every CTA fold its row's P pairs in a fixed tree (so all
+// CTAs of a row get the same bits), then re-reads its own segment (L2 when the row fits) and writes the result.
+template <bool WIN>
+__device__ __forceinline__ void online_segment(const RowView<WIN>& rv, size_t v0, size_t v1, float& m_out, float& s_out) {
+    constexpr int U = 4;
+    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float m = -INFINITY, s = 0.f;
+    for (size_t base = v0; base < v1; base += (size_t)kThreads * U) {
+        float4 x[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const size_t v = base + (size_t)j * kThreads + threadIdx.x;
+            x[j] = v < v1 ? rv.load(v, -INFINITY) : ninf4;
+        }
+        float tm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < U; ++j) tm = fmaxf(tm, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+        const float mn = fmaxf(m, tm);
+        const float ref = mn == -INFINITY ? 0.f : mn;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            acc += (expf(x[j].x - ref) + expf(x[j].y - ref)) + (expf(x[j].z - ref) + expf(x[j].w - ref));
+        s = s * expf(m - ref) + acc;
+        m = mn;
+    }
+    m_out = m;
+    s_out = s;
+}
+
+template <bool WIN>
+__global__ void __launch_bounds__(kThreads)
+softmax_split_stats_kernel(const float* __restrict__ in, size_t rows, size_t cols, unsigned mis0, size_t seg,
+                           float2* __restrict__ ws) {
+    __shared__ float s_w[kThreads / 32];
+    const size_t row = blockIdx.y;
+    const RowView<WIN> rv(in, nullptr, row, cols, mis0);
+    const size_t nvec = rv.nvec();
+    const size_t v0 = (size_t)blockIdx.x * seg;
+    const size_t v1 = v0 + seg < nvec ? v0 + seg : nvec;
+    float m, s;
+    online_segment<WIN>(rv, v0 < nvec ? v0 : nvec, v1, m, s);
+    const float M = block_max_256(m, s_w);
+    const float ref = M == -INFINITY ? 0.f : M;
+    const float S = block_sum_256(s * expf(m - ref), s_w);
+    if (threadIdx.x == 0) ws[row * gridDim.x + blockIdx.x] = make_float2(M, S);
+}
+
+template <bool LOG, bool WIN>
+__global__ void __launch_bounds__(kThreads)
+softmax_split_write_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0,
+                           size_t seg, const float2* __restrict__ ws) {
+    constexpr int U = 4;
+    __shared__ float s_w[kThreads / 32];
+    const size_t row = blockIdx.y;
+    const unsigned P = gridDim.x;
+    // the row's (M, S) from its P segment pairs: thread t folds pairs t, t + 256, ... in order, then fixed block trees
+    float m = -INFINITY, s = 0.f;
+    for (unsigned p = threadIdx.x; p < P; p += kThreads) {
+        const float2 q = ws[row * P + p];
+        const float mn = fmaxf(m, q.x);
+        const float ref = mn == -INFINITY ? 0.f : mn;
+        s = s * expf(m - ref) + q.y * expf(q.x - ref);
+        m = mn;
+    }
+    const float M = block_max_256(m, s_w);
+    const float ref = M == -INFINITY ? 0.f : M;
+    const float S = block_sum_256(s * expf(m - ref), s_w);
+
+    const RowView<WIN> rv(in, out, row, cols, mis0);
+    const size_t nvec = rv.nvec();
+    const size_t v0 = (size_t)blockIdx.x * seg;
+    const size_t v1 = v0 + seg < nvec ? v0 + seg : nvec;
+    const float lse = LOG ? logf(S) : 0.f;
+    const float inv = LOG ? 0.f : __frcp_rn(S);
+    for (size_t base = v0; base < v1; base += (size_t)kThreads * U) {
+        float4 x[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const size_t v = base + (size_t)j * kThreads + threadIdx.x;
+            x[j] = v < v1 ? rv.load(v, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const size_t v = base + (size_t)j * kThreads + threadIdx.x;
+            if (v < v1) {
+                float4 y;
+                if (LOG) {
+                    y.x = (x[j].x - M) - lse; y.y = (x[j].y - M) - lse;
+                    y.z = (x[j].z - M) - lse; y.w = (x[j].w - M) - lse;
+                } else {
+                    y.x = expf(x[j].x - M) * inv; y.y = expf(x[j].y - M) * inv;
+                    y.z = expf(x[j].z - M) * inv; y.w = expf(x[j].w - M) * inv;
+                }
+                rv.store(v, y);
+            }
+        }
+    }
+}
+
+template <bool LOG, bool WIN>
+static int launch_split(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, int sm_count, cudaStream_t s) {
+    const size_t nvec = WIN ? (cols + 6) / 4 : cols / 4;
+    const size_t unit = (size_t)kThreads * 4;                 // vectors one CTA consumes per loop step
+    size_t P = (nvec + 2 * unit - 1) / (2 * unit);            // at least two steps per segment
+    const size_t cap = (size_t)sm_count * 8 / rows;           // ~8 resident CTAs per SM over all rows
+    if (P > cap) P = cap;
+    if (P < 1) P = 1;
+    if (P > 65535 * 16) P = 65535 * 16;
+    const size_t seg = ((nvec + P - 1) / P + unit - 1) / unit * unit;   // whole loop steps -> aligned segment starts
+    P = (nvec + seg - 1) / seg;
+    float2* ws = nullptr;
+    TRN_TRY(scratch_alloc(reinterpret_cast<void**>(&ws), rows * P * sizeof(float2), s));
+    const dim3 grid((unsigned)P, (unsigned)rows);
+    softmax_split_stats_kernel<WIN><<<grid, kThreads, 0, s>>>(a, rows, cols, mis0, seg, ws);
+    softmax_split_write_kernel<LOG, WIN><<<grid, kThreads, 0, s>>>(a, out, rows, cols, mis0, seg, ws);
+    count_launch(2);
+    const cudaError_t e = cudaGetLastError();
+    TRN_TRY(scratch_free(ws, s));
+    TRN_CUDA(e);
+    return TRN_OK;
 }
 
 // Fallback: any cols / alignment.  One CTA per row, three passes (max, exp-sum, write); passes 2
@@ -546,46 +830,65 @@ softmax_rows_generic_kernel(const float* __restrict__ in, float* __restrict__ ou
     }
 }
 
-template <int CS, int VPT, bool LOG>
-static int launch_cluster(const float* a, float* out, size_t rows, size_t cols, int sm_count, cudaStream_t s) {
+template <typename K>
+static int launch_clustered(K kernel, int cs, const float* a, float* out, size_t rows, size_t cols, unsigned mis0,
+                            cudaStream_t s) {
     // flat grid, one row per cluster — measured faster than a capped persistent grid (3.9 -> 4.7 TB/s at 65 536
     // columns) for the same reason as the map kernels
-    (void)sm_count;
-    size_t want = (size_t)0x7FFFFFFF / CS;
+    size_t want = (size_t)0x7FFFFFFF / cs;
     size_t clusters = rows < want ? rows : want;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * CS));
+    cfg.gridDim = dim3((unsigned)(clusters * cs));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.x = cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TRN_CUDA(cudaLaunchKernelEx(&cfg, softmax_rows_cluster_kernel<CS, VPT, LOG>, a, out, rows, cols));
+    TRN_CUDA(cudaLaunchKernelEx(&cfg, kernel, a, out, rows, cols, mis0));
     count_launch();
     return TRN_OK;
 }
 
+static bool force_generic() {
+    static const bool v = [] { const char* e = getenv("TRN_ROWS_GENERIC"); return e && e[0] == '1'; }();
+    return v;
+}
+
+template <bool LOG, bool WIN>
+static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, int sm_count, cudaStream_t s) {
+    // vectors per row: exact when aligned, the longest window any row can need otherwise
+    const size_t nvec = WIN ? (cols + 6) / 4 : cols / 4;
+    // smallest configuration whose register slots hold the row (see the file header)
+    if (nvec <= kThreads * 1)      return launch_rows_warp<LOG ? 1 : 0, WIN>(a, out, rows, cols, nullptr, nullptr, 0.f, mis0, s);
+    if (nvec <= kThreads * 2)      return launch_cta<256, 2, LOG, WIN>(a, out, rows, cols, mis0, s);
+    if (nvec <= kThreads * 4)      return launch_cta<256, 4, LOG, WIN>(a, out, rows, cols, mis0, s);
+    if (nvec <= kThreads * 8)      return launch_cta<256, 8, LOG, WIN>(a, out, rows, cols, mis0, s);
+    if (nvec <= 512 * 8)           return launch_cta<512, 8, LOG, WIN>(a, out, rows, cols, mis0, s);
+    // (a 1024-thread CTA holding a 32 000-float row measured 4.9 TB/s against the ring kernel's 6.0: one CTA
+    //  per SM leaves nothing to overlap a row's load phase with)
+    if (!WIN && nvec <= (size_t)ring::kChunkVec * ring::kMaxChunks) return launch_ring<LOG>(a, out, rows, cols, sm_count, s);
+    if (nvec <= (size_t)kThreads * 8 * 8)   // <= 65536 (the window form also covers the ring kernel's range)
+        return launch_clustered(softmax_rows_cluster_kernel<8, 8, LOG, WIN>, 8, a, out, rows, cols, mis0, s);
+    if (rows * 8 <= (size_t)sm_count)   // too few rows to fill the machine with one cluster per row
+        return launch_split<LOG, WIN>(a, out, rows, cols, mis0, sm_count, s);
+    return launch_clustered(softmax_rows_long_kernel<8, LOG, WIN>, 8, a, out, rows, cols, mis0, s);
+}
+
 template <bool LOG>
 static int dispatch(const float* a, float* out, size_t rows, size_t cols, int sm_count, cudaStream_t s) {
-    const bool vec_ok = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-    const size_t nvec = cols / 4;
-    if (vec_ok && nvec <= (size_t)kThreads * 8 * 8) {
-        // smallest configuration whose register slots hold the row (see the file header)
-        if (nvec <= kThreads * 1)      return launch_rows_warp<LOG ? 1 : 0>(a, out, rows, cols, nullptr, nullptr, 0.f, s);
-        if (nvec <= kThreads * 2)      return launch_cta<256, 2, LOG>(a, out, rows, cols, s);
-        if (nvec <= kThreads * 4)      return launch_cta<256, 4, LOG>(a, out, rows, cols, s);
-        if (nvec <= kThreads * 8)      return launch_cta<256, 8, LOG>(a, out, rows, cols, s);
-        if (nvec <= 512 * 8)           return launch_cta<512, 8, LOG>(a, out, rows, cols, s);
-        // (a 1024-thread CTA holding a 32 000-float row measured 4.9 TB/s against the ring kernel's 6.0: one CTA
-        //  per SM leaves nothing to overlap a row's load phase with)
-        if (nvec <= (size_t)ring::kChunkVec * ring::kMaxChunks) return launch_ring<LOG>(a, out, rows, cols, sm_count, s);
-        return launch_cluster<8, 8, LOG>(a, out, rows, cols, sm_count, s);   // 32768 < cols <= 65536
+    // misalignment of the first row in elements; rows are addressable as 128-bit vectors (directly or through
+    // their aligned windows) when input and output share it
+    const unsigned mis_in = (unsigned)((reinterpret_cast<uintptr_t>(a) >> 2) & 3u);
+    const unsigned mis_out = (unsigned)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u);
+    const bool word_ok = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out)) & 3u) == 0;
+    if (word_ok && mis_in == mis_out && !force_generic()) {
+        if (cols % 4 == 0 && mis_in == 0) return dispatch_vec<LOG, false>(a, out, rows, cols, 0u, sm_count, s);
+        return dispatch_vec<LOG, true>(a, out, rows, cols, mis_in, sm_count, s);
     }
     size_t cap = (size_t)sm_count * 8;
     int grid = (int)(rows < cap ? rows : cap);
@@ -639,13 +942,14 @@ int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta
     const bool vec_ok = (cols % 4 == 0) && (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out) |
                                               reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15u) == 0);
     const size_t nvec = cols / 4;
-    if (vec_ok && nvec <= 256) return launch_rows_warp<2>(a, out, rows, cols, gamma, beta, eps, s);
-    if (vec_ok && nvec <= (size_t)kThreads * 8) {
+    if (vec_ok && nvec <= 256) return launch_rows_warp<2, false>(a, out, rows, cols, gamma, beta, eps, 0u, s);
+    if (vec_ok && nvec <= (size_t)512 * 8) {
         if (rows > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "%zu rows exceed the launch grid", rows);
         const unsigned grid = (unsigned)rows;   // flat: one row per CTA
-        if (nvec <= kThreads * 2)      layer_norm_rows_reg_kernel<2><<<grid, kThreads, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
-        else if (nvec <= kThreads * 4) layer_norm_rows_reg_kernel<4><<<grid, kThreads, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
-        else                           layer_norm_rows_reg_kernel<8><<<grid, kThreads, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
+        if (nvec <= kThreads * 2)      layer_norm_rows_reg_kernel<256, 2><<<grid, 256, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
+        else if (nvec <= kThreads * 4) layer_norm_rows_reg_kernel<256, 4><<<grid, 256, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
+        else if (nvec <= kThreads * 8) layer_norm_rows_reg_kernel<256, 8><<<grid, 256, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
+        else                           layer_norm_rows_reg_kernel<512, 8><<<grid, 512, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
         count_launch();
         TRN_CUDA(cudaGetLastError());
         return TRN_OK;
