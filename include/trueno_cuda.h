@@ -51,7 +51,7 @@ typedef enum trn_status {
     TRN_SIZE_MISMATCH = 1,       /* SizeMismatch { expected, actual } */
     TRN_INVALID_INPUT = 2,       /* InvalidInput(String) */
     TRN_EMPTY_VECTOR = 3,        /* EmptyVector */
-    TRN_DIVISION_BY_ZERO = 4,    /* DivisionByZero (unused by the hot path; kept for ABI completeness) */
+    TRN_DIVISION_BY_ZERO = 4,    /* DivisionByZero (zscore / minmax_normalize / correlation on constant vectors) */
     TRN_GPU_ERROR = 5,           /* GpuError(String) — any CUDA failure; never a fallback */
     TRN_UNSUPPORTED_BACKEND = 6  /* UnsupportedBackend(Backend) — not an sm_100 device */
 } trn_status;
@@ -257,6 +257,78 @@ TRN_API int trn_fma_f32_dev(const float* a, size_t na, const float* b, size_t nb
 TRN_API int trn_mean_f32(const float* a, size_t n, float* out);
 TRN_API int trn_variance_f32(const float* a, size_t n, float* out);
 TRN_API int trn_stddev_f32(const float* a, size_t n, float* out);
+
+/* ---- the rest of Vector's element-wise / statistics API (widening past SURVEY.md 8f) ----------
+ * Vector methods the reference implements as scalar closures over the host buffer (src/vector.rs), some with GpuDevice
+ * hooks (leaky_relu / elu / clip: src/backends/gpu/device.rs).  Same conventions as above.  Error contract per op as in
+ * src/vector.rs: hardswish / mish / selu / leaky_relu / elu on an empty vector -> TRN_EMPTY_VECTOR; leaky_relu with a
+ * slope outside [0, 1) -> TRN_INVALID_INPUT("negative_slope must be in [0.0, 1.0), got {}"); elu with alpha <= 0 ->
+ * TRN_INVALID_INPUT("alpha must be > 0, got {}"); clip with min > max -> TRN_INVALID_INPUT("min_val ({}) must be <=
+ * max_val ({})"); minimum / maximum / copysign / covariance / correlation -> TRN_SIZE_MISMATCH; zscore /
+ * minmax_normalize / correlation on a constant vector -> TRN_DIVISION_BY_ZERO.  neg, signum, trunc, fract, hardswish,
+ * leaky_relu, minimum, maximum, copysign, clip and minmax_normalize are bit-exact against the reference. */
+TRN_API int trn_neg_f32(const float* a, size_t n, float* out);   /* Vector::neg, src/vector.rs:4399 */
+TRN_API int trn_neg_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_signum_f32(const float* a, size_t n, float* out);   /* Vector::signum, src/vector.rs:4261 */
+TRN_API int trn_signum_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_trunc_f32(const float* a, size_t n, float* out);   /* Vector::trunc, src/vector.rs:4211 */
+TRN_API int trn_trunc_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_fract_f32(const float* a, size_t n, float* out);   /* Vector::fract, src/vector.rs:4237 */
+TRN_API int trn_fract_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_sinh_f32(const float* a, size_t n, float* out);   /* Vector::sinh, src/vector.rs:3885 */
+TRN_API int trn_sinh_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_cosh_f32(const float* a, size_t n, float* out);   /* Vector::cosh, src/vector.rs:3916 */
+TRN_API int trn_cosh_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_asin_f32(const float* a, size_t n, float* out);   /* Vector::asin, src/vector.rs:3761 */
+TRN_API int trn_asin_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_acos_f32(const float* a, size_t n, float* out);   /* Vector::acos, src/vector.rs:3807 */
+TRN_API int trn_acos_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_atan_f32(const float* a, size_t n, float* out);   /* Vector::atan, src/vector.rs:3855 */
+TRN_API int trn_atan_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_asinh_f32(const float* a, size_t n, float* out);   /* Vector::asinh, src/vector.rs:4059 */
+TRN_API int trn_asinh_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_acosh_f32(const float* a, size_t n, float* out);   /* Vector::acosh, src/vector.rs:4089 */
+TRN_API int trn_acosh_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_atanh_f32(const float* a, size_t n, float* out);   /* Vector::atanh, src/vector.rs:4111 */
+TRN_API int trn_atanh_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_hardswish_f32(const float* a, size_t n, float* out);   /* Vector::hardswish, src/vector.rs:2409 */
+TRN_API int trn_hardswish_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_mish_f32(const float* a, size_t n, float* out);   /* Vector::mish, src/vector.rs:2477 */
+TRN_API int trn_mish_f32_dev(const float* a, size_t n, float* out, void* stream);
+TRN_API int trn_selu_f32(const float* a, size_t n, float* out);   /* Vector::selu, src/vector.rs:2546 */
+TRN_API int trn_selu_f32_dev(const float* a, size_t n, float* out, void* stream);
+/* Vector::leaky_relu (src/vector.rs:1980; GpuDevice::leaky_relu): x > 0 ? x : negative_slope * x */
+TRN_API int trn_leaky_relu_f32(const float* a, size_t n, float negative_slope, float* out);
+TRN_API int trn_leaky_relu_f32_dev(const float* a, size_t n, float negative_slope, float* out, void* stream);
+/* Vector::elu (src/vector.rs:2085; GpuDevice::elu): x > 0 ? x : alpha * (exp(x) - 1) */
+TRN_API int trn_elu_f32(const float* a, size_t n, float alpha, float* out);
+TRN_API int trn_elu_f32_dev(const float* a, size_t n, float alpha, float* out, void* stream);
+/* Vector::pow (src/vector.rs:3342): powf(x, exponent) */
+TRN_API int trn_pow_f32(const float* a, size_t n, float exponent, float* out);
+TRN_API int trn_pow_f32_dev(const float* a, size_t n, float exponent, float* out, void* stream);
+/* Vector::clip (src/vector.rs:1448; GpuDevice::clip): x.max(min_val).min(max_val) */
+TRN_API int trn_clip_f32(const float* a, size_t n, float min_val, float max_val, float* out);
+TRN_API int trn_clip_f32_dev(const float* a, size_t n, float min_val, float max_val, float* out, void* stream);
+/* Vector::minimum / maximum / copysign (src/vector.rs:4328 / :4364 / :4292) */
+TRN_API int trn_minimum_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_minimum_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_maximum_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_maximum_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+TRN_API int trn_copysign_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_copysign_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream);
+/* out = (a - shift) * scale: the map half of zscore / minmax_normalize for device-resident callers */
+TRN_API int trn_affine_f32_dev(const float* a, size_t n, float shift, float scale, float* out, void* stream);
+/* Vector::sum_of_squares (src/vector.rs:898), covariance (:1063), correlation (:1119), zscore (:1180),
+ * minmax_normalize (:1248): one upload, reductions and map on the resident copy, scalars through the host as in
+ * the reference's own composition */
+TRN_API int trn_sum_of_squares_f32(const float* a, size_t n, float* out);
+TRN_API int trn_covariance_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_correlation_f32(const float* a, size_t na, const float* b, size_t nb, float* out);
+TRN_API int trn_zscore_f32(const float* a, size_t n, float* out);
+TRN_API int trn_minmax_normalize_f32(const float* a, size_t n, float* out);
+/* Vector::layer_norm_simple (src/vector.rs:1386): (x - mean) / sqrt(var + eps) per row, no gamma / beta */
+TRN_API int trn_layer_norm_simple_rows_f32(const float* a, float eps, float* out, size_t rows, size_t cols);
+TRN_API int trn_layer_norm_simple_rows_f32_dev(const float* a, float eps, float* out, size_t rows, size_t cols, void* stream);
 
 /* ---- device-resident op chaining --------------------------------------
  * The CUDA counterpart of GpuCommandBatch (src/backends/gpu/batch.rs:118-1019): queue uploads and ops, run

@@ -97,6 +97,10 @@ class Oracle:
         L.orc_scalar_map.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
         for name in ("scalar_sum_kahan", "scalar_norm_l1", "scalar_norm_linf"):
             f = getattr(L, "orc_" + name); f.restype = C.c_float; f.argtypes = [_f32p, C.c_size_t]
+        L.orc_vector_map.restype = None
+        L.orc_vector_map.argtypes = [C.c_int, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
+        L.orc_layer_norm_simple.restype = None
+        L.orc_layer_norm_simple.argtypes = [_f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
         L.orc_symmetric_eigen.restype = C.c_int
         L.orc_symmetric_eigen.argtypes = [_f32p, C.c_size_t, _f32p, _f32p]
         L.orc_convolve2d.restype = None
@@ -185,6 +189,75 @@ class Oracle:
         c = _f32(c) if c is not None else a
         out = np.empty(a.size, np.float32)
         self.lib.orc_scalar_map(self.MAP_OPS[op], _p(a), _p(b), _p(c), p0, p1, _p(out), a.size)
+        return out
+
+    # ---- the rest of Vector's element-wise / statistics API (scalar closures in src/vector.rs) ----
+    VMAP_OPS = {"neg": 0, "signum": 1, "trunc": 2, "fract": 3, "sinh": 4, "cosh": 5, "asin": 6, "acos": 7, "atan": 8,
+                "asinh": 9, "acosh": 10, "atanh": 11, "hardswish": 12, "mish": 13, "selu": 14, "leaky_relu": 15, "elu": 16,
+                "pow": 17, "clip": 18, "minimum": 19, "maximum": 20, "copysign": 21, "affine": 22}
+
+    def vector_map(self, op: str, a, b=None, p0: float = 0.0, p1: float = 0.0) -> np.ndarray:
+        a = _f32(a)
+        b = _f32(b) if b is not None else a
+        out = np.empty(a.size, np.float32)
+        self.lib.orc_vector_map(self.VMAP_OPS[op], _p(a), _p(b), p0, p1, _p(out), a.size)
+        return out
+
+    # statistics exactly as Vector composes them (src/vector.rs:898-1290) from its own sum / dot / min / max
+    def mean(self, a, backend=AVX2):
+        a = _f32(a)
+        if a.size == 0:
+            raise OracleError("EmptyVector", "Empty vector")
+        return np.float32(np.float32(self.sum(a, backend)) / np.float32(a.size))
+
+    def variance(self, a, backend=AVX2):   # src/vector.rs:983-1015: E[x^2] - mean^2
+        a = _f32(a)
+        m = self.mean(a, backend)
+        ex2 = np.float32(np.float32(self.dot(a, a, backend)) / np.float32(a.size))
+        return np.float32(ex2 - np.float32(m * m))
+
+    def stddev(self, a, backend=AVX2): return np.float32(np.sqrt(self.variance(a, backend)))
+
+    def covariance(self, a, b, backend=AVX2):   # :1063-1085
+        a, b = _f32(a), _f32(b)
+        if a.size == 0:
+            raise OracleError("EmptyVector", "Empty vector")
+        if a.size != b.size:
+            raise OracleError("SizeMismatch", f"Size mismatch: expected {a.size}, got {b.size}", a.size, b.size)
+        mx, my = self.mean(a, backend), self.mean(b, backend)
+        mxy = np.float32(np.float32(self.dot(a, b, backend)) / np.float32(a.size))
+        return np.float32(mxy - np.float32(mx * my))
+
+    def correlation(self, a, b, backend=AVX2):   # :1119-1135
+        cov = self.covariance(a, b, backend)
+        sx, sy = self.stddev(a, backend), self.stddev(b, backend)
+        if abs(sx) < 1e-10 or abs(sy) < 1e-10:
+            raise OracleError("DivisionByZero", "Division by zero")
+        return np.float32(min(max(np.float32(cov / np.float32(sx * sy)), np.float32(-1)), np.float32(1)))
+
+    def zscore(self, a, backend=AVX2):   # :1180-1203
+        a = _f32(a)
+        m, sd = self.mean(a, backend), self.stddev(a, backend)
+        if abs(sd) < 1e-10:
+            raise OracleError("DivisionByZero", "Division by zero")
+        return self.vector_map("affine", a, p0=float(m), p1=float(np.float32(1) / sd))
+
+    def minmax_normalize(self, a):   # :1248-1272
+        a = _f32(a)
+        if a.size == 0:
+            raise OracleError("EmptyVector", "Empty vector")
+        lo, hi = np.float32(self.min(a)), np.float32(self.max(a))
+        rng = np.float32(hi - lo)
+        if abs(rng) < 1e-10:
+            raise OracleError("DivisionByZero", "Division by zero")
+        return self.vector_map("affine", a, p0=float(lo), p1=float(np.float32(1) / rng))
+
+    def layer_norm_simple(self, a, eps, backend=AVX2):   # :1386-1412
+        a = _f32(a)
+        if a.size == 0:
+            raise OracleError("EmptyVector", "Empty vector")
+        out = np.empty(a.size, np.float32)
+        self.lib.orc_layer_norm_simple(_p(a), float(self.sum(a, backend)), eps, _p(out), a.size)
         return out
 
     def sum_kahan(self, a): a = _f32(a); return np.float32(self.lib.orc_scalar_sum_kahan(_p(a), a.size))

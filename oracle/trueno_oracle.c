@@ -791,6 +791,67 @@ ORC_API void orc_scalar_map(int op, const float* a, const float* b, const float*
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * The rest of Vector's element-wise / statistics API: the scalar closures in src/vector.rs, same operation
+ * order, libm (Rust std f32 methods) for transcendentals.  op codes are private to the oracle.
+ * Rust std semantics restated: f32::signum (+-1 by sign bit, NaN -> NaN), f32::fract = x - x.trunc(),
+ * f32::min / max (the non-NaN operand, like fminf / fmaxf), f32::copysign, f32::powf.
+ * f32::asinh / acosh / atanh are computed inside Rust std by formulas that vary between std versions (not under
+ * /root/reference); the oracle uses glibc's and the parity tests hold both sides to an ulp bound against f64.
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_vector_map(int op, const float* a, const float* b, float p0, float p1, float* out, size_t n) {
+    /* src/vector.rs:2546-2570: LAMBDA * ALPHA * (exp(x) - 1) parses as (LAMBDA * ALPHA) * (...), constants folded in f32 */
+    const float kLambda = 1.0507009873554804934193349852946f;
+    const float kAlpha = 1.6732632423543772848170429916717f;
+    const float kLA = kLambda * kAlpha;
+    for (size_t i = 0; i < n; ++i) {
+        const float x = a[i];
+        float r;
+        switch (op) {
+            case 0: r = -x; break;                                                    /* neg :4399 */
+            case 1: r = isnan(x) ? x : copysignf(1.0f, x); break;                     /* signum :4261 */
+            case 2: r = truncf(x); break;                                             /* trunc :4211 */
+            case 3: r = x - truncf(x); break;                                         /* fract :4237 */
+            case 4: r = sinhf(x); break;                                              /* :3885 */
+            case 5: r = coshf(x); break;                                              /* :3916 */
+            case 6: r = asinf(x); break;                                              /* :3761 */
+            case 7: r = acosf(x); break;                                              /* :3807 */
+            case 8: r = atanf(x); break;                                              /* :3855 */
+            case 9: r = asinhf(x); break;                                             /* :4059 */
+            case 10: r = acoshf(x); break;                                            /* :4089 */
+            case 11: r = atanhf(x); break;                                            /* :4111 */
+            case 12: r = x <= -3.0f ? 0.0f : (x >= 3.0f ? x : x * (x + 3.0f) / 6.0f); break;   /* hardswish :2409-2432 */
+            case 13:                                                                  /* mish :2477-2500 */
+                if (x < -20.0f) r = 0.0f;
+                else if (x > 20.0f) r = x;
+                else { float sp = logf(1.0f + expf(x)); r = x * tanhf(sp); }
+                break;
+            case 14: r = x > 0.0f ? kLambda * x : kLA * (expf(x) - 1.0f); break;      /* selu :2546-2570 */
+            case 15: r = x > 0.0f ? x : p0 * x; break;                                /* leaky_relu :2014-2019 */
+            case 16: r = x > 0.0f ? x : p0 * (expf(x) - 1.0f); break;                 /* elu :2118-2122 */
+            case 17: r = powf(x, p0); break;                                          /* pow :3342 */
+            case 18: r = fminf(fmaxf(x, p0), p1); break;                              /* clip :1475-1480 */
+            case 19: r = fminf(x, b[i]); break;                                       /* minimum :4328 */
+            case 20: r = fmaxf(x, b[i]); break;                                       /* maximum :4364 */
+            case 21: r = copysignf(x, b[i]); break;                                   /* copysign :4292 */
+            case 22: r = (x - p0) * p1; break;                                        /* (x - mean) * inv_std :1195-1200 */
+            default: r = x;
+        }
+        out[i] = r;
+    }
+}
+
+/* Vector::layer_norm_simple (src/vector.rs:1386-1412): mean = sum / n (`sum` is the caller's Vector::sum — passed in so
+ * the restatement can use the backend under test), sequential f32 variance, (x - mean) * inv_std */
+ORC_API void orc_layer_norm_simple(const float* x, float sum, float eps, float* y, size_t n) {
+    const float mean = sum / (float)n;
+    float var = 0.f;
+    for (size_t i = 0; i < n; ++i) { float d = x[i] - mean; var += d * d; }
+    var = var / (float)n;
+    const float inv_std = 1.0f / sqrtf(var + eps);
+    for (size_t i = 0; i < n; ++i) y[i] = (x[i] - mean) * inv_std;
+}
+
 /* scalar.rs:170-183 — Kahan-compensated sequential sum */
 ORC_API float orc_scalar_sum_kahan(const float* a, size_t n) {
     float sum = 0.f, c = 0.f;

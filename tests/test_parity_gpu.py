@@ -221,7 +221,7 @@ def test_softmax_rows_vs_oracle(trn, oracle, rows, cols):
     # (src/vector.rs:1548) drops every term below half an ulp of the running sum — measured 9.3e-5
     # relative at cols = 32 000 and 2.4e-4 at 200 003.  Ours (register tree / Kahan) stays within ulps.
     ref_noise = float(np.max(np.abs(want - truth) / np.maximum(truth, 1e-300))) + 1e-6
-    assert ref_noise < 1e-3
+    assert ref_noise < (1e-3 if cols <= 250_000 else 1e-2)
     assert np.all(np.abs(got - truth) <= np.minimum(1e-6, 8 * ulp(truth) + 1e-45))
     assert np.all(np.abs(got.astype(np.float64) - want) <= 1e-6 + ref_noise * want)
     assert np.max(np.abs(got.astype(np.float64).sum(1) - 1)) < 1e-5       # proptest: sums to 1 (src/vector.rs:13461)

@@ -36,6 +36,10 @@ _vp = C.c_void_p
 _UNARY_EXT = ("abs", "relu", "exp", "swish", "tanh", "sqrt", "recip", "ln", "log2", "log10", "sin", "cos", "tan",
               "floor", "ceil", "round")
 _REDUCE_EXT = ("sum_kahan", "norm_l1", "norm_linf", "mean", "variance", "stddev")
+# the rest of Vector's element-wise API (src/vector.rs:2409-4410)
+_UNARY_EXT2 = ("neg", "signum", "trunc", "fract", "sinh", "cosh", "asin", "acos", "atan", "asinh", "acosh", "atanh",
+               "hardswish", "mish", "selu")
+_BINARY_EXT2 = ("minimum", "maximum", "copysign")
 
 # name -> argtypes; every function returns int (trn_status) unless listed in _RESTYPES
 _SIGNATURES = {
@@ -81,6 +85,19 @@ _SIGNATURES = {
     **{f"trn_{n}_f32_dev": [_vp, _sz, _vp, _vp] for n in _UNARY_EXT},
     **{f"trn_{n}_f32": [_vp, _sz, _f32p] for n in _REDUCE_EXT},
     **{f"trn_{n}_f32_dev": [_vp, _sz, _vp, _vp] for n in _REDUCE_EXT[:3]},
+    **{f"trn_{n}_f32": [_vp, _sz, _vp] for n in _UNARY_EXT2},
+    **{f"trn_{n}_f32_dev": [_vp, _sz, _vp, _vp] for n in _UNARY_EXT2},
+    **{f"trn_{n}_f32": [_vp, _sz, _vp, _sz, _vp] for n in _BINARY_EXT2},
+    **{f"trn_{n}_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp] for n in _BINARY_EXT2},
+    **{f"trn_{n}_f32": [_vp, _sz, C.c_float, _vp] for n in ("leaky_relu", "elu", "pow")},
+    **{f"trn_{n}_f32_dev": [_vp, _sz, C.c_float, _vp, _vp] for n in ("leaky_relu", "elu", "pow")},
+    "trn_clip_f32": [_vp, _sz, C.c_float, C.c_float, _vp], "trn_clip_f32_dev": [_vp, _sz, C.c_float, C.c_float, _vp, _vp],
+    "trn_affine_f32_dev": [_vp, _sz, C.c_float, C.c_float, _vp, _vp],
+    "trn_sum_of_squares_f32": [_vp, _sz, _f32p],
+    "trn_covariance_f32": [_vp, _sz, _vp, _sz, _f32p], "trn_correlation_f32": [_vp, _sz, _vp, _sz, _f32p],
+    "trn_zscore_f32": [_vp, _sz, _vp], "trn_minmax_normalize_f32": [_vp, _sz, _vp],
+    "trn_layer_norm_simple_rows_f32": [_vp, C.c_float, _vp, _sz, _sz],
+    "trn_layer_norm_simple_rows_f32_dev": [_vp, C.c_float, _vp, _sz, _sz, _vp],
     "trn_sub_f32": [_vp, _sz, _vp, _sz, _vp], "trn_sub_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp],
     "trn_div_f32": [_vp, _sz, _vp, _sz, _vp], "trn_div_f32_dev": [_vp, _sz, _vp, _sz, _vp, _vp],
     "trn_scale_f32": [_vp, _sz, C.c_float, _vp], "trn_scale_f32_dev": [_vp, _sz, C.c_float, _vp, _vp],
@@ -369,6 +386,36 @@ class Vector:
         check(lib.trn_fma_f32(_ptr(self.data), self.data.size, _ptr(b.data), b.data.size, _ptr(c.data), c.data.size, _ptr(out)))
         return Vector(out)
 
+    # ---- the rest of Vector's element-wise / statistics API (unary maps are installed below) ----
+    def _map1(self, fn, *params) -> "Vector":
+        out = np.empty(self.data.size, np.float32)
+        check(fn(_ptr(self.data), self.data.size, *params, _ptr(out)))
+        return Vector(out)
+
+    def leaky_relu(self, negative_slope: float): return self._map1(lib.trn_leaky_relu_f32, negative_slope)   # src/vector.rs:1980
+    def elu(self, alpha: float): return self._map1(lib.trn_elu_f32, alpha)                                   # :2085
+    def pow(self, n: float): return self._map1(lib.trn_pow_f32, n)                                           # :3342
+    def clip(self, min_val: float, max_val: float): return self._map1(lib.trn_clip_f32, min_val, max_val)    # :1448
+    def minimum(self, other): return self._binary(lib.trn_minimum_f32, other)                                # :4328
+    def maximum(self, other): return self._binary(lib.trn_maximum_f32, other)                                # :4364
+    def copysign(self, sign): return self._binary(lib.trn_copysign_f32, sign)                                # :4292
+    def zscore(self): return self._map(lib.trn_zscore_f32)                                                   # :1180
+    def minmax_normalize(self): return self._map(lib.trn_minmax_normalize_f32)                               # :1248
+    def sum_of_squares(self): return self._reduce(lib.trn_sum_of_squares_f32)                                # :898
+
+    def _reduce2(self, fn, other: "Vector") -> float:
+        out = C.c_float()
+        check(fn(_ptr(self.data), self.data.size, _ptr(other.data), other.data.size, C.byref(out)))
+        return float(np.float32(out.value))
+
+    def covariance(self, other): return self._reduce2(lib.trn_covariance_f32, other)                         # :1063
+    def correlation(self, other): return self._reduce2(lib.trn_correlation_f32, other)                       # :1119
+
+    def layer_norm_simple(self, eps: float) -> "Vector":                                                     # :1386
+        out = np.empty(self.data.size, np.float32)
+        check(lib.trn_layer_norm_simple_rows_f32(_ptr(self.data), eps, _ptr(out), 1, self.data.size))
+        return Vector(out)
+
     def sum_kahan(self): return self._reduce(lib.trn_sum_kahan_f32)
     def norm_l1(self): return self._reduce(lib.trn_norm_l1_f32)
     def norm_linf(self): return self._reduce(lib.trn_norm_linf_f32)
@@ -621,7 +668,7 @@ def _install_unary_maps():
         method.__name__ = name
         method.__doc__ = f"Vector::{name} (src/vector.rs) -> trn_{name}_f32"
         return method
-    for name in _UNARY_EXT:
+    for name in _UNARY_EXT + _UNARY_EXT2:
         setattr(Vector, name, make(name))
 
 

@@ -712,6 +712,115 @@ int trn_fma_f32(const float* a, size_t na, const float* b, size_t nb, const floa
     return host_map(Map::Fma, a, b, c, out, na);
 }
 
+// ===================== the rest of Vector's element-wise / statistics API (src/vector.rs) =====================
+// Validation per op follows src/vector.rs: hardswish / mish / selu / leaky_relu / elu on an empty vector -> EmptyVector
+// (:2410, :2478, :2547, :1981, :2086); the plain maps (neg ... atanh, pow, clip) return an empty result for an empty
+// input; minimum / maximum / copysign -> SizeMismatch (:4329, :4365, :4293).
+#define TRN_UNARY(NAME, OP, EMPTY_IS_ERROR)                                                              \
+    int trn_##NAME##_f32_dev(const float* a, size_t n, float* out, void* stream) {                       \
+        if (EMPTY_IS_ERROR) TRN_TRY(check_nonempty_emptyvec(n));                                         \
+        TRN_TRY(need_ctx());                                                                             \
+        return launch_map(Map::OP, a, nullptr, nullptr, out, n, 0.f, 0.f, resolve_stream(stream));       \
+    }                                                                                                    \
+    int trn_##NAME##_f32(const float* a, size_t n, float* out) {                                         \
+        if (EMPTY_IS_ERROR) TRN_TRY(check_nonempty_emptyvec(n));                                         \
+        TRN_TRY(need_ctx());                                                                             \
+        return host_map(Map::OP, a, nullptr, nullptr, out, n);                                           \
+    }
+TRN_UNARY(neg, Neg, false)
+TRN_UNARY(signum, Signum, false)
+TRN_UNARY(trunc, Trunc, false)
+TRN_UNARY(fract, Fract, false)
+TRN_UNARY(sinh, Sinh, false)
+TRN_UNARY(cosh, Cosh, false)
+TRN_UNARY(asin, Asin, false)
+TRN_UNARY(acos, Acos, false)
+TRN_UNARY(atan, Atan, false)
+TRN_UNARY(asinh, Asinh, false)
+TRN_UNARY(acosh, Acosh, false)
+TRN_UNARY(atanh, Atanh, false)
+TRN_UNARY(hardswish, Hardswish, true)
+TRN_UNARY(mish, Mish, true)
+TRN_UNARY(selu, Selu, true)
+#undef TRN_UNARY
+
+#define TRN_BINARY(NAME, OP)                                                                             \
+    int trn_##NAME##_f32_dev(const float* a, size_t na, const float* b, size_t nb, float* out, void* stream) { \
+        TRN_TRY(check_same_len(na, nb));                                                                 \
+        TRN_TRY(need_ctx());                                                                             \
+        return launch_map(Map::OP, a, b, nullptr, out, na, 0.f, 0.f, resolve_stream(stream));            \
+    }                                                                                                    \
+    int trn_##NAME##_f32(const float* a, size_t na, const float* b, size_t nb, float* out) {             \
+        TRN_TRY(check_same_len(na, nb));                                                                 \
+        TRN_TRY(need_ctx());                                                                             \
+        return host_map(Map::OP, a, b, nullptr, out, na);                                                \
+    }
+TRN_BINARY(minimum, Minimum)
+TRN_BINARY(maximum, Maximum)
+TRN_BINARY(copysign, Copysign)
+#undef TRN_BINARY
+
+static int check_leaky_relu(size_t n, float slope) {   // src/vector.rs:1981-1991
+    TRN_TRY(check_nonempty_emptyvec(n));
+    if (!(slope >= 0.0f && slope < 1.0f))
+        return fail(TRN_INVALID_INPUT, "negative_slope must be in [0.0, 1.0), got %s", fmt_f32(slope).c_str());
+    return TRN_OK;
+}
+static int check_elu(size_t n, float alpha) {          // src/vector.rs:2086-2096
+    TRN_TRY(check_nonempty_emptyvec(n));
+    if (alpha <= 0.0f) return fail(TRN_INVALID_INPUT, "alpha must be > 0, got %s", fmt_f32(alpha).c_str());
+    return TRN_OK;
+}
+static int check_clip(float lo, float hi) {            // src/vector.rs:1449-1454
+    if (lo > hi)
+        return fail(TRN_INVALID_INPUT, "min_val (%s) must be <= max_val (%s)", fmt_f32(lo).c_str(), fmt_f32(hi).c_str());
+    return TRN_OK;
+}
+int trn_leaky_relu_f32_dev(const float* a, size_t n, float negative_slope, float* out, void* stream) {
+    TRN_TRY(check_leaky_relu(n, negative_slope));
+    TRN_TRY(need_ctx());
+    return launch_map(Map::LeakyRelu, a, nullptr, nullptr, out, n, negative_slope, 0.f, resolve_stream(stream));
+}
+int trn_leaky_relu_f32(const float* a, size_t n, float negative_slope, float* out) {
+    TRN_TRY(check_leaky_relu(n, negative_slope));
+    TRN_TRY(need_ctx());
+    return host_map(Map::LeakyRelu, a, nullptr, nullptr, out, n, negative_slope);
+}
+int trn_elu_f32_dev(const float* a, size_t n, float alpha, float* out, void* stream) {
+    TRN_TRY(check_elu(n, alpha));
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Elu, a, nullptr, nullptr, out, n, alpha, 0.f, resolve_stream(stream));
+}
+int trn_elu_f32(const float* a, size_t n, float alpha, float* out) {
+    TRN_TRY(check_elu(n, alpha));
+    TRN_TRY(need_ctx());
+    return host_map(Map::Elu, a, nullptr, nullptr, out, n, alpha);
+}
+int trn_pow_f32_dev(const float* a, size_t n, float exponent, float* out, void* stream) {
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Pow, a, nullptr, nullptr, out, n, exponent, 0.f, resolve_stream(stream));
+}
+int trn_pow_f32(const float* a, size_t n, float exponent, float* out) {
+    TRN_TRY(need_ctx());
+    return host_map(Map::Pow, a, nullptr, nullptr, out, n, exponent);
+}
+// Vector::clip (src/vector.rs:1448): x.max(min).min(max) — clamp's arithmetic, its own error text
+int trn_clip_f32_dev(const float* a, size_t n, float min_val, float max_val, float* out, void* stream) {
+    TRN_TRY(check_clip(min_val, max_val));
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Clamp, a, nullptr, nullptr, out, n, min_val, max_val, resolve_stream(stream));
+}
+int trn_clip_f32(const float* a, size_t n, float min_val, float max_val, float* out) {
+    TRN_TRY(check_clip(min_val, max_val));
+    TRN_TRY(need_ctx());
+    return host_map(Map::Clamp, a, nullptr, nullptr, out, n, min_val, max_val);
+}
+// out = (a - shift) * scale, the second half of zscore / minmax_normalize for device-resident callers
+int trn_affine_f32_dev(const float* a, size_t n, float shift, float scale, float* out, void* stream) {
+    TRN_TRY(need_ctx());
+    return launch_map(Map::Affine, a, nullptr, nullptr, out, n, shift, scale, resolve_stream(stream));
+}
+
 // ---- reductions: sum_kahan, norm_l1, norm_linf (empty -> 0, src/vector.rs:848, :2708, :2770) ----------------
 #define TRN_REDUCE(NAME, OP)                                                                             \
     int trn_##NAME##_f32_dev(const float* a, size_t n, float* out, void* stream) {                       \
@@ -764,6 +873,152 @@ int trn_stddev_f32(const float* a, size_t n, float* out) {
     TRN_TRY(host_moments(a, n, nullptr, &v));
     *out = sqrtf(v);
     return TRN_OK;
+}
+
+// ---- statistics composed in Vector itself (src/vector.rs:898-1290, :1386): ONE upload, the reductions and the
+//      map on the resident copy, one download.  Scalars come back to the host between the steps, as in the reference.
+namespace {
+struct Resident {          // a host vector uploaded once, with scalar reductions read back to the host
+    Context* c;
+    Workspace* w;
+    DevTemp d;
+    size_t n;
+    explicit Resident(Context* c_) : c(c_), w(workspace(c_->stream)), d(c_->stream), n(0) {}
+    int put(const float* a, size_t n_) {
+        if (!w) return fail(TRN_GPU_ERROR, "failed to allocate the reduction workspace");
+        n = n_;
+        TRN_TRY(d.alloc(n));
+        return upload(d.p, a, n, c->stream);
+    }
+    int scalar(float* out) {
+        TRN_CUDA(cudaMemcpyAsync(w->host_f32, w->scalar_f32, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        TRN_CUDA(cudaStreamSynchronize(c->stream));
+        *out = *w->host_f32;
+        return TRN_OK;
+    }
+    int reduce(Reduce op, const float* other, float* out) {
+        TRN_TRY(launch_reduce(op, d.p, other, n, w->scalar_f32, c->stream));
+        return scalar(out);
+    }
+    int extremum(int is_max, float* out) {
+        TRN_TRY(launch_argreduce(is_max, d.p, n, nullptr, w->scalar_f32, c->stream));
+        return scalar(out);
+    }
+    // mean = sum / n; variance = E[x^2] - mean^2 (src/vector.rs:935-1015)
+    int moments(float* mean, float* var) {
+        float sum = 0.f, sumsq = 0.f;
+        TRN_TRY(reduce(Reduce::Sum, nullptr, &sum));
+        const float m = sum / (float)n;
+        if (mean) *mean = m;
+        if (var) {
+            TRN_TRY(reduce(Reduce::SumSq, nullptr, &sumsq));
+            *var = sumsq / (float)n - m * m;
+        }
+        return TRN_OK;
+    }
+    int affine_out(float shift, float scale, float* out) {
+        DevTemp o(c->stream);
+        TRN_TRY(o.alloc(n));
+        TRN_TRY(launch_map(Map::Affine, d.p, nullptr, nullptr, o.p, n, shift, scale, c->stream));
+        return download(out, o.p, n, c->stream);
+    }
+};
+}  // namespace
+
+// Vector::sum_of_squares (src/vector.rs:898): dot(self, self); empty -> 0
+int trn_sum_of_squares_f32(const float* a, size_t n, float* out) {
+    TRN_TRY(need_ctx());
+    if (n == 0) { *out = 0.f; return TRN_OK; }
+    TRN_HOST_LOCK();
+    Resident x(ctx());
+    TRN_TRY(x.put(a, n));
+    return x.reduce(Reduce::SumSq, nullptr, out);
+}
+// Vector::covariance (src/vector.rs:1063): E[xy] - mean_x * mean_y; empty -> EmptyVector, then SizeMismatch
+static int covariance_resident(Resident& x, Resident& y, float* out) {
+    float mx = 0.f, my = 0.f, dot = 0.f;
+    TRN_TRY(x.moments(&mx, nullptr));
+    TRN_TRY(y.moments(&my, nullptr));
+    TRN_TRY(x.reduce(Reduce::Dot, y.d.p, &dot));
+    *out = dot / (float)x.n - mx * my;
+    return TRN_OK;
+}
+int trn_covariance_f32(const float* a, size_t na, const float* b, size_t nb, float* out) {
+    TRN_TRY(check_nonempty_emptyvec(na));
+    TRN_TRY(check_same_len(na, nb));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Resident x(ctx()), y(ctx());
+    TRN_TRY(x.put(a, na));
+    TRN_TRY(y.put(b, nb));
+    return covariance_resident(x, y, out);
+}
+// Vector::correlation (src/vector.rs:1119): cov / (std_x * std_y) clamped to [-1, 1]; |std| < 1e-10 -> DivisionByZero
+int trn_correlation_f32(const float* a, size_t na, const float* b, size_t nb, float* out) {
+    TRN_TRY(check_nonempty_emptyvec(na));
+    TRN_TRY(check_same_len(na, nb));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Resident x(ctx()), y(ctx());
+    TRN_TRY(x.put(a, na));
+    TRN_TRY(y.put(b, nb));
+    float cov = 0.f, vx = 0.f, vy = 0.f;
+    TRN_TRY(covariance_resident(x, y, &cov));
+    TRN_TRY(x.moments(nullptr, &vx));
+    TRN_TRY(y.moments(nullptr, &vy));
+    const float sx = sqrtf(vx), sy = sqrtf(vy);
+    if (fabsf(sx) < 1e-10f || fabsf(sy) < 1e-10f) return fail(TRN_DIVISION_BY_ZERO, "Division by zero");
+    const float corr = cov / (sx * sy);
+    *out = fminf(fmaxf(corr, -1.0f), 1.0f);
+    return TRN_OK;
+}
+// Vector::zscore (src/vector.rs:1180): (x - mean) * (1 / stddev); empty -> EmptyVector; |stddev| < 1e-10 -> DivisionByZero
+int trn_zscore_f32(const float* a, size_t n, float* out) {
+    TRN_TRY(check_nonempty_emptyvec(n));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Resident x(ctx());
+    TRN_TRY(x.put(a, n));
+    float mean = 0.f, var = 0.f;
+    TRN_TRY(x.moments(&mean, &var));
+    const float sd = sqrtf(var);
+    if (fabsf(sd) < 1e-10f) return fail(TRN_DIVISION_BY_ZERO, "Division by zero");
+    return x.affine_out(mean, 1.0f / sd, out);
+}
+// Vector::minmax_normalize (src/vector.rs:1248): (x - min) * (1 / (max - min)); |range| < 1e-10 -> DivisionByZero.
+// min / max are exact and the map is two rounded operations -> bit-exact against the reference.
+int trn_minmax_normalize_f32(const float* a, size_t n, float* out) {
+    TRN_TRY(check_nonempty_emptyvec(n));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Resident x(ctx());
+    TRN_TRY(x.put(a, n));
+    float lo = 0.f, hi = 0.f;
+    TRN_TRY(x.extremum(0, &lo));
+    TRN_TRY(x.extremum(1, &hi));
+    const float range = hi - lo;
+    if (fabsf(range) < 1e-10f) return fail(TRN_DIVISION_BY_ZERO, "Division by zero");
+    return x.affine_out(lo, 1.0f / range, out);
+}
+// Vector::layer_norm_simple (src/vector.rs:1386): layer_norm without gamma / beta: (x - mean) * inv_std with
+// variance = sum((x - mean)^2) / n — the row kernels with gamma == beta == nullptr
+int trn_layer_norm_simple_rows_f32_dev(const float* a, float eps, float* out, size_t rows, size_t cols, void* stream) {
+    TRN_TRY(check_nonempty_emptyvec(rows * cols));
+    TRN_TRY(need_ctx());
+    return launch_layer_norm_rows(a, nullptr, nullptr, eps, out, rows, cols, resolve_stream(stream));
+}
+int trn_layer_norm_simple_rows_f32(const float* a, float eps, float* out, size_t rows, size_t cols) {
+    TRN_TRY(check_nonempty_emptyvec(rows * cols));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Context* c = ctx();
+    const size_t n = rows * cols;
+    DevTemp da(c->stream), dout(c->stream);
+    TRN_TRY(da.alloc(n));
+    TRN_TRY(dout.alloc(n));
+    TRN_TRY(upload(da.p, a, n, c->stream));
+    TRN_TRY(launch_layer_norm_rows(da.p, nullptr, nullptr, eps, dout.p, rows, cols, c->stream));
+    return download(out, dout.p, n, c->stream);
 }
 
 // ===================== callers next to the path =====================

@@ -95,9 +95,13 @@ int launch_arg_combine(const trn_arg_pair* pairs, size_t count, int is_max, uint
                        cudaStream_t s);
 
 enum class Map { Add, Sub, Mul, Div, Scale, Abs, Clamp, Lerp, Fma, Relu, Exp, Sigmoid, Gelu, Swish, Tanh, Sqrt, Recip,
-                 Ln, Log2, Log10, Sin, Cos, Tan, Floor, Ceil, Round };
+                 Ln, Log2, Log10, Sin, Cos, Tan, Floor, Ceil, Round,
+                 // the rest of Vector's element-wise API (src/vector.rs:1448-4410)
+                 Neg, Signum, Trunc, Fract, Sinh, Cosh, Asin, Acos, Atan, Asinh, Acosh, Atanh, Hardswish, Mish, Selu,
+                 LeakyRelu, Elu, Pow, Minimum, Maximum, Copysign, Affine };
 // out[i] = op(a[i], b[i], c[i]; p0, p1): b / c are read only by binary / ternary ops, p0 / p1 only by scale
-// (p0 = scalar), clamp (p0 = min, p1 = max) and lerp (p0 = t)
+// (p0 = scalar), clamp (p0 = min, p1 = max), lerp (p0 = t), leaky_relu (p0 = slope), elu (p0 = alpha), pow (p0 = n)
+// and affine (out = (a - p0) * p1: zscore / minmax_normalize)
 int launch_map(Map op, const float* a, const float* b, const float* c, float* out, size_t n, float p0, float p1,
                cudaStream_t s);
 

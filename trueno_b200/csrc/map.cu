@@ -1,4 +1,6 @@
-// map.cu — elementwise kernels: the whole `VectorBackend` map surface (src/backends/mod.rs:52-385).
+// map.cu — elementwise kernels: the whole `VectorBackend` map surface (src/backends/mod.rs:52-385) and the rest of
+// Vector's element-wise API (neg ... atanh, hardswish, mish, selu, leaky_relu, elu, pow, minimum, maximum, copysign;
+// scalar closures in src/vector.rs:1448-4410).
 //
 // Replaces Avx2Backend::{add,sub,mul,div,scale,abs,clamp,lerp,fma,relu,exp,sigmoid,gelu,swish,tanh,sqrt,
 // recip,ln,log2,log10,sin,cos,tan,floor,ceil,round} (src/backends/avx2.rs) with the SEMANTICS of the scalar
@@ -23,7 +25,8 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 2;   // float4 per thread per input: 8 KiB tiles
 
 __host__ __device__ constexpr int map_arity(Map op) {
-    return (op == Map::Add || op == Map::Sub || op == Map::Mul || op == Map::Div || op == Map::Lerp) ? 2
+    return (op == Map::Add || op == Map::Sub || op == Map::Mul || op == Map::Div || op == Map::Lerp ||
+            op == Map::Minimum || op == Map::Maximum || op == Map::Copysign) ? 2
            : op == Map::Fma ? 3 : 1;
 }
 
@@ -71,6 +74,41 @@ __device__ __forceinline__ float apply(float x, float y, float z, float p0, floa
         case Map::Floor: return floorf(x);
         case Map::Ceil: return ceilf(x);
         case Map::Round: return roundf(x);                                // half away from zero == f32::round
+        // ---- the rest of Vector's element-wise API: scalar closures in src/vector.rs, Rust f32 semantics
+        case Map::Neg: return -x;                                         // :4399 (sign flip, NaN payload kept)
+        case Map::Signum: return x != x ? x : copysignf(1.0f, x);         // :4261 f32::signum: +-1 by sign bit, NaN -> NaN
+        case Map::Trunc: return truncf(x);                                // :4211
+        case Map::Fract: return __fsub_rn(x, truncf(x));                  // :4237 f32::fract = x - x.trunc()
+        case Map::Sinh: return sinhf(x);                                  // :3885
+        case Map::Cosh: return coshf(x);                                  // :3916
+        case Map::Asin: return asinf(x);                                  // :3761
+        case Map::Acos: return acosf(x);                                  // :3807
+        case Map::Atan: return atanf(x);                                  // :3855
+        case Map::Asinh: return asinhf(x);                                // :4059
+        case Map::Acosh: return acoshf(x);                                // :4089
+        case Map::Atanh: return atanhf(x);                                // :4111
+        case Map::Hardswish: {                                            // :2409-2432, x*(x+3)/6 unfused -> bit-exact
+            const float mid = __fdiv_rn(__fmul_rn(x, __fadd_rn(x, 3.0f)), 6.0f);
+            return x <= -3.0f ? 0.0f : (x >= 3.0f ? x : mid);
+        }
+        case Map::Mish: {                                                 // :2477-2500: x * tanh(ln(1 + e^x)), cut-offs +-20
+            const float sp = logf(__fadd_rn(1.0f, expf(x)));
+            const float r = __fmul_rn(x, tanhf(sp));
+            return x < -20.0f ? 0.0f : (x > 20.0f ? x : r);
+        }
+        case Map::Selu: {                                                 // :2546-2570; LAMBDA * ALPHA folds to one f32 constant
+            constexpr float kLambda = 1.0507009873554804934193349852946f;
+            constexpr float kAlpha = 1.6732632423543772848170429916717f;
+            constexpr float kLA = kLambda * kAlpha;
+            return x > 0.0f ? __fmul_rn(kLambda, x) : __fmul_rn(kLA, __fsub_rn(expf(x), 1.0f));
+        }
+        case Map::LeakyRelu: return x > 0.0f ? x : __fmul_rn(p0, x);      // :2014-2019 -> bit-exact
+        case Map::Elu: return x > 0.0f ? x : __fmul_rn(p0, __fsub_rn(expf(x), 1.0f));   // :2118-2122
+        case Map::Pow: return powf(x, p0);                                // :3342
+        case Map::Minimum: return fminf(x, y);                            // :4328 f32::min: the non-NaN operand
+        case Map::Maximum: return fmaxf(x, y);                            // :4364
+        case Map::Copysign: return copysignf(x, y);                       // :4292
+        case Map::Affine: return __fmul_rn(__fsub_rn(x, p0), p1);         // (x - mean) * inv_std, :1195-1200, :1265-1270
     }
     return x;
 }
@@ -161,6 +199,9 @@ int launch_map(Map op, const float* a, const float* b, const float* c3, float* o
         CASE(Add); CASE(Sub); CASE(Mul); CASE(Div); CASE(Scale); CASE(Abs); CASE(Clamp); CASE(Lerp); CASE(Fma);
         CASE(Relu); CASE(Exp); CASE(Sigmoid); CASE(Gelu); CASE(Swish); CASE(Tanh); CASE(Sqrt); CASE(Recip);
         CASE(Ln); CASE(Log2); CASE(Log10); CASE(Sin); CASE(Cos); CASE(Tan); CASE(Floor); CASE(Ceil); CASE(Round);
+        CASE(Neg); CASE(Signum); CASE(Trunc); CASE(Fract); CASE(Sinh); CASE(Cosh); CASE(Asin); CASE(Acos); CASE(Atan);
+        CASE(Asinh); CASE(Acosh); CASE(Atanh); CASE(Hardswish); CASE(Mish); CASE(Selu); CASE(LeakyRelu); CASE(Elu);
+        CASE(Pow); CASE(Minimum); CASE(Maximum); CASE(Copysign); CASE(Affine);
     }
 #undef CASE
     count_launch();

@@ -4,7 +4,7 @@
 // -> sum -> divide, i.e. 3 reads + 2 writes per element on the CPU, 4 dispatches with a host round
 // trip each in the wgpu path, src/backends/gpu/device.rs:956-971).
 //
-// Kernels, chosen by row length (cols % 4 == 0, 16-byte aligned rows); measured on B200 in scripts/sweep_rows.py:
+// Kernels, chosen by row length; measured on B200 in scripts/sweep_rows.py, scripts/sweep_rows_ext.py:
 //   * cols <= 1024: one WARP per row, 8 independent 128-bit loads in flight per lane, shuffle-only statistics,
 //     flat grid — 6.8 TB/s from 128 to 1024 columns (1.03 of the measured copy bandwidth).
 //   * 1024 < cols <= 16384: the row in the REGISTERS of one CTA (256 or 512 threads x up to 8 float4), one row
@@ -16,18 +16,16 @@
 //     max -> exp -> sum -> scale out of registers.  Because slots are released as soon as they are
 //     in registers, the next row's bulk copies (up to 224 KiB in flight per SM) run underneath the
 //     current row's exp and store phases — HBM reads never stop, with no register cost.  6.0 TB/s (0.91).
-//   * cols <= 65536: a row spread over a thread-block CLUSTER (CS CTAs x 256 threads x VPT float4);
-//     row max and exp-sum are combined through distributed shared memory in a fixed rank order (4.7 TB/s).
-//   * cols > 65536 (LLM-vocabulary rows: 128 256, 151 936, 262 144 ...): the LONG kernel — a row spread over an
-//     8-CTA cluster, two passes: pass 1 streams the row from HBM keeping an online (max, sum) pair per thread
-//     (one rescale per 16 elements), the pairs are folded through the block and through distributed shared
+//   * cols > 32768 (LLM-vocabulary rows: 50 257, 128 256, 151 936, 262 144 ...): the LONG kernel — a row spread
+//     over a 4- or 8-CTA cluster, two passes: pass 1 streams the row from HBM keeping an online (max, sum) pair per
+//     thread (one rescale per 16 elements), the pairs are folded through the block and through distributed shared
 //     memory in a fixed order; pass 2 re-reads the row (an L2 hit: a row is a few MB at most against 126 MB)
 //     and writes the result.  HBM still sees one read and one write per element.
+//   * a FEW long rows (one large Vector::softmax): every row split over many CTAs, two launches (segment pairs to
+//     a workspace, then fold + write) — the whole machine works on one vector.
 //   * rows that are not 16-byte aligned (cols % 4 != 0: 77, 1001, 50 257 ...; or a base pointer that is only
-//     4-byte aligned): the same warp / CTA / cluster / long kernels in their WINDOW form — a row is addressed
-//     through the 16-byte-aligned window that contains it, interior vectors move as 128-bit accesses and only
-//     the (up to) two edge vectors of a row fall back to predicated scalar accesses; nothing outside the row
-//     is ever read or written.
+//     4-byte aligned): the same kernels in their WINDOW form — the 16-byte aligned body of a row streams exactly
+//     as above and the up to 3 + 3 elements before / after it ride in six designated threads.
 // Only input / output pointers whose misalignment differs take the three-pass fallback kernel (TRN_ROWS_GENERIC=1
 // forces it, for A/B tests).  All reductions use fixed trees, so reruns are bit-identical.
 // Math: accurate expf / logf; softmax scales by the correctly rounded reciprocal of the row sum
@@ -67,129 +65,66 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_w) {
 }
 
 
-// A row seen as 128-bit vectors.  WIN = false: the row starts on a 16-byte boundary and cols % 4 == 0 (vector v is
-// elements 4v .. 4v+3).  WIN = true: the row starts `mis` elements (0..3) past a 16-byte boundary; vector v of the
-// aligned window covers elements 4v - mis .. 4v + 3 - mis.  Vectors that lie wholly inside the row move as one
-// 128-bit access; the first / last vector of a row may be partial and is handled element by element, so no byte
-// outside [row, row + cols) is touched.  Input and output share `mis` (checked by the dispatcher).
+// A row as a 16-byte aligned BODY of 128-bit vectors plus (WIN only) up to 3 + 3 edge elements.
+// WIN = false: the row starts on a 16-byte boundary and cols % 4 == 0 — the body is the row.  WIN = true: the row
+// starts `mis` elements (0..3) past a 16-byte boundary and / or cols % 4 != 0: the body starts at the first aligned
+// element, `head` = (4 - mis) & 3 elements precede it and `tail` = (cols - head) & 3 follow it.  Every kernel streams
+// the body exactly as in the aligned case and lets six designated threads carry one edge element each through the
+// same max / sum / normalise steps, so nothing outside [row, row + cols) is read or written and the body loop has no
+// per-vector tests.  Input and output share `mis` (checked by the dispatcher).
 template <bool WIN>
 struct RowView {
+    const float4* vsrc;
+    float4* vdst;
+    size_t nvec;           // body vectors
     const float* src;
     float* dst;
     size_t cols;
-    int mis;
+    unsigned head, tail;
     __device__ __forceinline__ RowView(const float* in, float* out, size_t row, size_t cols_, unsigned mis0)
-        : src(in + row * cols_), dst(out + row * cols_), cols(cols_),
-          mis(WIN ? (int)((mis0 + row * cols_) & 3u) : 0) {}
-    __device__ __forceinline__ size_t nvec() const { return WIN ? (cols + (size_t)mis + 3) >> 2 : cols >> 2; }
-    // caller guarantees v < nvec()
-    __device__ __forceinline__ float4 load(size_t v, float fill) const {
-        if (!WIN) return ld_stream(reinterpret_cast<const float4*>(src) + v);
-        const long long e0 = 4ll * (long long)v - mis;
-        if (e0 >= 0 && e0 + 4 <= (long long)cols) return ld_stream(reinterpret_cast<const float4*>(src + e0));
-        float4 r = make_float4(fill, fill, fill, fill);
-        if (e0 + 0 >= 0 && e0 + 0 < (long long)cols) r.x = ld_stream(src + e0 + 0);
-        if (e0 + 1 >= 0 && e0 + 1 < (long long)cols) r.y = ld_stream(src + e0 + 1);
-        if (e0 + 2 >= 0 && e0 + 2 < (long long)cols) r.z = ld_stream(src + e0 + 2);
-        if (e0 + 3 >= 0 && e0 + 3 < (long long)cols) r.w = ld_stream(src + e0 + 3);
+        : src(in + row * cols_), dst(out + row * cols_), cols(cols_) {
+        if (WIN) {
+            const unsigned mis = (unsigned)((mis0 + row * cols_) & 3u);
+            head = (4u - mis) & 3u;
+            if ((size_t)head > cols) head = (unsigned)cols;
+            nvec = (cols - head) >> 2;
+            tail = (unsigned)((cols - head) & 3u);
+        } else {
+            head = tail = 0;
+            nvec = cols >> 2;
+        }
+        vsrc = reinterpret_cast<const float4*>(src + head);
+        vdst = reinterpret_cast<float4*>(dst + head);
+    }
+    // edge element e (0 .. head + tail - 1) of the row; `fill` for every other e
+    __device__ __forceinline__ float edge_load(unsigned e, float fill) const {
+        if (!WIN) return fill;
+        float r = fill;
+        if (e < head) r = src[e];
+        else if (e < head + tail) r = src[cols - tail + (e - head)];
         return r;
     }
-    __device__ __forceinline__ void store(size_t v, const float4& y) const {
-        if (!WIN) { st_stream(reinterpret_cast<float4*>(dst) + v, y); return; }
-        const long long e0 = 4ll * (long long)v - mis;
-        if (e0 >= 0 && e0 + 4 <= (long long)cols) { st_stream(reinterpret_cast<float4*>(dst + e0), y); return; }
-        if (e0 + 0 >= 0 && e0 + 0 < (long long)cols) st_stream(dst + e0 + 0, y.x);
-        if (e0 + 1 >= 0 && e0 + 1 < (long long)cols) st_stream(dst + e0 + 1, y.y);
-        if (e0 + 2 >= 0 && e0 + 2 < (long long)cols) st_stream(dst + e0 + 2, y.z);
-        if (e0 + 3 >= 0 && e0 + 3 < (long long)cols) st_stream(dst + e0 + 3, y.w);
+    __device__ __forceinline__ void edge_store(unsigned e, float y) const {
+        if (!WIN) return;
+        if (e < head) dst[e] = y;
+        else if (e < head + tail) dst[cols - tail + (e - head)] = y;
     }
 };
 
-// One cluster per row (grid-strided over rows); the row in the registers of the cluster.
-template <int CS, int VPT, bool LOG, bool WIN>
-__global__ void __launch_bounds__(kThreads)
-softmax_rows_cluster_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols,
-                            unsigned mis0) {
-    __shared__ float s_w[kThreads / 32];
-    __shared__ float s_stat[2];  // [0] CTA max, [1] CTA exp-sum — read by cluster peers through DSMEM
-
-    unsigned rank = 0;
-    if (CS > 1) rank = cg::this_cluster().block_rank();
-    const size_t cluster_id = blockIdx.x / CS;
-    const size_t num_clusters = gridDim.x / CS;
-
-    for (size_t row = cluster_id; row < rows; row += num_clusters) {
-        const RowView<WIN> rv(in, out, row, cols, mis0);
-        const unsigned nvec = (unsigned)rv.nvec();
-
-        // ---- load: VPT independent 128-bit loads per thread; chunk j of the row is split
-        //      contiguously over the CS CTAs so every warp reads 512 contiguous bytes
-        float4 x[VPT];
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) {
-            const unsigned v = (j * CS + rank) * kThreads + threadIdx.x;
-            x[j] = v < nvec ? rv.load(v, -INFINITY) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
-
-        // ---- row max
-        float m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
-        m = block_max_256(m, s_w);
-        if (CS > 1) {
-            cg::cluster_group cluster = cg::this_cluster();
-            if (threadIdx.x == 0) s_stat[0] = m;
-            cluster.sync();
-            float r = *cluster.map_shared_rank(&s_stat[0], 0);
-#pragma unroll
-            for (int p = 1; p < CS; ++p) r = fmaxf(r, *cluster.map_shared_rank(&s_stat[0], p));
-            m = r;
-        }
-
-        // ---- exponentials and their sum.  Padding slots hold -inf -> expf(-inf) = 0 exactly.
-        float part = 0.f;
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) {
-            float4 e;
-            e.x = expf(x[j].x - m); e.y = expf(x[j].y - m); e.z = expf(x[j].z - m); e.w = expf(x[j].w - m);
-            part += (e.x + e.y) + (e.z + e.w);
-            if (!LOG) x[j] = e;
-        }
-        float sum = block_sum_256(part, s_w);
-        if (CS > 1) {
-            cg::cluster_group cluster = cg::this_cluster();
-            if (threadIdx.x == 0) s_stat[1] = sum;
-            cluster.sync();
-            float r = *cluster.map_shared_rank(&s_stat[1], 0);
-#pragma unroll
-            for (int p = 1; p < CS; ++p) r += *cluster.map_shared_rank(&s_stat[1], p);
-            sum = r;
-        }
-
-        // ---- normalise and store
-        const float lse = LOG ? logf(sum) : 0.f;
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) {
-            const unsigned v = (j * CS + rank) * kThreads + threadIdx.x;
-            if (v < nvec) {
-                float4 y;
-                if (LOG) {  // (x - max) - ln(sum), evaluated in that order (src/vector.rs:1617-1621)
-                    y.x = (x[j].x - m) - lse; y.y = (x[j].y - m) - lse;
-                    y.z = (x[j].z - m) - lse; y.w = (x[j].w - m) - lse;
-                } else {
-                    y.x = x[j].x / sum; y.y = x[j].y / sum; y.z = x[j].z / sum; y.w = x[j].w / sum;
-                }
-                rv.store(v, y);
-            }
-        }
-        // peers must be done reading this CTA's s_stat before the next row overwrites it
-        if (CS > 1) cg::this_cluster().sync();
+template <bool LOG>
+__device__ __forceinline__ float4 normalise4(const float4& x, float m, float lse, float inv) {
+    float4 y;
+    if (LOG) {  // (x - max) - ln(sum), evaluated in that order (src/vector.rs:1617-1621); x holds the inputs
+        y.x = (x.x - m) - lse; y.y = (x.y - m) - lse; y.z = (x.z - m) - lse; y.w = (x.w - m) - lse;
+    } else {    // x holds the exponentials
+        y.x = x.x * inv; y.y = x.y * inv; y.z = x.z * inv; y.w = x.w * inv;
     }
+    return y;
 }
 
 // ---- one row per CTA, row in registers, flat grid -------------------------------------------------------------
-// T threads x VPT float4 hold the row (T in {256, 512, 1024}); grid = rows.  The block scheduler keeps the SM's
-// load queue full across rows (several CTAs per SM for T = 256 / 512), statistics are two fixed block trees.
+// T threads x VPT float4 hold the row (T in {256, 512}); grid = rows.  The block scheduler keeps the SM's
+// load queue full across rows (several CTAs per SM), statistics are two fixed block trees.
 template <int T>
 __device__ __forceinline__ float block_max_t(float v, float* s_w) {
     v = warp_max(v);
@@ -219,14 +154,15 @@ softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, s
     __shared__ float s_w[T / 32];
     const size_t row = blockIdx.x;
     const RowView<WIN> rv(in, out, row, cols, mis0);
-    const unsigned nvec = (unsigned)rv.nvec();
+    const unsigned nvec = (unsigned)rv.nvec;
     float4 x[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
         const unsigned v = j * T + threadIdx.x;
-        x[j] = v < nvec ? rv.load(v, -INFINITY) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        x[j] = v < nvec ? ld_stream(rv.vsrc + v) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
-    float m = -INFINITY;
+    float xe = rv.edge_load(threadIdx.x, -INFINITY);
+    float m = xe;
 #pragma unroll
     for (int j = 0; j < VPT; ++j) m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
     m = block_max_t<T>(m, s_w);
@@ -238,22 +174,20 @@ softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, s
         part += (e.x + e.y) + (e.z + e.w);
         if (!LOG) x[j] = e;
     }
+    if (WIN) {
+        const float ee = expf(xe - m);
+        part += ee;
+        if (!LOG) xe = ee;
+    }
     const float sum = block_sum_t<T>(part, s_w);
     const float lse = LOG ? logf(sum) : 0.f;
     const float inv = LOG ? 0.f : __frcp_rn(sum);
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
         const unsigned v = j * T + threadIdx.x;
-        if (v < nvec) {
-            float4 y;
-            if (LOG) {
-                y.x = (x[j].x - m) - lse; y.y = (x[j].y - m) - lse; y.z = (x[j].z - m) - lse; y.w = (x[j].w - m) - lse;
-            } else {
-                y.x = x[j].x * inv; y.y = x[j].y * inv; y.z = x[j].z * inv; y.w = x[j].w * inv;
-            }
-            rv.store(v, y);
-        }
+        if (v < nvec) st_stream(rv.vdst + v, normalise4<LOG>(x[j], m, lse, inv));
     }
+    if (WIN) rv.edge_store(threadIdx.x, LOG ? (xe - m) - lse : xe * inv);
 }
 
 template <int T, int VPT, bool LOG, bool WIN>
@@ -276,9 +210,11 @@ constexpr int kSlots = 14;                      // 224 KiB ring
 constexpr uint32_t kSmemBytes = kSlots * kChunkBytes + 2 * kSlots * 8 + 2 * 16 * 4 + 128;
 }  // namespace ring
 
-template <bool LOG>
+// WIN: the producer bulk-copies the aligned body of each row; the (up to six) edge elements are read from global
+// memory by consumer threads 0..5.
+template <bool LOG, bool WIN>
 __global__ void __launch_bounds__(ring::kRingThreads, 1)
-softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
+softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
     using namespace ring;
     extern __shared__ uint8_t ring_smem_raw[];
     const uint32_t base = (smem_u32(ring_smem_raw) + 127u) & ~127u;
@@ -290,9 +226,6 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
     float* s_sum = s_max + 16;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned nvec = (unsigned)(cols >> 2);
-    const unsigned nchunks = (nvec + kChunkVec - 1) / kChunkVec;
-    const uint32_t row_bytes = nvec * 16u;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < (uint32_t)kSlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kConsumers / 32); }
@@ -305,7 +238,11 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
         if (elect_one()) {
             uint32_t slot = 0, phase = 0;
             for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
-                const char* src = reinterpret_cast<const char*>(in + row * cols);
+                const RowView<WIN> rv(in, out, row, cols, mis0);
+                const unsigned nvec = (unsigned)rv.nvec;
+                const unsigned nchunks = (nvec + kChunkVec - 1) / kChunkVec;
+                const uint32_t row_bytes = nvec * 16u;
+                const char* src = reinterpret_cast<const char*>(rv.vsrc);
                 for (unsigned j = 0; j < nchunks; ++j) {
                     mbar_wait(empty_bar(slot), phase ^ 1);
                     const uint32_t off = j * kChunkBytes;
@@ -323,6 +260,10 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
     const int t = threadIdx.x;
     uint32_t slot = 0, phase = 0;
     for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const RowView<WIN> rv(in, out, row, cols, mis0);
+        const unsigned nvec = (unsigned)rv.nvec;
+        const unsigned nchunks = (nvec + kChunkVec - 1) / kChunkVec;
+        float xe = rv.edge_load((unsigned)t, -INFINITY);
         float4 x[2 * kMaxChunks];
         // ---- ring -> registers; each slot goes back to the producer as soon as it has been read
 #pragma unroll
@@ -348,7 +289,7 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
         }
 
         // ---- row max: warp tree, then a fixed-order fold of the 16 warp values in every thread
-        float m = -INFINITY;
+        float m = xe;
 #pragma unroll
         for (int j = 0; j < 2 * kMaxChunks; ++j) m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
         m = warp_max(m);
@@ -367,43 +308,38 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
             part += (e.x + e.y) + (e.z + e.w);
             if (!LOG) x[j] = e;
         }
+        if (WIN) {
+            const float ee = expf(xe - m);
+            part += ee;
+            if (!LOG) xe = ee;
+        }
         part = warp_sum(part);
         if (lane == 0) s_sum[warp] = part;
         named_bar_sync(1, kConsumers);
         float sum = s_sum[0];
 #pragma unroll
         for (int w = 1; w < kConsumers / 32; ++w) sum += s_sum[w];
-        // (s_max is rewritten only after the next row's first barrier... no: after THIS barrier every
-        //  thread has read s_max; s_sum is rewritten after the next row's max barrier.)
+        // (after THIS barrier every thread has read s_max; s_sum is rewritten after the next row's max barrier.)
 
         // ---- scale and store straight from registers (512 contiguous bytes per warp per store)
         const float lse = LOG ? logf(sum) : 0.f;
         const float inv = LOG ? 0.f : __frcp_rn(sum);
-        float4* dst = reinterpret_cast<float4*>(out + row * cols);
 #pragma unroll
         for (int j = 0; j < 2 * kMaxChunks; ++j) {
             const unsigned v = (j >> 1) * kChunkVec + (j & 1) * kConsumers + t;
-            if (v < nvec) {
-                float4 y;
-                if (LOG) {  // (x - max) - ln(sum), evaluated in that order (src/vector.rs:1617-1621)
-                    y.x = (x[j].x - m) - lse; y.y = (x[j].y - m) - lse;
-                    y.z = (x[j].z - m) - lse; y.w = (x[j].w - m) - lse;
-                } else {
-                    y.x = x[j].x * inv; y.y = x[j].y * inv; y.z = x[j].z * inv; y.w = x[j].w * inv;
-                }
-                st_stream(dst + v, y);
-            }
+            if (v < nvec) st_stream(rv.vdst + v, normalise4<LOG>(x[j], m, lse, inv));
         }
+        if (WIN) rv.edge_store((unsigned)t, LOG ? (xe - m) - lse : xe * inv);
     }
 }
 
-template <bool LOG>
-static int launch_ring(const float* a, float* out, size_t rows, size_t cols, int sm_count, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <bool LOG, bool WIN>
+static int launch_ring(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, int sm_count, cudaStream_t s) {
+    static const cudaError_t attr = cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)ring::kSmemBytes);   // thread-safe, once
     TRN_CUDA(attr);
     const unsigned grid = (unsigned)(rows < (size_t)sm_count ? rows : (size_t)sm_count);
-    softmax_rows_ring_kernel<LOG><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols);
+    softmax_rows_ring_kernel<LOG, WIN><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols, mis0);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -413,7 +349,7 @@ static int launch_ring(const float* a, float* out, size_t rows, size_t cols, int
 // cols <= 1024 (attention-sized rows): a row is VPT float4 per lane, RPW rows per warp are loaded up front
 // (RPW * VPT = 8 independent 128-bit loads in flight per lane), all statistics are warp shuffles — no block
 // barrier at all — and a CTA of 8 warps moves 8 * RPW rows.  Flat grid.  MODE 0 softmax, 1 log_softmax,
-// 2 layer_norm (gamma / beta shared by all rows, src/vector.rs:1316-1362).
+// 2 layer_norm (gamma / beta shared by all rows, src/vector.rs:1316-1362; both null = layer_norm_simple, :1386).
 template <int VPT, int MODE, bool WIN>
 __global__ void __launch_bounds__(kThreads)
 rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols,
@@ -424,23 +360,25 @@ rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t r
     const size_t row0 = ((size_t)blockIdx.x * (kThreads / 32) + warp) * RPW;
     const float fill = MODE == 2 ? 0.f : -INFINITY;
     float4 x[RPW][VPT];
+    float xe[RPW];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const size_t row = row0 + r;
         const RowView<WIN> rv(in, out, row < rows ? row : 0, cols, mis0);
-        const unsigned nvec = (unsigned)rv.nvec();
+        const unsigned nvec = (unsigned)rv.nvec;
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
             const unsigned v = j * 32 + lane;
-            x[r][j] = (row < rows && v < nvec) ? rv.load(v, fill) : make_float4(fill, fill, fill, fill);
+            x[r][j] = (row < rows && v < nvec) ? ld_stream(rv.vsrc + v) : make_float4(fill, fill, fill, fill);
         }
+        xe[r] = (WIN && row < rows) ? rv.edge_load((unsigned)lane, fill) : fill;
     }
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const size_t row = row0 + r;
         if (row >= rows) break;   // warp-uniform
         const RowView<WIN> rv(in, out, row, cols, mis0);
-        const unsigned nvec = (unsigned)rv.nvec();
+        const unsigned nvec = (unsigned)rv.nvec;
         if (MODE == 2) {
             float part = 0.f;
 #pragma unroll
@@ -460,18 +398,25 @@ rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t r
             for (int j = 0; j < VPT; ++j) {
                 const unsigned v = j * 32 + lane;
                 if (v < nvec) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
-                    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
-                    float4 y;   // gamma * (x - mean) * inv_std + beta, evaluated in that order, unfused
-                    y.x = __fadd_rn(__fmul_rn(__fmul_rn(g.x, __fsub_rn(x[r][j].x, mean)), inv_std), bt.x);
-                    y.y = __fadd_rn(__fmul_rn(__fmul_rn(g.y, __fsub_rn(x[r][j].y, mean)), inv_std), bt.y);
-                    y.z = __fadd_rn(__fmul_rn(__fmul_rn(g.z, __fsub_rn(x[r][j].z, mean)), inv_std), bt.z);
-                    y.w = __fadd_rn(__fmul_rn(__fmul_rn(g.w, __fsub_rn(x[r][j].w, mean)), inv_std), bt.w);
-                    rv.store(v, y);
+                    float4 y;
+                    if (gamma) {   // gamma * (x - mean) * inv_std + beta, evaluated in that order, unfused
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+                        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
+                        y.x = __fadd_rn(__fmul_rn(__fmul_rn(g.x, __fsub_rn(x[r][j].x, mean)), inv_std), bt.x);
+                        y.y = __fadd_rn(__fmul_rn(__fmul_rn(g.y, __fsub_rn(x[r][j].y, mean)), inv_std), bt.y);
+                        y.z = __fadd_rn(__fmul_rn(__fmul_rn(g.z, __fsub_rn(x[r][j].z, mean)), inv_std), bt.z);
+                        y.w = __fadd_rn(__fmul_rn(__fmul_rn(g.w, __fsub_rn(x[r][j].w, mean)), inv_std), bt.w);
+                    } else {       // layer_norm_simple: (x - mean) * inv_std
+                        y.x = __fmul_rn(__fsub_rn(x[r][j].x, mean), inv_std);
+                        y.y = __fmul_rn(__fsub_rn(x[r][j].y, mean), inv_std);
+                        y.z = __fmul_rn(__fsub_rn(x[r][j].z, mean), inv_std);
+                        y.w = __fmul_rn(__fsub_rn(x[r][j].w, mean), inv_std);
+                    }
+                    st_stream(rv.vdst + v, y);
                 }
             }
         } else {
-            float m = -INFINITY;
+            float m = xe[r];
 #pragma unroll
             for (int j = 0; j < VPT; ++j) m = fmaxf(m, fmaxf(fmaxf(x[r][j].x, x[r][j].y), fmaxf(x[r][j].z, x[r][j].w)));
             m = warp_max(m);
@@ -483,23 +428,21 @@ rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t r
                 part += (e.x + e.y) + (e.z + e.w);
                 if (MODE == 0) x[r][j] = e;
             }
+            float xer = xe[r];
+            if (WIN) {
+                const float ee = expf(xer - m);
+                part += ee;
+                if (MODE == 0) xer = ee;
+            }
             const float sum = warp_sum(part);
             const float lse = MODE == 1 ? logf(sum) : 0.f;
             const float inv = MODE == 1 ? 0.f : __frcp_rn(sum);
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
                 const unsigned v = j * 32 + lane;
-                if (v < nvec) {
-                    float4 y;
-                    if (MODE == 1) {
-                        y.x = (x[r][j].x - m) - lse; y.y = (x[r][j].y - m) - lse;
-                        y.z = (x[r][j].z - m) - lse; y.w = (x[r][j].w - m) - lse;
-                    } else {
-                        y.x = x[r][j].x * inv; y.y = x[r][j].y * inv; y.z = x[r][j].z * inv; y.w = x[r][j].w * inv;
-                    }
-                    rv.store(v, y);
-                }
+                if (v < nvec) st_stream(rv.vdst + v, normalise4<MODE == 1>(x[r][j], m, lse, inv));
             }
+            if (WIN) rv.edge_store((unsigned)lane, MODE == 1 ? (xer - m) - lse : xer * inv);
         }
     }
 }
@@ -507,7 +450,7 @@ rows_warp_kernel(const float* __restrict__ in, float* __restrict__ out, size_t r
 template <int MODE, bool WIN>
 static int launch_rows_warp(const float* a, float* out, size_t rows, size_t cols, const float* gamma, const float* beta,
                             float eps, unsigned mis0, cudaStream_t s) {
-    const size_t nvec = WIN ? (cols + 6) / 4 : cols / 4;   // window form: the longest window any row can need
+    const size_t nvec = cols / 4;   // the body of a window row is never longer
     const int vpt = nvec <= 32 ? 1 : nvec <= 64 ? 2 : nvec <= 128 ? 4 : 8;
     const size_t rows_per_cta = (size_t)(kThreads / 32) * (8 / vpt);
     const size_t grid = (rows + rows_per_cta - 1) / rows_per_cta;
@@ -557,27 +500,71 @@ layer_norm_rows_reg_kernel(const float* __restrict__ in, const float* __restrict
         for (int j = 0; j < VPT; ++j) {
             const unsigned v = j * T + threadIdx.x;
             if (v < nvec) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
-                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
                 float4 y;
-                y.x = __fadd_rn(__fmul_rn(__fmul_rn(g.x, __fsub_rn(x[j].x, mean)), inv_std), bt.x);
-                y.y = __fadd_rn(__fmul_rn(__fmul_rn(g.y, __fsub_rn(x[j].y, mean)), inv_std), bt.y);
-                y.z = __fadd_rn(__fmul_rn(__fmul_rn(g.z, __fsub_rn(x[j].z, mean)), inv_std), bt.z);
-                y.w = __fadd_rn(__fmul_rn(__fmul_rn(g.w, __fsub_rn(x[j].w, mean)), inv_std), bt.w);
+                if (gamma) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+                    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
+                    y.x = __fadd_rn(__fmul_rn(__fmul_rn(g.x, __fsub_rn(x[j].x, mean)), inv_std), bt.x);
+                    y.y = __fadd_rn(__fmul_rn(__fmul_rn(g.y, __fsub_rn(x[j].y, mean)), inv_std), bt.y);
+                    y.z = __fadd_rn(__fmul_rn(__fmul_rn(g.z, __fsub_rn(x[j].z, mean)), inv_std), bt.z);
+                    y.w = __fadd_rn(__fmul_rn(__fmul_rn(g.w, __fsub_rn(x[j].w, mean)), inv_std), bt.w);
+                } else {
+                    y.x = __fmul_rn(__fsub_rn(x[j].x, mean), inv_std);
+                    y.y = __fmul_rn(__fsub_rn(x[j].y, mean), inv_std);
+                    y.z = __fmul_rn(__fsub_rn(x[j].z, mean), inv_std);
+                    y.w = __fmul_rn(__fsub_rn(x[j].w, mean), inv_std);
+                }
                 st_stream(dst + v, y);
             }
         }
     }
 }
 
-// ---- LONG rows: a row over an 8-CTA cluster, two passes, online (max, sum) ---------------------------------
-// cols > 65 536 (or any length in the window form).  Pass 1: every thread walks its share of the row in steps of
-// U independent 128-bit loads and keeps a running (m, s) pair, s = sum of exp(x - m) over what it has seen;
-// a step costs one rescale exp(m_old - m_new) per 16 elements.  The pairs fold to one (M, S) per CTA through a
-// fixed block tree and to the row's (M, S) through distributed shared memory in rank order -> deterministic.
-// Pass 2 re-reads the row (L2) and writes exp(x - M) / S or (x - M) - ln S, the reference's expressions
+// ---- LONG rows: a row over a CTA cluster, two passes, online (max, sum) -------------------------------------
+// cols > 32 768.  Pass 1: every thread walks its share of the row in steps of U independent 128-bit loads and keeps
+// a running (m, s) pair, s = sum of exp(x - m) over what it has seen; a step costs one rescale exp(m_old - m_new)
+// per 16 elements.  The pairs fold to one (M, S) per CTA through a fixed block tree and to the row's (M, S) through
+// distributed shared memory in rank order -> deterministic.  Pass 2 re-reads the row (L2: a row is a few MB at most
+// against 126 MB) and writes exp(x - M) / S or (x - M) - ln S, the reference's expressions
 // (src/vector.rs:1540-1553, :1605-1623).  An all -inf prefix keeps s = 0 (reference: exp(-inf - max) = 0); an
 // all -inf ROW gives NaN as the reference does (x - max = -inf - -inf).
+// Measured against a register-resident 8-CTA cluster kernel (one pass, the row in the registers of the cluster,
+// since removed): 40 000 columns 5.3 vs 3.3 TB/s, 65 536: 5.2 vs 4.7 (scripts/exp/exp_long_rows.py).
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+    const float mn = fmaxf(m, m2);
+    const float ref = mn == -INFINITY ? 0.f : mn;   // nothing finite seen yet: every term is exp(-inf) = 0
+    s = s * expf(m - ref) + s2 * expf(m2 - ref);
+    m = mn;
+}
+
+// online (max, sum) over body vectors [v0, v1) taken kThreads * U at a time with stride `stride` between a thread's
+// U vectors (callers interleave CTAs of a cluster through `first` / `stride`)
+template <int U>
+__device__ __forceinline__ void online_step(const float4 (&x)[U], float& m, float& s) {
+    float tm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < U; ++j) tm = fmaxf(tm, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+    const float mn = fmaxf(m, tm);
+    const float ref = mn == -INFINITY ? 0.f : mn;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+        acc += (expf(x[j].x - ref) + expf(x[j].y - ref)) + (expf(x[j].z - ref) + expf(x[j].w - ref));
+    s = s * expf(m - ref) + acc;
+    m = mn;
+}
+
+template <bool LOG>
+__device__ __forceinline__ float4 normalise_raw4(const float4& x, float M, float lse, float inv) {
+    float4 y;
+    if (LOG) {
+        y.x = (x.x - M) - lse; y.y = (x.y - M) - lse; y.z = (x.z - M) - lse; y.w = (x.w - M) - lse;
+    } else {
+        y.x = expf(x.x - M) * inv; y.y = expf(x.y - M) * inv; y.z = expf(x.z - M) * inv; y.w = expf(x.w - M) * inv;
+    }
+    return y;
+}
+
 template <int CS, bool LOG, bool WIN>
 __global__ void __launch_bounds__(kThreads)
 softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
@@ -593,30 +580,22 @@ softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, 
 
     for (size_t row = cluster_id; row < rows; row += num_clusters) {
         const RowView<WIN> rv(in, out, row, cols, mis0);
-        const size_t nvec = rv.nvec();
+        const size_t nvec = rv.nvec;
         const size_t step = (size_t)CS * kThreads * U;   // vectors the cluster consumes per step
 
-        // ---- pass 1: online (max, sum)
+        // ---- pass 1: online (max, sum); the edge elements ride in rank 0's threads 0..5
+        const float xe = (WIN && rank == 0) ? rv.edge_load(threadIdx.x, -INFINITY) : -INFINITY;
         float m = -INFINITY, s = 0.f;
         for (size_t base = 0; base < nvec; base += step) {
             float4 x[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
-                x[j] = v < nvec ? rv.load(v, -INFINITY) : ninf4;
+                x[j] = v < nvec ? ld_stream(rv.vsrc + v) : ninf4;
             }
-            float tm = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < U; ++j) tm = fmaxf(tm, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
-            const float mn = fmaxf(m, tm);
-            const float ref = mn == -INFINITY ? 0.f : mn;   // nothing finite seen yet: every term is exp(-inf) = 0
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < U; ++j)
-                acc += (expf(x[j].x - ref) + expf(x[j].y - ref)) + (expf(x[j].z - ref) + expf(x[j].w - ref));
-            s = s * expf(m - ref) + acc;
-            m = mn;
+            online_step<U>(x, m, s);
         }
+        if (WIN) online_merge(m, s, xe, xe == -INFINITY ? 0.f : 1.f);
 
         // ---- fold the pairs: block tree, then the cluster in rank order
         float M = block_max_256(m, s_w);
@@ -629,19 +608,10 @@ softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, 
             cg::cluster_group cluster = cg::this_cluster();
             if (threadIdx.x == 0) { s_stat[0] = M; s_stat[1] = S; }
             cluster.sync();
-            float pm[CS], ps[CS];
+            float gm = -INFINITY, gs = 0.f;
 #pragma unroll
-            for (int p = 0; p < CS; ++p) {
-                pm[p] = *cluster.map_shared_rank(&s_stat[0], p);
-                ps[p] = *cluster.map_shared_rank(&s_stat[1], p);
-            }
-            float gm = pm[0];
-#pragma unroll
-            for (int p = 1; p < CS; ++p) gm = fmaxf(gm, pm[p]);
-            const float ref = gm == -INFINITY ? 0.f : gm;
-            float gs = 0.f;
-#pragma unroll
-            for (int p = 0; p < CS; ++p) gs += ps[p] * expf(pm[p] - ref);
+            for (int p = 0; p < CS; ++p)
+                online_merge(gm, gs, *cluster.map_shared_rank(&s_stat[0], p), *cluster.map_shared_rank(&s_stat[1], p));
             M = gm;
             S = gs;
         }
@@ -654,24 +624,15 @@ softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, 
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
-                x[j] = v < nvec ? rv.load(v, -INFINITY) : ninf4;
+                x[j] = v < nvec ? ld_stream(rv.vsrc + v) : ninf4;
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
-                if (v < nvec) {
-                    float4 y;
-                    if (LOG) {  // (x - max) - ln(sum), evaluated in that order (src/vector.rs:1617-1621)
-                        y.x = (x[j].x - M) - lse; y.y = (x[j].y - M) - lse;
-                        y.z = (x[j].z - M) - lse; y.w = (x[j].w - M) - lse;
-                    } else {
-                        y.x = expf(x[j].x - M) * inv; y.y = expf(x[j].y - M) * inv;
-                        y.z = expf(x[j].z - M) * inv; y.w = expf(x[j].w - M) * inv;
-                    }
-                    rv.store(v, y);
-                }
+                if (v < nvec) st_stream(rv.vdst + v, normalise_raw4<LOG>(x[j], M, lse, inv));
             }
         }
+        if (WIN && rank == 0) rv.edge_store(threadIdx.x, LOG ? (xe - M) - lse : expf(xe - M) * inv);
         // peers must be done reading this CTA's s_stat before the next row overwrites it
         if (CS > 1) cg::this_cluster().sync();
     }
@@ -679,12 +640,19 @@ softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, 
 
 // ---- FEW long rows (Vector::softmax on one large vector): a row split over many CTAs, two launches ---------
 // With fewer rows than SM-eighths the cluster kernel above would leave most of the machine idle (one 4 GiB vector =
-// one cluster = 8 SMs).  Here every row is cut into P segments, grid (P, rows): launch 1 folds each segment to an
-// online (max, sum) pair in the workspace; launch 2 has every CTA fold its row's P pairs in a fixed tree (so all
-// CTAs of a row get the same bits), then re-reads its own segment (L2 when the row fits) and writes the result.
+// one cluster).  Here every row is cut into P segments, grid (P, rows): launch 1 folds each segment to an online
+// (max, sum) pair in the workspace; launch 2 has every CTA fold its row's P pairs in a fixed tree (so all CTAs of a
+// row get the same bits), then re-reads its own segment (L2 when the row fits) and writes the result.
 template <bool WIN>
-__device__ __forceinline__ void online_segment(const RowView<WIN>& rv, size_t v0, size_t v1, float& m_out, float& s_out) {
+__global__ void __launch_bounds__(kThreads)
+softmax_split_stats_kernel(const float* __restrict__ in, size_t rows, size_t cols, unsigned mis0, size_t seg,
+                           float2* __restrict__ ws) {
     constexpr int U = 4;
+    __shared__ float s_w[kThreads / 32];
+    const size_t row = blockIdx.y;
+    const RowView<WIN> rv(in, nullptr, row, cols, mis0);
+    const size_t v0 = (size_t)blockIdx.x * seg;
+    const size_t v1 = v0 + seg < rv.nvec ? v0 + seg : rv.nvec;
     const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     float m = -INFINITY, s = 0.f;
     for (size_t base = v0; base < v1; base += (size_t)kThreads * U) {
@@ -692,36 +660,14 @@ __device__ __forceinline__ void online_segment(const RowView<WIN>& rv, size_t v0
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const size_t v = base + (size_t)j * kThreads + threadIdx.x;
-            x[j] = v < v1 ? rv.load(v, -INFINITY) : ninf4;
+            x[j] = v < v1 ? ld_stream(rv.vsrc + v) : ninf4;
         }
-        float tm = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < U; ++j) tm = fmaxf(tm, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
-        const float mn = fmaxf(m, tm);
-        const float ref = mn == -INFINITY ? 0.f : mn;
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-            acc += (expf(x[j].x - ref) + expf(x[j].y - ref)) + (expf(x[j].z - ref) + expf(x[j].w - ref));
-        s = s * expf(m - ref) + acc;
-        m = mn;
+        online_step<U>(x, m, s);
     }
-    m_out = m;
-    s_out = s;
-}
-
-template <bool WIN>
-__global__ void __launch_bounds__(kThreads)
-softmax_split_stats_kernel(const float* __restrict__ in, size_t rows, size_t cols, unsigned mis0, size_t seg,
-                           float2* __restrict__ ws) {
-    __shared__ float s_w[kThreads / 32];
-    const size_t row = blockIdx.y;
-    const RowView<WIN> rv(in, nullptr, row, cols, mis0);
-    const size_t nvec = rv.nvec();
-    const size_t v0 = (size_t)blockIdx.x * seg;
-    const size_t v1 = v0 + seg < nvec ? v0 + seg : nvec;
-    float m, s;
-    online_segment<WIN>(rv, v0 < nvec ? v0 : nvec, v1, m, s);
+    if (WIN && blockIdx.x == 0) {   // the edge elements ride in segment 0's threads 0..5
+        const float xe = rv.edge_load(threadIdx.x, -INFINITY);
+        online_merge(m, s, xe, xe == -INFINITY ? 0.f : 1.f);
+    }
     const float M = block_max_256(m, s_w);
     const float ref = M == -INFINITY ? 0.f : M;
     const float S = block_sum_256(s * expf(m - ref), s_w);
@@ -740,19 +686,15 @@ softmax_split_write_kernel(const float* __restrict__ in, float* __restrict__ out
     float m = -INFINITY, s = 0.f;
     for (unsigned p = threadIdx.x; p < P; p += kThreads) {
         const float2 q = ws[row * P + p];
-        const float mn = fmaxf(m, q.x);
-        const float ref = mn == -INFINITY ? 0.f : mn;
-        s = s * expf(m - ref) + q.y * expf(q.x - ref);
-        m = mn;
+        online_merge(m, s, q.x, q.y);
     }
     const float M = block_max_256(m, s_w);
     const float ref = M == -INFINITY ? 0.f : M;
     const float S = block_sum_256(s * expf(m - ref), s_w);
 
     const RowView<WIN> rv(in, out, row, cols, mis0);
-    const size_t nvec = rv.nvec();
     const size_t v0 = (size_t)blockIdx.x * seg;
-    const size_t v1 = v0 + seg < nvec ? v0 + seg : nvec;
+    const size_t v1 = v0 + seg < rv.nvec ? v0 + seg : rv.nvec;
     const float lse = LOG ? logf(S) : 0.f;
     const float inv = LOG ? 0.f : __frcp_rn(S);
     for (size_t base = v0; base < v1; base += (size_t)kThreads * U) {
@@ -760,37 +702,31 @@ softmax_split_write_kernel(const float* __restrict__ in, float* __restrict__ out
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const size_t v = base + (size_t)j * kThreads + threadIdx.x;
-            x[j] = v < v1 ? rv.load(v, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[j] = v < v1 ? ld_stream(rv.vsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const size_t v = base + (size_t)j * kThreads + threadIdx.x;
-            if (v < v1) {
-                float4 y;
-                if (LOG) {
-                    y.x = (x[j].x - M) - lse; y.y = (x[j].y - M) - lse;
-                    y.z = (x[j].z - M) - lse; y.w = (x[j].w - M) - lse;
-                } else {
-                    y.x = expf(x[j].x - M) * inv; y.y = expf(x[j].y - M) * inv;
-                    y.z = expf(x[j].z - M) * inv; y.w = expf(x[j].w - M) * inv;
-                }
-                rv.store(v, y);
-            }
+            if (v < v1) st_stream(rv.vdst + v, normalise_raw4<LOG>(x[j], M, lse, inv));
         }
+    }
+    if (WIN && blockIdx.x == 0) {
+        const float xe = rv.edge_load(threadIdx.x, -INFINITY);
+        rv.edge_store(threadIdx.x, LOG ? (xe - M) - lse : expf(xe - M) * inv);
     }
 }
 
 template <bool LOG, bool WIN>
 static int launch_split(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, int sm_count, cudaStream_t s) {
-    const size_t nvec = WIN ? (cols + 6) / 4 : cols / 4;
+    const size_t nvec = cols / 4;                             // upper bound of a row's body
     const size_t unit = (size_t)kThreads * 4;                 // vectors one CTA consumes per loop step
     size_t P = (nvec + 2 * unit - 1) / (2 * unit);            // at least two steps per segment
     const size_t cap = (size_t)sm_count * 8 / rows;           // ~8 resident CTAs per SM over all rows
     if (P > cap) P = cap;
     if (P < 1) P = 1;
-    if (P > 65535 * 16) P = 65535 * 16;
     const size_t seg = ((nvec + P - 1) / P + unit - 1) / unit * unit;   // whole loop steps -> aligned segment starts
     P = (nvec + seg - 1) / seg;
+    if (P < 1) P = 1;
     float2* ws = nullptr;
     TRN_TRY(scratch_alloc(reinterpret_cast<void**>(&ws), rows * P * sizeof(float2), s));
     const dim3 grid((unsigned)P, (unsigned)rows);
@@ -803,8 +739,8 @@ static int launch_split(const float* a, float* out, size_t rows, size_t cols, un
     return TRN_OK;
 }
 
-// Fallback: any cols / alignment.  One CTA per row, three passes (max, exp-sum, write); passes 2
-// and 3 hit L2 for rows that fit there.
+// Fallback: input and output misaligned differently.  One CTA per row, three passes (max, exp-sum, write);
+// passes 2 and 3 hit L2 for rows that fit there.
 template <bool LOG>
 __global__ void __launch_bounds__(kThreads)
 softmax_rows_generic_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
@@ -833,8 +769,8 @@ softmax_rows_generic_kernel(const float* __restrict__ in, float* __restrict__ ou
 template <typename K>
 static int launch_clustered(K kernel, int cs, const float* a, float* out, size_t rows, size_t cols, unsigned mis0,
                             cudaStream_t s) {
-    // flat grid, one row per cluster — measured faster than a capped persistent grid (3.9 -> 4.7 TB/s at 65 536
-    // columns) for the same reason as the map kernels
+    // flat grid, one row per cluster — measured faster than a capped persistent grid for the same reason as the
+    // map kernels; capping the CTAs resident per SM (fewer rows in flight against L2) measured slower at every length
     size_t want = (size_t)0x7FFFFFFF / cs;
     size_t clusters = rows < want ? rows : want;
     cudaLaunchConfig_t cfg = {};
@@ -858,11 +794,24 @@ static bool force_generic() {
     static const bool v = [] { const char* e = getenv("TRN_ROWS_GENERIC"); return e && e[0] == '1'; }();
     return v;
 }
+static int env_int(const char* name) {   // tuning knob for scripts/exp/exp_long_rows.py; 0 = unset
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
+template <bool LOG, bool WIN>
+static int launch_long(int cs, const float* a, float* out, size_t rows, size_t cols, unsigned mis0, cudaStream_t s) {
+    switch (cs) {
+        case 1: return launch_clustered(softmax_rows_long_kernel<1, LOG, WIN>, 1, a, out, rows, cols, mis0, s);
+        case 2: return launch_clustered(softmax_rows_long_kernel<2, LOG, WIN>, 2, a, out, rows, cols, mis0, s);
+        case 4: return launch_clustered(softmax_rows_long_kernel<4, LOG, WIN>, 4, a, out, rows, cols, mis0, s);
+        default: return launch_clustered(softmax_rows_long_kernel<8, LOG, WIN>, 8, a, out, rows, cols, mis0, s);
+    }
+}
 
 template <bool LOG, bool WIN>
 static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, int sm_count, cudaStream_t s) {
-    // vectors per row: exact when aligned, the longest window any row can need otherwise
-    const size_t nvec = WIN ? (cols + 6) / 4 : cols / 4;
+    const size_t nvec = cols / 4;   // body vectors per row (the body of a window row is never longer)
     // smallest configuration whose register slots hold the row (see the file header)
     if (nvec <= kThreads * 1)      return launch_rows_warp<LOG ? 1 : 0, WIN>(a, out, rows, cols, nullptr, nullptr, 0.f, mis0, s);
     if (nvec <= kThreads * 2)      return launch_cta<256, 2, LOG, WIN>(a, out, rows, cols, mis0, s);
@@ -871,18 +820,19 @@ static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, un
     if (nvec <= 512 * 8)           return launch_cta<512, 8, LOG, WIN>(a, out, rows, cols, mis0, s);
     // (a 1024-thread CTA holding a 32 000-float row measured 4.9 TB/s against the ring kernel's 6.0: one CTA
     //  per SM leaves nothing to overlap a row's load phase with)
-    if (!WIN && nvec <= (size_t)ring::kChunkVec * ring::kMaxChunks) return launch_ring<LOG>(a, out, rows, cols, sm_count, s);
-    if (nvec <= (size_t)kThreads * 8 * 8)   // <= 65536 (the window form also covers the ring kernel's range)
-        return launch_clustered(softmax_rows_cluster_kernel<8, 8, LOG, WIN>, 8, a, out, rows, cols, mis0, s);
-    if (rows * 8 <= (size_t)sm_count)   // too few rows to fill the machine with one cluster per row
+    const int force_cs = env_int("TRN_ROWS_LONG_CS");
+    if (!force_cs && nvec <= (size_t)ring::kChunkVec * ring::kMaxChunks) return launch_ring<LOG, WIN>(a, out, rows, cols, mis0, sm_count, s);
+    if (!force_cs && rows * 8 <= (size_t)sm_count)   // too few rows to fill the machine with one cluster per row
         return launch_split<LOG, WIN>(a, out, rows, cols, mis0, sm_count, s);
-    return launch_clustered(softmax_rows_long_kernel<8, LOG, WIN>, 8, a, out, rows, cols, mis0, s);
+    // cluster size by row length (scripts/exp/exp_long_rows.py): 4 CTAs up to 65 536 columns and from 2^20, 8 between
+    const int cs = force_cs ? force_cs : (cols <= 65536 || cols >= (1u << 20)) ? 4 : 8;
+    return launch_long<LOG, WIN>(cs, a, out, rows, cols, mis0, s);
 }
 
 template <bool LOG>
 static int dispatch(const float* a, float* out, size_t rows, size_t cols, int sm_count, cudaStream_t s) {
-    // misalignment of the first row in elements; rows are addressable as 128-bit vectors (directly or through
-    // their aligned windows) when input and output share it
+    // misalignment of the first row in elements; rows are addressable as an aligned body plus edge elements when
+    // input and output share it
     const unsigned mis_in = (unsigned)((reinterpret_cast<uintptr_t>(a) >> 2) & 3u);
     const unsigned mis_out = (unsigned)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u);
     const bool word_ok = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out)) & 3u) == 0;
@@ -929,7 +879,8 @@ layer_norm_rows_kernel(const float* __restrict__ in, const float* __restrict__ g
         const float var = block_sum_256(part, s_w) / (float)cols;
         const float inv_std = 1.0f / sqrtf(var + eps);
         for (size_t i = threadIdx.x; i < cols; i += kThreads)
-            dst[i] = __fadd_rn(__fmul_rn(__fmul_rn(gamma[i], __fsub_rn(src[i], mean)), inv_std), beta[i]);
+            dst[i] = gamma ? __fadd_rn(__fmul_rn(__fmul_rn(gamma[i], __fsub_rn(src[i], mean)), inv_std), beta[i])
+                           : __fmul_rn(__fsub_rn(src[i], mean), inv_std);   // layer_norm_simple (src/vector.rs:1386)
     }
 }
 
