@@ -207,6 +207,55 @@ public:
         if (st != TRN_OK) return detail::from_status(st);
         return out;
     }
+    // the rest of Vector's element-wise / statistics API (src/vector.rs:898-1480, 1980-2570, 3342-4410)
+    Result<Vector> neg() const { return map(trn_neg_f32); }
+    Result<Vector> signum() const { return map(trn_signum_f32); }
+    Result<Vector> trunc() const { return map(trn_trunc_f32); }
+    Result<Vector> fract() const { return map(trn_fract_f32); }
+    Result<Vector> sinh() const { return map(trn_sinh_f32); }
+    Result<Vector> cosh() const { return map(trn_cosh_f32); }
+    Result<Vector> asin() const { return map(trn_asin_f32); }
+    Result<Vector> acos() const { return map(trn_acos_f32); }
+    Result<Vector> atan() const { return map(trn_atan_f32); }
+    Result<Vector> asinh() const { return map(trn_asinh_f32); }
+    Result<Vector> acosh() const { return map(trn_acosh_f32); }
+    Result<Vector> atanh() const { return map(trn_atanh_f32); }
+    Result<Vector> hardswish() const { return map(trn_hardswish_f32); }
+    Result<Vector> mish() const { return map(trn_mish_f32); }
+    Result<Vector> selu() const { return map(trn_selu_f32); }
+    Result<Vector> leaky_relu(float negative_slope) const {
+        return map([negative_slope](const float* a, size_t n, float* o) { return trn_leaky_relu_f32(a, n, negative_slope, o); });
+    }
+    Result<Vector> elu(float alpha) const {
+        return map([alpha](const float* a, size_t n, float* o) { return trn_elu_f32(a, n, alpha, o); });
+    }
+    Result<Vector> pow(float e) const {
+        return map([e](const float* a, size_t n, float* o) { return trn_pow_f32(a, n, e, o); });
+    }
+    Result<Vector> clip(float lo, float hi) const {
+        return map([lo, hi](const float* a, size_t n, float* o) { return trn_clip_f32(a, n, lo, hi, o); });
+    }
+    Result<Vector> minimum(const Vector& o) const { return zip(o, trn_minimum_f32); }
+    Result<Vector> maximum(const Vector& o) const { return zip(o, trn_maximum_f32); }
+    Result<Vector> copysign(const Vector& sign) const { return zip(sign, trn_copysign_f32); }
+    Result<Vector> zscore() const { return map(trn_zscore_f32); }
+    Result<Vector> minmax_normalize() const { return map(trn_minmax_normalize_f32); }
+    Result<Vector> layer_norm_simple(float eps) const {
+        return map([eps](const float* a, size_t n, float* o) { return trn_layer_norm_simple_rows_f32(a, eps, o, 1, n); });
+    }
+    Result<float> sum_of_squares() const { return reduce(trn_sum_of_squares_f32); }
+    Result<float> covariance(const Vector& o) const {
+        float out = 0.f;
+        const int st = trn_covariance_f32(data_.data(), data_.size(), o.data_.data(), o.data_.size(), &out);
+        if (st != TRN_OK) return detail::from_status(st);
+        return out;
+    }
+    Result<float> correlation(const Vector& o) const {
+        float out = 0.f;
+        const int st = trn_correlation_f32(data_.data(), data_.size(), o.data_.data(), o.data_.size(), &out);
+        if (st != TRN_OK) return detail::from_status(st);
+        return out;
+    }
     Result<Vector> normalize() const {                                                      // src/vector.rs:2665-2678
         auto n = norm_l2();
         if (n.is_err()) return n.unwrap_err();

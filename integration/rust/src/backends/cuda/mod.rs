@@ -110,6 +110,74 @@ impl CudaBackend {
     unary_map!(sigmoid, trn_sigmoid_f32);
     unary_map!(gelu, trn_gelu_f32);
 
+    // remaining `VectorBackend` maps (src/backends/mod.rs:52-385) and the rest of Vector's element-wise API
+    // (src/vector.rs:1448-4410): same macro, one FFI symbol each
+    unary_map!(abs, trn_abs_f32);
+    unary_map!(relu, trn_relu_f32);
+    unary_map!(exp, trn_exp_f32);
+    unary_map!(swish, trn_swish_f32);
+    unary_map!(tanh, trn_tanh_f32);
+    unary_map!(sqrt, trn_sqrt_f32);
+    unary_map!(recip, trn_recip_f32);
+    unary_map!(ln, trn_ln_f32);
+    unary_map!(log2, trn_log2_f32);
+    unary_map!(log10, trn_log10_f32);
+    unary_map!(sin, trn_sin_f32);
+    unary_map!(cos, trn_cos_f32);
+    unary_map!(tan, trn_tan_f32);
+    unary_map!(floor, trn_floor_f32);
+    unary_map!(ceil, trn_ceil_f32);
+    unary_map!(round, trn_round_f32);
+    unary_map!(neg, trn_neg_f32);
+    unary_map!(signum, trn_signum_f32);
+    unary_map!(trunc, trn_trunc_f32);
+    unary_map!(fract, trn_fract_f32);
+    unary_map!(sinh, trn_sinh_f32);
+    unary_map!(cosh, trn_cosh_f32);
+    unary_map!(asin, trn_asin_f32);
+    unary_map!(acos, trn_acos_f32);
+    unary_map!(atan, trn_atan_f32);
+    unary_map!(asinh, trn_asinh_f32);
+    unary_map!(acosh, trn_acosh_f32);
+    unary_map!(atanh, trn_atanh_f32);
+    unary_map!(hardswish, trn_hardswish_f32);
+    unary_map!(mish, trn_mish_f32);
+    unary_map!(selu, trn_selu_f32);
+    binary_map!(sub, trn_sub_f32);
+    binary_map!(div, trn_div_f32);
+    binary_map!(minimum, trn_minimum_f32);
+    binary_map!(maximum, trn_maximum_f32);
+    binary_map!(copysign, trn_copysign_f32);
+    pub fn leaky_relu(a: &[f32], result: &mut [f32], negative_slope: f32) -> Result<(), TruenoError> {
+        check(unsafe { sys::trn_leaky_relu_f32(a.as_ptr(), a.len(), negative_slope, result.as_mut_ptr()) })
+    }
+    pub fn elu(a: &[f32], result: &mut [f32], alpha: f32) -> Result<(), TruenoError> {
+        check(unsafe { sys::trn_elu_f32(a.as_ptr(), a.len(), alpha, result.as_mut_ptr()) })
+    }
+    pub fn pow(a: &[f32], result: &mut [f32], n: f32) -> Result<(), TruenoError> {
+        check(unsafe { sys::trn_pow_f32(a.as_ptr(), a.len(), n, result.as_mut_ptr()) })
+    }
+    /// `GpuDevice::clip` (src/backends/gpu/device.rs) for `Vector::clip` (src/vector.rs:1448)
+    pub fn clip(a: &[f32], result: &mut [f32], min_val: f32, max_val: f32) -> Result<(), TruenoError> {
+        check(unsafe { sys::trn_clip_f32(a.as_ptr(), a.len(), min_val, max_val, result.as_mut_ptr()) })
+    }
+    unary_map!(zscore, trn_zscore_f32);
+    unary_map!(minmax_normalize, trn_minmax_normalize_f32);
+    reduce_f32!(sum_of_squares, trn_sum_of_squares_f32);
+    pub fn covariance(a: &[f32], b: &[f32]) -> Result<f32, TruenoError> {
+        let mut out = 0.0f32;
+        check(unsafe { sys::trn_covariance_f32(a.as_ptr(), a.len(), b.as_ptr(), b.len(), &mut out) })?;
+        Ok(out)
+    }
+    pub fn correlation(a: &[f32], b: &[f32]) -> Result<f32, TruenoError> {
+        let mut out = 0.0f32;
+        check(unsafe { sys::trn_correlation_f32(a.as_ptr(), a.len(), b.as_ptr(), b.len(), &mut out) })?;
+        Ok(out)
+    }
+    pub fn layer_norm_simple(a: &[f32], result: &mut [f32], eps: f32) -> Result<(), TruenoError> {
+        check(unsafe { sys::trn_layer_norm_simple_rows_f32(a.as_ptr(), eps, result.as_mut_ptr(), 1, a.len()) })
+    }
+
     /// One row (`rows == 1`) is exactly `Vector::softmax` (src/vector.rs:1516).
     pub fn softmax_rows(a: &[f32], result: &mut [f32], rows: usize, cols: usize) -> Result<(), TruenoError> {
         check(unsafe { sys::trn_softmax_rows_f32(a.as_ptr(), result.as_mut_ptr(), rows, cols) })

@@ -163,6 +163,59 @@ extern "C" {
     pub fn trn_fma_f32(a: *const f32, na: usize, b: *const f32, nb: usize, c: *const f32, nc: usize, out: *mut f32) -> c_int;
     pub fn trn_fma_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, c: *const f32, nc: usize, out: *mut f32,
                            stream: *mut c_void) -> c_int;
+    // the rest of Vector's element-wise / statistics API (include/trueno_cuda.h, same order)
+    pub fn trn_neg_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_neg_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_signum_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_signum_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_trunc_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_trunc_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_fract_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_fract_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sinh_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_sinh_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_cosh_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_cosh_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_asin_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_asin_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_acos_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_acos_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_atan_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_atan_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_asinh_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_asinh_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_acosh_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_acosh_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_atanh_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_atanh_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_hardswish_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_hardswish_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_mish_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_mish_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_selu_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_selu_f32_dev(a: *const f32, n: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_leaky_relu_f32(a: *const f32, n: usize, negative_slope: f32, out: *mut f32) -> c_int;
+    pub fn trn_leaky_relu_f32_dev(a: *const f32, n: usize, negative_slope: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_elu_f32(a: *const f32, n: usize, alpha: f32, out: *mut f32) -> c_int;
+    pub fn trn_elu_f32_dev(a: *const f32, n: usize, alpha: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_pow_f32(a: *const f32, n: usize, exponent: f32, out: *mut f32) -> c_int;
+    pub fn trn_pow_f32_dev(a: *const f32, n: usize, exponent: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_clip_f32(a: *const f32, n: usize, min_val: f32, max_val: f32, out: *mut f32) -> c_int;
+    pub fn trn_clip_f32_dev(a: *const f32, n: usize, min_val: f32, max_val: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_minimum_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_minimum_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_maximum_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_maximum_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_copysign_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_copysign_f32_dev(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_affine_f32_dev(a: *const f32, n: usize, shift: f32, scale: f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_sum_of_squares_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_covariance_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_correlation_f32(a: *const f32, na: usize, b: *const f32, nb: usize, out: *mut f32) -> c_int;
+    pub fn trn_zscore_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_minmax_normalize_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
+    pub fn trn_layer_norm_simple_rows_f32(a: *const f32, eps: f32, out: *mut f32, rows: usize, cols: usize) -> c_int;
+    pub fn trn_layer_norm_simple_rows_f32_dev(a: *const f32, eps: f32, out: *mut f32, rows: usize, cols: usize, stream: *mut c_void) -> c_int;
     pub fn trn_mean_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     pub fn trn_variance_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     pub fn trn_stddev_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;

@@ -1,5 +1,6 @@
-"""Long / unaligned softmax rows: the two-pass long kernel by cluster size and occupancy cap against the default dispatch.
-TRN_ROWS_LONG_CS / TRN_ROWS_LONG_OCC are read per call by csrc/softmax.cu."""
+"""Long / unaligned softmax rows: the two-pass long kernel by cluster size against the default dispatch.
+TRN_ROWS_LONG_CS is read per call by csrc/softmax.cu.  (An occupancy cap — fewer rows in flight against L2 — and a
+shared-memory-resident one-pass cluster kernel were measured here too and were slower at every length; both are gone.)"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -18,17 +19,20 @@ torch.cuda.set_device(0); trn.check(trn.lib.trn_cuda_init(0))
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); st = stream.cuda_stream
 L = trn.lib
 target = 1 << 27
-for cols in [16387, 32001, 32768, 40000, 50257, 65536, 100003, 128256, 151936, 200019, 262144, 524288, 1 << 20]:
+def run(cols, env):
+    for k in ("TRN_ROWS_LONG_CS",):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    t1 = timeit(lambda: trn.check(L.trn_softmax_rows_f32_dev(x.data_ptr(), y.data_ptr(), rows, cols, st)))
+    t2 = timeit(lambda: trn.check(L.trn_log_softmax_rows_f32_dev(x.data_ptr(), y.data_ptr(), rows, cols, st)))
+    return f"{nb/t1/1e6:5.0f}/{nb/t2/1e6:5.0f}"
+
+for cols in [20000, 24576, 32000, 32001, 32768, 40000, 50257, 65536, 65540, 100003, 128256, 131072, 151936, 196608, 200019, 262144, 524288, 1 << 20]:
     rows = max(1, target // cols)
     x = torch.randn(rows, cols, device="cuda"); y = torch.empty_like(x)
     nb = 8.0 * rows * cols
-    line = f"{rows:6d} x {cols:8d}:"
-    for cs, occ in [(0, 0), (1, 0), (2, 0), (4, 0), (8, 0), (8, 4), (8, 2), (4, 4), (4, 2), (2, 2)]:
-        if cs: os.environ["TRN_ROWS_LONG_CS"] = str(cs)
-        else: os.environ.pop("TRN_ROWS_LONG_CS", None)
-        os.environ["TRN_ROWS_LONG_OCC"] = str(occ)
-        t1 = timeit(lambda: trn.check(L.trn_softmax_rows_f32_dev(x.data_ptr(), y.data_ptr(), rows, cols, st)))
-        t2 = timeit(lambda: trn.check(L.trn_log_softmax_rows_f32_dev(x.data_ptr(), y.data_ptr(), rows, cols, st)))
-        line += f"  [{'dflt' if not cs else f'cs{cs}/o{occ}'}] {nb/t1/1e6:5.0f}/{nb/t2/1e6:5.0f}"
+    line = f"{rows:6d} x {cols:8d}:  [default] {run(cols, {})}"
+    for cs in (1, 2, 4, 8):
+        line += f"  [two-pass cs{cs}] {run(cols, {'TRN_ROWS_LONG_CS': str(cs)})}"
     print(line, flush=True)
     del x, y

@@ -1,7 +1,7 @@
 """One launch of every hot-path kernel at its BASELINE size between cudaProfilerStart/Stop, for
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_all python scripts/profile_kernels.py
 Warm-up launches run before the profiler range so the captured launch is steady-state (apart from ncu's own
-cache control).  usage: python scripts/profile_kernels.py [gemm] [batched] [reduce] [map] [softmax] [rows] [matvec] [attention] [conv]"""
+cache control).  usage: python scripts/profile_kernels.py [gemm] [batched] [reduce] [map] [softmax] [rows] [rows2] [matvec] [attention] [conv]"""
 import os
 import sys
 
@@ -69,6 +69,22 @@ def main():
         t_out = torch.empty(8192, 16384, device="cuda")
         keep += [t_in, t_out]
         ops.append(lambda: trn.check(L.trn_transpose_f32_dev(t_in.data_ptr(), 16384, 8192, t_out.data_ptr(), st)))
+    if "rows2" in which:
+        # long / window / split row kernels: LLM-vocabulary rows (128 256 aligned; 50 257 and 100 003 not 16-byte aligned),
+        # window forms of the warp / CTA / ring kernels, one large Vector::softmax
+        for rr, cc in ((1046, 128256), (2670, 50257), (1342, 100003), (134083, 1001), (16386, 8191), (4194, 32001), (1, 1 << 27)):
+            w = torch.randn(rr, cc, device="cuda")
+            wo = torch.empty_like(w)
+            keep += [w, wo]
+            ops += [lambda w=w, wo=wo, rr=rr, cc=cc: trn.check(L.trn_softmax_rows_f32_dev(w.data_ptr(), wo.data_ptr(), rr, cc, st)),
+                    lambda w=w, wo=wo, rr=rr, cc=cc: trn.check(L.trn_log_softmax_rows_f32_dev(w.data_ptr(), wo.data_ptr(), rr, cc, st))]
+        w = torch.randn(8192, 16384, device="cuda")
+        wo = torch.empty_like(w)
+        g, bb = torch.randn(16384, device="cuda"), torch.randn(16384, device="cuda")
+        keep += [w, wo, g, bb]
+        ops.append(lambda: trn.check(L.trn_layer_norm_rows_f32_dev(w.data_ptr(), g.data_ptr(), 16384, bb.data_ptr(), 16384, 1e-5, wo.data_ptr(), 8192, 16384, st)))
+        ops.append(lambda: trn.check(L.trn_mish_f32_dev(w.data_ptr(), w.numel(), wo.data_ptr(), st)))
+        ops.append(lambda: trn.check(L.trn_hardswish_f32_dev(w.data_ptr(), w.numel(), wo.data_ptr(), st)))
     if "matvec" in which:
         r = 16384
         ma, mv, my = torch.randn(r, r, device="cuda"), torch.randn(r, device="cuda"), torch.empty(r, device="cuda")

@@ -39,6 +39,16 @@ static void validation_tests() {
     CHECK(c.is_err() && c.unwrap_err() == TruenoError::invalid_input("Invalid clamp range: min (10) > max (0)"));
     // src/vector.rs:7715-7733 layer_norm size mismatches
     CHECK(V({1, 2, 3}).layer_norm(V({1, 1}), V({0, 0, 0}), 1e-5f).unwrap_err() == TruenoError::size_mismatch(3, 2));
+    // the rest of Vector's element-wise / statistics API: error contract (src/vector.rs:1449, :1981-1991, :2086-2096, :4329)
+    CHECK(V({1, 2, 3}).leaky_relu(1.5f).unwrap_err() == TruenoError::invalid_input("negative_slope must be in [0.0, 1.0), got 1.5"));
+    CHECK(V({1, 2, 3}).elu(0.0f).unwrap_err() == TruenoError::invalid_input("alpha must be > 0, got 0"));
+    CHECK(V({1, 2, 3}).clip(10.f, 5.f).unwrap_err() == TruenoError::invalid_input("min_val (10) must be <= max_val (5)"));
+    CHECK(Vector().hardswish().unwrap_err() == TruenoError::empty_vector());
+    CHECK(Vector().mish().unwrap_err() == TruenoError::empty_vector());
+    CHECK(Vector().selu().unwrap_err() == TruenoError::empty_vector());
+    CHECK(Vector().zscore().unwrap_err() == TruenoError::empty_vector());
+    CHECK(V({1, 2}).minimum(V({1, 2, 3})).unwrap_err() == TruenoError::size_mismatch(2, 3));
+    CHECK(V({1, 2}).covariance(V({1, 2, 3})).unwrap_err() == TruenoError::size_mismatch(2, 3));
     // src/matrix.rs:108-117
     auto m = Matrix::from_vec(2, 2, {1, 2, 3});
     CHECK(m.is_err() && m.unwrap_err().message == "Data length 3 does not match matrix dimensions 2x2 (expected 4)");
@@ -94,6 +104,28 @@ static void device_tests() {
     CHECK(V({2, 3, 4}).fma(V({5, 6, 7}), V({1, 2, 3})).unwrap() == V({11, 20, 31}));
     CHECK(V({3.2f, 3.7f, -2.3f, -2.8f, 5.0f}).round().unwrap() == V({3, 4, -2, -3, 5}));
     CHECK(V({-2, -1, 0, 1, 2}).relu().unwrap() == V({0, 0, 0, 1, 2}));                        // src/vector.rs:8018
+    // the rest of Vector's element-wise / statistics API: the reference's KATs (src/vector.rs:7219-8721, test_*_basic)
+    CHECK(V({-2, -1, 0, 1, 2}).leaky_relu(0.01f).unwrap() == V({-0.02f, -0.01f, 0, 1, 2}));
+    CHECK(V({-5, 0, 5, 10, 15}).clip(0, 10).unwrap() == V({0, 0, 5, 10, 10}));
+    CHECK(V({5, -3, 0, -0.0f}).signum().unwrap() == V({1, -1, 1, -1}));
+    CHECK(V({3.2f, 3.7f, -2.3f, -2.8f, 5.0f}).trunc().unwrap() == V({3, 3, -2, -2, 5}));
+    CHECK(V({5, 3, 2, 4}).copysign(V({-1, 1, -1, 1})).unwrap() == V({-5, 3, -2, 4}));
+    CHECK(V({1, 5, 3, 2}).minimum(V({2, 3, 4, 1})).unwrap() == V({1, 3, 3, 1}));
+    CHECK(V({1, 5, 3, 2}).maximum(V({2, 3, 4, 1})).unwrap() == V({2, 5, 4, 2}));
+    CHECK(V({1, -2, 3, -4}).neg().unwrap() == V({-1, 2, -3, 4}));
+    CHECK(V({2, 3, 4, 5}).pow(2.0f).unwrap() == V({4, 9, 16, 25}));
+    {
+        auto h = V({-4, -3, -1.5f, 0, 1.5f, 3, 4}).hardswish().unwrap();
+        CHECK(h.as_slice()[0] == 0.f && h.as_slice()[1] == 0.f && h.as_slice()[5] == 3.f && h.as_slice()[6] == 4.f);
+        CHECK_NEAR(h.as_slice()[2], -0.375, 1e-5);
+        CHECK_NEAR(h.as_slice()[4], 1.125, 1e-5);
+    }
+    CHECK(V({3, 4}).sum_of_squares().unwrap() == 25.0f);
+    CHECK_NEAR(V({1, 2, 3}).covariance(V({2, 4, 6})).unwrap(), 4.0 / 3.0, 1e-5);
+    CHECK_NEAR(V({1, 2, 3, 4}).correlation(V({4, 3, 2, 1})).unwrap(), -1.0, 1e-5);
+    CHECK(V({5, 5, 5}).correlation(V({1, 2, 3})).unwrap_err() == TruenoError::division_by_zero());
+    CHECK(V({3, 3, 3, 3}).zscore().unwrap_err() == TruenoError::division_by_zero());
+    CHECK(V({1, 2, 3, 4, 5}).minmax_normalize().unwrap() == V({0, 0.25f, 0.5f, 0.75f, 1}));
     // src/vector.rs:8087-8096 sigmoid; 8352-8360 gelu(0) == 0; 7866-7875 uniform softmax
     auto s = V({0, 2, -2}).sigmoid().unwrap().as_slice();
     CHECK(s[0] == 0.5f);

@@ -149,9 +149,8 @@ __device__ __forceinline__ float block_sum_t(float v, float* s_w) {
 }
 
 template <int T, int VPT, bool LOG, bool WIN>
-__global__ void __launch_bounds__(T)
-softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
-    __shared__ float s_w[T / 32];
+__device__ __forceinline__ void softmax_rows_cta_body(const float* __restrict__ in, float* __restrict__ out, size_t rows,
+                                                      size_t cols, unsigned mis0, float* s_w) {
     const size_t row = blockIdx.x;
     const RowView<WIN> rv(in, out, row, cols, mis0);
     const unsigned nvec = (unsigned)rv.nvec;
@@ -190,10 +189,28 @@ softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, s
     if (WIN) rv.edge_store(threadIdx.x, LOG ? (xe - m) - lse : xe * inv);
 }
 
+// Two entry points over the same body.  The log + window variants at VPT = 8 take 67-75 registers and would halve the
+// occupancy, so they are compiled with a 64-register cap (1024 / T resident CTAs); every other variant is compiled
+// WITHOUT a minimum-blocks argument: naming one (even 1) changes ptxas' scheduling — 95 registers, or the same count
+// and 15 % less throughput at 4099 columns (measured, scripts/sweep_rows_ext.py).
+template <int T, int VPT, bool LOG, bool WIN>
+__global__ void __launch_bounds__(T)
+softmax_rows_cta_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
+    __shared__ float s_w[T / 32];
+    softmax_rows_cta_body<T, VPT, LOG, WIN>(in, out, rows, cols, mis0, s_w);
+}
+template <int T, int VPT, bool LOG, bool WIN>
+__global__ void __launch_bounds__(T, 1024 / T)
+softmax_rows_cta_capped_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
+    __shared__ float s_w[T / 32];
+    softmax_rows_cta_body<T, VPT, LOG, WIN>(in, out, rows, cols, mis0, s_w);
+}
+
 template <int T, int VPT, bool LOG, bool WIN>
 static int launch_cta(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, cudaStream_t s) {
     if (rows > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "%zu rows exceed the launch grid", rows);
-    softmax_rows_cta_kernel<T, VPT, LOG, WIN><<<(unsigned)rows, T, 0, s>>>(a, out, rows, cols, mis0);
+    if constexpr (VPT == 8 && LOG && WIN) softmax_rows_cta_capped_kernel<T, VPT, LOG, WIN><<<(unsigned)rows, T, 0, s>>>(a, out, rows, cols, mis0);
+    else                        softmax_rows_cta_kernel<T, VPT, LOG, WIN><<<(unsigned)rows, T, 0, s>>>(a, out, rows, cols, mis0);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -528,8 +545,11 @@ layer_norm_rows_reg_kernel(const float* __restrict__ in, const float* __restrict
 // against 126 MB) and writes exp(x - M) / S or (x - M) - ln S, the reference's expressions
 // (src/vector.rs:1540-1553, :1605-1623).  An all -inf prefix keeps s = 0 (reference: exp(-inf - max) = 0); an
 // all -inf ROW gives NaN as the reference does (x - max = -inf - -inf).
-// Measured against a register-resident 8-CTA cluster kernel (one pass, the row in the registers of the cluster,
-// since removed): 40 000 columns 5.3 vs 3.3 TB/s, 65 536: 5.2 vs 4.7 (scripts/exp/exp_long_rows.py).
+// Measured against two one-pass forms, both since removed (scripts/exp/exp_long_rows.py): a register-resident 8-CTA
+// cluster kernel (40 000 columns 5.3 vs 3.3 TB/s, 65 536: 5.2 vs 4.7) and a shared-memory-resident cluster kernel (every
+// CTA bulk-copies its slice of the row into shared memory, one exponential per element, pass 2 from shared memory:
+// 50 257 columns 5.1 vs 4.3, 128 256: 5.0 vs 4.5 — one row per CTA leaves the TMA round trip and the cluster barrier
+// uncovered, where this kernel keeps eight CTAs of plain loads per SM in flight).
 __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
     const float mn = fmaxf(m, m2);
     const float ref = mn == -INFINITY ? 0.f : mn;   // nothing finite seen yet: every term is exp(-inf) = 0
@@ -824,8 +844,8 @@ static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, un
     if (!force_cs && nvec <= (size_t)ring::kChunkVec * ring::kMaxChunks) return launch_ring<LOG, WIN>(a, out, rows, cols, mis0, sm_count, s);
     if (!force_cs && rows * 8 <= (size_t)sm_count)   // too few rows to fill the machine with one cluster per row
         return launch_split<LOG, WIN>(a, out, rows, cols, mis0, sm_count, s);
-    // cluster size by row length (scripts/exp/exp_long_rows.py): 4 CTAs up to 65 536 columns and from 2^20, 8 between
-    const int cs = force_cs ? force_cs : (cols <= 65536 || cols >= (1u << 20)) ? 4 : 8;
+    // cluster size by row length (scripts/exp/exp_long_rows.py): 4 CTAs up to ~96 K columns and from ~768 K, 8 between
+    const int cs = force_cs ? force_cs : (cols <= 98304 || cols >= 786432) ? 4 : 8;
     return launch_long<LOG, WIN>(cs, a, out, rows, cols, mis0, s);
 }
 
