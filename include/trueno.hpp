@@ -329,6 +329,14 @@ public:
         if (st != TRN_OK) return detail::from_status(st);
         return out;
     }
+    Result<Matrix> embedding_lookup(const std::vector<size_t>& indices) const {             // src/matrix.rs:2008
+        std::vector<uint64_t> idx(indices.begin(), indices.end());
+        Matrix out(indices.size(), cols_, {});
+        out.data_.resize(out.rows_ * out.cols_);
+        const int st = trn_embedding_lookup_f32(data_.data(), rows_, cols_, idx.data(), idx.size(), out.data_.data());
+        if (st != TRN_OK) return detail::from_status(st);
+        return out;
+    }
     static Result<Vector> vecmat(const Vector& v, const Matrix& m) {                        // src/matrix.rs:1782
         Vector out{std::vector<float>(m.cols_)};
         const int st = trn_vecmat_f32(v.data_.data(), v.data_.size(), m.data_.data(), m.rows_, m.cols_, out.data_.data());

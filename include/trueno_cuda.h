@@ -330,6 +330,16 @@ TRN_API int trn_minmax_normalize_f32(const float* a, size_t n, float* out);
 TRN_API int trn_layer_norm_simple_rows_f32(const float* a, float eps, float* out, size_t rows, size_t cols);
 TRN_API int trn_layer_norm_simple_rows_f32_dev(const float* a, float eps, float* out, size_t rows, size_t cols, void* stream);
 
+/* Matrix::embedding_lookup (src/matrix.rs:2008-2041; embedding_lookup_sparse :2059 adds the sorted unique indices, host
+ * metadata): out[r, :] = table[indices[r], :], table rows x cols row-major, out n_indices x cols.  Bit-exact (byte
+ * movement).  Host-slice call: an index >= rows -> TRN_INVALID_INPUT("Index {} at position {} is out of bounds for
+ * embedding table with {} rows"), checked before anything is launched; empty indices -> nothing written.  Resident
+ * twin: indices are device memory (uint64), an out-of-range index yields a zero row. */
+TRN_API int trn_embedding_lookup_f32(const float* table, size_t rows, size_t cols, const uint64_t* indices, size_t n_indices,
+                                     float* out);
+TRN_API int trn_embedding_lookup_f32_dev(const float* table, size_t rows, size_t cols, const uint64_t* indices,
+                                         size_t n_indices, float* out, void* stream);
+
 /* ---- device-resident op chaining --------------------------------------
  * The CUDA counterpart of GpuCommandBatch (src/backends/gpu/batch.rs:118-1019): queue uploads and ops, run
  * them with ONE graph launch, read results back.  Every BufferId is a slice of one device arena; execute()

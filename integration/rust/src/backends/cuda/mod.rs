@@ -231,6 +231,13 @@ impl CudaBackend {
         check(unsafe { sys::trn_matvec_f32(a.as_ptr(), rows, cols, v.as_ptr(), v.len(), y.as_mut_ptr()) })?;
         Ok(y)
     }
+    /// `Matrix::embedding_lookup` (src/matrix.rs:2008): rows of `table` selected by `indices`.
+    pub fn embedding_lookup(table: &[f32], rows: usize, cols: usize, indices: &[usize]) -> Result<Vec<f32>, TruenoError> {
+        let idx: Vec<u64> = indices.iter().map(|&i| i as u64).collect();
+        let mut out = vec![0.0f32; indices.len() * cols];
+        check(unsafe { sys::trn_embedding_lookup_f32(table.as_ptr(), rows, cols, idx.as_ptr(), idx.len(), out.as_mut_ptr()) })?;
+        Ok(out)
+    }
     pub fn transpose(a: &[f32], rows: usize, cols: usize) -> Result<Vec<f32>, TruenoError> {
         let mut out = vec![0.0f32; rows * cols];
         check(unsafe { sys::trn_transpose_f32(a.as_ptr(), rows, cols, out.as_mut_ptr()) })?;

@@ -101,6 +101,8 @@ class Oracle:
         L.orc_vector_map.argtypes = [C.c_int, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
         L.orc_layer_norm_simple.restype = None
         L.orc_layer_norm_simple.argtypes = [_f32p, C.c_float, C.c_float, _f32p, C.c_size_t]
+        L.orc_embedding_lookup.restype = C.c_int
+        L.orc_embedding_lookup.argtypes = [_f32p, C.c_size_t, C.c_size_t, _u64p, C.c_size_t, _f32p]
         L.orc_symmetric_eigen.restype = C.c_int
         L.orc_symmetric_eigen.argtypes = [_f32p, C.c_size_t, _f32p, _f32p]
         L.orc_convolve2d.restype = None
@@ -283,6 +285,14 @@ class Oracle:
         if self.lib.orc_symmetric_eigen(_p(A), rows, _p(vals), _p(vecs)) != 0:
             raise OracleError("InvalidInput", "Jacobi algorithm failed to converge after 50 sweeps")
         return vals, vecs.reshape(rows, rows)
+
+    def embedding_lookup(self, table, rows, cols, indices):
+        """Matrix::embedding_lookup (src/matrix.rs:2008-2041)"""
+        table = _f32(table)
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64).reshape(-1))
+        out = np.empty(idx.size * cols, np.float32)
+        self._check(self.lib.orc_embedding_lookup(_p(table), rows, cols, idx.ctypes.data_as(_u64p), idx.size, _p(out)))
+        return out.reshape(idx.size, cols)
 
     def vecmat(self, v, A, rows, cols):
         v, A = _f32(v), _f32(A)

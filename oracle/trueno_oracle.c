@@ -852,6 +852,19 @@ ORC_API void orc_layer_norm_simple(const float* x, float sum, float eps, float* 
     for (size_t i = 0; i < n; ++i) y[i] = (x[i] - mean) * inv_std;
 }
 
+/* Matrix::embedding_lookup (src/matrix.rs:2008-2041): validate every index first, then copy one row per index.
+ * Returns 0, or 2 (InvalidInput) with the reference's message in orc_last_message(). */
+ORC_API int orc_embedding_lookup(const float* table, size_t rows, size_t cols, const uint64_t* idx, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i)
+        if (idx[i] >= rows) {
+            snprintf(g_msg, sizeof g_msg, "Index %llu at position %zu is out of bounds for embedding table with %zu rows",
+                     (unsigned long long)idx[i], i, rows);
+            return ORC_INVALID_INPUT;
+        }
+    for (size_t r = 0; r < n; ++r) memcpy(out + r * cols, table + idx[r] * cols, cols * sizeof(float));
+    return 0;
+}
+
 /* scalar.rs:170-183 — Kahan-compensated sequential sum */
 ORC_API float orc_scalar_sum_kahan(const float* a, size_t n) {
     float sum = 0.f, c = 0.f;

@@ -49,3 +49,14 @@ if tag == "new":
         t6 = timeit(lambda: torch.nn.functional.layer_norm(x, (cols,), g, b, 1e-5))
         print(f"[{tag}] {rows:8d} x {cols:8d}: layer_norm {nb/t3/1e6:6.0f}  torch.layer_norm {nb/t6/1e6:6.0f} GB/s", flush=True)
         del x, y
+if tag == "new":
+    # Matrix::embedding_lookup: 8 B per output element (4 read + 4 written)
+    for rows, cols, n in [(50257, 768, 1 << 19), (32000, 4096, 1 << 16), (128256, 8192, 1 << 14), (1000, 64, 1 << 22), (50257, 1001, 1 << 18)]:
+        table = torch.randn(rows, cols, device="cuda")
+        idx = torch.randint(0, rows, (n,), device="cuda", dtype=torch.int64)
+        out = torch.empty(n, cols, device="cuda")
+        nb = 8.0 * n * cols
+        t1 = timeit(lambda: trn.check(L.trn_embedding_lookup_f32_dev(table.data_ptr(), rows, cols, idx.data_ptr(), n, out.data_ptr(), st)))
+        t2 = timeit(lambda: torch.index_select(table, 0, idx, out=out))
+        print(f"[{tag}] embedding_lookup {rows} x {cols}, {n} indices: {nb/t1/1e6:6.0f}  torch.index_select {nb/t2/1e6:6.0f} GB/s", flush=True)
+        del table, out

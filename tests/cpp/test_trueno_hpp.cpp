@@ -49,6 +49,10 @@ static void validation_tests() {
     CHECK(Vector().zscore().unwrap_err() == TruenoError::empty_vector());
     CHECK(V({1, 2}).minimum(V({1, 2, 3})).unwrap_err() == TruenoError::size_mismatch(2, 3));
     CHECK(V({1, 2}).covariance(V({1, 2, 3})).unwrap_err() == TruenoError::size_mismatch(2, 3));
+    {   // Matrix::embedding_lookup out of bounds (src/matrix.rs:3801-3810): checked before anything is launched
+        auto r = Matrix::from_vec(3, 2, {1, 2, 3, 4, 5, 6}).unwrap().embedding_lookup({0, 5, 1});
+        CHECK(r.is_err() && r.unwrap_err() == TruenoError::invalid_input("Index 5 at position 1 is out of bounds for embedding table with 3 rows"));
+    }
     // src/matrix.rs:108-117
     auto m = Matrix::from_vec(2, 2, {1, 2, 3});
     CHECK(m.is_err() && m.unwrap_err().message == "Data length 3 does not match matrix dimensions 2x2 (expected 4)");
@@ -119,6 +123,10 @@ static void device_tests() {
         CHECK(h.as_slice()[0] == 0.f && h.as_slice()[1] == 0.f && h.as_slice()[5] == 3.f && h.as_slice()[6] == 4.f);
         CHECK_NEAR(h.as_slice()[2], -0.375, 1e-5);
         CHECK_NEAR(h.as_slice()[4], 1.125, 1e-5);
+    }
+    {   // src/matrix.rs:3727-3762
+        auto e = Matrix::from_vec(4, 3, {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12}).unwrap().embedding_lookup({1, 3, 0}).unwrap();
+        CHECK(e.rows() == 3 && e.cols() == 3 && e.as_slice() == std::vector<float>({4, 5, 6, 10, 11, 12, 1, 2, 3}));
     }
     CHECK(V({3, 4}).sum_of_squares().unwrap() == 25.0f);
     CHECK_NEAR(V({1, 2, 3}).covariance(V({2, 4, 6})).unwrap(), 4.0 / 3.0, 1e-5);

@@ -82,3 +82,21 @@ def test_oracle_vector_map_against_numpy(oracle):
     hs = np.where(x <= -3, f32(0), np.where(x >= 3, x, (x * (x + f32(3))) / f32(6))).astype(f32)
     assert np.array_equal(oracle.vector_map("hardswish", x), hs)
     assert np.array_equal(oracle.vector_map("leaky_relu", x, p0=0.01), np.where(x > 0, x, f32(0.01) * x).astype(f32))
+
+
+def test_oracle_embedding_lookup_kats(oracle):
+    """src/matrix.rs:3727-3848"""
+    import oracle as O
+    t = np.arange(1, 13, dtype=f32)
+    r = oracle.embedding_lookup(t, 4, 3, [1, 3, 0])
+    assert np.array_equal(r, np.array([[4, 5, 6], [10, 11, 12], [1, 2, 3]], f32))
+    assert np.array_equal(oracle.embedding_lookup([1, 2, 3, 4, 5, 6], 3, 2, [1]), np.array([[3, 4]], f32))
+    r = oracle.embedding_lookup([1, 2, 3, 4, 5, 6], 2, 3, [0, 0, 1, 0])
+    assert r.shape == (4, 3) and np.array_equal(r[0], r[1]) and np.array_equal(r[0], r[3])
+    assert oracle.embedding_lookup([1, 2, 3, 4, 5, 6], 3, 2, []).shape == (0, 2)
+    with pytest.raises(O.OracleError) as e:
+        oracle.embedding_lookup([1, 2, 3, 4, 5, 6], 3, 2, [0, 5, 1])
+    assert e.value.variant == "InvalidInput" and "Index 5 at position 1 is out of bounds for embedding table with 3 rows" in str(e.value)
+    big = np.arange(1000 * 256, dtype=f32)
+    r = oracle.embedding_lookup(big, 1000, 256, [0, 500, 999, 42, 100])
+    assert r.shape == (5, 256) and r[0, 0] == 0 and r[1, 0] == 500 * 256 and r[2, 0] == 999 * 256

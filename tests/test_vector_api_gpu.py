@@ -175,3 +175,51 @@ def test_layer_norm_simple_rows_dev_and_affine_dev(trn):
     trn.check(trn.lib.trn_affine_f32_dev(x.data_ptr(), x.numel(), 0.25, 3.0, y.data_ptr(), st))
     torch.cuda.synchronize()
     assert torch.equal(y, (x - 0.25) * 3.0)
+
+
+def test_embedding_lookup_reference_kats(trn):
+    """src/matrix.rs:3727-3848"""
+    M = trn.Matrix
+    r = M.from_vec(4, 3, np.arange(1, 13)).embedding_lookup([1, 3, 0])
+    assert r.shape() == (3, 3) and np.array_equal(r.as_slice(), np.array([4, 5, 6, 10, 11, 12, 1, 2, 3], f32))
+    r = M.from_vec(3, 2, [1, 2, 3, 4, 5, 6]).embedding_lookup([1])
+    assert r.shape() == (1, 2) and r.get(0, 0) == 3.0 and r.get(0, 1) == 4.0
+    r = M.from_vec(2, 3, [1, 2, 3, 4, 5, 6]).embedding_lookup([0, 0, 1, 0])
+    assert r.shape() == (4, 3) and r.get(0, 0) == r.get(1, 0) == r.get(3, 0)
+    assert M.from_vec(3, 2, [1, 2, 3, 4, 5, 6]).embedding_lookup([]).shape() == (0, 2)
+    with pytest.raises(trn.TruenoError) as e:
+        M.from_vec(3, 2, [1, 2, 3, 4, 5, 6]).embedding_lookup([0, 5, 1])
+    assert e.value == trn.TruenoError.InvalidInput("Index 5 at position 1 is out of bounds for embedding table with 3 rows")
+    emb, uniq = M.from_vec(4, 2, [1, 2, 3, 4, 5, 6, 7, 8]).embedding_lookup_sparse([1, 3, 1, 0, 3])
+    assert emb.shape() == (5, 2) and uniq == [0, 1, 3]
+    r = M.from_vec(1000, 256, np.arange(1000 * 256)).embedding_lookup([0, 500, 999, 42, 100])
+    assert r.shape() == (5, 256) and r.get(0, 0) == 0 and r.get(1, 0) == 500 * 256 and r.get(2, 0) == 999 * 256
+
+
+@pytest.mark.parametrize("rows,cols,n", [(7, 1, 33), (50, 3, 1000), (1000, 64, 5000), (4000, 768, 3000), (300, 1001, 700),
+                                         (128, 4096, 500), (64, 20000, 40), (9, 100_003, 12)])
+def test_embedding_lookup_bit_exact_vs_oracle(trn, oracle, rows, cols, n):
+    rng = np.random.default_rng(rows + cols + n)
+    table = rng.standard_normal(rows * cols).astype(f32)
+    table[:3] = [np.nan, np.inf, -0.0][: min(3, table.size)]
+    idx = rng.integers(0, rows, n)
+    got = trn.Matrix.from_vec(rows, cols, table).embedding_lookup(idx).as_slice()
+    want = oracle.embedding_lookup(table, rows, cols, idx).reshape(-1)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_embedding_lookup_dev_resident_and_out_of_range(trn):
+    torch = pytest.importorskip("torch")
+    trn.check(trn.lib.trn_cuda_init(0))
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream or 1
+    for rows, cols in [(32000, 4096), (50257, 768), (1000, 1001)]:
+        table = torch.randn(rows, cols, device=dev)
+        idx = torch.randint(0, rows, (8192,), device=dev, dtype=torch.int64)
+        idx[5] = rows + 7          # resident twin: an out-of-range index yields a zero row
+        out = torch.full((idx.numel(), cols), 9.0, device=dev)
+        trn.check(trn.lib.trn_embedding_lookup_f32_dev(table.data_ptr(), rows, cols, idx.data_ptr(), idx.numel(), out.data_ptr(), st))
+        torch.cuda.synchronize()
+        ok = torch.ones(idx.numel(), dtype=torch.bool, device=dev)
+        ok[5] = False
+        assert torch.equal(out[ok], table[idx[ok]]) and bool((out[5] == 0).all())

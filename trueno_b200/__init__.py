@@ -117,6 +117,7 @@ _SIGNATURES = {
     "trn_norm_l2_allreduce_f32_dev": [_vp, _vp, _sz, _vp, _vp],
     "trn_argmax_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
     "trn_argmin_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
+    "trn_embedding_lookup_f32": [_vp, _sz, _sz, _vp, _sz, _vp], "trn_embedding_lookup_f32_dev": [_vp, _sz, _sz, _vp, _sz, _vp, _vp],
     "trn_convolve2d_f32": [_vp, _sz, _sz, _vp, _sz, _sz, _vp], "trn_convolve2d_f32_dev": [_vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp],
     "trn_attention_f32": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, C.c_float, C.c_int],
     "trn_attention_f32_dev": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, C.c_float, C.c_int, _vp],
@@ -507,6 +508,18 @@ class Matrix:
         out = np.empty(orows * ocols, np.float32)
         check(lib.trn_convolve2d_f32(_ptr(self.data), self._rows, self._cols, _ptr(kernel.data), kernel._rows, kernel._cols, _ptr(out)))
         return Matrix(orows, ocols, out)
+
+    def embedding_lookup(self, indices) -> "Matrix":
+        """Matrix::embedding_lookup (src/matrix.rs:2008): rows of the table selected by `indices` (usize)."""
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64).reshape(-1))
+        out = np.empty(idx.size * self._cols, np.float32)
+        check(lib.trn_embedding_lookup_f32(_ptr(self.data), self._rows, self._cols, idx.ctypes.data, idx.size, _ptr(out)))
+        return Matrix(idx.size, self._cols, out)
+
+    def embedding_lookup_sparse(self, indices):
+        """Matrix::embedding_lookup_sparse (src/matrix.rs:2059): (embeddings, sorted unique indices)."""
+        emb = self.embedding_lookup(indices)
+        return emb, sorted(set(int(i) for i in np.asarray(indices, dtype=np.uint64).reshape(-1)))
 
     @staticmethod
     def vecmat(v: Vector, m: "Matrix") -> Vector:

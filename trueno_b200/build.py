@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtrueno_cuda.so")
 OBJ_DIR = os.path.join(HERE, "_build")
-SOURCES = ["context.cu", "reduce.cu", "map.cu", "softmax.cu", "gemm_simt.cu", "gemm_tc.cu", "batch.cu", "peer.cu", "conv.cu", "attention.cu", "eigen.cu", "api.cu"]
+SOURCES = ["context.cu", "reduce.cu", "map.cu", "softmax.cu", "gemm_simt.cu", "gemm_tc.cu", "batch.cu", "peer.cu", "conv.cu", "attention.cu", "eigen.cu", "gather.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

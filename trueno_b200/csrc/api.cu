@@ -1054,6 +1054,34 @@ int trn_vecmat_f32(const float* v, size_t v_len, const float* a, size_t rows, si
     return download(y, dy.p, cols, c->stream);
 }
 
+// Matrix::embedding_lookup (src/matrix.rs:2008): out[r, :] = table[indices[r], :].  An index >= rows ->
+// InvalidInput("Index {} at position {} is out of bounds for embedding table with {} rows") from the host-slice call
+// (indices are host memory there); the resident twin cannot see its indices and writes a zero row instead.
+int trn_embedding_lookup_f32_dev(const float* table, size_t rows, size_t cols, const uint64_t* indices, size_t n_indices,
+                                 float* out, void* stream) {
+    TRN_TRY(need_ctx());
+    return launch_gather_rows(table, rows, cols, indices, n_indices, out, resolve_stream(stream));
+}
+int trn_embedding_lookup_f32(const float* table, size_t rows, size_t cols, const uint64_t* indices, size_t n_indices,
+                             float* out) {
+    for (size_t i = 0; i < n_indices; ++i)
+        if (indices[i] >= rows)
+            return fail(TRN_INVALID_INPUT, "Index %llu at position %zu is out of bounds for embedding table with %zu rows",
+                        (unsigned long long)indices[i], i, rows);
+    TRN_TRY(need_ctx());
+    if (n_indices == 0 || cols == 0) return TRN_OK;
+    TRN_HOST_LOCK();
+    Context* c = ctx();
+    DevTemp dt(c->stream), dout(c->stream), didx(c->stream);
+    TRN_TRY(dt.alloc(rows * cols));
+    TRN_TRY(dout.alloc(n_indices * cols));
+    TRN_TRY(didx.alloc(2 * n_indices));   // u64 indices in a float-typed scratch block
+    TRN_TRY(upload(dt.p, table, rows * cols, c->stream));
+    TRN_CUDA(cudaMemcpyAsync(didx.p, indices, n_indices * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    TRN_TRY(launch_gather_rows(dt.p, rows, cols, reinterpret_cast<const uint64_t*>(didx.p), n_indices, dout.p, c->stream));
+    return download(out, dout.p, n_indices * cols, c->stream);
+}
+
 // Vector::layer_norm (src/vector.rs:1316): `rows` vectors of `cols` elements sharing gamma / beta (rows == 1 is
 // exactly the reference call).  Empty -> EmptyVector; gamma / beta length != cols -> SizeMismatch{cols, len}.
 static int check_layer_norm(size_t rows, size_t cols, size_t ng, size_t nb) {

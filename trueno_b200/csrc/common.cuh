@@ -108,6 +108,9 @@ int launch_map(Map op, const float* a, const float* b, const float* c, float* ou
 int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows, size_t cols, cudaStream_t s);
 
 int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaStream_t s);
+// Matrix::embedding_lookup (gather.cu): out[r, :] = table[idx[r], :]; an index >= rows yields a zero row
+int launch_gather_rows(const float* table, size_t rows, size_t cols, const uint64_t* idx, size_t n_idx, float* out,
+                       cudaStream_t s);
 int launch_convolve2d(const float* in, size_t rows, size_t cols, const float* kernel, size_t kr, size_t kc, float* out,
                       cudaStream_t s);
 // fused attention (attention.cu): q, k, v, out [heads][seq][d]; engine 0 auto, 1 SIMT, 2 tcgen05
