@@ -373,6 +373,16 @@ TRN_API int trn_layer_norm_rows_f32(const float* a, const float* gamma, size_t g
 TRN_API int trn_layer_norm_rows_f32_dev(const float* a, const float* gamma, size_t gamma_len, const float* beta,
                                         size_t beta_len, float eps, float* out, size_t rows, size_t cols, void* stream);
 
+/* ---- ONE Vector::softmax / log_softmax sharded over several GPUs -----------------
+ * (src/vector.rs:1516 / :1581 on a vector whose contiguous slices live on different GPUs.)  Step 1, per rank:
+ * pair_out[0] = max of the slice, pair_out[1] = sum of exp(x - max) over the slice (device memory, 8-byte aligned).
+ * The ranks all_gather their pairs (rank order).  Step 2, per rank: out = exp(x - M) / S or (x - M) - ln S with (M, S)
+ * the fold of all `npairs` pairs, evaluated in rank order by every rank -> identical bits everywhere.  a and out must
+ * share their alignment modulo 16 bytes.  Empty slice -> TRN_EMPTY_VECTOR. */
+TRN_API int trn_softmax_slice_stats_f32_dev(const float* a, size_t n, float* pair_out, void* stream);
+TRN_API int trn_softmax_slice_apply_f32_dev(const float* a, size_t n, const float* pairs, size_t npairs, int log_variant,
+                                            float* out, void* stream);
+
 /* ---- fused slice reduction + exchange over NVLink peer memory -----------------
  * One process per GPU.  Each process exports a small mailbox (trn_comm_local_handle: a 64-byte CUDA IPC
  * handle), the host all-gathers the handles once, trn_comm_create maps the peers' mailboxes.  The

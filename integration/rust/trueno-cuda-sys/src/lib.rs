@@ -216,6 +216,9 @@ extern "C" {
     pub fn trn_minmax_normalize_f32(a: *const f32, n: usize, out: *mut f32) -> c_int;
     pub fn trn_layer_norm_simple_rows_f32(a: *const f32, eps: f32, out: *mut f32, rows: usize, cols: usize) -> c_int;
     pub fn trn_layer_norm_simple_rows_f32_dev(a: *const f32, eps: f32, out: *mut f32, rows: usize, cols: usize, stream: *mut c_void) -> c_int;
+    pub fn trn_softmax_slice_stats_f32_dev(a: *const f32, n: usize, pair_out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_softmax_slice_apply_f32_dev(a: *const f32, n: usize, pairs: *const f32, npairs: usize, log_variant: c_int,
+                                           out: *mut f32, stream: *mut c_void) -> c_int;
     pub fn trn_embedding_lookup_f32(table: *const f32, rows: usize, cols: usize, indices: *const u64, n_indices: usize,
                                     out: *mut f32) -> c_int;
     pub fn trn_embedding_lookup_f32_dev(table: *const f32, rows: usize, cols: usize, indices: *const u64, n_indices: usize,

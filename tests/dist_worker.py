@@ -66,6 +66,30 @@ def main() -> int:
             for _ in range(5):
                 assert int(vn.argmax()) == 0 and int(vn.argmin()) == 0
 
+    # ---- ONE softmax / log_softmax vector sharded over the ranks: slice stats -> all_gather of pairs -> fold + write
+    for n in (1 << 22, (1 << 22) + 37, 1001):
+        a = (rng.standard_normal(n) * 4).astype(f32)
+        a[n - 3] = 11.0          # the maximum lives in the last rank's slice
+        sh = par.shard_range(n, rank, world, align=4)
+        va = par.ShardedVector(torch.from_numpy(a[sh.start:sh.start + sh.count]).to(dev), sh)
+        arg = (a - a.max()).astype(f32).astype(np.float64)
+        e64 = np.exp(arg)
+        for log in (False, True):
+            got = va.softmax(log=log)
+            torch.cuda.synchronize()
+            g64 = got.cpu().numpy().astype(np.float64)
+            want = (arg - np.log(e64.sum()) if log else e64 / e64.sum())[sh.start:sh.start + sh.count]
+            ulp = np.spacing(np.abs(want).astype(f32)).astype(np.float64)
+            if log:
+                assert np.all(np.abs(g64 - want) <= 4 * ulp + 2.0 ** -20)
+            else:
+                assert np.all(np.abs(g64 - want) <= np.minimum(1e-6, 8 * ulp + 1e-45))
+            # slices of every rank add up to one; the same bits normalise every slice
+            tot = torch.tensor([g64.sum() if not log else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(tot)
+            if not log:
+                assert abs(float(tot) - 1.0) < 1e-5
+
     # ---- config 3 (scaled): batch x head ranges, no collective; every rank checks its own heads ---------
     B, H, m, k, n = 2, 8, 256, 128, 384
     A = rng.uniform(-1, 1, (B * H, m, k)).astype(f32)

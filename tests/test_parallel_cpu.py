@@ -75,6 +75,16 @@ def _worker(rank, world, port, cases, results):
                 v, i = f32(-np.inf if is_max else np.inf), par.NO_CANDIDATE
             gv, gi = par.combine_arg(torch.tensor([v], dtype=torch.float32), torch.tensor([i], dtype=torch.int64), is_max)
             res += [float(gv), int(gi)]
+        # ONE softmax vector over the ranks: all_gather of (max, sum of exp) pairs in rank order
+        with np.errstate(all="ignore"):
+            if sh.count:
+                m = f32(np.fmax.reduce(la))
+                pair = [m, f32(np.sum(np.exp((la - m).astype(f32)), dtype=np.float64))]
+            else:
+                pair = [f32(-np.inf), f32(0)]
+        pairs = par.gather_softmax_pairs(torch.tensor(pair, dtype=torch.float32))
+        assert pairs.shape == (world, 2)
+        res.append(pairs.numpy().astype(np.float64).tolist())
         out.append(res)
     if rank == 0:
         results.put(out)
@@ -103,6 +113,7 @@ def _cases():
 def test_exchange_steps_over_gloo(world):
     import oracle
     from oracle import SCALAR
+    from trueno_b200.parallel import shard_range
     orc = oracle.get()
     cases = _cases()
     ctx = mp.get_context("spawn")
@@ -116,7 +127,23 @@ def test_exchange_steps_over_gloo(world):
         p.join(60)
         assert p.exitcode == 0
     for (a, b), res in zip(cases, got):
-        dot, nrm, mx, vmax, imax, vmin, imin = res
+        dot, nrm, mx, vmax, imax, vmin, imin, pairs = res
+        # the gathered pairs are the slices' pairs in rank order, and their fold is the whole vector's (max, sum of exp)
+        with np.errstate(all="ignore"):
+            fold_m, fold_s = -np.inf, 0.0
+            for r, (pm, ps) in enumerate(pairs):
+                sh = shard_range(a.size, r, world, align=4)
+                la = a[sh.start:sh.start + sh.count]
+                if sh.count and not np.isnan(la).all():
+                    assert pm == np.fmax.reduce(la) or (np.isnan(pm) and np.isnan(np.fmax.reduce(la)))
+                mn = max(fold_m, pm) if not np.isnan(pm) else fold_m
+                ref = 0.0 if mn == -np.inf else mn
+                fold_s = fold_s * np.exp(fold_m - ref) + ps * np.exp(pm - ref)
+                fold_m = mn
+            if np.isfinite(a).all():
+                tm = a.max()
+                ts = np.sum(np.exp((a - tm).astype(np.float64)))
+                assert fold_m == tm and abs(fold_s - ts) <= 1e-6 * ts
         tdot, adot = orc.f64_dot(a, b)
         if np.isfinite(tdot):
             assert abs(dot - tdot) <= 1e-5 * adot + 1e-30

@@ -309,6 +309,54 @@ def test_softmax_rows_misaligned_base(trn, rows, cols, mis_in, mis_out):
             assert np.all(np.abs(got - want) <= np.minimum(1e-6, 8 * ulp(want) + 1e-45))
 
 
+@pytest.mark.parametrize("n,cuts", [(1000, [0, 300, 1000]), (1 << 20, [0, 1 << 18, 1 << 19, 1 << 20]), (3_000_001, [0, 1_000_001, 1_000_002, 3_000_001]),
+                                    (100, [0, 1, 99, 100])])
+def test_softmax_slices_of_one_vector(trn, n, cuts):
+    """trn_softmax_slice_{stats,apply}_f32_dev: the vector cut into slices (as ranks would hold them; unaligned cuts ->
+    window kernels), pairs concatenated in slice order, every slice normalised by their fold == softmax of the whole."""
+    torch = pytest.importorskip("torch")
+    trn.check(trn.lib.trn_cuda_init(0))
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream or 1
+    g = torch.Generator(device="cpu").manual_seed(n)
+    host = (torch.randn(n, generator=g) * 4).float()
+    host[n // 2] = 9.0
+    x = host.to(dev)
+    L = trn.lib
+    k = len(cuts) - 1
+    pairs = torch.empty(k, 2, device=dev)
+    for i in range(k):
+        sl = x[cuts[i]:cuts[i + 1]]
+        trn.check(L.trn_softmax_slice_stats_f32_dev(sl.data_ptr(), sl.numel(), pairs[i].data_ptr(), st))
+    torch.cuda.synchronize()
+    hp = pairs.cpu().numpy().astype(np.float64)
+    xs = host.numpy()
+    for i in range(k):
+        seg = xs[cuts[i]:cuts[i + 1]]
+        assert hp[i, 0] == seg.max()
+        assert abs(hp[i, 1] - np.exp((seg - seg.max()).astype(np.float64)).sum()) <= 1e-5 * hp[i, 1]
+    for log in (0, 1):
+        y = torch.full((n + 8,), 7.0, device=dev)
+        for i in range(k):
+            sl = x[cuts[i]:cuts[i + 1]]
+            # the output slice shares the input slice's alignment (both are views at the same element offset + 4)
+            out = y[4 + cuts[i]: 4 + cuts[i + 1]]
+            trn.check(L.trn_softmax_slice_apply_f32_dev(sl.data_ptr(), sl.numel(), pairs.data_ptr(), k, log, out.data_ptr(), st))
+        torch.cuda.synchronize()
+        got = y.cpu().numpy()
+        assert np.all(got[:4] == 7.0) and np.all(got[4 + n:] == 7.0)
+        want = _softmax_ref(xs.reshape(1, n), log=bool(log)).reshape(-1)
+        g64 = got[4:4 + n].astype(np.float64)
+        if log:
+            assert np.all(np.abs(g64 - want) <= 4 * ulp(want) + 2.0 ** -20)
+        else:
+            assert np.all(np.abs(g64 - want) <= np.minimum(1e-6, 8 * ulp(want) + 1e-45))
+            assert abs(g64.sum() - 1) < 1e-5
+    # contract errors
+    assert L.trn_softmax_slice_apply_f32_dev(x.data_ptr(), n, pairs.data_ptr(), k, 0, y.data_ptr() + 4, st) == 2   # alignments differ
+    assert L.trn_softmax_slice_stats_f32_dev(x.data_ptr(), 0, pairs.data_ptr(), st) == 3                            # EmptyVector
+
+
 def test_softmax_window_kernels_match_fallback():
     """A/B: the vector / window / long kernels against the three-pass fallback (TRN_ROWS_GENERIC=1) in a subprocess."""
     import os

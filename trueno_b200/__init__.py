@@ -117,6 +117,8 @@ _SIGNATURES = {
     "trn_norm_l2_allreduce_f32_dev": [_vp, _vp, _sz, _vp, _vp],
     "trn_argmax_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
     "trn_argmin_allgather_f32_dev": [_vp, _vp, _sz, C.c_uint64, _vp, _vp, _vp],
+    "trn_softmax_slice_stats_f32_dev": [_vp, _sz, _vp, _vp],
+    "trn_softmax_slice_apply_f32_dev": [_vp, _sz, _vp, _sz, C.c_int, _vp, _vp],
     "trn_embedding_lookup_f32": [_vp, _sz, _sz, _vp, _sz, _vp], "trn_embedding_lookup_f32_dev": [_vp, _sz, _sz, _vp, _sz, _vp, _vp],
     "trn_convolve2d_f32": [_vp, _sz, _sz, _vp, _sz, _sz, _vp], "trn_convolve2d_f32_dev": [_vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp],
     "trn_attention_f32": [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _sz, C.c_float, C.c_int],

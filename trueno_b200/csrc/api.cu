@@ -298,6 +298,20 @@ int trn_softmax_rows_f32_dev(const float* a, float* out, size_t rows, size_t col
     TRN_TRY(need_ctx());
     return launch_softmax_rows(0, a, out, rows, cols, resolve_stream(stream));
 }
+// One Vector::softmax / log_softmax sharded over several GPUs: stats of this rank's slice, then — after
+// the ranks have all_gathered their pairs — normalisation of the slice by the fold of all pairs.
+int trn_softmax_slice_stats_f32_dev(const float* a, size_t n, float* pair_out, void* stream) {
+    TRN_TRY(check_nonempty_emptyvec(n));
+    TRN_TRY(need_ctx());
+    return launch_softmax_slice_stats(a, n, pair_out, resolve_stream(stream));
+}
+int trn_softmax_slice_apply_f32_dev(const float* a, size_t n, const float* pairs, size_t npairs, int log_variant, float* out,
+                                    void* stream) {
+    TRN_TRY(check_nonempty_emptyvec(n));
+    if (npairs == 0) return fail(TRN_INVALID_INPUT, "no (max, sum) pairs to normalise by");
+    TRN_TRY(need_ctx());
+    return launch_softmax_slice_apply(a, n, pairs, npairs, log_variant, out, resolve_stream(stream));
+}
 int trn_log_softmax_rows_f32_dev(const float* a, float* out, size_t rows, size_t cols, void* stream) {
     TRN_TRY(check_nonempty_emptyvec(rows * cols));
     TRN_TRY(need_ctx());

@@ -106,6 +106,11 @@ int launch_map(Map op, const float* a, const float* b, const float* c, float* ou
                cudaStream_t s);
 
 int launch_softmax_rows(int log_variant, const float* a, float* out, size_t rows, size_t cols, cudaStream_t s);
+// one vector sharded over ranks: slice -> one (max, sum-of-exp relative to it) pair; then normalise the slice by the
+// fold of every rank's pair (pairs: npairs x {max, sum}, rank order)
+int launch_softmax_slice_stats(const float* a, size_t n, float* pair_out, cudaStream_t s);
+int launch_softmax_slice_apply(const float* a, size_t n, const float* pairs, size_t npairs, int log_variant, float* out,
+                               cudaStream_t s);
 
 int launch_transpose(const float* a, size_t rows, size_t cols, float* out, cudaStream_t s);
 // Matrix::embedding_lookup (gather.cu): out[r, :] = table[idx[r], :]; an index >= rows yields a zero row

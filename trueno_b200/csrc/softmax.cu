@@ -697,11 +697,10 @@ softmax_split_stats_kernel(const float* __restrict__ in, size_t rows, size_t col
 template <bool LOG, bool WIN>
 __global__ void __launch_bounds__(kThreads)
 softmax_split_write_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0,
-                           size_t seg, const float2* __restrict__ ws) {
+                           size_t seg, const float2* __restrict__ ws, unsigned P) {
     constexpr int U = 4;
     __shared__ float s_w[kThreads / 32];
     const size_t row = blockIdx.y;
-    const unsigned P = gridDim.x;
     // the row's (M, S) from its P segment pairs: thread t folds pairs t, t + 256, ... in order, then fixed block trees
     float m = -INFINITY, s = 0.f;
     for (unsigned p = threadIdx.x; p < P; p += kThreads) {
@@ -751,11 +750,89 @@ static int launch_split(const float* a, float* out, size_t rows, size_t cols, un
     TRN_TRY(scratch_alloc(reinterpret_cast<void**>(&ws), rows * P * sizeof(float2), s));
     const dim3 grid((unsigned)P, (unsigned)rows);
     softmax_split_stats_kernel<WIN><<<grid, kThreads, 0, s>>>(a, rows, cols, mis0, seg, ws);
-    softmax_split_write_kernel<LOG, WIN><<<grid, kThreads, 0, s>>>(a, out, rows, cols, mis0, seg, ws);
+    softmax_split_write_kernel<LOG, WIN><<<grid, kThreads, 0, s>>>(a, out, rows, cols, mis0, seg, ws, (unsigned)P);
     count_launch(2);
     const cudaError_t e = cudaGetLastError();
     TRN_TRY(scratch_free(ws, s));
     TRN_CUDA(e);
+    return TRN_OK;
+}
+
+// ---- one vector sharded over several GPUs ("a single 2^30 vector softmax would need two exchanges") ----
+// The split-row kernels with the exchange in the middle: every rank folds its slice to ONE (max, sum) pair
+// (launch_softmax_slice_stats), the ranks all_gather their pairs (8 bytes each), and every rank folds the gathered
+// pairs in rank order inside its write kernel (launch_softmax_slice_apply) — so all ranks normalise by the same bits.
+__global__ void __launch_bounds__(kThreads)
+softmax_fold_pairs_kernel(const float2* __restrict__ ws, unsigned P, float2* __restrict__ out) {
+    __shared__ float s_w[kThreads / 32];
+    float m = -INFINITY, s = 0.f;
+    for (unsigned p = threadIdx.x; p < P; p += kThreads) {
+        const float2 q = ws[p];
+        online_merge(m, s, q.x, q.y);
+    }
+    const float M = block_max_256(m, s_w);
+    const float ref = M == -INFINITY ? 0.f : M;
+    const float S = block_sum_256(s * expf(m - ref), s_w);
+    if (threadIdx.x == 0) *out = make_float2(M, S);
+}
+
+static void split_geometry(size_t n, int sm_count, size_t& P, size_t& seg) {
+    const size_t nvec = n / 4;
+    const size_t unit = (size_t)kThreads * 4;
+    P = (nvec + 2 * unit - 1) / (2 * unit);
+    const size_t cap = (size_t)sm_count * 8;
+    if (P > cap) P = cap;
+    if (P < 1) P = 1;
+    seg = ((nvec + P - 1) / P + unit - 1) / unit * unit;
+    if (seg == 0) seg = unit;   // a slice shorter than one vector: edge elements only
+    P = (nvec + seg - 1) / seg;
+    if (P < 1) P = 1;
+}
+
+int launch_softmax_slice_stats(const float* a, size_t n, float* pair_out, cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    if (reinterpret_cast<uintptr_t>(a) & 3u) return fail(TRN_INVALID_INPUT, "slice pointer is not 4-byte aligned");
+    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(a) >> 2) & 3u);
+    size_t P, seg;
+    split_geometry(n, c->sm_count, P, seg);
+    float2* ws = nullptr;
+    TRN_TRY(scratch_alloc(reinterpret_cast<void**>(&ws), P * sizeof(float2), s));
+    const dim3 grid((unsigned)P, 1);
+    if (mis == 0 && n % 4 == 0) softmax_split_stats_kernel<false><<<grid, kThreads, 0, s>>>(a, 1, n, 0u, seg, ws);
+    else                        softmax_split_stats_kernel<true><<<grid, kThreads, 0, s>>>(a, 1, n, mis, seg, ws);
+    softmax_fold_pairs_kernel<<<1, kThreads, 0, s>>>(ws, (unsigned)P, reinterpret_cast<float2*>(pair_out));
+    count_launch(2);
+    const cudaError_t e = cudaGetLastError();
+    TRN_TRY(scratch_free(ws, s));
+    TRN_CUDA(e);
+    return TRN_OK;
+}
+
+int launch_softmax_slice_apply(const float* a, size_t n, const float* pairs, size_t npairs, int log_variant, float* out,
+                               cudaStream_t s) {
+    Context* c = ctx();
+    if (!c) return TRN_GPU_ERROR;
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out)) & 3u)
+        return fail(TRN_INVALID_INPUT, "slice pointer is not 4-byte aligned");
+    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(a) >> 2) & 3u);
+    if (mis != (unsigned)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u))
+        return fail(TRN_INVALID_INPUT, "input and output slices must share their alignment modulo 16 bytes");
+    if (reinterpret_cast<uintptr_t>(pairs) & 7u) return fail(TRN_INVALID_INPUT, "pairs pointer is not 8-byte aligned");
+    size_t P, seg;
+    split_geometry(n, c->sm_count, P, seg);
+    const dim3 grid((unsigned)P, 1);
+    const float2* ws = reinterpret_cast<const float2*>(pairs);
+    const bool win = !(mis == 0 && n % 4 == 0);
+    if (log_variant) {
+        if (win) softmax_split_write_kernel<true, true><<<grid, kThreads, 0, s>>>(a, out, 1, n, mis, seg, ws, (unsigned)npairs);
+        else     softmax_split_write_kernel<true, false><<<grid, kThreads, 0, s>>>(a, out, 1, n, 0u, seg, ws, (unsigned)npairs);
+    } else {
+        if (win) softmax_split_write_kernel<false, true><<<grid, kThreads, 0, s>>>(a, out, 1, n, mis, seg, ws, (unsigned)npairs);
+        else     softmax_split_write_kernel<false, false><<<grid, kThreads, 0, s>>>(a, out, 1, n, 0u, seg, ws, (unsigned)npairs);
+    }
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
     return TRN_OK;
 }
 

@@ -10,6 +10,8 @@ The reference has no multi-GPU code at all; this module impleme
   argmin / argmax                      contiguous slices, global u64 index  all_gather of (value, index) pairs,
                                                                             best value then LOWEST index wins
   softmax / log_softmax rows, maps     row / slice blocks                   none
+  ONE softmax / log_softmax vector     contiguous slices of the vector      all_gather of (max, sum-of-exp) pairs,
+                                                                            folded in rank order by every rank
   batched_matmul_4d                    contiguous ranges of batch*head      none
   matmul (large)                       C / A row blocks, B replicated       none
 
@@ -130,6 +132,17 @@ def pick_arg(vals: torch.Tensor, idxs: torch.Tensor, is_max: bool) -> tuple[torc
 
 
 # ---- fused exchange over NVLink peer memory ------------------------------------------------------------
+def gather_softmax_pairs(pair: torch.Tensor) -> torch.Tensor:
+    """all_gather of one (max, sum of exp(x - max)) pair per rank -> [world, 2] in rank order (CPU tensors under gloo
+    in the tests; on the GPU the collective is enqueued on the current stream behind the stats kernel)."""
+    w = world_size()
+    if w == 1:
+        return pair.reshape(1, 2)
+    out = torch.empty(2 * w, dtype=pair.dtype, device=pair.device)
+    dist.all_gather_into_tensor(out, pair.reshape(2).contiguous())
+    return out.reshape(w, 2)
+
+
 class PeerComm:
     """Peer mailboxes for the fused "slice reduction + exchange" kernels (csrc/peer.cu, csrc/reduce.cu).
     Every rank exports a 64-byte CUDA IPC handle; ONE all_gather of those handles at construction is all the
@@ -249,6 +262,25 @@ class ShardedVector:
         trn.check(L.trn_arg_combine_f32_dev(pairs.data_ptr(), w, int(is_max), self._i64.data_ptr(), self._f32.data_ptr(),
                                             self._stream()))
         return self._f32, self._i64
+
+    def softmax(self, log: bool = False, out: "torch.Tensor | None" = None) -> torch.Tensor:
+        """Vector::softmax / log_softmax (src/vector.rs:1516 / :1581) of the WHOLE sharded vector; returns this rank's
+        slice of the result.  slice stats -> one all_gather of 8-byte pairs -> fold + write kernel, all on the current
+        stream; every rank folds the same pairs in the same order, so all ranks normalise by identical bits."""
+        import trueno_b200 as trn
+        L = trn.lib
+        if out is None:
+            out = torch.empty_like(self.local)
+        n = self.local.numel()
+        pair = torch.empty(2, dtype=torch.float32, device=self.local.device)
+        trn.check(L.trn_softmax_slice_stats_f32_dev(self.local.data_ptr(), n, pair.data_ptr(), self._stream()))
+        pairs = gather_softmax_pairs(pair)
+        trn.check(L.trn_softmax_slice_apply_f32_dev(self.local.data_ptr(), n, pairs.data_ptr(), pairs.shape[0], int(log),
+                                                    out.data_ptr(), self._stream()))
+        return out
+
+    def log_softmax(self, out: "torch.Tensor | None" = None) -> torch.Tensor:
+        return self.softmax(log=True, out=out)
 
     def argmax(self) -> torch.Tensor:
         return self._arg(True)[1]
