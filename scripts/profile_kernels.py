@@ -83,6 +83,11 @@ def main():
         g, bb = torch.randn(16384, device="cuda"), torch.randn(16384, device="cuda")
         keep += [w, wo, g, bb]
         ops.append(lambda: trn.check(L.trn_layer_norm_rows_f32_dev(w.data_ptr(), g.data_ptr(), 16384, bb.data_ptr(), 16384, 1e-5, wo.data_ptr(), 8192, 16384, st)))
+        tab = torch.randn(50257, 768, device="cuda")
+        tidx = torch.randint(0, 50257, (1 << 19,), device="cuda", dtype=torch.int64)
+        tout = torch.empty(1 << 19, 768, device="cuda")
+        keep += [tab, tidx, tout]
+        ops.append(lambda: trn.check(L.trn_embedding_lookup_f32_dev(tab.data_ptr(), 50257, 768, tidx.data_ptr(), tidx.numel(), tout.data_ptr(), st)))
         ops.append(lambda: trn.check(L.trn_mish_f32_dev(w.data_ptr(), w.numel(), wo.data_ptr(), st)))
         ops.append(lambda: trn.check(L.trn_hardswish_f32_dev(w.data_ptr(), w.numel(), wo.data_ptr(), st)))
     if "matvec" in which:

@@ -164,6 +164,24 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+// L2 eviction policies for two-pass kernels: pass 1 asks L2 to KEEP what it streams in (evict_last), pass 2 reads it
+// back and lets it go (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_drop() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_stream_hint(const float4* p, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
 // 128-bit streaming store (evict-first: the output is not re-read by this kernel)
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"

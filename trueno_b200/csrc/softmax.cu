@@ -585,7 +585,7 @@ __device__ __forceinline__ float4 normalise_raw4(const float4& x, float M, float
     return y;
 }
 
-template <int CS, bool LOG, bool WIN>
+template <int CS, bool LOG, bool WIN, bool HINT>
 __global__ void __launch_bounds__(kThreads)
 softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
     constexpr int U = 4;
@@ -597,6 +597,7 @@ softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, 
     const size_t cluster_id = blockIdx.x / CS;
     const size_t num_clusters = gridDim.x / CS;
     const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const uint64_t keep = l2_policy_keep(), drop = l2_policy_drop();   // pass 1 parks the row in L2, pass 2 releases it
 
     for (size_t row = cluster_id; row < rows; row += num_clusters) {
         const RowView<WIN> rv(in, out, row, cols, mis0);
@@ -611,7 +612,7 @@ softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, 
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
-                x[j] = v < nvec ? ld_stream(rv.vsrc + v) : ninf4;
+                x[j] = v < nvec ? (HINT ? ld_stream_hint(rv.vsrc + v, keep) : ld_stream(rv.vsrc + v)) : ninf4;
             }
             online_step<U>(x, m, s);
         }
@@ -644,7 +645,7 @@ softmax_rows_long_kernel(const float* __restrict__ in, float* __restrict__ out, 
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
-                x[j] = v < nvec ? ld_stream(rv.vsrc + v) : ninf4;
+                x[j] = v < nvec ? (HINT ? ld_stream_hint(rv.vsrc + v, drop) : ld_stream(rv.vsrc + v)) : ninf4;
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
@@ -674,13 +675,14 @@ softmax_split_stats_kernel(const float* __restrict__ in, size_t rows, size_t col
     const size_t v0 = (size_t)blockIdx.x * seg;
     const size_t v1 = v0 + seg < rv.nvec ? v0 + seg : rv.nvec;
     const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const uint64_t keep = l2_policy_keep();   // the write launch re-reads the row: park it in L2 if it fits
     float m = -INFINITY, s = 0.f;
     for (size_t base = v0; base < v1; base += (size_t)kThreads * U) {
         float4 x[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const size_t v = base + (size_t)j * kThreads + threadIdx.x;
-            x[j] = v < v1 ? ld_stream(rv.vsrc + v) : ninf4;
+            x[j] = v < v1 ? ld_stream_hint(rv.vsrc + v, keep) : ninf4;
         }
         online_step<U>(x, m, s);
     }
@@ -716,12 +718,13 @@ softmax_split_write_kernel(const float* __restrict__ in, float* __restrict__ out
     const size_t v1 = v0 + seg < rv.nvec ? v0 + seg : rv.nvec;
     const float lse = LOG ? logf(S) : 0.f;
     const float inv = LOG ? 0.f : __frcp_rn(S);
+    const uint64_t drop = l2_policy_drop();
     for (size_t base = v0; base < v1; base += (size_t)kThreads * U) {
         float4 x[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const size_t v = base + (size_t)j * kThreads + threadIdx.x;
-            x[j] = v < v1 ? ld_stream(rv.vsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[j] = v < v1 ? ld_stream_hint(rv.vsrc + v, drop) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
@@ -898,12 +901,19 @@ static int env_int(const char* name) {   // tuning knob for scripts/exp/exp_long
 
 template <bool LOG, bool WIN>
 static int launch_long(int cs, const float* a, float* out, size_t rows, size_t cols, unsigned mis0, cudaStream_t s) {
+    // L2 eviction hints (pass 1 evict_last, pass 2 evict_first) while the rows in flight can stay in L2: 65 536 columns
+    // 4.8 -> 5.9 TB/s, 128 256: 4.8 -> 5.4, 262 144: 4.5 -> 4.9; from ~3 MB rows on they thrash (2^20 columns 4.04 -> 3.94)
+    const bool hint = env_int("TRN_ROWS_L2HINT") != 1 && cols < 786432;   // knob for scripts/exp/exp_long_rows.py: 1 = plain loads
+#define TRN_LONG(CS_)                                                                                                   \
+    return hint ? launch_clustered(softmax_rows_long_kernel<CS_, LOG, WIN, true>, CS_, a, out, rows, cols, mis0, s)     \
+                : launch_clustered(softmax_rows_long_kernel<CS_, LOG, WIN, false>, CS_, a, out, rows, cols, mis0, s)
     switch (cs) {
-        case 1: return launch_clustered(softmax_rows_long_kernel<1, LOG, WIN>, 1, a, out, rows, cols, mis0, s);
-        case 2: return launch_clustered(softmax_rows_long_kernel<2, LOG, WIN>, 2, a, out, rows, cols, mis0, s);
-        case 4: return launch_clustered(softmax_rows_long_kernel<4, LOG, WIN>, 4, a, out, rows, cols, mis0, s);
-        default: return launch_clustered(softmax_rows_long_kernel<8, LOG, WIN>, 8, a, out, rows, cols, mis0, s);
+        case 1: TRN_LONG(1);
+        case 2: TRN_LONG(2);
+        case 4: TRN_LONG(4);
+        default: TRN_LONG(8);
     }
+#undef TRN_LONG
 }
 
 template <bool LOG, bool WIN>
