@@ -206,7 +206,10 @@ def test_pixel_fkr_softmax(trn, oracle):
                                        (9, 77), (64, 1018), (5, 1019), (5, 1023), (3, 4099), (5, 16387), (5, 32001),
                                        (33, 50257), (3, 65530), (3, 65531), (3, 65537), (4, 128256), (2, 151936),
                                        (2, 262144), (1, 1_000_003), (40, 131072), (19, 66666), (20, 65537), (20, 65540),
-                                       (1, 4_194_304 + 4), (2, 3_000_001)])
+                                       (1, 4_194_304 + 4), (2, 3_000_001),
+                                       # two-pass cluster kernel at every cluster size (1 / 2 / 4 / 8 CTAs per row), aligned and window
+                                       (7, 16388), (9, 20480), (160, 20484), (150, 36001), (200, 40000), (90, 50257), (80, 65540),
+                                       (76, 100000), (40, 100004), (38, 200_003)])
 def test_softmax_rows_vs_oracle(trn, oracle, rows, cols):
     rng = np.random.default_rng(rows * 131 + cols)
     x = (rng.standard_normal((rows, cols)) * 4).astype(f32)
@@ -254,7 +257,7 @@ def _softmax_ref(x, log=False):
         return arg - np.log(ssum) if log else e / ssum
 
 
-@pytest.mark.parametrize("rows", [6, 24], ids=["few_rows", "many_rows"])   # few long rows: split kernels; many: cluster
+@pytest.mark.parametrize("rows", [6, 80], ids=["few_rows", "many_rows"])   # few long rows: split kernels; many: cluster
 @pytest.mark.parametrize("cols", [77, 5001, 50257, 70000, 70001, 131072, 300_001])
 def test_softmax_special_rows(trn, rows, cols):
     """-inf prefixes / blocks (online max must not manufacture NaN), an all -inf row and a +inf row (NaN, as the

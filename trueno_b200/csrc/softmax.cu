@@ -220,19 +220,21 @@ static int launch_cta(const float* a, float* out, size_t rows, size_t cols, unsi
 namespace ring {
 constexpr int kConsumers = 512;                 // 16 consumer warps
 constexpr int kRingThreads = kConsumers + 32;   // + 1 producer warp
-constexpr int kChunkVec = 2 * kConsumers;       // float4 per slot: two per consumer thread
-constexpr uint32_t kChunkBytes = kChunkVec * 16;  // 16 KiB
-constexpr int kMaxChunks = 8;                   // row <= 8 slots = 32 768 floats
-constexpr int kSlots = 14;                      // 224 KiB ring
-constexpr uint32_t kSmemBytes = kSlots * kChunkBytes + 2 * kSlots * 8 + 2 * 16 * 4 + 128;
+constexpr int kRowVec = 16 * kConsumers;        // a row is <= 16 float4 per consumer thread = 32 768 floats
+constexpr uint32_t kRingBytes = 224 * 1024;     // the ring: 28 / HPC slots of HPC * 8 KiB (HPC float4 per consumer thread per slot)
+constexpr uint32_t kSmemBytes = kRingBytes + 2 * 28 * 8 + 2 * 16 * 4 + 128;
 }  // namespace ring
 
 // WIN: the producer bulk-copies the aligned body of each row; the (up to six) edge elements are read from global
 // memory by consumer threads 0..5.
-template <bool LOG, bool WIN>
+template <bool LOG, bool WIN, int HPC>
 __global__ void __launch_bounds__(ring::kRingThreads, 1)
 softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
     using namespace ring;
+    constexpr int kChunkVec = HPC * kConsumers;
+    constexpr uint32_t kChunkBytes = kChunkVec * 16;
+    constexpr int kMaxChunks = 16 / HPC;
+    constexpr int kSlots = 28 / HPC;
     extern __shared__ uint8_t ring_smem_raw[];
     const uint32_t base = (smem_u32(ring_smem_raw) + 127u) & ~127u;
     uint8_t* gen = ring_smem_raw + (base - smem_u32(ring_smem_raw));
@@ -281,7 +283,7 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
         const unsigned nvec = (unsigned)rv.nvec;
         const unsigned nchunks = (nvec + kChunkVec - 1) / kChunkVec;
         float xe = rv.edge_load((unsigned)t, -INFINITY);
-        float4 x[2 * kMaxChunks];
+        float4 x[HPC * kMaxChunks];
         // ---- ring -> registers; each slot goes back to the producer as soon as it has been read
 #pragma unroll
         for (int j = 0; j < kMaxChunks; ++j) {
@@ -289,26 +291,27 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
                 mbar_wait(full_bar(slot), phase);
                 const uint32_t sb = base + slot * kChunkBytes;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < HPC; ++h) {
                     const unsigned v = j * kChunkVec + h * kConsumers + t;
                     float4 r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
                     if (v < nvec)
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sb + (h * kConsumers + t) * 16u));
-                    x[2 * j + h] = r;
+                    x[HPC * j + h] = r;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_bar(slot));
                 if (++slot == (uint32_t)kSlots) { slot = 0; phase ^= 1; }
             } else {
-                x[2 * j] = x[2 * j + 1] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+                for (int h = 0; h < HPC; ++h) x[HPC * j + h] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
             }
         }
 
         // ---- row max: warp tree, then a fixed-order fold of the 16 warp values in every thread
         float m = xe;
 #pragma unroll
-        for (int j = 0; j < 2 * kMaxChunks; ++j) m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+        for (int j = 0; j < HPC * kMaxChunks; ++j) m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
         m = warp_max(m);
         if (lane == 0) s_max[warp] = m;
         named_bar_sync(1, kConsumers);
@@ -319,7 +322,7 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
         // ---- exponentials and their sum.  Padding slots hold -inf -> expf(-inf) = 0 exactly.
         float part = 0.f;
 #pragma unroll
-        for (int j = 0; j < 2 * kMaxChunks; ++j) {
+        for (int j = 0; j < HPC * kMaxChunks; ++j) {
             float4 e;
             e.x = expf(x[j].x - m); e.y = expf(x[j].y - m); e.z = expf(x[j].z - m); e.w = expf(x[j].w - m);
             part += (e.x + e.y) + (e.z + e.w);
@@ -342,21 +345,21 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
         const float lse = LOG ? logf(sum) : 0.f;
         const float inv = LOG ? 0.f : __frcp_rn(sum);
 #pragma unroll
-        for (int j = 0; j < 2 * kMaxChunks; ++j) {
-            const unsigned v = (j >> 1) * kChunkVec + (j & 1) * kConsumers + t;
+        for (int j = 0; j < HPC * kMaxChunks; ++j) {
+            const unsigned v = j * kConsumers + t;   // = (j / HPC) * kChunkVec + (j % HPC) * kConsumers + t
             if (v < nvec) st_stream(rv.vdst + v, normalise4<LOG>(x[j], m, lse, inv));
         }
         if (WIN) rv.edge_store((unsigned)t, LOG ? (xe - m) - lse : xe * inv);
     }
 }
 
-template <bool LOG, bool WIN>
+template <bool LOG, bool WIN, int HPC>
 static int launch_ring(const float* a, float* out, size_t rows, size_t cols, unsigned mis0, int sm_count, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static const cudaError_t attr = cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG, WIN, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)ring::kSmemBytes);   // thread-safe, once
     TRN_CUDA(attr);
     const unsigned grid = (unsigned)(rows < (size_t)sm_count ? rows : (size_t)sm_count);
-    softmax_rows_ring_kernel<LOG, WIN><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols, mis0);
+    softmax_rows_ring_kernel<LOG, WIN, HPC><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols, mis0);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -927,12 +930,26 @@ static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, un
     if (nvec <= 512 * 8)           return launch_cta<512, 8, LOG, WIN>(a, out, rows, cols, mis0, s);
     // (a 1024-thread CTA holding a 32 000-float row measured 4.9 TB/s against the ring kernel's 6.0: one CTA
     //  per SM leaves nothing to overlap a row's load phase with)
+    // Rows longer than the register kernels hold (scripts/exp/exp_ring.py, scripts/exp/exp_long_cs.py):
+    //   * aligned rows of 28 672 < cols <= 32 768 (config 5: 32 000): the TMA ring kernel — 32 KiB slots for softmax,
+    //     16 KiB for log_softmax (5.98 / 6.07-6.13 TB/s at 32 000; the two-pass kernel ties there at 5.98 / 6.09);
+    //   * a few long rows: the split-row kernels;
+    //   * everything else: the two-pass cluster kernel, cluster size by row length — 1 CTA up to 20 480 columns
+    //     (17 000: 6.0 TB/s where the ring reached 4.1-4.4), 2 up to 43 008 (24 576: 6.15 vs 5.2-5.6), 4 up to 100 000,
+    //     8 beyond, 4 again from 786 432 (rows that no longer fit L2 between the passes).
     const int force_cs = env_int("TRN_ROWS_LONG_CS");
-    if (!force_cs && nvec <= (size_t)ring::kChunkVec * ring::kMaxChunks) return launch_ring<LOG, WIN>(a, out, rows, cols, mis0, sm_count, s);
-    if (!force_cs && rows * 8 <= (size_t)sm_count)   // too few rows to fill the machine with one cluster per row
+    const int force_hpc = env_int("TRN_RING_HPC");   // experiment knobs, read per call
+    if (!force_cs && (force_hpc || (!WIN && cols > 28672)) && nvec <= (size_t)ring::kRowVec) {
+        const int hpc = force_hpc ? force_hpc : (LOG ? 2 : 4);
+        switch (hpc) {
+            case 1: return launch_ring<LOG, WIN, 1>(a, out, rows, cols, mis0, sm_count, s);
+            case 4: return launch_ring<LOG, WIN, 4>(a, out, rows, cols, mis0, sm_count, s);
+            default: return launch_ring<LOG, WIN, 2>(a, out, rows, cols, mis0, sm_count, s);
+        }
+    }
+    const int cs = force_cs ? force_cs : cols <= 20480 ? 1 : cols <= 43008 ? 2 : (cols <= 100000 || cols >= 786432) ? 4 : 8;
+    if (!force_cs && rows * (size_t)cs < 2 * (size_t)sm_count && cols > 32768)   // fewer than two CTAs per SM: split the rows
         return launch_split<LOG, WIN>(a, out, rows, cols, mis0, sm_count, s);
-    // cluster size by row length (scripts/exp/exp_long_rows.py): 4 CTAs up to ~96 K columns and from ~768 K, 8 between
-    const int cs = force_cs ? force_cs : (cols <= 98304 || cols >= 786432) ? 4 : 8;
     return launch_long<LOG, WIN>(cs, a, out, rows, cols, mis0, s);
 }
 
