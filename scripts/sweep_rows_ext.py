@@ -41,7 +41,7 @@ for rows, cols in [(1, 1 << 20), (1, 1 << 24), (1, (1 << 27) + 1), (1, 1 << 28),
     print(f"[{tag}] {rows:8d} x {cols:9d}: softmax {nb/t1/1e6:6.0f}  log_softmax {nb/t2/1e6:6.0f}  torch.softmax {nb/t5/1e6:6.0f} GB/s  ({t1*1e3:.0f} us)", flush=True)
     del x, y
 if tag == "new":
-    for rows, cols in [(1 << 14, 8192), (10922, 12288), (8192, 16384)]:
+    for rows, cols in [(1 << 14, 8192), (10922, 12288), (8192, 16384), (6553, 20480), (4096, 32768), (2048, 65536), (1024, 131072), (512, 262144)]:
         x = torch.randn(rows, cols, device="cuda"); y = torch.empty_like(x)
         g = torch.randn(cols, device="cuda"); b = torch.randn(cols, device="cuda")
         nb = 8.0 * rows * cols

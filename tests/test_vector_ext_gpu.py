@@ -164,7 +164,7 @@ def test_layer_norm_reference_tests_and_oracle(trn, oracle):
     assert e.value == E.SizeMismatch(3, 2)
     assert np.all(np.abs(V.from_slice([5] * 4).layer_norm(V.from_slice([1] * 4), V.from_slice([0] * 4), 1e-5).as_slice()) < 1e-3)
     rng = np.random.default_rng(12)
-    for n in (1, 5, 1000, 4097, 8192, 8196, 12288, 16384, 16388, 100_003):
+    for n in (1, 5, 1000, 4097, 8192, 8196, 12288, 16384, 16388, 20000, 32768, 50000, 131072, 200_000, 100_003):
         x = (rng.standard_normal(n) * 3 + 1).astype(f32)
         g, b = rng.standard_normal(n).astype(f32), rng.standard_normal(n).astype(f32)
         got = V.from_slice(x).layer_norm(V.from_slice(g), V.from_slice(b), 1e-5).as_slice()
@@ -175,6 +175,17 @@ def test_layer_norm_reference_tests_and_oracle(trn, oracle):
         scale = np.abs(g) * np.abs(xd - xd.mean()) / np.sqrt(xd.var() + 1e-5) + np.abs(b) + 1e-6
         assert np.all(np.abs(got - truth) <= 1e-5 * scale + 2e-6 * np.abs(g)), n
         assert np.all(np.abs(got - want) <= 2e-5 * scale + 4e-6 * np.abs(g)), n
+    # long rows over a cluster (cols > 16 384): every row equals the single-vector call, reruns are bit-identical
+    for rows, cols in ((5, 24576), (3, 65536), (9, 120_000)):
+        X = (rng.standard_normal((rows, cols)) * 2 - 0.5).astype(f32)
+        g, b = rng.standard_normal(cols).astype(f32), rng.standard_normal(cols).astype(f32)
+        out = np.empty_like(X)
+        out2 = np.empty_like(X)
+        trn.check(trn.lib.trn_layer_norm_rows_f32(X.ctypes.data, g.ctypes.data, cols, b.ctypes.data, cols, 1e-5, out.ctypes.data, rows, cols))
+        trn.check(trn.lib.trn_layer_norm_rows_f32(X.ctypes.data, g.ctypes.data, cols, b.ctypes.data, cols, 1e-5, out2.ctypes.data, rows, cols))
+        assert np.array_equal(out, out2)
+        for r in (0, rows - 1):
+            assert np.array_equal(out[r], V.from_slice(X[r]).layer_norm(V.from_slice(g), V.from_slice(b), 1e-5).as_slice())
     # rows sharing gamma / beta: every row equals the single-vector call
     rows, cols = 33, 2048
     X = rng.standard_normal((rows, cols)).astype(f32)

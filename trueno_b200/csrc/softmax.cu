@@ -1008,6 +1008,130 @@ layer_norm_rows_kernel(const float* __restrict__ in, const float* __restrict__ g
     }
 }
 
+// layer_norm for rows longer than the register kernels hold (cols > 16 384, 16-byte aligned): a row over a CS-CTA
+// cluster, THREE streaming passes with the reference's own two-pass variance — sum -> mean, sum((x - mean)^2) -> variance,
+// then the per-element formula — of which only the first reads HBM: it parks the row in L2 (evict_last), passes 2 and 3
+// re-read it from there (the last one with evict_first).  Block trees + a rank-order fold through distributed shared
+// memory -> deterministic.  Replaces the one-CTA-per-row scalar fallback for these rows (2.7-3.6 TB/s).
+template <int CS>
+__global__ void __launch_bounds__(kThreads)
+layer_norm_rows_long_kernel(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            float eps, float* __restrict__ out, size_t rows, size_t cols) {
+    constexpr int U = 4;
+    __shared__ float s_w[kThreads / 32];
+    __shared__ float s_stat[2];
+    unsigned rank = 0;
+    if (CS > 1) rank = cg::this_cluster().block_rank();
+    const size_t cluster_id = blockIdx.x / CS, num_clusters = gridDim.x / CS;
+    const uint64_t keep = l2_policy_keep(), drop = l2_policy_drop();
+    const size_t nvec = cols >> 2;
+    const size_t step = (size_t)CS * kThreads * U;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // sum over the cluster of a per-CTA value, folded in rank order by every CTA; slot 0 / 1 alternate between the passes
+    auto cluster_sum = [&](float v, int slot) {
+        float r = block_sum_256(v, s_w);
+        if (CS > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (threadIdx.x == 0) s_stat[slot] = r;
+            cluster.sync();
+            float t = 0.f;
+#pragma unroll
+            for (int p = 0; p < CS; ++p) t += *cluster.map_shared_rank(&s_stat[slot], p);
+            r = t;
+        }
+        return r;
+    };
+
+    for (size_t row = cluster_id; row < rows; row += num_clusters) {
+        const float4* src = reinterpret_cast<const float4*>(in + row * cols);
+        float4* dst = reinterpret_cast<float4*>(out + row * cols);
+        // ---- pass 1 (HBM): sum -> mean
+        float part = 0.f;
+        for (size_t base = 0; base < nvec; base += step) {
+            float4 x[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
+                x[j] = v < nvec ? ld_stream_hint(src + v, keep) : zero4;
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) part += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+        }
+        const float mean = cluster_sum(part, 0) / (float)cols;
+        // ---- pass 2 (L2): sum((x - mean)^2) -> variance
+        part = 0.f;
+        for (size_t base = 0; base < nvec; base += step) {
+            float4 x[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
+                x[j] = v < nvec ? ld_stream_hint(src + v, keep) : make_float4(mean, mean, mean, mean);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const float a = __fsub_rn(x[j].x, mean), b = __fsub_rn(x[j].y, mean);
+                const float c = __fsub_rn(x[j].z, mean), d = __fsub_rn(x[j].w, mean);
+                part += (__fmul_rn(a, a) + __fmul_rn(b, b)) + (__fmul_rn(c, c) + __fmul_rn(d, d));
+            }
+        }
+        const float inv_std = 1.0f / sqrtf(cluster_sum(part, 1) / (float)cols + eps);
+        // ---- pass 3 (L2): gamma * (x - mean) * inv_std + beta, evaluated in that order, unfused
+        for (size_t base = 0; base < nvec; base += step) {
+            float4 x[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
+                x[j] = v < nvec ? ld_stream_hint(src + v, drop) : zero4;
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const size_t v = base + ((size_t)j * CS + rank) * kThreads + threadIdx.x;
+                if (v < nvec) {
+                    float4 y;
+                    if (gamma) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+                        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
+                        y.x = __fadd_rn(__fmul_rn(__fmul_rn(g.x, __fsub_rn(x[j].x, mean)), inv_std), bt.x);
+                        y.y = __fadd_rn(__fmul_rn(__fmul_rn(g.y, __fsub_rn(x[j].y, mean)), inv_std), bt.y);
+                        y.z = __fadd_rn(__fmul_rn(__fmul_rn(g.z, __fsub_rn(x[j].z, mean)), inv_std), bt.z);
+                        y.w = __fadd_rn(__fmul_rn(__fmul_rn(g.w, __fsub_rn(x[j].w, mean)), inv_std), bt.w);
+                    } else {
+                        y.x = __fmul_rn(__fsub_rn(x[j].x, mean), inv_std);
+                        y.y = __fmul_rn(__fsub_rn(x[j].y, mean), inv_std);
+                        y.z = __fmul_rn(__fsub_rn(x[j].z, mean), inv_std);
+                        y.w = __fmul_rn(__fsub_rn(x[j].w, mean), inv_std);
+                    }
+                    st_stream(dst + v, y);
+                }
+            }
+        }
+        // peers must have read both s_stat slots of this row before the next row's pass 1 overwrites slot 0
+        if (CS > 1) cg::this_cluster().sync();
+    }
+}
+
+template <int CS>
+static int launch_layer_norm_long(const float* a, const float* gamma, const float* beta, float eps, float* out, size_t rows,
+                                  size_t cols, cudaStream_t s) {
+    size_t want = (size_t)0x7FFFFFFF / CS;
+    size_t clusters = rows < want ? rows : want;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CS));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TRN_CUDA(cudaLaunchKernelEx(&cfg, layer_norm_rows_long_kernel<CS>, a, gamma, beta, eps, out, rows, cols));
+    count_launch();
+    return TRN_OK;
+}
+
 int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta, float eps, float* out, size_t rows,
                            size_t cols, cudaStream_t s) {
     Context* c = ctx();
@@ -1028,6 +1152,12 @@ int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta
         count_launch();
         TRN_CUDA(cudaGetLastError());
         return TRN_OK;
+    }
+    if (vec_ok) {   // long aligned rows: three streaming passes over a cluster, two of them from L2 (cluster size as for softmax)
+        if (cols <= 20480)  return launch_layer_norm_long<1>(a, gamma, beta, eps, out, rows, cols, s);
+        if (cols <= 43008)  return launch_layer_norm_long<2>(a, gamma, beta, eps, out, rows, cols, s);
+        if (cols <= 100000) return launch_layer_norm_long<4>(a, gamma, beta, eps, out, rows, cols, s);
+        return launch_layer_norm_long<8>(a, gamma, beta, eps, out, rows, cols, s);
     }
     layer_norm_rows_kernel<<<(unsigned)(rows < cap ? rows : cap), kThreads, 0, s>>>(a, gamma, beta, eps, out, rows, cols);
     count_launch();
