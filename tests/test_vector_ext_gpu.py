@@ -174,7 +174,10 @@ def test_layer_norm_reference_tests_and_oracle(trn, oracle):
         # stated tolerance: 1e-5 relative to |gamma| * |x - mean| / std + |beta| (mean / variance are f32 sums)
         scale = np.abs(g) * np.abs(xd - xd.mean()) / np.sqrt(xd.var() + 1e-5) + np.abs(b) + 1e-6
         assert np.all(np.abs(got - truth) <= 1e-5 * scale + 2e-6 * np.abs(g)), n
-        assert np.all(np.abs(got - want) <= 2e-5 * scale + 4e-6 * np.abs(g)), n
+        # the reference's own deviation (sequential f32 sums of n terms, src/vector.rs:1316-1340) grows with n and is
+        # added to the bound: at n = 200 000 it alone exceeds 2e-5 * scale on some elements
+        ref_noise = np.abs(want - truth) if n > 100_003 else 0.0
+        assert np.all(np.abs(got - want) <= 2e-5 * scale + 4e-6 * np.abs(g) + ref_noise), n
     # long rows over a cluster (cols > 16 384): every row equals the single-vector call, reruns are bit-identical
     for rows, cols in ((5, 24576), (3, 65536), (9, 120_000)):
         X = (rng.standard_normal((rows, cols)) * 2 - 0.5).astype(f32)
