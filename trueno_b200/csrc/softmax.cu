@@ -9,18 +9,17 @@
 //     flat grid — 6.8 TB/s from 128 to 1024 columns (1.03 of the measured copy bandwidth).
 //   * 1024 < cols <= 16384: the row in the REGISTERS of one CTA (256 or 512 threads x up to 8 float4), one row
 //     per CTA on a flat grid — 6.7-6.9 TB/s.
-//   * 16384 < cols <= 32768 (config 5: 32 000): the TMA RING kernel.  One persistent CTA per SM;
-//     a producer warp streams rows into a 14-slot x 16 KiB shared-memory ring with 1-D bulk copies
-//     (cp.async.bulk + mbarrier complete_tx), 16 consumer warps pull each slot into registers
-//     (a row = <= 8 slots = 16 float4 per thread), release the slot at once, and compute
-//     max -> exp -> sum -> scale out of registers.  Because slots are released as soon as they are
-//     in registers, the next row's bulk copies (up to 224 KiB in flight per SM) run underneath the
-//     current row's exp and store phases — HBM reads never stop, with no register cost.  6.0 TB/s (0.91).
-//   * cols > 32768 (LLM-vocabulary rows: 50 257, 128 256, 151 936, 262 144 ...): the LONG kernel — a row spread
-//     over a 4- or 8-CTA cluster, two passes: pass 1 streams the row from HBM keeping an online (max, sum) pair per
-//     thread (one rescale per 16 elements), the pairs are folded through the block and through distributed shared
-//     memory in a fixed order; pass 2 re-reads the row (an L2 hit: a row is a few MB at most against 126 MB)
-//     and writes the result.  HBM still sees one read and one write per element.
+//   * aligned rows of 28672 < cols <= 32768 (config 5: 32 000): the TMA RING kernel.  One persistent CTA per SM;
+//     a producer warp streams rows into a 224 KiB shared-memory ring (7 x 32 KiB or 14 x 16 KiB slots) with 1-D bulk
+//     copies (cp.async.bulk + mbarrier complete_tx), 16 consumer warps pull each slot into registers
+//     (a row = 16 float4 per thread), release the slot at once, and compute max -> exp -> sum -> scale out of
+//     registers.  Because slots are released as soon as they are in registers, the next row's bulk copies run
+//     underneath the current row's exp and store phases — HBM reads never stop, with no register cost.  6.0 TB/s (0.91).
+//   * every other row longer than 16384 columns (LLM-vocabulary rows: 32 001, 50 257, 128 256, 151 936, 262 144 ...):
+//     the TWO-PASS cluster kernel — a row spread over a 1- / 2- / 4- / 8-CTA cluster: pass 1 streams the row from HBM
+//     keeping an online (max, sum) pair per thread (one rescale per 16 elements) and parks it in L2 (evict_last hint),
+//     the pairs are folded through the block and through distributed shared memory in a fixed order; pass 2 re-reads
+//     the row from L2 (evict_first) and writes the result.  HBM sees one read and one write per element.  5.2-6.2 TB/s.
 //   * a FEW long rows (one large Vector::softmax): every row split over many CTAs, two launches (segment pairs to
 //     a workspace, then fold + write) — the whole machine works on one vector.
 //   * rows that are not 16-byte aligned (cols % 4 != 0: 77, 1001, 50 257 ...; or a base pointer that is only
