@@ -930,8 +930,8 @@ static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, un
     // (a 1024-thread CTA holding a 32 000-float row measured 4.9 TB/s against the ring kernel's 6.0: one CTA
     //  per SM leaves nothing to overlap a row's load phase with)
     // Rows longer than the register kernels hold (scripts/exp/exp_ring.py, scripts/exp/exp_long_cs.py):
-    //   * aligned rows of 28 672 < cols <= 32 768 (config 5: 32 000): the TMA ring kernel — 32 KiB slots for softmax,
-    //     16 KiB for log_softmax (5.98 / 6.07-6.13 TB/s at 32 000; the two-pass kernel ties there at 5.98 / 6.09);
+    //   * aligned rows of 28 672 < cols <= 32 768 (config 5: 32 000): the TMA ring kernel (5.98 / 6.13 TB/s at
+    //     4096 x 32 000, 6.12 / 6.43 at 8192 rows; the two-pass kernel ties at 4096 rows and is 2 % behind at 8192);
     //   * a few long rows: the split-row kernels;
     //   * everything else: the two-pass cluster kernel, cluster size by row length — 1 CTA up to 20 480 columns
     //     (17 000: 6.0 TB/s where the ring reached 4.1-4.4), 2 up to 43 008 (24 576: 6.15 vs 5.2-5.6), 4 up to 100 000,
@@ -939,7 +939,9 @@ static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, un
     const int force_cs = env_int("TRN_ROWS_LONG_CS");
     const int force_hpc = env_int("TRN_RING_HPC");   // experiment knobs, read per call
     if (!force_cs && (force_hpc || (!WIN && cols > 28672)) && nvec <= (size_t)ring::kRowVec) {
-        const int hpc = force_hpc ? force_hpc : (LOG ? 2 : 4);
+        // 32 KiB slots (7 of them) beat 16 KiB ones by 4-9 % at every row count from 512 to 8192 x 32 000, except for
+        // log_softmax on rows of exactly four slots (32 768 columns: 5.7 vs 6.06 TB/s)
+        const int hpc = force_hpc ? force_hpc : (LOG && cols > 32512) ? 2 : 4;
         switch (hpc) {
             case 1: return launch_ring<LOG, WIN, 1>(a, out, rows, cols, mis0, sm_count, s);
             case 4: return launch_ring<LOG, WIN, 4>(a, out, rows, cols, mis0, sm_count, s);
