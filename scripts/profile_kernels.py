@@ -72,7 +72,7 @@ def main():
     if "rows2" in which:
         # long / window / split row kernels: LLM-vocabulary rows (128 256 aligned; 50 257 and 100 003 not 16-byte aligned),
         # window forms of the warp / CTA / ring kernels, one large Vector::softmax
-        for rr, cc in ((1046, 128256), (2670, 50257), (1342, 100003), (134083, 1001), (16386, 8191), (4194, 32001), (1, 1 << 27)):
+        for rr, cc in ((4096, 32000), (1046, 128256), (2670, 50257), (1342, 100003), (5461, 24576), (134083, 1001), (16386, 8191), (4194, 32001), (1, 1 << 27)):
             w = torch.randn(rr, cc, device="cuda")
             wo = torch.empty_like(w)
             keep += [w, wo]
