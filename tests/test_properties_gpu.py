@@ -153,3 +153,94 @@ def test_attention_properties(trn, data):
     lo, hi = v64.min(axis=1, keepdims=True), v64.max(axis=1, keepdims=True)
     span = (hi - lo) + np.abs(hi) + np.abs(lo)
     assert np.all(got >= lo - 1e-5 * span) and np.all(got <= hi + 1e-5 * span)
+
+
+# ---- statistics and activations of the widened Vector API (src/vector.rs:12763-13330 and the per-op proptests) ----
+@CASES
+@given(a=vec(-100.0, 100.0), k=st.floats(-5, 5, width=32))
+def test_sum_of_squares_properties(trn, a, k):                      # src/vector.rs:12763-12820
+    v = trn.Vector(a)
+    ss = float(v.sum_of_squares())
+    assert ss >= 0.0
+    assert abs(ss - float(v.dot(v))) < 1e-4 * max(1.0, ss)
+    small = (a / f32(10)).astype(f32)
+    vs = trn.Vector(small)
+    want = float(k) * float(k) * float(vs.sum_of_squares())
+    assert abs(float(vs.scale(float(k)).sum_of_squares()) - want) < 1e-3 * max(abs(want), 1.0)
+
+
+@CASES
+@given(data=st.data())
+def test_covariance_and_correlation_properties(trn, data):          # src/vector.rs:13020-13170
+    n = data.draw(st.integers(2, 100))
+    a = data.draw(hnp.arrays(f32, n, elements=st.floats(-50, 50, width=32)))
+    b = data.draw(hnp.arrays(f32, n, elements=st.floats(-50, 50, width=32)))
+    va, vb = trn.Vector(a), trn.Vector(b)
+    var = float(va.variance())
+    assert abs(float(va.covariance(va)) - var) < 1e-3 * max(abs(var), 1e-5) + 1e-3        # Cov(X, X) = Var(X)
+    cab, cba = float(va.covariance(vb)), float(vb.covariance(va))
+    assert abs(cab - cba) <= 1e-4 * max(abs(cab), 1e-5) + 1e-4                             # symmetry
+    # E[x^2] - mean^2 in f32 (the reference's formula, src/vector.rs:983-995) cancels for nearly constant vectors:
+    # correlation is only meaningful (in the reference too) when the spread is not tiny against the magnitude
+    if min(a.std() / max(1.0, np.abs(a).max()), b.std() / max(1.0, np.abs(b).max())) < 0.05:
+        return
+    try:
+        r = float(va.correlation(vb))
+    except trn.TruenoError as e:                                                           # constant vector
+        assert e.variant == "DivisionByZero"
+        return
+    assert -1.0 <= r <= 1.0                                                                # bounded
+    assert abs(r - float(vb.correlation(va))) < 1e-3                                       # symmetric
+
+
+@CASES
+@given(a=vec(-100.0, 100.0, min_len=2))
+def test_zscore_and_minmax_properties(trn, a):                      # src/vector.rs:13176-13330
+    v = trn.Vector(a)
+    if a.std() / max(1.0, np.abs(a).max()) < 0.05:      # see the note on E[x^2] - mean^2 above
+        return
+    z = v.zscore().as_slice().astype(np.float64)
+    assert abs(z.mean()) < 1e-3 and abs(z.std() - 1.0) < 2e-2
+    m = v.minmax_normalize().as_slice()
+    assert float(m.min()) == 0.0 and abs(float(m.max()) - 1.0) < 1e-5 and ((m >= 0) & (m <= 1.0 + 1e-6)).all()
+    assert np.all(np.diff(m[np.argsort(a, kind="stable")]) >= 0)                           # order preserving
+
+
+@CASES
+@given(a=vec(-100.0, 100.0), slope=st.floats(0.0, 0.99, width=32), alpha=st.floats(0.01, 5.0, width=32))
+def test_activation_properties(trn, a, slope, alpha):               # src/vector.rs: leaky_relu / elu / hardswish / mish / selu proptests
+    v = trn.Vector(a)
+    pos = a > 0
+    lr = v.leaky_relu(float(slope)).as_slice()
+    assert np.array_equal(lr[pos], a[pos]) and np.array_equal(lr[~pos], (f32(slope) * a[~pos]).astype(f32))
+    el = v.elu(float(alpha)).as_slice()
+    assert np.array_equal(el[pos], a[pos]) and (el[~pos] >= -f32(alpha) * (1 + 1e-6)).all() and (el[~pos] <= 0).all()
+    hs = v.hardswish().as_slice()
+    assert np.array_equal(hs[a >= 3], a[a >= 3]) and (hs[a <= -3] == 0).all() and (hs >= -0.375 - 1e-6).all()
+    mi = v.mish().as_slice()
+    assert (mi >= -0.31).all() and np.all(np.abs(mi[a > 20] - a[a > 20]) == 0) and (mi[a < -20] == 0).all()
+    se = v.selu().as_slice()
+    assert (se[pos] > 0).all() and (se[~pos] <= 0).all() and (se >= -1.7581 - 1e-4).all()
+    # clip is idempotent and bounded; minimum / maximum bracket their operands
+    c = v.clip(-10.0, 10.0)
+    assert np.array_equal(c.clip(-10.0, 10.0).as_slice(), c.as_slice()) and np.abs(c.as_slice()).max() <= 10.0
+    w = trn.Vector(a[::-1].copy())
+    lo, hi = v.minimum(w).as_slice(), v.maximum(w).as_slice()
+    assert (lo <= hi).all() and np.array_equal(lo + hi, a + a[::-1])
+    assert np.array_equal(v.neg().neg().as_slice(), a) and np.array_equal(np.abs(v.signum().as_slice()), np.ones_like(a))
+    assert np.array_equal(v.trunc().as_slice() + v.fract().as_slice(), a) or np.allclose(v.trunc().as_slice() + v.fract().as_slice(), a, rtol=0, atol=1e-4)
+
+
+@CASES
+@given(data=st.data())
+def test_embedding_lookup_properties(trn, data):                    # gather: rows come back verbatim, order and repeats preserved
+    rows = data.draw(st.integers(1, 40))
+    cols = data.draw(st.integers(1, 70))
+    table = data.draw(hnp.arrays(f32, rows * cols, elements=st.floats(-1000, 1000, width=32)))
+    idx = data.draw(st.lists(st.integers(0, rows - 1), min_size=0, max_size=60))
+    m = trn.Matrix.from_vec(rows, cols, table)
+    got = m.embedding_lookup(idx)
+    assert got.shape() == (len(idx), cols)
+    assert np.array_equal(got.as_slice().reshape(len(idx), cols), table.reshape(rows, cols)[np.asarray(idx, dtype=np.int64)])
+    emb, uniq = m.embedding_lookup_sparse(idx)
+    assert uniq == sorted(set(idx)) and np.array_equal(emb.as_slice(), got.as_slice())
