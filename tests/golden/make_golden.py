@@ -10,6 +10,8 @@ outputs.  What CAN be pinned, and is:
                         sin/cos dot and norm fixtures (tests/smoke_e2e.rs:54-91) and a splitmix slice of every
                         BASELINE config — so a later change to the oracle or the kernels is caught against a
                         frozen file, not against a moving oracle.
+  vector_api_fixtures.npz  the oracle's outputs for the widened Vector / Matrix API (22 maps, statistics,
+                        embedding_lookup) on the same xorshift fixtures, frozen the same way.
 Run from the repository root:  python tests/golden/make_golden.py
 """
 import json
@@ -76,6 +78,34 @@ def main():
     out["splitmix_slice_sum_dot_norm"] = np.array([orc.sum(s, backend=SCALAR), orc.dot(s, t, backend=SCALAR), orc.norm_l2(s, backend=SCALAR)], f32)
     out["splitmix_slice_argmax_argmin"] = np.array([orc.argmax(s), orc.argmin(s)], np.int64)
     np.savez_compressed(os.path.join(HERE, "seeded_fixtures.npz"), **out)
+
+    # ---- the widened Vector / Matrix API (a separate file: seeded_fixtures.npz stays byte-identical) ----
+    api = {}
+    x = kats.SimpleRng(22222).gen_vec(2048) * f32(4)        # xorshift fixture scaled to (-4, 4)
+    y = kats.SimpleRng(34567).gen_vec(2048) * f32(4)
+    api["x"], api["y"] = x, y
+    for op in ("neg", "signum", "trunc", "fract", "hardswish", "mish", "selu", "sinh", "cosh", "atan", "asinh"):
+        api[op] = orc.vector_map(op, x)
+    u = (x / f32(4.5)).astype(f32)                           # inside (-1, 1)
+    api["u"] = u
+    for op in ("asin", "acos", "atanh"):
+        api[op] = orc.vector_map(op, u)
+    api["acosh"] = orc.vector_map("acosh", (np.abs(x) + f32(1)).astype(f32))
+    api["leaky_relu_0.01"] = orc.vector_map("leaky_relu", x, p0=0.01)
+    api["elu_1.5"] = orc.vector_map("elu", x, p0=1.5)
+    api["pow_2"] = orc.vector_map("pow", x, p0=2.0)
+    api["clip_-0.5_0.75"] = orc.vector_map("clip", x, p0=-0.5, p1=0.75)
+    for op in ("minimum", "maximum", "copysign"):
+        api[op] = orc.vector_map(op, x, y)
+    api["minmax_normalize"] = orc.minmax_normalize(x)
+    api["zscore"] = orc.zscore(x, backend=SCALAR)
+    api["layer_norm_simple_1e-5"] = orc.layer_norm_simple(x, 1e-5, backend=SCALAR)
+    api["stats"] = np.array([orc.dot(x, x, backend=SCALAR), orc.covariance(x, y, backend=SCALAR),
+                             orc.correlation(x, y, backend=SCALAR)], f32)
+    idx = (np.arange(97, dtype=np.uint64) * 37) % 64
+    api["embedding_idx"] = idx
+    api["embedding_64x32"] = orc.embedding_lookup(x, 64, 32, idx)
+    np.savez_compressed(os.path.join(HERE, "vector_api_fixtures.npz"), **api)
     print("wrote", sorted(os.listdir(HERE)))
 
 

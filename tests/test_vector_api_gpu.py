@@ -223,3 +223,43 @@ def test_embedding_lookup_dev_resident_and_out_of_range(trn):
         ok = torch.ones(idx.numel(), dtype=torch.bool, device=dev)
         ok[5] = False
         assert torch.equal(out[ok], table[idx[ok]]) and bool((out[5] == 0).all())
+
+
+def test_cuda_path_against_committed_vector_api_golden(trn):
+    """CUDA path vs the frozen golden file tests/golden/vector_api_fixtures.npz (oracle outputs on the xorshift fixtures) —
+    no oracle call here, so an oracle change cannot mask a kernel change."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vector_api_fixtures.npz"))
+    x, y, u = g["x"], g["y"], g["u"]
+    V = trn.Vector
+    vx, vy, vu = V.from_slice(x), V.from_slice(y), V.from_slice(u)
+    for op in ("neg", "signum", "trunc", "fract", "hardswish"):                                  # bit-exact
+        assert np.array_equal(getattr(vx, op)().as_slice(), g[op]), op
+    assert np.array_equal(vx.leaky_relu(0.01).as_slice(), g["leaky_relu_0.01"])
+    assert np.array_equal(vx.clip(-0.5, 0.75).as_slice(), g["clip_-0.5_0.75"])
+    for op in ("minimum", "maximum", "copysign"):
+        assert np.array_equal(getattr(vx, op)(vy).as_slice(), g[op]), op
+    assert np.array_equal(vx.minmax_normalize().as_slice(), g["minmax_normalize"])
+    for op, k in (("sinh", 4), ("cosh", 4), ("atan", 4), ("asinh", 6)):                         # CUDA vs glibc: <= k ulp apart
+        want = g[op].astype(np.float64)
+        assert np.all(np.abs(getattr(vx, op)().as_slice() - want) <= k * ulp(want)), op
+    for op, k in (("asin", 4), ("acos", 4), ("atanh", 6)):
+        want = g[op].astype(np.float64)
+        assert np.all(np.abs(getattr(vu, op)().as_slice() - want) <= k * ulp(want)), op
+    want = g["acosh"].astype(np.float64)
+    assert np.all(np.abs(V.from_slice((np.abs(x) + f32(1)).astype(f32)).acosh().as_slice() - want) <= 6 * ulp(want) + 1e-7)
+    want = g["pow_2"].astype(np.float64)
+    assert np.all(np.abs(vx.pow(2.0).as_slice() - want) <= 4 * ulp(want))
+    for op, got, amp in (("mish", vx.mish().as_slice(), 1.0), ("selu", vx.selu().as_slice(), 1.76), ("elu_1.5", vx.elu(1.5).as_slice(), 1.5)):
+        want = g[op].astype(np.float64)
+        assert np.all(np.abs(got - want) <= 8 * ulp(want) + amp * 8 * 2.0 ** -24), op
+    want = g["zscore"].astype(np.float64)
+    assert np.all(np.abs(vx.zscore().as_slice() - want) <= 2e-5 * (np.abs(want) + 1))
+    want = g["layer_norm_simple_1e-5"].astype(np.float64)
+    assert np.all(np.abs(vx.layer_norm_simple(1e-5).as_slice() - want) <= 2e-5 * (np.abs(want) + 1))
+    ss, cov, corr = (float(v) for v in g["stats"])
+    assert abs(float(vx.sum_of_squares()) - ss) <= 1e-5 * ss
+    scale = float(np.mean(np.abs(x.astype(np.float64) * y)) + abs(x.mean() * y.mean()))
+    assert abs(float(vx.covariance(vy)) - cov) <= 4e-5 * scale and abs(float(vx.correlation(vy)) - corr) <= 1e-4
+    got = trn.Matrix.from_vec(64, 32, x).embedding_lookup(g["embedding_idx"]).as_slice().reshape(-1, 32)
+    assert np.array_equal(got, g["embedding_64x32"])
