@@ -145,7 +145,6 @@ def main():
 
     if "attention" in which:
         # BASELINE config 3's head shape, now fused: out = softmax(scale * Q K^T) V per head
-        import os
         H, seq, d = int(os.environ.get("ATT_HEADS", 256)), int(os.environ.get("ATT_SEQ", 2048)), int(os.environ.get("ATT_D", 128))
         q = torch.randn(H * seq * d, device="cuda"); k = torch.randn(H * seq * d, device="cuda"); v = torch.randn(H * seq * d, device="cuda")
         o = torch.empty(H * seq * d, device="cuda")
