@@ -939,9 +939,10 @@ static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, un
     const int force_cs = env_int("TRN_ROWS_LONG_CS");
     const int force_hpc = env_int("TRN_RING_HPC");   // experiment knobs, read per call
     if (!force_cs && (force_hpc || (!WIN && cols > 28672)) && nvec <= (size_t)ring::kRowVec) {
-        // 32 KiB slots (7 of them) beat 16 KiB ones by 4-9 % at every row count from 512 to 8192 x 32 000, except for
-        // log_softmax on rows of exactly four slots (32 768 columns: 5.7 vs 6.06 TB/s)
-        const int hpc = force_hpc ? force_hpc : (LOG && cols > 32512) ? 2 : 4;
+        // softmax: 32 KiB slots (7 of them) beat 16 KiB ones by 2-5 % in every run (5.98-6.15 vs 5.67-6.06 TB/s at
+        // 32 000 columns).  log_softmax is bimodal with 32 KiB slots from one box visit to the next (5.56-5.68 or
+        // 6.13-6.43) and steady with 16 KiB ones (5.87-6.08): it keeps 16 KiB.
+        const int hpc = force_hpc ? force_hpc : LOG ? 2 : 4;
         switch (hpc) {
             case 1: return launch_ring<LOG, WIN, 1>(a, out, rows, cols, mis0, sm_count, s);
             case 4: return launch_ring<LOG, WIN, 4>(a, out, rows, cols, mis0, sm_count, s);
