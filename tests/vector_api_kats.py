@@ -77,6 +77,25 @@ def run(call):
     _raises(lambda: call("copysign", [1, 2], [1]), "SizeMismatch")
     assert np.array_equal(call("neg", [1, -2, 3, -4]), np.array([-1, 2, -3, 4], f32))                               # test_neg_basic
     assert np.array_equal(call("pow", [2, 3, 4, 5], p=(2.0,)), np.array([4, 9, 16, 25], f32))                       # test_pow_basic
+    assert np.array_equal(call("pow", [4, 9, 16], p=(0.5,)), np.array([2, 3, 4], f32))                              # test_pow_fractional
+    assert np.array_equal(call("pow", [2, 4, 10], p=(-1.0,)), np.array([0.5, 0.25, 0.1], f32))                      # test_pow_negative_exponent
+    assert np.array_equal(call("pow", [2, 3, 4], p=(0.0,)), np.array([1, 1, 1], f32))                               # test_pow_zero_exponent
+    assert np.array_equal(call("pow", [2, 3, 4], p=(1.0,)), np.array([2, 3, 4], f32))                               # test_pow_one_exponent
+    _close(call("pow", [2, 3], p=(3.0,)), [8, 27], 1e-5)                                                            # test_pow_cube
+    assert np.array_equal(call("copysign", [5, 5], [np.inf, -np.inf]), np.array([5, -5], f32))                      # test_copysign_infinity
+    assert np.array_equal(call("copysign", [3, 3], [0.0, -0.0]), np.array([3, -3], f32))                            # test_copysign_zero
+    assert np.array_equal(call("minimum", [np.inf, 5, -np.inf], [3, np.inf, -10]), np.array([3, 5, -np.inf], f32))  # test_minimum_infinity
+    r = call("maximum", [np.nan, 5.0, np.nan], [3.0, np.nan, np.nan])                                               # test_maximum_nan
+    assert r[0] == 3 and r[1] == 5 and np.isnan(r[2])
+    r = call("neg", [0.0, -0.0])                                                                                    # test_neg_zero
+    assert np.signbit(r[0]) and not np.signbit(r[1]) and r[0] == 0 and r[1] == 0
+    r = call("neg", [np.nan, 5.0])                                                                                  # test_neg_nan
+    assert np.isnan(r[0]) and r[1] == -5
+    assert np.array_equal(call("neg", [np.inf, -np.inf]), np.array([-np.inf, np.inf], f32))                         # test_neg_infinity
+    _close(call("fract", [-1.2, -2.5, -3.9]), [-0.2, -0.5, -0.9], 1e-5)                                             # test_fract_negative
+    assert np.array_equal(call("trunc", [2.7, -2.7, 5.3, -5.3]), np.array([2, -2, 5, -5], f32))                     # test_trunc_toward_zero
+    assert abs(call("acosh", [1.0])[0]) < 1e-5                                                                      # test_acosh_one
+    assert np.isnan(call("acosh", [0.5])[0]) and np.isnan(call("asin", [1.5])[0])                                   # outside the domain -> NaN
     _close(call("sinh", [0, 1, -1]), [0, math.sinh(1), -math.sinh(1)], 1e-5)
     _close(call("cosh", [0, 1, -1]), [1, math.cosh(1), math.cosh(1)], 1e-5)
     _close(call("asin", [0, 1, -1, 0.5]), [0, PI / 2, -PI / 2, PI / 6], 1e-5)

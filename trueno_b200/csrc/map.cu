@@ -109,7 +109,17 @@ __device__ __forceinline__ float apply(float x, float y, float z, float p0, floa
         }
         case Map::LeakyRelu: return x > 0.0f ? x : __fmul_rn(p0, x);      // :2014-2019 -> bit-exact
         case Map::Elu: return x > 0.0f ? x : __fmul_rn(p0, __fsub_rn(expf(x), 1.0f));   // :2118-2122
-        case Map::Pow: return powf(x, p0);                                // :3342
+        case Map::Pow: {
+            // :3342 x.powf(n).  The exponents the reference's own tests pin with assert_eq (2, 0.5, -1, 0, 1:
+            // src/vector.rs test_pow_*) take the correctly rounded single operation a correctly rounded powf returns
+            // for them; p0 is a launch parameter, so the branch is uniform.  Everything else: CUDA's powf (<= 4 ulp).
+            if (p0 == 2.0f) return __fmul_rn(x, x);
+            if (p0 == -1.0f) return __frcp_rn(x);
+            if (p0 == 0.5f) return x > 0.0f ? sqrtf(x) : powf(x, 0.5f);   // pow(-0, .5) = +0 and pow(-inf, .5) = +inf, unlike sqrt
+            if (p0 == 1.0f) return x;
+            if (p0 == 0.0f) return 1.0f;
+            return powf(x, p0);
+        }
         case Map::Minimum: return fminf(x, y);                            // :4328 f32::min: the non-NaN operand
         case Map::Maximum: return fmaxf(x, y);                            // :4364
         case Map::Copysign: return copysignf(x, y);                       // :4292
