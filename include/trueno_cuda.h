@@ -303,7 +303,8 @@ TRN_API int trn_leaky_relu_f32_dev(const float* a, size_t n, float negative_slop
 /* Vector::elu (src/vector.rs:2085; GpuDevice::elu): x > 0 ? x : alpha * (exp(x) - 1) */
 TRN_API int trn_elu_f32(const float* a, size_t n, float alpha, float* out);
 TRN_API int trn_elu_f32_dev(const float* a, size_t n, float alpha, float* out, void* stream);
-/* Vector::pow (src/vector.rs:3342): powf(x, exponent) */
+/* Vector::pow (src/vector.rs:3342): powf(x, exponent); exponents 2, 0.5, -1, 0 and 1 are evaluated as the single
+ * correctly rounded operation a correctly rounded powf returns (x*x, sqrt, 1/x, 1, x) */
 TRN_API int trn_pow_f32(const float* a, size_t n, float exponent, float* out);
 TRN_API int trn_pow_f32_dev(const float* a, size_t n, float exponent, float* out, void* stream);
 /* Vector::clip (src/vector.rs:1448; GpuDevice::clip): x.max(min_val).min(max_val) */
