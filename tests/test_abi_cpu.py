@@ -85,3 +85,59 @@ def test_compute_fails_loudly_without_gpu(trn):
     with pytest.raises(trn.TruenoError) as e:
         trn.Matrix.identity(4).matmul(trn.Matrix.identity(4))
     assert e.value.variant == "GpuError"
+
+
+def test_widened_api_validation_errors_match_reference(trn):
+    """The error contract of the widened Vector / Matrix API is checked before any device work, so it holds on a box
+    without a GPU too (values and message text of src/vector.rs / src/matrix.rs)."""
+    V, M, E = trn.Vector, trn.Matrix, trn.TruenoError
+    for op in ("hardswish", "mish", "selu", "zscore", "minmax_normalize"):       # src/vector.rs:2410, :2478, :2547, :1181, :1249
+        with pytest.raises(E) as e:
+            getattr(V.from_slice([]), op)()
+        assert e.value == E.EmptyVector, op
+    with pytest.raises(E) as e:
+        V.from_slice([]).leaky_relu(0.01)                                         # :1981
+    assert e.value == E.EmptyVector
+    with pytest.raises(E) as e:
+        V.from_slice([]).elu(1.0)                                                 # :2086
+    assert e.value == E.EmptyVector
+    with pytest.raises(E) as e:
+        V.from_slice([]).layer_norm_simple(1e-5)                                  # :1387
+    assert e.value == E.EmptyVector
+    for bad, text in ((-0.1, "-0.1"), (1.0, "1"), (1.5, "1.5")):                  # :1986-1990
+        with pytest.raises(E) as e:
+            V.from_slice([1, 2, 3]).leaky_relu(bad)
+        assert e.value == E.InvalidInput(f"negative_slope must be in [0.0, 1.0), got {text}")
+    for bad, text in ((0.0, "0"), (-1.0, "-1")):                                  # :2091-2095
+        with pytest.raises(E) as e:
+            V.from_slice([1, 2, 3]).elu(bad)
+        assert e.value == E.InvalidInput(f"alpha must be > 0, got {text}")
+    with pytest.raises(E) as e:
+        V.from_slice([1, 2, 3]).clip(10.0, 5.0)                                   # :1449-1454
+    assert e.value == E.InvalidInput("min_val (10) must be <= max_val (5)")
+    for op in ("minimum", "maximum", "copysign", "covariance", "correlation"):   # :4329, :4365, :4293, :1067, :1119
+        with pytest.raises(E) as e:
+            getattr(V.from_slice([1, 2]), op)(V.from_slice([1, 2, 3]))
+        assert e.value == E.SizeMismatch(2, 3), op
+    with pytest.raises(E) as e:
+        V.from_slice([]).covariance(V.from_slice([]))                             # :1064
+    assert e.value == E.EmptyVector
+    with pytest.raises(E) as e:                                                   # src/matrix.rs:2010-2017
+        M.from_vec(3, 2, [1, 2, 3, 4, 5, 6]).embedding_lookup([0, 5, 1])
+    assert e.value == E.InvalidInput("Index 5 at position 1 is out of bounds for embedding table with 3 rows")
+
+
+def test_widened_api_fails_loudly_without_gpu(trn):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-GPU contract is checked on CPU boxes")
+    V, M = trn.Vector, trn.Matrix
+    calls = [lambda: V.from_slice([1, 2, 3]).hardswish(), lambda: V.from_slice([1, 2, 3]).leaky_relu(0.1),
+             lambda: V.from_slice([1, 2, 3]).zscore(), lambda: V.from_slice([1, 2, 3]).covariance(V.from_slice([3, 2, 1])),
+             lambda: V.from_slice([1, 2, 3]).minimum(V.from_slice([3, 2, 1])), lambda: V.from_slice([1, 2, 3]).pow(2.0),
+             lambda: M.from_vec(2, 2, [1, 2, 3, 4]).embedding_lookup([1, 0]),
+             lambda: trn.softmax_rows(np.ones((2, 50257), np.float32), 2, 50257)]
+    for c in calls:
+        with pytest.raises(trn.TruenoError) as e:
+            c()
+        assert e.value.variant == "GpuError"
