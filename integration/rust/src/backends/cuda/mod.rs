@@ -186,6 +186,24 @@ impl CudaBackend {
         check(unsafe { sys::trn_log_softmax_rows_f32(a.as_ptr(), result.as_mut_ptr(), rows, cols) })
     }
 
+    /// One `Vector::softmax` / `log_softmax` whose contiguous slices live on different GPUs (one process per GPU):
+    /// step 1 folds this rank's resident slice to a (max, sum of exp) pair in device memory; the ranks all_gather their
+    /// pairs (NCCL or any transport); step 2 normalises the slice by the fold of all pairs (rank order, same bits on
+    /// every rank).  Raw device pointers: the slices are `DeviceBuffer`s (buffer.rs), never host memory.
+    ///
+    /// # Safety
+    /// `slice`, `pair_out`, `pairs` and `out` must be valid device pointers on the current device.
+    pub unsafe fn softmax_slice_stats(slice: *const f32, n: usize, pair_out: *mut f32, stream: *mut core::ffi::c_void)
+        -> Result<(), TruenoError> {
+        check(sys::trn_softmax_slice_stats_f32_dev(slice, n, pair_out, stream))
+    }
+    /// # Safety
+    /// see `softmax_slice_stats`
+    pub unsafe fn softmax_slice_apply(slice: *const f32, n: usize, pairs: *const f32, npairs: usize, log: bool, out: *mut f32,
+                                      stream: *mut core::ffi::c_void) -> Result<(), TruenoError> {
+        check(sys::trn_softmax_slice_apply_f32_dev(slice, n, pairs, npairs, log as i32, out, stream))
+    }
+
     /// `GpuBackend::matmul(a, b, m, k, n)` (src/backends/gpu/mod.rs:434) — same argument meaning.
     pub fn matmul(a: &[f32], b: &[f32], m: usize, k: usize, n: usize) -> Result<Vec<f32>, TruenoError> {
         let mut c = vec![0.0f32; m * n];
