@@ -8,9 +8,14 @@ use std::env;
 use std::path::PathBuf;
 use std::process::Command;
 
+// Every translation unit under trueno_b200/csrc — the same list, in the same order, as trueno_b200/build.py
+// (tests/test_build_recipes_cpu.py compares the two with the directory listing).
 const SOURCES: &[&str] = &[
-    "context.cu", "reduce.cu", "map.cu", "softmax.cu", "gemm_simt.cu", "gemm_tc.cu", "batch.cu", "peer.cu", "conv.cu", "api.cu",
+    "context.cu", "reduce.cu", "map.cu", "softmax.cu", "gemm_simt.cu", "gemm_tc.cu", "batch.cu", "peer.cu", "conv.cu",
+    "attention.cu", "eigen.cu", "gather.cu", "api.cu",
 ];
+// Headers every object depends on.
+const HEADERS: &[&str] = &["common.cuh", "tcgen05.cuh"];
 
 fn main() {
     let manifest = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap());
@@ -37,12 +42,16 @@ fn main() {
         assert!(status.success(), "nvcc failed for {}", src);
         objs.push(obj);
     }
-    println!("cargo:rerun-if-changed={}", csrc.join("common.cuh").display());
+    for h in HEADERS {
+        println!("cargo:rerun-if-changed={}", csrc.join(h).display());
+    }
     println!("cargo:rerun-if-changed={}", include.join("trueno_cuda.h").display());
 
     let lib = out.join("libtrueno_cuda.so");
     let status = Command::new(&nvcc)
         .args(["-shared", "-cudart", "shared", "-o"]).arg(&lib).args(&objs)
+        // a source missing from SOURCES must fail HERE, not when the library is loaded
+        .args(["-Xlinker", "-rpath,/usr/local/cuda/lib64", "-Xlinker", "--no-undefined"])
         .status()
         .expect("nvcc link step failed to start");
     assert!(status.success(), "linking libtrueno_cuda.so failed");

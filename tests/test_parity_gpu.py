@@ -617,7 +617,7 @@ def test_pipelined_host_gemm_matches_resident(trn, shape):
         trn.check(trn.lib.trn_matmul_f32(ha.ctypes.data, m, k, hb.ctypes.data, k, n, hc.ctypes.data))
     else:
         trn.check(trn.lib.trn_batched_matmul_f32(ha.ctypes.data, ha.size, hb.ctypes.data, hb.size, hc.ctypes.data, batch, m, k, n))
-    assert trn.launch_count() - launches0 > 4          # several blocks => the pipelined path really ran
+    assert trn.launch_count() - launches0 >= 4         # several blocks (>= 2 launches each) => the pipelined path really ran
     da, db, dc = trn.DeviceBuffer.from_host(ha), trn.DeviceBuffer.from_host(hb), trn.DeviceBuffer(batch * m * n)
     trn.check(trn.lib.trn_batched_matmul_f32_dev(da.ptr, ha.size, db.ptr, hb.size, dc.ptr, batch, m, k, n, None))
     trn.synchronize()

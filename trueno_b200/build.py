@@ -33,7 +33,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "trueno_cuda.h"), __file__]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tcgen05.cuh"), os.path.join(ROOT, "include", "trueno_cuda.h"), __file__]
     objs, procs = [], []
     for src in SOURCES:
         path = os.path.join(CSRC, src)

@@ -466,6 +466,9 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     cudaStream_t s_main = cx->stream, s_up = cx->copy_stream, s_down = cx->d2h_stream;
     const size_t kpad = gemm_tc_kpad(k);
     const bool single = batch == 1;
+    // the same kernel choice as the resident call (gemm_tc.cu): results stay bit-identical to it.  Scratch sub-buffers
+    // are 256-byte aligned, so alignment never differs from an aligned resident operand.
+    const bool fused = gemm_tc_uses_fused(nullptr, nullptr, m, k, n);
     // work units: row blocks of one product, or groups of whole (batch*head) products
     size_t units = batch, per_block = 1;
     std::vector<size_t> row_start;   // single product: start row of every block, plus m as the sentinel
@@ -488,6 +491,8 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
             row_start.push_back(r + rest);
             if (last - rest > 256) row_start.push_back(r + rest + 256);
         }
+        // the fused-split kernel needs more than one 128-row tile per block: a short tail joins the block before it
+        while (fused && row_start.size() > 1 && m - row_start.back() <= 128) row_start.pop_back();
         units = row_start.size();
         row_start.push_back(m);
     } else {
@@ -499,7 +504,7 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     }
 
     const size_t na = batch * m * k, nb = batch * k * n, nc = batch * m * n;
-    const size_t a_split = batch * m * kpad, b_split = batch * n * kpad;
+    const size_t a_split = fused ? 0 : batch * m * kpad, b_split = fused ? 0 : batch * n * kpad;
     // every sub-buffer starts on a 256-byte boundary (TMA needs 16-byte aligned tensor bases)
     auto pad64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
     float* dev = nullptr;
@@ -530,7 +535,7 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
         TRN_CUDA(cudaMemcpyAsync(db, b, nb * sizeof(float), cudaMemcpyHostToDevice, s_up));
         TRN_CUDA(cudaEventRecord(up[units].e, s_up));
         TRN_CUDA(cudaStreamWaitEvent(s_main, up[units].e, 0));
-        st = gemm_tc_split_b(db, b_hi, b_lo, 1, k, n, flag, s_main);
+        if (!fused) st = gemm_tc_split_b(db, b_hi, b_lo, 1, k, n, flag, s_main);
     }
     for (size_t u = 0; u < units && st == TRN_OK; ++u) {
         if (single) {
@@ -538,8 +543,12 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
             TRN_CUDA(cudaMemcpyAsync(da + r0 * k, a + r0 * k, rows * k * sizeof(float), cudaMemcpyHostToDevice, s_up));
             TRN_CUDA(cudaEventRecord(up[u].e, s_up));
             TRN_CUDA(cudaStreamWaitEvent(s_main, up[u].e, 0));
-            st = gemm_tc_split_a(da + r0 * k, a_hi + r0 * kpad, a_lo + r0 * kpad, 1, rows, k, flag, s_main);
-            if (st == TRN_OK) st = gemm_tc_main(a_hi + r0 * kpad, a_lo + r0 * kpad, b_hi, b_lo, dc + r0 * n, 1, rows, k, n, 3, flag, s_main);
+            if (fused) {
+                st = gemm_tc_fused_main(da + r0 * k, db, dc + r0 * n, 1, rows, k, n, flag, s_main);
+            } else {
+                st = gemm_tc_split_a(da + r0 * k, a_hi + r0 * kpad, a_lo + r0 * kpad, 1, rows, k, flag, s_main);
+                if (st == TRN_OK) st = gemm_tc_main(a_hi + r0 * kpad, a_lo + r0 * kpad, b_hi, b_lo, dc + r0 * n, 1, rows, k, n, 3, flag, s_main);
+            }
             if (st == TRN_OK) st = launch_gemm_simt(da + r0 * k, db, dc + r0 * n, 1, rows, k, n, s_main, flag);
             TRN_CUDA(cudaEventRecord(done[u].e, s_main));
             TRN_CUDA(cudaStreamWaitEvent(s_down, done[u].e, 0));
@@ -550,10 +559,14 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
             TRN_CUDA(cudaMemcpyAsync(db + b0 * k * n, b + b0 * k * n, cnt * k * n * sizeof(float), cudaMemcpyHostToDevice, s_up));
             TRN_CUDA(cudaEventRecord(up[u].e, s_up));
             TRN_CUDA(cudaStreamWaitEvent(s_main, up[u].e, 0));
-            st = gemm_tc_split_a(da + b0 * m * k, a_hi + b0 * m * kpad, a_lo + b0 * m * kpad, cnt, m, k, flag, s_main);
-            if (st == TRN_OK) st = gemm_tc_split_b(db + b0 * k * n, b_hi + b0 * n * kpad, b_lo + b0 * n * kpad, cnt, k, n, flag, s_main);
-            if (st == TRN_OK) st = gemm_tc_main(a_hi + b0 * m * kpad, a_lo + b0 * m * kpad, b_hi + b0 * n * kpad, b_lo + b0 * n * kpad,
-                                                dc + b0 * m * n, cnt, m, k, n, 3, flag, s_main);
+            if (fused) {
+                st = gemm_tc_fused_main(da + b0 * m * k, db + b0 * k * n, dc + b0 * m * n, cnt, m, k, n, flag, s_main);
+            } else {
+                st = gemm_tc_split_a(da + b0 * m * k, a_hi + b0 * m * kpad, a_lo + b0 * m * kpad, cnt, m, k, flag, s_main);
+                if (st == TRN_OK) st = gemm_tc_split_b(db + b0 * k * n, b_hi + b0 * n * kpad, b_lo + b0 * n * kpad, cnt, k, n, flag, s_main);
+                if (st == TRN_OK) st = gemm_tc_main(a_hi + b0 * m * kpad, a_lo + b0 * m * kpad, b_hi + b0 * n * kpad, b_lo + b0 * n * kpad,
+                                                    dc + b0 * m * n, cnt, m, k, n, 3, flag, s_main);
+            }
             if (st == TRN_OK) st = launch_gemm_simt(da + b0 * m * k, db + b0 * k * n, dc + b0 * m * n, cnt, m, k, n, s_main, flag);
             TRN_CUDA(cudaEventRecord(done[u].e, s_main));
             TRN_CUDA(cudaStreamWaitEvent(s_down, done[u].e, 0));

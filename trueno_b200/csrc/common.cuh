@@ -143,6 +143,10 @@ int gemm_tc_split_a(const float* a, float* a_hi, float* a_lo, size_t batch, size
 int gemm_tc_split_b(const float* b, float* b_hi, float* b_lo, size_t batch, size_t k, size_t n, int* flag, cudaStream_t s);
 int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* c, size_t batch,
                  size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s);
+// fused-split variant (no pre-pass, raw operands; gemm_tc.cu): preconditions + default rule, and the kernel itself
+bool gemm_tc_uses_fused(const float* a, const float* b, size_t m, size_t k, size_t n);
+int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int* flag,
+                       cudaStream_t s);
 // auto-dispatch rule shared by the resident and the pipelined host paths (api.cu)
 bool gemm_auto_uses_tc(size_t m, size_t k, size_t n);
 bool is_pinned_host(const void* p);

@@ -79,6 +79,7 @@ struct Params {
     uint32_t m, n;            // C rows / cols per batch
     uint32_t num_kb;          // Kpad / BK
     uint32_t tiles_m, tiles_n, batch;
+    uint32_t terms_mask;      // fused kernel, debugging: bit 0 lo*hi, bit 1 hi*lo, bit 2 hi*hi (7 = the product)
 };
 
 // Tile order: batch-major, then groups of 16 m-tiles, n fastest-but-one inside a group, so CTAs
@@ -486,6 +487,270 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     }
 }
 
+// =====================================================================================================
+// Fused-split CTA-pair kernel: the same cta_group::2 tile machine WITHOUT the operand pre-pass.
+//
+// Why: at short K the pre-pass is a large share of the call (config 3, K = 128: 0.24 of 1.6 ms) and, worse, the
+// pre-split operands double the L2 -> SM traffic of every tile.  Config 3 moves 256 KiB of split operands in and
+// 128 KiB of C out per tile and SM, 62 B/clk/SM against an L2 slice throughput of ~42 B/clk/SM (6300 B/clk per chip):
+// the tile period was 9000 cycles for 6144 cycles of math.  Here TMA brings the RAW f32 tiles (half the bytes):
+//   * hi operand = the raw f32 words as they lie: kind::tf32 reads the top 19 bits of each word, i.e. the tensor
+//     core itself truncates x to hi = x & 0xFFFFE000;
+//   * lo operand = tf32_rna(x - hi), computed by two splitter warps per CTA from shared memory into a second copy
+//     of the tile AT THE SAME OFFSETS — an element-wise pass over the swizzled bytes that needs no knowledge of the
+//     layout.  x - hi is exact (13 bits) and its rounding to 11 bits costs 2^-10 * 2^-12 = 2^-22 of |x|, the same
+//     error as the pre-pass's round-to-nearest hi / lo pair; the dropped lo*lo term is <= 2^-20 relative.
+//   * A stays K-major ([m][k] rows, SWIZZLE_64B boxes of 128 x 16); B is consumed as it lies in memory, [k][n]
+//     row-major = MN-major for the tensor core (instruction-descriptor bit 16).  For 32-bit operands the only MN-major
+//     shared-memory layout is the 128-byte swizzle with 32-byte atoms (descriptor layout type 1, TMA swizzle
+//     128B_ATOM_32B: atoms of 32 n x 4 k; TMA boxes of 32 n x 16 k), so there is no transpose either.
+// K, m and n tails are zero-filled by TMA (no padding pass); Inf/NaN inputs are detected by the splitter warps,
+// which raise the same device flag the pre-pass raises: the gated SIMT kernel enqueued behind this one then
+// recomputes C with IEEE semantics.  Needs k % 4 == 0, n % 4 == 0 and 16-byte aligned operands (TMA strides).
+// Pipeline per stage: TMA (full) -> splitter warps of BOTH CTAs (ready, on the leader) -> MMA -> commit (empty).
+// =====================================================================================================
+namespace fused {
+constexpr int SBK = 16;
+constexpr uint32_t kARaw = BM * SBK * 4;            // 8 KiB: this CTA's 128 rows of A, K-major
+constexpr uint32_t kBBox = 32 * SBK * 4;            // 2 KiB: one TMA box of B, 32 n x 16 k (four 512-byte swizzle atoms)
+constexpr uint32_t kBRaw = (BN / 2 / 32) * kBBox;   // 8 KiB: this CTA's 128 of the tile's 256 columns of B
+constexpr uint32_t kRawBytes = kARaw + kBRaw;       // what TMA lands per stage
+constexpr uint32_t kStageBytes = 2 * kRawBytes;     // raw + lo
+constexpr int kStages = 6;
+constexpr uint32_t kChunkKB = kChunkK / SBK;
+constexpr uint32_t kStoreBytes = kEpiWarps * 4096;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 + 256;
+constexpr int kSplitWarps = 2;                      // warps 2-3 of warpgroup 0
+}  // namespace fused
+
+__device__ __forceinline__ uint32_t split_lo_bits(uint32_t x, bool& bad) {
+    bad |= (x & 0x7F800000u) == 0x7F800000u;
+    const float r = __uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u);   // exact
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+    return l;
+}
+
+__global__ void __launch_bounds__(kPairThreads, 1)
+gemm_tf32x3_fused_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                              const __grid_constant__ CUtensorMap map_c, const Params p, int* raise_flag) {
+    using namespace fused;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t store_base = smem_base + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * kStageBytes + kStoreBytes);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (3 * kStages + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (3 * kStages + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const uint32_t total_tiles = p.tiles_m * p.tiles_n * p.batch;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+            mbar_init(ready_bar(s), 2 * kSplitWarps);   // the splitter warps of both CTAs (leader's copy is the one used)
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 2 * kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs, own tiles, own barrier) =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
+                uint32_t b, mt, nt;
+                tile_coords<8>(t, p, b, mt, nt);
+                const int m0 = (int)(mt * 2 * BM + rank * BM), n0 = (int)(nt * BN + rank * (BN / 2));
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * kStageBytes;
+                    mbar_expect_tx(full_bar(stage), kRawBytes);
+                    const int k0 = (int)(kb * SBK);
+                    tma_load_3d(sa, &map_a, full_bar(stage), k0, m0, (int)b);
+#pragma unroll
+                    for (int j = 0; j < BN / 2 / 32; ++j)
+                        tma_load_3d(sa + kARaw + j * kBBox, &map_b, full_bar(stage), n0 + 32 * j, k0, (int)b);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(2 * BM, BN) | (1u << 16);   // B is MN-major
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    const uint32_t in_chunk = kb % kChunkKB;
+                    if (in_chunk == 0) {
+                        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t d = tmem_base + acc * BN;
+                    mbar_wait(ready_bar(stage), phase);   // both CTAs' stages are landed and split
+                    tc_fence_after();
+                    const bool chunk_end = in_chunk == kChunkKB - 1 || kb == p.num_kb - 1;
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint32_t a_hi = sa, b_hi = sa + kARaw;
+                        const uint32_t a_lo = sa + kRawBytes, b_lo = a_lo + kARaw;
+#pragma unroll
+                        for (int k = 0; k < SBK / UMMA_K; ++k) {
+                            const uint32_t ka = k * UMMA_K * 4;   // A: 32 bytes along K inside the 64-byte swizzled row
+                            const uint32_t kbo = k * 1024;        // B: the next 8 k-rows (two 4-row swizzle atoms) of every box
+                            const uint32_t accum = (in_chunk | (uint32_t)k) != 0;
+                            if (p.terms_mask == 7u) {
+                                umma_tf32_pair(d, make_desc_k<SBK>(a_lo + ka), make_desc_mn_tf32(b_hi + kbo, kBBox), idesc, accum);
+                                umma_tf32_pair(d, make_desc_k<SBK>(a_hi + ka), make_desc_mn_tf32(b_lo + kbo, kBBox), idesc, 1u);
+                                umma_tf32_pair(d, make_desc_k<SBK>(a_hi + ka), make_desc_mn_tf32(b_hi + kbo, kBBox), idesc, 1u);
+                            } else {   // TRN_GEMM_FUSED_TERMS: single terms for debugging / the 1xTF32 probe
+                                uint32_t acc1 = accum;
+                                if (p.terms_mask & 1u) { umma_tf32_pair(d, make_desc_k<SBK>(a_lo + ka), make_desc_mn_tf32(b_hi + kbo, kBBox), idesc, acc1); acc1 = 1u; }
+                                if (p.terms_mask & 2u) { umma_tf32_pair(d, make_desc_k<SBK>(a_hi + ka), make_desc_mn_tf32(b_lo + kbo, kBBox), idesc, acc1); acc1 = 1u; }
+                                if (p.terms_mask & 4u) { umma_tf32_pair(d, make_desc_k<SBK>(a_hi + ka), make_desc_mn_tf32(b_hi + kbo, kBBox), idesc, acc1); }
+                            }
+                        }
+                        umma_commit_pair(empty_bar(stage));
+                        if (chunk_end) umma_commit_pair(tmem_full_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (chunk_end && ++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== splitter warps (2-3, both CTAs): lo = tf32_rna(x - trunc_tf32(x)) =====================
+        const uint32_t sw = (uint32_t)warp - 2;
+        bool bad = false;
+        uint32_t stage = 0, phase = 0;
+        constexpr uint32_t kPerWarp = kRawBytes / 16 / kSplitWarps;   // float4 per warp per stage (512)
+        for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
+            for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                const uint32_t raw = smem_base + stage * kStageBytes + (sw * kPerWarp + (uint32_t)lane) * 16u;
+#pragma unroll
+                for (uint32_t h = 0; h < kPerWarp / 32 / 8; ++h) {
+                    uint32_t v[8][4];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                                     : "r"(raw + (h * 8 + u) * 512u));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[u][e] = split_lo_bits(v[u][e], bad);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(raw + kRawBytes + (h * 8 + u) * 512u), "r"(v[u][0]),
+                                     "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3]) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tensor core reads lo through the async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ready_bar(stage) & kPeerMask);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        if (bad) *raise_flag = 1;
+    }
+    } else {
+        // ===================== epilogue (warps 4..11, both CTAs, own 128 rows): as in the pre-split pair kernel ==========
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+        const uint32_t quad = warp & 3;
+        const uint32_t half = (warp - 4) >> 2;
+        const uint32_t num_chunks = (p.num_kb + kChunkKB - 1) / kChunkKB;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
+            uint32_t b, mt, nt;
+            tile_coords<8>(t, p, b, mt, nt);
+            float sum[128];
+            for (uint32_t ch = 0; ch < num_chunks; ++ch) {
+                mbar_wait(tmem_full_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * BN + half * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + j * 32, r);
+                    tmem_ld_wait();
+                    if (ch == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __uint_as_float(r[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __fadd_rn(sum[j * 32 + i], __uint_as_float(r[i]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(acc) & kPeerMask);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            const uint32_t row0 = mt * 2 * BM + rank * BM + quad * 32;
+            const uint32_t row = row0 + lane;
+            const uint32_t col_base = nt * BN + half * 128;
+            if (p.tma_store) {
+                const uint32_t stage_addr = store_base + (uint32_t)(warp - 4) * 4096u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t dst = stage_addr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) * 16);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(dst), "f"(sum[j * 32 + 4 * q]),
+                                     "f"(sum[j * 32 + 4 * q + 1]), "f"(sum[j * 32 + 4 * q + 2]), "f"(sum[j * 32 + 4 * q + 3])
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && row0 < p.m && col_base + j * 32 < p.n) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     :: "l"(&map_c), "r"(stage_addr), "r"((int)(col_base + j * 32)), "r"((int)row0), "r"((int)b)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else if (row < p.m && col_base < p.n) {
+                float* crow = p.c + ((size_t)b * p.m + row) * p.n + col_base;
+#pragma unroll
+                for (int j = 0; j < 128; ++j)
+                    if (col_base + j < p.n) crow[j] = sum[j];
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ---- operand pre-pass: split into tf32 hi/lo, pad K, lay B out K-major ------------------------------
 // returns true when x is Inf/NaN (the caller raises the fallback flag)
 __device__ __forceinline__ bool split_tf32(float x, float& hi, float& lo) {
@@ -626,7 +891,7 @@ static EncodeTiledFn get_encode() {
 
 // [batch][rows][kpad] f32, box = {box_cols, box_rows, 1}; swizzle span = box_cols * 4 bytes (128 or 64)
 int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows,
-             uint32_t box_cols) {
+             uint32_t box_cols, bool atom32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     cuuint64_t dims[3] = {kpad, rows, batch};
@@ -634,7 +899,8 @@ int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, siz
     cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TRN_GPU_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -793,6 +1059,72 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
     return launch<1, 32>(map_ah, map_al, map_bh, map_bl, map_c, p, cx->sm_count, s);
 }
 
+// The fused-split kernel's preconditions (TMA strides of the RAW operands) and the shapes it is the default for.
+// TRN_GEMM_FUSED = 0 / 1 forces the pre-pass / the fused kernel for A/B measurements and the parity tests.
+bool gemm_tc_fused_ok(const float* a, const float* b, size_t m, size_t k, size_t n) {
+    return m > (size_t)tc::BM && k % 4 == 0 && n % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
+}
+static int fused_mode() {
+    static const int mode = [] { const char* e = getenv("TRN_GEMM_FUSED"); return e ? atoi(e) : -1; }();
+    return mode;
+}
+static size_t fused_max_k() {
+    static const size_t v = [] { const char* e = getenv("TRN_GEMM_FUSED_MAXK"); return e ? (size_t)atol(e) : (size_t)384; }();
+    return v;
+}
+bool gemm_tc_uses_fused(const float* a, const float* b, size_t m, size_t k, size_t n) {
+    if (!gemm_tc_fused_ok(a, b, m, k, n)) return false;
+    const int mode = fused_mode();
+    return mode == 1 || (mode != 0 && k <= fused_max_k());
+}
+
+// C[b] = A[b] * B[b] straight from the raw operands (no scratch): the splitter warps raise *flag on Inf/NaN.
+int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int* flag,
+                       cudaStream_t s) {
+    using namespace tc;
+    Context* cx = ctx();
+    if (!cx) return TRN_GPU_ERROR;
+    if (batch == 0 || m == 0 || n == 0) return TRN_OK;
+    CUtensorMap ma, mb, mc;
+    TRN_TRY(make_map(&ma, a, batch, m, k, BM, fused::SBK));     // [batch][m][k], boxes of 128 rows x 16 k, SWIZZLE_64B
+    TRN_TRY(make_map(&mb, b, batch, k, n, fused::SBK, 32, true));   // [batch][k][n], boxes of 16 k x 32 n, SWIZZLE_128B_ATOM_32B
+    mc = ma;
+    const bool tma_store = (reinterpret_cast<uintptr_t>(c) & 15u) == 0;   // n % 4 == 0 is a precondition here
+    if (tma_store) TRN_TRY(make_map(&mc, c, batch, m, n, 32, 32));
+    Params p;
+    p.c = c;
+    p.tma_store = tma_store ? 1u : 0u;
+    p.nonfinite_flag = flag;
+    p.m = (uint32_t)m;
+    p.n = (uint32_t)n;
+    p.num_kb = (uint32_t)((k + fused::SBK - 1) / fused::SBK);
+    p.tiles_m = (uint32_t)((m + 2 * BM - 1) / (2 * BM));
+    p.tiles_n = (uint32_t)((n + BN - 1) / BN);
+    p.batch = (uint32_t)batch;
+    static const uint32_t terms_mask = [] { const char* e = getenv("TRN_GEMM_FUSED_TERMS"); const int v = e ? atoi(e) : 7; return (uint32_t)(v >= 1 && v <= 7 ? v : 7); }();
+    p.terms_mask = terms_mask;
+    static const cudaError_t smem_optin = cudaFuncSetAttribute(gemm_tf32x3_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmemBytes);
+    TRN_CUDA(smem_optin);
+    const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
+    const uint32_t max_pairs = (uint32_t)cx->sm_count / 2;
+    const uint32_t pairs = total < max_pairs ? total : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kPairThreads);
+    cfg.dynamicSmemBytes = fused::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TRN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused_pair_kernel, ma, mb, mc, p, flag));
+    count_launch();
+    return TRN_OK;
+}
+
 int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int terms,
                    cudaStream_t s) {
     Context* cx = ctx();
@@ -800,6 +1132,31 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     if (batch == 0 || m == 0 || n == 0) return TRN_OK;
     const size_t kpad = gemm_tc_kpad(k);
     const size_t a_elems = batch * m * kpad, b_elems = batch * n * kpad;
+
+    if (terms == 3 && gemm_tc_uses_fused(a, b, m, k, n)) {
+        // no pre-pass, no operand scratch: only the 4-byte non-finite flag the splitter warps may raise
+        int* flag = nullptr;
+        TRN_TRY(scratch_alloc((void**)&flag, 256, s));
+        TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+        cudaEvent_t* ev = nullptr;
+        if (g_profile) {
+            if (!g_ev_created) {
+                for (auto& t : g_ev) for (auto& e : t) TRN_CUDA(cudaEventCreate(&e));
+                g_ev_created = true;
+            }
+            ev = g_ev[g_ev_count % kProfRing];
+            TRN_CUDA(cudaEventRecord(ev[0], s));
+            TRN_CUDA(cudaEventRecord(ev[1], s));
+        }
+        int st = gemm_tc_fused_main(a, b, c, batch, m, k, n, flag, s);
+        if (ev) {
+            TRN_CUDA(cudaEventRecord(ev[2], s));
+            ++g_ev_count;
+        }
+        if (st == TRN_OK) st = launch_gemm_simt(a, b, c, batch, m, k, n, s, flag);
+        scratch_free(flag, s);
+        return st;
+    }
 
     // scratch: A_hi, A_lo, Bt_hi, Bt_lo (stream-ordered pool; stays cached between calls)
     float* scratch = nullptr;

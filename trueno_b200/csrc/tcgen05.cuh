@@ -89,6 +89,15 @@ __host__ __device__ constexpr uint64_t make_desc_k(uint32_t smem_addr) {
     constexpr uint64_t type = SBK == 32 ? 2ull : 4ull;
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
+// MN-major descriptor for 32-bit operands (an operand consumed as it lies in a row-major [k][mn] array).  tf32 has ONE
+// MN-major shared-memory layout: the 128-byte swizzle with 32-byte atoms (layout type 1, SWIZZLE_128B_BASE32B;
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B on the TMA side).  In bytes: 128 contiguous bytes (32 tf32) along MN per k-row,
+// rows 128 bytes apart, the four 32-byte chunks of a row XOR-ed with (row & 3) — a 512-byte atom of 32 mn x 4 k;
+// SBO = bytes between 4-row atoms along K (512 when rows are consecutive), LBO = bytes between 32-wide blocks along MN.
+__host__ __device__ constexpr uint64_t make_desc_mn_tf32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes = 512) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (1ull << 61);
+}
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
@@ -119,6 +128,22 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
 }
+// release at cluster scope: the arriving thread's earlier shared-memory writes (and proxy fences) are visible to the
+// thread of the OTHER CTA that acquires the barrier
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "WAIT_DONE_C:\n\t"
+        "}" :: "r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -140,7 +165,7 @@ __device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem
 
 // [batch][rows][kpad] f32 tensor map, box = {box_cols, box_rows, 1}; swizzle span = box_cols * 4 bytes (128 or 64)
 int make_map(CUtensorMap* map, const float* base, size_t batch, size_t rows, size_t kpad, uint32_t box_rows,
-             uint32_t box_cols);
+             uint32_t box_cols, bool atom32 = false);
 
 }  // namespace tc
 }  // namespace trn
