@@ -17,7 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # (batch, m, k, n): K tails (k % 16 != 0), n % 32 != 0, m tails inside a 256-row pair tile, one and many k-chunks
 SHAPES = [(1, 256, 128, 256), (1, 129, 4, 4), (1, 300, 36, 260), (1, 257, 200, 516), (3, 384, 72, 132), (1, 1024, 1024, 1024),
-          (2, 130, 2052, 300), (1, 2048, 128, 2048), (4, 512, 64, 512), (1, 131, 16, 100)]
+          (2, 130, 2052, 300), (1, 2048, 128, 2048), (4, 512, 64, 512), (1, 131, 16, 100),
+          # K <= 128 with several n-tiles: the A-stationary form (panel changes inside a pair's tile range, ragged edges)
+          (2, 520, 128, 1100), (1, 256, 4, 516), (5, 300, 100, 772), (37, 256, 32, 512)]
 
 
 def _worker():

@@ -79,6 +79,9 @@ struct Params {
     uint32_t m, n;            // C rows / cols per batch
     uint32_t num_kb;          // Kpad / BK
     uint32_t tiles_m, tiles_n, batch;
+    uint32_t nseg;            // A-stationary kernel: n-segments per A panel (work unit = panel x segment)
+    uint32_t store_hint;      // fused kernels: 1 = C stores carry an L2 evict_first policy (C much larger than L2)
+    uint32_t debug;           // fused kernels, experiments (TRN_GEMM_DEBUG): bit 0 skip the C stores, bit 1 aim every store at batch 0
     uint32_t terms_mask;      // fused kernel, debugging: bit 0 lo*hi, bit 1 hi*lo, bit 2 hi*hi (7 = the product)
 };
 
@@ -509,6 +512,80 @@ gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 // recomputes C with IEEE semantics.  Needs k % 4 == 0, n % 4 == 0 and 16-byte aligned operands (TMA strides).
 // Pipeline per stage: TMA (full) -> splitter warps of BOTH CTAs (ready, on the leader) -> MMA -> commit (empty).
 // =====================================================================================================
+// One tile of the CTA-pair epilogue (shared by the fused-split kernels): drain this CTA's 128 rows of the accumulator,
+// chunk by chunk, into register accumulators (the second accumulation level), then registers -> swizzled 32x32 staging
+// block -> TMA tensor store.  `ewarp` 0..7: TMEM lane quadrant ewarp % 4, column half ewarp / 4.
+__device__ __forceinline__ void pair_epilogue_tile(const CUtensorMap* map_c, const Params& p, uint32_t tmem_base, uint32_t store_base,
+                                                   uint32_t tmem_full0, uint32_t tmem_empty0, uint32_t num_chunks, uint32_t& acc,
+                                                   uint32_t& acc_phase, uint32_t b, uint32_t mt, uint32_t nt, int ewarp, int lane,
+                                                   uint32_t rank) {
+    const uint32_t quad = (uint32_t)ewarp & 3u, half = (uint32_t)ewarp >> 2;
+    auto cblock = [&](int j) -> uint32_t { return half * 4u + (uint32_t)j; };   // the 32-column blocks this warp owns
+    float sum[128];
+    for (uint32_t ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(tmem_full0 + 8u * acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * BN;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + cblock(j) * 32, r);
+            tmem_ld_wait();
+            if (ch == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __uint_as_float(r[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __fadd_rn(sum[j * 32 + i], __uint_as_float(r[i]));
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster((tmem_empty0 + 8u * acc) & kPeerMask);   // on the leader's barrier
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    const uint32_t row0 = mt * 2 * BM + rank * BM + quad * 32;
+    const uint32_t row = row0 + lane;
+    const uint32_t col_base = nt * BN + half * 128;
+    if (p.tma_store) {
+        const uint32_t stage_addr = store_base + (uint32_t)ewarp * 4096u;
+        // C larger than L2 is a pure stream: evict_first keeps it from displacing the operand tiles and lets L2 write it
+        // back in arrival order (config 3, 4 GiB of C: 1.325 -> 1.27 ms; no effect in the pre-split kernel of round 1)
+        uint64_t policy = 0;
+        if (p.store_hint) policy = l2_policy_drop();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t dst = stage_addr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) * 16);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(dst), "f"(sum[j * 32 + 4 * q]),
+                             "f"(sum[j * 32 + 4 * q + 1]), "f"(sum[j * 32 + 4 * q + 2]), "f"(sum[j * 32 + 4 * q + 3])
+                             : "memory");
+            }
+            const uint32_t col = nt * BN + cblock(j) * 32;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && row0 < p.m && col < p.n && !(p.debug & 1u)) {
+                if (p.store_hint)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                                 :: "l"(map_c), "r"(stage_addr), "r"((int)col), "r"((int)row0), "r"((int)b), "l"(policy) : "memory");
+                else
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                             :: "l"(map_c), "r"(stage_addr), "r"((int)col), "r"((int)row0), "r"((int)((p.debug & 2u) ? 0u : b))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    } else if (row < p.m && col_base < p.n) {
+        float* crow = p.c + ((size_t)b * p.m + row) * p.n + col_base;
+#pragma unroll
+        for (int j = 0; j < 128; ++j)
+            if (col_base + j < p.n) crow[j] = sum[j];
+    }
+}
+
 namespace fused {
 constexpr int SBK = 16;
 constexpr uint32_t kARaw = BM * SBK * 4;            // 8 KiB: this CTA's 128 rows of A, K-major
@@ -675,69 +752,251 @@ gemm_tf32x3_fused_pair_kernel(const __grid_constant__ CUtensorMap map_a, const _
         if (bad) *raise_flag = 1;
     }
     } else {
-        // ===================== epilogue (warps 4..11, both CTAs, own 128 rows): as in the pre-split pair kernel ==========
+        // ===================== epilogue (warps 4..11, both CTAs, own 128 rows) =====================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
-        const uint32_t quad = warp & 3;
-        const uint32_t half = (warp - 4) >> 2;
         const uint32_t num_chunks = (p.num_kb + kChunkKB - 1) / kChunkKB;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = pair_id; t < total_tiles; t += num_pairs) {
             uint32_t b, mt, nt;
             tile_coords<8>(t, p, b, mt, nt);
-            float sum[128];
-            for (uint32_t ch = 0; ch < num_chunks; ++ch) {
-                mbar_wait(tmem_full_bar(acc), acc_phase);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * BN + half * 128;
+            pair_epilogue_tile(&map_c, p, tmem_base, store_base, tmem_full_bar(0), tmem_empty_bar(0), num_chunks, acc, acc_phase,
+                               b, mt, nt, warp - 4, lane, rank);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// =====================================================================================================
+// A-stationary fused-split kernel for K <= 128 (the batched Q K^T shape of config 3: 256 heads of 2048 x 128 x 2048).
+//
+// ncu on the fused kernel above at config 3: tile period 9700 cycles for 6144 cycles of math, the SM's shared-memory data
+// pipe ~97 % busy — per tile and CTA 3077 wavefronts (128 B) of MMA operand reads, 3072 of splitter / staging LSU traffic,
+// 2048 of TMA writes (operands) and reads (C stores), plus arbitration losses.  This kernel keeps the pair's 256-row A panel
+// (raw + lo, 128 KiB per CTA at K = 128) in shared memory for ALL the n-tiles of its row of C and rings only B (4 stages
+// of 16 KiB): per tile that removes 7/8 of A's TMA writes and of A's splitter reads and writes (1344 wavefronts) and
+// halves the L2 -> SM operand traffic again.  A pair works through whole (panel, n-segment) units; the next panel is
+// loaded k-block by k-block into the slots the LAST tile of the current unit frees (a_empty[kb], committed only in that
+// tile), which hides the reload under that tile's remaining MMAs.
+// =====================================================================================================
+namespace astat {
+constexpr int SBK = 16;
+constexpr int kMaxKB = 8;                            // K <= 128
+constexpr uint32_t kABlk = BM * SBK * 4;             // 8 KiB: one k-block of this CTA's 128 A rows (raw; the lo copy follows it)
+constexpr uint32_t kASlot = 2 * kABlk;               // 16 KiB per k-block: raw + lo
+constexpr uint32_t kPanelBytes = kMaxKB * kASlot;    // 128 KiB
+constexpr uint32_t kBBox = 32 * SBK * 4;             // 2 KiB: 32 n x 16 k
+constexpr uint32_t kBRaw = (BN / 2 / 32) * kBBox;    // 8 KiB: this CTA's 128 columns of one k-block of B
+constexpr uint32_t kBStage = 2 * kBRaw;              // raw + lo
+constexpr int kBStages = 4;
+constexpr uint32_t kStoreBytes = kEpiWarps * 4096;
+constexpr uint32_t kSmemBytes = kPanelBytes + kBStages * kBStage + kStoreBytes + 1024 + 512;
+constexpr int kSplitWarps = 2;
+}  // namespace astat
+
+// one 8 KiB block (512 float4) over the two splitter warps: 8 float4 per lane, all loads in flight before the first store
+__device__ __forceinline__ void split_block_8k(uint32_t raw_addr, uint32_t lo_addr, uint32_t sw, int lane, bool& bad) {
+    const uint32_t off = (sw * 256u + (uint32_t)lane) * 16u;
+    uint32_t v[8][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + j * 32, r);
-                    tmem_ld_wait();
-                    if (ch == 0) {
+    for (int u = 0; u < 8; ++u)
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                     : "r"(raw_addr + off + u * 512u));
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __uint_as_float(r[i]);
-                    } else {
+    for (int u = 0; u < 8; ++u) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) sum[j * 32 + i] = __fadd_rn(sum[j * 32 + i], __uint_as_float(r[i]));
+        for (int e = 0; e < 4; ++e) v[u][e] = split_lo_bits(v[u][e], bad);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(lo_addr + off + u * 512u), "r"(v[u][0]), "r"(v[u][1]),
+                     "r"(v[u][2]), "r"(v[u][3]) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(kPairThreads, 1)
+gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                    const __grid_constant__ CUtensorMap map_c, const Params p, int* raise_flag) {
+    using namespace astat;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t panel_base = smem_base;
+    const uint32_t ring_base = smem_base + kPanelBytes;
+    const uint32_t store_base = ring_base + kBStages * kBStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kPanelBytes + kBStages * kBStage + kStoreBytes);
+    const uint32_t bar_base = smem_u32(bars);
+    auto a_full = [&](int kb) { return bar_base + 8u * kb; };
+    auto a_ready = [&](int kb) { return bar_base + 8u * (kMaxKB + kb); };
+    auto a_empty = [&](int kb) { return bar_base + 8u * (2 * kMaxKB + kb); };
+    auto b_full = [&](int s) { return bar_base + 8u * (3 * kMaxKB + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (3 * kMaxKB + kBStages + s); };
+    auto b_ready = [&](int s) { return bar_base + 8u * (3 * kMaxKB + 2 * kBStages + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (3 * kMaxKB + 3 * kBStages + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxKB + 3 * kBStages + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxKB + 3 * kBStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const uint32_t total_tiles = p.tiles_m * p.tiles_n * p.batch;
+    // Work unit = one A panel (b, mt) x one segment of its n-tiles; units are dealt round-robin in the order
+    // (b, segment, mt), so the pairs that run side by side hold different panels of the SAME batch entry and
+    // walk the same B tiles together (L2 hits).  p.nseg segments per panel (1 when there are panels enough).
+    const uint32_t units = p.batch * p.tiles_m * p.nseg;
+    auto unit_coords = [&](uint32_t u, uint32_t& b, uint32_t& mt, uint32_t& n_lo, uint32_t& n_hi) {
+        mt = u % p.tiles_m;
+        const uint32_t r = u / p.tiles_m;
+        const uint32_t seg = r % p.nseg;
+        b = r / p.nseg;
+        n_lo = (uint32_t)(((uint64_t)seg * p.tiles_n) / p.nseg);
+        n_hi = (uint32_t)(((uint64_t)(seg + 1) * p.tiles_n) / p.nseg);
+    };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
+        for (int kb = 0; kb < kMaxKB; ++kb) {
+            mbar_init(a_full(kb), 1);
+            mbar_init(a_ready(kb), 2 * kSplitWarps);
+            mbar_init(a_empty(kb), 1);
+        }
+        for (int s = 0; s < kBStages; ++s) {
+            mbar_init(b_full(s), 1);
+            mbar_init(b_empty(s), 1);
+            mbar_init(b_ready(s), 2 * kSplitWarps);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 2 * kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0, panel = 0;
+            for (uint32_t u = pair_id; u < units; u += num_pairs, ++panel) {
+              uint32_t b, mt, n_lo, n_hi;
+              unit_coords(u, b, mt, n_lo, n_hi);
+              const uint32_t a_par = panel & 1u;
+              for (uint32_t nt = n_lo; nt < n_hi; ++nt) {
+                const bool new_panel = nt == n_lo;
+                const int m0 = (int)(mt * 2 * BM + rank * BM), n0 = (int)(nt * BN + rank * (BN / 2));
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    const int k0 = (int)(kb * SBK);
+                    if (new_panel) {
+                        mbar_wait(a_empty(kb), a_par ^ 1);   // the previous panel's last tile is done with this k-block
+                        mbar_expect_tx(a_full(kb), kABlk);
+                        tma_load_3d(panel_base + kb * kASlot, &map_a, a_full(kb), k0, m0, (int)b);
                     }
+                    mbar_wait(b_empty(stage), phase ^ 1);
+                    const uint32_t sb = ring_base + stage * kBStage;
+                    mbar_expect_tx(b_full(stage), kBRaw);
+#pragma unroll
+                    for (int j = 0; j < BN / 2 / 32; ++j)
+                        tma_load_3d(sb + j * kBBox, &map_b, b_full(stage), n0 + 32 * j, k0, (int)b);
+                    if (++stage == kBStages) { stage = 0; phase ^= 1; }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(acc) & kPeerMask);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+              }
             }
-            const uint32_t row0 = mt * 2 * BM + rank * BM + quad * 32;
-            const uint32_t row = row0 + lane;
-            const uint32_t col_base = nt * BN + half * 128;
-            if (p.tma_store) {
-                const uint32_t stage_addr = store_base + (uint32_t)(warp - 4) * 4096u;
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(2 * BM, BN) | (1u << 16);   // B is MN-major
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, panel = 0;
+            for (uint32_t u = pair_id; u < units; u += num_pairs, ++panel) {
+              uint32_t b, mt, n_lo, n_hi;
+              unit_coords(u, b, mt, n_lo, n_hi);
+              const uint32_t a_par = panel & 1u;
+              for (uint32_t nt = n_lo; nt < n_hi; ++nt) {
+                const bool new_panel = nt == n_lo;
+                const bool last_in_panel = nt + 1 == n_hi;
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);   // K <= 128: one TMEM partial per tile
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    if (new_panel) mbar_wait(a_ready(kb), a_par);
+                    mbar_wait(b_ready(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = panel_base + kb * kASlot, a_lo = a_hi + kABlk;
+                        const uint32_t b_hi = ring_base + stage * kBStage, b_lo = b_hi + kBRaw;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t dst = stage_addr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) * 16);
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(dst), "f"(sum[j * 32 + 4 * q]),
-                                     "f"(sum[j * 32 + 4 * q + 1]), "f"(sum[j * 32 + 4 * q + 2]), "f"(sum[j * 32 + 4 * q + 3])
-                                     : "memory");
+                        for (int k = 0; k < SBK / UMMA_K; ++k) {
+                            const uint32_t ka = k * UMMA_K * 4;
+                            const uint32_t kbo = k * 1024;
+                            const uint32_t accum = (kb | (uint32_t)k) != 0;
+                            umma_tf32_pair(d, make_desc_k<SBK>(a_lo + ka), make_desc_mn_tf32(b_hi + kbo, kBBox), idesc, accum);
+                            umma_tf32_pair(d, make_desc_k<SBK>(a_hi + ka), make_desc_mn_tf32(b_lo + kbo, kBBox), idesc, 1u);
+                            umma_tf32_pair(d, make_desc_k<SBK>(a_hi + ka), make_desc_mn_tf32(b_hi + kbo, kBBox), idesc, 1u);
+                        }
+                        umma_commit_pair(b_empty(stage));
+                        if (last_in_panel) umma_commit_pair(a_empty(kb));
+                        if (kb + 1 == p.num_kb) umma_commit_pair(tmem_full_bar(acc));
                     }
+                    __syncwarp();
+                    if (++stage == kBStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+              }
+            }
+        }
+    } else {
+        // ===================== splitter warps (2-3, both CTAs) =====================
+        const uint32_t sw = (uint32_t)warp - 2;
+        bool bad = false;
+        uint32_t stage = 0, phase = 0, panel = 0;
+        for (uint32_t u = pair_id; u < units; u += num_pairs, ++panel) {
+          uint32_t b, mt, n_lo, n_hi;
+          unit_coords(u, b, mt, n_lo, n_hi);
+          const uint32_t a_par = panel & 1u;
+          for (uint32_t nt = n_lo; nt < n_hi; ++nt) {
+            const bool new_panel = nt == n_lo;
+            for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                if (new_panel) {
+                    mbar_wait(a_full(kb), a_par);
+                    const uint32_t sa = panel_base + kb * kASlot;
+                    split_block_8k(sa, sa + kABlk, sw, lane, bad);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0 && row0 < p.m && col_base + j * 32 < p.n) {
-                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                     :: "l"(&map_c), "r"(stage_addr), "r"((int)(col_base + j * 32)), "r"((int)row0), "r"((int)b)
-                                     : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
+                    if (lane == 0) mbar_arrive_cluster(a_ready(kb) & kPeerMask);
                 }
-            } else if (row < p.m && col_base < p.n) {
-                float* crow = p.c + ((size_t)b * p.m + row) * p.n + col_base;
-#pragma unroll
-                for (int j = 0; j < 128; ++j)
-                    if (col_base + j < p.n) crow[j] = sum[j];
+                mbar_wait(b_full(stage), phase);
+                const uint32_t sb = ring_base + stage * kBStage;
+                split_block_8k(sb, sb + kBRaw, sw, lane, bad);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(b_ready(stage) & kPeerMask);
+                if (++stage == kBStages) { stage = 0; phase ^= 1; }
             }
+          }
+        }
+        if (bad) *raise_flag = 1;
+    }
+    } else {
+        // ===================== epilogue (warps 4..11, both CTAs, own 128 rows) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t u = pair_id; u < units; u += num_pairs) {
+            uint32_t b, mt, n_lo, n_hi;
+            unit_coords(u, b, mt, n_lo, n_hi);
+            for (uint32_t nt = n_lo; nt < n_hi; ++nt)
+                pair_epilogue_tile(&map_c, p, tmem_base, store_base, tmem_full_bar(0), tmem_empty_bar(0), 1u, acc, acc_phase,
+                                   b, mt, nt, warp - 4, lane, rank);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -1103,15 +1362,39 @@ int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, s
     p.batch = (uint32_t)batch;
     static const uint32_t terms_mask = [] { const char* e = getenv("TRN_GEMM_FUSED_TERMS"); const int v = e ? atoi(e) : 7; return (uint32_t)(v >= 1 && v <= 7 ? v : 7); }();
     p.terms_mask = terms_mask;
+    static const uint32_t debug_bits = [] { const char* e = getenv("TRN_GEMM_DEBUG"); return (uint32_t)(e ? atoi(e) : 0); }();
+    p.debug = debug_bits;
+    static const int hint_on = [] { const char* e = getenv("TRN_GEMM_STORE_HINT"); return e ? atoi(e) : 1; }();
+    p.store_hint = (hint_on && batch * m * n * sizeof(float) > ((size_t)64 << 20)) ? 1u : 0u;
     static const cudaError_t smem_optin = cudaFuncSetAttribute(gemm_tf32x3_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmemBytes);
     TRN_CUDA(smem_optin);
-    const uint32_t total = p.tiles_m * p.tiles_n * p.batch;
+    static const cudaError_t smem_optin2 = cudaFuncSetAttribute(gemm_tf32x3_fused_astat_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, astat::kSmemBytes);
+    TRN_CUDA(smem_optin2);
+    // K <= 128 and at least two n-tiles per row of C: keep the A panel in shared memory (TRN_GEMM_ASTAT=0 disables)
+    static const int astat_on = [] { const char* e = getenv("TRN_GEMM_ASTAT"); return e ? atoi(e) : 1; }();
+    const bool use_astat = astat_on && p.num_kb <= (uint32_t)astat::kMaxKB && p.tiles_n >= 2;
+    const uint32_t max_pairs_hw = (uint32_t)cx->sm_count / 2;
+    {   // segments per A panel: the split that minimises the busiest pair's work — rounds of units x (tiles per unit + a
+        // panel-switch allowance); config 3 (2048 panels) keeps whole panels, one 8192 x 128 x 8192 product gets 16 segments
+        const uint64_t panels = (uint64_t)p.batch * p.tiles_m;
+        double best = 1e300;
+        uint32_t best_nseg = 1;
+        for (uint32_t nseg = 1; nseg <= p.tiles_n; ++nseg) {
+            const uint64_t units = panels * nseg;
+            const uint64_t rounds = (units + max_pairs_hw - 1) / max_pairs_hw;
+            const uint32_t tpu = (p.tiles_n + nseg - 1) / nseg;
+            const double cost = (double)rounds * ((double)tpu + 0.35);
+            if (cost < best - 1e-9) { best = cost; best_nseg = nseg; }
+        }
+        p.nseg = best_nseg;
+    }
+    const uint64_t total = use_astat ? (uint64_t)p.tiles_m * p.batch * p.nseg : (uint64_t)p.tiles_m * p.tiles_n * p.batch;
     const uint32_t max_pairs = (uint32_t)cx->sm_count / 2;
-    const uint32_t pairs = total < max_pairs ? total : max_pairs;
+    const uint32_t pairs = total < max_pairs ? (uint32_t)total : max_pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kPairThreads);
-    cfg.dynamicSmemBytes = fused::kSmemBytes;
+    cfg.dynamicSmemBytes = use_astat ? astat::kSmemBytes : fused::kSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1120,7 +1403,8 @@ int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, s
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TRN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused_pair_kernel, ma, mb, mc, p, flag));
+    if (use_astat) TRN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused_astat_pair_kernel, ma, mb, mc, p, flag));
+    else TRN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused_pair_kernel, ma, mb, mc, p, flag));
     count_launch();
     return TRN_OK;
 }
