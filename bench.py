@@ -4,24 +4,31 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Headline metric (BASELINE.json): f32 matmul TFLOP/s at 8192^2 — Matrix::matmul 8192x8192x8192
-(config 2, "3xTF32 tcgen05").  One step = one pass of the hot path over one batch: C = A * B with
-A, B resident in HBM (value) or in pinned host memory through the host-slice C-ABI call (e2e).
-At N > 1 the path shards by output row blocks: every rank owns an 8192-row block
-of A and C and a replica of B — weak scaling, no data-path collective.  The reduction half of the
-BASELINE metric (dot / sum / argmax / norm_l2 GB/s on 2^30 f32, sliced across the ranks with an
-NCCL all-reduce of the partials) and the config-5 row kernels are measured after the timed region
-and reported under "secondary"; they are explanatory, not the headline value.
+Headline metric (BASELINE.json): f32 matmul TFLOP/s.
+  N = 1  Matrix::matmul 8192x8192x8192 (configs[1], "3xTF32 tcgen05"): one step = C = A * B with A, B resident in HBM
+         (`value`) or in pinned host memory through the host-slice C-ABI call (`e2e`).
+  N > 1  Matrix::matmul 32768x32768x32768 sharded by output row blocks over the N ranks (configs[4]; the loop it replaces is
+         the reference's rayon fan-out over 256-row blocks, src/matrix.rs:962-1011): ONE product, strong scaling.  Every rank
+         owns 32768/N rows of A and C (parallel.ShardedMatrix) and a replica of B whose tf32 split is prepared once
+         (parallel.ReplicatedMatrix) outside the timed region; no data-path collective.  `e2e`: the same row block from
+         pinned host memory, H2D of the A rows and D2H of the C rows inside the timed region (B stays resident).
+The reduction half of the BASELINE metric (dot / sum / argmax / norm_l2 GB/s on 2^30 f32 sliced over the ranks, exchange
+fused into the slice kernel over NVLink peer memory), min / max, the sharded matvec, the config-5 row kernels and maps and
+config 3 are measured after the timed region and reported under "secondary" — each with the CPU port timed beside it and
+an end-to-end (host slices) number at N = 1, and with its strong-scaling speed-up over ONE GPU (measured on rank 0 in the
+same run) at N > 1.  Every sharded result is checked against f64 / closed-form truths outside the timed regions
+("parity"); a failed check makes the run exit non-zero.
 
---impl reference times the CPU restatement of trueno's own AVX2 path (oracle/, all host threads,
-the `parallel`-feature partitioning) on the same workload — the reference itself is Rust and
-cannot be built in this image (no cargo), see DESIGN.md.
+--impl reference times the CPU restatement of trueno's own AVX2 path (oracle/, all host threads, the `parallel`-feature
+partitioning) on the same workload and config — the reference itself is Rust and cannot be built in this image (no
+cargo), see DESIGN.md.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -32,12 +39,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-M = K = N = 8192
-FLOP_PER_STEP = 2.0 * M * K * N
-WORKLOAD = "Matrix::matmul 8192x8192x8192 f32 (BASELINE.json configs[1])"
-
+M = K = N = 8192                      # configs[1]
+BIG = 32768                           # configs[4]: 32768^3, row-block sharded
+SEED_A, SEED_B = 0x5EED0001, 0x5EED0002
+GENERATOR = "u01(splitmix64(seed ^ idx)), seeds 0x5EED0001/2"
 
 line_holder: list[str] = []   # the JSON line, emitted by main() once fd 1 points at the real stdout again
+
+
+def workload_config(world: int) -> tuple[str, dict]:
+    """metric + config of the run: identical for both arms (the driver compares them)."""
+    if world == 1:
+        return "f32 matmul TFLOP/s (8192^2)", {
+            "workload": "Matrix::matmul 8192x8192x8192 f32 (BASELINE.json configs[1])",
+            "engine": "tcgen05 cta_group::2 3xTF32, two-level accumulation", "sharding": "single GPU",
+            "l2": "inputs (2 x 256 MiB + 1 GiB split scratch) exceed the 126 MB L2", "generator": GENERATOR}
+    return "f32 matmul TFLOP/s (32768^2, row-block sharded)", {
+        "workload": f"Matrix::matmul 32768x32768x32768 f32 sharded by C row blocks over {world} GPUs (BASELINE.json configs[4])",
+        "engine": "tcgen05 cta_group::2 3xTF32, two-level accumulation",
+        "sharding": f"{BIG // world} rows of A and C per GPU (whole 256-row blocks, src/matrix.rs:962-1011), B replicated and "
+                    f"pre-split once outside the timed region, no collective",
+        "l2": "per-GPU operands (>= 4.5 GiB) exceed the 126 MB L2", "generator": GENERATOR}
 
 
 def load_peaks() -> dict:
@@ -47,14 +69,32 @@ def load_peaks() -> dict:
         return {}
 
 
-def splitmix_u01_torch(torch, seed: int, n: int, device):
-    """x = u01(splitmix64(seed ^ idx)) — same generator as tests/kats.py, on device."""
-    idx = torch.arange(n, dtype=torch.int64, device=device)
-    z = (idx ^ seed) + (-7046029254386353131)            # 0x9E3779B97F4A7C15 as int64
-    z = (z ^ (z >> 30 & 0x3FFFFFFFF)) * (-4658895280553007687)   # 0xBF58476D1CE4E5B9
-    z = (z ^ (z >> 27 & 0x1FFFFFFFFF)) * (-7723592293110705685)  # 0x94D049BB133111EB
-    z = z ^ (z >> 31 & 0x1FFFFFFFF)
-    return ((z >> 40) & 0xFFFFFF).to(torch.float32) * (1.0 / (1 << 24))
+def splitmix_u01_torch(torch, seed: int, n: int, device, start: int = 0, out=None, chunk: int = 1 << 26):
+    """x[i] = u01(splitmix64(seed ^ (start + i))) — same generator as tests/kats.py, on device, generated
+    in chunks so the int64 temporaries stay small; any slice of the global array can be regenerated on any rank."""
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=device)
+    for c0 in range(0, n, chunk):
+        cnt = min(chunk, n - c0)
+        idx = torch.arange(start + c0, start + c0 + cnt, dtype=torch.int64, device=device)
+        z = (idx ^ seed) + (-7046029254386353131)            # 0x9E3779B97F4A7C15 as int64
+        z = (z ^ (z >> 30 & 0x3FFFFFFFF)) * (-4658895280553007687)   # 0xBF58476D1CE4E5B9
+        z = (z ^ (z >> 27 & 0x1FFFFFFFFF)) * (-7723592293110705685)  # 0x94D049BB133111EB
+        z = z ^ (z >> 31 & 0x1FFFFFFFF)
+        out[c0:c0 + cnt] = ((z >> 40) & 0xFFFFFF).to(torch.float32) * (1.0 / (1 << 24))
+        del idx, z
+    return out
+
+
+def splitmix_u01_numpy(seed: int, n: int, start: int = 0):
+    import numpy as np
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (idx ^ np.uint64(seed)) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(40)) & np.uint64(0xFFFFFF)).astype(np.float32) * np.float32(1.0 / (1 << 24))
 
 
 class ClockSampler:
@@ -83,7 +123,7 @@ class ClockSampler:
     def stop(self, region: tuple[float, float] | None = None, load_window: tuple[float, float] | None = None) -> dict:
         """Summarises the samples that fell inside the timed region; a region shorter than three
         sampling periods falls back to the surrounding window in which the same kernel was running
-        back to back (warm-up + timed + roofline loops) and says so in `window`."""
+        back to back (warm-up + timed loops) and says so in `window`."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +139,7 @@ class ClockSampler:
                 rows, window = inside, "timed region"
             elif load_window:
                 rows = [r for t, r in self.rows if load_window[0] <= t <= load_window[1]] or rows
-                window = "timed region < 3 samples: warm-up + timed + roofline loops (same kernel, back to back)"
+                window = "timed region < 3 samples: warm-up + timed loops (same kernel, back to back)"
         sm, smax, reasons, power = [], [], set(), []
         for r in rows:
             try:
@@ -116,65 +156,65 @@ class ClockSampler:
 
 
 # ==================================================================================================
-# reference arm: the CPU port of trueno's AVX2 matmul path, all host threads
+# CPU legs: the port of trueno's own CPU path (oracle/), timed on the box's host cores
 # ==================================================================================================
-def cpu_matmul_sample(rows: int, threads: int | None = None, reps: int = 1):
-    """Times `rows` output rows of the 8192^3 product with the oracle's blocked AVX2 path
-    (matmul_simd, src/matrix.rs:912-1401, `parallel` feature = 256-row blocks over all threads)."""
+def cpu_matmul(world: int, threads: int, reps: int):
+    """The reference arm's step: N = 1 the FULL 8192^3 product (same generator as our arm); N > 1 a bounded sample of the
+    32768^3 product — every host thread gets one 256-row block (the unit the reference's rayon path schedules,
+    src/matrix.rs:962-1011) against a 4096-column slab of B, all of K.  Returns (TFLOP/s, seconds per step, description)."""
     import numpy as np
     import oracle
     orc = oracle.get()
-    if threads:
-        orc.set_threads(threads)
-    rng = np.random.default_rng(0x5EED0001)
-    A = rng.random((rows, K), dtype=np.float32)
-    B = rng.random((K, N), dtype=np.float32)
-    best = float("inf")
+    orc.set_threads(threads)
+    if world == 1:
+        rows, k, n = M, K, N
+        what = "the full 8192x8192x8192 product per step"
+    else:
+        rows, k, n = 256 * max(1, min(BIG // 256, threads)), BIG, 4096
+        what = f"{rows}x{k}x{n} slab of the 32768^3 product per step (one 256-row block per host thread, 4096 columns of B)"
+    A = splitmix_u01_numpy(SEED_A, rows * k).reshape(rows, k)
+    B = splitmix_u01_numpy(SEED_B, k * n).reshape(k, n)
+    times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        orc.matmul_simd(A, B, rows, K, N, parallel=True)
-        best = min(best, time.perf_counter() - t0)
-    return 2.0 * rows * K * N / best / 1e12, best, orc.num_threads()
+        orc.matmul_simd(A, B, rows, k, n, parallel=True)
+        times.append(time.perf_counter() - t0)
+    return A, B, times, 2.0 * rows * k * n, what, orc.num_threads()
 
 
 def run_reference(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import numpy as np
-    import oracle
-    orc = oracle.get()
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
     cores = os.cpu_count() or 1
-    orc.set_threads(cores)
-    # bounded sample: one 256-row block (the unit the reference's rayon path schedules,
-    # src/matrix.rs:962-1011) per host thread, at most the 32 blocks the full 8192-row product has;
-    # same k and n as the full workload.
-    rows = 256 * max(1, min(32, cores))
-    rng = np.random.default_rng(0x5EED0001)
-    A = rng.random((rows, K), dtype=np.float32)
-    B = rng.random((K, N), dtype=np.float32)
-    times = []
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        orc.matmul_simd(A, B, rows, K, N, parallel=True)
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
+    metric, config = workload_config(world)
+    _, _, times, flop, what, nthreads = cpu_matmul(world, cores, args.warmup + args.steps)
+    times = times[args.warmup:]
     per_step = sum(times) / len(times)
-    value = 2.0 * rows * K * N / per_step / 1e12
+    value = flop / per_step / 1e12
     line = {
-        "impl": "reference", "metric": "f32 matmul TFLOP/s (8192^2)", "value": value, "unit": "TFLOP/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{rows} of 8192 output rows per step", "timing": "host clock"},
-        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": min(cores, orc.num_threads()), "kind": "port",
-                         "sample": f"{rows}x{K}x{N} slice of the 8192^3 product per step, oracle matmul_simd "
-                                   f"(AVX2 4x1 microkernel, 256-row blocks over OpenMP threads)"},
+        "impl": "reference", "metric": metric, "value": value, "unit": "TFLOP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": min(cores, nthreads), "kind": "port",
+                         "sample": f"{what}; oracle matmul_simd (trueno's AVX2 4x1 microkernel, `parallel`-feature 256-row "
+                                   f"blocks over OpenMP threads), host clock"},
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     line_holder.append(json.dumps(line))
     return 0
+
+
+def best_of(fn, reps: int) -> float:
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
 
 
 # ==================================================================================================
@@ -203,6 +243,9 @@ def run_ours(args) -> int:
     bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
     bf16_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured" if peaks else "fallback"
+    warmup = max(args.warmup, 3)
+    metric, config = workload_config(world)
+    cores = os.cpu_count() or 1
 
     def barrier():
         if world > 1:
@@ -216,20 +259,36 @@ def run_ours(args) -> int:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- inputs: this rank's 8192-row block of A, the replica of B; U[0,1) from the counter generator
-    a = splitmix_u01_torch(torch, 0x5EED0001 + 7919 * rank, M * K, dev).view(M, K)   # distinct row block per rank
-    b = splitmix_u01_torch(torch, 0x5EED0002, K * N, dev).view(K, N)
-    c = torch.empty(M, N, dtype=torch.float32, device=dev)
+    # ---------------------------------------------------------------------------------------------------------------
+    # headline
+    # ---------------------------------------------------------------------------------------------------------------
+    if world == 1:
+        rows_local, kk, nn, row0 = M, K, N, 0
+    else:
+        rsh = par.ShardedMatrix.row_shard(BIG, rank, world)
+        rows_local, kk, nn, row0 = rsh.count, BIG, BIG, rsh.start
+    flop_total = 2.0 * (M if world == 1 else BIG) * kk * nn
+    a = splitmix_u01_torch(torch, SEED_A, rows_local * kk, dev, start=row0 * kk)     # this rank's rows of the global A
+    b = splitmix_u01_torch(torch, SEED_B, kk * nn, dev)                              # every rank regenerates B in place
+    c = torch.empty(rows_local * nn, dtype=torch.float32, device=dev)
+    if world == 1:
+        bmat = None
 
-    def step_dev():
-        trn.check(L.trn_matmul_f32_dev(a.data_ptr(), M, K, b.data_ptr(), K, N, c.data_ptr(), st))
+        def step_dev():
+            trn.check(L.trn_matmul_f32_dev(a.data_ptr(), M, K, b.data_ptr(), K, N, c.data_ptr(), st))
+    else:
+        amat = par.ShardedMatrix(a, rsh, kk)
+        bmat = par.ReplicatedMatrix(b, kk, nn).prepare()     # tf32 split of B: once, outside the timed region
+
+        def step_dev():
+            amat.matmul(bmat, out=c)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.5)   # nvidia-smi start-up
     t_load0 = time.time()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step_dev()
     barrier()
 
@@ -252,172 +311,565 @@ def run_ours(args) -> int:
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = trn.launch_count() - launches0
     ms_per_step = elapsed_ms / args.steps
-    value = FLOP_PER_STEP * world / (ms_per_step * 1e-3) / 1e12
+    value = flop_total / (ms_per_step * 1e-3) / 1e12
 
     # ---- roofline of the dominant kernel: mean duration over the (last <= 64) steps of the timed region
     p_ms, k_ms = C.c_float(), C.c_float()
     trn.check(L.trn_profile_last_gemm(C.byref(p_ms), C.byref(k_ms)))
-    kern_ms, pre_ms = [k_ms.value], [p_ms.value]
     torch.cuda.synchronize()
     clocks = sampler.stop((t_region0, t_region1), (t_load0, time.time())) if rank == 0 else {}
-    kernel_ms = sum(kern_ms) / len(kern_ms)
-    achieved = FLOP_PER_STEP / (kernel_ms * 1e-3) / 1e12
-    tf32x3_peak = bf16_peak / 6.0   # TF32 runs at half the bf16 rate; 3 TF32 MMAs per f32 product
+    kernel_ms = k_ms.value
+    flop_launch = 2.0 * rows_local * kk * nn
+    achieved = flop_launch / (kernel_ms * 1e-3) / 1e12
+    # TF32 runs at half the bf16 rate; 3 TF32 MMAs per f32 product.  A kernel of tens of milliseconds (the row-block
+    # shards) runs under the sustained power cap: the sustained figure is its denominator (B200_PROFILING.md).
+    long_kernel = kernel_ms > 20.0
+    tf32x3_burst, tf32x3_sustained = bf16_peak / 6.0, bf16_sustained / 6.0
+    tf32x3_peak = tf32x3_sustained if long_kernel else tf32x3_burst
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("dram_bytes_per_launch") if world == 1 else None
     except Exception:
         pass
     roofline = {
         "bound": "tensor", "kernel": "gemm_tf32x3_pair_kernel (tcgen05.mma.cta_group::2 kind::tf32, 3xTF32)", "achieved": achieved,
         "peak": tf32x3_peak, "unit": "TFLOP/s", "frac": achieved / tf32x3_peak, "traffic": traffic,
-        "peak_note": f"{peak_src} bf16 burst {bf16_peak} TF/s / 2 (TF32 rate) / 3 (3xTF32); sustained figure "
-                     f"{bf16_sustained / 6.0:.1f}",
-        "frac_of_sustained": achieved / (bf16_sustained / 6.0),
-        "kernel_ms": kernel_ms, "prepass_ms": sum(pre_ms) / len(pre_ms),
-        "algorithmic_flop_per_launch": FLOP_PER_STEP,
+        "traffic_note": "static: one `ncu --set full` capture of this kernel at 8192^3 (profiles/gemm_traffic.json), not measured in this run",
+        "peak_note": f"{peak_src} bf16 {'sustained' if long_kernel else 'burst'} {bf16_sustained if long_kernel else bf16_peak} TF/s / 2 (TF32 rate) / 3 "
+                     f"(3xTF32); burst figure {tf32x3_burst:.1f}, sustained {tf32x3_sustained:.1f}",
+        "frac_of_sustained": achieved / tf32x3_sustained,
+        "kernel_ms": kernel_ms, "prepass_ms": p_ms.value,
+        "algorithmic_flop_per_launch": flop_launch,
     }
 
-    # ---- e2e: the host-slice C-ABI call with pinned HOST buffers; H2D of A and B and D2H of C inside
-    e2e = None
-    if True:
-        ha, hb, hc = trn.pinned_empty(M * K), trn.pinned_empty(K * N), trn.pinned_empty(M * N)
-        ha[:] = a.view(-1).cpu().numpy()
-        hb[:] = b.view(-1).cpu().numpy()
-        e2e_steps = max(2, min(args.steps, 5))
+    # ---- headline parity (outside the timed region): sampled rows of this rank's C block against the f64 product
+    parity = {"checked": 0, "failed": 0, "failures": []}
+
+    def check(name: str, ok: bool, detail: str = ""):
+        parity["checked"] += 1
+        if not ok:
+            parity["failed"] += 1
+            parity["failures"].append(f"rank {rank}: {name} {detail}"[:160])
+
+    def check_matmul_rows(name, a2, b2, c2, rows, k_, n_, sample_rows, col_slabs):
+        for c0 in col_slabs:
+            bs = b2.view(k_, n_)[:, c0:c0 + 2048].double()
+            ar = a2.view(rows, k_)[sample_rows].double()
+            truth, scale = ar @ bs, ar.abs() @ bs.abs()
+            err = ((c2.view(rows, n_)[sample_rows][:, c0:c0 + 2048].double() - truth).abs() / scale).max().item()
+            check(f"{name} rows {sample_rows} cols {c0}..", err <= 1e-5, f"err/(sum|a||b|) = {err:.2e}")
+            del bs, ar, truth, scale
+
+    check_matmul_rows("matmul", a, b, c, rows_local, kk, nn, [0, rows_local // 2 + 1, rows_local - 1], [0, nn - 2048])
+
+    # ---- e2e: the host-slice C-ABI call with pinned HOST buffers; copies inside the timed region
+    e2e_steps = max(2, min(args.steps, 5 if world == 1 else 3))
+    ha, hc = trn.pinned_empty(rows_local * kk), trn.pinned_empty(rows_local * nn)
+    ha[:] = a.cpu().numpy()
+    if world == 1:
+        hb = trn.pinned_empty(K * N)
+        hb[:] = b.cpu().numpy()
 
         def step_host():
             trn.check(L.trn_matmul_f32(ha.ctypes.data, M, K, hb.ctypes.data, K, N, hc.ctypes.data))
-
+        api = "trn_matmul_f32 (host slices, pinned; A and B up, C down every step)"
+        h2d = 4 * (M * K + K * N)
+    else:
+        def step_host():
+            trn.check(L.trn_matmul_prepared_f32(ha.ctypes.data, rows_local, kk, bmat._handle, hc.ctypes.data))
+        api = ("trn_matmul_prepared_f32 (this rank's A rows up and C rows down every step from pinned host slices; B is the "
+               "resident pre-split replica)")
+        h2d = 4 * rows_local * kk
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
         step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_host()
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        if world > 1:
-            dist.barrier()
-        e2e = {"value": FLOP_PER_STEP * world * e2e_steps / dt / 1e12, "unit": "TFLOP/s",
-               "h2d_bytes_per_step": 4 * (M * K + K * N), "d2h_bytes_per_step": 4 * M * N,
-               "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
-               "api": "trn_matmul_f32 (host slices, pinned)", "checksum": float(hc[:1024].sum())}
-        del ha, hb, hc
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    check("e2e result == resident result (bit-identical)", bool(np.array_equal(np.asarray(hc[:nn]), c[:nn].cpu().numpy())))
+    e2e = {"value": flop_total * e2e_steps / dt / 1e12, "unit": "TFLOP/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * rows_local * nn,
+           "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "api": api, "checksum": float(hc[:1024].sum())}
+    del ha, hc
+    if world == 1:
+        del hb
 
-    # ---- secondary: reductions on 2^30 f32 sliced over the ranks (+ all-reduce), config-5 row kernels
-    secondary = []
-    del a, b, c
+    # ---------------------------------------------------------------------------------------------------------------
+    # secondaries.  Timing: `iters` calls captured once into a CUDA graph (parallel.CapturedLoop) and replayed between two
+    # events — at 8 GPUs a sharded map runs for ~20 us, less than the host needs to issue the next call; lines whose
+    # exchange is an NCCL call are timed as a plain loop.  Device time, max over ranks.
+    # ---------------------------------------------------------------------------------------------------------------
+    secondary: list[dict] = []
+    single: dict[str, float] = {}      # N > 1: the same op at FULL size on ONE GPU (rank 0, same run), ms
+    del c
     torch.cuda.empty_cache()
 
-    def timed(fn, iters=20):
-        for _ in range(3):
-            fn()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        for _ in range(iters):
-            fn()
-        s1.record(stream)
-        barrier()
-        return max_over_ranks(s0.elapsed_time(s1)) / iters
+    def timed(fn, iters=20, graph=True, sync_ranks=True):
+        if graph:
+            loop = par.CapturedLoop(fn, iters)
+            run = loop.replay
+        else:
+            def run():
+                for _ in range(iters):
+                    fn()
+        run()
+        if sync_ranks:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(2):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            run()
+            s1.record(stream)
+            if sync_ranks:
+                barrier()
+                best = min(best, max_over_ranks(s0.elapsed_time(s1)) / iters)
+            else:
+                torch.cuda.synchronize()
+                best = min(best, s0.elapsed_time(s1) / iters)
+        return best
 
+    def add_line(key, metric_name, ms, work, unit_scale, bound, extra=None):
+        """work / ms -> value in GB/s (unit_scale 1e6) or TFLOP/s (1e9); roofline against N x the single-GPU peak."""
+        val = work / ms / unit_scale
+        peak = (hbm_peak if bound == "hbm" else tf32x3_burst) * world
+        e = {"key": key, "metric": metric_name, "value": val, "ms": ms, "roofline_frac": val / peak, "bound": bound}
+        if bound == "hbm":
+            e["roofline_frac_nominal_8TBs"] = val / (8000.0 * world)
+        if extra:
+            e.update(extra)
+        secondary.append(e)
+        return e
+
+    # ---- config 4: reductions on 2^30 f32 sliced over the ranks -------------------------------------------------------
     n_total = 1 << 30
     sh = par.shard_range(n_total, rank, world, align=4)
-    x = (splitmix_u01_torch(torch, 0x5EED0005 + rank, sh.count, dev) * 2 - 1)
-    y = (splitmix_u01_torch(torch, 0x5EED0006 + rank, sh.count, dev) * 2 - 1)
-    # N > 1: the exchange step runs INSIDE the slice kernel over NVLink peer memory (csrc/peer.cu); the
-    # kernel + NCCL variant is timed beside it for comparison
+    x = splitmix_u01_torch(torch, 0x5EED0005, sh.count, dev, start=sh.start).mul_(2).sub_(1)
+    y = splitmix_u01_torch(torch, 0x5EED0006, sh.count, dev, start=sh.start).mul_(2).sub_(1)
+    # planted extrema (closed-form argmax / argmin): the maximum sits in the MIDDLE rank's slice and again, equal, at a
+    # higher index in the LAST rank's slice — the lowest global index must win across ranks; likewise the minimum
+    mid, last = par.shard_range(n_total, world // 2, world, 4), par.shard_range(n_total, world - 1, world, 4)
+    i_max, i_max2 = mid.start + 12345, last.start + last.count - 7
+    i_min, i_min2 = mid.start + 54321, last.start + last.count - 77
+    for gi, val in ((i_max, 2.0), (i_max2, 2.0), (i_min, -3.0), (i_min2, -3.0)):
+        if sh.start <= gi < sh.start + sh.count:
+            x[gi - sh.start] = val
     comm = par.PeerComm() if world > 1 else None
-    variants = [("", comm)] + ([(" [kernel + NCCL exchange]", None)] if world > 1 else [])
-    for suffix, cm in variants:
-        vx, vy = par.ShardedVector(x, sh, cm), par.ShardedVector(y, sh, cm)
-        for name, fn, nbytes in (("dot", lambda: vx.dot(vy), 8 * n_total), ("sum", lambda: vx.sum(), 4 * n_total),
-                                 ("argmax", lambda: vx.argmax(), 4 * n_total), ("norm_l2", lambda: vx.norm_l2(), 4 * n_total)):
-            ms = timed(fn)
-            gbs = nbytes / ms / 1e6
-            secondary.append({"metric": f"{name} 2^30 f32 GB/s{suffix}", "value": gbs, "ms": ms,
-                              "roofline_frac": gbs / (hbm_peak * world), "bound": "hbm",
-                              "exchange": "none (1 GPU)" if world == 1 else ("fused P2P over NVLink" if cm else "NCCL")})
-    del x, y, vx, vy
-    if comm is not None:
-        torch.cuda.synchronize()
+    vx, vy = par.ShardedVector(x, sh, comm), par.ShardedVector(y, sh, comm)
+    exchange = "none (1 GPU)" if world == 1 else "fused into the slice kernel: P2P stores over NVLink peer memory"
+    red_ops = (("dot", lambda: vx.dot(vy), 8), ("sum", lambda: vx.sum(), 4), ("argmax", lambda: vx.argmax(), 4),
+               ("norm_l2", lambda: vx.norm_l2(), 4), ("max", lambda: vx.max(), 4), ("min", lambda: vx.min(), 4))
+    for name, fn, bpe in red_ops:
+        ms = timed(fn)
+        add_line(name, f"{name} 2^30 f32 GB/s", ms, bpe * n_total, 1e6, "hbm", {"exchange": exchange})
+    if world > 1:   # the kernel + NCCL collective variant, for comparison
+        nx, ny = par.ShardedVector(x, sh, None), par.ShardedVector(y, sh, None)
+        for name, fn, bpe in (("sum", lambda: nx.sum(), 4), ("argmax", lambda: nx.argmax(), 4)):
+            ms = timed(fn, graph=False)
+            add_line(name + "_nccl", f"{name} 2^30 f32 GB/s [slice kernel + NCCL exchange]", ms, bpe * n_total, 1e6, "hbm",
+                     {"exchange": "NCCL"})
+    # parity: f64 truths of the slices, summed over the ranks in f64
+    def f64_parts(t, fn, chunk=1 << 26):
+        tot = torch.zeros((), dtype=torch.float64, device=dev)
+        for i in range(0, t.numel(), chunk):
+            tot += fn(i, i + chunk)
+        return tot
+    truths = torch.stack([
+        f64_parts(x, lambda i, j: x[i:j].double().sum()), f64_parts(x, lambda i, j: x[i:j].double().abs().sum()),
+        f64_parts(x, lambda i, j: (x[i:j].double() * y[i:j].double()).sum()),
+        f64_parts(x, lambda i, j: (x[i:j].double() * y[i:j].double()).abs().sum()),
+        f64_parts(x, lambda i, j: (x[i:j].double() ** 2).sum())])
+    if world > 1:
+        dist.all_reduce(truths)
+    tsum, asum, tdot, adot, tsq = [float(v) for v in truths]
+    got = {name: fn().clone() for name, fn, _ in red_ops}
+    torch.cuda.synchronize()
+    check("sum vs f64", abs(float(got["sum"]) - tsum) <= 1e-5 * asum, f"{float(got['sum'])} vs {tsum}")
+    check("dot vs f64", abs(float(got["dot"]) - tdot) <= 1e-5 * adot, f"{float(got['dot'])} vs {tdot}")
+    check("norm_l2 vs f64", abs(float(got["norm_l2"]) - math.sqrt(tsq)) <= 1e-5 * math.sqrt(tsq))
+    check("argmax: planted cross-rank tie -> lowest global index", int(got["argmax"]) == i_max, f"{int(got['argmax'])} vs {i_max}")
+    check("max == planted", float(got["max"]) == 2.0)
+    check("min == planted", float(got["min"]) == -3.0)
+    check("argmin: planted cross-rank tie -> lowest global index", int(vx.argmin()) == i_min)
+    if world > 1:
+        gath = [torch.empty(1, device=dev) for _ in range(world)]
+        dist.all_gather(gath, got["dot"].reshape(1))
+        check("fused exchange: bit-identical result on every rank", all(torch.equal(gath[0], g) for g in gath))
+        trn.check(L.trn_comm_status(comm.handle))
+    if world > 1 and rank == 0:   # single-GPU leg of the strong-scaling figures: the WHOLE vector on one GPU
+        fx = splitmix_u01_torch(torch, 0x5EED0005, n_total, dev).mul_(2).sub_(1)
+        fy = splitmix_u01_torch(torch, 0x5EED0006, n_total, dev).mul_(2).sub_(1)
+        # world_size() > 1 here, so the single-GPU kernels are called directly
+        f1, i1 = torch.zeros(1, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
+        for name, fn in (("dot", lambda: trn.check(L.trn_dot_f32_dev(fx.data_ptr(), n_total, fy.data_ptr(), n_total, f1.data_ptr(), st))),
+                         ("sum", lambda: trn.check(L.trn_sum_f32_dev(fx.data_ptr(), n_total, f1.data_ptr(), st))),
+                         ("argmax", lambda: trn.check(L.trn_argmax_f32_dev(fx.data_ptr(), n_total, i1.data_ptr(), f1.data_ptr(), st))),
+                         ("norm_l2", lambda: trn.check(L.trn_norm_l2_f32_dev(fx.data_ptr(), n_total, f1.data_ptr(), st))),
+                         ("max", lambda: trn.check(L.trn_max_f32_dev(fx.data_ptr(), n_total, f1.data_ptr(), st))),
+                         ("min", lambda: trn.check(L.trn_min_f32_dev(fx.data_ptr(), n_total, f1.data_ptr(), st)))):
+            single[name] = timed(fn, sync_ranks=False)
+        del fx, fy
+    if world > 1:
         dist.barrier()
-    rows_total, cols = 4096, 32000
-    rsh = par.shard_range(rows_total, rank, world)
-    logits = torch.randn(rsh.count, cols, device=dev) * 4
-    out = torch.empty_like(logits)
-    for name, fn in (("softmax", L.trn_softmax_rows_f32_dev), ("log_softmax", L.trn_log_softmax_rows_f32_dev)):
-        ms = timed(lambda: trn.check(fn(logits.data_ptr(), out.data_ptr(), rsh.count, cols, st)))
-        gbs = 8.0 * rows_total * cols / ms / 1e6
-        secondary.append({"metric": f"{name} 4096x32000 f32 GB/s", "value": gbs, "ms": ms,
-                          "roofline_frac": gbs / (hbm_peak * world), "bound": "hbm"})
-    ms = timed(lambda: trn.check(L.trn_gelu_f32_dev(logits.data_ptr(), logits.numel(), out.data_ptr(), st)))
-    gbs = 8.0 * rows_total * cols / ms / 1e6
-    secondary.append({"metric": "gelu 4096x32000 f32 GB/s", "value": gbs, "ms": ms,
-                      "roofline_frac": gbs / (hbm_peak * world), "bound": "hbm"})
-    del logits, out
+    cpu_lines: dict[str, dict] = {}
+    e2e_lines: dict[str, dict] = {}
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        import oracle
+        orc = oracle.get()
+        orc.set_threads(1)
+        ns = 1 << 27   # bounded CPU sample: 2^27 of the 2^30 elements (0.5 GiB per operand)
+        cx, cy = x[:ns].cpu().numpy(), y[:ns].cpu().numpy()
+        for name, fn, bpe in (("dot", lambda: orc.dot(cx, cy, backend=oracle.AVX2), 8), ("sum", lambda: orc.sum(cx, backend=oracle.AVX2), 4),
+                              ("argmax", lambda: orc.argmax(cx, backend=oracle.AVX2), 4), ("norm_l2", lambda: orc.norm_l2(cx, backend=oracle.AVX2), 4),
+                              ("max", lambda: orc.max(cx, backend=oracle.AVX2), 4), ("min", lambda: orc.min(cx, backend=oracle.AVX2), 4)):
+            secs = best_of(fn, 3)
+            cpu_lines[name] = {"value": bpe * ns / secs / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                               "sample": f"first 2^27 of the 2^30 elements, oracle Avx2Backend::{name} (single thread: the reference "
+                                         f"has no rayon path for reductions, src/vector.rs:588-827), best of 3, {secs * 1e3:.1f} ms"}
+        del cx, cy
+        # e2e: the host-slice calls on the full 2^30-element vectors from pinned host memory (H2D inside the timed region)
+        hx, hy = trn.pinned_empty(n_total), trn.pinned_empty(n_total)
+        hx[:] = x.cpu().numpy()
+        hy[:] = y.cpu().numpy()
+        of, oi = C.c_float(), C.c_uint64()
+        for name, fn, bpe in (("dot", lambda: trn.check(L.trn_dot_f32(hx.ctypes.data, n_total, hy.ctypes.data, n_total, C.byref(of))), 8),
+                              ("sum", lambda: trn.check(L.trn_sum_f32(hx.ctypes.data, n_total, C.byref(of))), 4),
+                              ("argmax", lambda: trn.check(L.trn_argmax_f32(hx.ctypes.data, n_total, C.byref(oi))), 4),
+                              ("norm_l2", lambda: trn.check(L.trn_norm_l2_f32(hx.ctypes.data, n_total, C.byref(of))), 4),
+                              ("max", lambda: trn.check(L.trn_max_f32(hx.ctypes.data, n_total, C.byref(of))), 4),
+                              ("min", lambda: trn.check(L.trn_min_f32(hx.ctypes.data, n_total, C.byref(of))), 4)):
+            fn()
+            secs = best_of(fn, 2)
+            e2e_lines[name] = {"value": bpe * n_total / secs / 1e9, "unit": "GB/s", "h2d_bytes_per_step": bpe * n_total,
+                               "d2h_bytes_per_step": 8 if name == "argmax" else 4, "ms": secs * 1e3,
+                               "api": f"trn_{name}_f32 (host slice, pinned)"}
+        del hx, hy
+    del x, y, vx, vy
+    torch.cuda.empty_cache()
 
-    # ---- secondary: BASELINE config 3 (Q K^T, batch 8 x heads 32, seq 2048, head_dim 128, heads sharded over the
-    # ranks, no collective) and the same heads through the fused attention kernel (scores never leave the SM)
+    # ---- sharded matvec (section 8e last row): A 32768 x 32768 by row blocks, v replicated -----------------------------------
+    mv_rows = mv_cols = BIG
+    mvs = par.ShardedMatrix.row_shard(mv_rows, rank, world)
+    if world == 1:
+        amv = splitmix_u01_torch(torch, SEED_A, mvs.count * mv_cols, dev, start=mvs.start * mv_cols)
+    else:
+        amv = a    # the headline's row block of A is exactly this shard
+    vvec = splitmix_u01_torch(torch, 0x5EED0008, mv_cols, dev).mul_(2).sub_(1)
+    amat_mv = par.ShardedMatrix(amv, mvs, mv_cols)
+    yv = torch.empty(mvs.count, device=dev)
+    ms = timed(lambda: amat_mv.matvec(vvec, out=yv))
+    add_line("matvec", "matvec 32768x32768 f32 GB/s", ms, 4.0 * mv_rows * mv_cols, 1e6, "hbm",
+             {"sharding": "row blocks of A, v replicated, y sharded like the rows; no collective"})
+    rs_ = [0, mvs.count // 3, mvs.count - 1]
+    tr = amv.view(mvs.count, mv_cols)[rs_].double() @ vvec.double()
+    sc = amv.view(mvs.count, mv_cols)[rs_].double().abs() @ vvec.double().abs()
+    check("matvec rows vs f64", bool((((yv[rs_].double() - tr).abs()) <= 1e-5 * sc).all()))
+    if world > 1 and rank == 0:
+        afull = splitmix_u01_torch(torch, SEED_A, BIG * BIG, dev)
+        yfull = torch.empty(BIG, device=dev)
+        single["matvec"] = timed(lambda: trn.check(L.trn_matvec_f32_dev(afull.data_ptr(), BIG, BIG, vvec.data_ptr(), BIG, yfull.data_ptr(), st)),
+                                 sync_ranks=False)
+        # and the single-GPU leg of the headline: the whole 32768^3 product on one GPU, B prepared as on every rank
+        cfull = torch.empty(BIG * BIG, device=dev)
+        fullm = par.ShardedMatrix(afull, par.shard_range(BIG, 0, 1, 256), BIG)
+        single["matmul"] = timed(lambda: fullm.matmul(bmat, out=cfull), iters=2, graph=False, sync_ranks=False)
+        del afull, yfull, cfull, fullm
+    if world > 1:
+        dist.barrier()
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        rows_s = 2048
+        ca, cv = amv[:rows_s * mv_cols].cpu().numpy(), vvec.cpu().numpy()
+        orc.set_threads(cores)
+        secs = best_of(lambda: orc.matvec(ca, rows_s, mv_cols, cv, parallel=True), 3)
+        orc.set_threads(1)
+        secs1 = best_of(lambda: orc.matvec(ca, rows_s, mv_cols, cv, parallel=False), 2)
+        cpu_lines["matvec"] = {"value": 4.0 * rows_s * mv_cols / secs / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                               "single_thread_value": 4.0 * rows_s * mv_cols / secs1 / 1e9,
+                               "sample": f"first {rows_s} of the 32768 rows, oracle matvec (one Avx2Backend::dot per row; rayon over rows at "
+                                         f">= 4096 rows, src/matrix.rs:1676-1716 -> OpenMP, {cores} threads), best of 3"}
+        del ca, cv
+    del amv, amat_mv, yv, a
+    if bmat is not None:
+        bmat.close()
+    del b, bmat
+    torch.cuda.empty_cache()
+
+    # ---- config 5: row kernels and maps over 4096 x 32000 logits, rows sharded -------------------------------------------
+    rows_total, cols = 4096, 32000
+    rsh5 = par.shard_range(rows_total, rank, world)
+    def make_logits(r0, cnt):
+        # N(0,1) * 4, reproducible per global row range: one generator state per call, offset by the first row
+        gg = torch.Generator(device=dev)
+        gg.manual_seed(0x5EED0007 + r0)
+        return torch.randn(cnt, cols, device=dev, generator=gg) * 4
+    logits = make_logits(rsh5.start, rsh5.count)
+    logits2 = make_logits(rsh5.start + 100003, rsh5.count)
+    out = torch.empty_like(logits)
+    n5 = logits.numel()
+    ops5 = (("softmax", lambda: trn.check(L.trn_softmax_rows_f32_dev(logits.data_ptr(), out.data_ptr(), rsh5.count, cols, st)), 8.0),
+            ("log_softmax", lambda: trn.check(L.trn_log_softmax_rows_f32_dev(logits.data_ptr(), out.data_ptr(), rsh5.count, cols, st)), 8.0),
+            ("gelu", lambda: trn.check(L.trn_gelu_f32_dev(logits.data_ptr(), n5, out.data_ptr(), st)), 8.0),
+            ("sigmoid", lambda: trn.check(L.trn_sigmoid_f32_dev(logits.data_ptr(), n5, out.data_ptr(), st)), 8.0),
+            ("add", lambda: trn.check(L.trn_add_f32_dev(logits.data_ptr(), n5, logits2.data_ptr(), n5, out.data_ptr(), st)), 12.0))
+    for name, fn, bpe in ops5:
+        ms = timed(fn)
+        add_line(name, f"{name} 4096x32000 f32 GB/s", ms, bpe * rows_total * cols, 1e6, "hbm",
+                 {"sharding": "rows / contiguous slices over the ranks, no collective"})
+        # parity on sampled rows of this rank's block
+        fn()
+        torch.cuda.synchronize()
+        rr = [0, rsh5.count // 2, rsh5.count - 1]
+        xs = logits[rr].double()
+        o = out[rr].double()
+        if name == "softmax":
+            check("softmax rows sum to 1", bool(((out.double().sum(dim=1) - 1).abs() <= 1e-5).all()))
+            check("softmax vs f64", bool(((o - torch.softmax(xs, dim=1)).abs() <= 1e-6).all()))
+        elif name == "log_softmax":
+            check("log_softmax vs f64", bool(((o - torch.log_softmax(xs, dim=1)).abs() <= 4e-6 * (1 + o.abs())).all()))
+        elif name == "gelu":
+            want = 0.5 * xs * (1 + torch.tanh(0.7978846 * (xs + 0.044715 * xs ** 3)))
+            check("gelu vs f64", bool(((o - want).abs() <= 2e-6 * (1 + xs.abs())).all()))
+        elif name == "sigmoid":
+            check("sigmoid vs f64", bool(((o - torch.sigmoid(xs)).abs() <= 1e-6).all()))
+        else:
+            check("add bit-exact", bool(torch.equal(out[rr], logits[rr] + logits2[rr])))
+    if world > 1 and rank == 0:
+        fl, fl2 = make_logits(0, rows_total), make_logits(100003, rows_total)
+        fo = torch.empty_like(fl)
+        nf = fl.numel()
+        for name, fn in (("softmax", lambda: trn.check(L.trn_softmax_rows_f32_dev(fl.data_ptr(), fo.data_ptr(), rows_total, cols, st))),
+                         ("log_softmax", lambda: trn.check(L.trn_log_softmax_rows_f32_dev(fl.data_ptr(), fo.data_ptr(), rows_total, cols, st))),
+                         ("gelu", lambda: trn.check(L.trn_gelu_f32_dev(fl.data_ptr(), nf, fo.data_ptr(), st))),
+                         ("sigmoid", lambda: trn.check(L.trn_sigmoid_f32_dev(fl.data_ptr(), nf, fo.data_ptr(), st))),
+                         ("add", lambda: trn.check(L.trn_add_f32_dev(fl.data_ptr(), nf, fl2.data_ptr(), nf, fo.data_ptr(), st)))):
+            single[name] = timed(fn, sync_ranks=False)
+        del fl, fl2, fo
+    if world > 1:
+        dist.barrier()
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        rows_s = 256
+        cl, cl2 = logits[:rows_s].cpu().numpy().reshape(-1), logits2[:rows_s].cpu().numpy().reshape(-1)
+        orc.set_threads(1)
+        for name, fn, bpe in (("softmax", lambda: orc.softmax_rows(cl, rows_s, cols, backend=oracle.AVX2), 8.0),
+                              ("log_softmax", lambda: orc.softmax_rows(cl, rows_s, cols, log=True, backend=oracle.AVX2), 8.0),
+                              ("gelu", lambda: orc.gelu(cl, backend=oracle.AVX2), 8.0),
+                              ("sigmoid", lambda: orc.sigmoid(cl, backend=oracle.AVX2), 8.0)):
+            secs = best_of(fn, 2)
+            cpu_lines[name] = {"value": bpe * rows_s * cols / secs / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                               "sample": f"first {rows_s} of the 4096 rows, oracle restatement of Vector::{name} on the AVX2 backend (one "
+                                         f"Vector per row, single thread: no rayon path, src/vector.rs:1516-2217), best of 2"}
+        orc.set_threads(cores)
+        secs = best_of(lambda: orc.map_parallel("add", cl, cl2), 3)
+        orc.set_threads(1)
+        secs1 = best_of(lambda: orc.add(cl, cl2), 2)
+        cpu_lines["add"] = {"value": 12.0 * rows_s * cols / secs / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                            "single_thread_value": 12.0 * rows_s * cols / secs1 / 1e9,
+                            "sample": f"first {rows_s} rows, oracle Avx2Backend::add with the `parallel`-feature chunks of 65 536 elements "
+                                      f"(src/vector.rs:369-390) over {cores} threads, best of 3"}
+        del cl, cl2
+        hl, ho = trn.pinned_empty(n5), trn.pinned_empty(n5)
+        hl[:] = logits.cpu().numpy().reshape(-1)
+        for name, fn in (("softmax", lambda: trn.check(L.trn_softmax_rows_f32(hl.ctypes.data, ho.ctypes.data, rows_total, cols))),
+                         ("log_softmax", lambda: trn.check(L.trn_log_softmax_rows_f32(hl.ctypes.data, ho.ctypes.data, rows_total, cols))),
+                         ("gelu", lambda: trn.check(L.trn_gelu_f32(hl.ctypes.data, n5, ho.ctypes.data))),
+                         ("sigmoid", lambda: trn.check(L.trn_sigmoid_f32(hl.ctypes.data, n5, ho.ctypes.data))),
+                         ("add", lambda: trn.check(L.trn_add_f32(hl.ctypes.data, n5, hl.ctypes.data, n5, ho.ctypes.data)))):
+            fn()
+            secs = best_of(fn, 3)
+            nin = 2 if name == "add" else 1
+            e2e_lines[name] = {"value": 4.0 * (nin + 1) * n5 / secs / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * nin * n5,
+                               "d2h_bytes_per_step": 4 * n5, "ms": secs * 1e3, "api": f"trn_{name}{'_rows' if 'softmax' in name else ''}_f32 (host slices, pinned)"}
+        del hl, ho
+    del logits, logits2, out
+    torch.cuda.empty_cache()
+
+    # ---- config 3: Q K^T over batch 8 x heads 32 (heads sharded over the ranks), and the same heads through fused attention
     B3, H3, S3, D3 = 8, 32, 2048, 128
     hsh = par.shard_range(B3 * H3, rank, world)
-    q3 = torch.randn(hsh.count * S3 * D3, device=dev)
-    k3 = torch.randn(hsh.count * S3 * D3, device=dev)
-    v3 = torch.randn(hsh.count * S3 * D3, device=dev)
+
+    def make_heads(h0, cnt, salt):
+        gg = torch.Generator(device=dev)
+        gg.manual_seed(0x5EED0003 + 7 * h0 + salt)
+        return torch.randn(cnt * S3 * D3, device=dev, generator=gg)
+    q3, k3, v3 = make_heads(hsh.start, hsh.count, 0), make_heads(hsh.start, hsh.count, 1), make_heads(hsh.start, hsh.count, 2)
     kt3 = k3.view(hsh.count, S3, D3).transpose(1, 2).contiguous().view(-1)
     c3 = torch.empty(hsh.count * S3 * S3, device=dev)
+    flop3 = 2.0 * B3 * H3 * S3 * S3 * D3
     ms = timed(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(q3.data_ptr(), q3.numel(), kt3.data_ptr(), kt3.numel(),
-                                                                 c3.data_ptr(), 1, hsh.count, S3, D3, S3, st)), iters=10)
-    secondary.append({"metric": "batched_matmul_4d Q K^T 8x32x2048x128 TFLOP/s", "value": 2.0 * B3 * H3 * S3 * S3 * D3 / ms / 1e9,
-                      "ms": ms, "roofline_frac": 2.0 * B3 * H3 * S3 * S3 * D3 / ms / 1e9 / (tf32x3_peak * world), "bound": "tensor"})
-    del c3, kt3
+                                                                 c3.data_ptr(), 1, hsh.count, S3, D3, S3, st)), iters=10, graph=False)
+    add_line("batched_qkt", "batched_matmul_4d Q K^T 8x32x2048x128x2048 TFLOP/s", ms, flop3, 1e9, "tensor",
+             {"min_time_bound_ms": {"tensor": flop3 / tf32x3_burst / 1e9 / world, "hbm": 4831838208 / hbm_peak / 1e6 / world},
+              "sharding": "contiguous (batch*head) ranges over the ranks, no collective"})
+    hh = hsh.count - 1
+    check_rows = [0, 1000, S3 - 1]
+    tr = q3.view(hsh.count, S3, D3)[hh][check_rows].double() @ kt3.view(hsh.count, D3, S3)[hh].double()
+    sc = q3.view(hsh.count, S3, D3)[hh][check_rows].double().abs() @ kt3.view(hsh.count, D3, S3)[hh].double().abs()
+    err = ((c3.view(hsh.count, S3, S3)[hh][check_rows].double() - tr).abs() / sc).max().item()
+    check("batched Q K^T head rows vs f64", err <= 1e-5, f"{err:.2e}")
+    del c3
     o3 = torch.empty_like(q3)
+    att_ms = {}
     for causal in (0, 1):
         flop = 4.0 * B3 * H3 * S3 * S3 * D3 * (0.5 if causal else 1.0)
         ms = timed(lambda: trn.check(L.trn_attention_f32_dev(q3.data_ptr(), q3.numel(), k3.data_ptr(), k3.numel(), v3.data_ptr(),
                                                              v3.numel(), o3.data_ptr(), hsh.count, S3, D3, 1.0 / D3 ** 0.5, causal, st)),
-                   iters=10)
-        secondary.append({"metric": f"fused attention 256 heads x 2048 x 128{' causal' if causal else ''} TFLOP/s",
-                          "value": flop / ms / 1e9, "ms": ms, "roofline_frac": flop / ms / 1e9 / (tf32x3_peak * world),
-                          "bound": "tensor"})
-    del q3, k3, v3, o3
+                   iters=10, graph=False)
+        att_ms[causal] = ms
+        add_line("attention_causal" if causal else "attention", f"fused attention 256 heads x 2048 x 128{' causal' if causal else ''} TFLOP/s",
+                 ms, flop, 1e9, "tensor")
+    if world > 1 and rank == 0:
+        fq, fk = make_heads(0, B3 * H3, 0), make_heads(0, B3 * H3, 1)
+        fkt = fk.view(B3 * H3, S3, D3).transpose(1, 2).contiguous().view(-1)
+        fc = torch.empty(B3 * H3 * S3 * S3, device=dev)
+        single["batched_qkt"] = timed(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(fq.data_ptr(), fq.numel(), fkt.data_ptr(), fkt.numel(),
+                                                                                         fc.data_ptr(), B3, H3, S3, D3, S3, st)),
+                                      iters=5, graph=False, sync_ranks=False)
+        del fc, fkt
+        fv, fo = make_heads(0, B3 * H3, 2), torch.empty_like(fq)
+        single["attention"] = timed(lambda: trn.check(L.trn_attention_f32_dev(fq.data_ptr(), fq.numel(), fk.data_ptr(), fk.numel(), fv.data_ptr(),
+                                                                              fv.numel(), fo.data_ptr(), B3 * H3, S3, D3, 1.0 / D3 ** 0.5, 0, st)),
+                                    iters=5, graph=False, sync_ranks=False)
+        del fq, fk, fv, fo
+    if world > 1:
+        dist.barrier()
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        heads_s = max(1, min(8, cores))
+        cq = q3[:heads_s * S3 * D3].cpu().numpy()
+        ckt = kt3[:heads_s * S3 * D3].cpu().numpy()
+        orc.set_threads(1)
+        secs = best_of(lambda: orc.batched_matmul_4d(cq, ckt, 1, heads_s, S3, D3, S3), 1)
+        cpu_lines["batched_qkt"] = {"value": 2.0 * heads_s * S3 * S3 * D3 / secs / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": "port",
+                                    "sample": f"first {heads_s} of the 256 heads, oracle batched_matmul_4d (sequential loop over heads, each a "
+                                              f"single-threaded matmul_simd: k = 128 < 1024 has no rayon path, src/matrix.rs:507-524), {secs:.2f} s"}
+        del cq, ckt
+    del q3, k3, v3, kt3, o3
+    torch.cuda.empty_cache()
 
-    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
+    # ---- config 1 (N = 1 only): the reference's own CPU-runnable case, exactly as its benches generate it -------------------
+    config1 = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        i512 = np.arange(512 * 512)
+        A1 = (i512 % 100).astype(np.float32)                       # benches/matrix_ops.rs:23-25
+        B1 = ((i512 * 2) % 100).astype(np.float32)
+        v1 = (np.arange(1_000_000, dtype=np.float32) * np.float32(0.5))   # benches/vector_ops.rs:28-30, extended to 1M
+        orc.set_threads(1)
+        t_mm = best_of(lambda: orc.matmul(A1, (512, 512), B1, (512, 512)), 5)
+        t_dot = best_of(lambda: orc.dot(v1, v1, backend=oracle.AVX2), 20)
+        t_sum = best_of(lambda: orc.sum(v1, backend=oracle.AVX2), 20)
+        C1 = np.empty(512 * 512, np.float32)
+        of = C.c_float()
+        g_mm = best_of(lambda: trn.check(L.trn_matmul_f32(A1.ctypes.data, 512, 512, B1.ctypes.data, 512, 512, C1.ctypes.data)), 20)
+        g_dot = best_of(lambda: trn.check(L.trn_dot_f32(v1.ctypes.data, v1.size, v1.ctypes.data, v1.size, C.byref(of))), 20)
+        g_sum = best_of(lambda: trn.check(L.trn_sum_f32(v1.ctypes.data, v1.size, C.byref(of))), 20)
+        dA, dB, dC, dv = (torch.from_numpy(A1).to(dev), torch.from_numpy(B1).to(dev), torch.empty(512 * 512, device=dev),
+                          torch.from_numpy(v1).to(dev))
+        d1 = torch.zeros(1, device=dev)
+        r_mm = timed(lambda: trn.check(L.trn_matmul_f32_dev(dA.data_ptr(), 512, 512, dB.data_ptr(), 512, 512, dC.data_ptr(), st)), graph=False)
+        r_dot = timed(lambda: trn.check(L.trn_dot_f32_dev(dv.data_ptr(), dv.numel(), dv.data_ptr(), dv.numel(), d1.data_ptr(), st)))
+        r_sum = timed(lambda: trn.check(L.trn_sum_f32_dev(dv.data_ptr(), dv.numel(), d1.data_ptr(), st)))
+        check("config 1 matmul == f64 product (exact integers)", bool(np.array_equal(
+            C1.reshape(512, 512).astype(np.float64), A1.reshape(512, 512).astype(np.float64) @ B1.reshape(512, 512).astype(np.float64))))
+        mmf, vb = 2.0 * 512 ** 3, 4.0 * v1.size
+        config1 = {
+            "workload": "BASELINE configs[0]: Matrix::matmul 512x512 (A[i]=i%100, B[i]=(2i)%100, benches/matrix_ops.rs:23-25) and "
+                        "Vector dot / sum on 1M f32 (x[i]=0.5i, benches/vector_ops.rs:28-30)",
+            "cpu_port_1_thread": {"matmul_ms": t_mm * 1e3, "matmul_gflops": mmf / t_mm / 1e9, "dot_us": t_dot * 1e6,
+                                  "dot_gbs": 2 * vb / t_dot / 1e9, "sum_us": t_sum * 1e6, "sum_gbs": vb / t_sum / 1e9,
+                                  "note": "oracle port of the AVX2 path, one thread = `cargo bench` default features; best of 5 / 20"},
+            "cuda_host_slices": {"matmul_ms": g_mm * 1e3, "matmul_gflops": mmf / g_mm / 1e9, "dot_us": g_dot * 1e6,
+                                 "dot_gbs": 2 * vb / g_dot / 1e9, "sum_us": g_sum * 1e6, "sum_gbs": vb / g_sum / 1e9,
+                                 "note": "trn_matmul_f32 / trn_dot_f32 / trn_sum_f32 on pageable host slices (what the Rust API passes): "
+                                         "staging + PCIe + launch latency bound at these sizes"},
+            "cuda_resident": {"matmul_us": r_mm * 1e3, "matmul_gflops": mmf / r_mm / 1e6, "dot_us": r_dot * 1e3,
+                              "dot_gbs": 2 * vb / r_dot / 1e6, "sum_us": r_sum * 1e3, "sum_gbs": vb / r_sum / 1e6,
+                              "note": "`_dev` calls on resident operands, back to back (launch-latency bound: 1 MiB / 4 MB operands)"},
+        }
+
+    # ---- CPU baseline of the headline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        rows = 256 * max(1, min(32, cores))
-        tf, secs, nthreads = cpu_matmul_sample(rows, threads=cores, reps=2)
-        tf1, secs1, _ = cpu_matmul_sample(256, threads=1, reps=1)
-        cpu_baseline = {"value": tf, "unit": "TFLOP/s", "cores": min(cores, nthreads), "kind": "port",
-                        "sample": f"{rows} of 8192 output rows of the same 8192^3 product ({secs:.2f} s), oracle "
-                                  f"matmul_simd with the `parallel`-feature partitioning over all host threads",
-                        "single_thread_value": tf1,
+        import oracle
+        orc = oracle.get()
+        rows_s = 256 * max(1, min(32, cores))
+        As = splitmix_u01_numpy(SEED_A, rows_s * K).reshape(rows_s, K)
+        Bs = splitmix_u01_numpy(SEED_B, K * N).reshape(K, N)
+        orc.set_threads(cores)
+        secs = best_of(lambda: orc.matmul_simd(As, Bs, rows_s, K, N, parallel=True), 2)
+        orc.set_threads(1)
+        secs1 = best_of(lambda: orc.matmul_simd(As[:256], Bs, 256, K, N, parallel=False), 1)
+        cpu_baseline = {"value": 2.0 * rows_s * K * N / secs / 1e12, "unit": "TFLOP/s", "cores": min(cores, orc.num_threads() if cores > 1 else 1),
+                        "kind": "port",
+                        "sample": f"{rows_s} of 8192 output rows of the same 8192^3 product ({secs:.2f} s), oracle matmul_simd with the "
+                                  f"`parallel`-feature partitioning over all host threads; `--impl reference` times the full product",
+                        "single_thread_value": 2.0 * 256 * K * N / secs1 / 1e12,
                         "single_thread_sample": f"256 output rows, 1 thread ({secs1:.2f} s) — `cargo bench` default features"}
+        del As, Bs
 
-    # HBM-bound lines are reported against the measured copy bandwidth AND the nominal 8 TB/s
-    for entry in secondary:
-        if entry.get("bound") == "hbm":
-            entry["roofline_frac_nominal_8TBs"] = entry["value"] / (8000.0 * world)
+    for e in secondary:
+        if e["key"] in cpu_lines:
+            e["cpu_baseline"] = cpu_lines[e["key"]]
+        if e["key"] in e2e_lines:
+            e["e2e"] = e2e_lines[e["key"]]
+
+    # ---- strong scaling (N > 1): single-GPU time of the same full-size op (rank 0, this run) / sharded time
+    strong = None
+    if world > 1:
+        sv = torch.zeros(32, dtype=torch.float64, device=dev)
+        keys = ["matmul", "dot", "sum", "argmax", "norm_l2", "max", "min", "matvec", "softmax", "log_softmax", "gelu", "sigmoid", "add",
+                "batched_qkt", "attention"]
+        if rank == 0:
+            for i, kname in enumerate(keys):
+                sv[i] = single.get(kname, 0.0)
+        dist.broadcast(sv, src=0)
+        sharded_ms = {e["key"]: e["ms"] for e in secondary}
+        sharded_ms["matmul"] = ms_per_step
+        strong = {}
+        for i, kname in enumerate(keys):
+            t1 = float(sv[i])
+            if t1 > 0 and kname in sharded_ms:
+                strong[kname] = round(t1 / sharded_ms[kname], 2)
+                for e in secondary:
+                    if e["key"] == kname:
+                        e["ms_one_gpu"] = t1
+
+    # parity over all ranks
+    pv = torch.tensor([parity["checked"], parity["failed"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(pv)
+        fails = [None] * world
+        dist.all_gather_object(fails, parity["failures"])
+        parity["failures"] = [f for fl_ in fails for f in fl_][:8]
+    parity["checked"], parity["failed"] = int(pv[0]), int(pv[1])
+    if not parity["failures"]:
+        parity.pop("failures")
 
     if rank == 0:
         line = {
-            "metric": "f32 matmul TFLOP/s (8192^2)", "value": value, "unit": "TFLOP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "engine": "tcgen05 cta_group::2 3xTF32, two-level accumulation",
-                       "sharding": f"C/A row blocks of {M} rows per GPU, B replicated, no collective" if world > 1 else "single GPU",
-                       "l2": "inputs (2 x 256 MiB + 1 GiB split scratch) exceed the 126 MB L2",
-                       "generator": "u01(splitmix64(seed ^ idx)), seeds 0x5EED0001/2"},
+            "metric": metric, "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": clocks, "secondary": secondary,
+            "secondary_timing": "CUDA-graph replay of 20 captured calls per line (10-call plain loops for the GEMM-family and NCCL lines), "
+                                "CUDA events, max over ranks, best of 2",
             "device": trn.device_info()["name"],
         }
+        if config1 is not None:
+            line["config1"] = config1
+        line["parity"] = parity
+        if strong is not None:
+            line["strong_scaling"] = strong      # LAST key: survives a truncated tail
         line_holder.append(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 1 if parity["failed"] else 0
 
 
 def main() -> int:

@@ -403,6 +403,10 @@ TRN_API int trn_argmax_allgather_f32_dev(trn_comm* comm, const float* a, size_t 
                                          float* out_value, void* stream);
 TRN_API int trn_argmin_allgather_f32_dev(trn_comm* comm, const float* a, size_t n, uint64_t slice_start, uint64_t* out_idx,
                                          float* out_value, void* stream);
+/* TRN_OK, or TRN_GPU_ERROR once an exchange on this communicator has given up waiting for a peer (TRN_PEER_TIMEOUT_MS,
+ * default 30 s): a dead or desynchronised peer surfaces as TruenoError::GpuError (src/error.rs:27-28), never as a hang.
+ * The timed-out call returns NaN / index UINT64_MAX; every later call on the communicator fails before launching. */
+TRN_API int trn_comm_status(trn_comm* comm);
 
 /* Matrix::convolve2d (src/matrix.rs:1868): valid-padding 2-D cross-correlation, out is
  * (rows - k_rows + 1) x (cols - k_cols + 1); accumulated in the reference's order, unfused -> bit-exact.  Kernel larger
@@ -437,6 +441,20 @@ TRN_API int trn_attention_f32_dev(const float* q, size_t q_len, const float* k, 
 TRN_API int trn_symmetric_eigen_f32(const float* a, size_t rows, size_t cols, float* eigenvalues, float* eigenvectors);
 TRN_API int trn_symmetric_eigen_f32_dev(const float* a, size_t rows, size_t cols, float* eigenvalues, float* eigenvectors,
                                         void* stream);
+
+/* ---- pre-split right-hand operand ------------------------------------------------------------
+ * Matrix::matmul(&self, other) reads `other` on every call (src/matrix.rs:285; the CPU path re-transposes it each time,
+ * :934).  The tensor-core path splits B into tf32 (hi, lo) halves per call — 2 x |B| of writes; a caller that multiplies
+ * many A's by ONE B (the row blocks of a sharded product src/matrix.rs:962-1011, SymmetricEigen::reconstruct
+ * src/eigen.rs:483-485, weights) prepares it once.  `b` is borrowed: alive and unchanged while the handle is in use.
+ * trn_matmul_prepared_f32_dev(a, handle) == trn_matmul_f32_dev(a, b) bit for bit, same errors. */
+typedef struct trn_gemm_b trn_gemm_b;
+TRN_API int trn_gemm_prepare_b_dev(const float* b, size_t b_rows, size_t b_cols, trn_gemm_b** out, void* stream);
+TRN_API int trn_gemm_b_free(trn_gemm_b* handle);
+TRN_API int trn_matmul_prepared_f32_dev(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* b, float* c,
+                                        void* stream);
+/* host-slice twin: A and C are host slices (pinned ones are pipelined by row blocks), B stays resident in HBM */
+TRN_API int trn_matmul_prepared_f32(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* b, float* c);
 
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT

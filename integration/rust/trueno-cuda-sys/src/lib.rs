@@ -28,6 +28,11 @@ pub struct trn_batch {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct trn_gemm_b {
+    _private: [u8; 0],
+}
+
 pub const TRN_OK: c_int = 0;
 pub const TRN_SIZE_MISMATCH: c_int = 1;
 pub const TRN_INVALID_INPUT: c_int = 2;
@@ -258,6 +263,13 @@ extern "C" {
                                         out_value: *mut f32, stream: *mut c_void) -> c_int;
     pub fn trn_argmin_allgather_f32_dev(comm: *mut trn_comm, a: *const f32, n: usize, slice_start: u64, out_idx: *mut u64,
                                         out_value: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_comm_status(comm: *mut trn_comm) -> c_int;
+    // pre-split right-hand operand: many products against one B (row-block shards, SymmetricEigen::reconstruct, weights)
+    pub fn trn_gemm_prepare_b_dev(b: *const f32, b_rows: usize, b_cols: usize, out: *mut *mut trn_gemm_b, stream: *mut c_void) -> c_int;
+    pub fn trn_gemm_b_free(handle: *mut trn_gemm_b) -> c_int;
+    pub fn trn_matmul_prepared_f32_dev(a: *const f32, a_rows: usize, a_cols: usize, b: *const trn_gemm_b, c: *mut f32,
+                                       stream: *mut c_void) -> c_int;
+    pub fn trn_matmul_prepared_f32(a: *const f32, a_rows: usize, a_cols: usize, b: *const trn_gemm_b, c: *mut f32) -> c_int;
     // device-resident op chaining (GpuCommandBatch counterpart, src/backends/gpu/batch.rs)
     pub fn trn_batch_create(out: *mut *mut trn_batch) -> c_int;
     pub fn trn_batch_destroy(batch: *mut trn_batch) -> c_int;

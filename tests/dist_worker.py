@@ -66,6 +66,56 @@ def main() -> int:
             for _ in range(5):
                 assert int(vn.argmax()) == 0 and int(vn.argmin()) == 0
 
+    # ---- fewer aligned blocks than ranks: some slices are EMPTY and still take part in every exchange (no rank left waiting)
+    for n, use_comm in [(x, c) for x in (3, 5, 9) for c in (None, comm)]:
+        a = np.arange(1, n + 1, dtype=f32)
+        a[n - 1] = -7
+        sh = par.shard_range(n, rank, world, align=4)
+        va = par.ShardedVector(torch.from_numpy(a[sh.start:sh.start + sh.count]).to(dev), sh, use_comm)
+        assert float(va.sum()) == float(a.sum()) and int(va.argmin()) == n - 1 and int(va.argmax()) == n - 2
+        assert float(va.min()) == -7.0 and float(va.max()) == float(n - 1)
+        got = va.softmax()
+        torch.cuda.synchronize()
+        e = np.exp((a - a.max()).astype(np.float64))
+        assert np.allclose(got.cpu().numpy(), (e / e.sum())[sh.start:sh.start + sh.count], atol=1e-6)
+    empty = par.ShardedVector(torch.empty(0, device=dev), par.shard_range(0, rank, world, 4), comm)
+    for op in ("argmax", "min"):
+        try:
+            getattr(empty, op)()
+            raise AssertionError("empty vector must raise")
+        except trn.TruenoError as err:
+            assert err == trn.TruenoError.InvalidInput("Empty vector")
+    assert float(empty.sum()) == 0.0            # src/vector.rs:635: the sum of an empty vector is 0.0
+
+    # ---- a chain of fused reductions captured in a CUDA graph and replayed (device-side call numbers)
+    n = 1 << 20
+    a = rng.uniform(-1, 1, n).astype(f32)
+    sh = par.shard_range(n, rank, world, align=4)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        va = par.ShardedVector(torch.from_numpy(a[sh.start:sh.start + sh.count]).to(dev), sh, comm)
+        loop = par.CapturedLoop(lambda: (va.sum(), va.norm_l2(), va.argmax()), 6)
+        for _ in range(3):
+            loop.replay()
+        stream.synchronize()
+        tsum, asum = orc.f64_sum(a)
+        assert float(va._f32) == float(a.max()) and int(va._i64) == orc.argmax(a, backend=SCALAR)   # last call of the chain: argmax
+        assert abs(float(va.sum()) - tsum) <= 1e-5 * asum
+    trn.check(trn.lib.trn_comm_status(comm.handle))
+
+    # ---- entry points called from a worker thread of a process bound to device `local_rank` (per-thread current device)
+    import threading
+    box = {}
+
+    def from_thread():
+        v = trn.Vector.from_slice(np.arange(1000, dtype=f32))
+        box["sum"] = float(v.sum())
+        box["mm"] = trn.Matrix.from_vec(2, 2, [1, 2, 3, 4]).matmul(trn.Matrix.from_vec(2, 2, [5, 6, 7, 8])).to_numpy().tolist()
+    t = threading.Thread(target=from_thread)
+    t.start()
+    t.join()
+    assert box == {"sum": 499500.0, "mm": [[19.0, 22.0], [43.0, 50.0]]}, box
+
     # ---- ONE softmax / log_softmax vector sharded over the ranks: slice stats -> all_gather of pairs -> fold + write
     for n in (1 << 22, (1 << 22) + 37, 1001):
         a = (rng.standard_normal(n) * 4).astype(f32)
@@ -138,6 +188,40 @@ def main() -> int:
     truth = A2.astype(np.float64) @ B2.astype(np.float64)
     scale = np.abs(A2).astype(np.float64) @ np.abs(B2).astype(np.float64)
     assert np.all(np.abs(full - truth) <= 1e-5 * scale)
+
+    # ---- ShardedMatrix: row blocks of whole 256-row tiles, B replicated by ONE broadcast and pre-split once; matvec by rows
+    M, K, N = 1024 + 300, 640, 512
+    A3 = rng.uniform(-1, 1, (M, K)).astype(f32)
+    B3 = rng.uniform(-1, 1, (K, N)).astype(f32)
+    v3 = rng.uniform(-1, 1, K).astype(f32)
+    rs3 = par.ShardedMatrix.row_shard(M)
+    assert rs3.start % par.ROW_BLOCK == 0
+    Am = par.ShardedMatrix(torch.from_numpy(A3[rs3.start:rs3.start + rs3.count]).to(dev).reshape(-1).contiguous(), rs3, K)
+    Bsrc = torch.from_numpy(B3).to(dev).reshape(-1) if rank == 0 else None          # only rank 0 holds B
+    Bm = par.ReplicatedMatrix.broadcast(Bsrc, K, N, src=0, device=dev)
+    plain = Am.matmul(Bm).gather()
+    prepared = Am.matmul(Bm.prepare()).gather()
+    torch.cuda.synchronize()
+    assert torch.equal(plain, prepared)                       # the prepared handle changes no bit
+    truth = A3.astype(np.float64) @ B3.astype(np.float64)
+    scale = np.abs(A3).astype(np.float64) @ np.abs(B3).astype(np.float64)
+    assert np.all(np.abs(plain.cpu().numpy() - truth) <= 1e-5 * scale)
+    if rs3.count:                                             # and none against the unsharded product of the same rows
+        whole = torch.empty(M * N, device=dev)
+        dA = torch.from_numpy(A3).to(dev)
+        trn.check(trn.lib.trn_matmul_f32_dev(dA.data_ptr(), M, K, Bm.data.data_ptr(), K, N, whole.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert torch.equal(whole.view(M, N)[rs3.start:rs3.start + rs3.count], plain[rs3.start:rs3.start + rs3.count])
+    y = par.gather_vector(Am.matvec(torch.from_numpy(v3).to(dev)))
+    ty = A3.astype(np.float64) @ v3.astype(np.float64)
+    sy = np.abs(A3).astype(np.float64) @ np.abs(v3).astype(np.float64)
+    assert np.all(np.abs(y.cpu().numpy() - ty) <= 1e-5 * sy)
+    try:
+        Am.matmul(par.ReplicatedMatrix(torch.zeros(3 * 4, device=dev), 3, 4))
+        raise AssertionError("inner dimensions must be checked")
+    except trn.TruenoError as err:
+        assert err.variant == "InvalidInput" and f"inner dimensions {K} and 3 must match" in err.message
+    Bm.close()
 
     dist.barrier()
     if rank == 0:

@@ -36,6 +36,19 @@ def test_shard_range_partitions_exactly():
     assert [shard_range(256, r, 8).count for r in range(8)] == [32] * 8
 
 
+def test_row_blocks_of_a_sharded_matrix_are_whole_tiles():
+    """ShardedMatrix.row_shard: the reference's rayon unit is a 256-row block (src/matrix.rs:962-1011); every rank owns a
+    run of whole blocks, the last non-empty one takes the ragged tail, nothing is lost or duplicated."""
+    from trueno_b200.parallel import ROW_BLOCK, ShardedMatrix
+    for rows in (0, 1, 255, 256, 1000, 1324, 8192, 32768, 32768 + 5):
+        for world in (1, 2, 3, 4, 8):
+            shards = [ShardedMatrix.row_shard(rows, r, world) for r in range(world)]
+            assert shards[0].start == 0 and sum(s.count for s in shards) == rows
+            for a, b in zip(shards, shards[1:]):
+                assert a.start + a.count == b.start and (b.start % ROW_BLOCK == 0 or b.count == 0)
+    assert [ShardedMatrix.row_shard(32768, r, 8).count for r in range(8)] == [4096] * 8      # BASELINE configs[4]
+
+
 def _slice_partial(orc, a, start, is_max):
     """What trn_arg{max,min}_slice_f32_dev reports for one slice (see reduce.cu / parallel.py)."""
     from oracle import SCALAR

@@ -13,10 +13,20 @@
 
 using namespace trn;
 
+// pre-split right-hand operand (trn_gemm_prepare_b_dev, below)
+struct trn_gemm_b {
+    const float* b = nullptr;   // borrowed: the caller's B in HBM
+    size_t k = 0, n = 0;
+    float* split = nullptr;     // B_hi then B_lo, [n][kpad] each; null when no kernel would read them
+    int* flag = nullptr;        // raised by the split when B holds an Inf / NaN
+};
+
 namespace {
 
 // Rust's `{}` for f32: shortest representation that round-trips, integers without a fraction ("1", "0.5", "-2.25")
 std::string fmt_f32(float v) {
+    if (v != v) return "NaN";                       // Rust's Display for f32
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
     char buf[64];
     for (int prec = 1; prec <= 9; ++prec) {
         snprintf(buf, sizeof buf, "%.*g", prec, (double)v);
@@ -24,8 +34,12 @@ std::string fmt_f32(float v) {
     }
     std::string r(buf);
     if (r.find('e') != std::string::npos) {   // Rust never prints exponents for f32 Display
-        snprintf(buf, sizeof buf, "%.9f", (double)v);
+        snprintf(buf, sizeof buf, "%.60f", (double)v);   // Rust prints the shortest round-tripping digits, positionally
         r = buf;
+        // cut to the shortest prefix that still round-trips
+        const size_t dot = r.find('.');
+        for (size_t len = dot + 2; len <= r.size(); ++len)
+            if (strtof(r.substr(0, len).c_str(), nullptr) == v) { r = r.substr(0, len); break; }
         while (r.find('.') != std::string::npos && (r.back() == '0' || r.back() == '.')) { const bool dot = r.back() == '.'; r.pop_back(); if (dot) break; }
     }
     return r;
@@ -36,8 +50,7 @@ std::atomic<int> g_engine{0};
 // Host-slice calls stage through the ONE backend stream and its per-stream scalar slots / pinned staging ring,
 // so concurrent callers (the reference's rayon workers may call a backend from several threads) are serialised
 // here.  `_dev` calls take caller-owned memory and streams and need no lock.
-std::mutex g_host_mu;
-#define TRN_HOST_LOCK() std::lock_guard<std::mutex> _host_lock(g_host_mu)
+#define TRN_HOST_LOCK() std::lock_guard<std::mutex> _host_lock(trn::host_mutex())
 
 // U+00D7 MULTIPLICATION SIGN, as the reference's format strings use (src/matrix.rs:288, :398, :484)
 #define X "\xC3\x97"
@@ -201,6 +214,9 @@ int check_clamp(float lo, float hi) {  // src/vector.rs:2964-2969
 
 extern "C" {
 
+static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
+                               const trn_gemm_b* prepared);
+
 int trn_set_gemm_engine(int engine) {
     if (engine < 0 || engine > 3) return fail(TRN_INVALID_INPUT, "unknown GEMM engine %d", engine);
     g_engine.store(engine);
@@ -259,12 +275,12 @@ int trn_argmin_slice_f32_dev(const float* a, size_t n, int first_slice, uint64_t
     return launch_argreduce(0, a, n, out, out_value, resolve_stream(stream), first_slice != 0);
 }
 int trn_argmax_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream) {
-    TRN_TRY(check_nonempty_invalid(n));
+    if (slice_start == 0) TRN_TRY(check_nonempty_invalid(n));   // an empty INTERIOR slice reports "no candidate"
     TRN_TRY(need_ctx());
     return launch_argreduce(1, a, n, nullptr, nullptr, resolve_stream(stream), slice_start == 0, slice_start, out);
 }
 int trn_argmin_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream) {
-    TRN_TRY(check_nonempty_invalid(n));
+    if (slice_start == 0) TRN_TRY(check_nonempty_invalid(n));   // an empty INTERIOR slice reports "no candidate"
     TRN_TRY(need_ctx());
     return launch_argreduce(0, a, n, nullptr, nullptr, resolve_stream(stream), slice_start == 0, slice_start, out);
 }
@@ -301,13 +317,17 @@ int trn_softmax_rows_f32_dev(const float* a, float* out, size_t rows, size_t col
 // One Vector::softmax / log_softmax sharded over several GPUs: stats of this rank's slice, then — after
 // the ranks have all_gathered their pairs — normalisation of the slice by the fold of all pairs.
 int trn_softmax_slice_stats_f32_dev(const float* a, size_t n, float* pair_out, void* stream) {
-    TRN_TRY(check_nonempty_emptyvec(n));
     TRN_TRY(need_ctx());
+    if (n == 0) {   // an empty slice of a sharded vector takes part with the identity pair (-inf, 0)
+        static const float kIdentity[2] = {-INFINITY, 0.0f};
+        TRN_CUDA(cudaMemcpyAsync(pair_out, kIdentity, sizeof kIdentity, cudaMemcpyHostToDevice, resolve_stream(stream)));
+        return TRN_OK;
+    }
     return launch_softmax_slice_stats(a, n, pair_out, resolve_stream(stream));
 }
 int trn_softmax_slice_apply_f32_dev(const float* a, size_t n, const float* pairs, size_t npairs, int log_variant, float* out,
                                     void* stream) {
-    TRN_TRY(check_nonempty_emptyvec(n));
+    if (n == 0) return TRN_OK;   // nothing to write for an empty slice
     if (npairs == 0) return fail(TRN_INVALID_INPUT, "no (max, sum) pairs to normalise by");
     TRN_TRY(need_ctx());
     return launch_softmax_slice_apply(a, n, pairs, npairs, log_variant, out, resolve_stream(stream));
@@ -350,6 +370,95 @@ int trn_batched_matmul_4d_f32_dev(const float* a, size_t a_len, const float* b, 
     }
     return gemm_dispatch(a, b, c, batch * heads, m, k, n, s);
 }
+// ---- pre-split right-hand operand (repeated products against the same B) ------------------------------------------
+// Matrix::matmul re-reads `other` on every call (the CPU path even re-transposes it, src/matrix.rs:934); on the device the
+// tensor-core path re-SPLITS it: 2 x |B| of writes per call (2.4 ms for the 4 GiB B of a 32768^2 row-block shard).  A
+// handle keeps B_hi / B_lo (K-major, padded) in HBM, so every later product pays for A only.  Shapes that take another
+// kernel (fused-split, SIMT, vecmat) need nothing prepared: the handle then just remembers B.  B itself is BORROWED: it
+// must stay alive and unchanged while the handle is used (the IEEE fallback for Inf/NaN inputs and the non-tensor kernels
+// read it).  Results are bit-identical to trn_matmul_f32_dev(a, b).
+int trn_gemm_prepare_b_dev(const float* b, size_t b_rows, size_t b_cols, trn_gemm_b** out, void* stream) {
+    if (!out) return fail(TRN_INVALID_INPUT, "trn_gemm_prepare_b_dev: null output handle");
+    TRN_TRY(need_ctx());
+    cudaStream_t s = resolve_stream(stream);
+    trn_gemm_b* h = new trn_gemm_b();
+    h->b = b;
+    h->k = b_rows;
+    h->n = b_cols;
+    const size_t kpad = gemm_tc_kpad(b_rows);
+    const size_t elems = b_cols * kpad;
+    // prepared only for the pre-pass tensor-core kernel: gemm_prepared_uses_split() repeats this test per product
+    if (b_rows > 0 && b_cols > 0 && gemm_tc_supported(256, b_rows, b_cols) && !gemm_tc_uses_fused(nullptr, b, 256, b_rows, b_cols)) {
+        cudaError_t e = cudaMalloc(&h->split, (2 * elems) * sizeof(float) + 256);
+        if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaMalloc (pre-split B)"); }
+        h->flag = reinterpret_cast<int*>(h->split + 2 * elems);
+        int st = cudaMemsetAsync(h->flag, 0, sizeof(int), s) == cudaSuccess ? TRN_OK : fail(TRN_GPU_ERROR, "cudaMemsetAsync failed");
+        if (st == TRN_OK) st = gemm_tc_split_b(b, h->split, h->split + elems, 1, b_rows, b_cols, h->flag, s);
+        if (st != TRN_OK) { cudaFree(h->split); delete h; return st; }
+    }
+    *out = h;
+    return TRN_OK;
+}
+
+int trn_gemm_b_free(trn_gemm_b* h) {
+    if (!h) return TRN_OK;
+    cudaError_t e = h->split ? cudaFree(h->split) : cudaSuccess;   // cudaFree waits for the work that still reads it
+    delete h;
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFree (pre-split B)");
+    return TRN_OK;
+}
+
+int trn_matmul_prepared_f32_dev(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* bh, float* c, void* stream) {
+    if (!bh) return fail(TRN_INVALID_INPUT, "trn_matmul_prepared_f32_dev: null B handle");
+    TRN_TRY(check_matmul(a_rows, a_cols, bh->k, bh->n));
+    TRN_TRY(need_ctx());
+    cudaStream_t s = resolve_stream(stream);
+    const size_t m = a_rows, k = a_cols, n = bh->n;
+    if (k == 0 && m * n > 0) {
+        TRN_CUDA(cudaMemsetAsync(c, 0, m * n * sizeof(float), s));
+        return TRN_OK;
+    }
+    // the same routing as trn_matmul_f32_dev; only the pre-pass tensor-core product has something to reuse
+    const int engine = g_engine.load();
+    const bool tc3 = m > 1 && (engine == 2 || (engine == 0 && gemm_auto_uses_tc(m, k, n)));
+    if (!bh->split || !tc3 || gemm_tc_uses_fused(a, bh->b, m, k, n)) return gemm_dispatch(a, bh->b, c, 1, m, k, n, s);
+    const size_t kpad = gemm_tc_kpad(k);
+    float* scratch = nullptr;
+    TRN_TRY(scratch_alloc((void**)&scratch, 2 * m * kpad * sizeof(float) + 256, s));
+    int* flag = reinterpret_cast<int*>(scratch + 2 * m * kpad);
+    // start from B's verdict, then let the split of A add its own
+    int st = cudaMemcpyAsync(flag, bh->flag, sizeof(int), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? TRN_OK : fail(TRN_GPU_ERROR, "cudaMemcpyAsync failed");
+    gemm_profile_begin(s);
+    if (st == TRN_OK) st = gemm_tc_split_a(a, scratch, scratch + m * kpad, 1, m, k, flag, s);
+    gemm_profile_mid(s);
+    if (st == TRN_OK) st = gemm_tc_main(scratch, scratch + m * kpad, bh->split, bh->split + n * kpad, c, 1, m, k, n, 3, flag, s);
+    gemm_profile_end(s);
+    if (st == TRN_OK) st = launch_gemm_simt(a, bh->b, c, 1, m, k, n, s, flag);
+    scratch_free(scratch, s);
+    return st;
+}
+
+// host-slice twin: A and C are host slices, B stays resident.  Pinned slices of large tensor-core products are pipelined
+// (row blocks of A up, GEMM, row blocks of C down, on three streams); results are bit-identical to the resident call.
+int trn_matmul_prepared_f32(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* bh, float* c) {
+    if (!bh) return fail(TRN_INVALID_INPUT, "trn_matmul_prepared_f32: null B handle");
+    TRN_TRY(check_matmul(a_rows, a_cols, bh->k, bh->n));
+    TRN_TRY(need_ctx());
+    TRN_HOST_LOCK();
+    Context* cx = ctx();
+    const size_t m = a_rows, k = a_cols, n = bh->n;
+    if (m * n == 0) return TRN_OK;
+    if (g_engine.load() == 0 && k > 0 && m >= 1024 && gemm_auto_uses_tc(m, k, n) && (m * k + m * n) * sizeof(float) >= ((size_t)64 << 20) &&
+        (bh->split || gemm_tc_uses_fused(nullptr, bh->b, m, k, n)) && is_pinned_host(a) && is_pinned_host(c))
+        return host_gemm_pipelined(a, nullptr, c, 1, m, k, n, bh);
+    DevTemp da(cx->stream), dc(cx->stream);
+    TRN_TRY(da.alloc(m * k));
+    TRN_TRY(dc.alloc(m * n));
+    TRN_TRY(upload(da.p, a, m * k, cx->stream));
+    TRN_TRY(trn_matmul_prepared_f32_dev(da.p, m, k, bh, dc.p, cx->stream));
+    return download(c, dc.p, m * n, cx->stream);
+}
+
 int trn_matvec_f32_dev(const float* a, size_t rows, size_t cols, const float* v, size_t v_len, float* y,
                        void* stream) {
     TRN_TRY(check_matvec(cols, v_len));
@@ -461,7 +570,10 @@ struct Event {
     ~Event() { if (e) cudaEventDestroy(e); }
 };
 
-static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n) {
+// `prepared` != nullptr (single products only): B is already resident — and split, when the kernel wants that — so only
+// the row blocks of A go up and the row blocks of C come down.
+static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
+                               const trn_gemm_b* prepared) {
     Context* cx = ctx();
     cudaStream_t s_main = cx->stream, s_up = cx->copy_stream, s_down = cx->d2h_stream;
     const size_t kpad = gemm_tc_kpad(k);
@@ -503,8 +615,8 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
         units = (batch + per_block - 1) / per_block;
     }
 
-    const size_t na = batch * m * k, nb = batch * k * n, nc = batch * m * n;
-    const size_t a_split = fused ? 0 : batch * m * kpad, b_split = fused ? 0 : batch * n * kpad;
+    const size_t na = batch * m * k, nb = prepared ? 0 : batch * k * n, nc = batch * m * n;
+    const size_t a_split = fused ? 0 : batch * m * kpad, b_split = (fused || prepared) ? 0 : batch * n * kpad;
     // every sub-buffer starts on a 256-byte boundary (TMA needs 16-byte aligned tensor bases)
     auto pad64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
     float* dev = nullptr;
@@ -517,7 +629,16 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     float* b_hi = a_lo + pad64(a_split);
     float* b_lo = b_hi + pad64(b_split);
     int* flag = reinterpret_cast<int*>(b_lo + pad64(b_split));
-    TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s_main));
+    if (prepared) {
+        db = const_cast<float*>(prepared->b);
+        if (!fused) { b_hi = prepared->split; b_lo = prepared->split + n * kpad; }
+    }
+
+    // Everything that can fail runs inside `enqueue`; whatever it returns, the three streams are drained before the
+    // borrowed host slices go back to the caller and the scratch is released (no leak, no copy still in flight).
+    auto enqueue = [&]() -> int {
+    if (prepared && prepared->flag) TRN_CUDA(cudaMemcpyAsync(flag, prepared->flag, sizeof(int), cudaMemcpyDeviceToDevice, s_main));
+    else TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s_main));
 
     std::vector<Event> up(units + 1), done(units);
     Event ready, drained;
@@ -531,7 +652,7 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     TRN_CUDA(cudaStreamWaitEvent(s_down, ready.e, 0));
 
     int st = TRN_OK;
-    if (single) {
+    if (single && !prepared) {
         TRN_CUDA(cudaMemcpyAsync(db, b, nb * sizeof(float), cudaMemcpyHostToDevice, s_up));
         TRN_CUDA(cudaEventRecord(up[units].e, s_up));
         TRN_CUDA(cudaStreamWaitEvent(s_main, up[units].e, 0));
@@ -573,6 +694,9 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
             TRN_CUDA(cudaMemcpyAsync(c + b0 * m * n, dc + b0 * m * n, cnt * m * n * sizeof(float), cudaMemcpyDeviceToHost, s_down));
         }
     }
+    return st;
+    };
+    const int st = enqueue();
     // the host slices are borrowed: everything must have landed before the call returns
     cudaError_t e1 = cudaStreamSynchronize(s_up), e2 = cudaStreamSynchronize(s_main), e3 = cudaStreamSynchronize(s_down);
     scratch_free(dev, s_main);
@@ -591,7 +715,7 @@ static int host_gemm(const float* a, const float* b, float* c, size_t batch, siz
     // large tensor-core products from pinned host memory: overlap the PCIe transfers with the math
     if (g_engine.load() == 0 && k > 0 && m > 1 && gemm_auto_uses_tc(m, k, n) && (na + nb + nc) * sizeof(float) >= ((size_t)64 << 20) &&
         (batch > 1 || m >= 1024) && is_pinned_host(a) && is_pinned_host(b) && is_pinned_host(c))
-        return host_gemm_pipelined(a, b, c, batch, m, k, n);
+        return host_gemm_pipelined(a, b, c, batch, m, k, n, nullptr);
     DevTemp da(cx->stream), db(cx->stream), dc(cx->stream);
     TRN_TRY(da.alloc(na));
     TRN_TRY(db.alloc(nb));
@@ -996,7 +1120,7 @@ int trn_correlation_f32(const float* a, size_t na, const float* b, size_t nb, fl
     const float sx = sqrtf(vx), sy = sqrtf(vy);
     if (fabsf(sx) < 1e-10f || fabsf(sy) < 1e-10f) return fail(TRN_DIVISION_BY_ZERO, "Division by zero");
     const float corr = cov / (sx * sy);
-    *out = fminf(fmaxf(corr, -1.0f), 1.0f);
+    *out = corr != corr ? corr : fminf(fmaxf(corr, -1.0f), 1.0f);   // f32::clamp (src/vector.rs:1153) propagates NaN
     return TRN_OK;
 }
 // Vector::zscore (src/vector.rs:1180): (x - mean) * (1 / stddev); empty -> EmptyVector; |stddev| < 1e-10 -> DivisionByZero

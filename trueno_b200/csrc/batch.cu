@@ -147,6 +147,8 @@ int trn_batch_execute(trn_batch* b) {   // batch.rs:362
     if (!b) return fail(TRN_INVALID_INPUT, "trn_batch_execute: null batch");
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
+    // the backend stream goes into capture below and carries the uploads: no host-slice call may touch it meanwhile
+    std::lock_guard<std::mutex> host_lock(host_mutex());
     cudaStream_t s = c->stream;
     // (re)plan when buffers or ops were added since the last execute
     if (b->planned_bufs != b->bufs.size() || b->planned_ops != b->ops.size()) {
@@ -193,6 +195,7 @@ int trn_batch_read(trn_batch* b, uint32_t id, float* out, size_t len) {   // bat
     if (len != b->bufs[id].len) return fail_mismatch(b->bufs[id].len, len);
     Context* c = ctx();
     if (!c) return TRN_GPU_ERROR;
+    std::lock_guard<std::mutex> host_lock(host_mutex());
     return download(out, b->arena + b->bufs[id].offset, len, c->stream);
 }
 

@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "trueno_cuda.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -79,8 +81,13 @@ int download(float* dst_host, const float* src_dev, size_t n, cudaStream_t s);
 constexpr int kMaxPeers = 8;
 struct PeerCtx {
     unsigned long long* box[kMaxPeers];   // mailbox of every rank, mapped into this process (box[rank] is local)
+    unsigned* seq;                        // DEVICE counter of the collective calls made on this communicator (lives beside
+                                          // the local mailbox, bumped by the kernel itself: the calls can be captured in a
+                                          // CUDA graph and replayed)
+    unsigned* err;                        // host-mapped error words {call number, rank waited for + 1}: written by the first
+                                          // exchange that gives up, read by the host entry points
+    unsigned long long timeout_ns;        // spin budget of one exchange
     int rank, world;
-    unsigned seq;                         // collective call number: identical on every rank
 };
 
 enum class Reduce { Sum, Dot, SumSq, NormL2, SumAbs, MaxAbs, SumKahan };
@@ -147,9 +154,15 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
 bool gemm_tc_uses_fused(const float* a, const float* b, size_t m, size_t k, size_t n);
 int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int* flag,
                        cudaStream_t s);
+// live timing brackets of one GEMM call (trn_profile_*): before the pre-pass, after it, after the main kernel
+void gemm_profile_begin(cudaStream_t s);
+void gemm_profile_mid(cudaStream_t s);
+void gemm_profile_end(cudaStream_t s);
 // auto-dispatch rule shared by the resident and the pipelined host paths (api.cu)
 bool gemm_auto_uses_tc(size_t m, size_t k, size_t n);
 bool is_pinned_host(const void* p);
+// serialises the host-slice entry points, the command batch and trn_buf transfers on the backend's own stream
+std::mutex& host_mutex();
 
 // ---------------------------------------------------------------------------------------------
 // Device helpers

@@ -105,10 +105,27 @@ static int init_locked(int device) {
     return TRN_OK;
 }
 
+// The current CUDA device is per-THREAD state: a worker thread that calls into the backend for the first time (the
+// reference's rayon workers do, src/vector.rs:377-383) still has device 0 current, and its launches on the backend's
+// streams would fail with "invalid resource handle" in a process bound to another GPU.  Every entry point goes through
+// here, so this is where the calling thread is bound to the backend's device (one cudaGetDevice per call).
 Context* ctx() {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx && init_locked(-1) != TRN_OK) return nullptr;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != g_ctx->device) {
+        if (cudaSetDevice(g_ctx->device) != cudaSuccess) {
+            fail(TRN_GPU_ERROR, "cannot bind the calling thread to CUDA device %d", g_ctx->device);
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
     return g_ctx;
+}
+
+std::mutex& host_mutex() {
+    static std::mutex mu;
+    return mu;
 }
 
 cudaStream_t resolve_stream(void* s) {
@@ -350,6 +367,7 @@ int trn_buf_upload(trn_buf* buf, const float* host, size_t len) {
     if (!c) return TRN_GPU_ERROR;
     if (!buf) return fail(TRN_INVALID_INPUT, "trn_buf_upload: null buffer");
     if (len != buf->len) return fail_mismatch(buf->len, len);
+    std::lock_guard<std::mutex> host_lock(host_mutex());
     TRN_TRY(upload(buf->dev, host, len, c->stream));
     TRN_CUDA(cudaStreamSynchronize(c->stream));  // the borrowed host slice may be dropped on return
     return TRN_OK;
@@ -360,6 +378,7 @@ int trn_buf_download(const trn_buf* buf, float* host, size_t len) {
     if (!c) return TRN_GPU_ERROR;
     if (!buf) return fail(TRN_INVALID_INPUT, "trn_buf_download: null buffer");
     if (len != buf->len) return fail_mismatch(buf->len, len);
+    std::lock_guard<std::mutex> host_lock(host_mutex());
     return download(host, buf->dev, len, c->stream);
 }
 

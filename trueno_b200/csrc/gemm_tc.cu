@@ -844,7 +844,6 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const uint32_t pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-    const uint32_t total_tiles = p.tiles_m * p.tiles_n * p.batch;
     // Work unit = one A panel (b, mt) x one segment of its n-tiles; units are dealt round-robin in the order
     // (b, segment, mt), so the pairs that run side by side hold different panels of the SAME batch entry and
     // walk the same B tiles together (L2 hits).  p.nseg segments per panel (1 when there are panels enough).
@@ -1192,6 +1191,24 @@ static cudaEvent_t g_ev[kProfRing][3];
 static bool g_ev_created = false;
 static unsigned g_ev_count = 0;
 
+// brackets of one profiled GEMM call: begin (before the pre-pass), mid (pre-pass done), end (main kernel done)
+static cudaEvent_t* profile_slot() {
+    if (!g_profile) return nullptr;
+    if (!g_ev_created) {
+        for (auto& t : g_ev) for (auto& e : t) if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        g_ev_created = true;
+    }
+    return g_ev[g_ev_count % kProfRing];
+}
+void gemm_profile_begin(cudaStream_t s) { if (cudaEvent_t* ev = profile_slot()) cudaEventRecord(ev[0], s); }
+void gemm_profile_mid(cudaStream_t s) { if (cudaEvent_t* ev = profile_slot()) cudaEventRecord(ev[1], s); }
+void gemm_profile_end(cudaStream_t s) {
+    if (cudaEvent_t* ev = profile_slot()) {
+        cudaEventRecord(ev[2], s);
+        ++g_ev_count;
+    }
+}
+
 bool gemm_tc_supported(size_t m, size_t k, size_t n) {
     // 32-bit tile coordinates and TMA dimension limits; any m, n, k >= 1 otherwise
     return m >= 1 && n >= 1 && k >= 1 && m < (1u << 30) && n < (1u << 30) && k < (1u << 30);
@@ -1422,21 +1439,10 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
         int* flag = nullptr;
         TRN_TRY(scratch_alloc((void**)&flag, 256, s));
         TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
-        cudaEvent_t* ev = nullptr;
-        if (g_profile) {
-            if (!g_ev_created) {
-                for (auto& t : g_ev) for (auto& e : t) TRN_CUDA(cudaEventCreate(&e));
-                g_ev_created = true;
-            }
-            ev = g_ev[g_ev_count % kProfRing];
-            TRN_CUDA(cudaEventRecord(ev[0], s));
-            TRN_CUDA(cudaEventRecord(ev[1], s));
-        }
+        gemm_profile_begin(s);
+        gemm_profile_mid(s);
         int st = gemm_tc_fused_main(a, b, c, batch, m, k, n, flag, s);
-        if (ev) {
-            TRN_CUDA(cudaEventRecord(ev[2], s));
-            ++g_ev_count;
-        }
+        gemm_profile_end(s);
         if (st == TRN_OK) st = launch_gemm_simt(a, b, c, batch, m, k, n, s, flag);
         scratch_free(flag, s);
         return st;
@@ -1452,23 +1458,12 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     int* flag = reinterpret_cast<int*>(b_lo + b_elems);   // non-finite-input flag (see header)
     TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
 
-    cudaEvent_t* ev = nullptr;
-    if (g_profile) {
-        if (!g_ev_created) {
-            for (auto& t : g_ev) for (auto& e : t) TRN_CUDA(cudaEventCreate(&e));
-            g_ev_created = true;
-        }
-        ev = g_ev[g_ev_count % kProfRing];
-        TRN_CUDA(cudaEventRecord(ev[0], s));
-    }
+    gemm_profile_begin(s);
     int st = gemm_tc_split_a(a, a_hi, a_lo, batch, m, k, flag, s);
     if (st == TRN_OK) st = gemm_tc_split_b(b, b_hi, b_lo, batch, k, n, flag, s);
-    if (ev) TRN_CUDA(cudaEventRecord(ev[1], s));
+    gemm_profile_mid(s);
     if (st == TRN_OK) st = gemm_tc_main(a_hi, a_lo, b_hi, b_lo, c, batch, m, k, n, terms, flag, s);
-    if (ev) {
-        TRN_CUDA(cudaEventRecord(ev[2], s));
-        ++g_ev_count;
-    }
+    gemm_profile_end(s);
     // IEEE fallback for Inf/NaN inputs: runs only when the flag is set (checked on the device)
     if (st == TRN_OK) st = launch_gemm_simt(a, b, c, batch, m, k, n, s, flag);
     scratch_free(scratch, s);

@@ -50,25 +50,60 @@ constexpr int kPeerWords = 4;   // 32-bit payload words per rank per call
 __device__ __forceinline__ unsigned long long* peer_slot(unsigned long long* box, unsigned parity, int src, int word) {
     return box + ((parity * kMaxPeers + src) * kPeerWords + word);
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Returns false when a peer's message did not arrive within pc.timeout_ns: the payload of that rank is then NaN bits,
+// the error words are raised for the host (the communicator is poisoned: later calls fail with GpuError before they
+// launch) and the caller writes a NaN / "no index" result — a dead or desynchronised peer is an error, never a hang.
 template <int NW>
-__device__ __forceinline__ void peer_exchange(const PeerCtx& pc, const uint32_t (&mine)[NW], uint32_t (*all)[kPeerWords]) {
-    const unsigned parity = pc.seq & 1u;
+__device__ __forceinline__ bool peer_exchange(const PeerCtx& pc, const uint32_t (&mine)[NW], uint32_t (*all)[kPeerWords]) {
+    __shared__ unsigned s_seq;
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) {
+        unsigned q = *pc.seq + 1u;
+        if (q == 0) q = 1;              // 0 is the "never written" state of a fresh mailbox
+        *pc.seq = q;
+        s_seq = q;
+        s_failed = 0;
+    }
+    __syncthreads();
+    const unsigned seq = s_seq, parity = seq & 1u;
     const int t = threadIdx.x;
     if (t < pc.world * NW) {
         const int dst = t / NW, w = t % NW;
-        const unsigned long long msg = ((unsigned long long)pc.seq << 32) | mine[w];
+        const unsigned long long msg = ((unsigned long long)seq << 32) | mine[w];
         asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peer_slot(pc.box[dst], parity, pc.rank, w)), "l"(msg) : "memory");
     }
     if (t < pc.world * NW) {
         const int src = t / NW, w = t % NW;
         const unsigned long long* slot = peer_slot(pc.box[pc.rank], parity, src, w);
+        const unsigned long long t0 = global_ns();
         unsigned long long v;
-        do {
+        unsigned spins = 0;
+        bool ok = true;
+        for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
-        } while ((unsigned)(v >> 32) != pc.seq);
-        all[src][w] = (uint32_t)v;
+            if ((unsigned)(v >> 32) == seq) break;
+            if ((++spins & 255u) == 0 && global_ns() - t0 > pc.timeout_ns) { ok = false; break; }
+        }
+        if (ok) {
+            all[src][w] = (uint32_t)v;
+        } else {
+            all[src][w] = 0x7FC00000u;   // NaN
+            if (atomicExch(&s_failed, 1) == 0) {
+                volatile unsigned* e = pc.err;
+                e[1] = (unsigned)src + 1u;
+                __threadfence_system();
+                e[0] = seq;
+                __threadfence_system();
+            }
+        }
     }
     __syncthreads();
+    return s_failed == 0;
 }
 
 __device__ __forceinline__ float block_sum(float v) {
@@ -225,9 +260,10 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
                 if (threadIdx.x == 0) { s_pair[0] = rh; s_pair[1] = rl; }
                 __syncthreads();
                 const uint32_t mine[2] = {__float_as_uint(s_pair[0]), __float_as_uint(s_pair[1])};
-                peer_exchange<2>(pc, mine, s_all);
+                const bool ok = peer_exchange<2>(pc, mine, s_all);
                 rh = 0.f; rl = 0.f;
                 for (int r = 0; r < pc.world; ++r) pair_add(rh, rl, __uint_as_float(s_all[r][0]), __uint_as_float(s_all[r][1]));
+                if (!ok) rh = __uint_as_float(0x7FC00000u);
             }
             if (threadIdx.x == 0) *out = __fadd_rn(rh, rl);
         }
@@ -251,9 +287,10 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
             if (threadIdx.x == 0) s_tot = r;
             __syncthreads();
             const uint32_t mine[1] = {__float_as_uint(s_tot)};
-            peer_exchange<1>(pc, mine, s_all);
+            const bool ok = peer_exchange<1>(pc, mine, s_all);
             r = 0.f;
             for (int q = 0; q < pc.world; ++q) r = ISMAX ? fmaxf(r, __uint_as_float(s_all[q][0])) : r + __uint_as_float(s_all[q][0]);
+            if (!ok) r = __uint_as_float(0x7FC00000u);
         }
         if (threadIdx.x == 0) *out = SQRT ? sqrtf(r) : r;
     }
@@ -377,7 +414,7 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             __shared__ float s_v;
             __shared__ uint64_t s_i;
             if (threadIdx.x == 0) {
-                if (seed_rule) {
+                if (seed_rule && n > 0) {
                     const float seed = a[0];
                     if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
                 }
@@ -386,8 +423,12 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             }
             __syncthreads();
             const uint32_t mine[3] = {__float_as_uint(s_v), (uint32_t)s_i, (uint32_t)(s_i >> 32)};
-            peer_exchange<3>(pc, mine, s_all);
-            if (threadIdx.x == 0) {
+            const bool ok = peer_exchange<3>(pc, mine, s_all);
+            if (threadIdx.x == 0 && !ok) {
+                if (out_idx) *out_idx = kNoIndex;
+                if (out_val) *out_val = __uint_as_float(0x7FC00000u);
+            }
+            if (threadIdx.x == 0 && ok) {
                 const float v0 = __uint_as_float(s_all[0][0]);
                 float bv = MAX ? -INFINITY : INFINITY;
                 uint64_t bi = kNoIndex;
@@ -408,7 +449,7 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             // value or NaN, so nothing is strictly better than a[0] either: the answer is index 0.
             // seed_rule == 0: an interior slice of a sharded vector — no seed; "no candidate" is
             // reported as index ~0 so the cross-slice combine can skip it (trueno_b200/parallel.py).
-            if (seed_rule) {
+            if (seed_rule && n > 0) {
                 const float seed = a[0];
                 if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
             }

@@ -13,7 +13,9 @@ The reference has no multi-GPU code at all; this module impleme
   ONE softmax / log_softmax vector     contiguous slices of the vector      all_gather of (max, sum-of-exp) pairs,
                                                                             folded in rank order by every rank
   batched_matmul_4d                    contiguous ranges of batch*head      none
-  matmul (large)                       C / A row blocks, B replicated       none
+  matmul (large)                       C / A row blocks of whole 256-row    none on the product (one broadcast of B
+                                       tiles, B replicated (ShardedMatrix)  when only one rank holds it)
+  matvec                               A row blocks, v replicated           none (all_gather of y on request)
 
 Partials are produced by the `_dev` kernels on the CURRENT torch stream and the collective is
 enqueued on the same stream right behind them (no host synchronisation in between).  Tensors are
@@ -237,18 +239,28 @@ class ShardedVector:
     def norm_l2(self) -> torch.Tensor:
         if self.comm is not None:
             return self._fused("trn_norm_l2_allreduce_f32_dev")
+        if world_size() == 1:
+            return self._partial("trn_norm_l2_f32_dev")      # one launch, sqrt inside the kernel
         return combine_sum(self._partial("trn_sumsq_f32_dev")).sqrt_()
 
     def _arg(self, is_max: bool) -> tuple[torch.Tensor, torch.Tensor]:
         """slice kernel -> ONE all_gather of 16-byte (value, global index) pairs -> ONE combine kernel; all three are
-        enqueued on the current stream with no host synchronisation (NCCL has no arg-reduce)."""
+        enqueued on the current stream with no host synchronisation (NCCL has no arg-reduce).
+        An EMPTY vector is the reference's InvalidInput("Empty vector") on every rank alike (src/vector.rs:750-752); an
+        empty SLICE (more ranks than aligned blocks) takes part in the exchange with "no candidate"."""
         import trueno_b200 as trn
         L = trn.lib
         w = world_size()
+        if self.shard.total == 0:
+            raise trn.TruenoError.InvalidInput("Empty vector")
         if self.comm is not None:   # fused: the slice kernel exchanges the pairs itself and applies the rule
             fused = L.trn_argmax_allgather_f32_dev if is_max else L.trn_argmin_allgather_f32_dev
             trn.check(fused(self.comm.handle, self.local.data_ptr(), self.local.numel(), self.shard.start,
                             self._i64.data_ptr(), self._f32.data_ptr(), self._stream()))
+            return self._f32, self._i64
+        if w == 1:   # the whole vector is here: one launch, no combine step
+            one = L.trn_argmax_f32_dev if is_max else L.trn_argmin_f32_dev
+            trn.check(one(self.local.data_ptr(), self.local.numel(), self._i64.data_ptr(), self._f32.data_ptr(), self._stream()))
             return self._f32, self._i64
         fn = L.trn_argmax_slice_pair_f32_dev if is_max else L.trn_argmin_slice_pair_f32_dev
         trn.check(fn(self.local.data_ptr(), self.local.numel(), self.shard.start, self._pair.data_ptr(), self._stream()))
@@ -269,6 +281,8 @@ class ShardedVector:
         stream; every rank folds the same pairs in the same order, so all ranks normalise by identical bits."""
         import trueno_b200 as trn
         L = trn.lib
+        if self.shard.total == 0:
+            raise trn.TruenoError("EmptyVector")
         if out is None:
             out = torch.empty_like(self.local)
         n = self.local.numel()
@@ -293,3 +307,150 @@ class ShardedVector:
 
     def min(self) -> torch.Tensor:
         return self._arg(False)[0]
+
+
+# ---- row-block sharded matrices (matmul by C row blocks, matvec by row blocks) -----------------------------
+ROW_BLOCK = 256   # the reference's rayon unit (256-row blocks, src/matrix.rs:962-1011) == one tcgen05 CTA-pair tile of C
+
+
+class ReplicatedMatrix:
+    """A k x n f32 matrix every rank holds in full — the right-hand side of a row-block sharded product.  `prepare()`
+    keeps its tf32 (hi, lo) split in HBM (trn_gemm_prepare_b_dev), so the products of all the row blocks — and every
+    later product against it — split only their own rows of A."""
+
+    def __init__(self, data: torch.Tensor, rows: int, cols: int):
+        assert data.is_cuda and data.dtype == torch.float32 and data.is_contiguous() and data.numel() == rows * cols
+        self.data, self.rows, self.cols = data, rows, cols
+        self._handle = None
+
+    @classmethod
+    def broadcast(cls, data: "torch.Tensor | None", rows: int, cols: int, src: int = 0, device=None) -> "ReplicatedMatrix":
+        """One broadcast of B from `src` to every rank (the only large transfer of the path)."""
+        if data is None:
+            data = torch.empty(rows * cols, dtype=torch.float32, device=device)
+        if world_size() > 1:
+            dist.broadcast(data, src=src)
+        return cls(data.reshape(-1), rows, cols)
+
+    def prepare(self) -> "ReplicatedMatrix":
+        import ctypes as C
+
+        import trueno_b200 as trn
+        if self._handle is None:
+            h = C.c_void_p()
+            trn.check(trn.lib.trn_gemm_prepare_b_dev(self.data.data_ptr(), self.rows, self.cols, C.byref(h), current_stream_handle()))
+            self._handle = h
+        return self
+
+    def close(self):
+        import trueno_b200 as trn
+        if self._handle is not None:
+            trn.lib.trn_gemm_b_free(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedMatrix:
+    """This rank's block of consecutive rows of a global rows x cols f32 matrix (row-major), resident in HBM.
+    Row blocks are whole multiples of ROW_BLOCK rows (the last rank takes the ragged tail)."""
+
+    def __init__(self, local: torch.Tensor, shard: Shard, cols: int):
+        assert local.is_cuda and local.dtype == torch.float32 and local.is_contiguous() and local.numel() == shard.count * cols
+        self.local, self.shard, self.cols = local, shard, cols
+
+    @staticmethod
+    def row_shard(rows: int, rank: "int | None" = None, world: "int | None" = None) -> Shard:
+        if world is None:
+            world = world_size()
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        return shard_range(rows, rank, world, align=ROW_BLOCK)
+
+    @property
+    def rows(self) -> int:
+        return self.shard.total
+
+    def matmul(self, b: "ReplicatedMatrix", out: "torch.Tensor | None" = None) -> "ShardedMatrix":
+        """Matrix::matmul (src/matrix.rs:285) with C sharded like A: every rank multiplies its row block by the whole
+        of B — no collective, no partial sums, so every element of C is computed exactly as on one GPU (same kernel,
+        same k order: bit-identical to the unsharded product).  Error text as the reference's (src/matrix.rs:286-291)."""
+        import trueno_b200 as trn
+        L = trn.lib
+        if self.cols != b.rows:
+            raise trn.TruenoError.InvalidInput(
+                f"Matrix dimension mismatch for multiplication: {self.rows}\u00d7{self.cols} \u00d7 {b.rows}\u00d7{b.cols} "
+                f"(inner dimensions {self.cols} and {b.rows} must match)")
+        m = self.shard.count
+        if out is None:
+            out = torch.empty(m * b.cols, dtype=torch.float32, device=self.local.device)
+        if m > 0 and b.cols > 0:
+            if b._handle is not None:
+                trn.check(L.trn_matmul_prepared_f32_dev(self.local.data_ptr(), m, self.cols, b._handle, out.data_ptr(),
+                                                        current_stream_handle()))
+            else:
+                trn.check(L.trn_matmul_f32_dev(self.local.data_ptr(), m, self.cols, b.data.data_ptr(), b.rows, b.cols,
+                                               out.data_ptr(), current_stream_handle()))
+        return ShardedMatrix(out, self.shard, b.cols)
+
+    def matvec(self, v: torch.Tensor, out: "torch.Tensor | None" = None) -> "ShardedVector":
+        """Matrix::matvec (src/matrix.rs:1657; its rayon path splits the rows, :1676-1716): y = A v with v replicated and y
+        sharded like the rows of A — no collective.  Returns the ShardedVector of this rank's rows of y."""
+        import trueno_b200 as trn
+        if v.numel() != self.cols:
+            raise trn.TruenoError.InvalidInput(
+                f"Vector length {v.numel()} does not match matrix columns {self.cols} for matrix-vector multiplication")
+        m = self.shard.count
+        if out is None:
+            out = torch.empty(m, dtype=torch.float32, device=self.local.device)
+        if m > 0:
+            trn.check(trn.lib.trn_matvec_f32_dev(self.local.data_ptr(), m, self.cols, v.data_ptr(), v.numel(), out.data_ptr(),
+                                                 current_stream_handle()))
+        return ShardedVector(out, self.shard)
+
+    def gather(self) -> torch.Tensor:
+        """all_gather of the row blocks (the optional last step of section 8e): the whole matrix on every rank."""
+        w = world_size()
+        if w == 1:
+            return self.local.reshape(self.shard.count, self.cols)
+        blocks = [torch.empty(self.row_shard(self.rows, r, w).count * self.cols, dtype=torch.float32, device=self.local.device)
+                  for r in range(w)]
+        dist.all_gather(blocks, self.local.reshape(-1))
+        return torch.cat(blocks).reshape(self.rows, self.cols)
+
+
+def gather_vector(v: "ShardedVector") -> torch.Tensor:
+    """all_gather of the slices of a sharded vector (ragged slices allowed)."""
+    w = world_size()
+    if w == 1:
+        return v.local
+    sizes = torch.zeros(w, dtype=torch.int64, device=v.local.device)
+    sizes[dist.get_rank()] = v.local.numel()
+    dist.all_reduce(sizes)
+    parts = [torch.empty(int(n), dtype=torch.float32, device=v.local.device) for n in sizes.tolist()]
+    dist.all_gather(parts, v.local)
+    return torch.cat(parts)
+
+
+# ---- CUDA graphs for launch-bound inner loops --------------------------------------------------------------------------
+class CapturedLoop:
+    """`iters` back-to-back calls of `fn` (C-ABI `_dev` launches, fused peer exchanges and NCCL collectives on the current
+    stream) captured ONCE into a CUDA graph; replay() is one graph launch.  At 8 GPUs a sharded map or row kernel runs for
+    ~20 us — shorter than the host takes to issue the next call — so the per-rank launch sequence goes into a graph
+    (the Blackwell-native replacement for a tracing compiler: streams and graphs).  `fn` must not allocate or synchronise."""
+
+    def __init__(self, fn, iters: int):
+        self.iters = iters
+        fn()                                   # warm-up outside capture: lazy workspaces, NCCL channels
+        torch.cuda.current_stream().synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream(), capture_error_mode="relaxed"):
+            for _ in range(iters):
+                fn()
+
+    def replay(self):
+        self.graph.replay()
