@@ -407,7 +407,12 @@ def run_ours(args) -> int:
     del c
     torch.cuda.empty_cache()
 
-    def timed(fn, iters=20, graph=True, sync_ranks=True):
+    rank_ms: list[list[float]] = []   # N > 1: per-rank ms of every sharded timing, in call order (the spread behind each max)
+
+    def timed(fn, iters=20, graph=True, sync_ranks=True, target_ms=4.0):
+        """ms per call.  The loop (graph replay or plain) first runs back to back until the GPU has been busy for a few
+        milliseconds — an idle B200 drops to a few hundred MHz and takes about a millisecond to come back, longer than a
+        whole sharded loop — and the timed repetitions follow WITHOUT a host synchronisation in between."""
         if graph:
             loop = par.CapturedLoop(fn, iters)
             run = loop.replay
@@ -415,30 +420,44 @@ def run_ours(args) -> int:
             def run():
                 for _ in range(iters):
                     fn()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
         run()
+        p1.record(stream)
+        torch.cuda.synchronize()
+        est = max(p0.elapsed_time(p1), 1e-3)                 # one loop, cold
+        reps = int(min(50, max(1, math.ceil(target_ms / est))))
+        if sync_ranks and world > 1:                         # the same repetition count on every rank (exchange steps!)
+            t = torch.tensor([reps], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            reps = int(t.item())
+            barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(reps):                                # warm: clocks up, caches and NVLink mappings touched
+            run()
+        s0.record(stream)
+        for _ in range(reps):
+            run()
+        s1.record(stream)
         if sync_ranks:
             barrier()
-        else:
-            torch.cuda.synchronize()
-        best = float("inf")
-        for _ in range(2):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(stream)
-            run()
-            s1.record(stream)
-            if sync_ranks:
-                barrier()
-                best = min(best, max_over_ranks(s0.elapsed_time(s1)) / iters)
-            else:
-                torch.cuda.synchronize()
-                best = min(best, s0.elapsed_time(s1) / iters)
-        return best
+            mine = s0.elapsed_time(s1) / (reps * iters)
+            if world > 1:
+                allr = torch.zeros(world, dtype=torch.float64, device=dev)
+                allr[rank] = mine
+                dist.all_reduce(allr)
+                rank_ms.append([round(float(v), 5) for v in allr])
+            return max_over_ranks(s0.elapsed_time(s1)) / (reps * iters)
+        torch.cuda.synchronize()
+        return s0.elapsed_time(s1) / (reps * iters)
 
     def add_line(key, metric_name, ms, work, unit_scale, bound, extra=None):
         """work / ms -> value in GB/s (unit_scale 1e6) or TFLOP/s (1e9); roofline against N x the single-GPU peak."""
         val = work / ms / unit_scale
         peak = (hbm_peak if bound == "hbm" else tf32x3_burst) * world
         e = {"key": key, "metric": metric_name, "value": val, "ms": ms, "roofline_frac": val / peak, "bound": bound}
+        if world > 1 and rank_ms:
+            e["ms_per_rank"] = rank_ms[-1]
         if bound == "hbm":
             e["roofline_frac_nominal_8TBs"] = val / (8000.0 * world)
         if extra:
@@ -856,8 +875,9 @@ def run_ours(args) -> int:
             "config": config,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": clocks, "secondary": secondary,
-            "secondary_timing": "CUDA-graph replay of 20 captured calls per line (10-call plain loops for the GEMM-family and NCCL lines), "
-                                "CUDA events, max over ranks, best of 2",
+            "secondary_timing": "CUDA-graph replay of 20 captured calls per line (plain loops for the GEMM-family and NCCL lines), repeated "
+                                "back to back for >= 4 ms of warm-up and again, without a host sync in between, for the timed region; CUDA "
+                                "events on the launching stream, max over ranks",
             "device": trn.device_info()["name"],
         }
         if config1 is not None:

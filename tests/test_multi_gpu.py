@@ -25,5 +25,6 @@ def test_sharded_path_on_all_visible_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    first = r.stderr.find("Traceback")          # the first rank to fail, not the launcher's summary of all of them
+    assert r.returncode == 0, r.stdout[-1500:] + (r.stderr[first:first + 4000] if first >= 0 else r.stderr[-3000:])
     assert "dist_worker ok" in r.stdout

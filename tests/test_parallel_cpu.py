@@ -169,3 +169,42 @@ def test_exchange_steps_over_gloo(world):
         wmax, wmin = orc.max(a, backend=SCALAR), orc.min(a, backend=SCALAR)
         assert (np.isnan(vmax) and np.isnan(wmax)) or vmax == wmax
         assert (np.isnan(vmin) and np.isnan(wmin)) or vmin == wmin
+
+
+def _ragged_worker(rank, world, port, counts):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from trueno_b200 import parallel as par
+    par.init_distributed("gloo")
+    local = torch.arange(counts[rank], dtype=torch.float32) + 100 * rank
+    out = par._gather_ragged(local, counts)
+    want = torch.cat([torch.arange(c, dtype=torch.float32) + 100 * r for r, c in enumerate(counts)])
+    assert torch.equal(out, want), (out, want)
+    # the host-side contract of the sharded containers: an EMPTY sharded vector is the reference's error on every rank
+    # alike (src/vector.rs:750-752, :1517-1519), before anything is launched or exchanged
+    import trueno_b200 as trn
+    empty = par.ShardedVector.__new__(par.ShardedVector)
+    empty.local, empty.shard, empty.comm = torch.empty(0), par.shard_range(0, rank, world, 4), None
+    for op, err in (("argmax", trn.TruenoError.InvalidInput("Empty vector")), ("min", trn.TruenoError.InvalidInput("Empty vector")),
+                    ("softmax", trn.TruenoError.EmptyVector)):
+        try:
+            getattr(empty, op)()
+            raise AssertionError(op)
+        except trn.TruenoError as e:
+            assert e == err
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [[5, 0, 2], [0, 0, 3], [4, 4]])
+def test_ragged_gather_and_empty_vector_contract_over_gloo(counts):
+    """ShardedMatrix.gather / gather_vector: slices of different (and zero) lengths, one padded all_gather."""
+    world = len(counts)
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_ragged_worker, args=(r, world, port, counts)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0

@@ -58,19 +58,18 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Returns false when a peer's message did not arrive within pc.timeout_ns: the payload of that rank is then NaN bits,
 // the error words are raised for the host (the communicator is poisoned: later calls fail with GpuError before they
 // launch) and the caller writes a NaN / "no index" result — a dead or desynchronised peer is an error, never a hang.
+// `seq` = this call's number: the caller read (*pc.seq + 1) at KERNEL START (the counter only changes in the last block of a
+// call, and calls on a communicator are stream-ordered), so the tail of the kernel does not wait for that load.
 template <int NW>
-__device__ __forceinline__ bool peer_exchange(const PeerCtx& pc, const uint32_t (&mine)[NW], uint32_t (*all)[kPeerWords]) {
-    __shared__ unsigned s_seq;
+__device__ __forceinline__ bool peer_exchange(const PeerCtx& pc, unsigned seq, const uint32_t (&mine)[NW], uint32_t (*all)[kPeerWords]) {
     __shared__ int s_failed;
+    if (seq == 0) seq = 1;              // 0 is the "never written" state of a fresh mailbox
     if (threadIdx.x == 0) {
-        unsigned q = *pc.seq + 1u;
-        if (q == 0) q = 1;              // 0 is the "never written" state of a fresh mailbox
-        *pc.seq = q;
-        s_seq = q;
+        *pc.seq = seq;
         s_failed = 0;
     }
     __syncthreads();
-    const unsigned seq = s_seq, parity = seq & 1u;
+    const unsigned parity = seq & 1u;
     const int t = threadIdx.x;
     if (t < pc.world * NW) {
         const int dst = t / NW, w = t % NW;
@@ -207,6 +206,7 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
                   float* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out,
                   float* __restrict__ partial_lo, const PeerCtx pc) {
     __shared__ uint32_t s_all[kMaxPeers][kPeerWords];
+    const unsigned call_seq = pc.world > 1 ? *pc.seq + 1u : 0u;
     float acc[kUnroll], comp[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) acc[u] = comp[u] = 0.f;
@@ -260,7 +260,7 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
                 if (threadIdx.x == 0) { s_pair[0] = rh; s_pair[1] = rl; }
                 __syncthreads();
                 const uint32_t mine[2] = {__float_as_uint(s_pair[0]), __float_as_uint(s_pair[1])};
-                const bool ok = peer_exchange<2>(pc, mine, s_all);
+                const bool ok = peer_exchange<2>(pc, call_seq, mine, s_all);
                 rh = 0.f; rl = 0.f;
                 for (int r = 0; r < pc.world; ++r) pair_add(rh, rl, __uint_as_float(s_all[r][0]), __uint_as_float(s_all[r][1]));
                 if (!ok) rh = __uint_as_float(0x7FC00000u);
@@ -287,7 +287,7 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
             if (threadIdx.x == 0) s_tot = r;
             __syncthreads();
             const uint32_t mine[1] = {__float_as_uint(s_tot)};
-            const bool ok = peer_exchange<1>(pc, mine, s_all);
+            const bool ok = peer_exchange<1>(pc, call_seq, mine, s_all);
             r = 0.f;
             for (int q = 0; q < pc.world; ++q) r = ISMAX ? fmaxf(r, __uint_as_float(s_all[q][0])) : r + __uint_as_float(s_all[q][0]);
             if (!ok) r = __uint_as_float(0x7FC00000u);
@@ -356,6 +356,7 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
                  uint64_t* __restrict__ out_idx, float* __restrict__ out_val, int seed_rule,
                  uint64_t index_base, trn_arg_pair* __restrict__ out_pair, const PeerCtx pc) {
     __shared__ uint32_t s_all[kMaxPeers][kPeerWords];
+    const unsigned call_seq = pc.world > 1 ? *pc.seq + 1u : 0u;
     Best best{MAX ? -INFINITY : INFINITY, kNoIndex};
     auto visit = [&](float x, uint64_t i) { if (better<MAX>(x, best.v)) { best.v = x; best.i = i; } };
 
@@ -423,7 +424,7 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             }
             __syncthreads();
             const uint32_t mine[3] = {__float_as_uint(s_v), (uint32_t)s_i, (uint32_t)(s_i >> 32)};
-            const bool ok = peer_exchange<3>(pc, mine, s_all);
+            const bool ok = peer_exchange<3>(pc, call_seq, mine, s_all);
             if (threadIdx.x == 0 && !ok) {
                 if (out_idx) *out_idx = kNoIndex;
                 if (out_val) *out_val = __uint_as_float(0x7FC00000u);

@@ -417,23 +417,31 @@ class ShardedMatrix:
         w = world_size()
         if w == 1:
             return self.local.reshape(self.shard.count, self.cols)
-        blocks = [torch.empty(self.row_shard(self.rows, r, w).count * self.cols, dtype=torch.float32, device=self.local.device)
-                  for r in range(w)]
-        dist.all_gather(blocks, self.local.reshape(-1))
-        return torch.cat(blocks).reshape(self.rows, self.cols)
+        counts = [self.row_shard(self.rows, r, w).count * self.cols for r in range(w)]
+        return _gather_ragged(self.local.reshape(-1), counts).reshape(self.rows, self.cols)
+
+
+def _gather_ragged(local: torch.Tensor, counts: "list[int]") -> torch.Tensor:
+    """all_gather of slices of different (possibly zero) lengths: every rank pads to the longest slice, ONE
+    all_gather_into_tensor, the padding is dropped on arrival."""
+    w, longest = len(counts), max(max(counts), 1)
+    padded = torch.zeros(longest, dtype=local.dtype, device=local.device)
+    padded[:local.numel()] = local
+    everything = torch.empty(w * longest, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(everything, padded)
+    return torch.cat([everything[r * longest:r * longest + counts[r]] for r in range(w)])
 
 
 def gather_vector(v: "ShardedVector") -> torch.Tensor:
-    """all_gather of the slices of a sharded vector (ragged slices allowed)."""
+    """all_gather of the slices of a sharded vector (ragged and empty slices allowed; the partition is the one the
+    vector was sharded with: `align` elements per block)."""
     w = world_size()
     if w == 1:
         return v.local
     sizes = torch.zeros(w, dtype=torch.int64, device=v.local.device)
     sizes[dist.get_rank()] = v.local.numel()
     dist.all_reduce(sizes)
-    parts = [torch.empty(int(n), dtype=torch.float32, device=v.local.device) for n in sizes.tolist()]
-    dist.all_gather(parts, v.local)
-    return torch.cat(parts)
+    return _gather_ragged(v.local, [int(n) for n in sizes.tolist()])
 
 
 # ---- CUDA graphs for launch-bound inner loops --------------------------------------------------------------------------
