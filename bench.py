@@ -404,6 +404,7 @@ def run_ours(args) -> int:
     # ---------------------------------------------------------------------------------------------------------------
     secondary: list[dict] = []
     single: dict[str, float] = {}      # N > 1: the same op at FULL size on ONE GPU (rank 0, same run), ms
+    single_legs: list = []             # ... measured by these, on rank 0, AFTER every sharded line (the GPUs are in the same state for those)
     del c
     torch.cuda.empty_cache()
 
@@ -520,7 +521,7 @@ def run_ours(args) -> int:
         dist.all_gather(gath, got["dot"].reshape(1))
         check("fused exchange: bit-identical result on every rank", all(torch.equal(gath[0], g) for g in gath))
         trn.check(L.trn_comm_status(comm.handle))
-    if world > 1 and rank == 0:   # single-GPU leg of the strong-scaling figures: the WHOLE vector on one GPU
+    def leg_reductions():   # single-GPU leg of the strong-scaling figures: the WHOLE vector on one GPU
         fx = splitmix_u01_torch(torch, 0x5EED0005, n_total, dev).mul_(2).sub_(1)
         fy = splitmix_u01_torch(torch, 0x5EED0006, n_total, dev).mul_(2).sub_(1)
         # world_size() > 1 here, so the single-GPU kernels are called directly
@@ -532,9 +533,7 @@ def run_ours(args) -> int:
                          ("max", lambda: trn.check(L.trn_max_f32_dev(fx.data_ptr(), n_total, f1.data_ptr(), st))),
                          ("min", lambda: trn.check(L.trn_min_f32_dev(fx.data_ptr(), n_total, f1.data_ptr(), st)))):
             single[name] = timed(fn, sync_ranks=False)
-        del fx, fy
-    if world > 1:
-        dist.barrier()
+    single_legs.append(leg_reductions)
     cpu_lines: dict[str, dict] = {}
     e2e_lines: dict[str, dict] = {}
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
@@ -588,18 +587,17 @@ def run_ours(args) -> int:
     tr = amv.view(mvs.count, mv_cols)[rs_].double() @ vvec.double()
     sc = amv.view(mvs.count, mv_cols)[rs_].double().abs() @ vvec.double().abs()
     check("matvec rows vs f64", bool((((yv[rs_].double() - tr).abs()) <= 1e-5 * sc).all()))
-    if world > 1 and rank == 0:
+    def leg_matrix():
+        vfull = splitmix_u01_torch(torch, 0x5EED0008, BIG, dev).mul_(2).sub_(1)
         afull = splitmix_u01_torch(torch, SEED_A, BIG * BIG, dev)
         yfull = torch.empty(BIG, device=dev)
-        single["matvec"] = timed(lambda: trn.check(L.trn_matvec_f32_dev(afull.data_ptr(), BIG, BIG, vvec.data_ptr(), BIG, yfull.data_ptr(), st)),
+        single["matvec"] = timed(lambda: trn.check(L.trn_matvec_f32_dev(afull.data_ptr(), BIG, BIG, vfull.data_ptr(), BIG, yfull.data_ptr(), st)),
                                  sync_ranks=False)
         # and the single-GPU leg of the headline: the whole 32768^3 product on one GPU, B prepared as on every rank
         cfull = torch.empty(BIG * BIG, device=dev)
         fullm = par.ShardedMatrix(afull, par.shard_range(BIG, 0, 1, 256), BIG)
-        single["matmul"] = timed(lambda: fullm.matmul(bmat, out=cfull), iters=2, graph=False, sync_ranks=False)
-        del afull, yfull, cfull, fullm
-    if world > 1:
-        dist.barrier()
+        single["matmul"] = timed(lambda: fullm.matmul(bmat_keep[0], out=cfull), iters=2, graph=False, sync_ranks=False)
+    single_legs.append(leg_matrix)
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         rows_s = 2048
         ca, cv = amv[:rows_s * mv_cols].cpu().numpy(), vvec.cpu().numpy()
@@ -613,9 +611,11 @@ def run_ours(args) -> int:
                                          f">= 4096 rows, src/matrix.rs:1676-1716 -> OpenMP, {cores} threads), best of 3"}
         del ca, cv
     del amv, amat_mv, yv, a
-    if bmat is not None:
+    bmat_keep = [bmat if (world > 1 and rank == 0) else None]     # rank 0 keeps the prepared B for its single-GPU leg
+    if bmat is not None and bmat_keep[0] is None:
         bmat.close()
-    del b, bmat
+        del b
+    del bmat
     torch.cuda.empty_cache()
 
     # ---- config 5: row kernels and maps over 4096 x 32000 logits, rows sharded -------------------------------------------
@@ -657,7 +657,7 @@ def run_ours(args) -> int:
             check("sigmoid vs f64", bool(((o - torch.sigmoid(xs)).abs() <= 1e-6).all()))
         else:
             check("add bit-exact", bool(torch.equal(out[rr], logits[rr] + logits2[rr])))
-    if world > 1 and rank == 0:
+    def leg_rows():
         fl, fl2 = make_logits(0, rows_total), make_logits(100003, rows_total)
         fo = torch.empty_like(fl)
         nf = fl.numel()
@@ -667,9 +667,7 @@ def run_ours(args) -> int:
                          ("sigmoid", lambda: trn.check(L.trn_sigmoid_f32_dev(fl.data_ptr(), nf, fo.data_ptr(), st))),
                          ("add", lambda: trn.check(L.trn_add_f32_dev(fl.data_ptr(), nf, fl2.data_ptr(), nf, fo.data_ptr(), st)))):
             single[name] = timed(fn, sync_ranks=False)
-        del fl, fl2, fo
-    if world > 1:
-        dist.barrier()
+    single_legs.append(leg_rows)
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         rows_s = 256
         cl, cl2 = logits[:rows_s].cpu().numpy().reshape(-1), logits2[:rows_s].cpu().numpy().reshape(-1)
@@ -741,7 +739,7 @@ def run_ours(args) -> int:
         att_ms[causal] = ms
         add_line("attention_causal" if causal else "attention", f"fused attention 256 heads x 2048 x 128{' causal' if causal else ''} TFLOP/s",
                  ms, flop, 1e9, "tensor")
-    if world > 1 and rank == 0:
+    def leg_heads():
         fq, fk = make_heads(0, B3 * H3, 0), make_heads(0, B3 * H3, 1)
         fkt = fk.view(B3 * H3, S3, D3).transpose(1, 2).contiguous().view(-1)
         fc = torch.empty(B3 * H3 * S3 * S3, device=dev)
@@ -753,9 +751,7 @@ def run_ours(args) -> int:
         single["attention"] = timed(lambda: trn.check(L.trn_attention_f32_dev(fq.data_ptr(), fq.numel(), fk.data_ptr(), fk.numel(), fv.data_ptr(),
                                                                               fv.numel(), fo.data_ptr(), B3 * H3, S3, D3, 1.0 / D3 ** 0.5, 0, st)),
                                     iters=5, graph=False, sync_ranks=False)
-        del fq, fk, fv, fo
-    if world > 1:
-        dist.barrier()
+    single_legs.append(leg_heads)
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         heads_s = max(1, min(8, cores))
         cq = q3[:heads_s * S3 * D3].cpu().numpy()
@@ -838,6 +834,11 @@ def run_ours(args) -> int:
     # ---- strong scaling (N > 1): single-GPU time of the same full-size op (rank 0, this run) / sharded time
     strong = None
     if world > 1:
+        if rank == 0:
+            for leg in single_legs:
+                leg()
+                torch.cuda.empty_cache()
+        dist.barrier()
         sv = torch.zeros(32, dtype=torch.float64, device=dev)
         keys = ["matmul", "dot", "sum", "argmax", "norm_l2", "max", "min", "matvec", "softmax", "log_softmax", "gelu", "sigmoid", "add",
                 "batched_qkt", "attention"]

@@ -165,7 +165,9 @@ TRN_API int trn_argmin_slice_f32_dev(const float* a, size_t n, int first_slice, 
 /* Same, packed for ONE all_gather: writes {value, GLOBAL index = slice_start + local index} (index UINT64_MAX =
  * "no candidate"); slice_start == 0 carries the a[0] seed rule.  trn_arg_combine_f32_dev folds `count` gathered
  * pairs (slice 0 first) into the whole-vector answer: NaN seed wins, else best value then lowest global index
- * (NCCL has no arg-reduce: SURVEY.md 8e).  One kernel each; no host synchronisation. */
+ * (NCCL has no arg-reduce: SURVEY.md 8e).  One kernel each; no host synchronisation.  An EMPTY slice with
+ * slice_start > 0 (more ranks than aligned blocks) reports "no candidate" and still takes part in the exchange; an empty
+ * slice 0 is an empty vector: TRN_INVALID_INPUT "Empty vector". */
 typedef struct trn_arg_pair { float value; uint32_t reserved; uint64_t index; } trn_arg_pair;
 TRN_API int trn_argmax_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream);
 TRN_API int trn_argmin_slice_pair_f32_dev(const float* a, size_t n, uint64_t slice_start, trn_arg_pair* out, void* stream);
@@ -379,7 +381,9 @@ TRN_API int trn_layer_norm_rows_f32_dev(const float* a, const float* gamma, size
  * pair_out[0] = max of the slice, pair_out[1] = sum of exp(x - max) over the slice (device memory, 8-byte aligned).
  * The ranks all_gather their pairs (rank order).  Step 2, per rank: out = exp(x - M) / S or (x - M) - ln S with (M, S)
  * the fold of all `npairs` pairs, evaluated in rank order by every rank -> identical bits everywhere.  a and out must
- * share their alignment modulo 16 bytes.  Empty slice -> TRN_EMPTY_VECTOR. */
+ * share their alignment modulo 16 bytes.  An EMPTY slice (more ranks than aligned blocks) contributes the identity pair
+ * (-inf, 0) and writes nothing, so no rank drops out of the exchange; the empty-VECTOR error (src/vector.rs:1517-1519) is
+ * raised by the caller that knows the whole length. */
 TRN_API int trn_softmax_slice_stats_f32_dev(const float* a, size_t n, float* pair_out, void* stream);
 TRN_API int trn_softmax_slice_apply_f32_dev(const float* a, size_t n, const float* pairs, size_t npairs, int log_variant,
                                             float* out, void* stream);

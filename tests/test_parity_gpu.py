@@ -357,7 +357,12 @@ def test_softmax_slices_of_one_vector(trn, n, cuts):
             assert abs(g64.sum() - 1) < 1e-5
     # contract errors
     assert L.trn_softmax_slice_apply_f32_dev(x.data_ptr(), n, pairs.data_ptr(), k, 0, y.data_ptr() + 4, st) == 2   # alignments differ
-    assert L.trn_softmax_slice_stats_f32_dev(x.data_ptr(), 0, pairs.data_ptr(), st) == 3                            # EmptyVector
+    # an EMPTY slice (more ranks than aligned blocks) takes part with the identity pair; the empty-VECTOR error belongs to
+    # the caller that knows the whole length (parallel.ShardedVector.softmax)
+    assert L.trn_softmax_slice_stats_f32_dev(x.data_ptr(), 0, pairs.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert pairs[0].cpu().tolist() == [float("-inf"), 0.0]
+    assert L.trn_softmax_slice_apply_f32_dev(x.data_ptr(), 0, pairs.data_ptr(), k, 0, y.data_ptr(), st) == 0
 
 
 def test_softmax_window_kernels_match_fallback():
@@ -645,6 +650,45 @@ def test_pipelined_host_gemm_nonfinite_block(trn):
     Cg = np.asarray(hc).reshape(m, n)
     assert np.isposinf(Cg[m // 2 + 5]).all()
     assert np.isfinite(np.delete(Cg, m // 2 + 5, 0)).all()
+
+
+def test_pipelined_host_maps_match_the_unpipelined_call(trn, oracle):
+    """Pinned host slices of >= 8 M elements take the chunked three-stream pipeline (api.cu host_pipeline: H2D of chunk
+    i+1, kernel on chunk i, D2H of chunk i-1); the ops are element- / row-wise, so every bit must equal the one-shot path
+    that pageable slices take — and both must meet the op's contract against the scalar-backend oracle on a sample."""
+    n = (9 << 20) + 12          # three chunks, ragged last one
+    rng = np.random.default_rng(2024)
+    ha, hb, ho = trn.pinned_empty(n), trn.pinned_empty(n), trn.pinned_empty(n)
+    ha[:] = rng.uniform(-4, 4, n).astype(f32)
+    hb[:] = rng.uniform(-4, 4, n).astype(f32)
+    pa, pb = np.array(ha), np.array(hb)          # pageable copies
+    po = np.empty(n, f32)
+    L = trn.lib
+    for name, pinned_call, pageable_call in (
+            ("gelu", lambda: L.trn_gelu_f32(ha.ctypes.data, n, ho.ctypes.data), lambda: L.trn_gelu_f32(pa.ctypes.data, n, po.ctypes.data)),
+            ("sigmoid", lambda: L.trn_sigmoid_f32(ha.ctypes.data, n, ho.ctypes.data), lambda: L.trn_sigmoid_f32(pa.ctypes.data, n, po.ctypes.data)),
+            ("add", lambda: L.trn_add_f32(ha.ctypes.data, n, hb.ctypes.data, n, ho.ctypes.data),
+             lambda: L.trn_add_f32(pa.ctypes.data, n, pb.ctypes.data, n, po.ctypes.data)),
+            ("fma", lambda: L.trn_fma_f32(ha.ctypes.data, n, hb.ctypes.data, n, ha.ctypes.data, n, ho.ctypes.data),
+             lambda: L.trn_fma_f32(pa.ctypes.data, n, pb.ctypes.data, n, pa.ctypes.data, n, po.ctypes.data))):
+        ho[:] = np.nan
+        po[:] = np.nan
+        trn.check(pinned_call())
+        trn.check(pageable_call())
+        assert np.array_equal(np.asarray(ho), po), name
+    assert np.array_equal(po, (pa * pb + pa).astype(f32))                      # fma = a * b + c, unfused (scalar.rs:271-286)
+    # rows: 300 x 32000 logits, chunks of 131 whole rows
+    rows, cols = 300, 32000
+    hl, hr = trn.pinned_empty(rows * cols), trn.pinned_empty(rows * cols)
+    hl[:] = (rng.standard_normal(rows * cols) * 4).astype(f32)
+    pl = np.array(hl)
+    pr = np.empty(rows * cols, f32)
+    for fn in (L.trn_softmax_rows_f32, L.trn_log_softmax_rows_f32):
+        trn.check(fn(hl.ctypes.data, hr.ctypes.data, rows, cols))
+        trn.check(fn(pl.ctypes.data, pr.ctypes.data, rows, cols))
+        assert np.array_equal(np.asarray(hr), pr)
+    want = oracle.softmax_rows(pl[:2 * cols], 2, cols, log=True, backend=SCALAR)
+    assert np.all(np.abs(pr[:2 * cols].reshape(2, cols) - want) <= 4 * ulp(want) + 2.0 ** -20)
 
 
 def test_arg_combine_kernel_matches_rule(trn):

@@ -185,10 +185,74 @@ int host_arg(int is_max, const float* a, size_t n, uint64_t* out_idx, float* out
     return TRN_OK;
 }
 
+// ---- pipelined host-slice maps and row kernels ---------------------------------------------------------------------------
+// An element-wise op on host slices is two PCIe transfers around a kernel that is ~50x shorter than either of them.  From
+// pinned memory the three legs run as a pipeline over three streams, chunk by chunk — H2D of chunk i+1, kernel on chunk i,
+// D2H of chunk i-1 — so the link works in BOTH directions at once (131 M-element gelu: 19.5 -> ~10.5 ms).  `launch(off,
+// cnt, stream)` enqueues the kernel for elements [off, off + cnt) of the device copies; the op is element- or row-wise, so
+// the result is bit-identical to the unchunked call.
+struct CudaEvent {
+    cudaEvent_t e = nullptr;
+    ~CudaEvent() { if (e) cudaEventDestroy(e); }
+};
+
+template <class F>
+int host_pipeline(const float* const* inputs, int n_in, float* out, size_t n, size_t chunk, F&& launch, float* const* dev_in, float* dev_out) {
+    Context* c = ctx();
+    cudaStream_t s_main = c->stream, s_up = c->copy_stream, s_down = c->d2h_stream;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    std::vector<CudaEvent> up(nchunks), done(nchunks);
+    CudaEvent ready;
+    auto enqueue = [&]() -> int {
+        for (auto& e : up) TRN_CUDA(cudaEventCreateWithFlags(&e.e, cudaEventDisableTiming));
+        for (auto& e : done) TRN_CUDA(cudaEventCreateWithFlags(&e.e, cudaEventDisableTiming));
+        TRN_CUDA(cudaEventCreateWithFlags(&ready.e, cudaEventDisableTiming));
+        TRN_CUDA(cudaEventRecord(ready.e, s_main));            // the stream-ordered allocations are complete
+        TRN_CUDA(cudaStreamWaitEvent(s_up, ready.e, 0));
+        TRN_CUDA(cudaStreamWaitEvent(s_down, ready.e, 0));
+        for (size_t i = 0; i < nchunks; ++i) {
+            const size_t off = i * chunk, cnt = n - off < chunk ? n - off : chunk;
+            for (int k = 0; k < n_in; ++k)
+                TRN_CUDA(cudaMemcpyAsync(dev_in[k] + off, inputs[k] + off, cnt * sizeof(float), cudaMemcpyHostToDevice, s_up));
+            TRN_CUDA(cudaEventRecord(up[i].e, s_up));
+            TRN_CUDA(cudaStreamWaitEvent(s_main, up[i].e, 0));
+            TRN_TRY(launch(off, cnt, s_main));
+            TRN_CUDA(cudaEventRecord(done[i].e, s_main));
+            TRN_CUDA(cudaStreamWaitEvent(s_down, done[i].e, 0));
+            TRN_CUDA(cudaMemcpyAsync(out + off, dev_out + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, s_down));
+        }
+        return TRN_OK;
+    };
+    const int st = enqueue();
+    // the host slices are borrowed: whatever happened, nothing may still be in flight when the call returns
+    const cudaError_t e1 = cudaStreamSynchronize(s_up), e2 = cudaStreamSynchronize(s_main), e3 = cudaStreamSynchronize(s_down);
+    if (st != TRN_OK) return st;
+    TRN_CUDA(e1);
+    TRN_CUDA(e2);
+    TRN_CUDA(e3);
+    return TRN_OK;
+}
+constexpr size_t kPipeChunk = (size_t)4 << 20;   // elements per chunk: 16 MiB per operand (~0.3 ms on the link)
+
 int host_map(Map op, const float* a, const float* b, const float* c3, float* out, size_t n, float p0 = 0.f, float p1 = 0.f) {
     TRN_HOST_LOCK();
     Context* c = ctx();
     if (n == 0) return TRN_OK;
+    if (n >= 2 * kPipeChunk && is_pinned_host(a) && (!b || is_pinned_host(b)) && (!c3 || is_pinned_host(c3)) && is_pinned_host(out)) {
+        DevTemp da(c->stream), db(c->stream), dc(c->stream), dout(c->stream);
+        TRN_TRY(da.alloc(n));
+        TRN_TRY(dout.alloc(n));
+        if (b) TRN_TRY(db.alloc(n));
+        if (c3) TRN_TRY(dc.alloc(n));
+        const float* ins[3] = {a, b, c3};
+        float* devs[3] = {da.p, db.p, dc.p};
+        int n_in = 1;
+        if (b) { ins[n_in] = b; devs[n_in] = db.p; ++n_in; }
+        if (c3) { ins[n_in] = c3; devs[n_in] = dc.p; ++n_in; }
+        return host_pipeline(ins, n_in, out, n, kPipeChunk, [&](size_t off, size_t cnt, cudaStream_t s) {
+            return launch_map(op, da.p + off, b ? db.p + off : nullptr, c3 ? dc.p + off : nullptr, dout.p + off, cnt, p0, p1, s);
+        }, devs, dout.p);
+    }
     DevTemp da(c->stream), db(c->stream), dc(c->stream), dout(c->stream);
     TRN_TRY(da.alloc(n));
     TRN_TRY(dout.alloc(n));
@@ -545,6 +609,16 @@ static int host_softmax(int log_variant, const float* a, float* out, size_t rows
     DevTemp da(c->stream), dout(c->stream);
     TRN_TRY(da.alloc(n));
     TRN_TRY(dout.alloc(n));
+    // many rows from pinned memory: pipeline whole-row chunks (the row kernels for cols <= 32768 are chosen by the row
+    // length alone, so chunking the rows changes no bit)
+    const size_t rows_per_chunk = cols ? kPipeChunk / cols : 0;
+    if (cols <= 32768 && cols % 4 == 0 && rows_per_chunk >= 16 && rows >= 2 * rows_per_chunk && is_pinned_host(a) && is_pinned_host(out)) {
+        const float* ins[1] = {a};
+        float* devs[1] = {da.p};
+        return host_pipeline(ins, 1, out, n, rows_per_chunk * cols, [&](size_t off, size_t cnt, cudaStream_t s) {
+            return launch_softmax_rows(log_variant, da.p + off, dout.p + off, cnt / cols, cols, s);
+        }, devs, dout.p);
+    }
     TRN_TRY(upload(da.p, a, n, c->stream));
     TRN_TRY(launch_softmax_rows(log_variant, da.p, dout.p, rows, cols, c->stream));
     return download(out, dout.p, n, c->stream);
