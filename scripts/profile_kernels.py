@@ -33,6 +33,21 @@ def main():
         keep += [qa, qb, qc]
         ops.append(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(qa.data_ptr(), qa.numel(), qb.data_ptr(), qb.numel(),
                                                                      qc.data_ptr(), B, H, m, k, nn, st)))
+    if "fused" in which:
+        # the fused-split GEMM (no pre-pass) at a K where it is the default but the A panel is not stationary (K = 256)
+        fm, fk, fn_ = 8192, 256, 8192
+        fa, fb, fc = torch.rand(fm, fk, device="cuda"), torch.rand(fk, fn_, device="cuda"), torch.empty(fm, fn_, device="cuda")
+        keep += [fa, fb, fc]
+        ops.append(lambda: trn.check(L.trn_matmul_f32_dev(fa.data_ptr(), fm, fk, fb.data_ptr(), fk, fn_, fc.data_ptr(), st)))
+    if "slice" in which:
+        # one GPU's slice of config 4 at 8 GPUs: 2^27 elements
+        ns = 1 << 27
+        sx_ = torch.rand(ns, device="cuda") * 2 - 1
+        so_ = torch.zeros(4, device="cuda")
+        si_ = torch.zeros(2, dtype=torch.int64, device="cuda")
+        keep += [sx_, so_, si_]
+        ops += [lambda: trn.check(L.trn_sum_f32_dev(sx_.data_ptr(), ns, so_.data_ptr(), st)),
+                lambda: trn.check(L.trn_argmax_f32_dev(sx_.data_ptr(), ns, si_.data_ptr(), so_.data_ptr(), st))]
     if "reduce" in which:
         n1 = 1 << 30
         x, y = torch.rand(n1, device="cuda") * 2 - 1, torch.rand(n1, device="cuda") * 2 - 1

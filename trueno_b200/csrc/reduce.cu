@@ -15,6 +15,7 @@
 //
 // Algorithmic bytes per element: sum/max/min/argmax/argmin/norm_l2 4 B, dot 8 B; HBM-bound.
 #include <cfloat>
+#include <cstdlib>
 #include <cmath>
 
 #include "common.cuh"
@@ -547,7 +548,12 @@ template <class K>
 static int blocks_per_sm(K kernel) {
     int v = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0) != cudaSuccess) { cudaGetLastError(); v = 4; }
-    return v < 1 ? 1 : (v > 8 ? 8 : v);
+    // Four resident CTAs per SM (64 KiB of loads in flight per array) stream as fast as the six to eight that fit, and the
+    // smaller grid starts, drains and folds faster: sum over 2^30 f32 612 -> 586 us, over 2^27 (one GPU's slice at 8 GPUs)
+    // 84.6 -> 80.1 us; two CTAs are too few (676 us).  TRN_REDUCE_PER_SM overrides (scripts/exp/exp_reduce_small.py).
+    static const int cap = [] { const char* e = getenv("TRN_REDUCE_PER_SM"); const int c = e ? atoi(e) : 0; return c > 0 ? c : 4; }();
+    v = v < 1 ? 1 : (v > 8 ? 8 : v);
+    return cap < v ? cap : v;
 }
 
 int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* out, cudaStream_t s, const PeerCtx* pc) {
