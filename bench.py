@@ -713,19 +713,22 @@ def run_ours(args) -> int:
         gg = torch.Generator(device=dev)
         gg.manual_seed(0x5EED0003 + 7 * h0 + salt)
         return torch.randn(cnt * S3 * D3, device=dev, generator=gg)
+    # config 3 proper: A [B,H,m,k] and B [B,H,k,n] from the counter generator, seeds 0x5EED0003 / 4 — every rank
+    # regenerates exactly its heads of the global operands; the attention lines below use N(0,1) q / k / v
+    qa3 = splitmix_u01_torch(torch, 0x5EED0003, hsh.count * S3 * D3, dev, start=hsh.start * S3 * D3)
+    kt3 = splitmix_u01_torch(torch, 0x5EED0004, hsh.count * D3 * S3, dev, start=hsh.start * D3 * S3)
     q3, k3, v3 = make_heads(hsh.start, hsh.count, 0), make_heads(hsh.start, hsh.count, 1), make_heads(hsh.start, hsh.count, 2)
-    kt3 = k3.view(hsh.count, S3, D3).transpose(1, 2).contiguous().view(-1)
     c3 = torch.empty(hsh.count * S3 * S3, device=dev)
     flop3 = 2.0 * B3 * H3 * S3 * S3 * D3
-    ms = timed(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(q3.data_ptr(), q3.numel(), kt3.data_ptr(), kt3.numel(),
+    ms = timed(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(qa3.data_ptr(), qa3.numel(), kt3.data_ptr(), kt3.numel(),
                                                                  c3.data_ptr(), 1, hsh.count, S3, D3, S3, st)), iters=10, graph=False)
     add_line("batched_qkt", "batched_matmul_4d Q K^T 8x32x2048x128x2048 TFLOP/s", ms, flop3, 1e9, "tensor",
              {"min_time_bound_ms": {"tensor": flop3 / tf32x3_burst / 1e9 / world, "hbm": 4831838208 / hbm_peak / 1e6 / world},
               "sharding": "contiguous (batch*head) ranges over the ranks, no collective"})
     hh = hsh.count - 1
     check_rows = [0, 1000, S3 - 1]
-    tr = q3.view(hsh.count, S3, D3)[hh][check_rows].double() @ kt3.view(hsh.count, D3, S3)[hh].double()
-    sc = q3.view(hsh.count, S3, D3)[hh][check_rows].double().abs() @ kt3.view(hsh.count, D3, S3)[hh].double().abs()
+    tr = qa3.view(hsh.count, S3, D3)[hh][check_rows].double() @ kt3.view(hsh.count, D3, S3)[hh].double()
+    sc = qa3.view(hsh.count, S3, D3)[hh][check_rows].double().abs() @ kt3.view(hsh.count, D3, S3)[hh].double().abs()
     err = ((c3.view(hsh.count, S3, S3)[hh][check_rows].double() - tr).abs() / sc).max().item()
     check("batched Q K^T head rows vs f64", err <= 1e-5, f"{err:.2e}")
     del c3
@@ -740,13 +743,14 @@ def run_ours(args) -> int:
         add_line("attention_causal" if causal else "attention", f"fused attention 256 heads x 2048 x 128{' causal' if causal else ''} TFLOP/s",
                  ms, flop, 1e9, "tensor")
     def leg_heads():
-        fq, fk = make_heads(0, B3 * H3, 0), make_heads(0, B3 * H3, 1)
-        fkt = fk.view(B3 * H3, S3, D3).transpose(1, 2).contiguous().view(-1)
+        fa = splitmix_u01_torch(torch, 0x5EED0003, B3 * H3 * S3 * D3, dev)
+        fkt = splitmix_u01_torch(torch, 0x5EED0004, B3 * H3 * D3 * S3, dev)
         fc = torch.empty(B3 * H3 * S3 * S3, device=dev)
-        single["batched_qkt"] = timed(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(fq.data_ptr(), fq.numel(), fkt.data_ptr(), fkt.numel(),
+        single["batched_qkt"] = timed(lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(fa.data_ptr(), fa.numel(), fkt.data_ptr(), fkt.numel(),
                                                                                          fc.data_ptr(), B3, H3, S3, D3, S3, st)),
                                       iters=5, graph=False, sync_ranks=False)
-        del fc, fkt
+        del fc, fkt, fa
+        fq, fk = make_heads(0, B3 * H3, 0), make_heads(0, B3 * H3, 1)
         fv, fo = make_heads(0, B3 * H3, 2), torch.empty_like(fq)
         single["attention"] = timed(lambda: trn.check(L.trn_attention_f32_dev(fq.data_ptr(), fq.numel(), fk.data_ptr(), fk.numel(), fv.data_ptr(),
                                                                               fv.numel(), fo.data_ptr(), B3 * H3, S3, D3, 1.0 / D3 ** 0.5, 0, st)),
@@ -754,7 +758,7 @@ def run_ours(args) -> int:
     single_legs.append(leg_heads)
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         heads_s = max(1, min(8, cores))
-        cq = q3[:heads_s * S3 * D3].cpu().numpy()
+        cq = qa3[:heads_s * S3 * D3].cpu().numpy()
         ckt = kt3[:heads_s * S3 * D3].cpu().numpy()
         orc.set_threads(1)
         secs = best_of(lambda: orc.batched_matmul_4d(cq, ckt, 1, heads_s, S3, D3, S3), 1)
@@ -762,7 +766,7 @@ def run_ours(args) -> int:
                                     "sample": f"first {heads_s} of the 256 heads, oracle batched_matmul_4d (sequential loop over heads, each a "
                                               f"single-threaded matmul_simd: k = 128 < 1024 has no rayon path, src/matrix.rs:507-524), {secs:.2f} s"}
         del cq, ckt
-    del q3, k3, v3, kt3, o3
+    del q3, k3, v3, kt3, qa3, o3
     torch.cuda.empty_cache()
 
     # ---- config 1 (N = 1 only): the reference's own CPU-runnable case, exactly as its benches generate it -------------------
