@@ -18,7 +18,7 @@ namespace trn {
 // ---------------------------------------------------------------------------------------------
 // Host-side context (context.cu)
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxReduceBlocks = 148 * 8;   // persistent reduction grid upper bound (B200: 148 SMs)
+constexpr int kMaxReduceBlocks = 1 << 18;   // reduction grid upper bound = per-block partials in the workspace (3 MiB per stream)
 
 struct Workspace {            // one per stream: scratch for the single-launch reductions
     float*    partial_val;    // [kMaxReduceBlocks] per-block partial values

@@ -75,7 +75,9 @@ __device__ __forceinline__ bool peer_exchange(const PeerCtx& pc, unsigned seq, c
     if (t < pc.world * NW) {
         const int dst = t / NW, w = t % NW;
         const unsigned long long msg = ((unsigned long long)seq << 32) | mine[w];
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peer_slot(pc.box[dst], parity, pc.rank, w)), "l"(msg) : "memory");
+        // relaxed, not release: payload and call number are ONE word, nothing else is published through it (a
+        // st.release.sys first drains every earlier write of the block to system scope: microseconds on the tail)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(peer_slot(pc.box[dst], parity, pc.rank, w)), "l"(msg) : "memory");
     }
     if (t < pc.world * NW) {
         const int src = t / NW, w = t % NW;
@@ -85,7 +87,7 @@ __device__ __forceinline__ bool peer_exchange(const PeerCtx& pc, unsigned seq, c
         unsigned spins = 0;
         bool ok = true;
         for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
             if ((unsigned)(v >> 32) == seq) break;
             if ((++spins & 255u) == 0 && global_ns() - t0 > pc.timeout_ns) { ok = false; break; }
         }
@@ -291,11 +293,17 @@ reduce_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size
 
     if (last_block_done(ticket)) {
         // fixed-order fold of the per-block partials (gridDim.x <= kMaxReduceBlocks)
-        float r = 0.f;
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) {
-            const float q = __ldcg(partial + i);
-            r = ISMAX ? fmaxf(r, q) : r + q;
+        // (four independent chains per thread: a flat grid leaves up to 2^18 partials, and one dependent chain of L2 loads
+        // per thread would put microseconds on the tail)
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 4 * kThreads) {
+            float q[4];   // 0 is the identity of both folds (max|x| >= 0); all four loads are in flight together
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = i + u * kThreads < gridDim.x ? __ldcg(partial + i + u * kThreads) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r4[u] = ISMAX ? fmaxf(r4[u], q[u]) : r4[u] + q[u];
         }
+        float r = ISMAX ? fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3])) : (r4[0] + r4[1]) + (r4[2] + r4[3]);
         r = ISMAX ? block_max(r) : block_sum(r);
         if (pc.world > 1) {   // slice totals of every rank, folded in rank order
             __shared__ float s_tot;
@@ -372,6 +380,8 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
                  uint64_t index_base, trn_arg_pair* __restrict__ out_pair, const PeerCtx pc) {
     __shared__ uint32_t s_all[kMaxPeers][kPeerWords];
     const unsigned call_seq = pc.world > 1 ? *pc.seq + 1u : 0u;
+    // a[0] seeds the scan (seed rule); read here, not by the last block behind the fold, where its latency would be serial
+    const float seed0 = (seed_rule && n > 0 && threadIdx.x == 0) ? a[0] : 0.f;
     Best best{MAX ? -INFINITY : INFINITY, kNoIndex};
     auto visit = [&](float x, uint64_t i) { if (better<MAX>(x, best.v)) { best.v = x; best.i = i; } };
 
@@ -433,8 +443,16 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
 
     if (last_block_done(ticket)) {
         Best r{MAX ? -INFINITY : INFINITY, kNoIndex};
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads)
-            r = combine<MAX>(r, Best{__ldcg(partial_v + i), __ldcg(partial_i + i)});
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 4 * kThreads) {   // four partials in flight per thread
+            Best q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                q[u] = Best{MAX ? -INFINITY : INFINITY, kNoIndex};
+                if (i + u * kThreads < gridDim.x) q[u] = Best{__ldcg(partial_v + i + u * kThreads), __ldcg(partial_i + i + u * kThreads)};
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r = combine<MAX>(r, q[u]);
+        }
         r = block_best<MAX>(r);
         if (pc.world > 1) {
             // fused cross-slice pick: exchange (value, global index) with every rank, then apply the rule
@@ -442,7 +460,7 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             __shared__ uint64_t s_i;
             if (threadIdx.x == 0) {
                 if (seed_rule && n > 0) {
-                    const float seed = a[0];
+                    const float seed = seed0;
                     if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
                 }
                 s_v = r.v;
@@ -477,7 +495,7 @@ argreduce_kernel(const float* __restrict__ a, size_t n, float* __restrict__ part
             // seed_rule == 0: an interior slice of a sharded vector — no seed; "no candidate" is
             // reported as index ~0 so the cross-slice combine can skip it (trueno_b200/parallel.py).
             if (seed_rule && n > 0) {
-                const float seed = a[0];
+                const float seed = seed0;
                 if (seed != seed || r.i == kNoIndex) { r.v = seed; r.i = 0; }
             }
             if (out_idx) *out_idx = r.i;
@@ -542,6 +560,18 @@ static int reduce_grid(size_t n, int sm_count, int per_sm) {
     size_t cap = (size_t)sm_count * (per_sm < 1 ? 1 : per_sm);
     if (cap > (size_t)kMaxReduceBlocks) cap = kMaxReduceBlocks;
     size_t g = tiles < cap ? tiles : cap;
+    // TRN_REDUCE_FLAT = tiles per block of a FLAT grid (scripts/exp/exp_reduce_flat.py).  Measured slower at every size: a block's
+    // fold + fence + ticket is paid per block, not once per SM slot (2^27 f32: 82.6 us persistent; 86.6 / 89.0 / 178.9 us at 16 /
+    // 8 / 1 tiles per block).  Per-CTA timestamps of the persistent form (scripts/exp/exp_reduce_trace.cu, 2^27): the median CTA
+    // ends its stream at 70.0 us (7.67 TB/s), the slowest at 73.7, the result is written at 75.5 and the next kernel's first CTA
+    // starts 4.1 us later; dynamic chunk claiming and programmatic dependent launch changed none of it (79.8 -> 80.6 / 82.6 us).
+    const char* e = getenv("TRN_REDUCE_FLAT");
+    const int flat = e ? atoi(e) : 0;
+    if (flat > 0) {
+        size_t f = (tiles + flat - 1) / flat;
+        if (f > (size_t)kMaxReduceBlocks) f = kMaxReduceBlocks;
+        if (f > g) g = f;
+    }
     return (int)(g ? g : 1);
 }
 template <class K>

@@ -368,6 +368,204 @@ static int launch_ring(const float* a, float* out, size_t rows, size_t cols, uns
     return TRN_OK;
 }
 
+// ---- config-5 rows over CTA PAIRS: two half-rows in flight per SM ------------------------------------------------------
+// The ring kernel above keeps ONE row per SM in flight and all sixteen consumer warps walk its phases in lock step (shared
+// memory -> registers, max, exp, sum, store): while they compute nothing is stored, while they store nothing is computed,
+// and a launch pays a whole 128 KB row of ramp-up and of drain per SM.  Here a row belongs to a 2-CTA cluster: each CTA
+// streams ITS HALF of every row of the cluster through its own ring, and its consumer warps form two groups of eight that
+// take alternate rows — two half-rows per SM in different phases, half the ramp, half the wave quantum (512 rows on 148 SMs:
+// 6.92 half-rows per SM instead of 3.46 rows).  The two halves of a row meet ONCE: each group folds its half to an online
+// (max, sum of exp relative to it) pair and sends it to the partner CTA with one `st.async` (8 bytes + the partner's
+// mbarrier transaction count: no fence, no cluster barrier in the row loop); both CTAs fold the two pairs in rank order,
+// so they normalise by identical bits.  softmax = exp(x - m_half) * (exp(m_half - M) / S), log_softmax = (x - M) - ln S.
+namespace ring2 {
+constexpr int kGroup = 256;                        // consumer threads per group
+constexpr int kThreads2 = 2 * kGroup + 32;         // two groups + the producer warp
+constexpr int kSlotVec = 4 * kGroup;               // float4 per slot: 4 per consumer thread (16 KiB)
+constexpr uint32_t kSlotBytes = kSlotVec * 16;
+constexpr int kSlots = 14;                         // 224 KiB of ring
+constexpr int kMaxChunks = 4;                      // a half-row is <= 16 float4 per thread = 16 384 floats
+constexpr uint32_t kSmemBytes = kSlots * kSlotBytes + 2 * kSlots * 8 + 4 * 8 /*xbar*/ + 4 * 8 /*mailbox*/ + 2 * 2 * 8 * 4 /*s_max, s_sum*/ + 128;
+}  // namespace ring2
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+
+template <bool LOG>
+__global__ void __launch_bounds__(ring2::kThreads2, 1)
+softmax_rows_ring2_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols) {
+    using namespace ring2;
+    extern __shared__ uint8_t ring2_smem_raw[];
+    const uint32_t base = (smem_u32(ring2_smem_raw) + 127u) & ~127u;
+    uint8_t* gen = ring2_smem_raw + (base - smem_u32(ring2_smem_raw));
+    const uint32_t bar_base = base + kSlots * kSlotBytes;
+    auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (kSlots + s); };
+    auto xbar = [&](uint32_t g, uint32_t par) { return bar_base + 8u * (2 * kSlots + 2 * g + par); };
+    const uint32_t mbox_base = bar_base + 8u * (2 * kSlots + 4);
+    auto mbox = [&](uint32_t g, uint32_t par) { return mbox_base + 8u * (2 * g + par); };
+    uint8_t* tail = gen + kSlots * kSlotBytes + 8 * (2 * kSlots + 4);
+    const volatile float2* mbox_gen = reinterpret_cast<const volatile float2*>(tail);
+    float* s_max = reinterpret_cast<float*>(tail + 4 * 8);   // [2 groups][8 warps]
+    float* s_sum = s_max + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const size_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const size_t my_rows = rows > cluster_id ? (rows - cluster_id + num_clusters - 1) / num_clusters : 0;
+    const unsigned hv = (unsigned)(cols >> 3);                 // float4 per half-row
+    const unsigned nchunks = (hv + kSlotVec - 1) / kSlotVec;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < (uint32_t)kSlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kGroup / 32); }
+        for (uint32_t g = 0; g < 2; ++g) for (uint32_t par = 0; par < 2; ++par) mbar_init(xbar(g, par), 1);
+        fence_barrier_init();
+    }
+    // the partner's messages must not arrive before these barriers exist
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    if (warp == 2 * kGroup / 32) {
+        // ===================== producer: this CTA's half of every row of the cluster, in row order =====================
+        if (elect_one()) {
+            uint32_t slot = 0, phase = 0;
+            for (size_t i = 0; i < my_rows; ++i) {
+                const size_t row = cluster_id + i * num_clusters;
+                const char* src = reinterpret_cast<const char*>(in + row * cols) + (size_t)rank * hv * 16u;
+                const uint32_t half_bytes = hv * 16u;
+                for (unsigned j = 0; j < nchunks; ++j) {
+                    mbar_wait(empty_bar(slot), phase ^ 1);
+                    const uint32_t off = j * kSlotBytes;
+                    const uint32_t bytes = half_bytes - off < kSlotBytes ? half_bytes - off : kSlotBytes;
+                    mbar_expect_tx(full_bar(slot), bytes);
+                    bulk_load_1d(base + slot * kSlotBytes, src + off, bytes, full_bar(slot));
+                    if (++slot == (uint32_t)kSlots) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== consumers: group g takes the cluster's rows g, g + 2, g + 4, ... =====================
+        const uint32_t g = (uint32_t)warp >> 3;
+        const int t = (int)threadIdx.x - (int)g * kGroup;
+        const int gw = warp & 7;
+        float* gmax = s_max + g * 8;
+        float* gsum = s_sum + g * 8;
+        const uint32_t partner = rank ^ 1u;
+        const uint32_t n_mine = (uint32_t)my_rows;
+        for (uint32_t i = g, k = 0; i < n_mine; i += 2, ++k) {
+            const size_t row = cluster_id + (size_t)i * num_clusters;
+            float4 x[4 * kMaxChunks];
+            // ---- ring -> registers; each slot goes back to the producer as soon as this group has read it
+#pragma unroll
+            for (int j = 0; j < kMaxChunks; ++j) {
+                if ((unsigned)j < nchunks) {
+                    const uint32_t cnt = i * nchunks + (uint32_t)j;      // position of this chunk in the producer's order
+                    const uint32_t slot = cnt % (uint32_t)kSlots, phase = (cnt / (uint32_t)kSlots) & 1u;
+                    mbar_wait(full_bar(slot), phase);
+                    const uint32_t sb = base + slot * kSlotBytes;
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const unsigned v = j * kSlotVec + h * kGroup + t;
+                        float4 r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                        if (v < hv)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sb + (h * kGroup + t) * 16u));
+                        x[4 * j + h] = r;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_bar(slot));
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) x[4 * j + h] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                }
+            }
+            // ---- this half's max: warp tree, then a fixed-order fold of the group's 8 warp values in every thread
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4 * kMaxChunks; ++j) m = fmaxf(m, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+            m = warp_max(m);
+            if (lane == 0) gmax[gw] = m;
+            named_bar_sync(1 + g, kGroup);
+            m = gmax[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) m = fmaxf(m, gmax[w]);
+            // ---- exponentials relative to THIS half's max and their sum (padding holds -inf -> exactly 0).  A half that is
+            // all -inf must contribute (max -inf, sum 0), not exp(-inf - -inf) = NaN: its exponentials are taken relative to 0
+            // (the row is NaN only when BOTH halves are -inf, through exp(m - M) below, as the reference's whole-row form is)
+            const float mref = m == -INFINITY ? 0.f : m;
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4 * kMaxChunks; ++j) {
+                float4 e;
+                e.x = expf(x[j].x - mref); e.y = expf(x[j].y - mref); e.z = expf(x[j].z - mref); e.w = expf(x[j].w - mref);
+                part += (e.x + e.y) + (e.z + e.w);
+                if (!LOG) x[j] = e;
+            }
+            part = warp_sum(part);
+            if (lane == 0) gsum[gw] = part;
+            named_bar_sync(1 + g, kGroup);
+            float sum = gsum[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) sum += gsum[w];
+            // ---- one exchange with the other half of the row: (m, sum) in one 8-byte st.async to the partner's mailbox
+            const uint32_t par = k & 1u, xphase = (k >> 1) & 1u;
+            if (t == 0) {
+                mbar_expect_tx(xbar(g, par), 8);
+                const unsigned long long msg = ((unsigned long long)__float_as_uint(sum) << 32) | __float_as_uint(m);
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                             :: "r"(mapa_u32(mbox(g, par), partner)), "l"(msg), "r"(mapa_u32(xbar(g, par), partner)) : "memory");
+            }
+            mbar_wait(xbar(g, par), xphase);
+            const float2 other = make_float2(mbox_gen[2 * g + par].x, mbox_gen[2 * g + par].y);   // {max, sum} of the other half
+            // fold in rank order: both CTAs of the pair get the same bits
+            const float m0 = rank == 0 ? m : other.x, s0 = rank == 0 ? sum : other.y;
+            const float m1 = rank == 0 ? other.x : m, s1 = rank == 0 ? other.y : sum;
+            const float M = fmaxf(m0, m1);
+            const float S = s0 * expf(m0 - M) + s1 * expf(m1 - M);
+            const float lse = LOG ? logf(S) : 0.f;
+            const float f = LOG ? 0.f : expf(m - M) / S;
+            float4* dst = reinterpret_cast<float4*>(out + row * cols) + (size_t)rank * hv;
+#pragma unroll
+            for (int j = 0; j < 4 * kMaxChunks; ++j) {
+                const unsigned v = j * kGroup + t;   // = (j / 4) * kSlotVec + (j % 4) * kGroup + t
+                if (v < hv) st_stream(dst + v, normalise4<LOG>(x[j], M, lse, f));
+            }
+            // every thread of the group has read the mailbox before its leader can announce the next row on this parity
+            named_bar_sync(1 + g, kGroup);
+        }
+    }
+    // neither CTA may leave while its partner can still write into its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool LOG>
+static int launch_ring2(const float* a, float* out, size_t rows, size_t cols, int sm_count, cudaStream_t s) {
+    static const cudaError_t attr = cudaFuncSetAttribute(softmax_rows_ring2_kernel<LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)ring2::kSmemBytes);   // thread-safe, once
+    TRN_CUDA(attr);
+    const size_t max_clusters = (size_t)sm_count / 2;
+    const size_t waves = (rows + max_clusters - 1) / max_clusters;       // even waves, as for the ring kernel
+    const size_t clusters = waves ? (rows + waves - 1) / waves : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(ring2::kThreads2);
+    cfg.dynamicSmemBytes = ring2::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    TRN_CUDA(cudaLaunchKernelEx(&cfg, softmax_rows_ring2_kernel<LOG>, a, out, rows, cols));
+    count_launch();
+    return TRN_OK;
+}
+
 // ---- short rows: one WARP per row -------------------------------------------------------------------------
 // cols <= 1024 (attention-sized rows): a row is VPT float4 per lane, RPW rows per warp are loaded up front
 // (RPW * VPT = 8 independent 128-bit loads in flight per lane), all statistics are warp shuffles — no block
@@ -904,6 +1102,11 @@ static int env_int(const char* name) {   // tuning knob for scripts/exp/exp_long
     const char* e = getenv(name);
     return e ? atoi(e) : 0;
 }
+static int env_int_default(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+constexpr int kRing2Default = 0;   // the CTA-pair ring kernel is opt-in until it has beaten the single-CTA ring on the part
 
 template <bool LOG, bool WIN>
 static int launch_long(int cs, const float* a, float* out, size_t rows, size_t cols, unsigned mis0, cudaStream_t s) {
@@ -942,6 +1145,11 @@ static int dispatch_vec(const float* a, float* out, size_t rows, size_t cols, un
     //     8 beyond, 4 again from 786 432 (rows that no longer fit L2 between the passes).
     const int force_cs = env_int("TRN_ROWS_LONG_CS");
     const int force_hpc = env_int("TRN_RING_HPC");   // experiment knobs, read per call
+    // TRN_RING2 (experiment knob, read per call): 1 forces the CTA-pair ring for aligned rows of 28 672 < cols <= 32 768
+    // with cols % 8 == 0, 0 keeps the single-CTA ring
+    const int ring2_mode = env_int_default("TRN_RING2", kRing2Default);
+    if (!force_cs && !force_hpc && !WIN && ring2_mode && cols > 28672 && cols <= 32768 && cols % 8 == 0)
+        return launch_ring2<LOG>(a, out, rows, cols, sm_count, s);
     if (!force_cs && (force_hpc || (!WIN && cols > 28672)) && nvec <= (size_t)ring::kRowVec) {
         // softmax: 32 KiB slots (7 of them) beat 16 KiB ones by 2-5 % in every run (5.98-6.15 vs 5.67-6.06 TB/s at
         // 32 000 columns).  log_softmax is bimodal with 32 KiB slots from one box visit to the next (5.56-5.68 or
