@@ -839,7 +839,10 @@ def run_ours(args) -> int:
     strong = None
     if world > 1:
         if rank == 0:
-            for leg in single_legs:
+            # the whole 32768^3 product (seconds of tensor work at the power cap) goes LAST: run before the row legs it left
+            # the SMs clocked down, and the issue-sensitive kernels (softmax, gelu) measured 30-37 % slow on one GPU — which
+            # inflated their speed-ups (8.2x / 9.7x where the driver's own N = 1 run gives 5.9x / 7.5x)
+            for leg in sorted(single_legs, key=lambda f: f.__name__ == "leg_matrix"):
                 leg()
                 torch.cuda.empty_cache()
         dist.barrier()

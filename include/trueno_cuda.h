@@ -460,6 +460,19 @@ TRN_API int trn_matmul_prepared_f32_dev(const float* a, size_t a_rows, size_t a_
 /* host-slice twin: A and C are host slices (pinned ones are pipelined by row blocks), B stays resident in HBM */
 TRN_API int trn_matmul_prepared_f32(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* b, float* c);
 
+/* ---- row blocks of ONE product (sharded Matrix::matmul) ------------------------------------------
+ * src/matrix.rs:962-1011 cuts C into 256-row blocks over rayon workers; every block runs the same dot loop, so the
+ * parallel product carries the bits of the sequential one.  Here `a` holds block_rows consecutive rows of an A with
+ * total_rows rows (one rank's share), `c` receives the same rows of C, and the kernel is chosen as trn_matmul_f32_dev
+ * chooses it for the WHOLE total_rows x a_cols x b_cols product — not by the block's own height, which would send a
+ * short last block to another kernel (other rounding) and a 1-row block into the vecmat special case.  Gathered row
+ * blocks == the unsharded product, bit for bit.  Errors: the reference's dimension-mismatch text on (total_rows,
+ * a_cols) x (b_rows, b_cols); block_rows > total_rows is InvalidInput. */
+TRN_API int trn_matmul_rowblock_f32_dev(const float* a, size_t block_rows, size_t total_rows, size_t a_cols, const float* b,
+                                        size_t b_rows, size_t b_cols, float* c, void* stream);
+TRN_API int trn_matmul_rowblock_prepared_f32_dev(const float* a, size_t block_rows, size_t total_rows, size_t a_cols,
+                                                 const trn_gemm_b* b, float* c, void* stream);
+
 /* ---- GEMM engine selection (measurement and tests) ------------------------------------------
  * The dispatcher picks the tcgen05 3xTF32 kernel for shapes that fill its tiles and the SIMT
  * FFMA kernel for small/skinny ones.  Tests and bench.py can force one engine to compare them

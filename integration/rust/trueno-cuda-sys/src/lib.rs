@@ -270,6 +270,11 @@ extern "C" {
     pub fn trn_matmul_prepared_f32_dev(a: *const f32, a_rows: usize, a_cols: usize, b: *const trn_gemm_b, c: *mut f32,
                                        stream: *mut c_void) -> c_int;
     pub fn trn_matmul_prepared_f32(a: *const f32, a_rows: usize, a_cols: usize, b: *const trn_gemm_b, c: *mut f32) -> c_int;
+    // row blocks of one sharded product: kernel chosen as for the whole total_rows-row product (bit-identical gather)
+    pub fn trn_matmul_rowblock_f32_dev(a: *const f32, block_rows: usize, total_rows: usize, a_cols: usize, b: *const f32,
+                                       b_rows: usize, b_cols: usize, c: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn trn_matmul_rowblock_prepared_f32_dev(a: *const f32, block_rows: usize, total_rows: usize, a_cols: usize,
+                                                b: *const trn_gemm_b, c: *mut f32, stream: *mut c_void) -> c_int;
     // device-resident op chaining (GpuCommandBatch counterpart, src/backends/gpu/batch.rs)
     pub fn trn_batch_create(out: *mut *mut trn_batch) -> c_int;
     pub fn trn_batch_destroy(batch: *mut trn_batch) -> c_int;

@@ -72,6 +72,18 @@ def test_validation_errors_match_reference(trn):
     with pytest.raises(E) as e:
         M.from_vec(2, 3, np.ones(6)).matvec(V.from_slice([1, 2]))
     assert e.value.message == "Vector length 2 does not match matrix columns 3 for matrix-vector multiplication"
+    # row blocks of a sharded product: the mismatch text names the WHOLE matrix (src/matrix.rs:286-291), and a block
+    # cannot be taller than it — both checked before any device work
+    L = trn.lib
+    with pytest.raises(E) as e:
+        trn.check(L.trn_matmul_rowblock_f32_dev(None, 2, 8, 3, None, 2, 2, None, None))
+    assert e.value.message == "Matrix dimension mismatch for multiplication: 8×3 × 2×2 (inner dimensions 3 and 2 must match)"
+    with pytest.raises(E) as e:
+        trn.check(L.trn_matmul_rowblock_f32_dev(None, 9, 8, 3, None, 3, 2, None, None))
+    assert e.value.variant == "InvalidInput" and e.value.message == "row block of 9 rows exceeds the 8 rows of the matrix"
+    with pytest.raises(E) as e:
+        trn.check(L.trn_matmul_rowblock_prepared_f32_dev(None, 9, 8, 3, None, None, None))
+    assert e.value.message == "row block of 9 rows exceeds the 8 rows of the matrix"
 
 
 def test_compute_fails_loudly_without_gpu(trn):

@@ -751,3 +751,51 @@ def test_cuda_path_against_committed_golden(trn):
     assert abs(float(vs.sum()) - gs[0]) <= 2e-5 * asum and abs(float(vs.dot(vt)) - gs[1]) <= 2e-5 * asum
     assert abs(float(vs.norm_l2()) - gs[2]) <= 2e-5 * gs[2]
     assert [vs.argmax(), vs.argmin()] == g["splitmix_slice_argmax_argmin"].tolist()
+
+
+# ---- row blocks of one product (sharded Matrix::matmul, src/matrix.rs:962-1011) -------------------------------------------
+# The reference's parallel product is bit-identical to its sequential one (every 256-row block runs the same dot loop).
+# trn_matmul_rowblock_* pick the kernel by the WHOLE product's shape, so that holds here for ANY block heights — including
+# a 44-row tail (which alone would route to the SIMT kernel), a 1-row block (alone: the vecmat special case), short K
+# (fused-split kernels), long K (pre-pass kernels), and a product small enough for the SIMT kernel.
+@pytest.mark.parametrize("m,k,n,cuts", [
+    (1324, 640, 512, [0, 256, 512, 768, 1024, 1280, 1324]),      # the 8-rank partition of tests/dist_worker.py
+    (1324, 128, 768, [0, 1, 45, 300, 1279, 1324]),               # K <= 128: A-stationary fused kernel; a 1-row block
+    (700, 256, 260, [0, 100, 228, 229, 700]),                    # fused kernel, blocks below one 128-row tile
+    (96, 64, 80, [0, 1, 50, 96]),                                # whole product on the SIMT kernel
+    (2048, 1024, 1024, [0, 1024, 1920, 2047, 2048]),
+], ids=["prepass-8rank", "astat-1row", "fused-short", "simt", "prepass-1row"])
+def test_row_blocks_carry_the_bits_of_the_whole_product(trn, m, k, n, cuts):
+    import ctypes as C
+    import torch
+    L = trn.lib
+    stream = torch.cuda.Stream()                      # (torch's default stream has handle 0 = "the backend's own stream")
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream                           # the calls are ordered with torch's own work on this stream
+    g = torch.Generator(device="cuda"); g.manual_seed(m * 31 + k)
+    a = torch.rand(m, k, device="cuda", generator=g) * 2 - 1
+    b = torch.rand(k, n, device="cuda", generator=g) * 2 - 1
+    whole = torch.empty(m, n, device="cuda")
+    trn.check(L.trn_matmul_f32_dev(a.data_ptr(), m, k, b.data_ptr(), k, n, whole.data_ptr(), st))
+    h = C.c_void_p()
+    trn.check(L.trn_gemm_prepare_b_dev(b.data_ptr(), k, n, C.byref(h), st))
+    try:
+        for prepared in (False, True):
+            got = torch.full((m, n), float("nan"), device="cuda")
+            for r0, r1 in zip(cuts[:-1], cuts[1:]):
+                blk = a[r0:r1].contiguous()
+                out = torch.empty(r1 - r0, n, device="cuda")
+                if prepared:
+                    trn.check(L.trn_matmul_rowblock_prepared_f32_dev(blk.data_ptr(), r1 - r0, m, k, h, out.data_ptr(), st))
+                else:
+                    trn.check(L.trn_matmul_rowblock_f32_dev(blk.data_ptr(), r1 - r0, m, k, b.data_ptr(), k, n, out.data_ptr(), st))
+                got[r0:r1] = out
+            torch.cuda.synchronize()
+            assert torch.equal(got, whole), (prepared, (got != whole).nonzero()[:4].tolist())
+    finally:
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        trn.check(L.trn_gemm_b_free(h))
+    truth = a.double() @ b.double()
+    scale = a.double().abs() @ b.double().abs()
+    assert bool(((whole.double() - truth).abs() <= 1e-5 * scale).all())

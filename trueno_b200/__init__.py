@@ -128,6 +128,8 @@ _SIGNATURES = {
     "trn_gemm_prepare_b_dev": [_vp, _sz, _sz, C.POINTER(_vp), _vp], "trn_gemm_b_free": [_vp],
     "trn_matmul_prepared_f32_dev": [_vp, _sz, _sz, _vp, _vp, _vp],
     "trn_matmul_prepared_f32": [_vp, _sz, _sz, _vp, _vp],
+    "trn_matmul_rowblock_f32_dev": [_vp, _sz, _sz, _sz, _vp, _sz, _sz, _vp, _vp],
+    "trn_matmul_rowblock_prepared_f32_dev": [_vp, _sz, _sz, _sz, _vp, _vp, _vp],
     "trn_set_gemm_engine": [C.c_int], "trn_get_gemm_engine": [],
     "trn_profile_enable": [C.c_int], "trn_profile_last_gemm": [_f32p, _f32p],
 }

@@ -121,21 +121,23 @@ namespace {
 // the device (north star: unconditional, no thresholds that fall back to the CPU) and only picks
 // WHICH device kernel: rows == 1 -> vecmat (reference quirk preserved); tiles that fill a tcgen05
 // tile -> 3xTF32; the rest -> SIMT FFMA.
+// route_m != 0: `a` holds a row block of a product with route_m rows, and the kernel is picked as for that whole product.
 int gemm_dispatch(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
-                  cudaStream_t s) {
+                  cudaStream_t s, size_t route_m = 0) {
     if (batch == 0 || m == 0 || n == 0) return TRN_OK;
-    if (m == 1 && k > 0) {
+    const size_t mr = route_m ? route_m : m;
+    if (mr == 1 && k > 0) {
         for (size_t i = 0; i < batch; ++i) TRN_TRY(launch_vecmat(a + i * k, b + i * k * n, k, n, c + i * n, s));
         return TRN_OK;
     }
     const int engine = g_engine.load();
     if (engine == 1) return launch_gemm_simt(a, b, c, batch, m, k, n, s);
     if (engine == 2 || engine == 3) {
-        if (!gemm_tc_supported(m, k, n))
-            return fail(TRN_INVALID_INPUT, "tcgen05 GEMM engine forced for an unsupported shape %zux%zux%zu", m, k, n);
-        return launch_gemm_tc(a, b, c, batch, m, k, n, engine == 2 ? 3 : 1, s);
+        if (!gemm_tc_supported(mr, k, n))
+            return fail(TRN_INVALID_INPUT, "tcgen05 GEMM engine forced for an unsupported shape %zux%zux%zu", mr, k, n);
+        return launch_gemm_tc(a, b, c, batch, m, k, n, engine == 2 ? 3 : 1, s, route_m);
     }
-    if (gemm_auto_uses_tc(m, k, n)) return launch_gemm_tc(a, b, c, batch, m, k, n, 3, s);
+    if (gemm_auto_uses_tc(mr, k, n)) return launch_gemm_tc(a, b, c, batch, m, k, n, 3, s, route_m);
     return launch_gemm_simt(a, b, c, batch, m, k, n, s);
 }
 
@@ -472,20 +474,22 @@ int trn_gemm_b_free(trn_gemm_b* h) {
     return TRN_OK;
 }
 
-int trn_matmul_prepared_f32_dev(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* bh, float* c, void* stream) {
-    if (!bh) return fail(TRN_INVALID_INPUT, "trn_matmul_prepared_f32_dev: null B handle");
+static int matmul_prepared_dev(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* bh, float* c, void* stream,
+                               size_t route_m, const char* who) {
+    if (!bh) return fail(TRN_INVALID_INPUT, "%s: null B handle", who);
     TRN_TRY(check_matmul(a_rows, a_cols, bh->k, bh->n));
     TRN_TRY(need_ctx());
     cudaStream_t s = resolve_stream(stream);
     const size_t m = a_rows, k = a_cols, n = bh->n;
+    const size_t mr = route_m ? route_m : m;
     if (k == 0 && m * n > 0) {
         TRN_CUDA(cudaMemsetAsync(c, 0, m * n * sizeof(float), s));
         return TRN_OK;
     }
     // the same routing as trn_matmul_f32_dev; only the pre-pass tensor-core product has something to reuse
     const int engine = g_engine.load();
-    const bool tc3 = m > 1 && (engine == 2 || (engine == 0 && gemm_auto_uses_tc(m, k, n)));
-    if (!bh->split || !tc3 || gemm_tc_uses_fused(a, bh->b, m, k, n)) return gemm_dispatch(a, bh->b, c, 1, m, k, n, s);
+    const bool tc3 = mr > 1 && (engine == 2 || (engine == 0 && gemm_auto_uses_tc(mr, k, n)));
+    if (!bh->split || !tc3 || gemm_tc_uses_fused(a, bh->b, mr, k, n)) return gemm_dispatch(a, bh->b, c, 1, m, k, n, s, route_m);
     const size_t kpad = gemm_tc_kpad(k);
     float* scratch = nullptr;
     TRN_TRY(scratch_alloc((void**)&scratch, 2 * m * kpad * sizeof(float) + 256, s));
@@ -495,11 +499,43 @@ int trn_matmul_prepared_f32_dev(const float* a, size_t a_rows, size_t a_cols, co
     gemm_profile_begin(s);
     if (st == TRN_OK) st = gemm_tc_split_a(a, scratch, scratch + m * kpad, 1, m, k, flag, s);
     gemm_profile_mid(s);
-    if (st == TRN_OK) st = gemm_tc_main(scratch, scratch + m * kpad, bh->split, bh->split + n * kpad, c, 1, m, k, n, 3, flag, s);
+    if (st == TRN_OK) st = gemm_tc_main(scratch, scratch + m * kpad, bh->split, bh->split + n * kpad, c, 1, m, k, n, 3, flag, s, route_m);
     gemm_profile_end(s);
     if (st == TRN_OK) st = launch_gemm_simt(a, bh->b, c, 1, m, k, n, s, flag);
     scratch_free(scratch, s);
     return st;
+}
+int trn_matmul_prepared_f32_dev(const float* a, size_t a_rows, size_t a_cols, const trn_gemm_b* bh, float* c, void* stream) {
+    return matmul_prepared_dev(a, a_rows, a_cols, bh, c, stream, 0, "trn_matmul_prepared_f32_dev");
+}
+
+// ---- row blocks of one product (Matrix::matmul sharded by C row blocks, src/matrix.rs:962-1011) ----------------
+// `a` holds block_rows consecutive rows of an A with total_rows rows.  The kernel family is chosen as trn_matmul_f32_dev
+// chooses it for the WHOLE product, whatever the block's own height (44 rows of a 1324-row product stay on the tensor
+// cores, one row of it does not become the vecmat special case): every kernel computes a row of C with the same
+// arithmetic in whichever tile the row lies, so the gathered row blocks are bit-identical to the unsharded product.
+static int check_rowblock(size_t block_rows, size_t total_rows) {
+    if (block_rows > total_rows)
+        return fail(TRN_INVALID_INPUT, "row block of %zu rows exceeds the %zu rows of the matrix", block_rows, total_rows);
+    return TRN_OK;
+}
+int trn_matmul_rowblock_f32_dev(const float* a, size_t block_rows, size_t total_rows, size_t a_cols, const float* b, size_t b_rows,
+                                size_t b_cols, float* c, void* stream) {
+    TRN_TRY(check_matmul(total_rows, a_cols, b_rows, b_cols));
+    TRN_TRY(check_rowblock(block_rows, total_rows));
+    TRN_TRY(need_ctx());
+    cudaStream_t s = resolve_stream(stream);
+    if (a_cols == 0 && block_rows * b_cols > 0) {
+        TRN_CUDA(cudaMemsetAsync(c, 0, block_rows * b_cols * sizeof(float), s));
+        return TRN_OK;
+    }
+    return gemm_dispatch(a, b, c, 1, block_rows, a_cols, b_cols, s, total_rows);
+}
+int trn_matmul_rowblock_prepared_f32_dev(const float* a, size_t block_rows, size_t total_rows, size_t a_cols, const trn_gemm_b* bh,
+                                         float* c, void* stream) {
+    TRN_TRY(check_rowblock(block_rows, total_rows));
+    if (block_rows == 0) return TRN_OK;
+    return matmul_prepared_dev(a, block_rows, a_cols, bh, c, stream, total_rows, "trn_matmul_rowblock_prepared_f32_dev");
 }
 
 // host-slice twin: A and C are host slices, B stays resident.  Pinned slices of large tensor-core products are pipelined

@@ -141,15 +141,18 @@ int launch_layer_norm_rows(const float* a, const float* gamma, const float* beta
 int launch_gemm_simt(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
                      cudaStream_t s, const int* only_if_flag = nullptr);
 // tcgen05 path; terms = 3 (3xTF32, fp32-accurate) or 1 (plain TF32, probe only)
+// route_m != 0: `a` is a ROW BLOCK of a product with route_m rows; the kernel family is chosen as for the whole product
+// (every kernel computes a row of C with the same arithmetic whatever tile it falls in, so the block's rows then carry
+// the bits the unsharded product gives them)
 int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n,
-                   int terms, cudaStream_t s);
+                   int terms, cudaStream_t s, size_t route_m = 0);
 bool gemm_tc_supported(size_t m, size_t k, size_t n);
 // the three phases of launch_gemm_tc, exposed so the host-slice path can pipeline them with transfers
 size_t gemm_tc_kpad(size_t k);
 int gemm_tc_split_a(const float* a, float* a_hi, float* a_lo, size_t batch, size_t m, size_t k, int* flag, cudaStream_t s);
 int gemm_tc_split_b(const float* b, float* b_hi, float* b_lo, size_t batch, size_t k, size_t n, int* flag, cudaStream_t s);
 int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* c, size_t batch,
-                 size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s);
+                 size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s, size_t route_m = 0);
 // fused-split variant (no pre-pass, raw operands; gemm_tc.cu): preconditions + default rule, and the kernel itself
 bool gemm_tc_uses_fused(const float* a, const float* b, size_t m, size_t k, size_t n);
 int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int* flag,

@@ -1255,7 +1255,7 @@ int gemm_tc_split_b(const float* b, float* b_hi, float* b_lo, size_t batch, size
 
 // C[b] = A[b] * B[b] from pre-split operands.  The tensor-core kernel returns at once when *flag != 0.
 int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* c, size_t batch,
-                 size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s) {
+                 size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s, size_t route_m) {
     using namespace tc;
     Context* cx = ctx();
     if (!cx) return TRN_GPU_ERROR;
@@ -1264,7 +1264,7 @@ int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const 
     // CTA-pair kernel (cta_group::2) for 3xTF32 whenever there are at least two 128-row tiles of C;
     // TRN_GEMM_PAIR=0 forces the single-CTA kernel (A/B measurements, and its own parity tests).
     static const int use_pair = [] { const char* e = getenv("TRN_GEMM_PAIR"); return e ? atoi(e) : 1; }();
-    if (terms == 3 && use_pair && m > (size_t)BM) {
+    if (terms == 3 && use_pair && (route_m ? route_m : m) > (size_t)BM) {   // (a short row block of a tall product keeps the pair kernel)
         CUtensorMap pa_h, pa_l, pb_h, pb_l, pc;
         TRN_TRY(make_map(&pa_h, a_hi, batch, m, kpad, BM, pair::SBK));
         TRN_TRY(make_map(&pa_l, a_lo, batch, m, kpad, BM, pair::SBK));
@@ -1427,14 +1427,14 @@ int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, s
 }
 
 int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_t m, size_t k, size_t n, int terms,
-                   cudaStream_t s) {
+                   cudaStream_t s, size_t route_m) {
     Context* cx = ctx();
     if (!cx) return TRN_GPU_ERROR;
     if (batch == 0 || m == 0 || n == 0) return TRN_OK;
     const size_t kpad = gemm_tc_kpad(k);
     const size_t a_elems = batch * m * kpad, b_elems = batch * n * kpad;
 
-    if (terms == 3 && gemm_tc_uses_fused(a, b, m, k, n)) {
+    if (terms == 3 && gemm_tc_uses_fused(a, b, route_m ? route_m : m, k, n)) {
         // no pre-pass, no operand scratch: only the 4-byte non-finite flag the splitter warps may raise
         int* flag = nullptr;
         TRN_TRY(scratch_alloc((void**)&flag, 256, s));
@@ -1462,7 +1462,7 @@ int launch_gemm_tc(const float* a, const float* b, float* c, size_t batch, size_
     int st = gemm_tc_split_a(a, a_hi, a_lo, batch, m, k, flag, s);
     if (st == TRN_OK) st = gemm_tc_split_b(b, b_hi, b_lo, batch, k, n, flag, s);
     gemm_profile_mid(s);
-    if (st == TRN_OK) st = gemm_tc_main(a_hi, a_lo, b_hi, b_lo, c, batch, m, k, n, terms, flag, s);
+    if (st == TRN_OK) st = gemm_tc_main(a_hi, a_lo, b_hi, b_lo, c, batch, m, k, n, terms, flag, s, route_m);
     gemm_profile_end(s);
     // IEEE fallback for Inf/NaN inputs: runs only when the flag is set (checked on the device)
     if (st == TRN_OK) st = launch_gemm_simt(a, b, c, batch, m, k, n, s, flag);

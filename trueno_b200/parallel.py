@@ -377,8 +377,8 @@ class ShardedMatrix:
 
     def matmul(self, b: "ReplicatedMatrix", out: "torch.Tensor | None" = None) -> "ShardedMatrix":
         """Matrix::matmul (src/matrix.rs:285) with C sharded like A: every rank multiplies its row block by the whole
-        of B — no collective, no partial sums, so every element of C is computed exactly as on one GPU (same kernel,
-        same k order: bit-identical to the unsharded product).  Error text as the reference's (src/matrix.rs:286-291)."""
+        of B — no collective, no partial sums, so every element of C is computed exactly as on one GPU (the kernel the
+        WHOLE product would take, same k order: bit-identical to the unsharded product whatever the block heights).  Error text as the reference's (src/matrix.rs:286-291)."""
         import trueno_b200 as trn
         L = trn.lib
         if self.cols != b.rows:
@@ -389,12 +389,14 @@ class ShardedMatrix:
         if out is None:
             out = torch.empty(m * b.cols, dtype=torch.float32, device=self.local.device)
         if m > 0 and b.cols > 0:
+            # the row-block entry points pick the kernel by the WHOLE product's shape, so a short last block (or a one-row
+            # block) does not fall to another kernel and another rounding
             if b._handle is not None:
-                trn.check(L.trn_matmul_prepared_f32_dev(self.local.data_ptr(), m, self.cols, b._handle, out.data_ptr(),
-                                                        current_stream_handle()))
+                trn.check(L.trn_matmul_rowblock_prepared_f32_dev(self.local.data_ptr(), m, self.rows, self.cols, b._handle,
+                                                                 out.data_ptr(), current_stream_handle()))
             else:
-                trn.check(L.trn_matmul_f32_dev(self.local.data_ptr(), m, self.cols, b.data.data_ptr(), b.rows, b.cols,
-                                               out.data_ptr(), current_stream_handle()))
+                trn.check(L.trn_matmul_rowblock_f32_dev(self.local.data_ptr(), m, self.rows, self.cols, b.data.data_ptr(), b.rows,
+                                                        b.cols, out.data_ptr(), current_stream_handle()))
         return ShardedMatrix(out, self.shard, b.cols)
 
     def matvec(self, v: torch.Tensor, out: "torch.Tensor | None" = None) -> "ShardedVector":
