@@ -40,9 +40,22 @@ def run(name, fn, secs=3.0):
 
 trn.set_gemm_engine(2)
 B, H, m, k, n = 8, 32, 2048, 128, 2048
-a = torch.rand(B * H * m * k, device="cuda"); b = torch.rand(B * H * k * n, device="cuda"); c = torch.empty(B * H * m * n, device="cuda")
-run("batched4d", lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), c.data_ptr(), B, H, m, k, n, st)))
-del a, b, c
+import os
+for kind in ("U[0,1)", "N(0,1)"):
+    a = torch.rand(B * H * m * k, device="cuda") if kind[0] == "U" else torch.randn(B * H * m * k, device="cuda")
+    b = torch.rand(B * H * k * n, device="cuda") if kind[0] == "U" else torch.randn(B * H * k * n, device="cuda")
+    c = torch.empty(B * H * m * n, device="cuda")
+    f = lambda: trn.check(L.trn_batched_matmul_4d_f32_dev(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), c.data_ptr(), B, H, m, k, n, st))
+    run(f"batched4d {kind} sustained 3 s", f)
+    # burst: one call at a time from an idle-ish GPU (2 ms pause), best and median of 30
+    ts = []
+    for _ in range(30):
+        time.sleep(0.002)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f(); e0.record(); f(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print(f"batched4d {kind} burst (pairs of calls after a 2 ms pause, 2nd timed): best {min(ts):.3f} median {statistics.median(ts):.3f} ms")
+    del a, b, c
 N = 8192
 a = torch.rand(N * N, device="cuda"); b = torch.rand(N * N, device="cuda"); c = torch.empty(N * N, device="cuda")
 run("matmul 8192", lambda: trn.check(L.trn_matmul_f32_dev(a.data_ptr(), N, N, b.data_ptr(), N, N, c.data_ptr(), st)))
