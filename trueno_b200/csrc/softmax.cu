@@ -216,19 +216,32 @@ static int launch_cta(const float* a, float* out, size_t rows, size_t cols, unsi
 }
 
 // ---- TMA ring kernel -----------------------------------------------------------------------------------
+static int env_int_default(const char* name, int dflt) {   // experiment knobs, read per call
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 namespace ring {
 constexpr int kConsumers = 512;                 // 16 consumer warps
 constexpr int kRingThreads = kConsumers + 32;   // + 1 producer warp
 constexpr int kRowVec = 16 * kConsumers;        // a row is <= 16 float4 per consumer thread = 32 768 floats
 constexpr uint32_t kRingBytes = 224 * 1024;     // the ring: 28 / HPC slots of HPC * 8 KiB (HPC float4 per consumer thread per slot)
-constexpr uint32_t kSmemBytes = kRingBytes + 2 * 28 * 8 + 2 * 16 * 4 + 128;
+constexpr int kRowQueue = 8;                    // row numbers handed from the producer to the consumers (it runs < 3 rows ahead)
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+constexpr uint32_t kSmemBytes = kRingBytes + 2 * 28 * 8 + 2 * 16 * 4 + kRowQueue * 4 + 128;
 }  // namespace ring
 
 // WIN: the producer bulk-copies the aligned body of each row; the (up to six) edge elements are read from global
 // memory by consumer threads 0..5.
+// Rows are CLAIMED, not dealt: after its first row (blockIdx.x) a CTA's producer takes the next unclaimed row from a counter
+// in the stream's workspace (`claim[0]`, offset by the grid size; `claim[1]` counts CTAs that are done, the last one zeroes
+// both for the next launch) and hands the row number to the consumers through a small queue in shared memory.  The SMs do
+// not stream at one pace; with dealt rows the slowest SM ends the kernel microseconds after the median one, with claimed rows
+// the SMs end together.  A row's result does not depend on which CTA computes it, so nothing changes bit-wise.
+// claim == nullptr: rows dealt round-robin (blockIdx.x + i * gridDim.x).
 template <bool LOG, bool WIN, int HPC>
 __global__ void __launch_bounds__(ring::kRingThreads, 1)
-softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0) {
+softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, size_t cols, unsigned mis0,
+                         unsigned* __restrict__ claim) {
     using namespace ring;
     constexpr int kChunkVec = HPC * kConsumers;
     constexpr uint32_t kChunkBytes = kChunkVec * 16;
@@ -242,6 +255,7 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
     auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (kSlots + s); };
     float* s_max = reinterpret_cast<float*>(gen + kSlots * kChunkBytes + 2 * kSlots * 8);
     float* s_sum = s_max + 16;
+    volatile uint32_t* s_rowq = reinterpret_cast<volatile uint32_t*>(s_sum + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -254,8 +268,17 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
     if (warp == kConsumers / 32) {
         // ===================== producer: one elected lane streams rows into the ring =====================
         if (elect_one()) {
-            uint32_t slot = 0, phase = 0;
-            for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+            uint32_t slot = 0, phase = 0, seq = 0;
+            size_t row = blockIdx.x;
+            for (;; ++seq) {
+                if (row >= rows) {
+                    // no row left: a queue entry that says so, published by completing the next slot's phase without data
+                    s_rowq[seq % kRowQueue] = kNoRow;
+                    mbar_wait(empty_bar(slot), phase ^ 1);
+                    mbar_arrive(full_bar(slot));
+                    break;
+                }
+                s_rowq[seq % kRowQueue] = (uint32_t)row;     // ordered before the row's first full-barrier arrive (release)
                 const RowView<WIN> rv(in, out, row, cols, mis0);
                 const unsigned nvec = (unsigned)rv.nvec;
                 const unsigned nchunks = (nvec + kChunkVec - 1) / kChunkVec;
@@ -269,6 +292,12 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
                     bulk_load_1d(base + slot * kChunkBytes, src + off, bytes, full_bar(slot));
                     if (++slot == (uint32_t)kSlots) { slot = 0; phase ^= 1; }
                 }
+                // the next row: claimed while this one is still landing (the atomic's round trip hides under the ring)
+                row = claim ? (size_t)gridDim.x + atomicAdd(&claim[0], 1u) : row + gridDim.x;
+            }
+            if (claim && atomicAdd(&claim[1], 1u) == gridDim.x - 1) {   // every CTA has made its last claim: reset for the next launch
+                claim[0] = 0;
+                claim[1] = 0;
             }
         }
         return;
@@ -277,7 +306,11 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
     // ===================== consumers =====================
     const int t = threadIdx.x;
     uint32_t slot = 0, phase = 0;
-    for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    for (uint32_t seq = 0;; ++seq) {
+        mbar_wait(full_bar(slot), phase);              // the next row's first chunk, or the "no row left" entry
+        const uint32_t qrow = s_rowq[seq % kRowQueue];
+        if (qrow == kNoRow) break;
+        const size_t row = qrow;
         const RowView<WIN> rv(in, out, row, cols, mis0);
         const unsigned nvec = (unsigned)rv.nvec;
         const unsigned nchunks = (nvec + kChunkVec - 1) / kChunkVec;
@@ -361,8 +394,17 @@ static int launch_ring(const float* a, float* out, size_t rows, size_t cols, uns
     // rows (4096 rows sharded over 8 GPUs) run as 128 CTAs x 4 rows instead of 148 CTAs of which 68 take a 4th row while 80
     // idle; a single SM's ring can absorb the bandwidth the idle ones leave (~60 vs 42 GB/s per SM).
     const size_t waves = (rows + (size_t)sm_count - 1) / (size_t)sm_count;
-    const unsigned grid = (unsigned)(waves ? (rows + waves - 1) / waves : 1);
-    softmax_rows_ring_kernel<LOG, WIN, HPC><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols, mis0);
+    unsigned grid = (unsigned)(waves ? (rows + waves - 1) / waves : 1);
+    // claimed rows (default; TRN_RING_DYN=0 deals them): one CTA per SM, the counters live behind the stream's reduction ticket
+    unsigned* claim = nullptr;
+    if (env_int_default("TRN_RING_DYN", 1) && rows < 0xFFFFFFFFull - 1024) {
+        Workspace* w = workspace(s);
+        if (w) {
+            claim = w->ticket + 4;
+            grid = (unsigned)(rows < (size_t)sm_count ? rows : (size_t)sm_count);
+        }
+    }
+    softmax_rows_ring_kernel<LOG, WIN, HPC><<<grid, ring::kRingThreads, ring::kSmemBytes, s>>>(a, out, rows, cols, mis0, claim);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
@@ -1101,10 +1143,6 @@ static bool force_generic() {
 static int env_int(const char* name) {   // tuning knob for scripts/exp/exp_long_rows.py; 0 = unset
     const char* e = getenv(name);
     return e ? atoi(e) : 0;
-}
-static int env_int_default(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
 }
 constexpr int kRing2Default = 0;   // the CTA-pair ring kernel is opt-in until it has beaten the single-CTA ring on the part
 
