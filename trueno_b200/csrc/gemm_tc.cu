@@ -42,6 +42,10 @@
 
 #include <cstdlib>
 
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -83,6 +87,7 @@ struct Params {
     uint32_t store_hint;      // fused kernels: 1 = C stores carry an L2 evict_first policy (C much larger than L2)
     uint32_t debug;           // fused kernels, experiments (TRN_GEMM_DEBUG): bit 0 skip the C stores, bit 1 aim every store at batch 0
     uint32_t terms_mask;      // fused kernel, debugging: bit 0 lo*hi, bit 1 hi*lo, bit 2 hi*hi (7 = the product)
+    unsigned long long* trace;  // A-stationary kernel, experiments (TRN_GEMM_TRACE): per-CTA %globaltimer at entry / exit
 };
 
 // Tile order: batch-major, then groups of 16 m-tiles, n fastest-but-one inside a group, so CTAs
@@ -878,6 +883,11 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
     }
     tc_fence_before();
     cluster_sync_all();
+    if (p.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[2 * blockIdx.x] = t;
+    }
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -999,6 +1009,11 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
+        if (p.trace && warp == 4 && lane == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[2 * blockIdx.x + 1] = t;
+        }
     }
 
     tc_fence_before();
@@ -1383,6 +1398,10 @@ int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, s
     p.debug = debug_bits;
     static const int hint_on = [] { const char* e = getenv("TRN_GEMM_STORE_HINT"); return e ? atoi(e) : 1; }();
     p.store_hint = (hint_on && batch * m * n * sizeof(float) > ((size_t)64 << 20)) ? 1u : 0u;
+    static const int trace_on = [] { const char* e = getenv("TRN_GEMM_TRACE"); return e ? atoi(e) : 0; }();
+    static unsigned long long* trace_buf = nullptr;
+    if (trace_on && !trace_buf) cudaMalloc(&trace_buf, 2 * 1024 * sizeof(unsigned long long));
+    p.trace = trace_on ? trace_buf : nullptr;
     static const cudaError_t smem_optin = cudaFuncSetAttribute(gemm_tf32x3_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::kSmemBytes);
     TRN_CUDA(smem_optin);
     static const cudaError_t smem_optin2 = cudaFuncSetAttribute(gemm_tf32x3_fused_astat_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, astat::kSmemBytes);
@@ -1423,6 +1442,18 @@ int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, s
     if (use_astat) TRN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused_astat_pair_kernel, ma, mb, mc, p, flag));
     else TRN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_fused_pair_kernel, ma, mb, mc, p, flag));
     count_launch();
+    if (p.trace && use_astat && trace_on > 1) {   // experiments only (TRN_GEMM_TRACE=2): when did every CTA finish?
+        cudaStreamSynchronize(s);
+        std::vector<unsigned long long> h(4 * pairs);
+        cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (uint32_t i = 0; i < 2 * pairs; ++i) t0 = h[2 * i] < t0 ? h[2 * i] : t0;
+        std::vector<double> st, en;
+        for (uint32_t i = 0; i < 2 * pairs; ++i) { st.push_back((h[2 * i] - t0) * 1e-3); en.push_back((h[2 * i + 1] - t0) * 1e-3); }
+        std::sort(st.begin(), st.end()); std::sort(en.begin(), en.end());
+        fprintf(stderr, "[gemm trace] %u CTAs: start max %.1f us; end min %.1f p10 %.1f median %.1f p90 %.1f max %.1f us\n", 2 * pairs,
+                st.back(), en.front(), en[en.size() / 10], en[en.size() / 2], en[en.size() * 9 / 10], en.back());
+    }
     return TRN_OK;
 }
 
