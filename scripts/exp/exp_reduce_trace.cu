@@ -22,6 +22,50 @@ __global__ void __launch_bounds__(kThreads) sum_kernel(const float* __restrict__
     if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const unsigned long long t0 = gns();
+    if (MODE == 3) {
+        // order-free reductions (max / min / arg): chunks are claimed, the accumulators simply carry on — no per-chunk fold.
+        // The next claim is fetched one chunk ahead; the only block-wide step per chunk is one barrier that publishes it.
+        __shared__ unsigned s_nx[2];
+        const size_t nvec = n >> 2;
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const unsigned ntiles = (unsigned)(nvec / kTileVec), nchunks = (ntiles + chunk - 1) / chunk;
+        float acc[kUnroll] = {0.f,0.f,0.f,0.f};
+        unsigned c = blockIdx.x, it = 0;
+        if (threadIdx.x == 0) s_nx[0] = atomicAdd(claim, 1u) + gridDim.x;
+        while (c < nchunks) {
+            const unsigned t_end = min(ntiles, (c + 1) * chunk);
+            for (unsigned t = c * chunk; t < t_end; ++t) {
+                const size_t base = (size_t)t * kTileVec + threadIdx.x;
+                float4 x[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) x[u] = ld_stream(a4 + base + u * kThreads);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) acc[u] = fmaxf(acc[u], fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
+            }
+            __syncthreads();
+            c = s_nx[it & 1];
+            ++it;
+            if (threadIdx.x == 0 && c < nchunks) s_nx[it & 1] = atomicAdd(claim, 1u) + gridDim.x;
+        }
+        const unsigned long long t1 = gns();
+        float r = block_sum(fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3])));
+        if (threadIdx.x == 0) partial[blockIdx.x] = r;
+        __shared__ bool s_last3;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned t = atomicAdd(ticket, 1u); s_last3 = (t == gridDim.x - 1); if (s_last3) { *ticket = 0; *claim = 0; } }
+        __syncthreads();
+        const unsigned long long t2 = gns();
+        if (threadIdx.x == 0) { ts[3 * blockIdx.x] = t0; ts[3 * blockIdx.x + 1] = t1; ts[3 * blockIdx.x + 2] = t2; }
+        if (s_last3) {
+            __threadfence();
+            float r4 = 0.f;
+            for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) r4 = fmaxf(r4, __ldcg(partial + i));
+            float rr = block_sum(r4);
+            if (threadIdx.x == 0) { *out = rr; ts[3 * gridDim.x] = gns(); }
+        }
+        return;
+    }
     if (MODE == 2) {
         __shared__ unsigned s_next[2];
         const size_t nvec = n >> 2;
@@ -156,7 +200,8 @@ int main(int argc, char** argv) {
         cfg.attrs = at; cfg.numAttrs = 1;
         if (mode == 0) CK(cudaLaunchKernelEx(&cfg, sum_kernel<0>, (const float*)a, n, partial, ticket, out, ts, pdl, chunk, claim));
         else if (mode == 1) CK(cudaLaunchKernelEx(&cfg, sum_kernel<1>, (const float*)a, n, partial, ticket, out, ts, pdl, chunk, claim));
-        else CK(cudaLaunchKernelEx(&cfg, sum_kernel<2>, (const float*)a, n, partial, ticket, out, ts, pdl, chunk, claim));
+        else if (mode == 2) CK(cudaLaunchKernelEx(&cfg, sum_kernel<2>, (const float*)a, n, partial, ticket, out, ts, pdl, chunk, claim));
+        else CK(cudaLaunchKernelEx(&cfg, sum_kernel<3>, (const float*)a, n, partial, ticket, out, ts, pdl, chunk, claim));
     };
     for (int i = 0; i < 20; ++i) launch();
     CK(cudaDeviceSynchronize());
