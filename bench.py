@@ -798,6 +798,29 @@ def run_ours(args) -> int:
                                     "d2h_bytes_per_step": 4 * hc.size, "ms": secs * 1e3,
                                     "api": "trn_batched_matmul_4d_f32 (host slices, pinned; PCIe-bound on the 4 GiB of products)"}
         del hq, hk, hc, c3b
+        # fused attention: the reference's CPU spelling of the same heads (transpose + matmul, scale, softmax per row, matmul:
+        # oracle.attention, one thread per its scalar / AVX2 operators) on ONE head, and the host-slice call on all 256
+        q1, k1, v1 = (t_[:S3 * D3].cpu().numpy() for t_ in (q3, k3, v3))
+        orc.set_threads(1)
+        for causal in (0, 1):
+            secs = best_of(lambda: orc.attention(q1, k1, v1, 1, S3, D3, causal=bool(causal)), 1)
+            key = "attention_causal" if causal else "attention"
+            cpu_lines[key] = {"value": 4.0 * S3 * S3 * D3 * (0.5 if causal else 1.0) / secs / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": "port",
+                              "sample": f"1 of the 256 heads, oracle.attention (the reference's CPU composition: Matrix::transpose + matmul_simd, "
+                                        f"scale, Vector::softmax per row, matmul_simd; single thread: k = 128 / 2048 rows have no rayon path), {secs:.2f} s"}
+        hq, hk, hv, ho_ = (trn.pinned_empty(q3.numel()) for _ in range(4))
+        torch.from_numpy(hq).copy_(q3); torch.from_numpy(hk).copy_(k3); torch.from_numpy(hv).copy_(v3)
+        for causal in (0, 1):
+            fn = lambda: trn.check(L.trn_attention_f32(hq.ctypes.data, hq.size, hk.ctypes.data, hk.size, hv.ctypes.data, hv.size, ho_.ctypes.data,
+                                                       B3 * H3, S3, D3, 1.0 / D3 ** 0.5, causal))
+            fn()
+            secs = best_of(fn, 2)
+            key = "attention_causal" if causal else "attention"
+            e2e_lines[key] = {"value": 4.0 * B3 * H3 * S3 * S3 * D3 * (0.5 if causal else 1.0) / secs / 1e12, "unit": "TFLOP/s",
+                              "h2d_bytes_per_step": 4 * 3 * hq.size, "d2h_bytes_per_step": 4 * ho_.size, "ms": secs * 1e3,
+                              "api": "trn_attention_f32 (host slices, pinned)"}
+        check("attention e2e == resident result (causal)", bool(np.array_equal(np.asarray(ho_), o3.cpu().numpy())))
+        del hq, hk, hv, ho_
     del q3, k3, v3, kt3, qa3, o3
     torch.cuda.empty_cache()
 
