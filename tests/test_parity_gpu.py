@@ -848,3 +848,27 @@ def test_ring_kernel_claimed_rows_equal_dealt_rows(trn):
             os.environ.pop("TRN_RING_DYN", None)
         else:
             os.environ["TRN_RING_DYN"] = old
+
+
+def test_ring_kernel_on_two_streams_at_once(trn):
+    """The claim counters of the ring kernel live in the per-STREAM workspace: two streams running config-5 rows at the same
+    time (their persistent CTAs interleave on the SMs) must not take rows from each other."""
+    import torch
+    L = trn.lib
+    rows, cols = 700, 32000
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    x1 = torch.randn(rows, cols, device="cuda", generator=g) * 4
+    x2 = torch.randn(rows, cols, device="cuda", generator=g) * 4
+    y1, y2 = torch.full_like(x1, float("nan")), torch.full_like(x2, float("nan"))
+    r1, r2 = torch.empty_like(x1), torch.empty_like(x2)
+    torch.cuda.synchronize()
+    trn.check(L.trn_softmax_rows_f32_dev(x1.data_ptr(), r1.data_ptr(), rows, cols, s1.cuda_stream))
+    torch.cuda.synchronize()
+    trn.check(L.trn_log_softmax_rows_f32_dev(x2.data_ptr(), r2.data_ptr(), rows, cols, s1.cuda_stream))
+    torch.cuda.synchronize()
+    for _ in range(10):
+        trn.check(L.trn_softmax_rows_f32_dev(x1.data_ptr(), y1.data_ptr(), rows, cols, s1.cuda_stream))
+        trn.check(L.trn_log_softmax_rows_f32_dev(x2.data_ptr(), y2.data_ptr(), rows, cols, s2.cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(y1, r1) and torch.equal(y2, r2)
