@@ -351,15 +351,19 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
 #pragma unroll
         for (int w = 1; w < kConsumers / 32; ++w) m = fmaxf(m, s_max[w]);
 
-        // ---- exponentials and their sum.  Padding slots hold -inf -> expf(-inf) = 0 exactly.
-        float part = 0.f;
+        // ---- exponentials and their sum.  Padding slots hold -inf -> expf(-inf) = 0 exactly.  The sum is a TREE at every
+        // level (four interleaved chains per thread, shuffle tree, pairwise fold of the warp sums): the row sum's rounding
+        // error lands on every element of the row, and a 16-long chain per thread plus a 16-long chain over the warps put the
+        // worst element of a 16 M-element input at 9.5 ulp where the 8-ulp contract allows expf's own 2 ulp little company.
+        float part4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < HPC * kMaxChunks; ++j) {
             float4 e;
             e.x = expf(x[j].x - m); e.y = expf(x[j].y - m); e.z = expf(x[j].z - m); e.w = expf(x[j].w - m);
-            part += (e.x + e.y) + (e.z + e.w);
+            part4[j & 3] += (e.x + e.y) + (e.z + e.w);
             if (!LOG) x[j] = e;
         }
+        float part = (part4[0] + part4[1]) + (part4[2] + part4[3]);
         if (WIN) {
             const float ee = expf(xe - m);
             part += ee;
@@ -368,9 +372,15 @@ softmax_rows_ring_kernel(const float* __restrict__ in, float* __restrict__ out, 
         part = warp_sum(part);
         if (lane == 0) s_sum[warp] = part;
         named_bar_sync(1, kConsumers);
-        float sum = s_sum[0];
+        float ws[kConsumers / 32];
 #pragma unroll
-        for (int w = 1; w < kConsumers / 32; ++w) sum += s_sum[w];
+        for (int w = 0; w < kConsumers / 32; ++w) ws[w] = s_sum[w];
+#pragma unroll
+        for (int step = 1; step < kConsumers / 32; step *= 2) {
+#pragma unroll
+            for (int w = 0; w + step < kConsumers / 32; w += 2 * step) ws[w] += ws[w + step];
+        }
+        const float sum = ws[0];
         // (after THIS barrier every thread has read s_max; s_sum is rewritten after the next row's max barrier.)
 
         // ---- scale and store straight from registers (512 contiguous bytes per warp per store)
