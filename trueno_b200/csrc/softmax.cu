@@ -400,9 +400,10 @@ static int launch_ring(const float* a, float* out, size_t rows, size_t cols, uns
     static const cudaError_t attr = cudaFuncSetAttribute(softmax_rows_ring_kernel<LOG, WIN, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)ring::kSmemBytes);   // thread-safe, once
     TRN_CUDA(attr);
-    // Even waves: every persistent CTA walks ceil(rows / SMs) rows, so the grid is the smallest one that still does — 512
-    // rows (4096 rows sharded over 8 GPUs) run as 128 CTAs x 4 rows instead of 148 CTAs of which 68 take a 4th row while 80
-    // idle; a single SM's ring can absorb the bandwidth the idle ones leave (~60 vs 42 GB/s per SM).
+    // Dealt rows (TRN_RING_DYN=0, or no workspace) go out in even waves: every persistent CTA walks ceil(rows / SMs) rows, so
+    // the grid is the smallest one that still does — 512 rows (4096 rows sharded over 8 GPUs) run as 128 CTAs x 4 rows instead
+    // of 148 CTAs of which 68 take a 4th row while 80 idle; a single SM's ring can absorb the bandwidth the idle ones leave
+    // (~60 vs 42 GB/s per SM).
     const size_t waves = (rows + (size_t)sm_count - 1) / (size_t)sm_count;
     unsigned grid = (unsigned)(waves ? (rows + waves - 1) / waves : 1);
     // claimed rows (default; TRN_RING_DYN=0 deals them): one CTA per SM, the counters live behind the stream's reduction ticket
