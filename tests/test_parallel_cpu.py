@@ -208,3 +208,37 @@ def test_ragged_gather_and_empty_vector_contract_over_gloo(counts):
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
+
+
+def _peer_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from trueno_b200 import parallel as par
+    comm = par.PeerComm.try_create()          # no GPU here: no rank can export a mailbox
+    raised = False
+    try:
+        par.PeerComm()
+    except Exception:
+        raised = True
+    dist.barrier()                             # both ranks got here: nobody was left inside a collective
+    if rank == 0:
+        results.put((comm is None, raised))
+    dist.destroy_process_group()
+
+
+def test_peer_comm_fails_on_every_rank_together_without_a_gpu():
+    """PeerComm's constructor keeps every rank inside the same collectives whatever fails locally, so a box without a P2P
+    path (here: without a GPU) yields the same error on all ranks — `try_create()` returns None and the sharded reductions
+    fall back to the NCCL exchange — instead of one rank raising while the others wait in an all_gather."""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the fused path is exercised by the -m gpu tests")
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() == (True, True)

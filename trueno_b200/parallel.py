@@ -158,18 +158,46 @@ class PeerComm:
         if not (dist.is_initialized() and dist.get_world_size() > 1):
             raise RuntimeError("PeerComm needs an initialised process group with world_size > 1")
         rank, world = dist.get_rank(), dist.get_world_size()
+        self._h = None
+        on_gpu = dist.get_backend() == "nccl"
+        # Every rank takes part in both collectives below whatever happened locally, and all ranks fail TOGETHER: a rank
+        # that cannot export or map a mailbox (no P2P path to a peer) must not leave the others waiting in a collective.
         buf = (C.c_ubyte * 64)()
-        trn.check(trn.lib.trn_comm_local_handle(buf))
-        mine = torch.tensor(list(buf), dtype=torch.uint8)
-        if dist.get_backend() == "nccl":
+        err = None
+        try:
+            trn.check(trn.lib.trn_comm_local_handle(buf))
+        except trn.TruenoError as e:
+            err = e
+        mine = torch.tensor(list(buf) + [0 if err is None else 1], dtype=torch.uint8)
+        if on_gpu:
             mine = mine.cuda()
-        gathered = torch.empty(64 * world, dtype=torch.uint8, device=mine.device)
+        gathered = torch.empty(65 * world, dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(gathered, mine)
-        handles = bytes(gathered.cpu().numpy().tobytes())
+        table = gathered.cpu().numpy().reshape(world, 65)
         h = C.c_void_p()
-        trn.check(trn.lib.trn_comm_create(rank, world, handles, C.byref(h)))
+        if err is None and not table[:, 64].any():
+            try:
+                trn.check(trn.lib.trn_comm_create(rank, world, bytes(table[:, :64].tobytes()), C.byref(h)))
+            except trn.TruenoError as e:
+                err = e
+        elif err is None:
+            err = RuntimeError(f"rank {int(table[:, 64].argmax())} could not export its peer mailbox")
+        failed = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=mine.device)
+        dist.all_reduce(failed, op=dist.ReduceOp.MAX)   # also: every rank has mapped every mailbox before the first fused call
+        if int(failed.item()):
+            if h.value:
+                trn.lib.trn_comm_destroy(h)
+            raise err if err is not None else RuntimeError("a peer rank could not map the peer mailboxes")
         self._h, self.rank, self.world = h, rank, world
-        dist.barrier()   # every rank has mapped every mailbox before the first fused call
+
+    @classmethod
+    def try_create(cls) -> "PeerComm | None":
+        """A PeerComm, or None on EVERY rank when the fused path is not available (some rank has no P2P path to a peer):
+        callers then pass `comm=None` and the sharded reductions exchange through NCCL."""
+        try:
+            return cls()
+        except Exception:
+            return None
 
     @property
     def handle(self):
