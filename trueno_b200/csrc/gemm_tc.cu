@@ -84,6 +84,7 @@ struct Params {
     uint32_t num_kb;          // Kpad / BK
     uint32_t tiles_m, tiles_n, batch;
     uint32_t nseg;            // A-stationary kernel: n-segments per A panel (work unit = panel x segment)
+    uint32_t rot_mult;        // A-stationary kernel: pair p starts its units at n-tile (p * rot_mult) mod (tiles of the unit)
     uint32_t store_hint;      // fused kernels: 1 = C stores carry an L2 evict_first policy (C much larger than L2)
     uint32_t debug;           // fused kernels, experiments (TRN_GEMM_DEBUG): bit 0 skip the C stores, bit 1 aim every store at batch 0
     uint32_t terms_mask;      // fused kernel, debugging: bit 0 lo*hi, bit 1 hi*lo, bit 2 hi*hi (7 = the product)
@@ -863,6 +864,17 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
         n_lo = (uint32_t)(((uint64_t)seg * p.tiles_n) / p.nseg);
         n_hi = (uint32_t)(((uint64_t)(seg + 1) * p.tiles_n) / p.nseg);
     };
+    // The i-th tile of a unit: every pair starts its panels at a DIFFERENT n-tile (rotation by pair_id * p.rot_mult; the
+    // multiplier sends neighbouring pairs ~0.6 of the way round).  The pairs run at one pace, so without the rotation all of
+    // them store the same 1 KiB column range of their 8 KiB rows of C at the same moment and load the same B tile; rotated,
+    // the stores of any moment cover every column range.  Config 3, alternating processes on one box (scripts/exp/
+    // exp_cfg3_ab.py, median ms): no rotation 1.260, rotation by pair_id 1.241, by 7 pair_id 1.240, by 3 pair_id 1.215, by
+    // 5 pair_id 1.208-1.211 (-4 %); de-phasing the pairs in TIME on top (quarter-tile start delays) added 0.3 % and is not
+    // done.  Tiles are independent: the order changes no bit of C.  TRN_GEMM_DEBUG bit 3 turns the rotation off.
+    auto unit_tile = [&](uint32_t i, uint32_t n_lo, uint32_t n_hi) -> uint32_t {
+        const uint32_t cnt = n_hi - n_lo;
+        return n_lo + ((p.debug & 8u) ? i : (i + (pair_id * p.rot_mult) % cnt) % cnt);
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
@@ -903,8 +915,9 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
               uint32_t b, mt, n_lo, n_hi;
               unit_coords(u, b, mt, n_lo, n_hi);
               const uint32_t a_par = panel & 1u;
-              for (uint32_t nt = n_lo; nt < n_hi; ++nt) {
-                const bool new_panel = nt == n_lo;
+              for (uint32_t ti = 0; ti < n_hi - n_lo; ++ti) {
+                const uint32_t nt = unit_tile(ti, n_lo, n_hi);
+                const bool new_panel = ti == 0;
                 const int m0 = (int)(mt * 2 * BM + rank * BM), n0 = (int)(nt * BN + rank * (BN / 2));
                 for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
                     const int k0 = (int)(kb * SBK);
@@ -933,9 +946,9 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
               uint32_t b, mt, n_lo, n_hi;
               unit_coords(u, b, mt, n_lo, n_hi);
               const uint32_t a_par = panel & 1u;
-              for (uint32_t nt = n_lo; nt < n_hi; ++nt) {
-                const bool new_panel = nt == n_lo;
-                const bool last_in_panel = nt + 1 == n_hi;
+              for (uint32_t ti = 0; ti < n_hi - n_lo; ++ti) {
+                const bool new_panel = ti == 0;
+                const bool last_in_panel = ti + 1 == n_hi - n_lo;
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);   // K <= 128: one TMEM partial per tile
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BN;
@@ -975,8 +988,8 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
           uint32_t b, mt, n_lo, n_hi;
           unit_coords(u, b, mt, n_lo, n_hi);
           const uint32_t a_par = panel & 1u;
-          for (uint32_t nt = n_lo; nt < n_hi; ++nt) {
-            const bool new_panel = nt == n_lo;
+          for (uint32_t ti = 0; ti < n_hi - n_lo; ++ti) {
+            const bool new_panel = ti == 0;
             for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
                 if (new_panel) {
                     mbar_wait(a_full(kb), a_par);
@@ -1005,9 +1018,9 @@ gemm_tf32x3_fused_astat_pair_kernel(const __grid_constant__ CUtensorMap map_a, c
         for (uint32_t u = pair_id; u < units; u += num_pairs) {
             uint32_t b, mt, n_lo, n_hi;
             unit_coords(u, b, mt, n_lo, n_hi);
-            for (uint32_t nt = n_lo; nt < n_hi; ++nt)
+            for (uint32_t ti = 0; ti < n_hi - n_lo; ++ti)
                 pair_epilogue_tile(&map_c, p, tmem_base, store_base, tmem_full_bar(0), tmem_empty_bar(0), 1u, acc, acc_phase,
-                                   b, mt, nt, warp - 4, lane, rank);
+                                   b, mt, unit_tile(ti, n_lo, n_hi), warp - 4, lane, rank);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -1425,6 +1438,18 @@ int gemm_tc_fused_main(const float* a, const float* b, float* c, size_t batch, s
             if (cost < best - 1e-9) { best = cost; best_nseg = nseg; }
         }
         p.nseg = best_nseg;
+        // rotation multiplier: the integer nearest 0.618 x (tiles per unit) that is coprime with it (8 tiles -> 5)
+        const uint32_t tpu = (p.tiles_n + p.nseg - 1) / p.nseg;
+        auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+        uint32_t mult = 1;
+        if (tpu > 2) {
+            const uint32_t want = (uint32_t)(0.618 * tpu + 0.5);
+            for (uint32_t d = 0; d < tpu; ++d) {
+                if (want + d < tpu && gcd(want + d, tpu) == 1) { mult = want + d; break; }
+                if (want > d && gcd(want - d, tpu) == 1) { mult = want - d; break; }
+            }
+        }
+        p.rot_mult = mult;
     }
     const uint64_t total = use_astat ? (uint64_t)p.tiles_m * p.batch * p.nseg : (uint64_t)p.tiles_m * p.tiles_n * p.batch;
     const uint32_t max_pairs = (uint32_t)cx->sm_count / 2;
