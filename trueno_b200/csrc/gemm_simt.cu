@@ -9,6 +9,8 @@
 // `a_k == 0.0 -> skip` rule, so 0*NaN contributes nothing on that path exactly as in the reference.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace trn {
@@ -122,15 +124,24 @@ matvec_kernel(const float* __restrict__ a, const float* __restrict__ v, float* _
 // Long rows: one CTA per row (256 threads x 4 chains, fixed block tree) so a handful of very long rows still
 // fills the machine (256 x 1M: 0.66 -> TB/s-class).  128-bit loads; requires the VEC preconditions.
 __global__ void __launch_bounds__(256)
-matvec_row_cta_kernel(const float* __restrict__ a, const float* __restrict__ v, float* __restrict__ y, size_t rows, size_t cols) {
+matvec_row_cta_kernel(const float* __restrict__ a, const float* __restrict__ v, float* __restrict__ y, size_t rows, size_t cols, unsigned rot_mult) {
     __shared__ float s_w[8];
     const size_t r = blockIdx.x;
     const float4* row4 = reinterpret_cast<const float4*>(a + r * cols);
     const float4* v4 = reinterpret_cast<const float4*>(v);
     const size_t nvec = cols >> 2;
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    // whole 16 KiB blocks of the row, walked from a row-dependent block on (block (3 r) mod blocks first, wrapping round): with
+    // a row length that is a power of two every resident CTA otherwise sits on the same address bits at the same progress.
+    // 32768^2: 588.7 -> 582.3 us, a 4096-row share of it 79.3 -> 77.6 us (scripts/exp/exp_matvec_rot.py; TRN_MATVEC_ROT=0
+    // walks every row from its first block).  The order of a row's partial sums changes with it, not their fixed tree.
+    const size_t nblk = nvec / 1024;
+    const size_t rot = (rot_mult && nblk) ? (r * rot_mult) % nblk : 0;
     size_t i = threadIdx.x;
-    for (; i + 768 < nvec; i += 1024) {
+    for (size_t bi = 0; bi < nblk; ++bi) {
+        size_t bb = bi + rot;
+        if (bb >= nblk) bb -= nblk;
+        i = bb * 1024 + threadIdx.x;
         const float4 x0 = ld_stream(row4 + i), x1 = ld_stream(row4 + i + 256), x2 = ld_stream(row4 + i + 512), x3 = ld_stream(row4 + i + 768);
         const float4 w0 = __ldg(v4 + i), w1 = __ldg(v4 + i + 256), w2 = __ldg(v4 + i + 512), w3 = __ldg(v4 + i + 768);
         c0 = fmaf(x0.x, w0.x, c0); c0 = fmaf(x0.y, w0.y, c0); c0 = fmaf(x0.z, w0.z, c0); c0 = fmaf(x0.w, w0.w, c0);
@@ -138,7 +149,7 @@ matvec_row_cta_kernel(const float* __restrict__ a, const float* __restrict__ v, 
         c2 = fmaf(x2.x, w2.x, c2); c2 = fmaf(x2.y, w2.y, c2); c2 = fmaf(x2.z, w2.z, c2); c2 = fmaf(x2.w, w2.w, c2);
         c3 = fmaf(x3.x, w3.x, c3); c3 = fmaf(x3.y, w3.y, c3); c3 = fmaf(x3.z, w3.z, c3); c3 = fmaf(x3.w, w3.w, c3);
     }
-    for (; i < nvec; i += 256) {
+    for (i = nblk * 1024 + threadIdx.x; i < nvec; i += 256) {
         const float4 x0 = ld_stream(row4 + i);
         const float4 w0 = __ldg(v4 + i);
         c0 = fmaf(x0.x, w0.x, c0); c0 = fmaf(x0.y, w0.y, c0); c0 = fmaf(x0.z, w0.z, c0); c0 = fmaf(x0.w, w0.w, c0);
@@ -162,7 +173,8 @@ int launch_matvec(const float* a, size_t rows, size_t cols, const float* v, floa
     if (rows > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "%zu rows exceed the launch grid", rows);
     // rows long enough to keep a whole CTA busy, or too few rows for one warp each to fill the SMs
     if (vec && (cols >= 16384 || (cols >= 4096 && rows < (size_t)c->sm_count * 16))) {
-        matvec_row_cta_kernel<<<(unsigned)rows, 256, 0, s>>>(a, v, y, rows, cols);
+        const char* e = getenv("TRN_MATVEC_ROT");   // experiment knob, read per call
+        matvec_row_cta_kernel<<<(unsigned)rows, 256, 0, s>>>(a, v, y, rows, cols, e ? (unsigned)atoi(e) : 3u);
     } else {
         // one warp per row, 8 rows per CTA: flat for rows of >= 4 KiB, a resident grid-stride wave for shorter rows
         // (measured: 1M x 256 runs 5.3 TB/s resident vs 4.0 flat; 16384^2 6.6 flat vs 6.0 resident)
