@@ -674,9 +674,13 @@ int trn_log_softmax_rows_f32(const float* a, float* out, size_t rows, size_t col
 //   d2h stream  : D2H of each finished C block while the next block is uploaded and computed
 // H2D and D2H run on different copy engines in opposite directions of the link.  Every block runs the same
 // kernels with the same k-order as the unblocked call: results are bit-identical to trn_matmul_f32_dev.
+static bool pipe_trace() {   // TRN_PIPE_TRACE=1: timing events in the pipelined GEMM, phase times on stderr (experiments)
+    static const bool on = [] { const char* e = getenv("TRN_PIPE_TRACE"); return e && atoi(e) != 0; }();
+    return on;
+}
 struct Event {
     cudaEvent_t e = nullptr;
-    int create() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess ? TRN_OK : fail(TRN_GPU_ERROR, "cudaEventCreate failed"); }
+    int create() { return cudaEventCreateWithFlags(&e, pipe_trace() ? cudaEventDefault : cudaEventDisableTiming) == cudaSuccess ? TRN_OK : fail(TRN_GPU_ERROR, "cudaEventCreate failed"); }
     ~Event() { if (e) cudaEventDestroy(e); }
 };
 
@@ -686,6 +690,9 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
                                const trn_gemm_b* prepared) {
     Context* cx = ctx();
     cudaStream_t s_main = cx->stream, s_up = cx->copy_stream, s_down = cx->d2h_stream;
+    // (Alternating the row blocks over TWO compute streams, so that a block's 22-tile second wave does not leave 52 CTA pairs
+    // idle behind a kernel boundary, measured SLOWER: 11.72 vs 11.40 ms at 8192^3 — the concurrent split / GEMM kernels of
+    // neighbouring blocks slow each other and the uploads.  TRN_PIPE_TRACE=1 prints the phase times of a call.)
     const size_t kpad = gemm_tc_kpad(k);
     const bool single = batch == 1;
     // the same kernel choice as the resident call (gemm_tc.cu): results stay bit-identical to it.  Scratch sub-buffers
@@ -698,9 +705,13 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
         // Row blocks of whole 256-row pair tiles.  After B has arrived the three stages of a block — upload of its A
         // rows, split + GEMM, download of its C rows — run as a pipeline over three streams; the end-to-end time is
         // B upload + (blocks + 2) x the slowest stage, so blocks should be as small as the GEMM stays efficient.
-        // Measured on 8192^3 (TRN_PIPE_ROWS): 256-row blocks 13.0 ms, 512 11.4, 768 11.15, 1024 11.5, 2304 12.6 —
-        // about eleven blocks; the PCIe floor (512 MiB up + 256 MiB down concurrently) is 10.3 ms.
+        // Measured on 8192^3 (TRN_PIPE_ROWS), round 1: 256-row blocks 13.0 ms, 512 11.4, 768 11.15, 1024 11.5, 2304 12.6;
+        // round 2 (with the phase trace, same box): 512 11.09, 768 11.37, 1024 11.87.  The PCIe floor (512 MiB up + 256 MiB
+        // down concurrently) is 10.3 ms.
         static const size_t forced_rows = [] { const char* e = getenv("TRN_PIPE_ROWS"); return e ? (size_t)atol(e) : (size_t)0; }();
+        // (One-wave blocks — 512 rows at n = 8192 are 64 CTA-pair tiles where 768 rows are 96 = 1.3 waves that take two — look
+        // better in a single phase trace, 11.09 vs 11.37 ms, but are bimodal over repeated processes on one box: 11.2-12.3 ms
+        // against a steady 11.4-11.6 for 768-row blocks.  Eleven blocks stay.)
         size_t unit_rows = forced_rows ? (forced_rows + 255) / 256 * 256 : 256 * ((m / 11 + 255) / 256);
         if (unit_rows < 256) unit_rows = 256;
         size_t r = 0;
@@ -746,12 +757,13 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
 
     // Everything that can fail runs inside `enqueue`; whatever it returns, the three streams are drained before the
     // borrowed host slices go back to the caller and the scratch is released (no leak, no copy still in flight).
+    std::vector<Event> up(units + 1), done(units), down(pipe_trace() ? units : 0);
+    Event ready, drained;
     auto enqueue = [&]() -> int {
     if (prepared && prepared->flag) TRN_CUDA(cudaMemcpyAsync(flag, prepared->flag, sizeof(int), cudaMemcpyDeviceToDevice, s_main));
     else TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s_main));
+    for (auto& e : down) TRN_TRY(e.create());
 
-    std::vector<Event> up(units + 1), done(units);
-    Event ready, drained;
     TRN_TRY(ready.create());
     TRN_TRY(drained.create());
     for (auto& e : up) TRN_TRY(e.create());
@@ -771,19 +783,21 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     for (size_t u = 0; u < units && st == TRN_OK; ++u) {
         if (single) {
             const size_t r0 = row_start[u], rows = row_start[u + 1] - r0;
+            cudaStream_t s_c = s_main;
             TRN_CUDA(cudaMemcpyAsync(da + r0 * k, a + r0 * k, rows * k * sizeof(float), cudaMemcpyHostToDevice, s_up));
             TRN_CUDA(cudaEventRecord(up[u].e, s_up));
-            TRN_CUDA(cudaStreamWaitEvent(s_main, up[u].e, 0));
+            TRN_CUDA(cudaStreamWaitEvent(s_c, up[u].e, 0));
             if (fused) {
-                st = gemm_tc_fused_main(da + r0 * k, db, dc + r0 * n, 1, rows, k, n, flag, s_main);
+                st = gemm_tc_fused_main(da + r0 * k, db, dc + r0 * n, 1, rows, k, n, flag, s_c);
             } else {
-                st = gemm_tc_split_a(da + r0 * k, a_hi + r0 * kpad, a_lo + r0 * kpad, 1, rows, k, flag, s_main);
-                if (st == TRN_OK) st = gemm_tc_main(a_hi + r0 * kpad, a_lo + r0 * kpad, b_hi, b_lo, dc + r0 * n, 1, rows, k, n, 3, flag, s_main);
+                st = gemm_tc_split_a(da + r0 * k, a_hi + r0 * kpad, a_lo + r0 * kpad, 1, rows, k, flag, s_c);
+                if (st == TRN_OK) st = gemm_tc_main(a_hi + r0 * kpad, a_lo + r0 * kpad, b_hi, b_lo, dc + r0 * n, 1, rows, k, n, 3, flag, s_c);
             }
-            if (st == TRN_OK) st = launch_gemm_simt(da + r0 * k, db, dc + r0 * n, 1, rows, k, n, s_main, flag);
-            TRN_CUDA(cudaEventRecord(done[u].e, s_main));
+            if (st == TRN_OK) st = launch_gemm_simt(da + r0 * k, db, dc + r0 * n, 1, rows, k, n, s_c, flag);
+            TRN_CUDA(cudaEventRecord(done[u].e, s_c));
             TRN_CUDA(cudaStreamWaitEvent(s_down, done[u].e, 0));
             TRN_CUDA(cudaMemcpyAsync(c + r0 * n, dc + r0 * n, rows * n * sizeof(float), cudaMemcpyDeviceToHost, s_down));
+            if (pipe_trace()) TRN_CUDA(cudaEventRecord(down[u].e, s_down));
         } else {
             const size_t b0 = u * per_block, cnt = batch - b0 < per_block ? batch - b0 : per_block;
             TRN_CUDA(cudaMemcpyAsync(da + b0 * m * k, a + b0 * m * k, cnt * m * k * sizeof(float), cudaMemcpyHostToDevice, s_up));
@@ -809,6 +823,13 @@ static int host_gemm_pipelined(const float* a, const float* b, float* c, size_t 
     const int st = enqueue();
     // the host slices are borrowed: everything must have landed before the call returns
     cudaError_t e1 = cudaStreamSynchronize(s_up), e2 = cudaStreamSynchronize(s_main), e3 = cudaStreamSynchronize(s_down);
+    if (pipe_trace() && single && st == TRN_OK && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
+        auto ms = [&](const Event& x) { float t = 0.f; cudaEventElapsedTime(&t, ready.e, x.e); return t; };
+        fprintf(stderr, "[pipe trace] %zu blocks:", units);
+        if (!prepared) fprintf(stderr, " B up %.2f |", ms(up[units]));
+        for (size_t u = 0; u < units; ++u) fprintf(stderr, " [%zu rows] up %.2f gemm %.2f down %.2f |", row_start[u + 1] - row_start[u], ms(up[u]), ms(done[u]), ms(down[u]));
+        fprintf(stderr, "\n");
+    }
     scratch_free(dev, s_main);
     if (st != TRN_OK) return st;
     TRN_CUDA(e1);
