@@ -601,7 +601,8 @@ int launch_reduce(Reduce op, const float* a, const float* b, size_t n, float* ou
 #define LAUNCH(OP, SQRT)                                                                                   \
     do {                                                                                                   \
         static const int per_sm = blocks_per_sm(reduce_sum_kernel<OP, true, SQRT>);   /* thread-safe, once */ \
-        const int grid = reduce_grid(n, c->sm_count, per_sm);                                              \
+        /* dot keeps two 16 KiB tiles in flight per CTA: three CTAs per SM stream best (2^30: 1205 -> 1191 us) */ \
+        const int grid = reduce_grid(n, c->sm_count, (OP == 1 && per_sm > 3 && !getenv("TRN_REDUCE_PER_SM")) ? 3 : per_sm); \
         if (vec) reduce_sum_kernel<OP, true, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx), pcv); \
         else     reduce_sum_kernel<OP, false, SQRT><<<grid, kThreads, 0, s>>>(a, b, n, w->partial_val, w->ticket, out, reinterpret_cast<float*>(w->partial_idx), pcv); \
     } while (0)
