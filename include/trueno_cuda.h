@@ -24,7 +24,12 @@
  *     CUDA allocation of the current device), are stream-ordered and return without
  *     synchronising, so chains of ops stay in HBM (the reference's precedent for this is
  *     `GpuCommandBatch`, src/backends/gpu/batch.rs:54-135).  Scalar results are written to
- *     device memory (`*_out` device pointers).
+ *     device memory (`*_out` device pointers).  Reductions and the persistent row kernels keep
+ *     small per-STREAM state in HBM (block partials, tickets, row-claim counters) that is valid
+ *     across launches because launches on one stream are ordered: `_dev` calls captured into a
+ *     CUDA graph on stream S must be replayed on S (or at least never concurrently with other
+ *     trueno work on S); the first call on a stream allocates that state and therefore must not
+ *     happen inside a capture (warm the stream up with one call before capturing).
  *   - All functions are thread-safe.  One process drives one GPU (trn_cuda_init(device)); the
  *     multi-GPU layer is one process per GPU (trueno_b200/parallel.py, torch.distributed/NCCL).
  *   - Matrices are dense row-major f32, exactly like `Matrix<f32>` (src/matrix.rs:49-54).
