@@ -24,4 +24,4 @@ h = 5
 qq, kk, vv = (t.view(H, S, D)[h].double() for t in (q, k, v))
 ref = torch.softmax(qq @ kk.T / D ** 0.5, dim=1) @ vv
 err = (o.view(H, S, D)[h].double() - ref).abs().max().item()
-print(f"TRN_ATT_ROT={os.environ.get('TRN_ATT_ROT', '0')}: min {min(ts):.4f} median {statistics.median(ts):.4f} ms  max abs err head 5 {err:.2e}")
+print(f"TRN_ATT_RAW_HI={os.environ.get('TRN_ATT_RAW_HI', '1')}: min {min(ts):.4f} median {statistics.median(ts):.4f} ms  max abs err head 5 {err:.2e}")

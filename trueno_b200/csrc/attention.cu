@@ -806,8 +806,15 @@ int launch_attention(const float* q, const float* k, const float* v, float* out,
     int st = TRN_OK;
     auto run = [&]() -> int {
         TRN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
-        TRN_TRY(gemm_tc_split_a(q, q_hi, q_lo, heads, seq, d, flag, s));
-        TRN_TRY(gemm_tc_split_a(k, k_hi, k_lo, heads, seq, d, flag, s));
+        // Q and K are K-major as they lie ([seq][d]): when head_dim needs no padding their RAW words are the hi operands
+        // (the tensor core reads the top 19 bits) and the pre-pass writes the lo halves only — 7 instead of 9 array passes
+        // over q / k / v (TRN_ATT_RAW_HI=0 writes rounded hi halves as before).  V is transposed on the way, so both halves go out.
+        static const bool raw_env = [] { const char* e = getenv("TRN_ATT_RAW_HI"); return !(e && atoi(e) == 0); }();
+        const bool raw_q = raw_env && gemm_tc_raw_hi_ok(q, d), raw_k = raw_env && gemm_tc_raw_hi_ok(k, d);
+        if (raw_q) { TRN_TRY(gemm_tc_split_a_lo(q, q_lo, heads, seq, d, flag, s)); q_hi = const_cast<float*>(q); }
+        else TRN_TRY(gemm_tc_split_a(q, q_hi, q_lo, heads, seq, d, flag, s));
+        if (raw_k) { TRN_TRY(gemm_tc_split_a_lo(k, k_lo, heads, seq, d, flag, s)); k_hi = const_cast<float*>(k); }
+        else TRN_TRY(gemm_tc_split_a(k, k_hi, k_lo, heads, seq, d, flag, s));
         TRN_TRY(gemm_tc_split_b(v, v_hi, v_lo, heads, seq, d, flag, s));
         Params p;
         p.out = out;

@@ -151,6 +151,9 @@ bool gemm_tc_supported(size_t m, size_t k, size_t n);
 size_t gemm_tc_kpad(size_t k);
 int gemm_tc_split_a(const float* a, float* a_hi, float* a_lo, size_t batch, size_t m, size_t k, int* flag, cudaStream_t s);
 int gemm_tc_split_b(const float* b, float* b_hi, float* b_lo, size_t batch, size_t k, size_t n, int* flag, cudaStream_t s);
+// lo half only, for an operand whose raw words can serve as the hi half (the tensor core reads their top 19 bits)
+bool gemm_tc_raw_hi_ok(const float* a, size_t k);
+int gemm_tc_split_a_lo(const float* a, float* a_lo, size_t batch, size_t m, size_t k, int* flag, cudaStream_t s);
 int gemm_tc_main(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* c, size_t batch,
                  size_t m, size_t k, size_t n, int terms, const int* flag, cudaStream_t s, size_t route_m = 0);
 // fused-split variant (no pre-pass, raw operands; gemm_tc.cu): preconditions + default rule, and the kernel itself

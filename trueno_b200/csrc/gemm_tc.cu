@@ -1160,6 +1160,32 @@ split_transpose_kernel(const float* __restrict__ in, float* __restrict__ hi, flo
     if (bad) *flag = 1;
 }
 
+// lo half only, for an operand whose RAW words serve as the hi half: kind::tf32 reads the top 19 bits of a word, i.e. the
+// tensor core itself uses hi = x & 0xFFFFE000 (as in the fused-split kernels), and lo = tf32_rna(x - hi) is all a pre-pass has
+// to write — one read and ONE write per element instead of two.  Needs k % 32 == 0 (no K padding) and 16-byte aligned data.
+__global__ void __launch_bounds__(256)
+split_rows_lo_kernel(const float* __restrict__ in, float* __restrict__ lo, size_t nvec, int* __restrict__ flag) {
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    float4* lo4 = reinterpret_cast<float4*>(lo);
+    bool bad = false;
+    auto one = [&](float x) -> float {
+        if (!isfinite(x)) { bad = true; return 0.f; }
+        const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);   // exact
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+        return __uint_as_float(l);
+    };
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const size_t i = (size_t)blockIdx.x * 512 + u * 256 + threadIdx.x;
+        if (i < nvec) {
+            const float4 x = ld_stream(in4 + i);
+            lo4[i] = make_float4(one(x.x), one(x.y), one(x.z), one(x.w));
+        }
+    }
+    if (bad) *flag = 1;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1260,6 +1286,19 @@ int gemm_tc_split_a(const float* a, float* a_hi, float* a_lo, size_t batch, size
     if (blocks > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "operand of %zu elements exceeds the launch grid", a_elems);
     if (vec) split_rows_vec_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
     else     split_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, a_hi, a_lo, batch * m, k, kpad, flag);
+    count_launch();
+    TRN_CUDA(cudaGetLastError());
+    return TRN_OK;
+}
+
+bool gemm_tc_raw_hi_ok(const float* a, size_t k) { return k % tc::BK == 0 && (reinterpret_cast<uintptr_t>(a) & 15u) == 0; }
+int gemm_tc_split_a_lo(const float* a, float* a_lo, size_t batch, size_t m, size_t k, int* flag, cudaStream_t s) {
+    if (!ctx()) return TRN_GPU_ERROR;
+    const size_t nvec = batch * m * k / 4;
+    if (nvec == 0) return TRN_OK;
+    const size_t blocks = (nvec + 511) / 512;
+    if (blocks > 0x7FFFFFFFull) return fail(TRN_INVALID_INPUT, "operand of %zu elements exceeds the launch grid", nvec * 4);
+    tc::split_rows_lo_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, a_lo, nvec, flag);
     count_launch();
     TRN_CUDA(cudaGetLastError());
     return TRN_OK;
